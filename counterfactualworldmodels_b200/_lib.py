@@ -1,0 +1,116 @@
+"""ctypes binding of ``libcwm_b200.so`` (the C ABI declared in ``include/cwm_b200.h``).
+
+The product path has no CPU fallback: if the shared library is missing, or the device is not sm_100, every op
+raises.  The library is built in-tree by ``__graft_entry__.build()`` / ``make -C csrc``.
+"""
+import ctypes
+import os
+from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcwm_b200.so")
+
+CWM_OK = 0
+EPI_F16, EPI_GELU_F16, EPI_RES_F32, EPI_F32 = 0, 1, 2, 3
+
+# every symbol include/cwm_b200.h declares (checked by tests/test_abi.py)
+EXPORTED_SYMBOLS = (
+    "cwm_abi_version", "cwm_last_error", "cwm_device_check", "cwm_compact_mask", "cwm_patch_gather",
+    "cwm_layernorm_f16", "cwm_gemm_f16", "cwm_attention_f16", "cwm_fill_mask_tokens",
+    "cwm_unpatchify_scatter", "cwm_vmae_workspace_bytes", "cwm_vmae_forward", "cwm_last_forward_launches",
+)
+
+
+class CwmError(RuntimeError):
+    """A libcwm_b200 entry point returned a negative status."""
+
+
+class GemmEpilogue(Structure):
+    _fields_ = [
+        ("mode", c_int32), ("bias", c_void_p), ("scale", c_float), ("scale_cols", c_int32),
+        ("res", c_void_p), ("ldr", c_int32), ("res_gather", c_void_p), ("gather_stride", c_int32),
+        ("grp_rows", c_int32), ("grp_out_stride", c_int32), ("out", c_void_p), ("ldo", c_int32),
+    ]
+
+
+class BlockWeights(Structure):
+    _fields_ = [(n, c_void_p) for n in (
+        "ln1_g", "ln1_b", "w_qkv", "b_qkv", "w_proj", "b_proj", "ln2_g", "ln2_b", "w_fc1", "b_fc1", "w_fc2",
+        "b_fc2")]
+
+
+class VmaeModel(Structure):
+    _fields_ = (
+        [(n, c_int32) for n in ("in_chans", "num_frames", "img_h", "img_w", "pt", "ph", "pw", "enc_dim",
+                                "enc_depth", "enc_heads", "enc_hidden", "dec_dim", "dec_depth", "dec_heads",
+                                "dec_hidden", "out_dim")]
+        + [("ln_eps", c_float), ("enc_qk_scale", c_float), ("dec_qk_scale", c_float)]
+        + [("w_patch", c_void_p), ("b_patch", c_void_p), ("pos_enc", c_void_p),
+           ("enc_blocks", POINTER(BlockWeights)), ("enc_norm_g", c_void_p), ("enc_norm_b", c_void_p),
+           ("w_e2d", c_void_p), ("mask_token", c_void_p), ("pos_dec", c_void_p),
+           ("dec_blocks", POINTER(BlockWeights)), ("dec_norm_g", c_void_p), ("dec_norm_b", c_void_p),
+           ("w_head", c_void_p), ("b_head", c_void_p)]
+    )
+
+
+_lib = None
+
+
+def _declare(lib):
+    i64x5 = POINTER(c_int64)
+    lib.cwm_abi_version.restype = c_int
+    lib.cwm_last_error.restype = c_char_p
+    lib.cwm_device_check.restype = c_int
+    lib.cwm_compact_mask.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.cwm_patch_gather.argtypes = [c_void_p, i64x5, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                     c_void_p, c_int, c_int, POINTER(c_float), POINTER(c_float), c_void_p,
+                                     c_void_p]
+    lib.cwm_layernorm_f16.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_int,
+                                      c_void_p, c_void_p]
+    lib.cwm_gemm_f16.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, POINTER(GemmEpilogue), c_void_p]
+    lib.cwm_attention_f16.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]
+    lib.cwm_fill_mask_tokens.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                         c_void_p]
+    lib.cwm_unpatchify_scatter.argtypes = [c_void_p, c_void_p, i64x5, c_void_p, c_int, c_int, c_int, c_int,
+                                           c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]
+    lib.cwm_vmae_workspace_bytes.argtypes = [POINTER(VmaeModel), c_int, c_int]
+    lib.cwm_vmae_workspace_bytes.restype = c_size_t
+    lib.cwm_vmae_forward.argtypes = [POINTER(VmaeModel), c_void_p, i64x5, c_int, POINTER(c_float),
+                                     POINTER(c_float), c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.cwm_last_forward_launches.restype = c_int
+    for name in EXPORTED_SYMBOLS:
+        fn = getattr(lib, name)
+        if fn.restype is c_int and name not in ("cwm_abi_version", "cwm_last_forward_launches"):
+            pass
+    return lib
+
+
+def load():
+    """Loads (once) and returns the ctypes handle.  Raises if the library has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CwmError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU or PyTorch fallback for the CWM VMAE path)")
+        import torch  # noqa: F401  -- makes sure libcudart.so.12 is already mapped (same SONAME is reused)
+        _lib = _declare(ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL))
+    return _lib
+
+
+def check(rc):
+    if rc != CWM_OK:
+        msg = load().cwm_last_error()
+        raise CwmError(f"libcwm_b200 error {rc}: {msg.decode() if msg else '?'}")
+
+
+def strides5(t):
+    """Element strides of a 5-D tensor as the ``int64_t[5]`` the C ABI wants."""
+    assert t.dim() == 5, t.shape
+    return (c_int64 * 5)(*t.stride())
+
+
+def float_array(vals):
+    if vals is None:
+        return None
+    return (c_float * len(vals))(*[float(v) for v in vals])

@@ -1,0 +1,154 @@
+// forward.cu -- cwm_vmae_forward: the whole `PretrainVisionTransformer.forward(x, mask)` chain
+// (cwm/models/VideoMAE/vmae.py:539-560) as a fixed sequence of launches on one stream.  No host
+// synchronisation, no allocation: the caller provides the workspace.
+#include "common.cuh"
+
+namespace cwm {
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Plan {
+  int Ntot, Nvis, Nmask, out_rows, Kp;
+  long long Me, Md, Mo;
+  size_t off_xe, off_xd, off_a16, off_qkv, off_attn, off_h16, total;
+};
+
+static int make_plan(const cwm_vmae_model* m, int B, int Nvis, Plan* p) {
+  if (!m) return fail(CWM_ERR_INVALID, "cwm_vmae: null model");
+  if (m->pt <= 0 || m->ph <= 0 || m->pw <= 0 || m->num_frames % m->pt || m->img_h % m->ph || m->img_w % m->pw)
+    return fail(CWM_ERR_INVALID, "Input image size(%d,%d) must be divisible by patch size (%d,%d)", m->img_h,
+                m->img_w, m->ph, m->pw);
+  p->Ntot = (m->num_frames / m->pt) * (m->img_h / m->ph) * (m->img_w / m->pw);
+  if (B < 0 || Nvis < 0 || Nvis > p->Ntot) return fail(CWM_ERR_INVALID, "cwm_vmae: bad B=%d / Nvis=%d (Ntot=%d)", B, Nvis, p->Ntot);
+  if (m->enc_dim % 128 || m->dec_dim % 128 || m->enc_dim > 1024 || m->dec_dim > 1024)
+    return fail(CWM_ERR_UNSUPPORTED, "cwm_vmae: embed dims (%d, %d) must be multiples of 128 and <= 1024", m->enc_dim, m->dec_dim);
+  if (m->enc_dim != m->enc_heads * 64 || m->dec_dim != m->dec_heads * 64)
+    return fail(CWM_ERR_UNSUPPORTED, "cwm_vmae: only head_dim 64 is implemented (enc %d/%d, dec %d/%d)", m->enc_dim,
+                m->enc_heads, m->dec_dim, m->dec_heads);
+  p->Nvis = Nvis;
+  p->Nmask = p->Ntot - Nvis;
+  p->out_rows = p->Nmask > 0 ? p->Nmask : p->Ntot;  // return_token_num == 0 -> all tokens (vmae.py:250-253)
+  p->Kp = m->in_chans * m->pt * m->ph * m->pw;
+  if (p->Kp % 16) return fail(CWM_ERR_UNSUPPORTED, "cwm_vmae: patch volume %d must be a multiple of 16", p->Kp);
+  p->Me = static_cast<long long>(B) * Nvis;
+  p->Md = static_cast<long long>(B) * p->Ntot;
+  p->Mo = static_cast<long long>(B) * p->out_rows;
+  auto mx = [](size_t a, size_t b) { return a > b ? a : b; };
+  size_t off = 0;
+  p->off_xe = off;  off = align_up(off + p->Me * m->enc_dim * 4, 1024);
+  p->off_xd = off;  off = align_up(off + p->Md * m->dec_dim * 4, 1024);
+  size_t a16 = mx(mx(p->Me * m->enc_dim, p->Md * m->dec_dim), mx(p->Me * p->Kp, p->Mo * m->dec_dim));
+  p->off_a16 = off; off = align_up(off + a16 * 2, 1024);
+  p->off_qkv = off; off = align_up(off + mx(p->Me * 3 * m->enc_dim, p->Md * 3 * m->dec_dim) * 2, 1024);
+  p->off_attn = off; off = align_up(off + mx(p->Me * m->enc_dim, p->Md * m->dec_dim) * 2, 1024);
+  p->off_h16 = off; off = align_up(off + mx(p->Me * m->enc_hidden, p->Md * m->dec_hidden) * 2, 1024);
+  p->total = off + 1024;
+  return CWM_OK;
+}
+
+static cwm_gemm_epilogue epi_f16(const float* bias, float scale, int scale_cols, void* out, int ldo) {
+  cwm_gemm_epilogue e = {};
+  e.mode = CWM_EPI_F16; e.bias = bias; e.scale = scale; e.scale_cols = scale_cols; e.out = out; e.ldo = ldo;
+  return e;
+}
+static cwm_gemm_epilogue epi_gelu(const float* bias, void* out, int ldo) {
+  cwm_gemm_epilogue e = {};
+  e.mode = CWM_EPI_GELU_F16; e.bias = bias; e.out = out; e.ldo = ldo;
+  return e;
+}
+static cwm_gemm_epilogue epi_res(const float* bias, float* x, int ld) {
+  cwm_gemm_epilogue e = {};
+  e.mode = CWM_EPI_RES_F32; e.bias = bias; e.res = x; e.ldr = ld; e.out = x; e.ldo = ld;
+  return e;
+}
+
+#define CWM_TRY(call)        \
+  do {                       \
+    int _rc = (call);        \
+    if (_rc != CWM_OK) return _rc; \
+  } while (0)
+
+// x += Attn(LN1(x)); x += Mlp(LN2(x))   (cwm/models/VideoMAE/utils.py:146-153, gamma_* = None)
+static int run_block(const cwm_block_weights& w, float* x, int Bn, int N, int C, int heads, int hidden, float eps,
+                     float qk_scale, uint16_t* a16, uint16_t* qkv, uint16_t* attn, uint16_t* h16,
+                     cwm_stream_t st) {
+  const int M = Bn * N;
+  CWM_TRY(cwm_layernorm_f16(x, M, C, w.ln1_g, w.ln1_b, eps, 0, 0, 0, a16, st));
+  cwm_gemm_epilogue e = epi_f16(w.b_qkv, qk_scale, C, qkv, 3 * C);  // (xW + [q_bias,0,v_bias]); q *= scale
+  CWM_TRY(cwm_gemm_f16(a16, w.w_qkv, M, 3 * C, C, &e, st));
+  CWM_TRY(cwm_attention_f16(qkv, Bn, N, heads, 64, attn, st));
+  e = epi_res(w.b_proj, x, C);
+  CWM_TRY(cwm_gemm_f16(attn, w.w_proj, M, C, C, &e, st));
+  CWM_TRY(cwm_layernorm_f16(x, M, C, w.ln2_g, w.ln2_b, eps, 0, 0, 0, a16, st));
+  e = epi_gelu(w.b_fc1, h16, hidden);
+  CWM_TRY(cwm_gemm_f16(a16, w.w_fc1, M, hidden, C, &e, st));
+  e = epi_res(w.b_fc2, x, C);
+  CWM_TRY(cwm_gemm_f16(h16, w.w_fc2, M, C, hidden, &e, st));
+  return CWM_OK;
+}
+
+}  // namespace cwm
+
+using namespace cwm;
+
+extern "C" size_t cwm_vmae_workspace_bytes(const cwm_vmae_model* model, int B, int Nvis) {
+  Plan p;
+  if (make_plan(model, B, Nvis, &p) != CWM_OK) return 0;
+  return p.total;
+}
+
+extern "C" int cwm_vmae_forward(const cwm_vmae_model* m, const float* x, const int64_t xs[5], int B,
+                                const float* norm_mean, const float* norm_std, const int32_t* perm, int Nvis,
+                                float* y, void* workspace, size_t workspace_bytes, cwm_stream_t st) {
+  reset_launches();
+  Plan p;
+  CWM_TRY(make_plan(m, B, Nvis, &p));
+  CWM_REQUIRE(x && xs && perm && y && workspace, "cwm_vmae_forward: null pointer");
+  if (workspace_bytes < p.total)
+    return fail(CWM_ERR_WORKSPACE, "cwm_vmae_forward: workspace %zu bytes < required %zu", workspace_bytes, p.total);
+  if (B == 0) return CWM_OK;
+  uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
+  float* xe = reinterpret_cast<float*>(ws + p.off_xe);
+  float* xd = reinterpret_cast<float*>(ws + p.off_xd);
+  uint16_t* a16 = reinterpret_cast<uint16_t*>(ws + p.off_a16);
+  uint16_t* qkv = reinterpret_cast<uint16_t*>(ws + p.off_qkv);
+  uint16_t* attn = reinterpret_cast<uint16_t*>(ws + p.off_attn);
+  uint16_t* h16 = reinterpret_cast<uint16_t*>(ws + p.off_h16);
+  const int Ce = m->enc_dim, Cd = m->dec_dim;
+
+  if (Nvis > 0) {
+    // a1-a4: normalise + gather visible patches, embed, add positional embedding of the gathered tokens
+    CWM_TRY(cwm_patch_gather(x, xs, B, m->in_chans, m->num_frames, m->img_h, m->img_w, m->pt, m->ph, m->pw, perm,
+                             p.Ntot, Nvis, norm_mean, norm_std, a16, st));
+    cwm_gemm_epilogue e = {};
+    e.mode = CWM_EPI_RES_F32; e.bias = m->b_patch; e.res = m->pos_enc; e.ldr = Ce; e.res_gather = perm;
+    e.gather_stride = p.Ntot; e.grp_rows = Nvis; e.grp_out_stride = Nvis; e.out = xe; e.ldo = Ce;
+    CWM_TRY(cwm_gemm_f16(a16, m->w_patch, static_cast<int>(p.Me), Ce, p.Kp, &e, st));
+    // a5-a7: encoder blocks
+    for (int l = 0; l < m->enc_depth; ++l)
+      CWM_TRY(run_block(m->enc_blocks[l], xe, B, Nvis, Ce, m->enc_heads, m->enc_hidden, m->ln_eps, m->enc_qk_scale,
+                        a16, qkv, attn, h16, st));
+    // a8-a10: final norm, encoder_to_decoder (no bias) written at the visible rows of the decoder sequence with
+    // the positional embedding of each visible token added
+    CWM_TRY(cwm_layernorm_f16(xe, static_cast<int>(p.Me), Ce, m->enc_norm_g, m->enc_norm_b, m->ln_eps, 0, 0, 0, a16, st));
+    e = {};
+    e.mode = CWM_EPI_RES_F32; e.bias = nullptr; e.res = m->pos_dec; e.ldr = Cd; e.res_gather = perm;
+    e.gather_stride = p.Ntot; e.grp_rows = Nvis; e.grp_out_stride = p.Ntot; e.out = xd; e.ldo = Cd;
+    CWM_TRY(cwm_gemm_f16(a16, m->w_e2d, static_cast<int>(p.Me), Cd, Ce, &e, st));
+  }
+  CWM_TRY(cwm_fill_mask_tokens(m->mask_token, m->pos_dec, perm, B, p.Ntot, Nvis, Cd, xd, st));
+  // a11: decoder blocks over all Ntot tokens, then head(norm(last Nmask tokens))
+  for (int l = 0; l < m->dec_depth; ++l)
+    CWM_TRY(run_block(m->dec_blocks[l], xd, B, p.Ntot, Cd, m->dec_heads, m->dec_hidden, m->ln_eps, m->dec_qk_scale, a16,
+                      qkv, attn, h16, st));
+  if (p.Nmask > 0) {
+    CWM_TRY(cwm_layernorm_f16(xd, static_cast<int>(p.Mo), Cd, m->dec_norm_g, m->dec_norm_b, m->ln_eps, p.Nmask, p.Ntot,
+                              Nvis, a16, st));
+  } else {
+    CWM_TRY(cwm_layernorm_f16(xd, static_cast<int>(p.Mo), Cd, m->dec_norm_g, m->dec_norm_b, m->ln_eps, 0, 0, 0, a16, st));
+  }
+  cwm_gemm_epilogue e = {};
+  e.mode = CWM_EPI_F32; e.bias = m->b_head; e.out = y; e.ldo = m->out_dim;
+  CWM_TRY(cwm_gemm_f16(a16, m->w_head, static_cast<int>(p.Mo), m->out_dim, Cd, &e, st));
+  return CWM_OK;
+}

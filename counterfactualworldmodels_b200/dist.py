@@ -1,0 +1,65 @@
+"""Sharding of a batch of counterfactual prompts over the GPUs of one box.
+
+The path is embarrassingly parallel over the sample axis: every rank holds a full replica of the predictor, takes a
+contiguous slice of the (already rectangularised) ``(x, mask)`` batch, runs the forward with no data-path
+collective, and one final gather brings the predicted frames (or any per-sample statistic) together.  NCCL over
+NVLink on the GPU box; the same code runs on ``gloo`` for the CPU tests of the host logic.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(num_samples, rank, world_size):
+    """Contiguous, balanced slice [lo, hi) of ``num_samples`` for ``rank`` (sizes differ by at most one)."""
+    base, rem = divmod(num_samples, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_samples(x, mask, rank=None, world_size=None):
+    """Slice of the sample axis owned by this rank.  Rectangularise the masks BEFORE sharding (the reference's
+    ``RectangularizeMasks`` draws from a global RNG, masking.py:119-128, so it must see the whole batch)."""
+    if world_size is None:
+        world_size = dist.get_world_size() if dist.is_initialized() else 1
+    if rank is None:
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    lo, hi = shard_bounds(x.shape[0], rank, world_size)
+    return x[lo:hi], mask[lo:hi], (lo, hi)
+
+
+def gather_samples(y_local, num_samples, dst=None):
+    """Inverse of ``shard_samples`` along dim 0.  ``dst=None`` -> all ranks get the full tensor (all_gather),
+    otherwise only rank ``dst`` does (others get None).  Shards may differ in size by one sample, so every rank
+    pads to the largest shard before the collective."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return y_local
+    world = dist.get_world_size()
+    rank = dist.get_rank()
+    sizes = [shard_bounds(num_samples, r, world)[1] - shard_bounds(num_samples, r, world)[0] for r in range(world)]
+    max_n = max(sizes)
+    pad = y_local
+    if y_local.shape[0] < max_n:
+        pad = torch.cat([y_local, y_local.new_zeros((max_n - y_local.shape[0],) + tuple(y_local.shape[1:]))], 0)
+    pad = pad.contiguous()
+    if dst is None:
+        out = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(out, pad)
+    else:
+        out = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+        dist.gather(pad, out, dst=dst)
+        if rank != dst:
+            return None
+    return torch.cat([o[:n] for o, n in zip(out, sizes)], 0)
+
+
+def sharded_predict(generator, x, mask, frame=-1, batch_size=None, gather=True, **kwargs):
+    """``PredictorBasedGenerator.batch_predict_per_sample(sample_dim=0)`` with the sample axis sharded over the
+    ranks of the default process group; returns the full [S, ...] prediction on every rank when ``gather``."""
+    S = x.shape[0]
+    xs, ms, _ = shard_samples(x, mask)
+    y = generator.batch_predict_per_sample(xs, ms, frame=frame, batch_size=batch_size, sample_dim=0, **kwargs) \
+        if xs.shape[0] > 0 else None
+    if y is None:  # a rank with no samples still has to join the collective with the right trailing shape
+        T = 1 if frame is not None else x.shape[1]
+        y = x.new_zeros((0, T) + tuple(x.shape[2:]), dtype=torch.float32)
+    return gather_samples(y, S) if gather else y

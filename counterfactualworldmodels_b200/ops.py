@@ -1,0 +1,90 @@
+"""Thin Python wrappers over the individual C-ABI entry points (one call = one kernel launch on the current
+stream).  The model forward does not use these -- it goes through ``cwm_vmae_forward`` in one call -- they exist
+for the stage-wise parity tests and for users who want a single fused op."""
+import ctypes
+
+import torch
+
+from . import _lib
+from .vmae import compact_mask  # noqa: F401  (re-export)
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _req_cuda(*ts):
+    for t in ts:
+        if t is not None and t.device.type != "cuda":
+            raise RuntimeError("libcwm_b200 ops need CUDA (B200) tensors; there is no CPU fallback")
+
+
+def patch_gather(x, perm, rows_per_sample, patch_size, input_norm=None):
+    """x [B,C,T,H,W] fp32 (any strides), perm int32 [B,Ntot] -> f16 [B*rows_per_sample, C*pt*ph*pw]."""
+    _req_cuda(x, perm)
+    lib = _lib.load()
+    B, C, T, H, W = x.shape
+    pt, ph, pw = patch_size
+    out = torch.empty(B * rows_per_sample, C * pt * ph * pw, dtype=torch.float16, device=x.device)
+    mean = std = None
+    if input_norm is not None:
+        mean, std = _lib.float_array(input_norm[0]), _lib.float_array(input_norm[1])
+    _lib.check(lib.cwm_patch_gather(x.data_ptr(), _lib.strides5(x), B, C, T, H, W, pt, ph, pw, perm.data_ptr(),
+                                    perm.shape[1], rows_per_sample, mean, std, out.data_ptr(), _stream(x)))
+    return out
+
+
+def layernorm_f16(x, gamma, beta, eps, M=None, grp_rows=0, grp_stride=0, grp_offset=0):
+    """x fp32 [rows, C] -> f16 [M, C] (M defaults to rows; optional row gather, see cwm_b200.h)."""
+    _req_cuda(x, gamma, beta)
+    lib = _lib.load()
+    C = x.shape[-1]
+    M = x.shape[0] if M is None else M
+    out = torch.empty(M, C, dtype=torch.float16, device=x.device)
+    _lib.check(lib.cwm_layernorm_f16(x.data_ptr(), M, C, gamma.data_ptr(), beta.data_ptr(), float(eps), grp_rows,
+                                     grp_stride, grp_offset, out.data_ptr(), _stream(x)))
+    return out
+
+
+def gemm_f16(a, w, mode, bias=None, scale=1.0, scale_cols=0, res=None, res_gather=None, gather_stride=0,
+             grp_rows=0, grp_out_stride=0, out=None, out_rows=None):
+    """epilogue(a[M,K] @ w[N,K]^T); a, w f16 contiguous.  Returns the output tensor (f16 or fp32 by mode)."""
+    _req_cuda(a, w, bias, res, res_gather, out)
+    lib = _lib.load()
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and a.is_contiguous() and w.is_contiguous()
+    f16_out = mode in (_lib.EPI_F16, _lib.EPI_GELU_F16)
+    if out is None:
+        rows = M if out_rows is None else out_rows
+        out = torch.zeros(rows, N, dtype=torch.float16 if f16_out else torch.float32, device=a.device)
+    e = _lib.GemmEpilogue()
+    e.mode = mode
+    e.bias = bias.data_ptr() if bias is not None else None
+    e.scale, e.scale_cols = float(scale), int(scale_cols)
+    e.res = res.data_ptr() if res is not None else None
+    e.ldr = res.shape[-1] if res is not None else 0
+    e.res_gather = res_gather.data_ptr() if res_gather is not None else None
+    e.gather_stride, e.grp_rows, e.grp_out_stride = int(gather_stride), int(grp_rows), int(grp_out_stride)
+    e.out, e.ldo = out.data_ptr(), out.shape[-1]
+    _lib.check(lib.cwm_gemm_f16(a.data_ptr(), w.data_ptr(), M, N, K, ctypes.byref(e), _stream(a)))
+    return out
+
+
+def attention_f16(qkv, B, N, H):
+    """qkv f16 [B*N, 3*H*64] (q pre-scaled) -> f16 [B*N, H*64]."""
+    _req_cuda(qkv)
+    lib = _lib.load()
+    out = torch.empty(B * N, H * 64, dtype=torch.float16, device=qkv.device)
+    _lib.check(lib.cwm_attention_f16(qkv.data_ptr(), B, N, H, 64, out.data_ptr(), _stream(qkv)))
+    return out
+
+
+def fill_mask_tokens(mask_token, pos, perm, n_vis, x_full):
+    """x_full [B, Ntot, C] fp32: rows n_vis.. of every sample <- mask_token + pos[perm]."""
+    _req_cuda(mask_token, pos, perm, x_full)
+    lib = _lib.load()
+    B, Ntot, C = x_full.shape
+    _lib.check(lib.cwm_fill_mask_tokens(mask_token.data_ptr(), pos.data_ptr(), perm.data_ptr(), B, Ntot, n_vis, C,
+                                        x_full.data_ptr(), _stream(x_full)))
+    return x_full

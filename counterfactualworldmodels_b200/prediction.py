@@ -1,0 +1,235 @@
+"""Host-side mirror of the reference's predictor wrapper for the hot path
+(``cwm/models/prediction.py``: ``PredictorBasedGenerator._preprocess / predict / pred_patches_to_video /
+predict_per_sample / batch_predict_per_sample``; ``cwm/models/masking.py:90-132`` ``RectangularizeMasks``).
+
+Same names, argument meaning and error behaviour as the reference for this path; the arithmetic
+(normalise, gather, VMAE forward, scatter + unpatchify) runs in libcwm_b200.  Mask *generation*, patch
+perturbations, RAFT flow and the statistics built on top are out of scope ("next").
+"""
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib
+from .vmae import (IMAGENET_DEFAULT_MEAN, IMAGENET_DEFAULT_STD, PretrainVisionTransformer, compact_mask)
+
+
+class RectangularizeMasks(nn.Module):
+    """Make sure all masks in a batch have the same number of 1s and 0s (cwm/models/masking.py:90-132).
+    Host-side integer bookkeeping; mutates ``masks`` in place like the reference and draws from the global torch
+    RNG (``torch.randperm``) only for rows that actually need changes."""
+
+    def __init__(self, truncation_mode='min'):
+        super().__init__()
+        self._mode = truncation_mode
+        assert self._mode in ['min', 'max', 'mean', 'full', 'none', None], (self._mode)
+
+    def set_mode(self, mode):
+        self._mode = mode
+
+    def __call__(self, masks):
+        if self._mode in ['none', None]:
+            return masks
+        assert isinstance(masks, torch.Tensor), type(masks)
+        if self._mode == 'full':
+            return torch.ones_like(masks)
+        shape = masks.shape
+        masks = masks.flatten(1)
+        B, N = masks.shape
+        num_masked = masks.float().sum(-1)
+        M = {'min': torch.amin, 'max': torch.amax, 'mean': torch.mean}[self._mode](num_masked).long()
+        num_changes = (num_masked.long() - M).cpu()
+        if not bool(num_changes.any()):
+            return masks.view(*shape) if list(masks.shape) != list(shape) else masks
+        for b in range(B):
+            nc = int(num_changes[b])
+            if nc > 0:
+                inds = torch.where(masks[b])[0]
+                inds = inds[torch.randperm(inds.size(0))[:nc].to(inds.device)]
+                masks[b, inds] = 0
+            elif nc < 0:
+                inds = torch.where(~masks[b])[0]
+                inds = inds[torch.randperm(inds.size(0))[:-nc].to(inds.device)]
+                masks[b, inds] = 1
+        if list(masks.shape) != list(shape):
+            masks = masks.view(*shape)
+        return masks
+
+
+def unpatchify_scatter(y, x_raw, inv_perm, n_vis, patch_size):
+    """a12: ``pred_patches_to_video`` (prediction.py:245-259): predictions at masked patches, the raw input at
+    visible patches (bit-exact copy), laid out back as a video [B, T, C, H, W]."""
+    lib = _lib.load()
+    B, T, C, H, W = x_raw.shape
+    pt, ph, pw = patch_size
+    if x_raw.dtype != torch.float32:
+        x_raw = x_raw.float()
+    out = torch.empty(B, T, C, H, W, dtype=torch.float32, device=x_raw.device)
+    if y is not None:
+        y = y.contiguous()
+        if y.dtype != torch.float32:
+            y = y.float()
+    stream = torch.cuda.current_stream(x_raw.device).cuda_stream
+    _lib.check(lib.cwm_unpatchify_scatter(y.data_ptr() if y is not None else None, x_raw.data_ptr(),
+                                          _lib.strides5(x_raw), inv_perm.data_ptr(), B, T, C, H, W, pt, ph, pw,
+                                          int(n_vis), out.data_ptr(), stream))
+    return out
+
+
+class PredictorBasedGenerator(nn.Module):
+    """The slice of cwm/models/prediction.py:16-540 that brackets the predictor call."""
+
+    def __init__(self, predictor=None, imagenet_normalize_inputs=False, temporal_dim=2, seed=0,
+                 mask_generator=None, **kwargs):
+        super().__init__()
+        if predictor is None:
+            raise ValueError("There is no predictor set for this generator and no model to load to")
+        self.predictor = predictor
+        self.imagenet_normalize_inputs = imagenet_normalize_inputs
+        self.set_temporal_dim(temporal_dim)
+        self.rng = np.random.RandomState(seed=seed)
+        self.seed = seed
+        self.mask_generator = mask_generator
+        self.mask_rectangularizer = RectangularizeMasks('min')
+        self.x = self.mask = self.inp_shape = None
+
+    # ---- attributes the callers read (prediction.py:131-214) ----
+    @property
+    def patch_size(self):
+        if hasattr(self.predictor, 'patch_size'):
+            return self.predictor.patch_size
+        return self.predictor.encoder.patch_embed.proj.kernel_size
+
+    @property
+    def image_size(self):
+        return self.predictor.image_size
+
+    @property
+    def sequence_length(self):
+        return getattr(self.predictor, 'num_frames', 2)
+
+    @property
+    def mask_shape(self):
+        pt, ph, pw = self.patch_size
+        h, w = self.image_size[-2:] if self.inp_shape is None else self.inp_shape[-2:]
+        return (self.sequence_length // pt, h // ph, w // pw)
+
+    def set_temporal_dim(self, t_dim=1):
+        if t_dim == 1:
+            self.predictor.t_dim, self.predictor.c_dim = 1, 2
+        elif t_dim == 2:
+            self.predictor.c_dim, self.predictor.t_dim = 1, 2
+        else:
+            raise ValueError("temporal_dim must be 1 or 2")
+
+    @property
+    def t_dim(self):
+        return self.predictor.t_dim
+
+    @property
+    def c_dim(self):
+        return self.predictor.c_dim
+
+    def set_image_size(self, *args, **kwargs):
+        if hasattr(self.predictor, 'set_image_size'):
+            self.predictor.set_image_size(*args, **kwargs)
+        else:
+            self.predictor.image_size = args[0]
+
+    def get_zeros_mask(self, x=None, frame=-1):
+        if x is None:
+            x = self.x
+        self.inp_shape = x.shape
+        mask = torch.zeros(self.mask_shape, device=x.device, dtype=torch.bool)
+        if frame is not None:
+            mask[frame, ...] = torch.ones_like(mask[frame, ...])
+        return mask.flatten().unsqueeze(0).expand(x.shape[0], -1)
+
+    def generate_mask(self, x=None):
+        assert self.mask_generator is not None
+        if x is None:
+            x = self.x
+        mask = self.mask_generator(x).view(x.size(0), -1).to(x.device)
+        return self.mask_rectangularizer(mask)
+
+    # ---- a1 ----
+    def _preprocess(self, x):
+        """prediction.py:304-312 (kept for callers that want the normalised tensor; ``predict`` itself fuses the
+        transpose + normalisation into the patch gather)."""
+        if self.t_dim != 1:
+            x = x.transpose(self.t_dim, self.c_dim)
+        if self.imagenet_normalize_inputs:
+            mean = torch.as_tensor(IMAGENET_DEFAULT_MEAN).to(x.device)[None, None, :, None, None].to(x)
+            std = torch.as_tensor(IMAGENET_DEFAULT_STD).to(x.device)[None, None, :, None, None].to(x)
+            if self.t_dim == 2:
+                mean, std = mean.transpose(1, 2), std.transpose(1, 2)
+            x = (x - mean) / std
+        return x
+
+    # ---- a12 ----
+    def pred_patches_to_video(self, y, x, mask):
+        """input at visible positions, preds at masked positions (prediction.py:245-259)."""
+        mask = mask.reshape(x.shape[0], -1)
+        _, inv, nvis = compact_mask(mask.to(x.device))
+        counts = nvis.cpu()
+        if not bool((counts == counts[0]).all()):
+            raise RuntimeError("shape mismatch: rows of the mask have different numbers of masked tokens")
+        return unpatchify_scatter(y, x, inv, int(counts[0]), self.patch_size)
+
+    # ---- the call into the predictor (prediction.py:406-454) ----
+    @torch.no_grad()
+    def predict(self, x=None, mask=None, frame=-1, reset_masks=True, *args, **kwargs):
+        if x is None:
+            x = self.x
+        if mask is None:
+            mask = self.generate_mask(x)
+        self.inp_shape = x.shape
+        self.set_image_size(x.shape[-2:])
+        mask = mask if (x.size(0) == 1) else self.mask_rectangularizer(mask)
+        if isinstance(self.predictor, PretrainVisionTransformer):
+            xin = x.transpose(self.t_dim, self.c_dim) if self.t_dim != 1 else x  # a view, never materialised
+            norm = (IMAGENET_DEFAULT_MEAN, IMAGENET_DEFAULT_STD) if self.imagenet_normalize_inputs else None
+            y = self.predictor(xin, mask, *args, input_norm=norm, **kwargs)
+            _, inv, n_vis = self.predictor.last_aux
+            y = unpatchify_scatter(y, x, inv, n_vis, self.patch_size)
+        else:
+            y = self.predictor(self._preprocess(x), mask, *args, **kwargs)
+            if len(y.shape) != 5:
+                y = self.pred_patches_to_video(y, x, mask=mask)
+        if frame is not None:
+            frame = frame % y.size(1)
+            y = y[:, frame:frame + 1]
+        return y
+
+    def forward(self, x, mask=None, frame=None, *args, **kwargs):
+        return self.predict(x, mask, frame, *args, **kwargs)
+
+    def predict_per_sample(self, x, masks, frame=-1, batch_size=None, split_samples=True, *args, **kwargs):
+        """Run predictions in parallel for S sample masks (prediction.py:456-482)."""
+        assert len(masks.shape) == 3, masks.shape
+        S = masks.size(-1)
+        if x is None:
+            x = self.x
+        B = x.size(0)
+        BS = B * S
+        x = x[:, None].expand(-1, S, -1, -1, -1, -1).reshape(BS, *x.shape[1:])
+        masks = masks.transpose(1, 2).reshape(BS, -1)
+        y = self.predict(x=x, mask=masks, frame=frame, *args, **kwargs)
+        if not split_samples:
+            return y
+        p_dims = tuple(range(2, len(y.shape) + 1))
+        return y.view(B, S, *y.shape[1:]).permute(0, *p_dims, 1)
+
+    def batch_predict_per_sample(self, x, masks, frame=-1, batch_size=None, sample_dim=None, **kwargs):
+        """prediction.py:497-540 for ``sample_dim=0`` (the layout every caller on the path uses,
+        segmentation.py:423-430): ``x`` [S, T, C, H, W] and ``masks`` [S, N], processed in chunks."""
+        if sample_dim != 0:
+            raise NotImplementedError("only sample_dim=0 is used by the counterfactual path")
+        S = masks.size(0)
+        if batch_size is None:
+            batch_size = S
+        batch_size = max(1, batch_size)
+        ys = []
+        for b0 in range(0, S, batch_size):
+            ys.append(self.predict(x[b0:b0 + batch_size], mask=masks[b0:b0 + batch_size], frame=frame, **kwargs))
+        return torch.cat(ys, 0)

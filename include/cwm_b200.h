@@ -1,0 +1,191 @@
+/*
+ * cwm_b200.h -- C ABI of libcwm_b200.so: the B200 (sm_100a) implementation of the CWM masked
+ * video-autoencoder (VMAE) forward path.
+ *
+ * This header is the drop-in boundary.  The reference (neuroailab/CounterfactualWorldModels) is pure
+ * Python/PyTorch and has no FFI of its own; the entry points below are what a ctypes binding inside the
+ * reference's `cwm/models/VideoMAE/vmae.py` would call.  Every function
+ *   - takes raw DEVICE pointers, plain ints and a cudaStream_t (as void*), no torch types;
+ *   - is asynchronous on `stream` and never synchronises the host;
+ *   - returns 0 on success or a negative cwm_status; the message is available from cwm_last_error();
+ *   - never throws across the ABI.
+ * All matrices are row-major.  "f16" buffers are IEEE binary16 stored as uint16_t.
+ *
+ * Reference citations are relative to /root/reference (file:line).
+ */
+#ifndef CWM_B200_H_
+#define CWM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CWM_B200_ABI_VERSION 1
+
+typedef void* cwm_stream_t; /* cudaStream_t */
+
+enum cwm_status {
+  CWM_OK = 0,
+  CWM_ERR_INVALID = -1,     /* bad argument (shape, alignment, null pointer)        */
+  CWM_ERR_CUDA = -2,        /* a CUDA runtime/driver call failed                    */
+  CWM_ERR_UNSUPPORTED = -3, /* valid in the reference but not implemented here      */
+  CWM_ERR_WORKSPACE = -4,   /* caller-provided workspace too small                  */
+  CWM_ERR_ARCH = -5         /* device is not sm_100                                 */
+};
+
+/* ---- library ------------------------------------------------------------------------------------- */
+int cwm_abi_version(void);
+const char* cwm_last_error(void);
+/* 0 when the current device is compute capability 10.x (B200), CWM_ERR_ARCH otherwise. */
+int cwm_device_check(void);
+
+/* ---- a4: visible-token compaction ---------------------------------------------------------------
+ * Replaces `x[~mask].reshape(B,-1,C)` (cwm/models/VideoMAE/vmae.py:166-167) and the two boolean gathers
+ * `expand_pos_embed[~mask]`, `expand_pos_embed[mask]` (vmae.py:555-556).
+ *   mask       [B, Ntot] bytes, non-zero = masked (torch.bool storage)
+ *   perm       [B, Ntot] int32 out: first n_visible[b] entries = visible token indices ascending, the
+ *              rest = masked token indices ascending.  This is exactly the decoder token order of
+ *              vmae.py:557 (`cat([x_vis, mask_tokens])`).
+ *   inv_perm   [B, Ntot] int32 out (may be NULL): inv_perm[b, perm[b, j]] = j
+ *   n_visible  [B] int32 out
+ * Integer work: bit-exact with torch.nonzero. */
+int cwm_compact_mask(const uint8_t* mask, int B, int Ntot, int32_t* perm, int32_t* inv_perm,
+                     int32_t* n_visible, cwm_stream_t stream);
+
+/* ---- a1+a2 (input side): normalise + gather visible patches --------------------------------------
+ * Replaces the im2col half of `PatchEmbed.forward` (cwm/models/VideoMAE/utils.py:178-198) for the visible
+ * tokens only, optionally fused with `imagenet_normalize` (cwm/models/utils.py:15-21).
+ *   x          fp32 video, logical layout [B, C, T, H, W] with arbitrary element strides xs[5]
+ *              (the reference hands a transposed view, cwm/models/prediction.py:304-312)
+ *   perm       as produced by cwm_compact_mask (row stride Ntot); rows_per_sample = Nvis entries are used
+ *   mean/stdv  NULL, or per-channel HOST arrays [C] fp32 (they are constants of the caller, utils.py:12-13):
+ *              value = (x - mean[c]) / stdv[c], same operation order as the reference
+ *   out        f16 [B*rows_per_sample, K], K = C*pt*ph*pw ordered (c, kt, kh, kw) = Conv3d weight order */
+int cwm_patch_gather(const float* x, const int64_t xs[5], int B, int C, int T, int H, int W, int pt,
+                     int ph, int pw, const int32_t* perm, int Ntot, int rows_per_sample,
+                     const float* mean, const float* stdv, uint16_t* out, cwm_stream_t stream);
+
+/* ---- LayerNorm (a5/a8/a11) -----------------------------------------------------------------------
+ * nn.LayerNorm(C, eps) over the last dim (cwm/models/VideoMAE/utils.py:130,136; vmae.py:84,206), fp32
+ * statistics, f16 output (the operand of the following GEMM).
+ * Row mapping: output row m reads input row (m / grp_rows) * grp_stride + grp_offset + m % grp_rows when
+ * grp_rows > 0 (used for `x[:, -return_token_num:]`, vmae.py:250-251), else row m. */
+int cwm_layernorm_f16(const float* x, int M, int C, const float* gamma, const float* beta, float eps,
+                      int grp_rows, int grp_stride, int grp_offset, uint16_t* out, cwm_stream_t stream);
+
+/* ---- GEMM with fused epilogue (a2, a6, a7, a9, a11) ---------------------------------------------
+ * Y[M,N] = epilogue(A[M,K] . W[N,K]^T), A and W f16 (K contiguous, like nn.Linear.weight), fp32
+ * accumulation in tensor memory (tcgen05.mma kind::f16).  K % 16 == 0 and K >= 16; lda = K, ldw = K.  */
+enum cwm_epilogue {
+  CWM_EPI_F16 = 0,      /* out_f16 = (acc + bias) * (col < scale_cols ? scale : 1)      (qkv: utils.py:89-97)  */
+  CWM_EPI_GELU_F16 = 1, /* out_f16 = gelu_erf(acc + bias)                               (fc1: utils.py:48-49)  */
+  CWM_EPI_RES_F32 = 2,  /* out_f32 = res_f32 + acc + bias                               (proj/fc2: utils.py:148-149) */
+  CWM_EPI_F32 = 3       /* out_f32 = acc + bias                                         (head: vmae.py:251)    */
+};
+
+typedef struct cwm_gemm_epilogue {
+  int32_t mode;          /* enum cwm_epilogue */
+  const float* bias;     /* [N] or NULL */
+  float scale;           /* CWM_EPI_F16 only */
+  int32_t scale_cols;    /* CWM_EPI_F16 only: columns [0, scale_cols) are multiplied by scale */
+  const float* res;      /* CWM_EPI_RES_F32: residual, leading dimension ldr */
+  int32_t ldr;
+  const int32_t* res_gather; /* optional: residual row = res_gather[(m / grp_rows) * gather_stride + m % grp_rows]
+                                (pos-embed add for visible tokens only: vmae.py:162-167, :555-557) */
+  int32_t gather_stride;
+  int32_t grp_rows;      /* > 0: output row = (m / grp_rows) * grp_out_stride + m % grp_rows (writes x_vis
+                            straight into the decoder sequence, vmae.py:557) */
+  int32_t grp_out_stride;
+  void* out;             /* f16 or fp32, leading dimension ldo */
+  int32_t ldo;
+} cwm_gemm_epilogue;
+
+int cwm_gemm_f16(const uint16_t* A, const uint16_t* W, int M, int N, int K, const cwm_gemm_epilogue* epi,
+                 cwm_stream_t stream);
+
+/* ---- attention (a6) --------------------------------------------------------------------------------
+ * softmax(q k^T) v per (sample, head), unmasked, head_dim 64 (cwm/models/VideoMAE/utils.py:108-113); q is
+ * already scaled (utils.py:97 is fused into the qkv GEMM epilogue).
+ *   qkv  f16 [B, N, 3, H, 64]  (the layout `F.linear(...).reshape(B,N,3,H,-1)` has, utils.py:93-94)
+ *   out  f16 [B, N, H*64]      (= `x.transpose(1,2).reshape(B,N,-1)`, utils.py:118)               */
+int cwm_attention_f16(const uint16_t* qkv, int B, int N, int H, int head_dim, uint16_t* out,
+                      cwm_stream_t stream);
+
+/* ---- a10: mask-token rows of the decoder input ---------------------------------------------------
+ * x_full[b, Nvis + j, :] = mask_token + pos[perm[b, Nvis + j], :]  (vmae.py:556-557).  The visible rows are
+ * written by the encoder_to_decoder GEMM epilogue. */
+int cwm_fill_mask_tokens(const float* mask_token, const float* pos, const int32_t* perm, int B, int Ntot,
+                         int Nvis, int C, float* x_full, cwm_stream_t stream);
+
+/* ---- a12: scatter predictions + unpatchify ------------------------------------------------------
+ * `pred_patches_to_video` (cwm/models/prediction.py:245-259) with `Patchify` (cwm/models/patches.py:67-109):
+ * out[b,t,c,y,x] = x_raw[...] where the patch is visible, else y[b, rank, ((kt*ph+kh)*pw+kw)*C + c].
+ *   y        fp32 [B, Nmask, D]
+ *   x_raw    fp32, logical [B, T, C, H, W] with element strides xs[5]
+ *   inv_perm from cwm_compact_mask
+ *   out      fp32 contiguous [B, T, C, H, W] */
+int cwm_unpatchify_scatter(const float* y, const float* x_raw, const int64_t xs[5], const int32_t* inv_perm,
+                           int B, int T, int C, int H, int W, int pt, int ph, int pw, int Nvis, float* out,
+                           cwm_stream_t stream);
+
+/* ---- whole forward (a1..a11) ---------------------------------------------------------------------
+ * `PretrainVisionTransformer.forward(x, mask)` (cwm/models/VideoMAE/vmae.py:539-560).                */
+typedef struct cwm_block_weights {
+  const float *ln1_g, *ln1_b;       /* norm1.{weight,bias}              */
+  const uint16_t* w_qkv;            /* attn.qkv.weight   f16 [3C, C]    */
+  const float* b_qkv;               /* cat(q_bias, 0, v_bias) [3C] or NULL (utils.py:89-91) */
+  const uint16_t* w_proj;           /* attn.proj.weight  f16 [C, C]     */
+  const float* b_proj;
+  const float *ln2_g, *ln2_b;
+  const uint16_t* w_fc1;            /* mlp.fc1.weight    f16 [hidden, C] */
+  const float* b_fc1;
+  const uint16_t* w_fc2;            /* mlp.fc2.weight    f16 [C, hidden] */
+  const float* b_fc2;
+} cwm_block_weights;
+
+typedef struct cwm_vmae_model {
+  /* geometry */
+  int32_t in_chans, num_frames, img_h, img_w, pt, ph, pw;
+  int32_t enc_dim, enc_depth, enc_heads, enc_hidden;
+  int32_t dec_dim, dec_depth, dec_heads, dec_hidden;
+  int32_t out_dim; /* D = decoder_num_classes */
+  float ln_eps;
+  float enc_qk_scale, dec_qk_scale; /* Attention.scale = qk_scale or head_dim ** -0.5 (utils.py:67) */
+  /* weights (device pointers, owned by the caller) */
+  const uint16_t* w_patch;    /* encoder.patch_embed.proj.weight f16 [Ce, C*pt*ph*pw] */
+  const float* b_patch;       /* [Ce] */
+  const float* pos_enc;       /* sinusoid table fp32 [Ntot, Ce] (utils.py:251-268) */
+  const cwm_block_weights* enc_blocks; /* HOST array, enc_depth entries */
+  const float *enc_norm_g, *enc_norm_b;
+  const uint16_t* w_e2d;      /* encoder_to_decoder.weight f16 [Cd, Ce], no bias (vmae.py:355) */
+  const float* mask_token;    /* [Cd] */
+  const float* pos_dec;       /* fp32 [Ntot, Cd] (vmae.py:366) */
+  const cwm_block_weights* dec_blocks; /* HOST array, dec_depth entries */
+  const float *dec_norm_g, *dec_norm_b;
+  const uint16_t* w_head;     /* decoder.head.weight f16 [D, Cd] */
+  const float* b_head;        /* [D] */
+} cwm_vmae_model;
+
+/* Bytes of scratch the forward needs for a batch of B samples with Nvis visible tokens each. */
+size_t cwm_vmae_workspace_bytes(const cwm_vmae_model* model, int B, int Nvis);
+
+/*   x         fp32 logical [B, C, T, H, W], element strides xs[5]
+ *   norm_mean/norm_std  NULL, or HOST arrays [C]: fuse imagenet_normalize (prediction.py:309-310) into the gather
+ *   perm      [B, Ntot] from cwm_compact_mask; every row must have exactly Nvis visible tokens (the reference
+ *             raises at vmae.py:167 otherwise; the host wrapper checks n_visible)
+ *   y         fp32 out [B, Ntot - Nvis, D]
+ *   workspace device scratch of at least cwm_vmae_workspace_bytes(model, B, Nvis) bytes, 1024-byte aligned */
+int cwm_vmae_forward(const cwm_vmae_model* model, const float* x, const int64_t xs[5], int B,
+                     const float* norm_mean, const float* norm_std, const int32_t* perm, int Nvis, float* y,
+                     void* workspace, size_t workspace_bytes, cwm_stream_t stream);
+
+/* Number of kernel launches the last cwm_vmae_forward on this thread enqueued (for bench accounting). */
+int cwm_last_forward_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CWM_B200_H_ */

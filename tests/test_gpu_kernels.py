@@ -1,0 +1,232 @@
+"""Stage-wise parity of every CUDA kernel, called through the C ABI, against the CPU oracle (integer stages:
+bit-exact) or a plain fp32 torch restatement of the same op (floating-point stages, tolerance stated per test)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import vmae_oracle as oracle
+from counterfactualworldmodels_b200 import _lib, ops, prediction, synthetic
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def test_device_is_sm100():
+    assert _lib.load().cwm_device_check() == 0
+
+
+# ---------------------------------------------------------------- a4 compaction (bit-exact)
+@pytest.mark.parametrize("B,N,p", [(1, 1, 0.5), (3, 97, 0.6), (4, 1568, 0.5), (2, 6272, 0.495), (5, 256, 0.0),
+                                   (5, 255, 1.0), (64, 1568, 0.5), (2, 6336, 0.3)])
+def test_compact_mask_bit_exact(B, N, p):
+    rng = np.random.RandomState(B * 1000 + N)
+    mask = rng.rand(B, N) < p
+    perm_o, inv_o, nvis_o = oracle.compact_mask(mask)
+    perm, inv, nvis = ops.compact_mask(torch.from_numpy(mask).to(DEV))
+    assert np.array_equal(perm.cpu().numpy(), perm_o)
+    assert np.array_equal(inv.cpu().numpy(), inv_o)
+    assert np.array_equal(nvis.cpu().numpy(), nvis_o)
+    # and against torch itself, the way the reference computes it (vmae.py:167, :555-556)
+    mt = torch.from_numpy(mask)
+    for b in range(B):
+        assert torch.equal(perm[b, :nvis_o[b]].cpu().long(), torch.nonzero(~mt[b]).flatten())
+        assert torch.equal(perm[b, nvis_o[b]:].cpu().long(), torch.nonzero(mt[b]).flatten())
+
+
+def test_compact_mask_empty_batch():
+    perm, inv, nvis = ops.compact_mask(torch.zeros(0, 16, dtype=torch.bool, device=DEV))
+    assert perm.shape == (0, 16)
+
+
+# ---------------------------------------------------------------- a1+a2 gather
+@pytest.mark.parametrize("cfg,normalize", [("tiny_4x4", True), ("tiny_8x8", False), ("base_8x8", True)])
+def test_patch_gather_matches_unfold(cfg, normalize):
+    hw = synthetic.image_hw(cfg)
+    msize = synthetic.mask_size(cfg)
+    ps = synthetic.oracle_cfg(cfg)["patch_size"]
+    B = 2
+    x_raw = synthetic.make_video(B, hw, seed=3)                      # [B,T,C,H,W]
+    mask = synthetic.make_mask(B, msize, num_clumps=2, seed=4)
+    perm_o, _, nvis_o = oracle.compact_mask(mask.numpy())
+    xin = x_raw.to(DEV).transpose(1, 2)                               # non-contiguous view, like _preprocess
+    perm, _, _ = ops.compact_mask(mask.to(DEV))
+    norm = (oracle.IMAGENET_DEFAULT_MEAN, oracle.IMAGENET_DEFAULT_STD) if normalize else None
+    a = ops.patch_gather(xin, perm, int(nvis_o[0]), ps, input_norm=norm)
+    # oracle: preprocess, then im2col in Conv3d weight order (c, kt, kh, kw)
+    xp = oracle.preprocess(x_raw, normalize)                          # [B,C,T,H,W]
+    pt, ph, pw = ps
+    Bc, C, T, H, W = xp.shape
+    cols = xp.reshape(B, C, T // pt, pt, H // ph, ph, W // pw, pw).permute(0, 2, 4, 6, 1, 3, 5, 7)
+    cols = cols.reshape(B, -1, C * pt * ph * pw)
+    want = torch.stack([cols[b, perm_o[b, :nvis_o[b]]] for b in range(B)]).reshape(-1, cols.shape[-1])
+    assert torch.equal(a.cpu(), want.to(torch.float16))               # same fp32 ops, then one rounding
+
+
+# ---------------------------------------------------------------- LayerNorm
+@pytest.mark.parametrize("M,C", [(7, 128), (1000, 384), (333, 512), (257, 768), (64, 1024)])
+def test_layernorm_f16(M, C):
+    g = torch.Generator().manual_seed(M + C)
+    x = torch.randn(M, C, generator=g) * 3 + 0.5
+    gamma = torch.rand(C, generator=g) + 0.5
+    beta = torch.randn(C, generator=g)
+    want = F.layer_norm(x, (C,), gamma, beta, 1e-6)
+    got = ops.layernorm_f16(x.to(DEV), gamma.to(DEV), beta.to(DEV), 1e-6).cpu().float()
+    # tolerance: one f16 rounding of values up to ~|10| (2^-11 relative) + fp32 statistics noise
+    assert (got - want).abs().max().item() <= 4e-3 + 1e-3 * want.abs().max().item()
+    assert (got - want.to(torch.float16).float()).abs().mean().item() < 1e-4
+
+
+def test_layernorm_row_gather():
+    B, Ntot, Nvis, C = 3, 50, 18, 256
+    x = torch.randn(B * Ntot, C)
+    gamma, beta = torch.ones(C), torch.zeros(C)
+    Nm = Ntot - Nvis
+    got = ops.layernorm_f16(x.to(DEV), gamma.to(DEV), beta.to(DEV), 1e-6, M=B * Nm, grp_rows=Nm, grp_stride=Ntot,
+                            grp_offset=Nvis).cpu().float()
+    want = F.layer_norm(x.view(B, Ntot, C)[:, -Nm:], (C,)).reshape(-1, C)
+    assert (got - want).abs().max().item() < 5e-3
+
+
+# ---------------------------------------------------------------- GEMM + epilogues
+def _gemm_ref(a, w):
+    return a.float() @ w.float().t()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (1, 64, 16), (300, 768, 192), (1000, 2304, 768), (257, 384, 384),
+                                   (513, 1152, 384), (130, 48, 512), (129, 192, 384), (1584, 1024, 48),
+                                   (777, 3072, 768), (50688, 768, 3072)])
+def test_gemm_f32_bias(M, N, K):
+    g = torch.Generator().manual_seed(M * 7 + N)
+    a = (torch.randn(M, K, generator=g)).to(torch.float16).to(DEV)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.float16).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    got = ops.gemm_f16(a, w, _lib.EPI_F32, bias=bias)
+    want = _gemm_ref(a, w) + bias
+    # fp32 accumulation of exact f16 products: only summation-order noise
+    assert (got - want).abs().max().item() < 2e-3
+    assert (got - want).abs().mean().item() < 1e-4
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 768, 768), (129, 2304, 768), (1000, 1536, 512)])
+def test_gemm_f16_scale_cols(M, N, K):
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(torch.float16).to(DEV)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.float16).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    sc = N // 3
+    got = ops.gemm_f16(a, w, _lib.EPI_F16, bias=bias, scale=0.125, scale_cols=sc).float()
+    want = _gemm_ref(a, w) + bias
+    want[:, :sc] *= 0.125
+    assert (got - want).abs().max().item() < 1e-2  # one f16 rounding of |values| < ~8
+    assert torch.equal(got.half(), want.half()) or (got - want).abs().mean().item() < 5e-4
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 3072, 768), (129, 512, 128), (640, 2048, 512)])
+def test_gemm_gelu(M, N, K):
+    g = torch.Generator().manual_seed(M + N)
+    a = torch.randn(M, K, generator=g).to(torch.float16).to(DEV)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.float16).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    got = ops.gemm_f16(a, w, _lib.EPI_GELU_F16, bias=bias).float()
+    want = F.gelu(_gemm_ref(a, w) + bias)
+    assert (got - want).abs().max().item() < 6e-3
+    assert (got - want).abs().mean().item() < 3e-4
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 768, 3072), (257, 384, 1536), (1000, 1024, 1024)])
+def test_gemm_residual_inplace(M, N, K):
+    g = torch.Generator().manual_seed(M + K)
+    a = torch.randn(M, K, generator=g).to(torch.float16).to(DEV)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.float16).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    x = torch.randn(M, N, generator=g).to(DEV)
+    want = x + _gemm_ref(a, w) + bias
+    got = ops.gemm_f16(a, w, _lib.EPI_RES_F32, bias=bias, res=x, out=x)
+    assert got.data_ptr() == x.data_ptr()
+    assert (got - want).abs().max().item() < 2e-3
+
+
+def test_gemm_gathered_residual_and_row_remap():
+    """The two special uses: patch-embed (+pos[perm]) and encoder_to_decoder written into the decoder sequence."""
+    B, Nvis, Ntot, K, N = 3, 37, 80, 192, 256
+    g = torch.Generator().manual_seed(5)
+    a = torch.randn(B * Nvis, K, generator=g).to(torch.float16).to(DEV)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.float16).to(DEV)
+    pos = torch.randn(Ntot, N, generator=g).to(DEV)
+    perm = torch.stack([torch.randperm(Ntot, generator=g) for _ in range(B)]).to(torch.int32).to(DEV)
+    acc = _gemm_ref(a, w).view(B, Nvis, N)
+    want_rows = acc + pos[perm[:, :Nvis].long()]
+    # (1) compact output
+    got = ops.gemm_f16(a, w, _lib.EPI_RES_F32, res=pos, res_gather=perm, gather_stride=Ntot, grp_rows=Nvis,
+                       grp_out_stride=Nvis)
+    assert (got.view(B, Nvis, N) - want_rows).abs().max().item() < 2e-3
+    # (2) scattered into [B, Ntot, N]; untouched rows keep their content
+    out = torch.full((B * Ntot, N), -7.0, device=DEV)
+    ops.gemm_f16(a, w, _lib.EPI_RES_F32, res=pos, res_gather=perm, gather_stride=Ntot, grp_rows=Nvis,
+                 grp_out_stride=Ntot, out=out)
+    out = out.view(B, Ntot, N)
+    assert (out[:, :Nvis] - want_rows).abs().max().item() < 2e-3
+    assert bool((out[:, Nvis:] == -7.0).all())
+
+
+# ---------------------------------------------------------------- attention
+def _attn_ref(qkv, B, N, H):
+    q, k, v = qkv.float().view(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)
+    p = (q @ k.transpose(-2, -1)).softmax(-1)
+    return (p @ v).transpose(1, 2).reshape(B * N, H * 64)
+
+
+@pytest.mark.parametrize("B,N,H", [(1, 128, 1), (2, 256, 2), (1, 100, 2), (2, 456, 4), (1, 792, 12), (2, 896, 2),
+                                   (1, 1568, 6), (1, 3168, 2), (1, 129, 1), (3, 385, 1)])
+def test_attention_matches_fp32_softmax(B, N, H):
+    g = torch.Generator().manual_seed(B * 100 + N + H)
+    qkv = torch.randn(B * N, 3 * H * 64, generator=g)
+    qkv[:, :H * 64] *= 0.125 * 3.0   # pre-scaled q, with enough spread that the running max moves
+    qkv = qkv.to(torch.float16).to(DEV)
+    got = ops.attention_f16(qkv, B, N, H).float()
+    want = _attn_ref(qkv, B, N, H)
+    # f16 P and V operands, fp32 accumulate: ~1e-3 absolute on O(1) outputs
+    assert torch.isfinite(got).all()
+    assert (got - want).abs().max().item() < 4e-3
+    assert (got - want).abs().mean().item() < 3e-4
+
+
+def test_attention_large_logits_rescale_path():
+    """Rows whose maximum keeps growing across KV tiles exercise the lazy O-rescale."""
+    B, N, H = 1, 640, 1
+    g = torch.Generator().manual_seed(9)
+    qkv = torch.randn(B * N, 3 * 64, generator=g)
+    ramp = torch.linspace(0.2, 4.0, N)[:, None]
+    qkv[:, 64:128] *= ramp           # keys grow with position -> later tiles dominate
+    qkv = qkv.to(torch.float16).to(DEV)
+    got = ops.attention_f16(qkv, B, N, H).float()
+    want = _attn_ref(qkv, B, N, H)
+    assert (got - want).abs().max().item() < 6e-3
+
+
+# ---------------------------------------------------------------- a10 / a12
+def test_fill_mask_tokens():
+    B, Ntot, Nvis, C = 2, 64, 20, 128
+    g = torch.Generator().manual_seed(1)
+    mt, pos = torch.randn(C, generator=g).to(DEV), torch.randn(Ntot, C, generator=g).to(DEV)
+    perm = torch.stack([torch.randperm(Ntot, generator=g) for _ in range(B)]).to(torch.int32).to(DEV)
+    x = torch.full((B, Ntot, C), 3.0, device=DEV)
+    ops.fill_mask_tokens(mt, pos, perm, Nvis, x)
+    assert bool((x[:, :Nvis] == 3.0).all())
+    assert torch.equal(x[:, Nvis:], mt + pos[perm[:, Nvis:].long()])
+
+
+@pytest.mark.parametrize("cfg", ["tiny_4x4", "tiny_8x8", "base_8x8"])
+def test_unpatchify_scatter_bit_exact(cfg):
+    hw, msize = synthetic.image_hw(cfg), synthetic.mask_size(cfg)
+    ps = synthetic.oracle_cfg(cfg)["patch_size"]
+    B = 2
+    x = synthetic.make_video(B, hw, seed=8)
+    mask = synthetic.make_mask(B, msize, num_clumps=3, seed=9)
+    D = 3 * ps[0] * ps[1] * ps[2]
+    y = torch.randn(B, int(mask[0].sum()), D)
+    want = oracle.pred_patches_to_video(y, x, mask, ps)
+    _, inv, nvis = ops.compact_mask(mask.to(DEV))
+    got = prediction.unpatchify_scatter(y.to(DEV), x.to(DEV), inv, int(nvis[0]), ps)
+    assert torch.equal(got.cpu(), want)   # pure data movement: bit-exact

@@ -1,0 +1,66 @@
+"""Known answers recorded by the reference's own notebook and structural parity of the
+drop-in module: parameter counts, token counts, mask shapes, state_dict keys."""
+import numpy as np
+import pytest
+import torch
+
+import vmae_oracle as oracle
+from conftest import load_golden
+from counterfactualworldmodels_b200 import synthetic, vmae
+
+
+def test_param_count_base_8x8():
+    m = vmae.base_8x8patch_2frames_1tube()
+    assert sum(p.numel() for p in m.parameters()) == 92661312  # SURVEY section 4 [probe]
+    assert m.num_patches == 1568 and m.mask_size == (2, 28, 28) and m.patch_size == (1, 8, 8)
+
+
+def test_param_count_large_4x4():
+    m = vmae.large_4x4patch_2frames_1tube()
+    assert sum(p.numel() for p in m.parameters()) == 340709936  # demo/MovabilityAndMotionCovariance.ipynb:244
+    assert m.num_patches == 6272  # "NUM PATCHES IN ENCODER 6272", ipynb:243
+
+
+def test_reference_mask_known_answer():
+    g = load_golden("large_4x4_b1_factual")
+    assert tuple(g["mask"].shape) == (1, 6272) and int(g["mask"].sum()) == 3104  # ipynb:290-291
+    g = load_golden("base_8x8_b1_factual")
+    assert tuple(g["mask"].shape) == (1, 1568) and int(g["mask"].sum()) == 776
+
+
+def test_golden_param_counts_match_ours():
+    for case, cfg in [("base_8x8_b1_factual", "base_8x8"), ("large_4x4_b1_factual", "large_4x4"),
+                      ("tiny_4x4_b2", "tiny_4x4")]:
+        g = load_golden(case)
+        m = vmae.PretrainVisionTransformer(**synthetic.model_kwargs(cfg))
+        assert sum(p.numel() for p in m.parameters()) == int(g["num_params"][0])
+
+
+def test_state_dict_keys_base():
+    m = vmae.base_8x8patch_2frames_1tube()
+    keys = list(m.state_dict().keys())
+    assert len(keys) == 218  # SURVEY section 8b [probe]
+    assert keys[0] == "mask_token" and keys[1] == "encoder.patch_embed.proj.weight"
+    sd = m.state_dict()
+    assert tuple(sd["encoder.patch_embed.proj.weight"].shape) == (768, 3, 1, 8, 8)
+    assert tuple(sd["encoder.blocks.0.attn.qkv.weight"].shape) == (2304, 768)
+    assert tuple(sd["encoder_to_decoder.weight"].shape) == (384, 768)
+    assert tuple(sd["decoder.head.weight"].shape) == (192, 384)
+    assert "pos_embed" not in sd and "encoder.pos_embed" not in sd  # plain tensors (vmae.py:75,366)
+
+
+@pytest.mark.parametrize("n,d", [(128, 128), (1568, 384), (6272, 512)])
+def test_sinusoid_table_matches_literal_restatement(n, d):
+    ours = vmae.get_sinusoid_encoding_table(n, d)
+    assert torch.equal(ours, oracle.sinusoid_table_cached(n, d))
+    if n <= 1568:
+        assert torch.equal(ours, oracle.sinusoid_table(n, d))
+
+
+def test_weights_regenerate_identically():
+    """The fixtures were produced with the reference model holding init_weights_(seed) weights; the same call on
+    our module must give the same tensors (checked through the stored fingerprint)."""
+    g = load_golden("tiny_4x4_b2")
+    m = vmae.PretrainVisionTransformer(**synthetic.model_kwargs("tiny_4x4"))
+    synthetic.init_weights_(m, seed=1, style="perturbed")
+    assert synthetic.weights_checksum(m) == pytest.approx(float(g["weights_checksum"][0]), rel=0, abs=1e-9)
