@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- counterfactual frames/s of the CWM VMAE hot path on B200 (contract: see the task prompt).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (one rank per GPU under torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...  the reference algorithm on the host cores (CPU oracle)
+
+A "step" is one pass of the hot path (a1..a12: normalise + gather, VMAE forward, scatter + unpatchify) over one
+batch of synthetic counterfactual prompts.  Default workload = BASELINE.json configs[1]: ViT-base VMAE, 8x8 patches,
+224 px, 2 frames, batch 64 motion counterfactuals per GPU (weak scaling: every rank runs its own batch of 64 and
+only the predicted frames are gathered to rank 0 over NCCL at the end of each step).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+# name -> (model config, per-GPU batch, visible 2x2 clumps in frame 1)
+WORKLOADS = {
+    "base_8x8_b64_counterfactual": ("base_8x8", 64, 1),      # BASELINE.json configs[1]
+    "base_4x4_b32": ("base_4x4", 32, 2),                      # configs[2]
+    "large_4x4_b32_movability": ("large_4x4", 32, 1),         # configs[3], per-GPU chunk of the 1024 sweep
+}
+DEFAULT_WORKLOAD = "base_8x8_b64_counterfactual"
+
+
+def flops_per_frame(cfg_name, n_vis):
+    """SURVEY.md section 8d / BASELINE.md section 3 (multiply-add = 2; LN/GELU/softmax excluded)."""
+    from counterfactualworldmodels_b200 import synthetic
+    kw = synthetic.CONFIGS[cfg_name]
+    T, h, w = synthetic.mask_size(cfg_name)
+    Ntot = T * h * w
+    Nmask = Ntot - n_vis
+    D = 3 * kw["tubelet_size"] * kw["patch_size"][0] * kw["patch_size"][1]
+    Ce, Le, Cd, Ld = kw["encoder_embed_dim"], kw["encoder_depth"], kw["decoder_embed_dim"], kw["decoder_depth"]
+    return (2 * Ntot * D * Ce + Le * (24 * n_vis * Ce ** 2 + 4 * n_vis ** 2 * Ce) + 2 * n_vis * Ce * Cd +
+            Ld * (24 * Ntot * Cd ** 2 + 4 * Ntot ** 2 * Cd) + 2 * Nmask * Cd * D)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=p["hbm_gbs"], tflops_burst=p["bf16_tflops"],
+                    tflops_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, tflops_burst=1590.0, tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.proc = None
+        self.lines = []
+        self.idx = device_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_frames_per_s(cfg_name, n_clumps, sample_frames, repeats, threads):
+    """The reference algorithm (CPU oracle port, fp32 eager) on the host cores: frames/s over `repeats` passes of a
+    `sample_frames`-frame sample of the workload."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import vmae_oracle as oracle
+    from counterfactualworldmodels_b200 import synthetic, vmae
+    torch.set_num_threads(threads)
+    m = vmae.PretrainVisionTransformer(**synthetic.model_kwargs(cfg_name))
+    synthetic.init_weights_(m, seed=0, style="reference")
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    x = synthetic.make_video(sample_frames, synthetic.image_hw(cfg_name), seed=0)
+    mask = synthetic.make_mask(sample_frames, synthetic.mask_size(cfg_name), num_clumps=n_clumps, seed=0)
+    ocfg = synthetic.oracle_cfg(cfg_name)
+    times = []
+    with torch.no_grad():
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            oracle.predict(sd, x, mask, ocfg, frame=None)
+            times.append(time.perf_counter() - t0)
+    return times
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg_name, B, n_clumps = WORKLOADS[args.workload]
+    threads = os.cpu_count() or 1
+    sample = args.ref_sample
+    times = cpu_oracle_frames_per_s(cfg_name, n_clumps, sample, args.warmup + args.steps, threads)
+    timed = times[args.warmup:]
+    total = sum(timed)
+    value = sample * len(timed) / total
+    line = {
+        "impl": "reference", "metric": "counterfactual frames/sec", "value": value, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(timed),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "model": cfg_name, "per_gpu_batch": B,
+                   "sample": f"{sample} frames per step (bounded sample of the batch-{B} workload)"},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample} frames x {len(timed)} steps, CPU oracle (oracle/vmae_oracle.py, the "
+                                   "reference algorithm in fp32 eager torch) on the host cores"},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--ref-sample", type=int, default=2, help="frames per step of the CPU reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--also", default="large_4x4_b32_movability",
+                    help="extra workloads measured briefly (comma separated, '' to skip)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch.distributed as dist
+    from counterfactualworldmodels_b200 import _lib, prediction, synthetic, vmae
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback; use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.check(_lib.load().cwm_device_check())
+    peaks = measured_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def measure(workload, steps, warmup, with_e2e, with_profile, sample_clocks):
+        cfg_name, B, n_clumps = WORKLOADS[workload]
+        model = vmae.PretrainVisionTransformer(**synthetic.model_kwargs(cfg_name))
+        synthetic.init_weights_(model, seed=0, style="reference")
+        model = model.to(dev).eval()
+        G = prediction.PredictorBasedGenerator(predictor=model, imagenet_normalize_inputs=True, temporal_dim=2)
+        hw = synthetic.image_hw(cfg_name)
+        n_rot = 3
+        xs_host = [synthetic.make_video(B, hw, seed=100 * rank + i).pin_memory() for i in range(n_rot)]
+        ms_host = [synthetic.make_mask(B, model.mask_size, num_clumps=n_clumps, seed=100 * rank + i).pin_memory()
+                   for i in range(n_rot)]
+        xs_dev = [x.to(dev) for x in xs_host]
+        ms_dev = [m.to(dev) for m in ms_host]
+        n_vis = int((~ms_host[0][0]).sum())
+        gather_buf = [torch.empty(B, 1, *xs_host[0].shape[2:], device=dev) for _ in range(world)] \
+            if (world > 1 and rank == 0) else None
+
+        def step(i, x, m):
+            video = G.predict(x, m, frame=None)
+            if world > 1:  # the only exchange of the sharded sweep: predicted frames -> rank 0 (NCCL gather)
+                dist.gather(video[:, -1:].contiguous(), gather_buf, dst=0)
+            return video
+
+        for i in range(warmup):
+            step(i, xs_dev[i % n_rot], ms_dev[i % n_rot])
+        launches_per_step = model.last_forward_launches + 1  # + unpatchify_scatter
+        barrier()
+        sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
+        if sampler:
+            sampler.start()
+        if with_profile:
+            _lib.profile_begin()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step(i, xs_dev[i % n_rot], ms_dev[i % n_rot])
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        prof = _lib.profile_end() if with_profile else []
+        clocks = sampler.stop() if sampler else None
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+
+        e2e = None
+        if with_e2e:
+            x_in = torch.empty_like(xs_dev[0])
+            m_in = torch.empty_like(ms_dev[0])
+            out_host = torch.empty(xs_host[0].shape, dtype=torch.float32).pin_memory()
+
+            def e2e_step(i):
+                x_in.copy_(xs_host[i % n_rot], non_blocking=True)
+                m_in.copy_(ms_host[i % n_rot], non_blocking=True)
+                video = step(i, x_in, m_in)
+                out_host.copy_(video, non_blocking=True)
+
+            for i in range(max(2, warmup // 2)):
+                e2e_step(i)
+            barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for i in range(steps):
+                e2e_step(i)
+            f1.record()
+            barrier()
+            t2 = torch.tensor([f0.elapsed_time(f1)], device=dev)
+            if world > 1:
+                dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t2.item())
+            e2e = {"value": world * B * steps / (e2e_ms * 1e-3), "unit": "frames/s",
+                   "h2d_bytes_per_step": xs_host[0].numel() * 4 + ms_host[0].numel(),
+                   "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": e2e_ms / steps}
+        del model, G
+        torch.cuda.empty_cache()
+        return dict(cfg=cfg_name, B=B, n_vis=n_vis, ms=ms, steps=steps, prof=prof, clocks=clocks, e2e=e2e,
+                    launches_per_step=launches_per_step,
+                    fps=world * B * steps / (ms * 1e-3), flops_frame=flops_per_frame(cfg_name, n_vis))
+
+    r = measure(args.workload, args.steps, args.warmup, with_e2e=True, with_profile=True, sample_clocks=True)
+
+    # ---- roofline of the dominant kernel class (device time measured live with CUDA events in the timed region)
+    kernels = []
+    for p in r["prof"]:
+        per = p["ms"] / max(1, p["launches"])
+        kernels.append({"name": p["name"], "launches": p["launches"], "ms_total": round(p["ms"], 3),
+                        "share": round(p["ms"] / max(1e-9, sum(q["ms"] for q in r["prof"])), 4),
+                        "tflops": round(p["flops"] / (p["ms"] * 1e-3) / 1e12, 1) if p["flops"] else None,
+                        "gbs": round(p["bytes"] / (p["ms"] * 1e-3) / 1e9, 1), "avg_ms": round(per, 4)})
+    roofline = None
+    if r["prof"]:
+        top = max(r["prof"], key=lambda p: p["ms"])
+        if top["flops"] > 0:
+            achieved = top["flops"] / (top["ms"] * 1e-3) / 1e12
+            roofline = {"kernel": top["name"], "bound": "tensor", "achieved": round(achieved, 1),
+                        "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                        "frac": round(achieved / peaks["tflops_sustained"], 4), "traffic": None,
+                        "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)"}
+        else:
+            achieved = top["bytes"] / (top["ms"] * 1e-3) / 1e9
+            roofline = {"kernel": top["name"], "bound": "hbm", "achieved": round(achieved, 1),
+                        "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4),
+                        "traffic": None, "peak_source": f"{peaks['source']} HBM copy"}
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                roofline["traffic"] = json.load(f).get(top["name"])
+
+    also = []
+    for w in [w for w in args.also.split(",") if w and w != args.workload]:
+        ra = measure(w, max(2, min(args.steps, 4)), 3, with_e2e=False, with_profile=False, sample_clocks=False)
+        also.append({"workload": w, "value": round(ra["fps"], 2), "unit": "frames/s",
+                     "ms_per_step": round(ra["ms"] / ra["steps"], 3),
+                     "tensor_frac_of_sustained_peak": round(ra["fps"] / world * ra["flops_frame"] / 1e12 /
+                                                            peaks["tflops_sustained"], 4),
+                     "gflop_per_frame": round(ra["flops_frame"] / 1e9, 1)})
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        cfg_name, B, n_clumps = WORKLOADS[args.workload]
+        times = cpu_oracle_frames_per_s(cfg_name, n_clumps, args.ref_sample, 4, threads)
+        timed = times[1:]
+        cpu_baseline = {"value": args.ref_sample * len(timed) / sum(timed), "unit": "frames/s", "cores": threads,
+                        "kind": "port", "sample": f"{args.ref_sample} frames x {len(timed)} passes (+1 warm-up) of the "
+                        f"same workload, CPU oracle (reference algorithm, fp32 eager torch, {threads} threads)"}
+
+    if rank == 0:
+        line = {
+            "metric": "counterfactual frames/sec", "value": round(r["fps"], 2), "unit": "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(r["ms"] / args.steps, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16 operands, f32 accumulate/residual/softmax", "data": "synthetic",
+            "config": {"workload": args.workload, "model": r["cfg"], "per_gpu_batch": r["B"],
+                       "global_batch": r["B"] * world, "visible_tokens": r["n_vis"],
+                       "parallelism": f"dp{world} replicas, samples sharded, NCCL gather of predicted frames",
+                       "l2": "3 rotating 77 MB input batches; > 1 GB of workspace is rewritten every step (>> 126 MB L2)",
+                       "gflop_per_frame": round(r["flops_frame"] / 1e9, 1)},
+            "tensor_frac_of_sustained_peak": round(r["fps"] / world * r["flops_frame"] / 1e12 /
+                                                   peaks["tflops_sustained"], 4),
+            "tensor_frac_of_burst_peak": round(r["fps"] / world * r["flops_frame"] / 1e12 / peaks["tflops_burst"], 4),
+            "e2e": r["e2e"], "gpu_launches": int(r["launches_per_step"] * args.steps),
+            "clocks": r["clocks"], "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels,
+            "also": also,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -18,6 +18,7 @@ EXPORTED_SYMBOLS = (
     "cwm_abi_version", "cwm_last_error", "cwm_device_check", "cwm_compact_mask", "cwm_patch_gather",
     "cwm_layernorm_f16", "cwm_gemm_f16", "cwm_attention_f16", "cwm_fill_mask_tokens",
     "cwm_unpatchify_scatter", "cwm_vmae_workspace_bytes", "cwm_vmae_forward", "cwm_last_forward_launches",
+    "cwm_profile_begin", "cwm_profile_end",
 )
 
 
@@ -53,6 +54,11 @@ class VmaeModel(Structure):
     )
 
 
+class ProfileEntry(Structure):
+    _fields_ = [("name", ctypes.c_char * 32), ("launches", c_int32), ("ms", ctypes.c_double),
+                ("flops", ctypes.c_double), ("bytes", ctypes.c_double)]
+
+
 _lib = None
 
 
@@ -78,6 +84,8 @@ def _declare(lib):
     lib.cwm_vmae_forward.argtypes = [POINTER(VmaeModel), c_void_p, i64x5, c_int, POINTER(c_float),
                                      POINTER(c_float), c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.cwm_last_forward_launches.restype = c_int
+    lib.cwm_profile_begin.restype = c_int
+    lib.cwm_profile_end.argtypes = [POINTER(ProfileEntry), c_int, POINTER(c_int)]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)
         if fn.restype is c_int and name not in ("cwm_abi_version", "cwm_last_forward_launches"):
@@ -102,6 +110,19 @@ def check(rc):
     if rc != CWM_OK:
         msg = load().cwm_last_error()
         raise CwmError(f"libcwm_b200 error {rc}: {msg.decode() if msg else '?'}")
+
+
+def profile_begin():
+    check(load().cwm_profile_begin())
+
+
+def profile_end():
+    """-> list of dict(name, launches, ms, flops, bytes), one per kernel class, in first-launch order."""
+    arr = (ProfileEntry * 32)()
+    n = c_int(0)
+    check(load().cwm_profile_end(arr, 32, ctypes.byref(n)))
+    return [dict(name=arr[i].name.decode(), launches=arr[i].launches, ms=arr[i].ms, flops=arr[i].flops,
+                 bytes=arr[i].bytes) for i in range(n.value)]
 
 
 def strides5(t):

@@ -1,7 +1,11 @@
 // api.cu -- library-level entry points, error string, TMA descriptor factory.
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
+#include <map>
 #include <mutex>
+#include <string>
+#include <vector>
 
 #include "common.cuh"
 
@@ -82,9 +86,76 @@ int num_sms() {
   return n;
 }
 
+// ---- profiling ---------------------------------------------------------------------------------------
+struct ProfRec {
+  const char* name;
+  double flops, bytes;
+  cudaEvent_t e0, e1;
+};
+static bool g_prof_on = false;
+static std::vector<ProfRec*> g_prof;
+
+ProfileScope::ProfileScope(cudaStream_t s, const char* name, double flops, double bytes) : stream(s) {
+  if (!g_prof_on) return;
+  ProfRec* r = new ProfRec{name, flops, bytes, nullptr, nullptr};
+  cudaEventCreate(&r->e0);
+  cudaEventCreate(&r->e1);
+  cudaEventRecord(r->e0, s);
+  rec = r;
+}
+ProfileScope::~ProfileScope() {
+  if (!rec) return;
+  ProfRec* r = static_cast<ProfRec*>(rec);
+  cudaEventRecord(r->e1, stream);
+  g_prof.push_back(r);
+}
+
 }  // namespace cwm
 
 extern "C" {
+
+int cwm_profile_begin(void) {
+  for (auto* r : cwm::g_prof) { cudaEventDestroy(r->e0); cudaEventDestroy(r->e1); delete r; }
+  cwm::g_prof.clear();
+  cwm::g_prof_on = true;
+  return CWM_OK;
+}
+
+int cwm_profile_end(cwm_profile_entry* out, int max_entries, int* n_entries) {
+  cwm::g_prof_on = false;
+  CWM_REQUIRE(out && n_entries && max_entries > 0, "cwm_profile_end: null pointer");
+  std::map<std::string, cwm_profile_entry> agg;
+  std::vector<std::string> order;
+  for (auto* r : cwm::g_prof) {
+    float ms = 0.f;
+    cudaError_t e = cudaEventSynchronize(r->e1);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, r->e0, r->e1);
+    if (e != cudaSuccess) return cwm::fail(CWM_ERR_CUDA, "cwm_profile_end: %s", cudaGetErrorString(e));
+    auto it = agg.find(r->name);
+    if (it == agg.end()) {
+      cwm_profile_entry en;
+      memset(&en, 0, sizeof(en));
+      strncpy(en.name, r->name, sizeof(en.name) - 1);
+      it = agg.emplace(r->name, en).first;
+      order.push_back(r->name);
+    }
+    it->second.launches += 1;
+    it->second.ms += ms;
+    it->second.flops += r->flops;
+    it->second.bytes += r->bytes;
+    cudaEventDestroy(r->e0);
+    cudaEventDestroy(r->e1);
+    delete r;
+  }
+  cwm::g_prof.clear();
+  int n = 0;
+  for (auto& k : order) {
+    if (n >= max_entries) break;
+    out[n++] = agg[k];
+  }
+  *n_entries = n;
+  return CWM_OK;
+}
 
 int cwm_abi_version(void) { return CWM_B200_ABI_VERSION; }
 

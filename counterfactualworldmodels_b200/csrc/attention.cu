@@ -334,6 +334,8 @@ extern "C" int cwm_attention_f16(const uint16_t* qkv, int B, int N, int H, int h
   CUtensorMap tm;
   int rc = make_tmap_2d_f16(&tm, qkv, static_cast<uint64_t>(B) * N, 3ull * C, 3ull * C, 128, 64);
   if (rc) return rc;
+  ProfileScope prof(static_cast<cudaStream_t>(stream), "attention_f16", 4.0 * B * H * static_cast<double>(N) * N * 64,
+                    static_cast<double>(B) * N * C * 2.0 * 4.0);
   dim3 grid((N + 255) / 256, H, B);
   attention_f16_kernel<<<grid, kAttnThreads, kAttnSmemBytes, static_cast<cudaStream_t>(stream)>>>(
       tm, N, H, reinterpret_cast<__half*>(out), kLog2e);

@@ -47,6 +47,14 @@ int make_tmap_2d_f16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t
                      uint32_t box_rows, uint32_t box_cols);
 int num_sms();
 
+// Optional per-launch CUDA-event timing (cwm_profile_begin/end).  No-op (one branch) when profiling is off.
+struct ProfileScope {
+  void* rec = nullptr;
+  cudaStream_t stream;
+  ProfileScope(cudaStream_t s, const char* name, double flops, double bytes);
+  ~ProfileScope();
+};
+
 // ---------------------------------------------------------------------------------------------
 // device-side PTX
 // ---------------------------------------------------------------------------------------------

@@ -67,9 +67,11 @@ compact_mask_kernel(const uint8_t* __restrict__ mask, int Ntot, int32_t* __restr
 
 extern "C" int cwm_compact_mask(const uint8_t* mask, int B, int Ntot, int32_t* perm, int32_t* inv_perm,
                                 int32_t* n_visible, cwm_stream_t stream) {
-  CWM_REQUIRE(mask && perm && n_visible, "cwm_compact_mask: null pointer");
   CWM_REQUIRE(B >= 0 && Ntot >= 0, "cwm_compact_mask: negative size (B=%d, Ntot=%d)", B, Ntot);
-  if (B == 0) return CWM_OK;
+  if (B == 0 || Ntot == 0) return CWM_OK;
+  CWM_REQUIRE(mask && perm && n_visible, "cwm_compact_mask: null pointer");
+  cwm::ProfileScope prof(static_cast<cudaStream_t>(stream), "compact_mask", 0.0,
+                         static_cast<double>(B) * Ntot * (1.0 + 4.0 + (inv_perm ? 4.0 : 0.0)));
   cwm::compact_mask_kernel<<<B, cwm::kCompactThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       mask, Ntot, perm, inv_perm, n_visible);
   CWM_LAUNCH_CHECK();

@@ -243,6 +243,8 @@ extern "C" int cwm_patch_gather(const float* x, const int64_t xs[5], int B, int 
              (p.st % 4 == 0) && (p.sh % 4 == 0);
   const int threads = 256;
   const long long blocks = (p.total + threads - 1) / threads;
+  ProfileScope prof(static_cast<cudaStream_t>(stream), "patch_gather", 0.0,
+                    static_cast<double>(B) * rows_per_sample * K * 6.0);
   patch_gather_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(p);
   CWM_LAUNCH_CHECK();
   return CWM_OK;
@@ -259,6 +261,7 @@ extern "C" int cwm_layernorm_f16(const float* x, int M, int C, const float* gamm
   const unsigned blocks = (M + rows_per_cta - 1) / rows_per_cta;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   __half* o = reinterpret_cast<__half*>(out);
+  ProfileScope prof(s, "layernorm_f16", 0.0, static_cast<double>(M) * C * 6.0);
 #define LN_CASE(V)                                                                                        \
   case V:                                                                                                 \
     layernorm_f16_kernel<V><<<blocks, threads, 0, s>>>(x, M, gamma, beta, eps, grp_rows, grp_stride,      \
@@ -283,6 +286,8 @@ extern "C" int cwm_fill_mask_tokens(const float* mask_token, const float* pos, c
   if (total == 0) return CWM_OK;
   const int threads = 256;
   const long long blocks = (total + threads - 1) / threads;
+  ProfileScope prof(static_cast<cudaStream_t>(stream), "fill_mask_tokens", 0.0,
+                    static_cast<double>(B) * (Ntot - Nvis) * C * 4.0);
   fill_mask_tokens_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const float4*>(mask_token), reinterpret_cast<const float4*>(pos), perm, Ntot, Nvis, C / 4,
       total, reinterpret_cast<float4*>(x_full));
@@ -316,6 +321,8 @@ extern "C" int cwm_unpatchify_scatter(const float* y, const float* x_raw, const 
   if (p.total == 0) return CWM_OK;
   const int threads = 256;
   const long long blocks = (p.total + threads - 1) / threads;
+  ProfileScope prof(static_cast<cudaStream_t>(stream), "unpatchify_scatter", 0.0,
+                    static_cast<double>(p.total) * 4 * 8.0);
   unpatchify_scatter_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(p);
   CWM_LAUNCH_CHECK();
   return CWM_OK;

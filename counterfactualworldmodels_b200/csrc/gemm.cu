@@ -329,6 +329,10 @@ extern "C" int cwm_gemm_f16(const uint16_t* A, const uint16_t* W, int M, int N, 
   rc = make_tmap_2d_f16(&tw, W, N, K, K, bn, BK);
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  static const char* kNames[4] = {"gemm_f16_out", "gemm_gelu_f16_out", "gemm_residual_f32", "gemm_f32_out"};
+  const double out_bytes = static_cast<double>(M) * N * (f16_out ? 2.0 : (e->mode == CWM_EPI_RES_F32 ? 8.0 : 4.0));
+  ProfileScope prof(s, kNames[e->mode], 2.0 * M * N * K,
+                    (static_cast<double>(M) * K + static_cast<double>(N) * K) * 2.0 + out_bytes);
   switch (bn) {
     case 64: return launch_gemm<64>(ta, tw, M, N, K, ep, s);
     case 128: return launch_gemm<128>(ta, tw, M, N, K, ep, s);

@@ -185,6 +185,20 @@ int cwm_vmae_forward(const cwm_vmae_model* model, const float* x, const int64_t 
 /* Number of kernel launches the last cwm_vmae_forward on this thread enqueued (for bench accounting). */
 int cwm_last_forward_launches(void);
 
+/* ---- per-kernel timing (bench.py's roofline numbers) -------------------------------------------------
+ * Between cwm_profile_begin() and cwm_profile_end() every launch made through this library is bracketed by two
+ * CUDA events on its own stream.  cwm_profile_end() synchronises those events and aggregates per kernel class:
+ * number of launches, total device milliseconds, algorithmic FLOPs and algorithmic bytes. */
+typedef struct cwm_profile_entry {
+  char name[32];
+  int32_t launches;
+  double ms;
+  double flops;
+  double bytes;
+} cwm_profile_entry;
+int cwm_profile_begin(void);
+int cwm_profile_end(cwm_profile_entry* out, int max_entries, int* n_entries);
+
 #ifdef __cplusplus
 }
 #endif
