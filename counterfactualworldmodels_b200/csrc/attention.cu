@@ -332,7 +332,7 @@ extern "C" int cwm_attention_f16(const uint16_t* qkv, int B, int N, int H, int h
   }
   const int C = H * 64;
   CUtensorMap tm;
-  int rc = make_tmap_2d_f16(&tm, qkv, static_cast<uint64_t>(B) * N, 3ull * C, 3ull * C, 128, 64);
+  int rc = make_tmap_2d(&tm, qkv, CWM_TMAP_F16, static_cast<uint64_t>(B) * N, 3ull * C, 3ull * C, 128, 64);
   if (rc) return rc;
   ProfileScope prof(static_cast<cudaStream_t>(stream), "attention_f16", 4.0 * B * H * static_cast<double>(N) * N * 64,
                     static_cast<double>(B) * N * C * 2.0 * 4.0);

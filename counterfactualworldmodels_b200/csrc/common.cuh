@@ -41,10 +41,11 @@ void reset_launches();
   } while (0)
 
 // TMA descriptor creation (driver entry point resolved at run time; no link-time libcuda dependency)
-// 2-D row-major f16 tensor [rows, cols] with leading dimension ld (elements), box [box_rows, box_cols],
-// 128-byte swizzle (box_cols * 2 bytes must be <= 128).
-int make_tmap_2d_f16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
-                     uint32_t box_rows, uint32_t box_cols);
+// 2-D row-major f16/f32 tensor [rows, cols] with leading dimension ld (elements), box [box_rows, box_cols],
+// 128-byte swizzle (box_cols * element size must be <= 128).
+enum { CWM_TMAP_F16 = 0, CWM_TMAP_F32 = 1 };
+int make_tmap_2d(CUtensorMap* map, const void* base, int dtype, uint64_t rows, uint64_t cols, uint64_t ld,
+                 uint32_t box_rows, uint32_t box_cols);
 int num_sms();
 
 // Optional per-launch CUDA-event timing (cwm_profile_begin/end).  No-op (one branch) when profiling is off.

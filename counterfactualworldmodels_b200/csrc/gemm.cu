@@ -6,14 +6,17 @@
 //               fp32 accumulators in tensor memory, two accumulator stages so the epilogue of tile i overlaps
 //               the main loop of tile i+1
 //   warp 2      TMEM allocator
-//   warps 4-11  epilogue: tcgen05.ld (32 lanes x 32/64 columns) -> registers -> per-warp padded smem transpose
-//               -> fully coalesced 128-byte global stores (and residual loads).  Two warps per TMEM lane
-//               quadrant split the column chunks.
-// Fused epilogues (cwm_epilogue): +bias, q-scale, GELU(erf), +residual (optionally row-gathered = positional
-// embedding of visible tokens), output row remap (writes x_vis straight into the decoder sequence).
+//   warps 4-11  epilogue, two warps per TMEM lane quadrant (they split the column chunks).  One thread owns one
+//               output row of a 32-row x 128-byte chunk:
+//                 tcgen05.ld -> registers -> (+bias, q-scale | GELU | +residual) -> 128B-swizzled smem -> TMA store.
+//               The fp32 residual chunk is TMA-loaded into the same smem buffer one chunk ahead (double buffered),
+//               so neither the residual read nor the output write occupies the LSU or stalls on global latency.
+//   A generic (slower) epilogue handles the two row-remapped / row-gathered uses (patch-embed + pos[perm], and
+//   encoder_to_decoder written into the decoder sequence): coalesced direct global accesses through a padded smem
+//   transpose.
 //
-// Roofline: tensor bound for K >= 512; the fp32-residual epilogues of the narrow decoder (K = 384/512) are HBM/L2
-// bound (8 bytes of residual traffic per output element) -- see DESIGN.md.
+// Roofline: tensor bound for K >= 768; the fp32-residual GEMMs with K <= 512 are HBM bound (8 bytes of residual
+// traffic per output element) -- see DESIGN.md.
 #include "common.cuh"
 
 namespace cwm {
@@ -22,17 +25,22 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 f16 = 128 bytes = one swizzle row
 constexpr int kGemmThreads = 384;
 constexpr int kEpiWarps = 8;
-constexpr int kStagingWords = 32 * 33;
+constexpr int kChunkBytes = 32 * 128;  // one epilogue chunk: 32 rows x 128 bytes
 
-template <int BN>
+template <int BN, bool kRes>
 struct GemmCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 192 ? 4 : 6);
+  // epilogue smem: kRes (fp32 out, optional residual): 2 buffers / warp, else 1 buffer / warp
+  static constexpr int kEpiBytes = kEpiWarps * kChunkBytes * (kRes ? 2 : 1);
+  static constexpr int kBiasBytes = kEpiWarps * 64 * 4;
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBudget = 232448 - kEpiBytes - kBiasBytes - 512;
+  static constexpr int kMaxStages = kBudget / kStageBytes;
+  static constexpr int kStages = kMaxStages > 6 ? 6 : kMaxStages;
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
-  static constexpr int kSmemBytes =
-      1024 + kStages * kStageBytes + kEpiWarps * kStagingWords * 4 + 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBiasBytes + 512;
+  static_assert(kStages >= 3, "pipeline too shallow");
 };
 
 struct EpiDev {
@@ -54,22 +62,57 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 
-template <int BN>
+// ---- explicit shared-space accesses (the smem pointers are carved from a uintptr_t, keep them out of the
+//      generic address space) ----
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void lds128(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_s(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+template <int BN, bool kRes>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w, int M, int N,
+gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w,
+                const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_res, int M, int N,
                 int K, EpiDev ep) {
-  using Cfg = GemmCfg<BN>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  using Cfg = GemmCfg<BN, kRes>;
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
-  uint32_t* staging = reinterpret_cast<uint32_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + kEpiWarps * kStagingWords * 4);
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + Cfg::kStages;
-  uint64_t* tfull_bar = bars + 2 * Cfg::kStages;
-  uint64_t* tempty_bar = bars + 2 * Cfg::kStages + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 4);
+  uint8_t* smem_epi = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint8_t* smem_bias = smem_epi + Cfg::kEpiBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_bias + Cfg::kBiasBytes);
+  uint64_t* full_bar = bars;                        // kStages
+  uint64_t* empty_bar = bars + Cfg::kStages;        // kStages
+  uint64_t* tfull_bar = bars + 2 * Cfg::kStages;    // 2
+  uint64_t* tempty_bar = tfull_bar + 2;             // 2
+  uint64_t* res_bar = tempty_bar + 2;               // kEpiWarps * 2 (residual chunk landed)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2 * kEpiWarps);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -79,9 +122,12 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (K + BK - 1) / BK;
 
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();  // swizzle-128B needs 1024-byte alignment
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_w);
+    tma_prefetch_desc(&tma_out);
+    if (kRes) tma_prefetch_desc(&tma_res);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
@@ -92,6 +138,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], kEpiWarps);
     }
+    for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -161,95 +208,216 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int ew = warp - 4;       // 0..7
-    const int quad = ew & 3;       // TMEM lane quadrant == warp % 4
-    const int half = ew >> 2;      // which column chunks this warp takes
-    uint32_t* stg = staging + ew * kStagingWords;
-    const bool f16_out = (ep.mode == CWM_EPI_F16 || ep.mode == CWM_EPI_GELU_F16);
+    const int ew = warp - 4;   // 0..7
+    const int quad = ew & 3;   // TMEM lane quadrant == warp % 4
+    const int half = ew >> 2;  // which column chunks this warp takes
+    const uint32_t buf0 = smem_u32(smem_epi) + ew * kChunkBytes * (kRes ? 2 : 1);
+    const uint32_t bias_s = smem_u32(smem_bias) + ew * 256;
+    const uint32_t row_s = lane * 128;      // this thread's row inside a chunk buffer
+    const uint32_t sw = lane & 7;           // 128B swizzle: 16-byte unit index ^= row % 8
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / tiles_n;
-      const int n_blk = tile - m_blk * tiles_n;
-      mbar_wait(&tfull_bar[as], aphase);
-      tc_fence_after();
-      const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
-      const int row0 = m_blk * BM + quad * 32;
-      if (f16_out) {
-        // 64-column chunks; math in row-owner layout, packed to half2, transposed through smem
-        constexpr int kChunks = BN / 64;
+
+    if constexpr (!kRes) {
+      // ---------------- f16 output: 64-column chunks, TMA store ----------------
+      constexpr int kChunks = BN / 64;
+      const bool gelu = (ep.mode == CWM_EPI_GELU_F16);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / tiles_n;
+        const int n_blk = tile - m_blk * tiles_n;
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
+        const int row0 = m_blk * BM + quad * 32;
         for (int c = half; c < kChunks; c += 2) {
           const int n0 = n_blk * BN + c * 64;
-          uint32_t acc0[32], acc1[32];
-          tmem_ld_x32(tmem_acc + c * 64, acc0);
-          tmem_ld_x32(tmem_acc + c * 64 + 32, acc1);
+          // bias of the 64 columns -> per-warp smem (broadcast reads below)
+          float b_lo = 0.f, b_hi = 0.f;
+          if (ep.bias != nullptr) {
+            if (n0 + lane < N) b_lo = __ldg(ep.bias + n0 + lane);
+            if (n0 + 32 + lane < N) b_hi = __ldg(ep.bias + n0 + 32 + lane);
+          }
+          uint32_t acc[64];
+          tmem_ld_x32(tmem_acc + c * 64, acc);
+          tmem_ld_x32(tmem_acc + c * 64 + 32, acc + 32);
+          __syncwarp();  // previous chunk's broadcast reads of bias_s are done
+          sts32(bias_s + lane * 4, __float_as_uint(b_lo));
+          sts32(bias_s + 128 + lane * 4, __float_as_uint(b_hi));
           tmem_ld_wait();
+          const bool last_chunk = (c + 2 >= kChunks);
+          if (last_chunk) {  // all TMEM reads of this tile by this warp are complete -> release the stage early
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+          }
+          __syncwarp();
+          if (lane == 0) bulk_wait_read0();  // the previous TMA store has finished reading the buffer
+          __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float v[4];
-            v[0] = __uint_as_float(acc0[j]);
-            v[1] = __uint_as_float(acc0[j + 1]);
-            v[2] = __uint_as_float(acc1[j]);
-            v[3] = __uint_as_float(acc1[j + 1]);
+          for (int u = 0; u < 8; ++u) {  // 16-byte unit u = columns 8u .. 8u+7
+            uint32_t bb[8];
+            lds128(bias_s + u * 32, bb[0], bb[1], bb[2], bb[3]);
+            lds128(bias_s + u * 32 + 16, bb[4], bb[5], bb[6], bb[7]);
+            float v[8];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int n = n0 + (q >> 1) * 32 + j + (q & 1);
-              if (ep.bias != nullptr && n < N) v[q] += __ldg(ep.bias + n);
-              if (ep.mode == CWM_EPI_GELU_F16) {
+            for (int q = 0; q < 8; ++q) {
+              v[q] = __uint_as_float(acc[u * 8 + q]) + __uint_as_float(bb[q]);
+              if (gelu) {
                 v[q] = gelu_erf(v[q]);
-              } else if (n < ep.scale_cols) {
+              } else if (n0 + u * 8 + q < ep.scale_cols) {
                 v[q] *= ep.scale;
               }
             }
-            stg[lane * 33 + (j >> 1)] = pack_half2(v[0], v[1]);
-            stg[lane * 33 + 16 + (j >> 1)] = pack_half2(v[2], v[3]);
+            sts128(buf0 + row_s + ((u ^ sw) << 4), pack_half2(v[0], v[1]), pack_half2(v[2], v[3]),
+                   pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
           }
+          fence_proxy_async_smem();
           __syncwarp();
-          const int n = n0 + 2 * lane;
-          if (n < N) {
-            __half* outp = reinterpret_cast<__half*>(ep.out);
-#pragma unroll 4
-            for (int r = 0; r < 32; ++r) {
-              const int m = row0 + r;
-              if (m >= M) break;
-              long long orow = m;
-              if (ep.grp_rows > 0) orow = static_cast<long long>(m / ep.grp_rows) * ep.grp_out_stride + m % ep.grp_rows;
-              *reinterpret_cast<uint32_t*>(outp + orow * ep.ldo + n) = stg[r * 33 + lane];
-            }
+          if (lane == 0) {
+            tma_store_2d(&tma_out, buf0, n0, row0);
+            bulk_commit();
           }
-          __syncwarp();
         }
-      } else {
-        // 32-column chunks; raw accumulators transposed through smem, math in column-owner layout
-        constexpr int kChunks = BN / 32;
+        if (half >= kChunks) {  // this warp had no chunk in this tile (BN == 64): still release the stage
+          tc_fence_before();
+          if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        }
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
+      }
+      if (lane == 0) bulk_wait_all();
+    } else if (ep.grp_rows <= 0) {
+      // ---------------- fp32 output (+ residual): 32-column chunks, TMA load of the residual one chunk ahead,
+      //                  TMA store ----------------
+      constexpr int kChunks = BN / 32;
+      const bool has_res = (ep.mode == CWM_EPI_RES_F32);
+      uint64_t* my_res_bar = res_bar + ew * 2;
+      // flat list of this warp's work items: (tile, chunk) with chunk = half, half+2, ...
+      const int my_chunks = (kChunks - half + 1) / 2;
+      const int my_tiles = (num_tiles > static_cast<int>(blockIdx.x))
+                               ? (num_tiles - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1
+                               : 0;
+      const int n_items = my_tiles * my_chunks;
+      auto item_coords = [&](int it, int& row0, int& n0, int& c, bool& first, bool& last) {
+        const int ti = it / my_chunks;
+        const int ci = it - ti * my_chunks;
+        const int tile = blockIdx.x + ti * gridDim.x;
+        const int m_blk = tile / tiles_n;
+        const int n_blk = tile - m_blk * tiles_n;
+        c = half + 2 * ci;
+        row0 = m_blk * BM + quad * 32;
+        n0 = n_blk * BN + c * 32;
+        first = (ci == 0);
+        last = (ci == my_chunks - 1);
+      };
+      if (has_res && n_items > 0 && lane == 0) {  // prefetch the residual chunk of the first item
+        int row0, n0, c;
+        bool f, l;
+        item_coords(0, row0, n0, c, f, l);
+        mbar_arrive_expect_tx(&my_res_bar[0], kChunkBytes);
+        tma_load_2d_s(buf0, &tma_res, smem_u32(&my_res_bar[0]), n0, row0);
+      }
+      for (int it = 0; it < n_items; ++it) {
+        int row0, n0, c;
+        bool first, last;
+        item_coords(it, row0, n0, c, first, last);
+        const uint32_t buf = buf0 + (it & 1) * kChunkBytes;
+        const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
+        float b_lo = 0.f;
+        if (ep.bias != nullptr && n0 + lane < N) b_lo = __ldg(ep.bias + n0 + lane);
+        if (first) {
+          mbar_wait(&tfull_bar[as], aphase);
+          tc_fence_after();
+        }
+        uint32_t acc[32];
+        tmem_ld_x32(tmem_acc + c * 32, acc);
+        __syncwarp();
+        sts32(bias_s + lane * 4, __float_as_uint(b_lo));
+        tmem_ld_wait();
+        if (last) {
+          tc_fence_before();
+          if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        }
+        __syncwarp();
+        if (lane == 0) {
+          // buffer (it+1)&1 was last used by item it-1: its store must have finished reading smem
+          bulk_wait_read0();
+          if (has_res && it + 1 < n_items) {
+            int r1, n1, c1;
+            bool f1, l1;
+            item_coords(it + 1, r1, n1, c1, f1, l1);
+            uint64_t* nb = &my_res_bar[(it + 1) & 1];
+            mbar_arrive_expect_tx(nb, kChunkBytes);
+            tma_load_2d_s(buf0 + ((it + 1) & 1) * kChunkBytes, &tma_res, smem_u32(nb), n1, r1);
+          }
+        }
+        if (has_res) mbar_wait(&my_res_bar[it & 1], (it >> 1) & 1);
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {  // 16-byte unit u = columns 4u .. 4u+3
+          uint32_t bb[4];
+          lds128(bias_s + u * 16, bb[0], bb[1], bb[2], bb[3]);
+          float v[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) v[q] = __uint_as_float(acc[u * 4 + q]) + __uint_as_float(bb[q]);
+          const uint32_t addr = buf + row_s + ((u ^ sw) << 4);
+          if (has_res) {
+            uint32_t r[4];
+            lds128(addr, r[0], r[1], r[2], r[3]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[q] += __uint_as_float(r[q]);
+          }
+          sts128(addr, __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tma_out, buf, n0, row0);
+          bulk_commit();
+        }
+        if (last) {
+          if (++as == 2) {
+            as = 0;
+            aphase ^= 1;
+          }
+        }
+      }
+      if (lane == 0) bulk_wait_all();
+    } else {
+      // ---------------- generic fp32 epilogue with row remap / gathered residual (two small GEMMs per forward):
+      //                  padded smem transpose, coalesced direct global accesses ----------------
+      constexpr int kChunks = BN / 32;
+      const uint32_t stg = buf0;  // 32 x 33 words = 4224 bytes <= 2 * kChunkBytes
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / tiles_n;
+        const int n_blk = tile - m_blk * tiles_n;
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
+        const int row0 = m_blk * BM + quad * 32;
         for (int c = half; c < kChunks; c += 2) {
           const int n0 = n_blk * BN + c * 32;
           uint32_t acc[32];
           tmem_ld_x32(tmem_acc + c * 32, acc);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = acc[j];
+          for (int j = 0; j < 32; ++j) sts32(stg + (lane * 33 + j) * 4, acc[j]);
           __syncwarp();
           const int n = n0 + lane;
           if (n < N) {
             const float bias = ep.bias != nullptr ? __ldg(ep.bias + n) : 0.f;
             float* outp = reinterpret_cast<float*>(ep.out);
-#pragma unroll 4
             for (int r = 0; r < 32; ++r) {
               const int m = row0 + r;
               if (m >= M) break;
-              long long orow = m;
-              int g = 0, j = m;
-              if (ep.grp_rows > 0) {
-                g = m / ep.grp_rows;
-                j = m - g * ep.grp_rows;
-                orow = static_cast<long long>(g) * ep.grp_out_stride + j;
-              }
-              float v = __uint_as_float(stg[r * 33 + lane]) + bias;
+              const int g = m / ep.grp_rows;
+              const int j = m - g * ep.grp_rows;
+              const long long orow = static_cast<long long>(g) * ep.grp_out_stride + j;
+              float v = __uint_as_float(lds32(stg + (r * 33 + lane) * 4)) + bias;
               if (ep.mode == CWM_EPI_RES_F32) {
                 long long rrow = orow;
-                if (ep.res_gather != nullptr)
-                  rrow = ep.res_gather[static_cast<long long>(g) * ep.gather_stride + j];
+                if (ep.res_gather != nullptr) rrow = ep.res_gather[static_cast<long long>(g) * ep.gather_stride + j];
                 v += ep.res[rrow * ep.ldr + n];
               }
               outp[orow * ep.ldo + n] = v;
@@ -257,13 +425,12 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
           }
           __syncwarp();
         }
-      }
-      // all tcgen05.ld of this warp have completed (tmem_ld_wait) -> release the accumulator stage
-      tc_fence_before();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
-      if (++as == 2) {
-        as = 0;
-        aphase ^= 1;
+        tc_fence_before();
+        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
       }
     }
   }
@@ -276,19 +443,19 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   }
 }
 
-template <int BN>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, int M, int N, int K, const EpiDev& ep,
-                       cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+template <int BN, bool kRes>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const CUtensorMap& tr, int M,
+                       int N, int K, const EpiDev& ep, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, kRes>;
   static bool attr_set = false;
   if (!attr_set) {
-    CWM_CUDA_CHECK(cudaFuncSetAttribute(gemm_f16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CWM_CUDA_CHECK(cudaFuncSetAttribute(gemm_f16_kernel<BN, kRes>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::kSmemBytes));
     attr_set = true;
   }
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_f16_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tw, M, N, K, ep);
+  gemm_f16_kernel<BN, kRes><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tw, to, tr, M, N, K, ep);
   CWM_LAUNCH_CHECK();
   return CWM_OK;
 }
@@ -315,28 +482,58 @@ extern "C" int cwm_gemm_f16(const uint16_t* A, const uint16_t* W, int M, int N, 
   CWM_REQUIRE(e->mode != CWM_EPI_RES_F32 || e->res != nullptr, "cwm_gemm_f16: residual epilogue without residual");
   CWM_REQUIRE(e->res_gather == nullptr || e->grp_rows > 0, "cwm_gemm_f16: res_gather needs grp_rows > 0");
   const bool f16_out = (e->mode == CWM_EPI_F16 || e->mode == CWM_EPI_GELU_F16);
-  CWM_REQUIRE(!f16_out || (N % 2 == 0 && e->ldo % 2 == 0 && reinterpret_cast<uintptr_t>(e->out) % 4 == 0),
-              "cwm_gemm_f16: f16 output needs even N/ldo and 4-byte aligned out");
+  CWM_REQUIRE(!(f16_out && e->grp_rows > 0), "cwm_gemm_f16: row remap is only available for fp32 outputs");
+  const int elt = f16_out ? 2 : 4;
+  CWM_REQUIRE(reinterpret_cast<uintptr_t>(e->out) % 16 == 0 && (static_cast<long long>(e->ldo) * elt) % 16 == 0 &&
+                  e->ldo >= N,
+              "cwm_gemm_f16: out must be 16-byte aligned with ldo*elt %% 16 == 0 and ldo >= N (ldo=%d)", e->ldo);
   if (M == 0) return CWM_OK;
   EpiDev ep;
   ep.mode = e->mode; ep.bias = e->bias; ep.scale = e->scale; ep.scale_cols = (e->mode == CWM_EPI_F16) ? e->scale_cols : 0;
   ep.res = e->res; ep.ldr = e->ldr; ep.res_gather = e->res_gather; ep.gather_stride = e->gather_stride;
   ep.grp_rows = e->grp_rows; ep.grp_out_stride = e->grp_out_stride; ep.out = e->out; ep.ldo = e->ldo;
   const int bn = pick_bn(N);
-  CUtensorMap ta, tw;
-  int rc = make_tmap_2d_f16(&ta, A, M, K, K, BM, BK);
+  CUtensorMap ta, tw, to, tr;
+  int rc = make_tmap_2d(&ta, A, CWM_TMAP_F16, M, K, K, BM, BK);
   if (rc) return rc;
-  rc = make_tmap_2d_f16(&tw, W, N, K, K, bn, BK);
+  rc = make_tmap_2d(&tw, W, CWM_TMAP_F16, N, K, K, bn, BK);
+  if (rc) return rc;
+  const bool remap = e->grp_rows > 0;
+  if (f16_out) {
+    rc = make_tmap_2d(&to, e->out, CWM_TMAP_F16, M, N, e->ldo, 32, 64);
+    tr = to;
+  } else if (!remap) {
+    rc = make_tmap_2d(&to, e->out, CWM_TMAP_F32, M, N, e->ldo, 32, 32);
+    if (rc) return rc;
+    if (e->mode == CWM_EPI_RES_F32) {
+      CWM_REQUIRE(reinterpret_cast<uintptr_t>(e->res) % 16 == 0 && (static_cast<long long>(e->ldr) * 4) % 16 == 0,
+                  "cwm_gemm_f16: residual must be 16-byte aligned");
+      rc = make_tmap_2d(&tr, e->res, CWM_TMAP_F32, M, N, e->ldr, 32, 32);
+    } else {
+      tr = to;
+    }
+  } else {
+    to = ta;  // unused by the generic epilogue
+    tr = ta;
+  }
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   static const char* kNames[4] = {"gemm_f16_out", "gemm_gelu_f16_out", "gemm_residual_f32", "gemm_f32_out"};
   const double out_bytes = static_cast<double>(M) * N * (f16_out ? 2.0 : (e->mode == CWM_EPI_RES_F32 ? 8.0 : 4.0));
   ProfileScope prof(s, kNames[e->mode], 2.0 * M * N * K,
                     (static_cast<double>(M) * K + static_cast<double>(N) * K) * 2.0 + out_bytes);
+  if (f16_out) {
+    switch (bn) {
+      case 64: return launch_gemm<64, false>(ta, tw, to, tr, M, N, K, ep, s);
+      case 128: return launch_gemm<128, false>(ta, tw, to, tr, M, N, K, ep, s);
+      case 192: return launch_gemm<192, false>(ta, tw, to, tr, M, N, K, ep, s);
+      default: return launch_gemm<256, false>(ta, tw, to, tr, M, N, K, ep, s);
+    }
+  }
   switch (bn) {
-    case 64: return launch_gemm<64>(ta, tw, M, N, K, ep, s);
-    case 128: return launch_gemm<128>(ta, tw, M, N, K, ep, s);
-    case 192: return launch_gemm<192>(ta, tw, M, N, K, ep, s);
-    default: return launch_gemm<256>(ta, tw, M, N, K, ep, s);
+    case 64: return launch_gemm<64, true>(ta, tw, to, tr, M, N, K, ep, s);
+    case 128: return launch_gemm<128, true>(ta, tw, to, tr, M, N, K, ep, s);
+    case 192: return launch_gemm<192, true>(ta, tw, to, tr, M, N, K, ep, s);
+    default: return launch_gemm<256, true>(ta, tw, to, tr, M, N, K, ep, s);
   }
 }
