@@ -10,11 +10,14 @@
 //   warps 4-7    softmax warpgroup for query tile 0, warps 8-11 for tile 1: one thread per query row (no
 //                shuffles): tcgen05.ld S row -> running max with lazy rescale (O is only rescaled when the max
 //                grows by more than 2^8) -> exp2 -> fp32 row sum -> f16 P written back over S in tensor memory
-// Tensor memory map (512 columns): S0 [0,128) (P0 aliases [0,64)), S1 [128,256) (P1 aliases [128,192)),
-//                                  O0 [256,320), O1 [320,384).
-// Ordering facts relied on: tcgen05.mma from one thread execute in issue order (P_t(j) is consumed by PV_t(j)
-// before QK_t(j+1) overwrites S_t), and a tcgen05.commit arrives only after ALL earlier MMAs completed (so when
-// s_full[t] fires for tile j+1, PV_t(j) has finished and O_t may be rescaled by the softmax warpgroup).
+// Tensor memory map (512 columns): three 128-column score buffers B0..B2 used round-robin -- the scores of
+// (query tile t, kv tile j) live in B[(2j + t) % 3] and P (f16 pairs) overwrites their first 64 columns -- so that
+// S_0(j+1) is computed while the softmax of S_0(j) is still running; O0 [384,448), O1 [448,512).
+// Ordering facts relied on: tcgen05.mma from one thread execute in issue order (a buffer's previous P has been
+// consumed by its PV before the next QK overwrites it), and a tcgen05.commit arrives only after ALL earlier MMAs
+// completed (pv_done[t] after PV_t(j) => O_t may be rescaled / read by the softmax warpgroup).
+// The last kv tile is issued with N = round_up(valid columns, 32), so ragged sequence lengths (788, 3140 ...)
+// do not pay for a full 128-column tile.
 #include "common.cuh"
 
 namespace cwm {
@@ -30,6 +33,31 @@ __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// packed dual-fp32 math (Blackwell FFMA2 / FADD2): one issue slot for two lanes of work
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b, float c) {
+  asm("{\n\t"
+      ".reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\t"
+      "mov.b64 rb, {%4, %4};\n\t"
+      "mov.b64 rc, {%5, %5};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t"
+      "}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b), "f"(c));
+}
+__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t"
+      ".reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\t"
+      "mov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t"
+      "}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
 
 template <int REGS>
@@ -57,8 +85,8 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tma_qkv, int N, int H, 
   uint64_t* v_empty = v_full + kKVStages;
   uint64_t* s_full = v_empty + kKVStages;     // 2
   uint64_t* p_full = s_full + 2;              // 2
-  uint64_t* o_full = p_full + 2;              // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  uint64_t* pv_done = p_full + 2;             // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -69,6 +97,7 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tma_qkv, int N, int H, 
   const bool t1_valid = (q0 + 128) < N;          // does query tile 1 contain any valid row?
   const int n_kv = (N + 127) / 128;
   const int row_base = b * N;                    // row of token 0 of this sample in the [B*N, 3C] matrix
+  const int cols_last = ((N - (n_kv - 1) * 128) + 31) & ~31;  // MMA columns of the last kv tile (32..128)
 
   if (warp == 0 && lane == 0) tma_prefetch_desc(&tma_qkv);
   if (warp == 1 && lane == 0) {
@@ -82,8 +111,8 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tma_qkv, int N, int H, 
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_full[t], 1);
       mbar_init(&p_full[t], 4);  // one elected lane per softmax warp
+      mbar_init(&pv_done[t], 1);
     }
-    mbar_init(o_full, 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -96,7 +125,7 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tma_qkv, int N, int H, 
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
-    reg_dec<40>();
+    reg_dec<56>();
     if (warp == 0) {
       // ===================== TMA producer =====================
       if (lane == 0) {
@@ -121,36 +150,38 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tma_qkv, int N, int H, 
     } else if (warp == 1) {
       // ===================== MMA issuer =====================
       if (lane == 0) {
-        constexpr uint32_t idesc_qk = umma_idesc_f16(128, 128, 0, 0);
         constexpr uint32_t idesc_pv = umma_idesc_f16(128, 64, 0, 1);  // B = V is MN-major
         const uint32_t q_addr0 = smem_u32(smem_q);
         const uint32_t q_addr1 = smem_u32(smem_q + kTileBytes);
-        const uint32_t tm_s0 = tmem_base + 0, tm_s1 = tmem_base + 128;
-        const uint32_t tm_o0 = tmem_base + 256, tm_o1 = tmem_base + 320;
+        const uint32_t tm_o0 = tmem_base + 384, tm_o1 = tmem_base + 448;
 
-        auto issue_qk = [&](uint32_t q_addr, uint32_t k_addr, uint32_t tm_s) {
+        auto issue_qk = [&](uint32_t q_addr, uint32_t k_addr, uint32_t tm_s, int ncols) {
+          const uint32_t idesc_qk = umma_idesc_f16(128, ncols, 0, 0);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_ss(tm_s, umma_desc_kmajor_sw128(q_addr + k * 32), umma_desc_kmajor_sw128(k_addr + k * 32),
                     idesc_qk, k != 0 ? 1u : 0u);
         };
-        auto issue_pv = [&](uint32_t tm_p, uint32_t v_addr, uint32_t tm_o, bool accumulate) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k)  // 16 kv rows per MMA: 8 TMEM columns of packed f16 pairs, 2048 B of V
+        auto issue_pv = [&](uint32_t tm_p, uint32_t v_addr, uint32_t tm_o, bool accumulate, int ksteps) {
+          for (int k = 0; k < ksteps; ++k)  // 16 kv rows per MMA: 8 TMEM columns of packed f16 pairs, 2048 B of V
             umma_ts(tm_o, tm_p + k * 8, umma_desc_mnmajor_sw128(v_addr + k * 2048, 0), idesc_pv,
                     (accumulate || k != 0) ? 1u : 0u);
         };
+        auto sbuf = [&](int j, int t) { return tmem_base + static_cast<uint32_t>(((2 * j + t) % 3) * 128); };
 
         mbar_wait(q_full, 0);
         mbar_wait(&k_full[0], 0);
         tc_fence_after();
-        issue_qk(q_addr0, smem_u32(smem_k), tm_s0);
-        umma_commit(&s_full[0]);
-        if (t1_valid) {
-          issue_qk(q_addr1, smem_u32(smem_k), tm_s1);
-          umma_commit(&s_full[1]);
+        {
+          const int nc0 = (n_kv == 1) ? cols_last : 128;
+          issue_qk(q_addr0, smem_u32(smem_k), sbuf(0, 0), nc0);
+          umma_commit(&s_full[0]);
+          if (t1_valid) {
+            issue_qk(q_addr1, smem_u32(smem_k), sbuf(0, 1), nc0);
+            umma_commit(&s_full[1]);
+          }
+          umma_commit(&k_empty[0]);
         }
-        umma_commit(&k_empty[0]);
 
         int stage = 0;       // stage of K_j / V_j
         uint32_t phase = 0;
@@ -162,35 +193,39 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tma_qkv, int N, int H, 
             nphase ^= 1;
           }
           const bool has_next = (j + 1) < n_kv;
+          const int nc_next = (j + 2 == n_kv) ? cols_last : 128;
+          const int ksteps = ((j + 1 == n_kv) ? cols_last : 128) >> 4;
           const uint32_t v_addr = smem_u32(smem_v + stage * kTileBytes);
           const uint32_t kn_addr = smem_u32(smem_k + nstage * kTileBytes);
-          // ---- query tile 0
-          mbar_wait(&p_full[0], j & 1);
-          mbar_wait(&v_full[stage], phase);
-          tc_fence_after();
-          issue_pv(tm_s0, v_addr, tm_o0, j > 0);
+          // ---- S_0(j+1) first: it lands in the buffer freed by PV_1(j-1), so tile 0 never waits for its scores
           if (has_next) {
             mbar_wait(&k_full[nstage], nphase);
             tc_fence_after();
-            issue_qk(q_addr0, kn_addr, tm_s0);
+            issue_qk(q_addr0, kn_addr, sbuf(j + 1, 0), nc_next);
             umma_commit(&s_full[0]);
           }
-          // ---- query tile 1
+          // ---- O_0 += P_0(j) V_j
+          mbar_wait(&p_full[0], j & 1);
+          mbar_wait(&v_full[stage], phase);
+          tc_fence_after();
+          issue_pv(sbuf(j, 0), v_addr, tm_o0, j > 0, ksteps);
+          umma_commit(&pv_done[0]);
           if (t1_valid) {
-            mbar_wait(&p_full[1], j & 1);
-            tc_fence_after();
-            issue_pv(tm_s1, v_addr, tm_o1, j > 0);
+            // ---- S_1(j+1) reuses the buffer P_0(j) just vacated (in-order execution after PV_0(j))
             if (has_next) {
-              issue_qk(q_addr1, kn_addr, tm_s1);
+              issue_qk(q_addr1, kn_addr, sbuf(j + 1, 1), nc_next);
               umma_commit(&s_full[1]);
             }
+            mbar_wait(&p_full[1], j & 1);
+            tc_fence_after();
+            issue_pv(sbuf(j, 1), v_addr, tm_o1, j > 0, ksteps);
+            umma_commit(&pv_done[1]);
           }
           umma_commit(&v_empty[stage]);
           if (has_next) umma_commit(&k_empty[nstage]);
           stage = nstage;
           phase = nphase;
         }
-        umma_commit(o_full);
       }
     }
   } else {
@@ -202,20 +237,23 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tma_qkv, int N, int H, 
     const int q_row = q0 + t * 128 + row_in_tile;  // row within the sample
     if (t == 0 || t1_valid) {
       const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-      const uint32_t tm_s = tmem_base + lane_off + t * 128;
-      const uint32_t tm_o = tmem_base + lane_off + 256 + t * 64;
+      const uint32_t tm_o = tmem_base + lane_off + 384 + t * 64;
       float m_ref = 0.f;   // running reference max (raw score units)
       float l_sum = 0.f;   // running sum of exp2((s - m_ref) * scale_log2)
       for (int j = 0; j < n_kv; ++j) {
+        const uint32_t tm_s = tmem_base + lane_off + static_cast<uint32_t>(((2 * j + t) % 3) * 128);
+        const int ncols = (j + 1 == n_kv) ? cols_last : 128;  // columns the MMA produced for this tile
+        const int kv_valid = N - j * 128;                     // columns >= kv_valid are padding
         mbar_wait(&s_full[t], j & 1);
         tc_fence_after();
         uint32_t s[128];
+        // all four chunks are always read (columns >= ncols hold stale data and are masked below); only the
+        // exp / P-store work is skipped for chunks the last, ragged MMA did not produce
         tmem_ld_x32(tm_s + 0, s);
         tmem_ld_x32(tm_s + 32, s + 32);
         tmem_ld_x32(tm_s + 64, s + 64);
         tmem_ld_x32(tm_s + 96, s + 96);
         tmem_ld_wait();
-        const int kv_valid = N - j * 128;  // columns >= kv_valid are padding (or the next sample's rows)
         if (kv_valid < 128) {
 #pragma unroll
           for (int i = 0; i < 128; ++i)
@@ -239,8 +277,11 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tma_qkv, int N, int H, 
             const float f = need ? ex2((m_ref - row_max) * scale_log2) : 1.0f;
             if (need) m_ref = row_max;
             l_sum *= f;
-            // O_t is quiescent here: s_full[t] for tile j implies PV_t(j-1) completed, and PV_t(j) is not
-            // issued before this warpgroup signals p_full[t].
+            // O_t is quiescent once PV_t(j-1) has completed: PV_t(j) is not issued before this warpgroup
+            // signals p_full[t].  (At step j the barrier has completed phase j-1 at most, so the parity is
+            // unambiguous even though this wait is only executed when a rescale is needed.)
+            mbar_wait(&pv_done[t], (j - 1) & 1);
+            tc_fence_after();
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
               uint32_t o[32];
@@ -256,23 +297,25 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tma_qkv, int N, int H, 
         const float neg_m = -m_ref * scale_log2;
         float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          uint32_t p[32];  // 64 kv elements as packed f16 pairs; P aliases the S columns already in registers
+        for (int c = 0; c < 4; ++c) {
+          if (c * 32 < ncols) {
+            uint32_t p[16];  // 32 kv elements as packed f16 pairs; P aliases S columns that are already in registers
 #pragma unroll
-          for (int i = 0; i < 64; i += 4) {
-            const int e = hh * 64 + i;
-            const float p0 = ex2(fmaf(__uint_as_float(s[e]), scale_log2, neg_m));
-            const float p1 = ex2(fmaf(__uint_as_float(s[e + 1]), scale_log2, neg_m));
-            const float p2 = ex2(fmaf(__uint_as_float(s[e + 2]), scale_log2, neg_m));
-            const float p3 = ex2(fmaf(__uint_as_float(s[e + 3]), scale_log2, neg_m));
-            sum0 += p0;
-            sum1 += p1;
-            sum2 += p2;
-            sum3 += p3;
-            p[(i >> 1)] = pack_half2(p0, p1);
-            p[(i >> 1) + 1] = pack_half2(p2, p3);
+            for (int i = 0; i < 32; i += 4) {
+              const int e = c * 32 + i;
+              const float p0 = ex2(fmaf(__uint_as_float(s[e]), scale_log2, neg_m));
+              const float p1 = ex2(fmaf(__uint_as_float(s[e + 1]), scale_log2, neg_m));
+              const float p2 = ex2(fmaf(__uint_as_float(s[e + 2]), scale_log2, neg_m));
+              const float p3 = ex2(fmaf(__uint_as_float(s[e + 3]), scale_log2, neg_m));
+              sum0 += p0;
+              sum1 += p1;
+              sum2 += p2;
+              sum3 += p3;
+              p[(i >> 1)] = pack_half2(p0, p1);
+              p[(i >> 1) + 1] = pack_half2(p2, p3);
+            }
+            tmem_st_x16(tm_s + c * 16, p);
           }
-          tmem_st_x32(tm_s + hh * 32, p);
         }
         tmem_st_wait();
         l_sum += (sum0 + sum1) + (sum2 + sum3);
@@ -281,7 +324,7 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tma_qkv, int N, int H, 
         if (lane == 0) mbar_arrive(&p_full[t]);
       }
       // ---- finalise: O / l -> f16 -> global
-      mbar_wait(o_full, 0);
+      mbar_wait(&pv_done[t], (n_kv - 1) & 1);
       tc_fence_after();
       const float inv_l = 1.0f / l_sum;
       __half* orow = out + (static_cast<long long>(row_base) + q_row) * C + h * 64;

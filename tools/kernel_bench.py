@@ -35,6 +35,7 @@ CASES = {
     "attn_dec_base": ("attn", 64, 1568, 6),
     "attn_enc_large": ("attn", 32, 3140, 16),
     "attn_dec_large": ("attn", 32, 6272, 8),
+    "attn_dec_large_b6": ("attn", 6, 6272, 8),
     "ln_base_enc": ("ln", 50432, 768),
 }
 
