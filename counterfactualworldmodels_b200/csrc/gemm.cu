@@ -125,7 +125,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   uint64_t* res_bar = tempty_bar + 2;               // kEpiWarps * 2 (residual chunk landed)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2 * kEpiWarps);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
 
   const int tiles_m = (M + BM - 1) / BM;
@@ -161,60 +161,65 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // NOTE: the producer and MMA roles run warp-uniformly (all 32 lanes execute the loops and the mbarrier waits) and
+  // only the TMA / tcgen05 instructions themselves are issued by one elected lane.  Running the whole role under
+  // `if (lane == 0)` makes every operand thread-private and the compiler wraps each TMA / MMA instruction in a
+  // per-lane "waterfall" loop (R2UR + BRA.U.ANY), ~100 cycles of issue per instruction.
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / tiles_n;
-        const int n_blk = tile - m_blk * tiles_n;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / tiles_n;
+      const int n_blk = tile - m_blk * tiles_n;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           tma_load_2d(smem_a + stage * Cfg::kABytes, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
           tma_load_2d(smem_b + stage * Cfg::kBBytes, &tma_w, &full_bar[stage], kb * BK, n_blk * BN);
-          if (++stage == Cfg::kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        if (++stage == Cfg::kStages) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(BM, BN, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int as = 0;
-      uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[as], aphase ^ 1);
+    constexpr uint32_t idesc = umma_idesc_f16(BM, BN, 0, 0);
+    const uint64_t adesc0 = umma_desc_kmajor_sw128(smem_u32(smem_a));
+    const uint64_t bdesc0 = umma_desc_kmajor_sw128(smem_u32(smem_b));
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + as * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::kABytes);
-          const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::kBBytes);
+        // descriptors: only the start-address field (>> 4 units) changes with the stage and the k-step
+        const uint64_t adesc = adesc0 + static_cast<uint64_t>(stage * (Cfg::kABytes >> 4));
+        const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(stage * (Cfg::kBBytes >> 4));
+        if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t adesc = umma_desc_kmajor_sw128(a_addr + k * 32);
-            const uint64_t bdesc = umma_desc_kmajor_sw128(b_addr + k * 32);
-            umma_ss(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < BK / 16; ++k) umma_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit(&empty_bar[stage]);  // frees the smem slot when the MMAs above have read it
-          if (++stage == Cfg::kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
+          if (kb == num_kb - 1) umma_commit(&tfull_bar[as]);  // accumulator complete
         }
-        umma_commit(&tfull_bar[as]);  // accumulator complete
-        if (++as == 2) {
-          as = 0;
-          aphase ^= 1;
+        __syncwarp();
+        if (++stage == Cfg::kStages) {
+          stage = 0;
+          phase ^= 1;
         }
+      }
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
       }
     }
   } else if (warp >= 4) {
@@ -261,7 +266,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
             if (lane == 0) mbar_arrive(&tempty_bar[as]);
           }
           __syncwarp();
-          if (lane == 0) bulk_wait_read0();  // the previous TMA store has finished reading the buffer
+          if (elect_one()) bulk_wait_read0();  // the previous TMA store has finished reading the buffer
           __syncwarp();
 #pragma unroll
           for (int u = 0; u < 8; ++u) {  // 16-byte unit u = columns 8u .. 8u+7
@@ -283,7 +288,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (elect_one()) {
             tma_store_2d(&tma_out, buf0, n0, row0);
             bulk_commit();
           }
@@ -297,7 +302,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
           aphase ^= 1;
         }
       }
-      if (lane == 0) bulk_wait_all();
+      if (elect_one()) bulk_wait_all();
     } else if (ep.grp_rows <= 0) {
       // ---------------- fp32 output (+ residual): 32-column chunks, TMA load of the residual one chunk ahead,
       //                  TMA store ----------------
@@ -322,7 +327,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         first = (ci == 0);
         last = (ci == my_chunks - 1);
       };
-      if (has_res && n_items > 0 && lane == 0) {  // prefetch the residual chunk of the first item
+      if (has_res && n_items > 0 && elect_one()) {  // prefetch the residual chunk of the first item
         int row0, n0, c;
         bool f, l;
         item_coords(0, row0, n0, c, f, l);
@@ -351,7 +356,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
           if (lane == 0) mbar_arrive(&tempty_bar[as]);
         }
         __syncwarp();
-        if (lane == 0) {
+        if (elect_one()) {
           // buffer (it+1)&1 was last used by item it-1: its store must have finished reading smem
           bulk_wait_read0();
           if (has_res && it + 1 < n_items) {
@@ -383,7 +388,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
+        if (elect_one()) {
           tma_store_2d(&tma_out, buf, n0, row0);
           bulk_commit();
         }
@@ -394,7 +399,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
           }
         }
       }
-      if (lane == 0) bulk_wait_all();
+      if (elect_one()) bulk_wait_all();
     } else {
       // ---------------- generic fp32 epilogue with row remap / gathered residual (two small GEMMs per forward):
       //                  padded smem transpose, coalesced direct global accesses ----------------

@@ -85,6 +85,12 @@ def run_case(name, iters=5):
 
 
 if __name__ == "__main__":
+    if os.environ.get("CWM_ATTN_POLY"):
+        import ctypes
+        lib = _lib.load()
+        lib.cwm_debug_attention_poly.argtypes = [ctypes.c_int]
+        lib.cwm_debug_attention_poly(int(os.environ["CWM_ATTN_POLY"]))
+        print("attention poly eighths =", os.environ["CWM_ATTN_POLY"])
     names = sys.argv[1:] or list(CASES)
     for n in names:
         run_case(n)
