@@ -18,7 +18,9 @@ EXPORTED_SYMBOLS = (
     "cwm_abi_version", "cwm_last_error", "cwm_device_check", "cwm_compact_mask", "cwm_patch_gather",
     "cwm_layernorm_f16", "cwm_gemm_f16", "cwm_attention_f16", "cwm_fill_mask_tokens",
     "cwm_unpatchify_scatter", "cwm_vmae_workspace_bytes", "cwm_vmae_forward", "cwm_last_forward_launches",
-    "cwm_profile_begin", "cwm_profile_end",
+    "cwm_profile_begin", "cwm_profile_end", "cwm_attention_generic_workspace_bytes", "cwm_attention_generic_f16",
+    "cwm_fill_pad_rows", "cwm_block_workspace_bytes", "cwm_block_forward", "cwm_cross_block_workspace_bytes",
+    "cwm_cross_block_forward", "cwm_launch_count_reset",
 )
 
 
@@ -38,6 +40,13 @@ class BlockWeights(Structure):
     _fields_ = [(n, c_void_p) for n in (
         "ln1_g", "ln1_b", "w_qkv", "b_qkv", "w_proj", "b_proj", "ln2_g", "ln2_b", "w_fc1", "b_fc1", "w_fc2",
         "b_fc2")]
+
+
+class CrossBlockWeights(Structure):
+    _fields_ = [(n, c_void_p) for n in (
+        "ln1_g", "ln1_b", "ln1s_g", "ln1s_b", "w_qkv", "w_qkv_s", "w_proj", "b_proj", "w_proj_s", "b_proj_s",
+        "ln2_g", "ln2_b", "ln2s_g", "ln2s_b", "w_fc1", "b_fc1", "w_fc2", "b_fc2", "w_fc1_s", "b_fc1_s", "w_fc2_s",
+        "b_fc2_s")]
 
 
 class VmaeModel(Structure):
@@ -84,6 +93,20 @@ def _declare(lib):
     lib.cwm_vmae_forward.argtypes = [POINTER(VmaeModel), c_void_p, i64x5, c_int, POINTER(c_float),
                                      POINTER(c_float), c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.cwm_last_forward_launches.restype = c_int
+    lib.cwm_launch_count_reset.restype = c_int
+    lib.cwm_attention_generic_workspace_bytes.argtypes = [c_int] * 5
+    lib.cwm_attention_generic_workspace_bytes.restype = c_size_t
+    lib.cwm_attention_generic_f16.argtypes = [c_void_p, c_void_p, c_void_p] + [c_int] * 11 + [c_void_p, c_int, c_void_p,
+                                                                                           c_size_t, c_void_p]
+    lib.cwm_fill_pad_rows.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]
+    lib.cwm_block_workspace_bytes.argtypes = [c_int] * 6
+    lib.cwm_block_workspace_bytes.restype = c_size_t
+    lib.cwm_block_forward.argtypes = [POINTER(BlockWeights), c_void_p] + [c_int] * 6 + [c_float, c_float, c_void_p,
+                                                                                      c_size_t, c_void_p]
+    lib.cwm_cross_block_workspace_bytes.argtypes = [c_int] * 9
+    lib.cwm_cross_block_workspace_bytes.restype = c_size_t
+    lib.cwm_cross_block_forward.argtypes = ([POINTER(CrossBlockWeights), c_void_p, c_void_p] + [c_int] * 9 +
+                                            [c_float, c_float, c_void_p, c_size_t, c_void_p])
     lib.cwm_profile_begin.restype = c_int
     lib.cwm_profile_end.argtypes = [POINTER(ProfileEntry), c_int, POINTER(c_int)]
     for name in EXPORTED_SYMBOLS:

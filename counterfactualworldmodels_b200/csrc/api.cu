@@ -174,4 +174,9 @@ int cwm_device_check(void) {
 
 int cwm_last_forward_launches(void) { return cwm::g_launches; }
 
+int cwm_launch_count_reset(void) {
+  cwm::g_launches = 0;
+  return CWM_OK;
+}
+
 }  // extern "C"

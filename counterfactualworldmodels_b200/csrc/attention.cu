@@ -500,7 +500,11 @@ extern "C" int cwm_attention_f16(const uint16_t* qkv, int B, int N, int H, int h
                                  cwm_stream_t stream) {
   CWM_REQUIRE(qkv && out, "cwm_attention_f16: null pointer");
   CWM_REQUIRE(B >= 0 && N > 0 && H > 0, "cwm_attention_f16: bad shape B=%d N=%d H=%d", B, N, H);
-  if (head_dim != 64) return fail(CWM_ERR_UNSUPPORTED, "cwm_attention_f16: head_dim %d (only 64 is implemented)", head_dim);
+  if (head_dim != 64) {  // 32 / 96 / 128 / 192: the generic warp-level tensor-core kernel (attn_mma.cu)
+    const int A = H * head_dim;
+    return cwm_attention_generic_f16(qkv, qkv + A, qkv + 2 * A, 3 * A, 3 * A, 3 * A, head_dim, head_dim, head_dim, B, N, N,
+                                     H, head_dim, out, A, nullptr, 0, stream);
+  }
   CWM_REQUIRE(H <= 65535 && B <= 65535, "cwm_attention_f16: grid too large");
   if (B == 0) return CWM_OK;
   using KernelFn = void (*)(const CUtensorMap, int, int, __half*, float, long long*);

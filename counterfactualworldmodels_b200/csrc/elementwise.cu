@@ -18,6 +18,7 @@ struct GatherParams {
   int K4;  // K / 4
   const int32_t* perm;
   int Ntot, rows_per_sample;
+  int n_tokens;  // real tokens (T/pt * n_h * n_w); ids >= n_tokens are padding positions -> zero rows
   float mean[8], stdv[8];
   int normalize;
   __half* out;
@@ -33,6 +34,10 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(GatherParams p) {
   const int j = static_cast<int>(m % p.rows_per_sample);
   const int b = static_cast<int>(m / p.rows_per_sample);
   const int tok = p.perm[static_cast<long long>(b) * p.Ntot + j];
+  if (tok >= p.n_tokens) {  // padding position of a PaddedVisionTransformer (conjoined_vmae.py:130-133)
+    *reinterpret_cast<uint2*>(p.out + m * (static_cast<long long>(p.K4) * 4) + k4 * 4) = make_uint2(0u, 0u);
+    return;
+  }
   const int n_hw = p.n_h * p.n_w;
   const int tt = tok / n_hw;
   const int rem = tok - tt * n_hw;
@@ -71,6 +76,37 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(GatherParams p) {
   o.x = *reinterpret_cast<uint32_t*>(&lo);
   o.y = *reinterpret_cast<uint32_t*>(&hi);
   *reinterpret_cast<uint2*>(p.out + m * (static_cast<long long>(p.K4) * 4) + k4 * 4) = o;
+}
+
+
+// scalar variant for patch widths that are not a multiple of 4 (the IMU "video" [B, 6, 400, 1, 1] with a
+// (16, 1, 1) tubelet, conjoined_vmae.py:1013-1038): one thread per element; K4 holds K here.
+__global__ void __launch_bounds__(256) patch_gather_scalar_kernel(GatherParams p) {
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= p.total) return;
+  const int K = p.K4;
+  const int k = static_cast<int>(i % K);
+  const long long m = i / K;
+  const int j = static_cast<int>(m % p.rows_per_sample);
+  const int b = static_cast<int>(m / p.rows_per_sample);
+  const int tok = p.perm[static_cast<long long>(b) * p.Ntot + j];
+  float v = 0.f;
+  if (tok < p.n_tokens) {
+    const int n_hw = p.n_h * p.n_w;
+    const int tt = tok / n_hw;
+    const int rem = tok - tt * n_hw;
+    const int hh = rem / p.n_w;
+    const int ww = rem - hh * p.n_w;
+    const int kw = k % p.pw;
+    int r = k / p.pw;
+    const int kh = r % p.ph;
+    r /= p.ph;
+    const int kt = r % p.pt;
+    const int c = r / p.pt;
+    v = __ldg(p.x + b * p.sb + c * p.sc + (tt * p.pt + kt) * p.st + (hh * p.ph + kh) * p.sh + (ww * p.pw + kw) * p.sw);
+    if (p.normalize) v = __fdiv_rn(v - p.mean[c], p.stdv[c]);
+  }
+  p.out[m * K + k] = __float2half_rn(v);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -125,6 +161,75 @@ layernorm_f16_kernel(const float* __restrict__ x, int M, const float* __restrict
     o.y = pack_half2(y2, y3);
     orow[lane + 32 * i] = o;
   }
+}
+
+
+// Same algorithm for widths that are not a multiple of 128 (context-stream widths 64 / 192, conjoined_vmae.py:
+// 1198-1204): C % 4 == 0, C <= 1024; lanes beyond the row end hold zeros and are excluded from the statistics.
+__global__ void __launch_bounds__(256)
+layernorm_f16_generic_kernel(const float* __restrict__ x, int M, int C, const float* __restrict__ gamma,
+                             const float* __restrict__ beta, float eps, int grp_rows, int grp_stride, int grp_offset,
+                             __half* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  long long in_row = warp;
+  if (grp_rows > 0) in_row = static_cast<long long>(warp / grp_rows) * grp_stride + grp_offset + warp % grp_rows;
+  const int C4 = C >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + in_row * C);
+  float4 v[8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c4 = lane + 32 * i;
+    v[i] = (c4 < C4) ? xr[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / static_cast<float>(C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (lane + 32 * i < C4) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / static_cast<float>(C) + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+  uint2* orow = reinterpret_cast<uint2*>(out + static_cast<long long>(warp) * C);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c4 = lane + 32 * i;
+    if (c4 < C4) {
+      const float4 g = __ldg(g4 + c4);
+      const float4 bb = __ldg(b4 + c4);
+      uint2 o;
+      o.x = pack_half2((v[i].x - mean) * rstd * g.x + bb.x, (v[i].y - mean) * rstd * g.y + bb.y);
+      o.y = pack_half2((v[i].z - mean) * rstd * g.z + bb.z, (v[i].w - mean) * rstd * g.w + bb.w);
+      orow[c4] = o;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// padding rows: x[b, j, :] = value (or 0) where perm[b, perm_offset + j] >= first_pad_token
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+fill_pad_rows_kernel(float4* __restrict__ x, int rows, int C4, const int32_t* __restrict__ perm, int perm_stride,
+                     int perm_offset, int first_pad_token, const float4* __restrict__ value, long long total) {
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c4 = static_cast<int>(i % C4);
+  const long long r = i / C4;
+  const int j = static_cast<int>(r % rows);
+  const long long b = r / rows;
+  if (perm[b * perm_stride + perm_offset + j] < first_pad_token) return;
+  x[i] = value != nullptr ? __ldg(value + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -220,7 +325,6 @@ extern "C" int cwm_patch_gather(const float* x, const int64_t xs[5], int B, int 
   CWM_REQUIRE(x && xs && perm && out, "cwm_patch_gather: null pointer");
   CWM_REQUIRE(pt > 0 && ph > 0 && pw > 0 && T % pt == 0 && H % ph == 0 && W % pw == 0,
               "Input image size(%d,%d) must be divisible by patch size (%d,%d)", H, W, ph, pw);
-  CWM_REQUIRE(pw % 4 == 0, "cwm_patch_gather: patch width %d must be a multiple of 4", pw);
   CWM_REQUIRE(C <= 8, "cwm_patch_gather: at most 8 input channels (got %d)", C);
   CWM_REQUIRE((mean == nullptr) == (stdv == nullptr), "cwm_patch_gather: mean/std must both be set or both NULL");
   if (B == 0 || rows_per_sample == 0) return CWM_OK;
@@ -229,8 +333,10 @@ extern "C" int cwm_patch_gather(const float* x, const int64_t xs[5], int B, int 
   p.sb = xs[0]; p.sc = xs[1]; p.st = xs[2]; p.sh = xs[3]; p.sw = xs[4];
   p.C = C; p.pt = pt; p.ph = ph; p.pw = pw; p.n_h = H / ph; p.n_w = W / pw;
   const int K = C * pt * ph * pw;
-  p.K4 = K / 4;
+  const bool vec4 = (pw % 4 == 0);
+  p.K4 = vec4 ? K / 4 : K;
   p.perm = perm; p.Ntot = Ntot; p.rows_per_sample = rows_per_sample;
+  p.n_tokens = (T / pt) * p.n_h * p.n_w;
   p.normalize = mean != nullptr;
   for (int c = 0; c < 8; ++c) { p.mean[c] = 0.f; p.stdv[c] = 1.f; }
   if (p.normalize) {
@@ -245,7 +351,10 @@ extern "C" int cwm_patch_gather(const float* x, const int64_t xs[5], int B, int 
   const long long blocks = (p.total + threads - 1) / threads;
   ProfileScope prof(static_cast<cudaStream_t>(stream), "patch_gather", 0.0,
                     static_cast<double>(B) * rows_per_sample * K * 6.0);
-  patch_gather_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  if (vec4)
+    patch_gather_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  else
+    patch_gather_scalar_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(p);
   CWM_LAUNCH_CHECK();
   return CWM_OK;
 }
@@ -254,7 +363,7 @@ extern "C" int cwm_layernorm_f16(const float* x, int M, int C, const float* gamm
                                  int grp_rows, int grp_stride, int grp_offset, uint16_t* out,
                                  cwm_stream_t stream) {
   CWM_REQUIRE(x && gamma && beta && out, "cwm_layernorm_f16: null pointer");
-  CWM_REQUIRE(C % 128 == 0 && C >= 128 && C <= 1024, "cwm_layernorm_f16: C=%d must be a multiple of 128 in [128,1024]", C);
+  CWM_REQUIRE(C % 4 == 0 && C >= 4 && C <= 1024, "cwm_layernorm_f16: C=%d must be a multiple of 4 in [4,1024]", C);
   if (M == 0) return CWM_OK;
   const int threads = 256;
   const int rows_per_cta = threads / 32;
@@ -262,6 +371,11 @@ extern "C" int cwm_layernorm_f16(const float* x, int M, int C, const float* gamm
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   __half* o = reinterpret_cast<__half*>(out);
   ProfileScope prof(s, "layernorm_f16", 0.0, static_cast<double>(M) * C * 6.0);
+  if (C % 128 != 0) {
+    layernorm_f16_generic_kernel<<<blocks, threads, 0, s>>>(x, M, C, gamma, beta, eps, grp_rows, grp_stride, grp_offset, o);
+    CWM_LAUNCH_CHECK();
+    return CWM_OK;
+  }
 #define LN_CASE(V)                                                                                        \
   case V:                                                                                                 \
     layernorm_f16_kernel<V><<<blocks, threads, 0, s>>>(x, M, gamma, beta, eps, grp_rows, grp_stride,      \
@@ -324,6 +438,23 @@ extern "C" int cwm_unpatchify_scatter(const float* y, const float* x_raw, const 
   ProfileScope prof(static_cast<cudaStream_t>(stream), "unpatchify_scatter", 0.0,
                     static_cast<double>(p.total) * 4 * 8.0);
   unpatchify_scatter_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  CWM_LAUNCH_CHECK();
+  return CWM_OK;
+}
+
+extern "C" int cwm_fill_pad_rows(float* x, int B, int rows, int C, const int32_t* perm, int perm_stride,
+                                 int perm_offset, int first_pad_token, const float* value, cwm_stream_t stream) {
+  CWM_REQUIRE(x && perm, "cwm_fill_pad_rows: null pointer");
+  CWM_REQUIRE(C % 4 == 0 && rows >= 0 && B >= 0 && perm_offset >= 0 && perm_offset + rows <= perm_stride,
+              "cwm_fill_pad_rows: bad shape rows=%d C=%d perm_offset=%d perm_stride=%d", rows, C, perm_offset, perm_stride);
+  const long long total = static_cast<long long>(B) * rows * (C / 4);
+  if (total == 0) return CWM_OK;
+  const int threads = 256;
+  const long long blocks = (total + threads - 1) / threads;
+  ProfileScope prof(static_cast<cudaStream_t>(stream), "fill_pad_rows", 0.0, static_cast<double>(B) * rows * 4.0);
+  fill_pad_rows_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<float4*>(x), rows, C / 4, perm, perm_stride, perm_offset, first_pad_token,
+      reinterpret_cast<const float4*>(value), total);
   CWM_LAUNCH_CHECK();
   return CWM_OK;
 }

@@ -69,22 +69,63 @@ static cwm_gemm_epilogue epi_res(const float* bias, float* x, int ld) {
   } while (0)
 
 // x += Attn(LN1(x)); x += Mlp(LN2(x))   (cwm/models/VideoMAE/utils.py:146-153, gamma_* = None)
-static int run_block(const cwm_block_weights& w, float* x, int Bn, int N, int C, int heads, int hidden, float eps,
-                     float qk_scale, uint16_t* a16, uint16_t* qkv, uint16_t* attn, uint16_t* h16,
+// inner attention width A = heads * head_dim; `attn` may alias `a16` (the LN output is dead once qkv is computed).
+static int run_block(const cwm_block_weights& w, float* x, int Bn, int N, int C, int heads, int head_dim, int hidden,
+                     float eps, float qk_scale, uint16_t* a16, uint16_t* qkv, uint16_t* attn, uint16_t* h16,
                      cwm_stream_t st) {
   const int M = Bn * N;
+  const int A = heads * head_dim;
   CWM_TRY(cwm_layernorm_f16(x, M, C, w.ln1_g, w.ln1_b, eps, 0, 0, 0, a16, st));
-  cwm_gemm_epilogue e = epi_f16(w.b_qkv, qk_scale, C, qkv, 3 * C);  // (xW + [q_bias,0,v_bias]); q *= scale
-  CWM_TRY(cwm_gemm_f16(a16, w.w_qkv, M, 3 * C, C, &e, st));
-  CWM_TRY(cwm_attention_f16(qkv, Bn, N, heads, 64, attn, st));
+  cwm_gemm_epilogue e = epi_f16(w.b_qkv, qk_scale, A, qkv, 3 * A);  // (xW + [q_bias,0,v_bias]); q *= scale
+  CWM_TRY(cwm_gemm_f16(a16, w.w_qkv, M, 3 * A, C, &e, st));
+  if (head_dim == 64) {
+    CWM_TRY(cwm_attention_f16(qkv, Bn, N, heads, 64, attn, st));
+  } else {
+    CWM_TRY(cwm_attention_generic_f16(qkv, qkv + A, qkv + 2 * A, 3 * A, 3 * A, 3 * A, head_dim, head_dim, head_dim, Bn,
+                                      N, N, heads, head_dim, attn, A, nullptr, 0, st));
+  }
   e = epi_res(w.b_proj, x, C);
-  CWM_TRY(cwm_gemm_f16(attn, w.w_proj, M, C, C, &e, st));
+  CWM_TRY(cwm_gemm_f16(attn, w.w_proj, M, C, A, &e, st));
   CWM_TRY(cwm_layernorm_f16(x, M, C, w.ln2_g, w.ln2_b, eps, 0, 0, 0, a16, st));
   e = epi_gelu(w.b_fc1, h16, hidden);
   CWM_TRY(cwm_gemm_f16(a16, w.w_fc1, M, hidden, C, &e, st));
   e = epi_res(w.b_fc2, x, C);
   CWM_TRY(cwm_gemm_f16(h16, w.w_fc2, M, C, hidden, &e, st));
   return CWM_OK;
+}
+
+struct BlockPlan {
+  size_t off_a16, off_qkv, off_h16, total;
+};
+static void make_block_plan(long long M, int C, int A, int hidden, BlockPlan* p) {
+  size_t off = 0;
+  p->off_a16 = off; off = align_up(off + M * (C > A ? C : A) * 2, 1024);
+  p->off_qkv = off; off = align_up(off + M * 3 * A * 2, 1024);
+  p->off_h16 = off; off = align_up(off + M * hidden * 2, 1024);
+  p->total = off + 1024;
+}
+
+struct CrossPlan {
+  size_t off_a16, off_qkv, off_y, off_h16, off_a16s, off_qkvs, off_ys, off_h16s, off_attn_ws, attn_ws_bytes, total;
+};
+static void make_cross_plan(int B, int N, int M, int C, int Cs, int heads, int head_dim, int hidden, int hidden_s,
+                            CrossPlan* p) {
+  const long long Mx = static_cast<long long>(B) * N, Ms = static_cast<long long>(B) * M;
+  const int D = heads * head_dim;
+  size_t off = 0;
+  p->off_a16 = off;  off = align_up(off + Mx * C * 2, 1024);
+  p->off_qkv = off;  off = align_up(off + Mx * 3 * D * 2, 1024);
+  p->off_y = off;    off = align_up(off + Mx * D * 2, 1024);
+  p->off_h16 = off;  off = align_up(off + Mx * hidden * 2, 1024);
+  p->off_a16s = off; off = align_up(off + Ms * Cs * 2, 1024);
+  p->off_qkvs = off; off = align_up(off + Ms * 3 * D * 2, 1024);
+  p->off_ys = off;   off = align_up(off + Ms * D * 2, 1024);
+  p->off_h16s = off; off = align_up(off + Ms * hidden_s * 2, 1024);
+  const size_t a = cwm_attention_generic_workspace_bytes(B, N, M, heads, head_dim);
+  const size_t b = cwm_attention_generic_workspace_bytes(B, M, N, heads, head_dim);
+  p->attn_ws_bytes = a > b ? a : b;
+  p->off_attn_ws = off; off = align_up(off + p->attn_ws_bytes, 1024);
+  p->total = off + 1024;
 }
 
 }  // namespace cwm
@@ -126,7 +167,7 @@ extern "C" int cwm_vmae_forward(const cwm_vmae_model* m, const float* x, const i
     CWM_TRY(cwm_gemm_f16(a16, m->w_patch, static_cast<int>(p.Me), Ce, p.Kp, &e, st));
     // a5-a7: encoder blocks
     for (int l = 0; l < m->enc_depth; ++l)
-      CWM_TRY(run_block(m->enc_blocks[l], xe, B, Nvis, Ce, m->enc_heads, m->enc_hidden, m->ln_eps, m->enc_qk_scale,
+      CWM_TRY(run_block(m->enc_blocks[l], xe, B, Nvis, Ce, m->enc_heads, 64, m->enc_hidden, m->ln_eps, m->enc_qk_scale,
                         a16, qkv, attn, h16, st));
     // a8-a10: final norm, encoder_to_decoder (no bias) written at the visible rows of the decoder sequence with
     // the positional embedding of each visible token added
@@ -139,7 +180,7 @@ extern "C" int cwm_vmae_forward(const cwm_vmae_model* m, const float* x, const i
   CWM_TRY(cwm_fill_mask_tokens(m->mask_token, m->pos_dec, perm, B, p.Ntot, Nvis, Cd, xd, st));
   // a11: decoder blocks over all Ntot tokens, then head(norm(last Nmask tokens))
   for (int l = 0; l < m->dec_depth; ++l)
-    CWM_TRY(run_block(m->dec_blocks[l], xd, B, p.Ntot, Cd, m->dec_heads, m->dec_hidden, m->ln_eps, m->dec_qk_scale, a16,
+    CWM_TRY(run_block(m->dec_blocks[l], xd, B, p.Ntot, Cd, m->dec_heads, 64, m->dec_hidden, m->ln_eps, m->dec_qk_scale, a16,
                       qkv, attn, h16, st));
   if (p.Nmask > 0) {
     CWM_TRY(cwm_layernorm_f16(xd, static_cast<int>(p.Mo), Cd, m->dec_norm_g, m->dec_norm_b, m->ln_eps, p.Nmask, p.Ntot,
@@ -150,5 +191,98 @@ extern "C" int cwm_vmae_forward(const cwm_vmae_model* m, const float* x, const i
   cwm_gemm_epilogue e = {};
   e.mode = CWM_EPI_F32; e.bias = m->b_head; e.out = y; e.ldo = m->out_dim;
   CWM_TRY(cwm_gemm_f16(a16, m->w_head, static_cast<int>(p.Mo), m->out_dim, Cd, &e, st));
+  return CWM_OK;
+}
+
+// ---- block-level entry points used by the conjoined (IMU-conditioned) models ------------------------------------
+static uint8_t* align_ws(void* workspace) {
+  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
+}
+
+extern "C" size_t cwm_block_workspace_bytes(int B, int N, int C, int heads, int head_dim, int hidden) {
+  if (B < 0 || N < 0 || C <= 0 || heads <= 0 || head_dim <= 0 || hidden <= 0) return 0;
+  BlockPlan p;
+  make_block_plan(static_cast<long long>(B) * N, C, heads * head_dim, hidden, &p);
+  return p.total;
+}
+
+extern "C" int cwm_block_forward(const cwm_block_weights* w, float* x, int B, int N, int C, int heads, int head_dim,
+                                 int hidden, float ln_eps, float qk_scale, void* workspace, size_t workspace_bytes,
+                                 cwm_stream_t st) {
+  CWM_REQUIRE(w && x && workspace, "cwm_block_forward: null pointer");
+  CWM_REQUIRE(B >= 0 && N > 0 && C > 0 && heads > 0 && head_dim > 0 && hidden > 0, "cwm_block_forward: bad shape");
+  BlockPlan p;
+  make_block_plan(static_cast<long long>(B) * N, C, heads * head_dim, hidden, &p);
+  if (workspace_bytes < p.total)
+    return fail(CWM_ERR_WORKSPACE, "cwm_block_forward: workspace %zu bytes < required %zu", workspace_bytes, p.total);
+  if (B == 0) return CWM_OK;
+  uint8_t* ws = align_ws(workspace);
+  uint16_t* a16 = reinterpret_cast<uint16_t*>(ws + p.off_a16);
+  return run_block(*w, x, B, N, C, heads, head_dim, hidden, ln_eps, qk_scale, a16,
+                   reinterpret_cast<uint16_t*>(ws + p.off_qkv), a16, reinterpret_cast<uint16_t*>(ws + p.off_h16), st);
+}
+
+extern "C" size_t cwm_cross_block_workspace_bytes(int B, int N, int M, int C, int Cs, int heads, int head_dim,
+                                                  int hidden, int hidden_s) {
+  if (B < 0 || N <= 0 || M <= 0 || C <= 0 || Cs <= 0 || heads <= 0 || head_dim <= 0) return 0;
+  CrossPlan p;
+  make_cross_plan(B, N, M, C, Cs, heads, head_dim, hidden, hidden_s, &p);
+  return p.total;
+}
+
+extern "C" int cwm_cross_block_forward(const cwm_cross_block_weights* w, float* x, float* src, int B, int N, int M,
+                                       int C, int Cs, int heads, int head_dim, int hidden, int hidden_s, float eps,
+                                       float scale, void* workspace, size_t workspace_bytes, cwm_stream_t st) {
+  CWM_REQUIRE(w && x && src && workspace, "cwm_cross_block_forward: null pointer");
+  CWM_REQUIRE(B >= 0 && N > 0 && M > 0 && C > 0 && Cs > 0 && heads > 0 && head_dim > 0 && hidden > 0 && hidden_s > 0,
+              "cwm_cross_block_forward: bad shape");
+  CrossPlan p;
+  make_cross_plan(B, N, M, C, Cs, heads, head_dim, hidden, hidden_s, &p);
+  if (workspace_bytes < p.total)
+    return fail(CWM_ERR_WORKSPACE, "cwm_cross_block_forward: workspace %zu bytes < required %zu", workspace_bytes, p.total);
+  if (B == 0) return CWM_OK;
+  uint8_t* ws = align_ws(workspace);
+  uint16_t* a16 = reinterpret_cast<uint16_t*>(ws + p.off_a16);
+  uint16_t* qkv = reinterpret_cast<uint16_t*>(ws + p.off_qkv);
+  uint16_t* y = reinterpret_cast<uint16_t*>(ws + p.off_y);
+  uint16_t* h16 = reinterpret_cast<uint16_t*>(ws + p.off_h16);
+  uint16_t* a16s = reinterpret_cast<uint16_t*>(ws + p.off_a16s);
+  uint16_t* qkvs = reinterpret_cast<uint16_t*>(ws + p.off_qkvs);
+  uint16_t* ys = reinterpret_cast<uint16_t*>(ws + p.off_ys);
+  uint16_t* h16s = reinterpret_cast<uint16_t*>(ws + p.off_h16s);
+  void* attn_ws = ws + p.off_attn_ws;
+  const int Mx = B * N, Ms = B * M, D = heads * head_dim, hd = head_dim;
+
+  // qk | v of both streams from the cross norms (transformer.py:539-546, :333-336); the softmax scale multiplies
+  // both halves of the main stream's qk (transformer.py:359, :363), qk_src stays unscaled
+  CWM_TRY(cwm_layernorm_f16(x, Mx, C, w->ln1_g, w->ln1_b, eps, 0, 0, 0, a16, st));
+  cwm_gemm_epilogue e = epi_f16(nullptr, scale, 2 * D, qkv, 3 * D);
+  CWM_TRY(cwm_gemm_f16(a16, w->w_qkv, Mx, 3 * D, C, &e, st));
+  CWM_TRY(cwm_layernorm_f16(src, Ms, Cs, w->ln1s_g, w->ln1s_b, eps, 0, 0, 0, a16s, st));
+  e = epi_f16(nullptr, 1.0f, 0, qkvs, 3 * D);
+  CWM_TRY(cwm_gemm_f16(a16s, w->w_qkv_s, Ms, 3 * D, Cs, &e, st));
+  // head h of qk occupies columns [2*hd*h, 2*hd*(h+1)): first hd = the "trg" similarity, last hd = the "src" one
+  // attn     = softmax(qk[..., :hd] qk_src[..., :hd]^T);   y     = attn @ v_src      (transformer.py:358-361, :370)
+  CWM_TRY(cwm_attention_generic_f16(qkv, qkvs, qkvs + 2 * D, 3 * D, 3 * D, 3 * D, 2 * hd, 2 * hd, hd, B, N, M, heads, hd, y,
+                                    D, attn_ws, p.attn_ws_bytes, st));
+  // attn_src = softmax(qk_src[..., hd:] qk[..., hd:]^T);   y_src = attn_src @ v      (transformer.py:362-365, :371)
+  CWM_TRY(cwm_attention_generic_f16(qkvs + hd, qkv + hd, qkv + 2 * D, 3 * D, 3 * D, 3 * D, 2 * hd, 2 * hd, hd, B, M, N, heads,
+                                    hd, ys, D, attn_ws, p.attn_ws_bytes, st));
+  // x += projection(y); src += projection_src(y_src)   (transformer.py:374-375, :569-575 with gamma_1 = 0)
+  e = epi_res(w->b_proj, x, C);
+  CWM_TRY(cwm_gemm_f16(y, w->w_proj, Mx, C, D, &e, st));
+  e = epi_res(w->b_proj_s, src, Cs);
+  CWM_TRY(cwm_gemm_f16(ys, w->w_proj_s, Ms, Cs, D, &e, st));
+  // per-stream MLP (transformer.py:578-580)
+  CWM_TRY(cwm_layernorm_f16(x, Mx, C, w->ln2_g, w->ln2_b, eps, 0, 0, 0, a16, st));
+  e = epi_gelu(w->b_fc1, h16, hidden);
+  CWM_TRY(cwm_gemm_f16(a16, w->w_fc1, Mx, hidden, C, &e, st));
+  e = epi_res(w->b_fc2, x, C);
+  CWM_TRY(cwm_gemm_f16(h16, w->w_fc2, Mx, C, hidden, &e, st));
+  CWM_TRY(cwm_layernorm_f16(src, Ms, Cs, w->ln2s_g, w->ln2s_b, eps, 0, 0, 0, a16s, st));
+  e = epi_gelu(w->b_fc1_s, h16s, hidden_s);
+  CWM_TRY(cwm_gemm_f16(a16s, w->w_fc1_s, Ms, hidden_s, Cs, &e, st));
+  e = epi_res(w->b_fc2_s, src, Cs);
+  CWM_TRY(cwm_gemm_f16(h16s, w->w_fc2_s, Ms, Cs, hidden_s, &e, st));
   return CWM_OK;
 }

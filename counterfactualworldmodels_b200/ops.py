@@ -88,3 +88,30 @@ def fill_mask_tokens(mask_token, pos, perm, n_vis, x_full):
     _lib.check(lib.cwm_fill_mask_tokens(mask_token.data_ptr(), pos.data_ptr(), perm.data_ptr(), B, Ntot, n_vis, C,
                                         x_full.data_ptr(), _stream(x_full)))
     return x_full
+
+
+def attention_generic_f16(q, k, v, B, Nq, Nk, H, head_dim, q_head_stride=None, k_head_stride=None,
+                          v_head_stride=None):
+    """softmax(q k^T) v with independently strided operands (see cwm_b200.h).  q, k, v: 2-D f16 *views* whose row
+    stride is ``.stride(0)`` and whose first element is head 0 (q pre-scaled) -> f16 [B*Nq, H*head_dim]."""
+    _req_cuda(q, k, v)
+    lib = _lib.load()
+    out = torch.empty(B * Nq, H * head_dim, dtype=torch.float16, device=q.device)
+    nbytes = lib.cwm_attention_generic_workspace_bytes(B, Nq, Nk, H, head_dim)
+    ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=q.device)
+    hs = [head_dim if s is None else int(s) for s in (q_head_stride, k_head_stride, v_head_stride)]
+    _lib.check(lib.cwm_attention_generic_f16(q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0), k.stride(0),
+                                             v.stride(0), hs[0], hs[1], hs[2], B, Nq, Nk, H, head_dim,
+                                             out.data_ptr(), out.shape[1], ws.data_ptr(), ws.numel(), _stream(q)))
+    return out
+
+
+def fill_pad_rows(x, perm, perm_offset, first_pad_token, value=None):
+    """x fp32 [B, rows, C] in place: rows whose token id perm[b, perm_offset + j] >= first_pad_token <- value / 0."""
+    _req_cuda(x, perm, value)
+    lib = _lib.load()
+    B, rows, C = x.shape
+    _lib.check(lib.cwm_fill_pad_rows(x.data_ptr(), B, rows, C, perm.data_ptr(), perm.shape[1], int(perm_offset),
+                                     int(first_pad_token), value.data_ptr() if value is not None else None,
+                                     _stream(x)))
+    return x

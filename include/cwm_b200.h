@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define CWM_B200_ABI_VERSION 1
+#define CWM_B200_ABI_VERSION 2
 
 typedef void* cwm_stream_t; /* cudaStream_t */
 
@@ -63,14 +63,15 @@ int cwm_compact_mask(const uint8_t* mask, int B, int Ntot, int32_t* perm, int32_
  *   perm       as produced by cwm_compact_mask (row stride Ntot); rows_per_sample = Nvis entries are used
  *   mean/stdv  NULL, or per-channel HOST arrays [C] fp32 (they are constants of the caller, utils.py:12-13):
  *              value = (x - mean[c]) / stdv[c], same operation order as the reference
- *   out        f16 [B*rows_per_sample, K], K = C*pt*ph*pw ordered (c, kt, kh, kw) = Conv3d weight order */
+ *   out        f16 [B*rows_per_sample, K], K = C*pt*ph*pw ordered (c, kt, kh, kw) = Conv3d weight order
+ * Token ids >= (T/pt)*(H/ph)*(W/pw) are padding positions (conjoined_vmae.py:130-133): their rows are zero. */
 int cwm_patch_gather(const float* x, const int64_t xs[5], int B, int C, int T, int H, int W, int pt,
                      int ph, int pw, const int32_t* perm, int Ntot, int rows_per_sample,
                      const float* mean, const float* stdv, uint16_t* out, cwm_stream_t stream);
 
 /* ---- LayerNorm (a5/a8/a11) -----------------------------------------------------------------------
  * nn.LayerNorm(C, eps) over the last dim (cwm/models/VideoMAE/utils.py:130,136; vmae.py:84,206), fp32
- * statistics, f16 output (the operand of the following GEMM).
+ * statistics, f16 output (the operand of the following GEMM).  C % 4 == 0, C <= 1024.
  * Row mapping: output row m reads input row (m / grp_rows) * grp_stride + grp_offset + m % grp_rows when
  * grp_rows > 0 (used for `x[:, -return_token_num:]`, vmae.py:250-251), else row m. */
 int cwm_layernorm_f16(const float* x, int M, int C, const float* gamma, const float* beta, float eps,
@@ -107,10 +108,11 @@ int cwm_gemm_f16(const uint16_t* A, const uint16_t* W, int M, int N, int K, cons
                  cwm_stream_t stream);
 
 /* ---- attention (a6) --------------------------------------------------------------------------------
- * softmax(q k^T) v per (sample, head), unmasked, head_dim 64 (cwm/models/VideoMAE/utils.py:108-113); q is
- * already scaled (utils.py:97 is fused into the qkv GEMM epilogue).
- *   qkv  f16 [B, N, 3, H, 64]  (the layout `F.linear(...).reshape(B,N,3,H,-1)` has, utils.py:93-94)
- *   out  f16 [B, N, H*64]      (= `x.transpose(1,2).reshape(B,N,-1)`, utils.py:118)               */
+ * softmax(q k^T) v per (sample, head), unmasked (cwm/models/VideoMAE/utils.py:108-113); q is already scaled
+ * (utils.py:97 is fused into the qkv GEMM epilogue).  head_dim 64 (every RGB stream) runs the tcgen05 kernel;
+ * 32 / 96 / 128 / 192 are forwarded to cwm_attention_generic_f16.
+ *   qkv  f16 [B, N, 3, H, d]  (the layout `F.linear(...).reshape(B,N,3,H,-1)` has, utils.py:93-94)
+ *   out  f16 [B, N, H*d]      (= `x.transpose(1,2).reshape(B,N,-1)`, utils.py:118)               */
 int cwm_attention_f16(const uint16_t* qkv, int B, int N, int H, int head_dim, uint16_t* out,
                       cwm_stream_t stream);
 
@@ -182,8 +184,76 @@ int cwm_vmae_forward(const cwm_vmae_model* model, const float* x, const int64_t 
                      const float* norm_mean, const float* norm_std, const int32_t* perm, int Nvis, float* y,
                      void* workspace, size_t workspace_bytes, cwm_stream_t stream);
 
-/* Number of kernel launches the last cwm_vmae_forward on this thread enqueued (for bench accounting). */
+/* ---- generic small attention (a6 for the context stream, a15 cross-attention) ------------------------
+ * softmax(q k^T) v for head dims 32 / 64 / 96 / 128 / 192 with independently strided q, k, v:
+ *   q row (b, i), head h starts at q + (b*Nq + i)*ldq + h*q_head_stride;  k, v likewise over Nk rows.
+ *   out[(b*Nq + i)*ldo + h*head_dim + c], f16.   q must be pre-scaled.
+ * Used for (i) self-attention of the 25..50 IMU tokens, head dim 32 (cwm/models/VideoMAE/utils.py:87-121 as
+ * instantiated by conjoined_vmae.py:1198-1216) and (ii) both directions of BidirectionalCrossAttention
+ * (cwm/models/transformer.py:358-372): N x M ("trg") and M x N ("src", key axis split internally; needs workspace). */
+size_t cwm_attention_generic_workspace_bytes(int B, int Nq, int Nk, int H, int head_dim);
+int cwm_attention_generic_f16(const uint16_t* q, const uint16_t* k, const uint16_t* v, int ldq, int ldk, int ldv,
+                              int q_head_stride, int k_head_stride, int v_head_stride, int B, int Nq, int Nk,
+                              int H, int head_dim, uint16_t* out, int ldo, void* workspace, size_t workspace_bytes,
+                              cwm_stream_t stream);
+
+/* ---- a13: null (padding) tokens ------------------------------------------------------------------------
+ * PaddedVisionTransformer (cwm/models/VideoMAE/conjoined_vmae.py:125-165, :207-208): token ids >= first_pad_token
+ * in `perm` are padding positions.  For every sample b and every j in [0, rows) with
+ * perm[b*perm_stride + perm_offset + j] >= first_pad_token:   x[b, j, :] = value  (all zeros when value == NULL).
+ *   encoder input: value = null_token_enc (pad_and_mask_input, :130-133); output rows: value = NULL (:207-208). */
+int cwm_fill_pad_rows(float* x, int B, int rows, int C, const int32_t* perm, int perm_stride, int perm_offset,
+                      int first_pad_token, const float* value, cwm_stream_t stream);
+
+/* ---- one transformer block (a5-a7) ---------------------------------------------------------------------
+ * `Block.forward` (cwm/models/VideoMAE/utils.py:146-153, gamma_* = None) in place on the fp32 residual stream
+ * x [B*N, C]: x += proj(Attn(LN1(x))); x += fc2(GELU(fc1(LN2(x)))).  heads*head_dim is the inner attention width
+ * (== C for every shipped model).  head_dim 64 runs the tcgen05 attention kernel, 32/96/128/192 the generic one.
+ * The conjoined models interleave these with cross blocks (conjoined_vmae.py:543-576, :688-720). */
+size_t cwm_block_workspace_bytes(int B, int N, int C, int heads, int head_dim, int hidden);
+int cwm_block_forward(const cwm_block_weights* w, float* x, int B, int N, int C, int heads, int head_dim, int hidden,
+                      float ln_eps, float qk_scale, void* workspace, size_t workspace_bytes, cwm_stream_t stream);
+
+/* ---- a14/a15: one conjoining (cross-attention) block ----------------------------------------------------
+ * `CrossAttentionTransformerBlock.forward` with with_self_attention=False (cwm/models/transformer.py:559-583;
+ * gamma_1 = 0, norm1 = Identity, shortcut = Identity) around `BidirectionalCrossAttention.forward`
+ * (:314-378, shared_similarity=False, no qkv bias), in place on both fp32 residual streams:
+ *   qk, v = LN1c(x) W;  qk_s, v_s = LN1sc(src) W_s
+ *   x   += projection    (softmax(scale * qk[..., :hd] qk_s[..., :hd]^T) v_s)        [N x M attention per head]
+ *   src += projection_src(softmax(scale * qk_s[..., hd:] qk[..., hd:]^T) v)          [M x N attention per head]
+ *   x   += fc2(GELU(fc1(LN2(x))));  src += fc2_s(GELU(fc1_s(LN2s(src))))
+ * x [B*N, C], src [B*M, Cs]; inner width D = heads*head_dim.  f16 weights are [out, in] row-major. */
+typedef struct cwm_cross_block_weights {
+  const float *ln1_g, *ln1_b;         /* norm1_cross           [C]  */
+  const float *ln1s_g, *ln1s_b;       /* norm1_src_cross       [Cs] */
+  const uint16_t* w_qkv;              /* cat(cross_attention.qk.weight, cross_attention.v.weight)         f16 [3D, C]  */
+  const uint16_t* w_qkv_s;            /* cat(cross_attention.qk_src.weight, cross_attention.v_src.weight) f16 [3D, Cs] */
+  const uint16_t* w_proj;             /* cross_attention.projection.weight      f16 [C, D]  */
+  const float* b_proj;
+  const uint16_t* w_proj_s;           /* cross_attention.projection_src.weight  f16 [Cs, D] */
+  const float* b_proj_s;
+  const float *ln2_g, *ln2_b;         /* norm2      [C]  */
+  const float *ln2s_g, *ln2s_b;       /* norm2_src  [Cs] */
+  const uint16_t* w_fc1;              /* mlp.trg.layers.0.weight f16 [hidden, C] */
+  const float* b_fc1;
+  const uint16_t* w_fc2;              /* mlp.trg.layers.2.weight f16 [C, hidden] */
+  const float* b_fc2;
+  const uint16_t* w_fc1_s;            /* mlp.src.layers.0.weight f16 [hidden_s, Cs] */
+  const float* b_fc1_s;
+  const uint16_t* w_fc2_s;            /* mlp.src.layers.2.weight f16 [Cs, hidden_s] */
+  const float* b_fc2_s;
+} cwm_cross_block_weights;
+
+size_t cwm_cross_block_workspace_bytes(int B, int N, int M, int C, int Cs, int heads, int head_dim, int hidden,
+                                       int hidden_s);
+int cwm_cross_block_forward(const cwm_cross_block_weights* w, float* x, float* src, int B, int N, int M, int C,
+                            int Cs, int heads, int head_dim, int hidden, int hidden_s, float ln_eps, float scale,
+                            void* workspace, size_t workspace_bytes, cwm_stream_t stream);
+
+/* Number of kernel launches this thread enqueued through the library since the last cwm_vmae_forward began or
+ * cwm_launch_count_reset() was called (for bench accounting). */
 int cwm_last_forward_launches(void);
+int cwm_launch_count_reset(void);
 
 /* ---- per-kernel timing (bench.py's roofline numbers) -------------------------------------------------
  * Between cwm_profile_begin() and cwm_profile_end() every launch made through this library is bracketed by two

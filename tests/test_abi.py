@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_error_string():
     lib = _lib.load()
-    assert lib.cwm_abi_version() == 1
+    assert lib.cwm_abi_version() == 2
     assert isinstance(lib.cwm_last_error(), bytes)
 
 
@@ -42,7 +42,7 @@ def test_argument_validation_without_gpu():
     lib = _lib.load()
     rc = lib.cwm_compact_mask(None, 1, 8, None, None, None, None)
     assert rc == -1 and b"null pointer" in lib.cwm_last_error()
-    rc = lib.cwm_attention_f16(1, 1, 8, 2, 32, 1, None)
+    rc = lib.cwm_attention_f16(16, 1, 8, 2, 40, 16, None)
     assert rc == -3 and b"head_dim" in lib.cwm_last_error()
     e = _lib.GemmEpilogue()
     e.mode, e.out = 0, 1

@@ -230,3 +230,96 @@ def test_unpatchify_scatter_bit_exact(cfg):
     _, inv, nvis = ops.compact_mask(mask.to(DEV))
     got = prediction.unpatchify_scatter(y.to(DEV), x.to(DEV), inv, int(nvis[0]), ps)
     assert torch.equal(got.cpu(), want)   # pure data movement: bit-exact
+
+
+# ---------------------------------------------------------------- config 5 kernels (a13-a16)
+@pytest.mark.parametrize("M,C", [(50, 64), (33, 192), (7, 4), (129, 96)])
+def test_layernorm_generic_widths(M, C):
+    g = torch.Generator().manual_seed(M * 7 + C)
+    x = torch.randn(M, C, generator=g) * 2 - 0.3
+    gamma = torch.rand(C, generator=g) + 0.5
+    beta = torch.randn(C, generator=g)
+    want = F.layer_norm(x, (C,), gamma, beta, 1e-6)
+    got = ops.layernorm_f16(x.to(DEV), gamma.to(DEV), beta.to(DEV), 1e-6).cpu().float()
+    assert (got - want).abs().max().item() <= 4e-3 + 1e-3 * want.abs().max().item()
+
+
+def _attn_ref(q, k, v):
+    """fp32 softmax(q k^T) v on f16-rounded operands; q,k,v [B,H,N,d]."""
+    s = q.float() @ k.float().transpose(-1, -2)
+    return s.softmax(-1) @ v.float()
+
+
+@pytest.mark.parametrize("B,Nq,Nk,H,d", [
+    (2, 25, 25, 12, 32), (3, 50, 50, 6, 32), (2, 26, 26, 4, 32), (1, 1, 1, 12, 32),   # context self-attention
+    (2, 788, 25, 4, 192), (2, 1600, 50, 4, 96), (1, 70, 5, 4, 64), (2, 100, 1, 4, 192),  # cross, trg direction
+    (2, 25, 3140, 4, 192), (2, 50, 6336, 4, 96), (1, 5, 72, 4, 32), (2, 1, 784, 4, 192),  # cross, src direction
+    (1, 300, 300, 2, 128),
+])
+def test_attention_generic(B, Nq, Nk, H, d):
+    g = torch.Generator().manual_seed(Nq * 31 + Nk)
+    q = (torch.randn(B, Nq, H, d, generator=g) * d ** -0.25).to(torch.float16)
+    k = (torch.randn(B, Nk, H, d, generator=g) * d ** -0.25).to(torch.float16)
+    v = torch.randn(B, Nk, H, d, generator=g).to(torch.float16)
+    want = _attn_ref(q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3), v.permute(0, 2, 1, 3))   # [B,H,Nq,d]
+    want = want.permute(0, 2, 1, 3).reshape(B * Nq, H * d)
+    got = ops.attention_generic_f16(q.reshape(B * Nq, H * d).to(DEV), k.reshape(B * Nk, H * d).to(DEV),
+                                    v.reshape(B * Nk, H * d).to(DEV), B, Nq, Nk, H, d).cpu().float()
+    # P is rounded to f16 for the PV product (2^-11 relative per term), output rounded to f16
+    err = (got - want).abs()
+    assert err.max().item() <= 6e-3 and err.mean().item() <= 6e-4, (err.max().item(), err.mean().item())
+
+
+def test_attention_generic_cross_layout():
+    """The interleaved [qk | v] layout of BidirectionalCrossAttention (transformer.py:333-365): head h of qk owns
+    columns [2*hd*h, 2*hd*(h+1)), first hd for the trg similarity, last hd for the src similarity."""
+    B, N, M, H, hd = 2, 300, 25, 4, 96
+    D = H * hd
+    g = torch.Generator().manual_seed(5)
+    qkv = (torch.randn(B * N, 3 * D, generator=g) * 0.3).to(torch.float16)
+    qkv_s = (torch.randn(B * M, 3 * D, generator=g) * 0.3).to(torch.float16)
+    qk = qkv[:, :2 * D].reshape(B, N, H, 2 * hd).permute(0, 2, 1, 3)
+    qk_s = qkv_s[:, :2 * D].reshape(B, M, H, 2 * hd).permute(0, 2, 1, 3)
+    v = qkv[:, 2 * D:].reshape(B, N, H, hd).permute(0, 2, 1, 3)
+    v_s = qkv_s[:, 2 * D:].reshape(B, M, H, hd).permute(0, 2, 1, 3)
+    y = _attn_ref(qk[..., :hd], qk_s[..., :hd], v_s).permute(0, 2, 1, 3).reshape(B * N, D)
+    y_s = _attn_ref(qk_s[..., hd:], qk[..., hd:], v).permute(0, 2, 1, 3).reshape(B * M, D)
+    qd, sd = qkv.to(DEV), qkv_s.to(DEV)
+    got = ops.attention_generic_f16(qd, sd, sd[:, 2 * D:], B, N, M, H, hd, 2 * hd, 2 * hd, hd).cpu().float()
+    got_s = ops.attention_generic_f16(sd[:, hd:], qd[:, hd:], qd[:, 2 * D:], B, M, N, H, hd, 2 * hd, 2 * hd,
+                                      hd).cpu().float()
+    assert (got - y).abs().max().item() <= 6e-3
+    assert (got_s - y_s).abs().max().item() <= 6e-3
+
+
+def test_patch_gather_imu_scalar_and_pad_tokens():
+    """IMU "video" [B, 6, 400, 1, 1] with a (16,1,1) tubelet (conjoined_vmae.py:1013-1038): scalar gather path; token
+    ids >= 25 are padding positions and give zero rows (conjoined_vmae.py:130-133)."""
+    B, C, L, pt = 3, 6, 400, 16
+    g = torch.Generator().manual_seed(9)
+    imu = torch.randn(B, C, L, generator=g)
+    perm = torch.stack([torch.randperm(25 + 5, generator=g) for _ in range(B)]).to(torch.int32)
+    rows = 12
+    a = ops.patch_gather(imu.to(DEV)[..., None, None], perm.to(DEV), rows, (pt, 1, 1)).cpu()
+    tok = imu.reshape(B, C, L // pt, pt).permute(0, 2, 1, 3).reshape(B, L // pt, C * pt)   # (c, kt) order
+    for b in range(B):
+        for j in range(rows):
+            t = int(perm[b, j])
+            want = tok[b, t].to(torch.float16) if t < 25 else torch.zeros(C * pt, dtype=torch.float16)
+            assert torch.equal(a[b * rows + j], want)
+
+
+def test_fill_pad_rows():
+    B, rows, C, first_pad = 3, 10, 64, 20
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, rows, C, generator=g)
+    perm = torch.stack([torch.randperm(28, generator=g) for _ in range(B)]).to(torch.int32)
+    val = torch.randn(C, generator=g)
+    for value in (val, None):
+        for off in (0, 7):
+            got = ops.fill_pad_rows(x.clone().to(DEV), perm.to(DEV), off, first_pad,
+                                    None if value is None else value.to(DEV)).cpu()
+            want = x.clone()
+            sel = perm[:, off:off + rows] >= first_pad
+            want[sel] = 0.0 if value is None else value
+            assert torch.equal(got, want)
