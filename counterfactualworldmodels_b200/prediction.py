@@ -11,6 +11,7 @@ import torch
 from torch import nn
 
 from . import _lib
+from .conjoined_vmae import ConjoinedPretrainVisionTransformer, PaddedVisionTransformer
 from .vmae import (IMAGENET_DEFAULT_MEAN, IMAGENET_DEFAULT_STD, PretrainVisionTransformer, compact_mask)
 
 
@@ -152,6 +153,16 @@ class PredictorBasedGenerator(nn.Module):
         mask = self.mask_generator(x).view(x.size(0), -1).to(x.device)
         return self.mask_rectangularizer(mask)
 
+    def reset_padding_masks(self):
+        """prediction.py:121-129."""
+        if hasattr(self.predictor, 'padding_mask') and not hasattr(self.predictor, 'main_stream'):
+            self.predictor._reset_padding_mask()
+        elif hasattr(self.predictor, 'main_stream'):
+            if hasattr(self.predictor.main_stream, 'padding_mask'):
+                self.predictor.main_stream._reset_padding_mask()
+            if hasattr(self.predictor.context_stream, 'padding_mask'):
+                self.predictor.context_stream._reset_padding_mask()
+
     # ---- a1 ----
     def _preprocess(self, x):
         """prediction.py:304-312 (kept for callers that want the normalised tensor; ``predict`` itself fuses the
@@ -186,7 +197,9 @@ class PredictorBasedGenerator(nn.Module):
         self.inp_shape = x.shape
         self.set_image_size(x.shape[-2:])
         mask = mask if (x.size(0) == 1) else self.mask_rectangularizer(mask)
-        if isinstance(self.predictor, PretrainVisionTransformer):
+        if isinstance(self.predictor, (ConjoinedPretrainVisionTransformer, PaddedVisionTransformer)):
+            y = self._predict_padded_or_conjoined(x, mask, *args, **kwargs)
+        elif isinstance(self.predictor, PretrainVisionTransformer):
             xin = x.transpose(self.t_dim, self.c_dim) if self.t_dim != 1 else x  # a view, never materialised
             norm = (IMAGENET_DEFAULT_MEAN, IMAGENET_DEFAULT_STD) if self.imagenet_normalize_inputs else None
             y = self.predictor(xin, mask, *args, input_norm=norm, **kwargs)
@@ -199,7 +212,43 @@ class PredictorBasedGenerator(nn.Module):
         if frame is not None:
             frame = frame % y.size(1)
             y = y[:, frame:frame + 1]
+        if reset_masks:
+            self.reset_padding_masks()
         return y
+
+    def _predict_padded_or_conjoined(self, x, mask, *args, **kwargs):
+        """prediction.py:412-446 for padded / conjoined predictors: the rows of the (max - min) padding positions are
+        stripped (:424-432) and the main-stream frames + mask go to `pred_patches_to_video` (:435-446).  The imagenet
+        normalisation is fused into the main stream's patch gather and the visible patches are copied from the raw
+        input (the reference round-trips them through normalise -> unnormalise, a <= 6e-8 difference)."""
+        P = self.predictor
+        is_padded = hasattr(P, 'padding_mask') and bool((mask.sum(-1).amax() != mask.sum(-1).amin()).item())
+        if is_padded:
+            print("Warning: passed a batch of images with different numbers of visible tokens.")
+        xin = x.transpose(self.t_dim, self.c_dim) if self.t_dim != 1 else x
+        norm = (IMAGENET_DEFAULT_MEAN, IMAGENET_DEFAULT_STD) if self.imagenet_normalize_inputs else None
+        y = P(xin, mask, *args, input_norm=norm, **kwargs)
+        conjoined = hasattr(P, 'main_stream')
+        if hasattr(P, 'padding_mask'):
+            ms = P.main_stream if conjoined else P
+            num_pad = ms.max_padding_tokens - ms.min_padding_tokens
+            y = y[:, :-num_pad]
+        if len(y.shape) == 5:
+            return y
+        if conjoined:
+            (_x, _mask, _), _ = P.get_stream_inputs(xin, mask.reshape(x.shape[0], -1), *args,
+                                                    **{k: v for k, v in kwargs.items()
+                                                       if k in ('timestamps', 'x_context', 'mask_context')})
+            if self.t_dim == 2:
+                _x = _x.transpose(1, 2)
+            patch_size = P.main_stream.patch_size
+        else:
+            _x, _mask, patch_size = x, mask, P.patch_size
+        _, inv, nvis = compact_mask(_mask.reshape(_x.shape[0], -1).to(_x.device))
+        counts = nvis.cpu()
+        if not bool((counts == counts[0]).all()):
+            raise RuntimeError("shape mismatch: rows of the mask have different numbers of masked tokens")
+        return unpatchify_scatter(y, _x, inv, int(counts[0]), patch_size)
 
     def forward(self, x, mask=None, frame=None, *args, **kwargs):
         return self.predict(x, mask, frame, *args, **kwargs)
@@ -231,5 +280,19 @@ class PredictorBasedGenerator(nn.Module):
         batch_size = max(1, batch_size)
         ys = []
         for b0 in range(0, S, batch_size):
-            ys.append(self.predict(x[b0:b0 + batch_size], mask=masks[b0:b0 + batch_size], frame=frame, **kwargs))
+            xb = x[b0:b0 + batch_size]
+            ys.append(self.predict(xb, mask=masks[b0:b0 + batch_size], frame=frame, reset_masks=True,
+                                   **self.sample_tile_all_tensors(xb.size(0), **kwargs)))
+            self.reset_padding_masks()
         return torch.cat(ys, 0)
+
+    def sample_tile(self, z, num_samples):
+        """prediction.py:484-487."""
+        S = num_samples
+        rank = len(z.shape)
+        return z[:, None].expand(-1, S, *([-1] * (rank - 1))).reshape(-1, *z.shape[1:])
+
+    def sample_tile_all_tensors(self, num_samples, **kwargs):
+        """prediction.py:489-495: per-image tensors (e.g. the IMU context) are repeated for every sample of a chunk."""
+        return {kw: self.sample_tile(val, num_samples) if isinstance(val, torch.Tensor) else val
+                for kw, val in kwargs.items()}

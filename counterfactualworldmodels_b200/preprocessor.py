@@ -1,0 +1,185 @@
+"""Stream preprocessors of the conjoined models (``cwm/models/preprocessor.py``): which frames of the input video a
+stream sees and how the IMU sequence is shaped.  Pure index-select / reshape -- no arithmetic -- so they stay on the
+host side.  The RAFT-based ``FramePairFlow`` family is out of scope (SURVEY.md section 2,
+rows 5 and 14): ``flowback_rgb01`` & co. need a caller-supplied flow network, see ``FramePairFlow``.
+"""
+import copy
+from functools import partial
+
+import torch
+import torch.nn as nn
+
+from .vmae import IMAGENET_DEFAULT_MEAN, IMAGENET_DEFAULT_STD
+
+
+class Preprocessor(nn.Module):
+    """preprocessor.py:18-136: select ``frames_list`` of the input along the temporal dim."""
+    num_channels = None
+
+    def __init__(self, frames_list=None, temporal_dim=2, channel_dim=None, preproc_func=None, preproc_kwargs={},
+                 num_frames=None, num_channels=None, stack=False, unnormalize=False, *args, **kwargs):
+        super().__init__()
+        if stack:
+            raise NotImplementedError("stacked frame inputs (rgb01stack) are not used by any CWM factory")
+        if preproc_func is not None:
+            raise NotImplementedError("custom preproc_func")
+        self.set_frames_list(frames_list)
+        self.temporal_dim = temporal_dim
+        self.channel_dim = (1 if temporal_dim == 2 else 2) if channel_dim is None else channel_dim
+        assert self.channel_dim != self.temporal_dim
+        self.num_frames = num_frames
+        if num_channels is not None:
+            self.num_channels = num_channels
+        self.stack = False
+        # get_preprocessor(name, unnormalize=True) composes imagenet_unnormalize (preprocessor.py:364-367)
+        self.unnormalize = unnormalize
+
+    @property
+    def t_dim(self):
+        return self.temporal_dim
+
+    @property
+    def c_dim(self):
+        return self.channel_dim
+
+    def set_frames_list(self, frames_list):
+        if frames_list is not None and isinstance(frames_list, int):
+            frames_list = [frames_list, frames_list + 1]
+        elif frames_list is not None and not isinstance(frames_list, list):
+            frames_list = list(frames_list)
+        self.frames_list = frames_list
+        if self.frames_list is not None:
+            self.num_input_frames = len(frames_list)
+
+    def get_num_frames(self):
+        if self.num_frames is None:
+            return len(self.frames_list) if self.frames_list is not None else None
+        return self.num_frames
+
+    def get_num_channels(self, x):
+        return x.shape[self.c_dim] if self.c_dim in range(len(x.shape)) else 0
+
+    def set_input_dims(self, x):
+        self.num_input_channels = self.get_num_channels(x)
+        self.T = x.shape[self.t_dim]
+        if self.frames_list is None:
+            self.frames_list = list(range(self.T))
+            self.num_input_frames = self.T
+        self.frames_list = [fr % self.T for fr in self.frames_list]
+
+    def set_output_dims(self, x):
+        if self.num_channels is None:
+            self.num_channels = self.get_num_channels(x)
+        else:
+            assert self.num_channels == self.get_num_channels(x), (self.num_channels, self.get_num_channels(x))
+        if self.num_frames is None:
+            self.num_frames = x.shape[self.t_dim]
+        else:
+            assert self.num_frames == x.shape[self.t_dim]
+
+    def get_input_frames(self, x):
+        idx = torch.tensor(self.frames_list).long().to(x.device)
+        return torch.index_select(x, dim=self.temporal_dim, index=idx)
+
+    def get_output_frames(self, y, temporal_dim=None):
+        idx = torch.tensor(self.frames_list[-self.num_frames:]).long().to(y.device)
+        return torch.index_select(y, dim=self.t_dim if temporal_dim is None else temporal_dim, index=idx)
+
+    def forward(self, x, *args, **kwargs):
+        self.set_input_dims(x)
+        x = self.get_input_frames(x)
+        if self.unnormalize:
+            # imagenet_unnormalize (models/utils.py:23-31).  No shipped factory takes this branch for an RGB stream
+            # (imu400_base_4x4 passes unnormalize=False, conjoined_vmae.py:1236), so it is plain host-side input
+            # construction rather than a fused kernel.
+            shape = [1] * x.dim()
+            shape[self.c_dim] = 3
+            mean = torch.as_tensor(IMAGENET_DEFAULT_MEAN, device=x.device, dtype=x.dtype).view(shape)
+            std = torch.as_tensor(IMAGENET_DEFAULT_STD, device=x.device, dtype=x.dtype).view(shape)
+            x = x * std + mean
+        self.set_output_dims(x)
+        return x
+
+
+class IMU(Preprocessor):
+    """preprocessor.py:169-206: [B, 6, L] -> [B, 6, L, 1, 1]; no frames."""
+    num_frames = None
+    num_channels = 6
+
+    def __init__(self, sequence_length=None, frames_list=None, temporal_dim=2, channel_dim=None, *args, **kwargs):
+        super().__init__(frames_list=frames_list, temporal_dim=temporal_dim, channel_dim=channel_dim)
+        self.num_frames = None
+        self.sequence_length = sequence_length
+
+    def set_output_dims(self, x):
+        super().set_output_dims(x)
+        self.num_frames = None
+        if self.sequence_length is not None:
+            assert self.sequence_length == x.shape[self.t_dim], (self.sequence_length, x.shape[self.t_dim])
+
+    def get_sequence_length(self):
+        return self.sequence_length
+
+    def forward(self, imu=None, timestamps=None, *args, **kwargs):
+        if imu is None:
+            return None
+        imu = imu.unsqueeze(-1).unsqueeze(-1)
+        self.set_input_dims(imu)
+        self.set_output_dims(imu)
+        return imu
+
+
+class FramePairFlow(Preprocessor):
+    """preprocessor.py:208-285 computes RAFT optical flow inside the model (out of scope: SURVEY.md section 2 row 14).
+    This holder keeps the frame / channel bookkeeping (2 flow channels, +2 backward, +3 rgb; one output frame) and
+    delegates the image -> stream-input map to a caller-supplied ``flow_model`` callable
+    ``flow_model(x [B,C,T,H,W]) -> [B, num_channels, 1, H, W]`` (e.g. the reference's own FlowBackRGB01 module)."""
+    num_channels = 2
+
+    def __init__(self, flow_model=None, concat_backward=False, concat_rgb=False, frames_list=None, temporal_dim=2,
+                 **kwargs):
+        super().__init__(frames_list=frames_list, temporal_dim=temporal_dim)
+        self.flow_model = flow_model
+        self.num_channels = 2 + (2 if concat_backward else 0) + (3 if concat_rgb else 0)
+        self.unnormalize = False
+        if self.frames_list is not None:
+            self.num_frames = self.num_input_frames - 1
+
+    def get_num_frames(self):
+        if self.num_frames is None:
+            return len(self.frames_list) - 1 if self.frames_list is not None else None
+        return self.num_frames
+
+    def forward(self, x, *args, **kwargs):
+        if self.flow_model is None:
+            raise NotImplementedError(
+                "flow-based stream inputs need an optical-flow network (RAFT is out of scope of the B200 path): pass "
+                "main_input_kwargs={'flow_model': callable} producing the [B, %d, 1, H, W] stream input" %
+                self.num_channels)
+        self.set_input_dims(x)
+        y = self.flow_model(self.get_input_frames(x))
+        self.set_output_dims(y)
+        return y
+
+
+_REGISTRY = {
+    'rgb01': partial(Preprocessor, num_channels=3, frames_list=[0, 1]),
+    'rgb02': partial(Preprocessor, num_channels=3, frames_list=[0, -1]),
+    'rgb0': partial(Preprocessor, num_channels=3, frames_list=[0]),
+    'rgb1': partial(Preprocessor, num_channels=3, frames_list=[1]),
+    'rgb12': partial(Preprocessor, num_channels=3, frames_list=[1, -1]),
+    'rgb012': partial(Preprocessor, num_channels=3, frames_list=[0, 1, -1]),
+    'flow01': partial(FramePairFlow, frames_list=[0, 1]),
+    'flow_rgb01': partial(FramePairFlow, frames_list=[0, 1], concat_rgb=True),
+    'flowback01': partial(FramePairFlow, frames_list=[0, 1], concat_backward=True),
+    'flowback_rgb01': partial(FramePairFlow, frames_list=[0, 1], concat_backward=True, concat_rgb=True),
+    'imu': IMU,
+}
+
+
+def get_preprocessor(name, temporal_dim=2, unnormalize=True, **kwargs):
+    """preprocessor.py:364-387."""
+    kwargs = copy.copy(kwargs)
+    if 'imu' not in name:
+        kwargs['unnormalize'] = unnormalize
+    return _REGISTRY[name](temporal_dim=temporal_dim, **kwargs)

@@ -72,9 +72,9 @@ def init_weights_(model, seed=0, style="reference"):
     with torch.no_grad():
         for name in sorted(sd.keys()):
             t = sd[name]
-            if name == "mask_token":
+            if name.endswith(("mask_token", "null_token_enc", "null_token_dec", "dummy_token")):
                 v = torch.empty(t.shape).normal_(0, 0.02, generator=g).clamp_(-0.02, 0.02)
-            elif name.endswith("norm1.weight") or name.endswith("norm2.weight") or name.endswith("norm.weight"):
+            elif t.dim() == 1 and name.endswith(".weight"):  # LayerNorm weights (norm1 / norm2 / norm / norm*_cross)
                 v = torch.ones(t.shape)
                 if style == "perturbed":
                     v = v + torch.empty(t.shape).uniform_(-0.2, 0.2, generator=g)
@@ -136,3 +136,87 @@ def make_mask(B, msize, num_clumps=2, clump=2, seed=0):
             cy, cx = (c // gw) * clump, (c % gw) * clump
             mask[b, -1, cy:cy + clump, cx:cx + clump] = False
     return mask.reshape(B, -1)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# conjoined / padded (IMU-conditioned) models -- SURVEY.md section 8a rows a13-a17, BASELINE config 5
+# ---------------------------------------------------------------------------------------------------------
+# name -> description of a conjoined model small enough for the CPU oracle; "imu400_base_4x4" is the real factory
+CONJOINED = {
+    # padded main (4x4 patches, 32 px, up to 8 null tokens) + padded IMU context (80 samples -> 5 tokens, 5 null tokens)
+    "conj_padded_small": dict(
+        kind="padded", img_size=32, patch_size=(4, 4), enc=(256, 4, 4), dec=(128, 2, 2), ctx_enc_dim=128,
+        ctx_dec_dim=64, seq_len=80, main_pad=8, ctx_pad=5, enc_layers=[0, 3], dec_layers=True, main_chans=3,
+        main_frames=[0, 1]),
+    # non-padded, dummy-token IMU context, 7-channel single-frame main stream (the flow2imu topology, a17)
+    "conj_flow2imu_small": dict(
+        kind="full", img_size=32, patch_size=(8, 8), enc=(256, 3, 4), dec=(128, 2, 2), ctx_enc_dim=128,
+        ctx_dec_dim=64, seq_len=80, main_pad=0, ctx_pad=0, enc_layers=[0, -1], dec_layers=True, main_chans=7,
+        main_frames=[1]),
+}
+
+
+def build_conjoined(ns, name, preproc_ns=None):
+    """Builds the conjoined model `name` from the classes of module `ns` (ours: counterfactualworldmodels_b200.
+    conjoined_vmae; or the reference's cwm.models.VideoMAE.conjoined_vmae -- same constructor signatures)."""
+    import copy
+    from functools import partial
+    import torch.nn as nn
+    if name == "imu400_base_4x4":
+        return ns.imu400_base_4x4patch_2frames_1tube()
+    c = CONJOINED[name]
+    (Ce, Le, He), (Cd, Ld, Hd) = c["enc"], c["dec"]
+    common = dict(img_size=c["img_size"], patch_size=c["patch_size"], encoder_embed_dim=Ce, encoder_depth=Le,
+                  encoder_num_heads=He, encoder_num_classes=0, decoder_embed_dim=Cd, decoder_num_heads=Hd,
+                  decoder_depth=Ld, mlp_ratio=4, qkv_bias=True, norm_layer=partial(nn.LayerNorm, eps=1e-6),
+                  conjoin_encoder_layers=c["enc_layers"], conjoin_decoder_layers=c["dec_layers"], context_input='imu')
+    ctx_kw = copy.deepcopy(ns.imu400_encoder_kwargs)
+    ctx_kw.update(dict(encoder_embed_dim=c["ctx_enc_dim"], decoder_embed_dim=c["ctx_dec_dim"],
+                       sequence_length=c["seq_len"]))
+    main_kw = copy.deepcopy(ns.rgb_encoder_kwargs)
+    if preproc_ns is None:
+        import importlib
+        preproc_ns = importlib.import_module(ns.__name__.rsplit(".", 1)[0] + ".preprocessor") \
+            if ns.__name__.startswith("counterfactualworldmodels_b200") else importlib.import_module("cwm.models.preprocessor")
+    if c["main_chans"] == 3:
+        main_input, main_input_kwargs = 'rgb01', {'unnormalize': False}
+    else:  # a pass-through of frame 1 of a 7-channel input stands in for the RAFT-based 'flowback_rgb01' preprocessor
+        main_input = partial(preproc_ns.Preprocessor, num_channels=c["main_chans"], frames_list=c["main_frames"])
+        main_input_kwargs = {}
+    if c["kind"] == "padded":
+        main_kw.update(dict(min_padding_tokens=0, max_padding_tokens=c["main_pad"]))
+        ctx_kw.update(dict(min_padding_tokens=0, max_padding_tokens=c["ctx_pad"], concat_dummy_token=False))
+        return ns.ConjoinedPaddedVisionTransformer(
+            main_model_func=ns.PaddedVisionTransformer, main_model_kwargs=main_kw, main_input=main_input,
+            main_input_kwargs=main_input_kwargs, context_model_func=ns.PaddedVisionTransformer,
+            context_model_kwargs=ctx_kw, **common)
+    return ns.ConjoinedPretrainVisionTransformer(
+        num_frames=2, main_model_kwargs=main_kw, main_input=main_input, main_input_kwargs=main_input_kwargs,
+        context_model_kwargs=ctx_kw, **common)
+
+
+def conjoined_oracle_cfg(name, model=None):
+    """Structure description `oracle/conjoined_oracle.py` needs (it works on a bare state_dict)."""
+    if name == "imu400_base_4x4":
+        return dict(main=dict(enc_heads=12, dec_heads=6, max_pad=64, min_pad=0, pos="sinusoid", eps=1e-6),
+                    ctx=dict(enc_heads=12, dec_heads=6, max_pad=25, min_pad=0, pos="torch", dummy=False, eps=1e-6),
+                    enc_pairs=[(0, 0), (3, 3), (6, 6), (9, 9)], dec_pairs=[(0, 0), (1, 1), (2, 2), (3, 3)],
+                    cross_heads=4, eps=1e-6, patch_size=(1, 4, 4))
+    c = CONJOINED[name]
+    Le, Ld = c["enc"][1], c["dec"][1]
+    enc_pairs = [(l % Le, l % Le) for l in c["enc_layers"]]
+    dec_pairs = [(l, l) for l in range(Ld)] if c["dec_layers"] is True else [(l % Ld, l % Ld) for l in c["dec_layers"]]
+    return dict(main=dict(enc_heads=c["enc"][2], dec_heads=c["dec"][2], max_pad=c["main_pad"], min_pad=0,
+                          pos="sinusoid", eps=1e-6),
+                ctx=dict(enc_heads=c["enc"][2], dec_heads=c["dec"][2], max_pad=c["ctx_pad"], min_pad=0, pos="torch",
+                         dummy=(c["kind"] == "full"), eps=1e-6),
+                enc_pairs=enc_pairs, dec_pairs=dec_pairs, cross_heads=4, eps=1e-6,
+                patch_size=(1,) + tuple(c["patch_size"]))
+
+
+def make_imu(B, seq_len, seed=0, channels=6):
+    """Synthetic IMU sequence [B, 6, L] (unit-variance noise plus a slow drift)."""
+    g = torch.Generator().manual_seed(3000 + seed)
+    t = torch.linspace(0, 1, seq_len)
+    return torch.randn(B, channels, seq_len, generator=g) * 0.5 + torch.sin(6.0 * t)[None, None] * \
+        torch.randn(B, channels, 1, generator=g)

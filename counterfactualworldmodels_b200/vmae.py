@@ -216,6 +216,43 @@ class PretrainVisionTransformerDecoder(nn.Module):
         _no_eager("PretrainVisionTransformerDecoder")
 
 
+class _Packer:
+    """Collects device copies of parameters (fp32 as is, GEMM weights as f16) and keeps them alive."""
+
+    def __init__(self, device):
+        self.device = device
+        self.keep = []
+
+    def f32(self, t):
+        t = t.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        self.keep.append(t)
+        return t.data_ptr()
+
+    def f16(self, t):
+        t = t.detach().to(device=self.device, dtype=torch.float32).contiguous().to(torch.float16)
+        self.keep.append(t)
+        return t.data_ptr()
+
+    def block_array(self, blocks):
+        arr = (_lib.BlockWeights * max(1, len(blocks)))()
+        for i, blk in enumerate(blocks):
+            w = arr[i]
+            w.ln1_g, w.ln1_b = self.f32(blk.norm1.weight), self.f32(blk.norm1.bias)
+            w.w_qkv = self.f16(blk.attn.qkv.weight)
+            if blk.attn.q_bias is not None:
+                # qkv_bias = cat(q_bias, zeros_like(v_bias), v_bias)  (utils.py:89-91)
+                w.b_qkv = self.f32(torch.cat([blk.attn.q_bias.detach(), torch.zeros_like(blk.attn.v_bias),
+                                              blk.attn.v_bias.detach()]))
+            else:
+                w.b_qkv = None
+            w.w_proj, w.b_proj = self.f16(blk.attn.proj.weight), self.f32(blk.attn.proj.bias)
+            w.ln2_g, w.ln2_b = self.f32(blk.norm2.weight), self.f32(blk.norm2.bias)
+            w.w_fc1, w.b_fc1 = self.f16(blk.mlp.fc1.weight), self.f32(blk.mlp.fc1.bias)
+            w.w_fc2, w.b_fc2 = self.f16(blk.mlp.fc2.weight), self.f32(blk.mlp.fc2.bias)
+        self.keep.append(arr)
+        return arr
+
+
 class _Engine:
     """Device-side state of one model: f16 copies of the GEMM weights, fused qkv biases, positional tables, the
     ``cwm_vmae_model`` struct and a growable workspace.  Rebuilt whenever a parameter's storage or version
@@ -240,36 +277,8 @@ class _Engine:
         return self.model
 
     def _build(self, m, device):
-        keep = []
-
-        def f32(t):
-            t = t.detach().to(device=device, dtype=torch.float32).contiguous()
-            keep.append(t)
-            return t.data_ptr()
-
-        def f16(t):
-            t = t.detach().to(device=device, dtype=torch.float32).contiguous().to(torch.float16)
-            keep.append(t)
-            return t.data_ptr()
-
-        def block_array(blocks):
-            arr = (_lib.BlockWeights * max(1, len(blocks)))()
-            for i, blk in enumerate(blocks):
-                w = arr[i]
-                w.ln1_g, w.ln1_b = f32(blk.norm1.weight), f32(blk.norm1.bias)
-                w.w_qkv = f16(blk.attn.qkv.weight)
-                if blk.attn.q_bias is not None:
-                    # qkv_bias = cat(q_bias, zeros_like(v_bias), v_bias)  (utils.py:89-91)
-                    w.b_qkv = f32(torch.cat([blk.attn.q_bias.detach(), torch.zeros_like(blk.attn.v_bias),
-                                             blk.attn.v_bias.detach()]))
-                else:
-                    w.b_qkv = None
-                w.w_proj, w.b_proj = f16(blk.attn.proj.weight), f32(blk.attn.proj.bias)
-                w.ln2_g, w.ln2_b = f32(blk.norm2.weight), f32(blk.norm2.bias)
-                w.w_fc1, w.b_fc1 = f16(blk.mlp.fc1.weight), f32(blk.mlp.fc1.bias)
-                w.w_fc2, w.b_fc2 = f16(blk.mlp.fc2.weight), f32(blk.mlp.fc2.bias)
-            keep.append(arr)
-            return arr
+        pk = _Packer(device)
+        keep, f32, f16, block_array = pk.keep, pk.f32, pk.f16, pk.block_array
 
         enc, dec = m.encoder, m.decoder
         s = _lib.VmaeModel()
@@ -388,10 +397,8 @@ class PretrainVisionTransformer(nn.Module):
         super().__init__()
         if main_input is not None:
             raise NotImplementedError("main_input preprocessors belong to the conjoined models (SURVEY 8a, a17)")
-        if encoder_func is not PretrainVisionTransformerEncoder:
-            raise NotImplementedError("custom encoder_func")
-        if spacetime_separable_pos_embed:
-            raise NotImplementedError("spacetime_separable_pos_embed is dead code in the reference (vmae.py:422-441)")
+        if not (isinstance(encoder_func, type) and issubclass(encoder_func, PretrainVisionTransformerEncoder)):
+            raise NotImplementedError("encoder_func must be PretrainVisionTransformerEncoder or a subclass (ImuEncoder)")
         if decoder_depth <= 0:
             raise NotImplementedError("decoder_depth=0 (encoder-only mode) is not exercised by any CWM factory")
         if drop_rate or attn_drop_rate or drop_path_rate:
@@ -401,7 +408,7 @@ class PretrainVisionTransformer(nn.Module):
         enc_kwargs = dict(encoder_block_kwargs, flash_attention=use_flash_attention)
         dec_kwargs = dict(decoder_block_kwargs, flash_attention=use_flash_attention)
         self.get_main_input = None
-        self.encoder = PretrainVisionTransformerEncoder(
+        self.encoder = encoder_func(
             img_size=img_size, patch_size=patch_size, in_chans=encoder_in_chans, num_classes=encoder_num_classes,
             embed_dim=encoder_embed_dim, depth=encoder_depth, num_heads=encoder_num_heads, mlp_ratio=mlp_ratio,
             qkv_bias=qkv_bias, qk_scale=qk_scale, drop_rate=drop_rate, attn_drop_rate=attn_drop_rate,
@@ -420,13 +427,22 @@ class PretrainVisionTransformer(nn.Module):
         self.encoder_to_decoder = nn.Linear(encoder_embed_dim, decoder_embed_dim, bias=False)
         self.mask_token = nn.Parameter(torch.zeros(1, 1, decoder_embed_dim))
         self._learnable_pos_embed = False
-        self._spacetime_separable_pos_embed = False
+        # The "spacetime separable" branch of the reference is dead code (vmae.py:422-441 would NameError on
+        # `transformer`; it needs stream timestamps that are never set, vmae.py:446-449) but its Linear is a real
+        # parameter of the shipped IMU checkpoints (conjoined_vmae.py:1198-1204), so it is kept for load_state_dict.
+        self._spacetime_separable_pos_embed = spacetime_separable_pos_embed
         self.timestamps = None
+        self.encoder.timestamps = None
         self.pos_embed = get_sinusoid_encoding_table(self.encoder.num_patches, decoder_embed_dim)  # vmae.py:366
+        if self._spacetime_separable_pos_embed:
+            self.pos_embed_encoder = nn.Linear(2 * decoder_embed_dim, decoder_embed_dim)  # vmae.py:368-369
         nn.init.trunc_normal_(self.mask_token, mean=0., std=.02, a=-.02, b=.02)  # vmae.py:25-26, :371
         self.num_frames = num_frames
         self.num_patches = self.encoder.num_patches
-        self.num_patches_per_frame = self.num_patches // self.num_frames
+        if self.num_frames is not None:
+            self.num_patches_per_frame = self.num_patches // self.num_frames
+        else:
+            self.num_patches_per_frame = self.num_patches
         self.patch_size = self.encoder.patch_size
         if isinstance(img_size, int):
             self.image_size = (img_size, img_size)

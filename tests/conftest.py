@@ -49,3 +49,20 @@ def golden_case_inputs(case):
     cfg_name, B, style, wseed, dseed, _ = make_golden.CASES[case]
     x = synthetic.make_video(B, synthetic.image_hw(cfg_name), seed=dseed)
     return cfg_name, B, style, wseed, x
+
+
+def load_golden_conjoined(case):
+    """Fixture written by oracle/make_golden_conjoined.py: masks unpacked to bool tensors, arrays to tensors."""
+    path = os.path.join(GOLDEN_DIR, case + ".npz")
+    if not os.path.exists(path):
+        pytest.skip(f"golden fixture {case} missing")
+    z = np.load(path)
+    d = {k: z[k] for k in z.files}
+    for key in ("mask", "mask_ctx"):
+        if key in d:
+            B, N = d[key + "_shape"]
+            d[key] = torch.from_numpy(np.unpackbits(d[key], axis=1)[:, :N].astype(bool))
+    for key in ("y", "y_ctx", "y_predict", "video"):
+        if key in d:
+            d[key] = torch.from_numpy(d[key])
+    return d
