@@ -28,12 +28,34 @@ WORKLOADS = {
     "base_8x8_b64_counterfactual": ("base_8x8", 64, 1),      # BASELINE.json configs[1]
     "base_4x4_b32": ("base_4x4", 32, 2),                      # configs[2]
     "large_4x4_b32_movability": ("large_4x4", 32, 1),         # configs[3], per-GPU chunk of the 1024 sweep
+    "imu400_base_4x4_b32": ("imu400_base_4x4", 32, 1),        # configs[4], per-GPU share of the 256 counterfactuals
 }
 DEFAULT_WORKLOAD = "base_8x8_b64_counterfactual"
 
 
+def flops_per_frame_conjoined(n_vis, n_ctx_vis=25):
+    """IMU-conditioned conjoined base 4x4 (BASELINE config 5): main stream as base 4x4 with a
+    6336-token decoder, 12+4 context blocks on 25 / 50 tokens, 4 encoder + 4 decoder conjoining blocks
+    (per block: qk|v 3C^2, projection C^2, MLP 2 x 2C^2 per token and stream, plus 8 N M C of cross attention)."""
+    Ntot, P, D, Ce, Cd, Le, Ld = 6272, 64, 48, 768, 384, 12, 4
+    Cse, Csd, M, Pc = 384, 192, 25, 25
+    Nd, Md = Ntot + P, M + Pc
+    blocks = lambda L, N, C: L * (24 * N * C ** 2 + 4 * N ** 2 * C)
+    f = 2 * Ntot * D * Ce + blocks(Le, n_vis, Ce) + 2 * n_vis * Ce * Cd + blocks(Ld, Nd, Cd) + 2 * (Nd - n_vis) * Cd * D
+    f += 2 * M * 96 * Cse + blocks(12, n_ctx_vis, Cse) + 2 * n_ctx_vis * Cse * Csd + blocks(4, Md, Csd) + \
+        2 * (Md - n_ctx_vis) * Csd * 96
+
+    def cross(N, Mc, C, Cs):
+        trg = 2 * N * C * (3 * C + C + 4 * C)
+        src = 2 * Mc * (Cs * 3 * C + C * Cs + 4 * Cs * Cs)
+        return trg + src + 8 * N * Mc * C
+    return f + 4 * cross(n_vis, n_ctx_vis, Ce, Cse) + 4 * cross(Nd, Md, Cd, Csd)
+
+
 def flops_per_frame(cfg_name, n_vis):
     """SURVEY.md section 8d / BASELINE.md section 3 (multiply-add = 2; LN/GELU/softmax excluded)."""
+    if cfg_name == "imu400_base_4x4":
+        return flops_per_frame_conjoined(n_vis)
     from counterfactualworldmodels_b200 import synthetic
     kw = synthetic.CONFIGS[cfg_name]
     T, h, w = synthetic.mask_size(cfg_name)
@@ -115,6 +137,25 @@ def cpu_oracle_frames_per_s(cfg_name, n_clumps, sample_frames, repeats, threads)
     import vmae_oracle as oracle
     from counterfactualworldmodels_b200 import synthetic, vmae
     torch.set_num_threads(threads)
+    if cfg_name == "imu400_base_4x4":
+        import conjoined_oracle as co
+        from counterfactualworldmodels_b200 import conjoined_vmae
+        m = conjoined_vmae.imu400_base_4x4patch_2frames_1tube()
+        synthetic.init_weights_(m, seed=0, style="reference")
+        sd = {k: v.clone() for k, v in m.state_dict().items()}
+        x = synthetic.make_video(sample_frames, (224, 224), seed=0)
+        mask = synthetic.make_mask(sample_frames, m.mask_size, num_clumps=n_clumps, seed=0)
+        imu = synthetic.make_imu(1, 400, seed=0).expand(sample_frames, -1, -1)
+        mc = torch.zeros(sample_frames, 25, dtype=torch.bool)
+        ocfg = synthetic.conjoined_oracle_cfg(cfg_name)
+        times = []
+        with torch.no_grad():
+            for _ in range(repeats):
+                t0 = time.perf_counter()
+                y = co.conjoined_forward(sd, oracle.preprocess(x), mask, imu[..., None, None], mc, ocfg, True, False)
+                oracle.pred_patches_to_video(y[:, :-64], x, mask, (1, 4, 4))
+                times.append(time.perf_counter() - t0)
+        return times
     m = vmae.PretrainVisionTransformer(**synthetic.model_kwargs(cfg_name))
     synthetic.init_weights_(m, seed=0, style="reference")
     sd = {k: v.clone() for k, v in m.state_dict().items()}
@@ -165,7 +206,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--ref-sample", type=int, default=2, help="frames per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--also", default="large_4x4_b32_movability",
+    ap.add_argument("--also", default="large_4x4_b32_movability,imu400_base_4x4_b32",
                     help="extra workloads measured briefly (comma separated, '' to skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
@@ -185,6 +226,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     _lib.check(_lib.load().cwm_device_check())
     peaks = measured_peaks()
@@ -196,11 +240,20 @@ def main():
 
     def measure(workload, steps, warmup, with_e2e, with_profile, sample_clocks):
         cfg_name, B, n_clumps = WORKLOADS[workload]
-        model = vmae.PretrainVisionTransformer(**synthetic.model_kwargs(cfg_name))
+        pred_kwargs = {}
+        if cfg_name == "imu400_base_4x4":
+            from counterfactualworldmodels_b200 import conjoined_vmae
+            model = conjoined_vmae.imu400_base_4x4patch_2frames_1tube()
+            hw = (224, 224)
+            # one IMU context per image (segmentation.py:939-963), fully visible, tiled over the counterfactual samples
+            pred_kwargs = dict(x_context=synthetic.make_imu(1, 400, seed=rank).expand(B, -1, -1).contiguous().to(dev),
+                               mask_context=torch.zeros(B, 25, dtype=torch.bool, device=dev))
+        else:
+            model = vmae.PretrainVisionTransformer(**synthetic.model_kwargs(cfg_name))
+            hw = synthetic.image_hw(cfg_name)
         synthetic.init_weights_(model, seed=0, style="reference")
         model = model.to(dev).eval()
         G = prediction.PredictorBasedGenerator(predictor=model, imagenet_normalize_inputs=True, temporal_dim=2)
-        hw = synthetic.image_hw(cfg_name)
         n_rot = 3
         xs_host = [synthetic.make_video(B, hw, seed=100 * rank + i).pin_memory() for i in range(n_rot)]
         ms_host = [synthetic.make_mask(B, model.mask_size, num_clumps=n_clumps, seed=100 * rank + i).pin_memory()
@@ -212,7 +265,7 @@ def main():
             if (world > 1 and rank == 0) else None
 
         def step(i, x, m):
-            video = G.predict(x, m, frame=None)
+            video = G.predict(x, m, frame=None, **pred_kwargs)
             if world > 1:  # the only exchange of the sharded sweep: predicted frames -> rank 0 (NCCL gather)
                 dist.gather(video[:, -1:].contiguous(), gather_buf, dst=0)
             return video
