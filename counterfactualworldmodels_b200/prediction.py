@@ -194,9 +194,16 @@ class PredictorBasedGenerator(nn.Module):
             x = self.x
         if mask is None:
             mask = self.generate_mask(x)
+        # extension used by HostPipeline: the caller already rectangularised the mask on the host and knows the
+        # per-row visible count, so neither step needs a device->host read here
+        num_visible = kwargs.pop('_num_visible', None)
         self.inp_shape = x.shape
         self.set_image_size(x.shape[-2:])
-        mask = mask if (x.size(0) == 1) else self.mask_rectangularizer(mask)
+        if num_visible is None:
+            mask = mask if (x.size(0) == 1) else self.mask_rectangularizer(mask)
+        elif isinstance(self.predictor, PretrainVisionTransformer) and \
+                not isinstance(self.predictor, PaddedVisionTransformer):
+            kwargs['num_visible'] = num_visible
         if isinstance(self.predictor, (ConjoinedPretrainVisionTransformer, PaddedVisionTransformer)):
             y = self._predict_padded_or_conjoined(x, mask, *args, **kwargs)
         elif isinstance(self.predictor, PretrainVisionTransformer):
@@ -296,3 +303,67 @@ class PredictorBasedGenerator(nn.Module):
         """prediction.py:489-495: per-image tensors (e.g. the IMU context) are repeated for every sample of a chunk."""
         return {kw: self.sample_tile(val, num_samples) if isinstance(val, torch.Tensor) else val
                 for kw, val in kwargs.items()}
+
+
+class HostPipeline:
+    """Host-buffer front end of ``PredictorBasedGenerator.predict`` for sweeps that do not fit (or do not start) in
+    device memory: batches live in pinned host memory, the predicted videos go back to pinned host memory, and the
+    host->device copy of batch i+1 and the device->host copy of batch i-1 overlap the kernels of batch i (three CUDA
+    streams, two device slots, events for ordering).  Numerically identical to calling ``predict`` per batch.
+
+        pipe = HostPipeline(G, batch_shape=(64, 2, 3, 224, 224), n_tokens=1568)
+        for x_host, mask_host, out_host in batches:
+            pipe.submit(x_host, mask_host, out_host, frame=None)
+        pipe.finish()            # all outputs have landed in their out_host buffers
+    """
+
+    def __init__(self, generator, batch_shape, n_tokens, device=None, post=None, **predict_kwargs):
+        self.G = generator
+        self.device = torch.device(device) if device is not None else next(generator.predictor.parameters()).device
+        self.kwargs = predict_kwargs
+        self.post = post  # optional callable(video) run on the compute stream right after predict (e.g. a gather)
+        with torch.cuda.device(self.device):
+            self.h2d, self.d2h = torch.cuda.Stream(), torch.cuda.Stream()
+            self.x = [torch.empty(batch_shape, dtype=torch.float32, device=self.device) for _ in range(2)]
+            self.m = [torch.empty(batch_shape[0], n_tokens, dtype=torch.bool, device=self.device) for _ in range(2)]
+            self.loaded = [torch.cuda.Event() for _ in range(2)]
+            self.computed = [torch.cuda.Event() for _ in range(2)]
+            self.stored = [torch.cuda.Event() for _ in range(2)]
+        self.i = 0
+        self.h2d_bytes = self.d2h_bytes = 0
+
+    def submit(self, x_host, mask_host, out_host, frame=None):
+        # host-side integer bookkeeping (what `predict` would do on the device with a sync): rectangularise in place
+        # like the reference (masking.py:100-132) and read the per-row visible count
+        if x_host.size(0) > 1:
+            mask_host = self.G.mask_rectangularizer(mask_host)
+        counts = (~mask_host.reshape(mask_host.size(0), -1)).sum(-1)
+        if not bool((counts == counts[0]).all()):
+            raise RuntimeError("rows of the mask have different numbers of visible tokens")
+        slot = self.i & 1
+        compute = torch.cuda.current_stream(self.device)
+        if self.i >= 2:
+            self.h2d.wait_event(self.computed[slot])   # the slot's previous batch has been consumed
+        with torch.cuda.stream(self.h2d):
+            self.x[slot].copy_(x_host, non_blocking=True)
+            self.m[slot].copy_(mask_host, non_blocking=True)
+            self.loaded[slot].record(self.h2d)
+        compute.wait_event(self.loaded[slot])
+        video = self.G.predict(self.x[slot], self.m[slot], frame=frame, _num_visible=int(counts[0]), **self.kwargs)
+        if self.post is not None:
+            self.post(video)
+        self.computed[slot].record(compute)
+        self.d2h.wait_event(self.computed[slot])
+        with torch.cuda.stream(self.d2h):
+            out_host.copy_(video, non_blocking=True)
+            self.stored[slot].record(self.d2h)
+        video.record_stream(self.d2h)
+        self.h2d_bytes = x_host.numel() * x_host.element_size() + mask_host.numel() * mask_host.element_size()
+        self.d2h_bytes = out_host.numel() * out_host.element_size()
+        self.i += 1
+
+    def finish(self):
+        """Makes the current stream wait for every outstanding copy (no host synchronisation)."""
+        compute = torch.cuda.current_stream(self.device)
+        for ev in self.stored[:min(self.i, 2)]:
+            compute.wait_event(ev)

@@ -129,3 +129,24 @@ def test_oracle_on_gpu_box_small():
     got = m(oracle.preprocess(x).to(DEV), mask.to(DEV)).cpu()
     err = (got - want).abs()
     assert err.max().item() <= MAX_ABS and err.mean().item() <= MEAN_ABS
+
+
+def test_host_pipeline_equals_predict():
+    """prediction.HostPipeline (pinned host buffers, copies overlapped with compute on 3 streams) returns exactly
+    what a per-batch `predict` returns, for more batches than it has device slots."""
+    cfg = "tiny_8x8"
+    m = _model(cfg, 7, "perturbed")
+    G = prediction.PredictorBasedGenerator(predictor=m, imagenet_normalize_inputs=True, temporal_dim=2)
+    B, n = 4, 5
+    xs = [synthetic.make_video(B, synthetic.image_hw(cfg), seed=40 + i).pin_memory() for i in range(n)]
+    ms = [synthetic.make_mask(B, m.mask_size, num_clumps=2, seed=50 + i).pin_memory() for i in range(n)]
+    outs = [torch.empty(xs[0].shape).pin_memory() for _ in range(n)]
+    pipe = prediction.HostPipeline(G, tuple(xs[0].shape), ms[0].shape[1], device=DEV)
+    for i in range(n):
+        pipe.submit(xs[i], ms[i], outs[i], frame=None)
+    pipe.finish()
+    torch.cuda.synchronize()
+    for i in range(n):
+        want = G.predict(xs[i].to(DEV), ms[i].to(DEV), frame=None).cpu()
+        assert torch.equal(outs[i], want)
+    assert pipe.h2d_bytes == xs[0].numel() * 4 + ms[0].numel() and pipe.d2h_bytes == outs[0].numel() * 4
