@@ -1,23 +1,36 @@
 // attention.cu -- softmax(q k^T) v, head_dim 64, unmasked, f16 operands, fp32 softmax statistics and fp32
 // accumulation in tensor memory (a6: cwm/models/VideoMAE/utils.py:108-113).
 //
-// Flash-style, warp-specialised, TMA-pipelined (sm_100a).  One CTA = 256 query rows (two 128-row tiles) of one
-// (sample, head); K/V are streamed once per CTA in 128-row tiles.
-//   warp 0       TMA producer (Q once, then K_j / V_j through a kKVStages-deep mbarrier ring)
+// Flash-style, warp-specialised, TMA-pipelined (sm_100a).  One work item = 256 query rows (two 128-row tiles) of one
+// (sample, head); K/V are streamed once per item in 128-row tiles.
+//   warp 0       TMA producer (Q, then K_j / V_j through a kKVStages-deep mbarrier ring)
 //   warp 1       MMA issuer: S_t = Q_t K_j^T (SS, M=128 N=128 K=64) and O_t += P_t V_j (TS: A = P from tensor
 //                memory, B = V from smem MN-major, M=128 N=64 K=128), interleaved over the two query tiles so the
 //                tensor core works on one tile while the other tile is in softmax
 //   warps 4-7    softmax warpgroup for query tile 0, warps 8-11 for tile 1: one thread per query row (no
 //                shuffles): tcgen05.ld S row -> running max with lazy rescale (O is only rescaled when the max
-//                grows by more than 2^8) -> exp2 -> fp32 row sum -> f16 P written back over S in tensor memory
-// Tensor memory map (512 columns): three 128-column score buffers B0..B2 used round-robin -- the scores of
-// (query tile t, kv tile j) live in B[(2j + t) % 3] and P (f16 pairs) overwrites their first 64 columns -- so that
-// S_0(j+1) is computed while the softmax of S_0(j) is still running; O0 [384,448), O1 [448,512).
-// Ordering facts relied on: tcgen05.mma from one thread execute in issue order (a buffer's previous P has been
-// consumed by its PV before the next QK overwrites it), and a tcgen05.commit arrives only after ALL earlier MMAs
-// completed (pv_done[t] after PV_t(j) => O_t may be rescaled / read by the softmax warpgroup).
-// The last kv tile is issued with N = round_up(valid columns, 32), so ragged sequence lengths (788, 3140 ...)
-// do not pay for a full 128-column tile.
+//                grows by more than 2^8) -> exp2 (packed FFMA2 / FADD2 math, 2 of every 8 on the FMA pipe through a
+//                degree-3 polynomial) -> fp32 row sum -> f16 P written back over S in tensor memory
+// Tensor memory map (512 columns): three 128-column score buffers used round-robin -- the scores of (query tile t,
+// kv step g) live in buffer (2g + t) % 3 and P (f16 pairs) overwrites their first 64 columns -- so that S_0(g+1) is
+// computed while the softmax of S_0(g) is still running; O0 [384,448), O1 [448,512).
+// The last kv tile is issued with N = round_up(valid columns, 32), so ragged sequence lengths (788, 3140 ...) do
+// not pay for a full 128-column tile.
+//
+// Synchronisation discipline (what tools/debug/attn_stress.py checks).  The three actors are deliberately allowed
+// to drift: the issuer runs up to two score tiles ahead of a softmax warpgroup, and the four warps of a warpgroup
+// are not synchronised with each other.  Therefore
+//   * every producer/consumer barrier whose consumer may lag by more than one phase exists TWICE and alternates by
+//     step parity (s_full, p_full, pv_done): a waiter can then never see a barrier two phases ahead (which a parity
+//     wait cannot distinguish from "not yet"), and a fast warp can never arrive twice in one phase;
+//   * a score tile is written into a buffer only after the PV product that read P from that buffer has COMPLETED
+//     (the issuer waits on pv_done), instead of relying on in-order execution inside the tensor pipe (war_safe).
+// The first version of this kernel had a single barrier per hand-off; it produced wrong rows (max error > 1) for
+// logits with a realistic spread at N = 788 / 1568 once more CTAs than SMs were in flight -- the parity tests, whose
+// random-init logits never trigger the rescale path or much warp drift, did not see it.
+
+#include <cstdio>
+
 #include "common.cuh"
 
 namespace cwm {
@@ -25,7 +38,6 @@ namespace cwm {
 constexpr int kAttnThreads = 384;
 constexpr int kKVStages = 4;
 constexpr int kTileBytes = 128 * 64 * 2;  // 16 KB
-constexpr int kAttnSmemBytes = 1024 + (2 + 2 * kKVStages) * kTileBytes + 256;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleThreshold = 8.0f;  // in log2 units
 constexpr int kDefaultPoly = 2;            // columns out of 8 whose exp2 runs on the FMA pipe (tools/kernel_bench.py sweep)
@@ -36,28 +48,10 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-// exp2 on the FMA / ALU pipes (no MUFU): Cody-Waite range reduction with the 1.5 * 2^23 magic constant and a
-// degree-3 minimax polynomial for 2^f on [-0.5, 0.5] (max relative error 7.5e-5, ~6x below the f16 rounding of P).
-// head dim 64 needs one exp per 256 tensor FLOPs and the SM has only 16 MUFU lanes, so a fixed fraction of the
-// elements of every row takes this path to balance the MUFU pipe against the FMA pipe.
-__device__ __forceinline__ float ex2_poly(float x) {
-  x = fmaxf(x, -126.0f);
-  const float t = x + 12582912.0f;   // low mantissa bits of t = round(x) (two's complement)
-  const float fi = t - 12582912.0f;
-  const float f = x - fi;
-  float p = fmaf(0.05517105013132095f, f, 0.24260960519313812f);
-  p = fmaf(p, f, 0.6932609677314758f);
-  p = fmaf(p, f, 0.9999281764030457f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));  // p * 2^round(x)
-}
-// which of every 8 consecutive columns use ex2_poly, for kPoly = 0..4 offloaded columns out of 8
-__device__ __forceinline__ constexpr bool use_poly(int kPoly, int i) {
-  return kPoly == 1 ? (i % 8 == 7)
-       : kPoly == 2 ? (i % 4 == 3)
-       : kPoly == 3 ? (i % 8 == 2 || i % 8 == 5 || i % 8 == 7)
-       : kPoly == 4 ? (i % 2 == 1)
-                    : false;
-}
+// exp2 on the FMA / ALU pipes (no MUFU), see ex2_poly2 below: Cody-Waite range reduction with the 1.5 * 2^23 magic
+// constant and a degree-3 minimax polynomial for 2^f on [-0.5, 0.5] (max relative error 7.5e-5, ~6x below the f16
+// rounding of P).  head dim 64 needs one exp per 256 tensor FLOPs and the SM has only 16 MUFU lanes, so a fixed
+// fraction of the elements of every row takes this path to balance the MUFU pipe against the FMA pipe.
 
 // packed dual-fp32 math (Blackwell FFMA2 / FADD2): one issue slot for two lanes of work
 __device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b, float c) {
@@ -128,58 +122,121 @@ __device__ __forceinline__ void reg_inc() {
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS));
 }
 
-// kTrace: CTA (0,0,0) records clock64() at the pipeline events of its first 16 kv iterations
-// (trace[role][iter][event], role 0 = MMA issuer, 1 / 2 = softmax warpgroup 0 / 1) -- tools/attn_trace.py.
-#define CWM_TRACE(role, it, ev)                                                              \
-  do {                                                                                       \
-    if (kTrace && trace_on && (it) < 16 && (threadIdx.x & 31) == 0) trace[((role) * 16 + (it)) * 8 + (ev)] = clock64(); \
-  } while (0)
+// ---------------------------------------------------------------------------------------------------------
+// The kernel.  Default launch: one work item (q block, head, sample) per CTA.  Experimental multi-item mode
+// (cwm_debug_attention_persistent(1)): one CTA per SM walks a contiguous, cost-balanced range of work items
+// and software-pipelines ACROSS items -- the producer prefetches the next item's Q (double-buffered) and K/V through
+// the same ring, the MMA warp issues S(next item, 0) while the softmax of the current item's last tile is still
+// running, and the softmax warpgroups normalise / store O of item i while the tensor core already works on item
+// i+1.  This hides the per-CTA launch, TMEM allocation, pipeline ramp-up and epilogue that dominate short sequences
+// (N = 788: 7 kv tiles per item).  Items of one (sample, head) are consecutive, so K/V are re-read from L2, and a
+// contiguous range keeps DRAM traffic at the algorithmic bytes.
+// All mbarrier phases are driven by running counters: g = global kv step of this CTA (S-buffer rotation, K/V ring),
+// g_t = steps that involved query tile t (tile 1 is absent in the last, <= 128-row q block of a sequence).
+// O_t needs no extra barrier: the softmax warpgroup reads O_t of item i (epilogue) before it signals p_full[t] for
+// step 0 of item i+1, and PV_t(i+1, 0) -- the first MMA that overwrites O_t -- is only issued after that p_full.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kPersistSmemBytes = 1024 + (4 + 2 * kKVStages) * kTileBytes + 512;
 
-template <bool kTrace, int kPoly, bool kPacked>
+struct ItemCoord {
+  int h, row_base, q0;
+  bool t1;
+};
+__device__ __forceinline__ ItemCoord decode_item(int item, int nq, int H, int N) {
+  const int grp = item / nq;
+  const int qb = item - grp * nq;
+  ItemCoord c;
+  c.h = grp % H;
+  c.row_base = (grp / H) * N;
+  c.q0 = qb * 256;
+  c.t1 = (c.q0 + 128) < N;
+  return c;
+}
+
+template <int kPoly, bool kDbg>
 __global__ void __launch_bounds__(kAttnThreads, 1)
-attention_f16_kernel(const __grid_constant__ CUtensorMap tma_qkv, int N, int H, __half* __restrict__ out,
-                     float scale_log2, long long* __restrict__ trace) {
-  const bool trace_on = kTrace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+attention_persist_kernel(const __grid_constant__ CUtensorMap tma_qkv, int N, int H, int B, __half* __restrict__ out,
+                         float scale_log2, int strided, int war_safe) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_q = smem;                               // 2 tiles
-  uint8_t* smem_k = smem + 2 * kTileBytes;              // kKVStages tiles
+  uint8_t* smem_q = smem;                               // 2 buffers x 2 tiles
+  uint8_t* smem_k = smem + 4 * kTileBytes;              // kKVStages tiles
   uint8_t* smem_v = smem_k + kKVStages * kTileBytes;    // kKVStages tiles
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_v + kKVStages * kTileBytes);
-  uint64_t* q_full = bars;                    // 1
-  uint64_t* k_full = bars + 1;                // kKVStages
+  uint64_t* q_full = bars;                    // 2
+  uint64_t* q_empty = bars + 2;               // 2
+  uint64_t* k_full = bars + 4;                // kKVStages
   uint64_t* k_empty = k_full + kKVStages;
   uint64_t* v_full = k_empty + kKVStages;
   uint64_t* v_empty = v_full + kKVStages;
-  uint64_t* s_full = v_empty + kKVStages;     // 2
-  uint64_t* p_full = s_full + 2;              // 2
-  uint64_t* pv_done = p_full + 2;             // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  uint64_t* s_full = v_empty + kKVStages;     // 2 tiles x 2 (alternating by step parity, see below)
+  uint64_t* p_full = s_full + 4;              // 2 tiles x 2 (alternating by step parity)
+  uint64_t* pv_done = p_full + 4;             // 2 tiles x 2 (alternating by step parity)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 4);
 
-  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
-  const int h = blockIdx.y;
-  const int b = blockIdx.z;
   const int C = H * 64;
-  const int q0 = blockIdx.x * 256;               // first query row of this CTA within the sample
-  const bool t1_valid = (q0 + 128) < N;          // does query tile 1 contain any valid row?
+  // kDbg: every mbarrier wait gives up after ~2^26 polls, reports who waited for what and traps (debug hook only)
+  auto WAIT = [&](uint64_t* bar, uint32_t parity, int tag, int step) {
+    if (!kDbg) {
+      mbar_wait(bar, parity);
+    } else {
+      long long n = 0;
+      while (!mbar_try_wait(bar, parity)) {
+        if (++n > (1ll << 24)) {
+          if (lane == 0)
+            printf("attention_persist: block %d warp %d stuck tag %d step %d parity %u\n", blockIdx.x, warp, tag, step, parity);
+          __trap();
+        }
+      }
+    }
+  };
   const int n_kv = (N + 127) / 128;
-  const int row_base = b * N;                    // row of token 0 of this sample in the [B*N, 3C] matrix
-  const int cols_last = ((N - (n_kv - 1) * 128) + 31) & ~31;  // MMA columns of the last kv tile (32..128)
+  const int cols_last = ((N - (n_kv - 1) * 128) + 31) & ~31;
+  // ---- this CTA's contiguous, cost-balanced item range (a q block with both tiles costs 2, a half block 1) ----
+  const int nq = (N + 255) / 256;
+  const int cost_grp = 2 * nq - (((N - (nq - 1) * 256) <= 128) ? 1 : 0);
+  const long long total_cost = static_cast<long long>(H) * B * cost_grp;
+  auto first_item = [&](long long t) -> int {
+    const long long g = t / cost_grp;
+    const int r = static_cast<int>(t - g * cost_grp);
+    return static_cast<int>(g * nq + ((r + 1) >> 1));
+  };
+  // Two item -> CTA maps.  Contiguous (short sequences): CTA c walks a cost-balanced contiguous range, so the K/V of a
+  // (sample, head) are re-read from L2 by the same SM.  Strided (long sequences, where the K/V of 148 concurrent
+  // (sample, head) groups would overflow L2): item = c + i * gridDim.x, so that the CTAs running at the same time
+  // share a few (sample, head) groups, exactly like a plain grid launch.
+  const int n_items = nq * H * B;
+  int item_first, item_step, n_my;
+  if (strided) {
+    item_first = blockIdx.x;
+    item_step = gridDim.x;
+    n_my = (n_items > static_cast<int>(blockIdx.x)) ? (n_items - 1 - static_cast<int>(blockIdx.x)) / item_step + 1 : 0;
+  } else {
+    item_first = first_item(total_cost * blockIdx.x / gridDim.x);
+    item_step = 1;
+    n_my = first_item(total_cost * (blockIdx.x + 1) / gridDim.x) - item_first;
+  }
+  auto item_of = [&](int e) { return item_first + e * item_step; };
 
   if (warp == 0 && lane == 0) tma_prefetch_desc(&tma_qkv);
   if (warp == 1 && lane == 0) {
-    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+      mbar_init(&s_full[2 * i], 1);
+      mbar_init(&s_full[2 * i + 1], 1);
+      mbar_init(&p_full[2 * i], 4);  // one elected lane per softmax warp
+      mbar_init(&p_full[2 * i + 1], 4);
+      mbar_init(&pv_done[2 * i], 1);
+      mbar_init(&pv_done[2 * i + 1], 1);
+    }
     for (int s = 0; s < kKVStages; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&k_empty[s], 1);
       mbar_init(&v_full[s], 1);
       mbar_init(&v_empty[s], 1);
-    }
-    for (int t = 0; t < 2; ++t) {
-      mbar_init(&s_full[t], 1);
-      mbar_init(&p_full[t], 4);  // one elected lane per softmax warp
-      mbar_init(&pv_done[t], 1);
     }
     fence_mbar_init();
   }
@@ -193,44 +250,43 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tma_qkv, int N, int H, 
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
-    reg_dec<56>();
-    // The producer / MMA roles run warp-uniformly; only the TMA / tcgen05 instructions are issued by one elected
-    // lane (see the note in gemm.cu: a role under `if (lane == 0)` costs ~100 cycles of issue per MMA).
+    reg_dec<64>();
     if (warp == 0) {
       // ===================== TMA producer =====================
-      if (elect_one()) {
-        mbar_arrive_expect_tx(q_full, (t1_valid ? 2 : 1) * kTileBytes);
-        tma_load_2d(smem_q, &tma_qkv, q_full, h * 64, row_base + q0);
-        if (t1_valid) tma_load_2d(smem_q + kTileBytes, &tma_qkv, q_full, h * 64, row_base + q0 + 128);
-      }
-      __syncwarp();
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int j = 0; j < n_kv; ++j) {
-        mbar_wait(&k_empty[stage], phase ^ 1);
+      int g = 0;  // global kv step
+      for (int e = 0; e < n_my; ++e) {  // e = item ordinal
+        const ItemCoord ic = decode_item(item_of(e), nq, H, N);
+        const int qb = e & 1;
+        WAIT(&q_empty[qb], ((e >> 1) & 1) ^ 1, 1, e);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&k_full[stage], kTileBytes);
-          tma_load_2d(smem_k + stage * kTileBytes, &tma_qkv, &k_full[stage], C + h * 64, row_base + j * 128);
+          mbar_arrive_expect_tx(&q_full[qb], (ic.t1 ? 2 : 1) * kTileBytes);
+          tma_load_2d(smem_q + (2 * qb) * kTileBytes, &tma_qkv, &q_full[qb], ic.h * 64, ic.row_base + ic.q0);
+          if (ic.t1)
+            tma_load_2d(smem_q + (2 * qb + 1) * kTileBytes, &tma_qkv, &q_full[qb], ic.h * 64, ic.row_base + ic.q0 + 128);
         }
         __syncwarp();
-        mbar_wait(&v_empty[stage], phase ^ 1);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&v_full[stage], kTileBytes);
-          tma_load_2d(smem_v + stage * kTileBytes, &tma_qkv, &v_full[stage], 2 * C + h * 64, row_base + j * 128);
-        }
-        __syncwarp();
-        if (++stage == kKVStages) {
-          stage = 0;
-          phase ^= 1;
+        for (int j = 0; j < n_kv; ++j, ++g) {
+          const int stage = g % kKVStages;
+          const uint32_t phase = (g / kKVStages) & 1;
+          WAIT(&k_empty[stage], phase ^ 1, 2, g);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&k_full[stage], kTileBytes);
+            tma_load_2d(smem_k + stage * kTileBytes, &tma_qkv, &k_full[stage], C + ic.h * 64, ic.row_base + j * 128);
+          }
+          __syncwarp();
+          WAIT(&v_empty[stage], phase ^ 1, 3, g);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&v_full[stage], kTileBytes);
+            tma_load_2d(smem_v + stage * kTileBytes, &tma_qkv, &v_full[stage], 2 * C + ic.h * 64, ic.row_base + j * 128);
+          }
+          __syncwarp();
         }
       }
-    } else if (warp == 1) {
+    } else if (warp == 1 && n_my > 0) {
       // ===================== MMA issuer =====================
       constexpr uint32_t idesc_pv = umma_idesc_f16(128, 64, 0, 1);  // B = V is MN-major
       const uint32_t tm_o0 = tmem_base + 384, tm_o1 = tmem_base + 448;
-      // Descriptors are built once; a stage / k-step only adds to the 14-bit start-address field (>> 4 units).
-      const uint64_t dq0 = umma_desc_kmajor_sw128(smem_u32(smem_q));
-      const uint64_t dq1 = umma_desc_kmajor_sw128(smem_u32(smem_q + kTileBytes));
+      const uint64_t dq_base = umma_desc_kmajor_sw128(smem_u32(smem_q));
       const uint64_t dk_base = umma_desc_kmajor_sw128(smem_u32(smem_k));
       const uint64_t dv_base = umma_desc_mnmajor_sw128(smem_u32(smem_v), 0);
       const uint32_t idesc_full = umma_idesc_f16(128, 128, 0, 0);
@@ -243,7 +299,6 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tma_qkv, int N, int H, 
         }
         __syncwarp();
       };
-      // 16 kv rows per MMA: 8 TMEM columns of packed f16 pairs, 2048 B of V
       auto issue_pv = [&](uint32_t tm_p, uint64_t dv, uint32_t tm_o, bool accumulate, int ksteps, uint64_t* bar) {
         if (elect_one()) {
           for (int k = 0; k < ksteps; ++k)
@@ -256,61 +311,88 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tma_qkv, int N, int H, 
         if (elect_one()) umma_commit(bar);
         __syncwarp();
       };
-      auto sbuf = [&](int j, int t) { return tmem_base + static_cast<uint32_t>(((2 * j + t) % 3) * 128); };
+      auto sbuf = [&](int gs, int t) { return tmem_base + static_cast<uint32_t>(((2 * gs + t) % 3) * 128); };
+      auto dq_of = [&](int e, int t) { return dq_base + static_cast<uint64_t>(((e & 1) * 2 + t) * (kTileBytes >> 4)); };
 
-      mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
+      // The issuer runs up to TWO score tiles ahead of a softmax warpgroup (S(g+1) is issued before it waits for
+      // P(g), and S(g+2) right after): with a single barrier per tile the warpgroup could find the barrier two phases
+      // ahead -- indistinguishable from "not yet" by parity -- whenever it is delayed (e.g. by an item's epilogue).
+      // Scores of tile t therefore alternate between two barriers, s_full[2t + (n & 1)], n = running tile-t step.
+      // p_full alternates the same way for a different reason: the four warps of a softmax warpgroup are not
+      // synchronised with each other, and because S(g+1) is available before P(g) is consumed a fast warp could
+      // arrive for step g+1 before a slow warp has arrived for step g -- on one barrier those two arrivals would
+      // complete phase g without the slow warp.  With two barriers a warp can only arrive on the same barrier again
+      // after S(g+2) exists, i.e. after the issuer has seen all four arrivals of step g.
+      int n_s0 = 1, n_s1 = 0;
+      // ---- prologue: scores of the first step ----
       {
-        const uint32_t id0 = (n_kv == 1) ? idesc_last : idesc_full;
-        issue_qk(dq0, dk_base, sbuf(0, 0), id0, &s_full[0]);
-        if (t1_valid) issue_qk(dq1, dk_base, sbuf(0, 1), id0, &s_full[1]);
-        commit(&k_empty[0]);
-      }
-
-      int stage = 0;       // stage of K_j / V_j
-      uint32_t phase = 0;
-      for (int j = 0; j < n_kv; ++j) {
-        int nstage = stage + 1;
-        uint32_t nphase = phase;
-        if (nstage == kKVStages) {
-          nstage = 0;
-          nphase ^= 1;
-        }
-        const bool has_next = (j + 1) < n_kv;
-        const uint32_t id_next = (j + 2 == n_kv) ? idesc_last : idesc_full;
-        const int ksteps = ((j + 1 == n_kv) ? cols_last : 128) >> 4;
-        const uint64_t dv = dv_base + static_cast<uint64_t>(stage * (kTileBytes >> 4));
-        const uint64_t dkn = dk_base + static_cast<uint64_t>(nstage * (kTileBytes >> 4));
-        // ---- S_0(j+1) first: it lands in the buffer freed by PV_1(j-1), so tile 0 never waits for its scores
-        if (has_next) {
-          mbar_wait(&k_full[nstage], nphase);
-          tc_fence_after();
-          CWM_TRACE(0, j, 0);
-          issue_qk(dq0, dkn, sbuf(j + 1, 0), id_next, &s_full[0]);
-          CWM_TRACE(0, j, 1);
-        }
-        // ---- O_0 += P_0(j) V_j
-        mbar_wait(&p_full[0], j & 1);
-        mbar_wait(&v_full[stage], phase);
+        const ItemCoord ic = decode_item(item_of(0), nq, H, N);
+        WAIT(&q_full[0], 0, 4, 0);
+        WAIT(&k_full[0], 0, 5, 0);
         tc_fence_after();
-        CWM_TRACE(0, j, 2);
-        issue_pv(sbuf(j, 0), dv, tm_o0, j > 0, ksteps, &pv_done[0]);
-        CWM_TRACE(0, j, 3);
-        if (t1_valid) {
-          // ---- S_1(j+1) reuses the buffer P_0(j) just vacated (in-order execution after PV_0(j))
-          if (has_next) issue_qk(dq1, dkn, sbuf(j + 1, 1), id_next, &s_full[1]);
-          CWM_TRACE(0, j, 4);
-          mbar_wait(&p_full[1], j & 1);
-          tc_fence_after();
-          CWM_TRACE(0, j, 5);
-          issue_pv(sbuf(j, 1), dv, tm_o1, j > 0, ksteps, &pv_done[1]);
-          CWM_TRACE(0, j, 6);
+        const uint32_t id0 = (n_kv == 1) ? idesc_last : idesc_full;
+        issue_qk(dq_of(0, 0), dk_base, sbuf(0, 0), id0, &s_full[0]);
+        if (ic.t1) {
+          issue_qk(dq_of(0, 1), dk_base, sbuf(0, 1), id0, &s_full[2]);
+          n_s1 = 1;
         }
-        commit(&v_empty[stage]);
-        if (has_next) commit(&k_empty[nstage]);
-        stage = nstage;
-        phase = nphase;
+        commit(&k_empty[0]);
+        if (n_kv == 1) commit(&q_empty[0]);
+      }
+      int g = 0, g1 = 0;
+      for (int e = 0; e < n_my; ++e) {
+        const bool t1_cur = decode_item(item_of(e), nq, H, N).t1;
+        for (int j = 0; j < n_kv; ++j, ++g) {
+          const bool same_item = (j + 1) < n_kv;
+          const bool has_next = same_item || (e + 1) < n_my;
+          const int next_j = same_item ? j + 1 : 0;
+          const int next_e = same_item ? e : e + 1;
+          const bool t1_next = has_next && (same_item ? t1_cur : decode_item(item_of(e + 1), nq, H, N).t1);
+          const int stage = g % kKVStages;
+          const uint32_t phase = (g / kKVStages) & 1;
+          const int nstage = (g + 1) % kKVStages;
+          const uint32_t nphase = ((g + 1) / kKVStages) & 1;
+          const uint32_t id_next = (next_j == n_kv - 1) ? idesc_last : idesc_full;
+          const int ksteps = ((j + 1 == n_kv) ? cols_last : 128) >> 4;
+          const uint64_t dv = dv_base + static_cast<uint64_t>(stage * (kTileBytes >> 4));
+          const uint64_t dkn = dk_base + static_cast<uint64_t>(nstage * (kTileBytes >> 4));
+          // ---- S_0(next) first: it lands in the buffer freed by PV_1 of the previous step
+          if (has_next) {
+            if (next_j == 0) WAIT(&q_full[next_e & 1], (next_e >> 1) & 1, 6, g);
+            WAIT(&k_full[nstage], nphase, 7, g);
+            // war_safe: S_0(g+1) overwrites the buffer P_1 of the previous tile-1 step was read from -- wait until
+            // that PV has COMPLETED instead of relying on in-order execution of the MMA pipe
+            if (war_safe && g1 > 0) WAIT(&pv_done[2 + ((g1 - 1) & 1)], ((g1 - 1) >> 1) & 1, 17, g);
+            tc_fence_after();
+            issue_qk(dq_of(next_e, 0), dkn, sbuf(g + 1, 0), id_next, &s_full[n_s0 & 1]);
+            ++n_s0;
+          }
+          // ---- O_0 += P_0 V
+          WAIT(&p_full[g & 1], (g >> 1) & 1, 8, g);
+          WAIT(&v_full[stage], phase, 9, g);
+          tc_fence_after();
+          issue_pv(sbuf(g, 0), dv, tm_o0, j > 0, ksteps, &pv_done[g & 1]);
+          // ---- S_1(next) reuses the buffer P_0 just vacated (in-order execution after PV_0)
+          if (t1_next) {
+            if (war_safe) {  // S_1(g+1) overwrites the buffer PV_0(g) reads P_0(g) from
+              WAIT(&pv_done[g & 1], (g >> 1) & 1, 18, g);
+              tc_fence_after();
+            }
+            issue_qk(dq_of(next_e, 1), dkn, sbuf(g + 1, 1), id_next, &s_full[2 + (n_s1 & 1)]);
+            ++n_s1;
+          }
+          if (t1_cur) {
+            WAIT(&p_full[2 + (g1 & 1)], (g1 >> 1) & 1, 10, g);
+            tc_fence_after();
+            issue_pv(sbuf(g, 1), dv, tm_o1, j > 0, ksteps, &pv_done[2 + (g1 & 1)]);
+            ++g1;
+          }
+          commit(&v_empty[stage]);
+          if (has_next) {
+            commit(&k_empty[nstage]);
+            if (next_j == n_kv - 1) commit(&q_empty[next_e & 1]);  // the last scores that read this Q buffer are issued
+          }
+        }
       }
     }
   } else {
@@ -319,30 +401,28 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tma_qkv, int N, int H, 
     const int t = (warp - 4) >> 2;          // query tile
     const int quad = warp & 3;              // TMEM lane quadrant
     const int row_in_tile = quad * 32 + lane;
-    const int q_row = q0 + t * 128 + row_in_tile;  // row within the sample
-    if (t == 0 || t1_valid) {
-      const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-      const uint32_t tm_o = tmem_base + lane_off + 384 + t * 64;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t tm_o = tmem_base + lane_off + 384 + t * 64;
+    int g = 0;   // global kv step of the first tile of the current item
+    int gt = 0;  // steps this tile took part in (barrier phases)
+    for (int e = 0; e < n_my; ++e, g += n_kv) {
+      const ItemCoord ic = decode_item(item_of(e), nq, H, N);
+      if (t == 1 && !ic.t1) continue;
+      const int q_row = ic.q0 + t * 128 + row_in_tile;  // row within the sample
       float m_ref = 0.f;   // running reference max (raw score units)
       float l_sum = 0.f;   // running sum of exp2((s - m_ref) * scale_log2)
-      for (int j = 0; j < n_kv; ++j) {
-        const uint32_t tm_s = tmem_base + lane_off + static_cast<uint32_t>(((2 * j + t) % 3) * 128);
+      for (int j = 0; j < n_kv; ++j, ++gt) {
+        const uint32_t tm_s = tmem_base + lane_off + static_cast<uint32_t>(((2 * (g + j) + t) % 3) * 128);
         const int ncols = (j + 1 == n_kv) ? cols_last : 128;  // columns the MMA produced for this tile
         const int kv_valid = N - j * 128;                     // columns >= kv_valid are padding
-        const bool tr = (quad == 0 && lane == 0);
-        if (tr) CWM_TRACE(1 + t, j, 0);
-        mbar_wait(&s_full[t], j & 1);
+        WAIT(&s_full[2 * t + (gt & 1)], (gt >> 1) & 1, 11 + t, gt);
         tc_fence_after();
-        if (tr) CWM_TRACE(1 + t, j, 1);
         uint32_t s[128];
-        // all four chunks are always read (columns >= ncols hold stale data and are masked below); only the
-        // exp / P-store work is skipped for chunks the last, ragged MMA did not produce
         tmem_ld_x32(tm_s + 0, s);
         tmem_ld_x32(tm_s + 32, s + 32);
         tmem_ld_x32(tm_s + 64, s + 64);
         tmem_ld_x32(tm_s + 96, s + 96);
         tmem_ld_wait();
-        if (tr) CWM_TRACE(1 + t, j, 2);
         if (kv_valid < 128) {
 #pragma unroll
           for (int i = 0; i < 128; ++i)
@@ -366,10 +446,13 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tma_qkv, int N, int H, 
             const float f = need ? ex2((m_ref - row_max) * scale_log2) : 1.0f;
             if (need) m_ref = row_max;
             l_sum *= f;
-            // O_t is quiescent once PV_t(j-1) has completed: PV_t(j) is not issued before this warpgroup
-            // signals p_full[t].  (At step j the barrier has completed phase j-1 at most, so the parity is
-            // unambiguous even though this wait is only executed when a rescale is needed.)
-            mbar_wait(&pv_done[t], (j - 1) & 1);
+            // O_t is quiescent once PV_t of the previous step has completed (PV_t of this step is not issued before
+            // this warpgroup signals p_full[t]).  pv_done alternates between two barriers by step parity: this warp
+            // does not observe every completion (the wait is lazy), and a warp may be a full step ahead of the
+            // slowest warp of its group, so on a single barrier "PV(gt-2) still pending" and "PV(gt-1) done" would
+            // have the same parity.  On barrier (gt-1)&1 the previous completion is PV(gt-3), which is known to be
+            // complete because S(gt-1) -- issued after it and already consumed by this warp -- has completed.
+            WAIT(&pv_done[2 * t + ((gt - 1) & 1)], ((gt - 1) >> 1) & 1, 13 + t, gt);
             tc_fence_after();
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
@@ -383,7 +466,6 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tma_qkv, int N, int H, 
             tmem_st_wait();
           }
         }
-        if (tr) CWM_TRACE(1 + t, j, 3);
         const float neg_m = -m_ref * scale_log2;
         float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
 #pragma unroll
@@ -392,65 +474,41 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tma_qkv, int N, int H, 
             uint32_t p[16];  // 32 kv elements as packed f16 pairs; P aliases S columns that are already in registers
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              const int e = c * 32 + i;
-              float x0, x1, x2, x3;
-              if (kPacked) {
-                ffma2(x0, x1, __uint_as_float(s[e]), __uint_as_float(s[e + 1]), scale_log2, neg_m);
-                ffma2(x2, x3, __uint_as_float(s[e + 2]), __uint_as_float(s[e + 3]), scale_log2, neg_m);
+              const int el = c * 32 + i;
+              float x0, x1, x2, x3, p0, p1, p2, p3;
+              ffma2(x0, x1, __uint_as_float(s[el]), __uint_as_float(s[el + 1]), scale_log2, neg_m);
+              ffma2(x2, x3, __uint_as_float(s[el + 2]), __uint_as_float(s[el + 3]), scale_log2, neg_m);
+              if (pair_poly(kPoly, el)) {
+                ex2_poly2(p0, p1, x0, x1);
               } else {
-                x0 = fmaf(__uint_as_float(s[e]), scale_log2, neg_m);
-                x1 = fmaf(__uint_as_float(s[e + 1]), scale_log2, neg_m);
-                x2 = fmaf(__uint_as_float(s[e + 2]), scale_log2, neg_m);
-                x3 = fmaf(__uint_as_float(s[e + 3]), scale_log2, neg_m);
+                p0 = ex2(x0);
+                p1 = ex2(x1);
               }
-              float p0, p1, p2, p3;
-              if (kPacked) {
-                if (pair_poly(kPoly, e)) {
-                  ex2_poly2(p0, p1, x0, x1);
-                } else {
-                  p0 = ex2(x0);
-                  p1 = ex2(x1);
-                }
-                if (pair_poly(kPoly, e + 2)) {
-                  ex2_poly2(p2, p3, x2, x3);
-                } else {
-                  p2 = ex2(x2);
-                  p3 = ex2(x3);
-                }
+              if (pair_poly(kPoly, el + 2)) {
+                ex2_poly2(p2, p3, x2, x3);
               } else {
-                p0 = use_poly(kPoly, e) ? ex2_poly(x0) : ex2(x0);
-                p1 = use_poly(kPoly, e + 1) ? ex2_poly(x1) : ex2(x1);
-                p2 = use_poly(kPoly, e + 2) ? ex2_poly(x2) : ex2(x2);
-                p3 = use_poly(kPoly, e + 3) ? ex2_poly(x3) : ex2(x3);
+                p2 = ex2(x2);
+                p3 = ex2(x3);
               }
-              if (kPacked) {
-                fadd2(sum0, sum1, sum0, sum1, p0, p1);
-                fadd2(sum2, sum3, sum2, sum3, p2, p3);
-              } else {
-                sum0 += p0;
-                sum1 += p1;
-                sum2 += p2;
-                sum3 += p3;
-              }
+              fadd2(sum0, sum1, sum0, sum1, p0, p1);
+              fadd2(sum2, sum3, sum2, sum3, p2, p3);
               p[(i >> 1)] = pack_half2(p0, p1);
               p[(i >> 1) + 1] = pack_half2(p2, p3);
             }
             tmem_st_x16(tm_s + c * 16, p);
           }
         }
-        if (tr) CWM_TRACE(1 + t, j, 4);
         tmem_st_wait();
         l_sum += (sum0 + sum1) + (sum2 + sum3);
         tc_fence_before();
         __syncwarp();
-        if (tr) CWM_TRACE(1 + t, j, 5);
-        if (lane == 0) mbar_arrive(&p_full[t]);
+        if (lane == 0) mbar_arrive(&p_full[2 * t + (gt & 1)]);
       }
-      // ---- finalise: O / l -> f16 -> global
-      mbar_wait(&pv_done[t], (n_kv - 1) & 1);
+      // ---- finalise this item: O / l -> f16 -> global (the tensor core is already busy with the next item)
+      WAIT(&pv_done[2 * t + ((gt - 1) & 1)], ((gt - 1) >> 1) & 1, 15 + t, gt);
       tc_fence_after();
       const float inv_l = 1.0f / l_sum;
-      __half* orow = out + (static_cast<long long>(row_base) + q_row) * C + h * 64;
+      __half* orow = out + (static_cast<long long>(ic.row_base) + q_row) * C + ic.h * 64;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t o[32];
@@ -483,18 +541,22 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tma_qkv, int N, int H, 
 
 using namespace cwm;
 
-// Debug hook (not part of the public header): device buffer of 3*16*8 int64 that receives the pipeline trace of
-// CTA (0,0,0) of every following cwm_attention_f16 call; NULL switches tracing off.
-static long long* g_attn_trace = nullptr;
-extern "C" void cwm_debug_attention_trace(long long* device_buffer) { g_attn_trace = device_buffer; }
 // Debug hook: how many of every 8 score columns take the polynomial exp2 (0..4); default kDefaultPoly.
 static int g_attn_poly = kDefaultPoly;
-static int g_attn_packed = 1;  // FFMA2 / FADD2 variant is the default (+4 % alone, +13 % with kPoly = 2)
 extern "C" void cwm_debug_attention_poly(int eighths) {
-  g_attn_packed = eighths >= 10;  // 10 + e selects the FFMA2 / FADD2 variant
-  if (eighths >= 10) eighths -= 10;
+  if (eighths >= 10) eighths -= 10;  // (the scalar-math variant selected by values < 10 no longer exists)
   g_attn_poly = eighths < 0 ? 0 : (eighths > 4 ? 4 : eighths);
 }
+
+// Debug hook: 3 (default) = one work item per CTA; 1 = EXPERIMENTAL multi-item persistent CTAs with cross-item
+// pipelining (+14 % at N = 788, but tools/debug/attn_stress.py still finds rare wrong rows for sequences of 2-3 kv
+// tiles -- not enabled); 2 / 4 = modes 1 / 3 with watchdog waits (report a stuck mbarrier wait and trap).
+static int g_attn_mode = 3;
+static int g_attn_persist_map = -1;  // -1 = automatic, 0 = contiguous ranges, 1 = strided
+static int g_attn_war_safe = 1;
+extern "C" void cwm_debug_attention_war_safe(int on) { g_attn_war_safe = on; }
+extern "C" void cwm_debug_attention_persistent(int mode) { g_attn_mode = (mode == 0) ? 3 : mode; }
+extern "C" void cwm_debug_attention_persist_map(int m) { g_attn_persist_map = m; }
 
 extern "C" int cwm_attention_f16(const uint16_t* qkv, int B, int N, int H, int head_dim, uint16_t* out,
                                  cwm_stream_t stream) {
@@ -505,20 +567,17 @@ extern "C" int cwm_attention_f16(const uint16_t* qkv, int B, int N, int H, int h
     return cwm_attention_generic_f16(qkv, qkv + A, qkv + 2 * A, 3 * A, 3 * A, 3 * A, head_dim, head_dim, head_dim, B, N, N,
                                      H, head_dim, out, A, nullptr, 0, stream);
   }
-  CWM_REQUIRE(H <= 65535 && B <= 65535, "cwm_attention_f16: grid too large");
   if (B == 0) return CWM_OK;
-  using KernelFn = void (*)(const CUtensorMap, int, int, __half*, float, long long*);
-  static const KernelFn kernels[10] = {
-      attention_f16_kernel<false, 0, false>, attention_f16_kernel<false, 1, false>, attention_f16_kernel<false, 2, false>,
-      attention_f16_kernel<false, 3, false>, attention_f16_kernel<false, 4, false>, attention_f16_kernel<false, 0, true>,
-      attention_f16_kernel<false, 1, true>,  attention_f16_kernel<false, 2, true>,  attention_f16_kernel<false, 3, true>,
-      attention_f16_kernel<false, 4, true>};
+  const long long n_items = static_cast<long long>((N + 255) / 256) * H * B;
+  CWM_REQUIRE(n_items < (1ll << 31), "cwm_attention_f16: too many work items");
+  using KernelFn = void (*)(const CUtensorMap, int, int, int, __half*, float, int, int);
+  static const KernelFn kernels[6] = {attention_persist_kernel<0, false>, attention_persist_kernel<1, false>,
+                                      attention_persist_kernel<2, false>, attention_persist_kernel<3, false>,
+                                      attention_persist_kernel<4, false>, attention_persist_kernel<kDefaultPoly, true>};
   static bool attr_set = false;
   if (!attr_set) {
-    for (int i = 0; i < 10; ++i)
-      CWM_CUDA_CHECK(cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
-    CWM_CUDA_CHECK(cudaFuncSetAttribute(attention_f16_kernel<true, kDefaultPoly, true>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
+    for (int i = 0; i < 6; ++i)
+      CWM_CUDA_CHECK(cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kPersistSmemBytes));
     attr_set = true;
   }
   const int C = H * 64;
@@ -527,13 +586,15 @@ extern "C" int cwm_attention_f16(const uint16_t* qkv, int B, int N, int H, int h
   if (rc) return rc;
   ProfileScope prof(static_cast<cudaStream_t>(stream), "attention_f16", 4.0 * B * H * static_cast<double>(N) * N * 64,
                     static_cast<double>(B) * N * C * 2.0 * 4.0);
-  dim3 grid((N + 255) / 256, H, B);
-  if (g_attn_trace != nullptr)
-    attention_f16_kernel<true, kDefaultPoly, true><<<grid, kAttnThreads, kAttnSmemBytes, static_cast<cudaStream_t>(stream)>>>(
-        tm, N, H, reinterpret_cast<__half*>(out), kLog2e, g_attn_trace);
-  else
-    kernels[g_attn_poly + (g_attn_packed ? 5 : 0)]<<<grid, kAttnThreads, kAttnSmemBytes, static_cast<cudaStream_t>(stream)>>>(
-        tm, N, H, reinterpret_cast<__half*>(out), kLog2e, nullptr);
+  const bool multi = (g_attn_mode == 1 || g_attn_mode == 2);
+  const int grid = multi ? static_cast<int>(n_items < num_sms() ? n_items : num_sms()) : static_cast<int>(n_items);
+  // multi-item maps: contiguous ranges while the K/V of the concurrently resident (sample, head) groups fit in
+  // (part of) the 126 MB L2, strided otherwise; one item per CTA is the strided map with grid = items
+  const double kv_resident = 2.0 * N * 64 * 2 * grid;
+  const int strided = !multi ? 1 : (g_attn_persist_map >= 0) ? g_attn_persist_map : (kv_resident > 48e6 ? 1 : 0);
+  kernels[(g_attn_mode == 2 || g_attn_mode == 4) ? 5 : g_attn_poly]<<<grid, kAttnThreads, kPersistSmemBytes,
+                                                                      static_cast<cudaStream_t>(stream)>>>(
+      tm, N, H, B, reinterpret_cast<__half*>(out), kLog2e, strided, g_attn_war_safe);
   CWM_LAUNCH_CHECK();
   return CWM_OK;
 }

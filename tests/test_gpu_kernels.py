@@ -178,7 +178,10 @@ def _attn_ref(qkv, B, N, H):
 
 
 @pytest.mark.parametrize("B,N,H", [(1, 128, 1), (2, 256, 2), (1, 100, 2), (2, 456, 4), (1, 792, 12), (2, 896, 2),
-                                   (1, 1568, 6), (1, 3168, 2), (1, 129, 1), (3, 385, 1)])
+                                   (1, 1568, 6), (1, 3168, 2), (1, 129, 1), (3, 385, 1),
+                                   # more work items than SMs: every persistent CTA pipelines across several items,
+                                   # with and without a half (<= 128-row) last q block, and single-tile sequences
+                                   (40, 300, 4), (30, 788, 12), (200, 100, 2), (64, 130, 6), (9, 520, 8)])
 def test_attention_matches_fp32_softmax(B, N, H):
     g = torch.Generator().manual_seed(B * 100 + N + H)
     qkv = torch.randn(B * N, 3 * H * 64, generator=g)
@@ -190,6 +193,25 @@ def test_attention_matches_fp32_softmax(B, N, H):
     assert torch.isfinite(got).all()
     assert (got - want).abs().max().item() < 4e-3
     assert (got - want).abs().mean().item() < 3e-4
+
+
+@pytest.mark.parametrize("B,N,H", [(64, 256, 6), (64, 130, 6), (30, 788, 12), (16, 1568, 6), (64, 384, 6)])
+def test_attention_stress_repeated(B, N, H):
+    """Race detector: more CTAs than SMs, logits with a realistic spread (the lazy-rescale path runs), 15 repetitions
+    per shape.  The first attention kernel (single mbarrier per hand-off) failed this on every repetition at
+    N = 788 / 1568 while passing every parity test."""
+    g = torch.Generator().manual_seed(B * 100 + N + H)
+    qkv = torch.randn(B * N, 3 * H * 64, generator=g)
+    qkv[:, :H * 64] *= 0.125 * 3.0
+    qkv = qkv.to(torch.float16).to(DEV)
+    want = _attn_ref(qkv, B, N, H)
+    first = None
+    for rep in range(15):
+        got = ops.attention_f16(qkv, B, N, H)
+        assert (got.float() - want).abs().max().item() < 4e-3, rep
+        if first is None:
+            first = got.clone()
+        assert torch.equal(got, first), rep     # and run-to-run deterministic
 
 
 def test_attention_large_logits_rescale_path():
@@ -244,7 +266,7 @@ def test_layernorm_generic_widths(M, C):
     assert (got - want).abs().max().item() <= 4e-3 + 1e-3 * want.abs().max().item()
 
 
-def _attn_ref(q, k, v):
+def _attn_ref3(q, k, v):
     """fp32 softmax(q k^T) v on f16-rounded operands; q,k,v [B,H,N,d]."""
     s = q.float() @ k.float().transpose(-1, -2)
     return s.softmax(-1) @ v.float()
@@ -261,7 +283,7 @@ def test_attention_generic(B, Nq, Nk, H, d):
     q = (torch.randn(B, Nq, H, d, generator=g) * d ** -0.25).to(torch.float16)
     k = (torch.randn(B, Nk, H, d, generator=g) * d ** -0.25).to(torch.float16)
     v = torch.randn(B, Nk, H, d, generator=g).to(torch.float16)
-    want = _attn_ref(q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3), v.permute(0, 2, 1, 3))   # [B,H,Nq,d]
+    want = _attn_ref3(q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3), v.permute(0, 2, 1, 3))   # [B,H,Nq,d]
     want = want.permute(0, 2, 1, 3).reshape(B * Nq, H * d)
     got = ops.attention_generic_f16(q.reshape(B * Nq, H * d).to(DEV), k.reshape(B * Nk, H * d).to(DEV),
                                     v.reshape(B * Nk, H * d).to(DEV), B, Nq, Nk, H, d).cpu().float()
@@ -282,8 +304,8 @@ def test_attention_generic_cross_layout():
     qk_s = qkv_s[:, :2 * D].reshape(B, M, H, 2 * hd).permute(0, 2, 1, 3)
     v = qkv[:, 2 * D:].reshape(B, N, H, hd).permute(0, 2, 1, 3)
     v_s = qkv_s[:, 2 * D:].reshape(B, M, H, hd).permute(0, 2, 1, 3)
-    y = _attn_ref(qk[..., :hd], qk_s[..., :hd], v_s).permute(0, 2, 1, 3).reshape(B * N, D)
-    y_s = _attn_ref(qk_s[..., hd:], qk[..., hd:], v).permute(0, 2, 1, 3).reshape(B * M, D)
+    y = _attn_ref3(qk[..., :hd], qk_s[..., :hd], v_s).permute(0, 2, 1, 3).reshape(B * N, D)
+    y_s = _attn_ref3(qk_s[..., hd:], qk[..., hd:], v).permute(0, 2, 1, 3).reshape(B * M, D)
     qd, sd = qkv.to(DEV), qkv_s.to(DEV)
     got = ops.attention_generic_f16(qd, sd, sd[:, 2 * D:], B, N, M, H, hd, 2 * hd, 2 * hd, hd).cpu().float()
     got_s = ops.attention_generic_f16(sd[:, hd:], qd[:, hd:], qd[:, 2 * D:], B, M, N, H, hd, 2 * hd, 2 * hd,

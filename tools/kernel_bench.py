@@ -91,6 +91,13 @@ if __name__ == "__main__":
         lib.cwm_debug_attention_poly.argtypes = [ctypes.c_int]
         lib.cwm_debug_attention_poly(int(os.environ["CWM_ATTN_POLY"]))
         print("attention poly eighths =", os.environ["CWM_ATTN_POLY"])
+    if os.environ.get("CWM_ATTN_PERSIST"):
+        lib = _lib.load()
+        lib.cwm_debug_attention_persistent(int(os.environ["CWM_ATTN_PERSIST"]))
+        print("attention mode (3 = one item per CTA, 1 = experimental multi-item) =", os.environ["CWM_ATTN_PERSIST"])
+    if os.environ.get("CWM_ATTN_MAP"):
+        _lib.load().cwm_debug_attention_persist_map(int(os.environ["CWM_ATTN_MAP"]))
+        print("attention persist map =", os.environ["CWM_ATTN_MAP"])
     names = sys.argv[1:] or list(CASES)
     for n in names:
         run_case(n)
