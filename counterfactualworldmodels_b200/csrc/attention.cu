@@ -123,8 +123,7 @@ __device__ __forceinline__ void reg_inc() {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// The kernel.  Default launch: one work item (q block, head, sample) per CTA.  Experimental multi-item mode
-// (cwm_debug_attention_persistent(1)): one CTA per SM walks a contiguous, cost-balanced range of work items
+// The kernel.  Default launch: persistent -- one CTA per SM walks a range of (q block, head, sample) work items
 // and software-pipelines ACROSS items -- the producer prefetches the next item's Q (double-buffered) and K/V through
 // the same ring, the MMA warp issues S(next item, 0) while the softmax of the current item's last tile is still
 // running, and the softmax warpgroups normalise / store O of item i while the tensor core already works on item
@@ -548,14 +547,13 @@ extern "C" void cwm_debug_attention_poly(int eighths) {
   g_attn_poly = eighths < 0 ? 0 : (eighths > 4 ? 4 : eighths);
 }
 
-// Debug hook: 3 (default) = one work item per CTA; 1 = EXPERIMENTAL multi-item persistent CTAs with cross-item
-// pipelining (+14 % at N = 788, but tools/debug/attn_stress.py still finds rare wrong rows for sequences of 2-3 kv
-// tiles -- not enabled); 2 / 4 = modes 1 / 3 with watchdog waits (report a stuck mbarrier wait and trap).
-static int g_attn_mode = 3;
+// Debug hook: 1 (default) = persistent CTAs (one per SM) that pipeline across work items; 3 = one work item per CTA
+// (same kernel, grid = items); 2 / 4 = modes 1 / 3 with watchdog waits (report a stuck mbarrier wait and trap).
+static int g_attn_mode = 1;
 static int g_attn_persist_map = -1;  // -1 = automatic, 0 = contiguous ranges, 1 = strided
 static int g_attn_war_safe = 1;
 extern "C" void cwm_debug_attention_war_safe(int on) { g_attn_war_safe = on; }
-extern "C" void cwm_debug_attention_persistent(int mode) { g_attn_mode = (mode == 0) ? 3 : mode; }
+extern "C" void cwm_debug_attention_persistent(int mode) { g_attn_mode = (mode <= 0) ? 3 : mode; }
 extern "C" void cwm_debug_attention_persist_map(int m) { g_attn_persist_map = m; }
 
 extern "C" int cwm_attention_f16(const uint16_t* qkv, int B, int N, int H, int head_dim, uint16_t* out,
