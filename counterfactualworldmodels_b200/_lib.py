@@ -20,7 +20,8 @@ EXPORTED_SYMBOLS = (
     "cwm_unpatchify_scatter", "cwm_vmae_workspace_bytes", "cwm_vmae_forward", "cwm_last_forward_launches",
     "cwm_profile_begin", "cwm_profile_end", "cwm_attention_generic_workspace_bytes", "cwm_attention_generic_f16",
     "cwm_fill_pad_rows", "cwm_block_workspace_bytes", "cwm_block_forward", "cwm_cross_block_workspace_bytes",
-    "cwm_cross_block_forward", "cwm_launch_count_reset",
+    "cwm_cross_block_forward", "cwm_launch_count_reset", "cwm_vmae_forward_cf", "cwm_cf_shift_masks",
+    "cwm_cf_build_videos", "cwm_cf_make_static", "cwm_patch_gather_cf", "cwm_unpatchify_scatter_cf",
 )
 
 
@@ -61,6 +62,12 @@ class VmaeModel(Structure):
            ("dec_blocks", POINTER(BlockWeights)), ("dec_norm_g", c_void_p), ("dec_norm_b", c_void_p),
            ("w_head", c_void_p), ("b_head", c_void_p)]
     )
+
+
+class CfSource(Structure):
+    """cwm_cf_source: the virtual counterfactual video (include/cwm_b200.h, section 8(f) rank 1)."""
+    _fields_ = [("x", c_void_p), ("xs", c_int64 * 5), ("sample_image", c_void_p), ("shift_px", c_void_p),
+                ("shifted_active", c_void_p), ("frame", c_int32), ("static_frame", c_int32)]
 
 
 class ProfileEntry(Structure):
@@ -107,6 +114,16 @@ def _declare(lib):
     lib.cwm_cross_block_workspace_bytes.restype = c_size_t
     lib.cwm_cross_block_forward.argtypes = ([POINTER(CrossBlockWeights), c_void_p, c_void_p] + [c_int] * 9 +
                                             [c_float, c_float, c_void_p, c_size_t, c_void_p])
+    lib.cwm_vmae_forward_cf.argtypes = [POINTER(VmaeModel), POINTER(CfSource), c_int, POINTER(c_float),
+                                        POINTER(c_float), c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.cwm_cf_shift_masks.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                       c_void_p, c_void_p]
+    lib.cwm_cf_build_videos.argtypes = [POINTER(CfSource)] + [c_int] * 7 + [c_void_p, c_void_p]
+    lib.cwm_cf_make_static.argtypes = [c_void_p, i64x5, c_void_p] + [c_int] * 7 + [c_void_p, c_void_p]
+    lib.cwm_patch_gather_cf.argtypes = [POINTER(CfSource)] + [c_int] * 8 + [c_void_p, c_int, c_int, POINTER(c_float),
+                                                                          POINTER(c_float), c_void_p, c_void_p]
+    lib.cwm_unpatchify_scatter_cf.argtypes = [c_void_p, POINTER(CfSource), c_void_p] + [c_int] * 9 + [c_void_p,
+                                                                                                   c_void_p]
     lib.cwm_profile_begin.restype = c_int
     lib.cwm_profile_end.argtypes = [POINTER(ProfileEntry), c_int, POINTER(c_int)]
     for name in EXPORTED_SYMBOLS:

@@ -138,13 +138,14 @@ extern "C" size_t cwm_vmae_workspace_bytes(const cwm_vmae_model* model, int B, i
   return p.total;
 }
 
-extern "C" int cwm_vmae_forward(const cwm_vmae_model* m, const float* x, const int64_t xs[5], int B,
-                                const float* norm_mean, const float* norm_std, const int32_t* perm, int Nvis,
-                                float* y, void* workspace, size_t workspace_bytes, cwm_stream_t st) {
+// The input is either a strided tensor (x, xs) or a counterfactual descriptor (cf): only the gather differs.
+static int vmae_forward_impl(const cwm_vmae_model* m, const float* x, const int64_t* xs, const cwm_cf_source* cf, int B,
+                             const float* norm_mean, const float* norm_std, const int32_t* perm, int Nvis,
+                             float* y, void* workspace, size_t workspace_bytes, cwm_stream_t st) {
   reset_launches();
   Plan p;
   CWM_TRY(make_plan(m, B, Nvis, &p));
-  CWM_REQUIRE(x && xs && perm && y && workspace, "cwm_vmae_forward: null pointer");
+  CWM_REQUIRE(((x && xs) || cf) && perm && y && workspace, "cwm_vmae_forward: null pointer");
   if (workspace_bytes < p.total)
     return fail(CWM_ERR_WORKSPACE, "cwm_vmae_forward: workspace %zu bytes < required %zu", workspace_bytes, p.total);
   if (B == 0) return CWM_OK;
@@ -159,8 +160,13 @@ extern "C" int cwm_vmae_forward(const cwm_vmae_model* m, const float* x, const i
 
   if (Nvis > 0) {
     // a1-a4: normalise + gather visible patches, embed, add positional embedding of the gathered tokens
-    CWM_TRY(cwm_patch_gather(x, xs, B, m->in_chans, m->num_frames, m->img_h, m->img_w, m->pt, m->ph, m->pw, perm,
-                             p.Ntot, Nvis, norm_mean, norm_std, a16, st));
+    if (cf) {
+      CWM_TRY(cwm_patch_gather_cf(cf, B, m->in_chans, m->num_frames, m->img_h, m->img_w, m->pt, m->ph, m->pw, perm,
+                                  p.Ntot, Nvis, norm_mean, norm_std, a16, st));
+    } else {
+      CWM_TRY(cwm_patch_gather(x, xs, B, m->in_chans, m->num_frames, m->img_h, m->img_w, m->pt, m->ph, m->pw, perm,
+                               p.Ntot, Nvis, norm_mean, norm_std, a16, st));
+    }
     cwm_gemm_epilogue e = {};
     e.mode = CWM_EPI_RES_F32; e.bias = m->b_patch; e.res = m->pos_enc; e.ldr = Ce; e.res_gather = perm;
     e.gather_stride = p.Ntot; e.grp_rows = Nvis; e.grp_out_stride = Nvis; e.out = xe; e.ldo = Ce;
@@ -192,6 +198,21 @@ extern "C" int cwm_vmae_forward(const cwm_vmae_model* m, const float* x, const i
   e.mode = CWM_EPI_F32; e.bias = m->b_head; e.out = y; e.ldo = m->out_dim;
   CWM_TRY(cwm_gemm_f16(a16, m->w_head, static_cast<int>(p.Mo), m->out_dim, Cd, &e, st));
   return CWM_OK;
+}
+
+extern "C" int cwm_vmae_forward(const cwm_vmae_model* m, const float* x, const int64_t xs[5], int B,
+                                const float* norm_mean, const float* norm_std, const int32_t* perm, int Nvis,
+                                float* y, void* workspace, size_t workspace_bytes, cwm_stream_t st) {
+  CWM_REQUIRE(x && xs, "cwm_vmae_forward: null pointer");
+  return vmae_forward_impl(m, x, xs, nullptr, B, norm_mean, norm_std, perm, Nvis, y, workspace, workspace_bytes, st);
+}
+
+extern "C" int cwm_vmae_forward_cf(const cwm_vmae_model* m, const cwm_cf_source* src, int S, const float* norm_mean,
+                                   const float* norm_std, const int32_t* perm, int Nvis, float* y, void* workspace,
+                                   size_t workspace_bytes, cwm_stream_t st) {
+  CWM_REQUIRE(src, "cwm_vmae_forward_cf: null pointer");
+  return vmae_forward_impl(m, nullptr, nullptr, src, S, norm_mean, norm_std, perm, Nvis, y, workspace, workspace_bytes,
+                           st);
 }
 
 // ---- block-level entry points used by the conjoined (IMU-conditioned) models ------------------------------------

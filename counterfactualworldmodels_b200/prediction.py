@@ -3,14 +3,18 @@
 predict_per_sample / batch_predict_per_sample``; ``cwm/models/masking.py:90-132`` ``RectangularizeMasks``).
 
 Same names, argument meaning and error behaviour as the reference for this path; the arithmetic
-(normalise, gather, VMAE forward, scatter + unpatchify) runs in libcwm_b200.  Mask *generation*, patch
-perturbations, RAFT flow and the statistics built on top are out of scope ("next").
+(normalise, gather, VMAE forward, scatter + unpatchify) runs in libcwm_b200.  Patch perturbations (the counterfactual prompts) live in
+``perturbation.py`` / ``segmentation.py``; mask *generation*, RAFT flow and the statistics built on top are out of
+scope ("next").
 """
 import numpy as np
 import torch
 from torch import nn
 
-from . import _lib
+import ctypes
+
+from . import _lib, perturbation
+from .perturbation import CounterfactualVideo
 from .conjoined_vmae import ConjoinedPretrainVisionTransformer, PaddedVisionTransformer
 from .vmae import (IMAGENET_DEFAULT_MEAN, IMAGENET_DEFAULT_STD, PretrainVisionTransformer, compact_mask)
 
@@ -63,6 +67,18 @@ def unpatchify_scatter(y, x_raw, inv_perm, n_vis, patch_size):
     lib = _lib.load()
     B, T, C, H, W = x_raw.shape
     pt, ph, pw = patch_size
+    if isinstance(x_raw, CounterfactualVideo):
+        # fused path: visible patches are read from the virtual counterfactual video
+        out = torch.empty(B, T, C, H, W, dtype=torch.float32, device=x_raw.device)
+        if y is not None:
+            y = y.contiguous().float()
+        src, keep = x_raw.c_struct()
+        stream = torch.cuda.current_stream(x_raw.device).cuda_stream
+        _lib.check(lib.cwm_unpatchify_scatter_cf(y.data_ptr() if y is not None else None, ctypes.byref(src),
+                                                 inv_perm.data_ptr(), B, T, C, H, W, pt, ph, pw, int(n_vis),
+                                                 out.data_ptr(), stream))
+        del keep
+        return out
     if x_raw.dtype != torch.float32:
         x_raw = x_raw.float()
     out = torch.empty(B, T, C, H, W, dtype=torch.float32, device=x_raw.device)
@@ -81,7 +97,7 @@ class PredictorBasedGenerator(nn.Module):
     """The slice of cwm/models/prediction.py:16-540 that brackets the predictor call."""
 
     def __init__(self, predictor=None, imagenet_normalize_inputs=False, temporal_dim=2, seed=0,
-                 mask_generator=None, **kwargs):
+                 mask_generator=None, max_shift_fraction=0.15, **kwargs):
         super().__init__()
         if predictor is None:
             raise ValueError("There is no predictor set for this generator and no model to load to")
@@ -92,6 +108,11 @@ class PredictorBasedGenerator(nn.Module):
         self.seed = seed
         self.mask_generator = mask_generator
         self.mask_rectangularizer = RectangularizeMasks('min')
+        # submodules of prediction.py:51-58 (the multi-patch shifter is not on the counterfactual path)
+        self.make_static = perturbation.MakeStatic(patch_size=self.predictor.patch_size)
+        self.shifter = perturbation.ShiftPatchesAndMask(
+            patch_size=self.predictor.patch_size, padding_mode='constant', max_shift_fraction=max_shift_fraction,
+            allow_fractional_shifts=False)
         self.x = self.mask = self.inp_shape = None
 
     # ---- attributes the callers read (prediction.py:131-214) ----
@@ -204,8 +225,18 @@ class PredictorBasedGenerator(nn.Module):
         elif isinstance(self.predictor, PretrainVisionTransformer) and \
                 not isinstance(self.predictor, PaddedVisionTransformer):
             kwargs['num_visible'] = num_visible
+        plain_vmae = isinstance(self.predictor, PretrainVisionTransformer) and not isinstance(
+            self.predictor, (ConjoinedPretrainVisionTransformer, PaddedVisionTransformer))
+        if isinstance(x, CounterfactualVideo) and not (plain_vmae and self.t_dim == 2):
+            x = x.materialize()  # other predictors take the materialised prompts (still one kernel, not a loop)
         if isinstance(self.predictor, (ConjoinedPretrainVisionTransformer, PaddedVisionTransformer)):
             y = self._predict_padded_or_conjoined(x, mask, *args, **kwargs)
+        elif isinstance(x, CounterfactualVideo):
+            # fused: the gather and the unpatchify read the virtual video; x_shift never touches HBM
+            norm = (IMAGENET_DEFAULT_MEAN, IMAGENET_DEFAULT_STD) if self.imagenet_normalize_inputs else None
+            y = self.predictor(x, mask, *args, input_norm=norm, **kwargs)
+            _, inv, n_vis = self.predictor.last_aux
+            y = unpatchify_scatter(y, x, inv, n_vis, self.patch_size)
         elif isinstance(self.predictor, PretrainVisionTransformer):
             xin = x.transpose(self.t_dim, self.c_dim) if self.t_dim != 1 else x  # a view, never materialised
             norm = (IMAGENET_DEFAULT_MEAN, IMAGENET_DEFAULT_STD) if self.imagenet_normalize_inputs else None
@@ -259,6 +290,79 @@ class PredictorBasedGenerator(nn.Module):
 
     def forward(self, x, mask=None, frame=None, *args, **kwargs):
         return self.predict(x, mask, frame, *args, **kwargs)
+
+    # ---- counterfactual prompts ----
+    def set_input(self, x, mask=None, make_mask=False, timestamps=None):
+        """prediction.py:703-724."""
+        shape = x.shape
+        if len(shape) == 4:
+            x = x.unsqueeze(1)
+        else:
+            assert len(shape) == 5, \
+                "Input must be a movie of shape [B,T,C,H,W]" + \
+                "or a single frame of shape [B,C,H,W]"
+        self.inp_shape = x.shape
+        self.x = x
+        self.B = self.inp_shape[0]
+        self.T = self.inp_shape[1]
+        self.C = self.inp_shape[2]
+        if mask is not None:
+            self.mask = mask
+        elif make_mask:
+            assert self.mask_generator is not None, "You need to have a mask generator to set a new mask"
+            self.mask = self.generate_mask(self.x)
+        if timestamps is not None:
+            self.timestamps = timestamps
+
+    def get_static_input(self, x=None):
+        """prediction.py:726-729."""
+        if x is None:
+            x = self.x
+        return torch.tile(x[:, 0:1], (1, x.size(1), 1, 1, 1))
+
+    def make_static_movie(self, x=None, T=None, frame=0):
+        """prediction.py:731-740."""
+        if x is None:
+            x = self.x
+        if T is None:
+            T = getattr(self.predictor, 'num_frames', 2)
+        if len(x.shape) == 4:
+            x = x[:, None]
+        assert len(x.shape) == 5, "x must be of shape [B,C,H,W] or [B,T,C,H,W], but is %s" % x.shape
+        return torch.tile(x[:, frame % x.size(1), None], (1, T, 1, 1, 1))
+
+    def _shift(self, x, mask, active_patches=None, shift=None, frame=1, virtual=False):
+        """prediction.py:756-779: ``shift`` is a mask shift (patch units)."""
+        if getattr(self, 'shifts', None) is None:
+            self.shifts = []
+        if active_patches is None:
+            active_patches = torch.ones_like(mask)
+        points = ~active_patches
+        x_shift, mask_shift = self.shifter(x, mask=torch.minimum(mask, active_patches), mask_shift=shift,
+                                           perturbation_points=points, frame=frame, virtual=virtual)
+        mask_shift = self.mask_rectangularizer(mask_shift)
+        self.shift = self.shifter.shift
+        self.shift = [self.shift[0] // self.patch_size[-2], self.shift[1] // self.patch_size[-1]]
+        self.shifts.append(np.array(self.shift))
+        return (x_shift, mask_shift)
+
+    def get_counterfactual_prediction(self, x, mask=None, active_patches=None, shift=None, fix_passive=False,
+                                      **kwargs):
+        """prediction.py:781-813."""
+        if len(x.shape) == 4:  # make into a 2-frame movie
+            x = x[:, None]
+        elif len(x.shape) == 3:
+            x = x[None, None]
+        if x.size(1) == 1:
+            x = self.make_static_movie(x, T=2)
+        if mask is None:
+            mask = self.get_zeros_mask(x)
+        if active_patches is None:
+            active_patches = self.get_zeros_mask(x)
+        if fix_passive:
+            x, _ = self.make_static(x, mask)
+        x_p, mask_p = self._shift(x, mask=mask, active_patches=active_patches, shift=shift, frame=1, virtual=True)
+        return self.predict(x_p, mask_p, frame=None, **kwargs)
 
     def predict_per_sample(self, x, masks, frame=-1, batch_size=None, split_samples=True, *args, **kwargs):
         """Run predictions in parallel for S sample masks (prediction.py:456-482)."""

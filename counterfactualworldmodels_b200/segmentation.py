@@ -1,0 +1,176 @@
+"""Host-side mirror of the counterfactual entry points of ``cwm/models/segmentation.py`` (``FlowGenerator`` :23-547),
+SURVEY.md section 8(f): the callers right above the VMAE hot path.
+
+Built so far (rank 1): ``create_motion_counterfactuals`` (:279-343) and ``predict_counterfactual_videos_and_flows``
+(:345-432) -- the per-sample Python loop over ``ShiftPatchesAndMask`` becomes one mask kernel plus a *virtual* video
+the VMAE forward reads directly, so the S prompts ``x_mocos`` (1.2 MB each) are never written to HBM.  RAFT stays out
+of scope: ``flow_model`` is a caller-supplied ``nn.Module`` (the reference's own constructor accepts one, :70-78);
+without it the flow entry points raise.
+
+Same method names, argument meaning and error behaviour as the reference.
+"""
+import numpy as np
+import torch
+from torch import nn
+
+from .perturbation import CounterfactualVideo, shift_patches_and_masks
+from .prediction import PredictorBasedGenerator
+
+
+class FlowGenerator(PredictorBasedGenerator):
+    """A wrapper for masked predictors that builds motion counterfactuals and (with a caller-supplied flow network)
+    runs the counterfactual movies through it (segmentation.py:23-41)."""
+
+    def __init__(self, *args, flow_model=None, raft_iters=24, **kwargs):
+        super().__init__(*args, **kwargs)
+        if flow_model is not None:
+            assert isinstance(flow_model, nn.Module)
+            self.flow_model = flow_model.eval().requires_grad_(False)
+        else:
+            self.flow_model = None  # the reference would load RAFT here (:70-75); RAFT is SURVEY 8(f) rank 3
+        self.raft_iters = raft_iters
+        self.shifts = None
+
+    # ---- small helpers (segmentation.py:130-140, :247-248) ----
+    @staticmethod
+    def batch_to_samples(flows, t=0, B=1):
+        assert len(flows.shape) == 5, flows.shape
+        x = flows[:, t]
+        return x.reshape(B, -1, *x.shape[1:]).permute(0, 2, 3, 4, 1)  # '(b s) c h w -> b c h w s'
+
+    def _batch_to_samples(self, flows, t=0):
+        assert self.x is not None
+        if len(flows.shape) != 5:
+            flows = flows.unsqueeze(1)
+            t = 0
+        return self.batch_to_samples(flows, t=t, B=self.x.size(0))
+
+    def reset_shifts(self):
+        self.shifts = []
+
+    def predict_flow(self, vid, backward=False, iters=None, **kwargs):
+        """segmentation.py:142-153."""
+        if self.flow_model is None:
+            raise RuntimeError("FlowGenerator.predict_flow needs a flow_model (RAFT is outside the B200 hot path; "
+                               "pass flow_model=<nn.Module> to the constructor)")
+        if iters is not None and hasattr(self.flow_model, 'iters'):
+            self.flow_model.iters = iters
+        return self.flow_model(vid, backward=backward, **kwargs).to(vid)
+
+    # ---- SURVEY 8(f) rank 1 ----
+    def create_motion_counterfactuals(self, x, masks, active_patches=None, shifts=None, frame=1, num_samples=None,
+                                      fix_passive=True, reset_shifts=False, virtual=False):
+        """Create motion counterfactuals by applying shifts to active_patches and no shifts to masks
+        (segmentation.py:279-343).  Returns ``(x_shift [B*S, T, C, H, W], mask_shift [B*S, N])`` after the mask
+        rectangulariser.  ``virtual=True`` (extension) returns the prompts as a ``CounterfactualVideo``."""
+        if (getattr(self, 'shifts', None) is None) or reset_shifts:
+            self.reset_shifts()
+        if len(masks.shape) == 2:
+            assert num_samples is not None, "Choose how many samples to shift with arg num_samples"
+            masks = masks.unsqueeze(-1).expand(-1, -1, num_samples)
+        else:
+            num_samples = masks.size(-1)
+        if active_patches is None:
+            active_patches = torch.ones_like(masks)
+        elif len(active_patches.shape) == 2:
+            active_patches = active_patches.unsqueeze(-1).expand(-1, -1, masks.size(-1))
+        B, N, S = masks.shape
+        assert active_patches.size(-1) in [1, S]
+        if active_patches.size(-1) == 1:
+            active_patches = active_patches.expand(-1, -1, S)
+
+        # `make_static_movie(x[:,0:1], T=2)` + `sample_tile(x, S)` (:309-312) are index arithmetic here: every
+        # frame of every sample reads frame 0 of image i // S
+        if fix_passive and x.size(1) != 2:
+            x = x[:, 0:1].expand(-1, 2, -1, -1, -1)
+        static_frame = 0 if fix_passive else -1
+        masks_bs = masks.transpose(1, 2).reshape(B * S, N)          # 'b n s -> (b s) n' (:313-314)
+        active_bs = active_patches.transpose(1, 2).reshape(B * S, N)
+
+        # set the shifts (:317-319)
+        self.shifter.set_shapes(x, mask=masks_bs)
+        self.shifter.set_num_shifts(S)
+        shifts = self.shifter._preprocess_shifts_sequence(shifts, is_mask_shift=True)
+        BS = B * S
+        if len(shifts) < BS:
+            # the reference indexes `shifts[i]` for i < B*S (:329): IndexError for B > 1 unless B*S shifts are given
+            raise IndexError("list index out of range")
+        shifts = [[int(s[0]), int(s[1])] for s in shifts[:BS]]
+        sample_image = torch.arange(BS, dtype=torch.int32, device=x.device) // S
+        video, mask_shift = shift_patches_and_masks(x, masks_bs, active_bs, shifts, self.patch_size, frame=frame,
+                                                    static_frame=static_frame, sample_image=sample_image)
+        for s in shifts:  # `self.shifts.append(np.array(self.shift))` per sample (:335-338)
+            px = (s[0] * self.patch_size[-2], s[1] * self.patch_size[-1])
+            self.shifter.shift = px
+            self.shift = [px[0] // self.patch_size[-2], px[1] // self.patch_size[-1]]
+            self.shifts.append(np.array(self.shift))
+        mask_shift = self.mask_rectangularizer(mask_shift)
+        return ((video if virtual else video.materialize()), mask_shift)
+
+    def predict_counterfactual_videos(self, x, active_patches, passive_patches=None, shifts=None, num_samples=8,
+                                      sample_batch_size=8, fix_passive=True, max_shift_fraction=None, frame=1,
+                                      **kwargs):
+        """The video half of ``predict_counterfactual_videos_and_flows`` (segmentation.py:345-430): the predicted
+        counterfactual movies ``y_mocos`` [B*S, T, C, H, W]."""
+        # preprocess the input to be a 2-frame movie, regardless of what it is (:364-373)
+        if len(x.shape) == 3:
+            x = x.unsqueeze(0).unsqueeze(1).expand(-1, 2, -1, -1, -1)
+            fix_passive = True
+        elif len(x.shape) == 4:
+            x = x.unsqueeze(1).expand(-1, 2, -1, -1, -1)
+            fix_passive = True
+        elif len(x.shape) == 5 and x.size(1) == 1:
+            x = x.expand(-1, 2, -1, -1, -1)
+        assert len(x.shape) == 5, x.shape
+        x = x[:, 0:2]
+        self.set_input(x)
+        self.reset_shifts()
+
+        # preprocess the patches and shifts so they all have the same number of samples (:379-410)
+        if passive_patches is None:
+            passive_patches = self.get_zeros_mask().unsqueeze(-1)
+        elif len(passive_patches.shape) == 2:
+            passive_patches = passive_patches.unsqueeze(-1)
+        if len(active_patches.shape) == 2:
+            active_patches = active_patches.unsqueeze(-1)
+        S = max(active_patches.size(-1), passive_patches.size(-1))
+        if (S == 1) and num_samples > 1:
+            S = num_samples
+        self.shifter.set_shapes(x, mask=active_patches[..., 0])
+        if shifts is None:
+            self.shifter.set_num_shifts(S)
+            if max_shift_fraction is not None:
+                self.shifter.max_shift_fraction = max_shift_fraction
+        else:
+            self.shifter.set_num_shifts(len(shifts) if not hasattr(shifts, 'shape') else shifts.shape[-1])
+        shifts = self.shifter._preprocess_shifts_sequence(shifts, is_mask_shift=True)
+        num_samples = len(shifts)
+        if (active_patches.size(-1) == 1) and (num_samples > 1):
+            active_patches = active_patches.expand(-1, -1, num_samples)
+        if (passive_patches.size(-1) == 1) and (num_samples > 1):
+            passive_patches = passive_patches.expand(-1, -1, num_samples)
+        assert active_patches.size(-1) == passive_patches.size(-1) == num_samples, \
+            (active_patches.shape, passive_patches.shape, num_samples)
+
+        x_mocos, masks_mocos = self.create_motion_counterfactuals(
+            x, masks=passive_patches, active_patches=active_patches, shifts=shifts, num_samples=num_samples,
+            fix_passive=fix_passive, reset_shifts=False, frame=frame, virtual=True)
+        # batch predict (:421-430)
+        return self.batch_predict_per_sample(x_mocos, masks=masks_mocos, frame=None,
+                                             batch_size=(sample_batch_size or x_mocos.size(0)), sample_dim=0,
+                                             **kwargs)
+
+    def predict_counterfactual_videos_and_flows(self, x, active_patches, passive_patches=None, shifts=None,
+                                                num_samples=8, sample_batch_size=8, fix_passive=True,
+                                                max_shift_fraction=None, frame=1, raft_iters=None, backward=False,
+                                                **kwargs):
+        """segmentation.py:345-432."""
+        y_mocos = self.predict_counterfactual_videos(
+            x, active_patches, passive_patches=passive_patches, shifts=shifts, num_samples=num_samples,
+            sample_batch_size=sample_batch_size, fix_passive=fix_passive, max_shift_fraction=max_shift_fraction,
+            frame=frame, **kwargs)
+        flow_mocos = self.predict_flow(y_mocos, backward=backward, iters=raft_iters)
+        return (y_mocos, flow_mocos)
+
+
+__all__ = ["FlowGenerator", "CounterfactualVideo"]

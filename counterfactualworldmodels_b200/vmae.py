@@ -483,7 +483,12 @@ class PretrainVisionTransformer(nn.Module):
                 "counterfactualworldmodels_b200: the VMAE forward only runs on a CUDA sm_100 (B200) device; "
                 "there is no CPU or PyTorch fallback")
         assert x.dim() == 5, x.shape
-        B, C, T, H, W = x.shape
+        from .perturbation import CounterfactualVideo
+        cf = x if isinstance(x, CounterfactualVideo) else None
+        if cf is not None:   # virtual video [S, T, C, H, W], consumed as its [S, C, T, H, W] view
+            B, T, C, H, W = x.shape
+        else:
+            B, C, T, H, W = x.shape
         self.device = x.device
         pt, ph, pw = self.patch_size
         assert (H % ph == 0) and (W % pw == 0), \
@@ -493,7 +498,7 @@ class PretrainVisionTransformer(nn.Module):
             raise NotImplementedError(
                 f"input size {(H, W)} differs from the model's image_size {tuple(self.image_size)}: the sinusoid "
                 "tables are built for num_patches tokens (the reference fails the same way at vmae.py:165)")
-        if x.dtype != torch.float32:
+        if cf is None and x.dtype != torch.float32:
             x = x.float()
         Ntot = self.num_patches
         mask = mask.reshape(B, -1)
@@ -524,8 +529,15 @@ class PretrainVisionTransformer(nn.Module):
             if input_norm is not None:
                 mean, std = _lib.float_array(input_norm[0]), _lib.float_array(input_norm[1])
             stream = torch.cuda.current_stream(x.device).cuda_stream
-            _lib.check(lib.cwm_vmae_forward(ctypes.byref(model), x.data_ptr(), _lib.strides5(x), B, mean, std,
-                                            perm.data_ptr(), n_vis, y.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+            if cf is not None:
+                src, keep = cf.c_struct()
+                _lib.check(lib.cwm_vmae_forward_cf(ctypes.byref(model), ctypes.byref(src), B, mean, std, perm.data_ptr(),
+                                                   n_vis, y.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+                del keep
+            else:
+                _lib.check(lib.cwm_vmae_forward(ctypes.byref(model), x.data_ptr(), _lib.strides5(x), B, mean, std,
+                                                perm.data_ptr(), n_vis, y.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                stream))
             self.last_forward_launches = lib.cwm_last_forward_launches() + 1  # + the compaction kernel
             self.last_aux = (perm, inv, n_vis)
         return y

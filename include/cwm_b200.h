@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define CWM_B200_ABI_VERSION 2
+#define CWM_B200_ABI_VERSION 3
 
 typedef void* cwm_stream_t; /* cudaStream_t */
 
@@ -184,6 +184,13 @@ int cwm_vmae_forward(const cwm_vmae_model* model, const float* x, const int64_t 
                      const float* norm_mean, const float* norm_std, const int32_t* perm, int Nvis, float* y,
                      void* workspace, size_t workspace_bytes, cwm_stream_t stream);
 
+/* Same forward with the input video given as a counterfactual descriptor (declared below, section 8(f) rank 1):
+ * equivalent to cwm_cf_build_videos + cwm_vmae_forward without materialising the videos. */
+struct cwm_cf_source;
+int cwm_vmae_forward_cf(const cwm_vmae_model* model, const struct cwm_cf_source* src, int S, const float* norm_mean,
+                        const float* norm_std, const int32_t* perm, int Nvis, float* y, void* workspace,
+                        size_t workspace_bytes, cwm_stream_t stream);
+
 /* ---- generic small attention (a6 for the context stream, a15 cross-attention) ------------------------
  * softmax(q k^T) v for head dims 32 / 64 / 96 / 128 / 192 with independently strided q, k, v:
  *   q row (b, i), head h starts at q + (b*Nq + i)*ldq + h*q_head_stride;  k, v likewise over Nk rows.
@@ -249,6 +256,60 @@ size_t cwm_cross_block_workspace_bytes(int B, int N, int M, int C, int Cs, int h
 int cwm_cross_block_forward(const cwm_cross_block_weights* w, float* x, float* src, int B, int N, int M, int C,
                             int Cs, int heads, int head_dim, int hidden, int hidden_s, float ln_eps, float scale,
                             void* workspace, size_t workspace_bytes, cwm_stream_t stream);
+
+/* ==== SURVEY.md section 8(f) rank 1: batched motion-counterfactual construction ===========================
+ * Replaces the per-sample Python loop `FlowGenerator.create_motion_counterfactuals`
+ * (cwm/models/segmentation.py:321-338) -> `PatchPerturbation.forward` (cwm/models/perturbation.py:99-112) ->
+ * `ShiftPatchesAndMask.perturb` (perturbation.py:245-289), and `MakeStatic.perturb` (perturbation.py:129-150).
+ * Conventions of the reference: masks are bytes with non-zero = masked; `active` is a mask whose ZERO entries are
+ * the patches to move; tokens are ordered (t, h, w); pt == 1; videos are logical [B, T, C, H, W].
+ * Integer work (masks) is bit-exact; pixels are bit-exact too: the blend `x_shift*(1-m) + x*m` (perturbation.py:
+ * 278-282) is evaluated literally in fp32 (one rounding per multiply and add, no fused multiply-add). */
+
+/* Masks of S samples in one launch.
+ *   passive, active  [S, T*n_h*n_w] bytes   (`masks`, `active_patches` after 'b n s -> (b s) n', segmentation.py:313-314)
+ *   mask_shift       [S, 2] int32 (my, mx): shift of the mask in patch units as applied by the mask padding
+ *                    (perturbation.py:234-243)
+ *   frame            the target frame (already reduced modulo T)
+ *   shifted_active   out [S, n_h*n_w]: the target frame of the shifted perturbation mask (perturbation.py:268-269,
+ *                    padding value 1); selects which patches of the target frame show the shifted image
+ *   mask_out         out [S, T*n_h*n_w]: `minimum(mask, mask_perturbed)` (perturbation.py:106-110), i.e.
+ *                    (passive | !active) & (t == frame ? shifted_active : active)                                */
+int cwm_cf_shift_masks(const uint8_t* passive, const uint8_t* active, const int32_t* mask_shift, int S, int T,
+                       int n_h, int n_w, int frame, uint8_t* shifted_active, uint8_t* mask_out, cwm_stream_t stream);
+
+/* The "virtual" counterfactual video of sample i (never materialised on the fused path):
+ *   v[i, t, c, y, x] = img[t', c, y, x]                                                  for t != frame
+ *   v[i, frame, c, y, x] = sh * (1 - m) + img[frame', c, y, x] * m,   m = shifted_active[i, y/ph, x/pw],
+ *   sh = img[frame', c, y - sy, x - sx] inside the image, 0 outside (perturbation.py:257-258), img = x[sample_image[i]],
+ *   t' = static_frame if static_frame >= 0 (`make_static_movie`, cwm/models/prediction.py:731-740) else t.       */
+typedef struct cwm_cf_source {
+  const float* x;               /* fp32 raw frames, logical [B_img, T, C, H, W] with element strides xs */
+  int64_t xs[5];
+  const int32_t* sample_image;  /* [S] image index of every sample (`sample_tile`, prediction.py:484-487) or NULL = 0 */
+  const int32_t* shift_px;      /* [S, 2] (sy, sx) pixel shift */
+  const uint8_t* shifted_active;/* [S, n_h*n_w] from cwm_cf_shift_masks */
+  int32_t frame;
+  int32_t static_frame;         /* -1, or the source frame every frame reads */
+} cwm_cf_source;
+
+/* Materialises the S counterfactual videos: out fp32 contiguous [S, T, C, H, W] (= `x_shift` of
+ * segmentation.py:339).  HBM-bound: 4*T*C*H*W bytes written per sample; the source image stays in L2. */
+int cwm_cf_build_videos(const cwm_cf_source* src, int S, int T, int C, int H, int W, int ph, int pw, float* out,
+                        cwm_stream_t stream);
+
+/* `MakeStatic.perturb` (perturbation.py:129-150): out[b,t] = (1 - m) * x[b,0] + m * x[b,t], m = mask[b,t,y/ph,x/pw]. */
+int cwm_cf_make_static(const float* x, const int64_t xs[5], const uint8_t* mask, int B, int T, int C, int H, int W,
+                       int ph, int pw, float* out, cwm_stream_t stream);
+
+/* Fused variants of cwm_patch_gather / cwm_unpatchify_scatter / cwm_vmae_forward that read the virtual video
+ * (`src`) instead of a tensor: the 1.2 MB/sample `x_shift` is never written to or read from HBM.  Same semantics
+ * as the tensor versions applied to cwm_cf_build_videos(src) viewed as [S, C, T, H, W]. */
+int cwm_patch_gather_cf(const cwm_cf_source* src, int S, int C, int T, int H, int W, int pt, int ph, int pw,
+                        const int32_t* perm, int Ntot, int rows_per_sample, const float* mean, const float* stdv,
+                        uint16_t* out, cwm_stream_t stream);
+int cwm_unpatchify_scatter_cf(const float* y, const cwm_cf_source* src, const int32_t* inv_perm, int S, int T, int C,
+                              int H, int W, int pt, int ph, int pw, int Nvis, float* out, cwm_stream_t stream);
 
 /* Number of kernel launches this thread enqueued through the library since the last cwm_vmae_forward began or
  * cwm_launch_count_reset() was called (for bench accounting). */
