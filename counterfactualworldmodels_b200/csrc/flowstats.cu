@@ -1,0 +1,291 @@
+// flowstats.cu -- SURVEY.md section 8(f) rank 2: flow-derived statistics of a counterfactual sweep on device.
+//
+//   FlowSampleFilter.compute_flow_magnitude / filter_by_* / forward      cwm/models/sampling.py:163-286
+//   FlowGenerator.compute_flow_samples_magnitude / compute_mean_motion_map  cwm/models/segmentation.py:250-276
+//
+// The flow samples are a logical [B, 2, H, W, S] fp32 tensor with arbitrary element strides: the reference hands a
+// permuted view of the flow network's [(b s), 2, H, W] output (segmentation.py:130-140), which is the layout these
+// kernels are fastest on (x contiguous); nothing is ever re-laid-out.  All kernels are HBM-bound streaming
+// reductions: every flow sample is read once per statistic (8*H*W bytes), outputs are O(B*S) or O(B*H*W).
+// Floating point: fp32 like the reference; sums over samples / pixels are tree- or atomics-ordered, so results match
+// the reference to rounding (tests: 1e-5 relative), thresholds are compared exactly as the reference does.
+#include "common.cuh"
+
+namespace cwm {
+
+struct FlowView {
+  const float* p;
+  int64_t sb, sc, sh, sw, ss;
+  int H, W, S;
+  __device__ __forceinline__ float mag(int b, int y, int x, int s) const {
+    const float* q = p + b * sb + y * sh + x * sw + s * ss;
+    const float u = __ldg(q), v = __ldg(q + sc);
+    // flow_samples.norm(dim=1, p=2) / square().sum().sqrt(): sqrt(u*u + v*v) with separate roundings
+    return __fsqrt_rn(__fadd_rn(__fmul_rn(u, u), __fmul_rn(v, v)));
+  }
+};
+
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (warp == 0) {
+    r = (lane < (blockDim.x >> 5)) ? sh[lane] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  }
+  __syncthreads();
+  return r;  // valid in warp 0
+}
+__device__ __forceinline__ float block_max(float v, float* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  float r = -INFINITY;
+  if (warp == 0) {
+    r = (lane < (blockDim.x >> 5)) ? sh[lane] : -INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, o));
+  }
+  __syncthreads();
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-sample statistics: one CTA per (b, s).
+//   stats[b, s, 0] = patch_flow_mag   (sampling.py:189-200: bilinear-downsampled magnitude averaged over the active
+//                                       patches of frame 2; align_corners=False source index like ATen)
+//   stats[b, s, 1] = flow_area        (:222-223: fraction of pixels with magnitude > threshold)
+//   stats[b, s, 2] = num_corners      (:232-247)
+//   stats[b, s, 3] = min magnitude, stats[b, s, 4] = max magnitude (per-sample normalisation, segmentation.py:252-254)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+flow_sample_stats_kernel(FlowView f, const uint8_t* __restrict__ active, int64_t ab, int64_t an, int64_t as_, int n_h,
+                         int n_w, float thr, float* __restrict__ stats) {
+  __shared__ float sh[8];
+  const int s = blockIdx.x % f.S, b = blockIdx.x / f.S;
+  const int HW = f.H * f.W;
+  float cnt = 0.f, mn = INFINITY, mx = -INFINITY;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    const int y = i / f.W, x = i - y * f.W;
+    const float m = f.mag(b, y, x, s);
+    cnt += (m > thr) ? 1.f : 0.f;
+    mn = fminf(mn, m);
+    mx = fmaxf(mx, m);
+  }
+  float psum = 0.f, pcnt = 0.f;
+  if (active != nullptr) {
+    const float sy = static_cast<float>(f.H) / n_h, sx = static_cast<float>(f.W) / n_w;
+    const int n = n_h * n_w;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      // active_second = 1 - active_patches[:, h*w:, :]  (sampling.py:190)
+      if (active[b * ab + (n + i) * an + s * as_] != 0) continue;
+      const int py = i / n_w, px = i - py * n_w;
+      // F.interpolate(mode='bilinear', align_corners=False): src = scale * (dst + 0.5) - 0.5, clamped at 0
+      float fy = fmaxf(sy * (py + 0.5f) - 0.5f, 0.f), fx = fmaxf(sx * (px + 0.5f) - 0.5f, 0.f);
+      const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+      const int y1 = min(y0 + 1, f.H - 1), x1 = min(x0 + 1, f.W - 1);
+      const float ly = fy - y0, lx = fx - x0;
+      const float v = (1.f - ly) * ((1.f - lx) * f.mag(b, y0, x0, s) + lx * f.mag(b, y0, x1, s)) +
+                      ly * ((1.f - lx) * f.mag(b, y1, x0, s) + lx * f.mag(b, y1, x1, s));
+      psum += v;
+      pcnt += 1.f;
+    }
+  }
+  const float t_cnt = block_sum(cnt, sh);
+  const float t_psum = block_sum(psum, sh);
+  const float t_pcnt = block_sum(pcnt, sh);
+  const float t_mn = -block_max(-mn, sh);
+  const float t_mx = block_max(mx, sh);
+  if (threadIdx.x == 0) {
+    float* o = stats + (static_cast<long long>(b) * f.S + s) * 5;
+    o[0] = t_psum / (t_pcnt + 1e-12f);
+    o[1] = t_cnt / static_cast<float>(HW);
+    const float c = ((f.mag(b, 0, 0, s) > thr) ? 1.f : 0.f) + ((f.mag(b, 0, f.W - 1, s) > thr) ? 1.f : 0.f) +
+                    ((f.mag(b, f.H - 1, 0, s) > thr) ? 1.f : 0.f) + ((f.mag(b, f.H - 1, f.W - 1, s) > thr) ? 1.f : 0.f);
+    o[2] = c;
+    o[3] = t_mn;
+    o[4] = t_mx;
+  }
+}
+
+// filter mask [B, S] from the statistics (sampling.py:202-247, :266-279); methods bit 0 = patch_magnitude,
+// bit 1 = flow_area, bit 2 = num_corners
+__global__ void flow_filter_mask_kernel(const float* __restrict__ stats, int n, int methods, float mag_thr, float area_thr,
+                                        float corners_thr, uint8_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* s = stats + static_cast<long long>(i) * 5;
+  bool f = false;
+  if (methods & 1) f = f || (s[0] < mag_thr);
+  if (methods & 2) f = f || (s[1] > area_thr);
+  if (methods & 4) f = f || (s[2] >= corners_thr);
+  out[i] = f ? 1 : 0;
+}
+
+// flow_samples[filter_mask] = 0  (sampling.py:282-284), in place on the strided view; one thread per element
+__global__ void __launch_bounds__(256)
+flow_zero_filtered_kernel(float* p, int64_t sb, int64_t sc, int64_t sh_, int64_t sw, int64_t ss, int H, int W, int S,
+                          const uint8_t* __restrict__ filt, long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int x = static_cast<int>(i % W);
+  long long r = i / W;
+  const int y = static_cast<int>(r % H);
+  r /= H;
+  const int c = static_cast<int>(r % 2);
+  r /= 2;
+  const int s = static_cast<int>(r % S);
+  const long long b = r / S;
+  if (filt[b * S + s]) p[b * sb + c * sc + y * sh_ + x * sw + s * ss] = 0.f;
+}
+
+// sum over samples of the (optionally per-sample normalised, optionally filtered) magnitude: one thread per pixel.
+//   out[b, y, x] (+)= sum_s w_s * g_s(mag),  g_s(m) = normalize_per_sample ? (m - min_s) / max(max_s - min_s, eps) : m
+// `accumulate` adds to out (multi-chunk / multi-rank partial sums).
+__global__ void __launch_bounds__(256)
+flow_magnitude_sum_kernel(FlowView f, const uint8_t* __restrict__ filt, const float* __restrict__ stats,
+                          int normalize_per_sample, float eps, int accumulate, long long total, float* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int x = static_cast<int>(i % f.W);
+  long long r = i / f.W;
+  const int y = static_cast<int>(r % f.H);
+  const int b = static_cast<int>(r / f.H);
+  float acc = 0.f;
+  for (int s = 0; s < f.S; ++s) {
+    const bool dropped = filt != nullptr && filt[b * f.S + s];
+    float m = dropped ? 0.f : f.mag(b, y, x, s);
+    if (normalize_per_sample) {
+      // a filtered sample is all zeros: min = max = 0 -> (0 - 0) / clamp(0, eps) = 0
+      const float* st = stats + (static_cast<long long>(b) * f.S + s) * 5;
+      const float mn = dropped ? 0.f : st[3], mx = dropped ? 0.f : st[4];
+      m = __fdiv_rn(m - mn, fmaxf(mx - mn, eps));
+    }
+    acc += m;
+  }
+  out[i] = accumulate ? out[i] + acc : acc;
+}
+
+// motion_map = sums / count (`flow_mags.mean(-1)`); then (optional) minus its min over (H, W), divided by max.clamp(eps)
+// (segmentation.py:268-275).  One CTA per image.
+__global__ void __launch_bounds__(1024)
+motion_map_finalize_kernel(const float* __restrict__ sums, int HW, float count, int normalize, float eps,
+                           float* __restrict__ out) {
+  __shared__ float sh[32];
+  __shared__ float s_mn, s_mx;
+  const float* in = sums + static_cast<long long>(blockIdx.x) * HW;
+  float* o = out + static_cast<long long>(blockIdx.x) * HW;
+  float mn = INFINITY, mx = -INFINITY;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    const float v = __fdiv_rn(in[i], count);
+    mn = fminf(mn, v);
+    mx = fmaxf(mx, v);
+  }
+  const float t_mn = -block_max(-mn, sh);
+  const float t_mx = block_max(mx, sh);
+  if (threadIdx.x == 0) { s_mn = t_mn; s_mx = t_mx; }
+  __syncthreads();
+  const float lo = normalize ? s_mn : 0.f;
+  const float den = normalize ? fmaxf(s_mx - s_mn, eps) : 1.f;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    const float v = __fdiv_rn(in[i], count);
+    o[i] = normalize ? __fdiv_rn(v - lo, den) : v;
+  }
+}
+
+static int make_view(const float* flows, const int64_t fs[5], int B, int H, int W, int S, FlowView* v, const char* who) {
+  if (!flows || !fs) return fail(CWM_ERR_INVALID, "%s: null pointer", who);
+  if (B < 0 || H <= 0 || W <= 0 || S < 0) return fail(CWM_ERR_INVALID, "%s: bad shape B=%d H=%d W=%d S=%d", who, B, H, W, S);
+  v->p = flows;
+  v->sb = fs[0]; v->sc = fs[1]; v->sh = fs[2]; v->sw = fs[3]; v->ss = fs[4];
+  v->H = H; v->W = W; v->S = S;
+  return CWM_OK;
+}
+
+}  // namespace cwm
+
+using namespace cwm;
+
+extern "C" int cwm_flow_sample_stats(const float* flows, const int64_t fs[5], int B, int H, int W, int S,
+                                     const uint8_t* active, const int64_t as[3], int n_h, int n_w,
+                                     float magnitude_threshold, float* stats, cwm_stream_t stream) {
+  FlowView v;
+  int rc = make_view(flows, fs, B, H, W, S, &v, "cwm_flow_sample_stats");
+  if (rc != CWM_OK) return rc;
+  CWM_REQUIRE(stats, "cwm_flow_sample_stats: null pointer");
+  CWM_REQUIRE(active == nullptr || (as && n_h > 0 && n_w > 0), "cwm_flow_sample_stats: active patches need strides and a grid");
+  if (B * S == 0) return CWM_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfileScope prof(st, "flow_sample_stats", 0.0, static_cast<double>(B) * S * H * W * 8.0);
+  flow_sample_stats_kernel<<<B * S, 256, 0, st>>>(v, active, active ? as[0] : 0, active ? as[1] : 0, active ? as[2] : 0,
+                                                  n_h, n_w, magnitude_threshold, stats);
+  CWM_LAUNCH_CHECK();
+  return CWM_OK;
+}
+
+extern "C" int cwm_flow_filter_mask(const float* stats, int B, int S, int methods, float magnitude_threshold,
+                                    float area_threshold, float corners_threshold, uint8_t* filter_mask,
+                                    cwm_stream_t stream) {
+  CWM_REQUIRE(stats && filter_mask, "cwm_flow_filter_mask: null pointer");
+  const int n = B * S;
+  if (n == 0) return CWM_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfileScope prof(st, "flow_filter_mask", 0.0, n * 21.0);
+  flow_filter_mask_kernel<<<(n + 255) / 256, 256, 0, st>>>(stats, n, methods, magnitude_threshold, area_threshold,
+                                                          corners_threshold, filter_mask);
+  CWM_LAUNCH_CHECK();
+  return CWM_OK;
+}
+
+extern "C" int cwm_flow_zero_filtered(float* flows, const int64_t fs[5], int B, int H, int W, int S,
+                                      const uint8_t* filter_mask, cwm_stream_t stream) {
+  FlowView v;
+  int rc = make_view(flows, fs, B, H, W, S, &v, "cwm_flow_zero_filtered");
+  if (rc != CWM_OK) return rc;
+  CWM_REQUIRE(filter_mask, "cwm_flow_zero_filtered: null pointer");
+  const long long total = static_cast<long long>(B) * S * 2 * H * W;
+  if (total == 0) return CWM_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfileScope prof(st, "flow_zero_filtered", 0.0, static_cast<double>(total) * 4.0);
+  flow_zero_filtered_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(flows, fs[0], fs[1], fs[2], fs[3],
+                                                                                        fs[4], H, W, S, filter_mask, total);
+  CWM_LAUNCH_CHECK();
+  return CWM_OK;
+}
+
+extern "C" int cwm_flow_magnitude_sum(const float* flows, const int64_t fs[5], int B, int H, int W, int S,
+                                      const uint8_t* filter_mask, const float* stats, int normalize_per_sample,
+                                      float eps, int accumulate, float* sums, cwm_stream_t stream) {
+  FlowView v;
+  int rc = make_view(flows, fs, B, H, W, S, &v, "cwm_flow_magnitude_sum");
+  if (rc != CWM_OK) return rc;
+  CWM_REQUIRE(sums, "cwm_flow_magnitude_sum: null pointer");
+  CWM_REQUIRE(!normalize_per_sample || stats, "cwm_flow_magnitude_sum: per-sample normalisation needs the statistics");
+  const long long total = static_cast<long long>(B) * H * W;
+  if (total == 0) return CWM_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfileScope prof(st, "flow_magnitude_sum", 0.0, static_cast<double>(total) * (8.0 * S + 4.0));
+  flow_magnitude_sum_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(v, filter_mask, stats,
+                                                                                        normalize_per_sample, eps,
+                                                                                        accumulate, total, sums);
+  CWM_LAUNCH_CHECK();
+  return CWM_OK;
+}
+
+extern "C" int cwm_motion_map_finalize(const float* sums, int B, int H, int W, float count, int normalize, float eps,
+                                       float* motion_map, cwm_stream_t stream) {
+  CWM_REQUIRE(sums && motion_map, "cwm_motion_map_finalize: null pointer");
+  CWM_REQUIRE(B >= 0 && H > 0 && W > 0 && count > 0.f, "cwm_motion_map_finalize: bad shape");
+  if (B == 0) return CWM_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfileScope prof(st, "motion_map_finalize", 0.0, static_cast<double>(B) * H * W * 12.0);
+  motion_map_finalize_kernel<<<B, 1024, 0, st>>>(sums, H * W, count, normalize, eps, motion_map);
+  CWM_LAUNCH_CHECK();
+  return CWM_OK;
+}

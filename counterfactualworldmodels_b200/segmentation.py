@@ -13,16 +13,27 @@ import numpy as np
 import torch
 from torch import nn
 
+from . import sampling
 from .perturbation import CounterfactualVideo, shift_patches_and_masks
 from .prediction import PredictorBasedGenerator
+from .sampling import FlowSampleFilter
 
 
 class FlowGenerator(PredictorBasedGenerator):
     """A wrapper for masked predictors that builds motion counterfactuals and (with a caller-supplied flow network)
     runs the counterfactual movies through it (segmentation.py:23-41)."""
 
-    def __init__(self, *args, flow_model=None, raft_iters=24, **kwargs):
+    default_flow_filter_params = {  # segmentation.py:29-34
+        'filter_methods': ['patch_magnitude', 'flow_area', 'num_corners'],
+        'flow_magnitude_threshold': 5.0,
+        'flow_area_threshold': 0.75,
+        'num_corners_threshold': 2
+    }
+
+    def __init__(self, *args, flow_model=None, raft_iters=24, flow_sample_filter=None, **kwargs):
         super().__init__(*args, **kwargs)
+        self.flow_sample_filter = flow_sample_filter if flow_sample_filter is not None else \
+            FlowSampleFilter(**self.default_flow_filter_params)
         if flow_model is not None:
             assert isinstance(flow_model, nn.Module)
             self.flow_model = flow_model.eval().requires_grad_(False)
@@ -56,6 +67,40 @@ class FlowGenerator(PredictorBasedGenerator):
         if iters is not None and hasattr(self.flow_model, 'iters'):
             self.flow_model.iters = iters
         return self.flow_model(vid, backward=backward, **kwargs).to(vid)
+
+    def set_flow_sample_filter(self, params=None):
+        """segmentation.py:92-96."""
+        self.flow_sample_filter = None if params is None else FlowSampleFilter(**params)
+
+    # ---- SURVEY 8(f) rank 2: flow-derived statistics ----
+    def compute_mean_motion_map(self, flows, normalize_per_sample=False, normalize=True, dim=-4, eps=1e-2,
+                                group=None, num_samples_total=None):
+        """segmentation.py:257-276: mean over the samples of the flow magnitude, normalised to [0, 1] per image.
+        ``flows`` [B, 2, H, W, S] (any strides), or an already computed distribution [B, 1, H, W] that is only
+        normalised.  Extension for sharded sweeps: with ``group`` (a torch.distributed process group) every rank passes
+        its local samples and the partial sums are combined with ONE all-reduce; ``num_samples_total`` is the S of
+        the whole sweep."""
+        if len(flows.shape) == 5:
+            if dim not in (-4, 1):
+                raise NotImplementedError("the flow channel axis must be dim 1 of [B, 2, H, W, S]")
+            sums = sampling.flow_magnitude_sum(flows, normalize_per_sample=normalize_per_sample, eps=eps)
+            count = flows.shape[-1]
+            if group is not None:
+                import torch.distributed as dist
+                dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+                count = num_samples_total if num_samples_total is not None else count * dist.get_world_size(group)
+        else:  # just normalize the input distribution
+            assert len(flows.shape) == 4 and flows.shape[1] == 1, flows.shape
+            sums, count, normalize = flows[:, 0].float(), 1, True
+        return sampling.motion_map_finalize(sums, count, normalize=normalize, eps=eps)
+
+    def filter_flow_samples(self, flows, active_patches, do_filter=True):
+        """The tail of ``sample_counterfactual_motion_map`` (segmentation.py:470-476): flows [(b s), T, 2, H, W] or
+        [(b s), 2, H, W] from the flow network -> [B, 2, H, W, S] view with the rejected samples zeroed."""
+        flows = self._batch_to_samples(flows)
+        if (self.flow_sample_filter is not None) and do_filter:
+            flows, _ = self.flow_sample_filter(flows, active_patches)
+        return flows
 
     # ---- SURVEY 8(f) rank 1 ----
     def create_motion_counterfactuals(self, x, masks, active_patches=None, shifts=None, frame=1, num_samples=None,

@@ -311,6 +311,40 @@ int cwm_patch_gather_cf(const cwm_cf_source* src, int S, int C, int T, int H, in
 int cwm_unpatchify_scatter_cf(const float* y, const cwm_cf_source* src, const int32_t* inv_perm, int S, int T, int C,
                               int H, int W, int pt, int ph, int pw, int Nvis, float* out, cwm_stream_t stream);
 
+/* ==== SURVEY.md section 8(f) rank 2: flow-derived statistics of a counterfactual sweep ======================
+ * `flows` is a logical [B, 2, H, W, S] fp32 tensor with arbitrary element strides fs[5] -- the reference hands the
+ * permuted view '(b s) c h w -> b c h w s' of the flow network's output (cwm/models/segmentation.py:130-140).
+ * fp32 like the reference; results match it to rounding (sums over pixels / samples are re-ordered). */
+
+/* Per-sample statistics, stats fp32 [B, S, 5]:
+ *   [0] patch_flow_mag: bilinear-downsampled (align_corners=False) magnitude averaged over the ACTIVE patches of
+ *       frame 2 (`FlowSampleFilter.compute_flow_magnitude`, cwm/models/sampling.py:163-203); active = `active_patches`
+ *       bytes, logical [B, 2*n_h*n_w, S] with element strides as[3], zero = active; NULL -> 0
+ *   [1] flow_area: fraction of pixels whose magnitude exceeds magnitude_threshold (sampling.py:214-224)
+ *   [2] num_corners: image corners whose magnitude exceeds magnitude_threshold (sampling.py:226-247)
+ *   [3], [4] min / max magnitude over the image (`compute_flow_samples_magnitude`, segmentation.py:250-255) */
+int cwm_flow_sample_stats(const float* flows, const int64_t fs[5], int B, int H, int W, int S, const uint8_t* active,
+                          const int64_t as[3], int n_h, int n_w, float magnitude_threshold, float* stats,
+                          cwm_stream_t stream);
+/* filter_mask[b, s] = OR over the enabled methods (bit 0 patch_magnitude: stats[0] < magnitude_threshold; bit 1
+ * flow_area: stats[1] > area_threshold; bit 2 num_corners: stats[2] >= corners_threshold) -- sampling.py:266-279. */
+int cwm_flow_filter_mask(const float* stats, int B, int S, int methods, float magnitude_threshold, float area_threshold,
+                         float corners_threshold, uint8_t* filter_mask, cwm_stream_t stream);
+/* `flow_samples[filter_mask] = 0` in place on the strided view (sampling.py:281-284). */
+int cwm_flow_zero_filtered(float* flows, const int64_t fs[5], int B, int H, int W, int S, const uint8_t* filter_mask,
+                           cwm_stream_t stream);
+/* sums[b, y, x] (+)= sum_s g_s(|flow[b, :, y, x, s]|): the numerator of `flow_mags.mean(-1)` (segmentation.py:257-267);
+ * filter_mask (optional) treats filtered samples as zero flow; normalize_per_sample applies
+ * (m - min_s) / max(max_s - min_s, eps) with stats from cwm_flow_sample_stats; accumulate != 0 adds to sums
+ * (chunks of a sweep; partial sums of the ranks are combined with one all-reduce). */
+int cwm_flow_magnitude_sum(const float* flows, const int64_t fs[5], int B, int H, int W, int S,
+                           const uint8_t* filter_mask, const float* stats, int normalize_per_sample, float eps,
+                           int accumulate, float* sums, cwm_stream_t stream);
+/* motion_map[b] = sums[b] / count, then (normalize != 0) minus its minimum and divided by its maximum clamped at eps
+ * (`compute_mean_motion_map`, segmentation.py:268-276).  sums / motion_map fp32 [B, H, W]. */
+int cwm_motion_map_finalize(const float* sums, int B, int H, int W, float count, int normalize, float eps,
+                            float* motion_map, cwm_stream_t stream);
+
 /* Number of kernel launches this thread enqueued through the library since the last cwm_vmae_forward began or
  * cwm_launch_count_reset() was called (for bench accounting). */
 int cwm_last_forward_launches(void);
