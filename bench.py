@@ -171,6 +171,70 @@ def cpu_oracle_frames_per_s(cfg_name, n_clumps, sample_frames, repeats, threads)
     return times
 
 
+def measure_cf_sweep(dev, workload, peaks, with_cpu):
+    """One counterfactual sweep per step: S = per-GPU batch samples of one image, each with one active 2x2 clump, one
+    passive 2x2 clump and a preset shift (ipynb:1726), through segmentation.FlowGenerator (fused construction)."""
+    import numpy as np
+    from counterfactualworldmodels_b200 import segmentation, synthetic, vmae
+    cfg_name, S, _ = WORKLOADS[workload]
+    if cfg_name == "imu400_base_4x4":
+        return {"workload": "cf_sweep", "skipped": "conjoined predictors take materialised prompts"}
+    model = vmae.PretrainVisionTransformer(**synthetic.model_kwargs(cfg_name))
+    synthetic.init_weights_(model, seed=0, style="reference")
+    model = model.to(dev).eval()
+    G = segmentation.FlowGenerator(predictor=model, imagenet_normalize_inputs=True, temporal_dim=2)
+    T, h, w = model.mask_size
+    rng = np.random.RandomState(0)
+    preset = [[2, 0], [0, 2], [-2, 0], [0, -2], [2, 2], [-2, -2], [2, -2], [-2, 2]]
+    active = torch.ones(1, T, h, w, S, dtype=torch.bool)
+    passive = torch.zeros(1, T, h, w, S, dtype=torch.bool)
+    passive[:, -1] = True
+    for s_ in range(S):
+        ay, ax = 2 * rng.randint(2, h // 4), 2 * rng.randint(2, w // 4)                    # left half, away from borders
+        py, px = 2 * rng.randint(2, h // 4), 2 * rng.randint(w // 4 + 2, w // 2 - 2)      # right half: never collides
+        active[0, -1, ay:ay + 2, ax:ax + 2, s_] = False
+        passive[0, -1, py:py + 2, px:px + 2, s_] = False
+    shifts = [preset[s_ % 8] for s_ in range(S)]
+    x_host = synthetic.make_video(1, synthetic.image_hw(cfg_name), seed=7)[:, 0].pin_memory()   # one image [1,3,H,W]
+    a_host, p_host = active.reshape(1, -1, S).pin_memory(), passive.reshape(1, -1, S).pin_memory()
+
+    def step():
+        x = x_host.to(dev, non_blocking=True)
+        a, p_ = a_host.to(dev, non_blocking=True), p_host.to(dev, non_blocking=True)
+        return G.predict_counterfactual_videos(x, a, passive_patches=p_, shifts=shifts, sample_batch_size=S)
+
+    for _ in range(3):
+        y = step()
+    torch.cuda.synchronize()
+    steps = 6
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        y = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    n_vis = h * w + 8
+    out = {"workload": f"cf_sweep_{cfg_name}_s{S}_fused", "value": round(S / ms * 1e3, 2), "unit": "frames/s",
+           "ms_per_step": round(ms, 3), "h2d_bytes_per_step": int(x_host.numel() * 4 + 2 * a_host.numel()),
+           "tensor_frac_of_sustained_peak": round(S / ms * 1e3 * flops_per_frame(cfg_name, n_vis) / 1e12 /
+                                                  peaks["tflops_sustained"], 4),
+           "api": "segmentation.FlowGenerator.predict_counterfactual_videos(image, active, passive, shifts)"}
+    if with_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import counterfactual_oracle as cfo
+        n = min(S, 16)
+        x2 = x_host.numpy()[:, None].repeat(2, axis=1)
+        t0 = time.perf_counter()
+        cfo.create_motion_counterfactuals(x2, p_host.numpy()[..., :n], a_host.numpy()[..., :n], shifts[:n],
+                                          tuple(model.patch_size), frame=1, fix_passive=True)
+        out["cpu_construction_ms_per_sample"] = round((time.perf_counter() - t0) / n * 1e3, 3)
+        out["cpu_construction_kind"] = "port (oracle/counterfactual_oracle.py, numpy, 1 thread), 16-sample bound"
+    del model, G
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -208,6 +272,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--also", default="large_4x4_b32_movability,imu400_base_4x4_b32",
                     help="extra workloads measured briefly (comma separated, '' to skip)")
+    ap.add_argument("--no-cf-sweep", dest="cf_sweep", action="store_false",
+                    help="skip the fused counterfactual-sweep line in `also`")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
 
@@ -381,6 +447,11 @@ def main():
                      "tensor_frac_of_sustained_peak": round(ra["fps"] / world * ra["flops_frame"] / 1e12 /
                                                             peaks["tflops_sustained"], 4),
                      "gflop_per_frame": round(ra["flops_frame"] / 1e9, 1)})
+
+    # the same workload driven from (image, patch descriptors, shifts) through the reference-facing
+    # `FlowGenerator.predict_counterfactual_videos` -- masks built on device, the 64 prompts never materialised
+    if world == 1 and args.cf_sweep:
+        also.append(measure_cf_sweep(dev, args.workload, peaks, not args.no_cpu_baseline))
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -9,6 +9,7 @@
 // Pixels are bit-exact with the reference: the blend `x_shift * (1 - m) + x * m` (perturbation.py:278-282) and
 // `(1 - m) * x0 + m * x` (perturbation.py:146) are evaluated literally with one rounding per multiply and add.
 #include "common.cuh"
+#include "pixelsrc.cuh"
 
 namespace cwm {
 
@@ -44,53 +45,9 @@ cf_shift_masks_kernel(const uint8_t* __restrict__ passive, const uint8_t* __rest
 // ---------------------------------------------------------------------------------------------
 // the virtual counterfactual video
 // ---------------------------------------------------------------------------------------------
-struct CfSrc {
-  const float* x;
-  int64_t sb, st, sc, sh, sw;  // logical [B_img, T, C, H, W]
-  const int32_t* sample_image;
-  const int32_t* shift_px;
-  const uint8_t* shifted_active;
-  int frame, static_frame;
-  int H, W, ph, pw, n_h, n_w;
-  int vec_ok;
-};
-
-// 4 consecutive pixels (x0 .. x0+3, x0 % 4 == 0, all inside one patch because pw % 4 == 0) of v[i, t, c, y, :]
+// CfSrc (the virtual video) lives in pixelsrc.cuh.
 __device__ __forceinline__ float4 cf_load4(const CfSrc& s, long long i, int t, int c, int y, int x0) {
-  const int b = s.sample_image ? s.sample_image[i] : 0;
-  const int ts = s.static_frame >= 0 ? s.static_frame : t;
-  const float* img = s.x + b * s.sb + ts * s.st + c * s.sc;
-  const float* src = img + y * s.sh + x0 * s.sw;
-  float4 o;
-  if (s.vec_ok) {
-    o = __ldg(reinterpret_cast<const float4*>(src));
-  } else {
-    o.x = __ldg(src); o.y = __ldg(src + s.sw); o.z = __ldg(src + 2 * s.sw); o.w = __ldg(src + 3 * s.sw);
-  }
-  if (t != s.frame) return o;
-  const float m = s.shifted_active[i * (s.n_h * s.n_w) + (y / s.ph) * s.n_w + x0 / s.pw] ? 1.f : 0.f;
-  const int sy = s.shift_px[2 * i], sx = s.shift_px[2 * i + 1];
-  const int ys = y - sy, xs = x0 - sx;
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);  // F.pad(..., value=0) (perturbation.py:258)
-  if (ys >= 0 && ys < s.H) {
-    const float* sp = img + ys * s.sh;
-    if (s.vec_ok && (sx & 3) == 0) {
-      if (xs >= 0 && xs < s.W) v = __ldg(reinterpret_cast<const float4*>(sp + xs));
-    } else {
-      if (xs >= 0 && xs < s.W) v.x = __ldg(sp + xs * s.sw);
-      if (xs + 1 >= 0 && xs + 1 < s.W) v.y = __ldg(sp + (xs + 1) * s.sw);
-      if (xs + 2 >= 0 && xs + 2 < s.W) v.z = __ldg(sp + (xs + 2) * s.sw);
-      if (xs + 3 >= 0 && xs + 3 < s.W) v.w = __ldg(sp + (xs + 3) * s.sw);
-    }
-  }
-  // x_shift * (1 - m) + x * m, literally (perturbation.py:278-282)
-  const float om = __fsub_rn(1.f, m);
-  float4 r;
-  r.x = __fadd_rn(__fmul_rn(v.x, om), __fmul_rn(o.x, m));
-  r.y = __fadd_rn(__fmul_rn(v.y, om), __fmul_rn(o.y, m));
-  r.z = __fadd_rn(__fmul_rn(v.z, om), __fmul_rn(o.z, m));
-  r.w = __fadd_rn(__fmul_rn(v.w, om), __fmul_rn(o.w, m));
-  return r;
+  return s.load4(i, t, c, y, x0);
 }
 
 // materialise: one thread per 4 output pixels, 16-byte coalesced stores.
@@ -296,6 +253,16 @@ extern "C" int cwm_cf_build_videos(const cwm_cf_source* src, int S, int T, int C
   const long long blocks = (total + threads - 1) / threads;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ProfileScope prof(st, "cf_build_videos", 0.0, static_cast<double>(total) * 16.0);
+  if (C == 3 && S <= 65535) {
+    UnpatchGeom g;
+    g.y = nullptr; g.inv_perm = nullptr; g.T = T; g.H = H; g.W = W; g.pt = 1; g.ph = ph; g.pw = pw; g.n_h = s.n_h;
+    g.n_w = s.n_w; g.Ntot = T * s.n_h * s.n_w; g.Nvis = g.Ntot; g.D = ph * pw * C; g.per_sample = T * H * (W / 4);
+    g.out = out;
+    dim3 grid((g.per_sample + threads - 1) / threads, S);
+    unpatchify2_kernel<CfSrc, 3><<<grid, threads, 0, st>>>(s, g);
+    CWM_LAUNCH_CHECK();
+    return CWM_OK;
+  }
   cf_build_videos_kernel<<<static_cast<unsigned>(blocks), threads, 0, st>>>(s, T, C, total, reinterpret_cast<float4*>(out));
   CWM_LAUNCH_CHECK();
   return CWM_OK;
@@ -349,6 +316,16 @@ extern "C" int cwm_patch_gather_cf(const cwm_cf_source* src, int S, int C, int T
   const long long blocks = (p.total + threads - 1) / threads;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ProfileScope prof(st, "patch_gather", 0.0, static_cast<double>(S) * rows_per_sample * K * 6.0);
+  if (p.K4 <= 256 && S <= 65535 && ph < 256 && pw < 256) {
+    GatherGeom g;
+    g.C = C; g.pt = pt; g.ph = ph; g.pw = pw; g.n_h = p.s.n_h; g.n_w = p.s.n_w; g.K4 = p.K4; g.tpb = 256 / p.K4;
+    g.perm = perm; g.Ntot = Ntot; g.rows_per_sample = rows_per_sample; g.n_tokens = p.n_tokens;
+    for (int c = 0; c < 8; ++c) { g.mean[c] = p.mean[c]; g.stdv[c] = p.stdv[c]; }
+    g.normalize = p.normalize; g.out = p.out;
+    launch_patch_gather2(p.s, g, S, st);
+    CWM_LAUNCH_CHECK();
+    return CWM_OK;
+  }
   cf_patch_gather_kernel<<<static_cast<unsigned>(blocks), threads, 0, st>>>(p);
   CWM_LAUNCH_CHECK();
   return CWM_OK;
@@ -376,6 +353,16 @@ extern "C" int cwm_unpatchify_scatter_cf(const float* y, const cwm_cf_source* sr
   const long long blocks = (p.total + threads - 1) / threads;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ProfileScope prof(st, "unpatchify_scatter", 0.0, static_cast<double>(p.total) * 4 * 8.0);
+  if (C == 3 && S <= 65535 && (y == nullptr || (reinterpret_cast<uintptr_t>(y) % 16 == 0 && p.D % 4 == 0)) &&
+      reinterpret_cast<uintptr_t>(out) % 16 == 0) {
+    UnpatchGeom g;
+    g.y = y; g.inv_perm = inv_perm; g.T = T; g.H = H; g.W = W; g.pt = pt; g.ph = ph; g.pw = pw; g.n_h = p.s.n_h;
+    g.n_w = p.s.n_w; g.Ntot = p.Ntot; g.Nvis = Nvis; g.D = p.D; g.per_sample = T * H * (W / 4); g.out = out;
+    dim3 grid((g.per_sample + threads - 1) / threads, S);
+    unpatchify2_kernel<CfSrc, 3><<<grid, threads, 0, st>>>(p.s, g);
+    CWM_LAUNCH_CHECK();
+    return CWM_OK;
+  }
   cf_unpatchify_scatter_kernel<<<static_cast<unsigned>(blocks), threads, 0, st>>>(p);
   CWM_LAUNCH_CHECK();
   return CWM_OK;

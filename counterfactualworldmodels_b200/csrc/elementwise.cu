@@ -2,6 +2,7 @@
 // mask-token fill (a10) and scatter+unpatchify (a12).  All are coalesced, 128-bit vectorised where alignment
 // allows, and sized so the grid is many waves over 148 SMs.
 #include "common.cuh"
+#include "pixelsrc.cuh"
 
 namespace cwm {
 
@@ -258,6 +259,27 @@ fill_mask_tokens_kernel(const float4* __restrict__ mask_token, const float4* __r
   x_full[(b * Ntot + Nvis + j) * C4 + c4] = o;
 }
 
+// v2: grid.y = sample, 32-bit index inside the sample (no 64-bit division on the address path); U float4 per thread
+template <int U>
+__global__ void __launch_bounds__(256)
+fill_mask_tokens2_kernel(const float4* __restrict__ mask_token, const float4* __restrict__ pos,
+                         const int32_t* __restrict__ perm, int Ntot, int Nvis, int C4, int per_sample,
+                         float4* __restrict__ x_full) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) * U;  // C4 % U == 0: the U vectors belong to one token
+  if (i >= per_sample) return;
+  const long long b = blockIdx.y;
+  const int j = i / C4;
+  const int c4 = i - j * C4;
+  const int tok = perm[b * Ntot + Nvis + j];
+  const float4* pe = pos + static_cast<long long>(tok) * C4 + c4;
+  float4 a[U], m[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) { a[u] = __ldg(pe + u); m[u] = __ldg(mask_token + c4 + u); }
+  float4* dst = x_full + (b * Ntot + Nvis + j) * C4 + c4;
+#pragma unroll
+  for (int u = 0; u < U; ++u) dst[u] = make_float4(m[u].x + a[u].x, m[u].y + a[u].y, m[u].z + a[u].z, m[u].w + a[u].w);
+}
+
 // ---------------------------------------------------------------------------------------------
 // scatter + unpatchify: one thread per 4 consecutive output pixels of a row (pw % 4 == 0 so the 4 pixels
 // belong to one patch).  Visible patches are copied from the raw input (bit-exact), masked patches come from
@@ -351,6 +373,19 @@ extern "C" int cwm_patch_gather(const float* x, const int64_t xs[5], int B, int 
   const long long blocks = (p.total + threads - 1) / threads;
   ProfileScope prof(static_cast<cudaStream_t>(stream), "patch_gather", 0.0,
                     static_cast<double>(B) * rows_per_sample * K * 6.0);
+  if (vec4 && p.K4 <= 256 && B <= 65535 && pt < 256 && ph < 256 && pw < 256) {
+    // v2: grid.y = sample, 32-bit index math, shared-memory decode of the patch-volume index (pixelsrc.cuh)
+    TensorSrc src;
+    src.x = x; src.sb = p.sb; src.st = p.st; src.sc = p.sc; src.sh = p.sh; src.sw = p.sw; src.vec_ok = p.vec_ok;
+    GatherGeom g;
+    g.C = C; g.pt = pt; g.ph = ph; g.pw = pw; g.n_h = p.n_h; g.n_w = p.n_w; g.K4 = p.K4; g.tpb = 256 / p.K4;
+    g.perm = perm; g.Ntot = Ntot; g.rows_per_sample = rows_per_sample; g.n_tokens = p.n_tokens;
+    for (int c = 0; c < 8; ++c) { g.mean[c] = p.mean[c]; g.stdv[c] = p.stdv[c]; }
+    g.normalize = p.normalize; g.out = p.out;
+    launch_patch_gather2(src, g, B, static_cast<cudaStream_t>(stream));
+    CWM_LAUNCH_CHECK();
+    return CWM_OK;
+  }
   if (vec4)
     patch_gather_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(p);
   else
@@ -402,6 +437,22 @@ extern "C" int cwm_fill_mask_tokens(const float* mask_token, const float* pos, c
   const long long blocks = (total + threads - 1) / threads;
   ProfileScope prof(static_cast<cudaStream_t>(stream), "fill_mask_tokens", 0.0,
                     static_cast<double>(B) * (Ntot - Nvis) * C * 4.0);
+  const long long per_sample = static_cast<long long>(Ntot - Nvis) * (C / 4);
+  if (B <= 65535 && per_sample < (1ll << 30)) {
+    if (false && (C / 4) % 4 == 0) {  // measured: 4 vectors per thread breaks store coalescing (27 -> 39 us)
+      dim3 grid(static_cast<unsigned>((per_sample / 4 + threads - 1) / threads), B);
+      fill_mask_tokens2_kernel<4><<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+          reinterpret_cast<const float4*>(mask_token), reinterpret_cast<const float4*>(pos), perm, Ntot, Nvis, C / 4,
+          static_cast<int>(per_sample), reinterpret_cast<float4*>(x_full));
+    } else {
+      dim3 grid(static_cast<unsigned>((per_sample + threads - 1) / threads), B);
+      fill_mask_tokens2_kernel<1><<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+          reinterpret_cast<const float4*>(mask_token), reinterpret_cast<const float4*>(pos), perm, Ntot, Nvis, C / 4,
+          static_cast<int>(per_sample), reinterpret_cast<float4*>(x_full));
+    }
+    CWM_LAUNCH_CHECK();
+    return CWM_OK;
+  }
   fill_mask_tokens_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const float4*>(mask_token), reinterpret_cast<const float4*>(pos), perm, Ntot, Nvis, C / 4,
       total, reinterpret_cast<float4*>(x_full));
@@ -437,6 +488,19 @@ extern "C" int cwm_unpatchify_scatter(const float* y, const float* x_raw, const 
   const long long blocks = (p.total + threads - 1) / threads;
   ProfileScope prof(static_cast<cudaStream_t>(stream), "unpatchify_scatter", 0.0,
                     static_cast<double>(p.total) * 4 * 8.0);
+  if (C == 3 && B <= 65535 && (y == nullptr || (reinterpret_cast<uintptr_t>(y) % 16 == 0 && p.D % 4 == 0)) &&
+      reinterpret_cast<uintptr_t>(out) % 16 == 0) {
+    // v2: one thread per 4 pixels x all channels, contiguous 16-byte reads of the prediction rows (pixelsrc.cuh)
+    TensorSrc src;
+    src.x = x_raw; src.sb = p.sb; src.st = p.st; src.sc = p.sc; src.sh = p.sh; src.sw = p.sw; src.vec_ok = p.vec_ok;
+    UnpatchGeom g;
+    g.y = y; g.inv_perm = inv_perm; g.T = T; g.H = H; g.W = W; g.pt = pt; g.ph = ph; g.pw = pw; g.n_h = p.n_h;
+    g.n_w = p.n_w; g.Ntot = p.Ntot; g.Nvis = Nvis; g.D = p.D; g.per_sample = T * H * (W / 4); g.out = out;
+    dim3 grid((g.per_sample + threads - 1) / threads, B);
+    unpatchify2_kernel<TensorSrc, 3><<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(src, g);
+    CWM_LAUNCH_CHECK();
+    return CWM_OK;
+  }
   unpatchify_scatter_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(p);
   CWM_LAUNCH_CHECK();
   return CWM_OK;

@@ -105,6 +105,7 @@ class PredictorBasedGenerator(nn.Module):
         self.imagenet_normalize_inputs = imagenet_normalize_inputs
         self.set_temporal_dim(temporal_dim)
         self.rng = np.random.RandomState(seed=seed)
+        self.torch_rng = torch.manual_seed(seed)  # prediction.py:44-45: the reference seeds the global generator
         self.seed = seed
         self.mask_generator = mask_generator
         self.mask_rectangularizer = RectangularizeMasks('min')

@@ -10,6 +10,7 @@ import torch
 from torch import nn
 
 from . import _lib
+from .masking import EnergySamplingMaskingGenerator, RotatedTableEnergyMaskingGenerator  # noqa: F401  (sampling.py:11-126)
 
 _METHOD_BITS = {'patch_magnitude': 1, 'flow_area': 2, 'num_corners': 4}
 

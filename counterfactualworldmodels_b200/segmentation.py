@@ -9,11 +9,14 @@ without it the flow entry points raise.
 
 Same method names, argument meaning and error behaviour as the reference.
 """
+import copy
+
 import numpy as np
 import torch
 from torch import nn
 
 from . import sampling
+from .masking import RotatedTableEnergyMaskingGenerator, boltzmann
 from .perturbation import CounterfactualVideo, shift_patches_and_masks
 from .prediction import PredictorBasedGenerator
 from .sampling import FlowSampleFilter
@@ -30,8 +33,23 @@ class FlowGenerator(PredictorBasedGenerator):
         'num_corners_threshold': 2
     }
 
-    def __init__(self, *args, flow_model=None, raft_iters=24, flow_sample_filter=None, **kwargs):
+    default_patch_sampling_kwargs = {  # segmentation.py:36-41
+        'energy_power': 1,
+        'eps': 1e-16,
+        'pool_mode': 'mean',
+        'resize': False
+    }
+
+    def __init__(self, *args, flow_model=None, raft_iters=24, flow_sample_filter=None,
+                 patch_sampling_func=RotatedTableEnergyMaskingGenerator,
+                 patch_sampling_kwargs=default_patch_sampling_kwargs, **kwargs):
         super().__init__(*args, **kwargs)
+        # submodule for sampling patches (segmentation.py:65-69): consumes one draw of self.rng like the reference
+        self._patch_sampling_func = patch_sampling_func
+        self._patch_sampling_kwargs = copy.deepcopy(self.default_patch_sampling_kwargs)
+        self._patch_sampling_kwargs.update(patch_sampling_kwargs)
+        self.patch_sampler = None
+        self.set_patch_sampler()
         self.flow_sample_filter = flow_sample_filter if flow_sample_filter is not None else \
             FlowSampleFilter(**self.default_flow_filter_params)
         if flow_model is not None:
@@ -67,6 +85,60 @@ class FlowGenerator(PredictorBasedGenerator):
         if iters is not None and hasattr(self.flow_model, 'iters'):
             self.flow_model.iters = iters
         return self.flow_model(vid, backward=backward, **kwargs).to(vid)
+
+    # ---- which patches to move (host-side mask bookkeeping, reference RNG streams) ----
+    def set_patch_sampler(self, num_visible=1, mask_ratio=None, **kwargs):
+        """segmentation.py:98-116."""
+        if (getattr(self, 'patch_sampler', None) is None) or len(kwargs.keys()):
+            _kwargs = copy.deepcopy(self._patch_sampling_kwargs)
+            _kwargs.update(kwargs)
+            try:
+                mask_shape = self.mask_shape
+            except Exception:
+                mask_shape = self.predictor.mask_size
+            self.patch_sampler = self._patch_sampling_func(
+                input_size=mask_shape, mask_ratio=(mask_ratio or 0), seed=self.rng.randint(9999), always_batch=True,
+                **_kwargs)
+        if mask_ratio is not None:
+            self.patch_sampler.mask_ratio = mask_ratio
+        elif num_visible is not None:
+            self.patch_sampler.num_visible = num_visible * self.patch_sampler.clumping_factor ** 2
+
+    def sample_patches_from_energy(self, energy=None, num_samples=10, num_visible=1, beta=None, **kwargs):
+        """segmentation.py:118-128: bool [B, N, num_samples], False = the sampled (visible / active) patches."""
+        self.set_patch_sampler(num_visible, **kwargs)
+        if num_visible == 0:
+            return torch.stack([self.get_zeros_mask() for _ in range(num_samples)], -1)
+        if energy is None:
+            assert self.x is not None
+            energy = torch.ones_like(self.x[:, 0, 0:1])
+        energy = boltzmann(energy, beta)
+        torch.manual_seed(self.rng.randint(99999))
+        return torch.stack([self.patch_sampler(energy) for _ in range(num_samples)], -1)
+
+    def sample_counterfactual_motion_map(self, x, active_sampling_distribution=None,
+                                         passive_sampling_distribution=None, active_patches=None,
+                                         passive_patches=None, num_active_patches=1, num_passive_patches=0,
+                                         num_samples=8, sample_batch_size=8, patch_sampling_kwargs={}, do_filter=True,
+                                         **kwargs):
+        """segmentation.py:434-476: sample the patches, predict the counterfactual movies and their flows, filter."""
+        self.set_input(x)
+
+        def _sample_patches(dist, num_visible):
+            return self.sample_patches_from_energy(energy=dist, num_samples=num_samples, num_visible=num_visible,
+                                                   **patch_sampling_kwargs)
+
+        if active_patches is None:
+            active_patches = _sample_patches(active_sampling_distribution, num_active_patches)
+        if passive_patches is None:
+            passive_patches = _sample_patches(passive_sampling_distribution, num_passive_patches)
+        ys, flows = self.predict_counterfactual_videos_and_flows(
+            x, active_patches=active_patches, passive_patches=passive_patches, num_samples=num_samples,
+            sample_batch_size=sample_batch_size, fix_passive=True, **kwargs)
+        flows = self._batch_to_samples(flows)
+        if (self.flow_sample_filter is not None) and do_filter:
+            flows, filter_mask = self.flow_sample_filter(flows, active_patches)
+        return (flows, active_patches, passive_patches)
 
     def set_flow_sample_filter(self, params=None):
         """segmentation.py:92-96."""

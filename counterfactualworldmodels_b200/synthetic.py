@@ -21,6 +21,14 @@ CONFIGS = {
     "small_4x4": dict(img_size=(64, 112), patch_size=(4, 4), encoder_embed_dim=192 + 64, encoder_depth=2,
                       encoder_num_heads=4, decoder_embed_dim=128, decoder_depth=2, decoder_num_heads=2, mlp_ratio=4,
                       qkv_bias=True, num_frames=2, tubelet_size=1),
+    # constructor options no BASELINE config uses but the reference supports (last paragraph)
+    "tiny_4x4_tube2": dict(img_size=32, patch_size=(4, 4), encoder_embed_dim=128, encoder_depth=2, encoder_num_heads=2,
+                           decoder_embed_dim=128, decoder_depth=1, decoder_num_heads=2, mlp_ratio=4, qkv_bias=True,
+                           num_frames=4, tubelet_size=2),
+    "tiny_8x8_layerscale_learnpos": dict(img_size=64, patch_size=(8, 8), encoder_embed_dim=256, encoder_depth=2,
+                                         encoder_num_heads=4, decoder_embed_dim=128, decoder_depth=2,
+                                         decoder_num_heads=2, mlp_ratio=4, qkv_bias=True, num_frames=2, tubelet_size=1,
+                                         init_values=0.5, use_learnable_pos_emb=True),
     # the BASELINE.json configurations (vmae.py:580-619)
     "base_8x8": dict(img_size=224, patch_size=(8, 8), encoder_embed_dim=768, encoder_depth=12, encoder_num_heads=12,
                      decoder_embed_dim=384, decoder_depth=4, decoder_num_heads=6, mlp_ratio=4, qkv_bias=True,
@@ -74,6 +82,10 @@ def init_weights_(model, seed=0, style="reference"):
             t = sd[name]
             if name.endswith(("mask_token", "null_token_enc", "null_token_dec", "dummy_token")):
                 v = torch.empty(t.shape).normal_(0, 0.02, generator=g).clamp_(-0.02, 0.02)
+            elif name.endswith(("gamma_1", "gamma_2")):  # layer scale (VideoMAE/utils.py:140-144)
+                v = 0.5 + torch.empty(t.shape).uniform_(-0.25, 0.25, generator=g)
+            elif name.endswith("pos_embed") and t.dim() == 3:  # learnable positional embedding (vmae.py:68-70)
+                v = torch.empty(t.shape).normal_(0, 0.2, generator=g)
             elif t.dim() == 1 and name.endswith(".weight"):  # LayerNorm weights (norm1 / norm2 / norm / norm*_cross)
                 v = torch.ones(t.shape)
                 if style == "perturbed":

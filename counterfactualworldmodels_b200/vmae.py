@@ -94,8 +94,6 @@ class Block(nn.Module):
                  drop_path=0., init_values=None, act_layer=nn.GELU, norm_layer=nn.LayerNorm, attn_head_dim=None,
                  in_dim=None, flash_attention=False):
         super().__init__()
-        if (init_values or 0) > 0:
-            raise NotImplementedError("layer-scale (init_values > 0) is not exercised by any CWM factory")
         if drop_path and drop_path > 0:
             raise NotImplementedError("drop_path_rate > 0 (training only)")
         self.norm1 = norm_layer(dim)
@@ -103,7 +101,11 @@ class Block(nn.Module):
                               proj_drop=drop, attn_head_dim=attn_head_dim, flash_attention=flash_attention)
         self.norm2 = norm_layer(dim)
         self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
-        self.gamma_1, self.gamma_2 = None, None
+        if (init_values or 0) > 0:  # layer scale (utils.py:140-144): folded into the proj / fc2 weights when packed
+            self.gamma_1 = nn.Parameter(init_values * torch.ones((dim)), requires_grad=True)
+            self.gamma_2 = nn.Parameter(init_values * torch.ones((dim)), requires_grad=True)
+        else:
+            self.gamma_1, self.gamma_2 = None, None
 
     def forward(self, x, attn_mask=None):
         _no_eager("Block")
@@ -152,8 +154,6 @@ class PretrainVisionTransformerEncoder(nn.Module):
         super().__init__()
         if embed_per_frame:
             raise NotImplementedError("embed_per_frame=True is not exercised by any CWM factory")
-        if use_learnable_pos_emb:
-            raise NotImplementedError("use_learnable_pos_emb=True is not exercised by any CWM factory")
         if num_classes:
             raise NotImplementedError("encoder_num_classes > 0 (classification head)")
         if block_func is not Block:
@@ -168,8 +168,13 @@ class PretrainVisionTransformerEncoder(nn.Module):
         self.image_size = img_size
         self.num_patches = self.patch_embed.num_patches
         self.num_frames = num_frames
-        self._learnable_pos_embed = False
-        self.pos_embed = get_sinusoid_encoding_table(self.num_patches, embed_dim)  # plain tensor (vmae.py:75)
+        if use_learnable_pos_emb:  # vmae.py:68-70, :87-88
+            self._learnable_pos_embed = True
+            self.pos_embed = nn.Parameter(torch.zeros(1, self.num_patches, embed_dim))
+            nn.init.trunc_normal_(self.pos_embed, mean=0., std=.02, a=-.02, b=.02)
+        else:
+            self._learnable_pos_embed = False
+            self.pos_embed = get_sinusoid_encoding_table(self.num_patches, embed_dim)  # plain tensor (vmae.py:75)
         self.blocks = nn.ModuleList([
             Block(dim=embed_dim, in_dim=embed_dim, num_heads=num_heads, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias,
                   qk_scale=qk_scale, drop=drop_rate, attn_drop=attn_drop_rate, drop_path=0.,
@@ -245,10 +250,19 @@ class _Packer:
                                               blk.attn.v_bias.detach()]))
             else:
                 w.b_qkv = None
-            w.w_proj, w.b_proj = self.f16(blk.attn.proj.weight), self.f32(blk.attn.proj.bias)
+            # layer scale x + gamma * f(x) (utils.py:151-152) == a row scaling of the last linear map of f
+            g1 = getattr(blk, "gamma_1", None)
+            g2 = getattr(blk, "gamma_2", None)
+            wp, bp = blk.attn.proj.weight.detach().float(), blk.attn.proj.bias.detach().float()
+            w2, b2 = blk.mlp.fc2.weight.detach().float(), blk.mlp.fc2.bias.detach().float()
+            if g1 is not None:
+                wp, bp = g1.detach().float()[:, None] * wp, g1.detach().float() * bp
+            if g2 is not None:
+                w2, b2 = g2.detach().float()[:, None] * w2, g2.detach().float() * b2
+            w.w_proj, w.b_proj = self.f16(wp), self.f32(bp)
             w.ln2_g, w.ln2_b = self.f32(blk.norm2.weight), self.f32(blk.norm2.bias)
             w.w_fc1, w.b_fc1 = self.f16(blk.mlp.fc1.weight), self.f32(blk.mlp.fc1.bias)
-            w.w_fc2, w.b_fc2 = self.f16(blk.mlp.fc2.weight), self.f32(blk.mlp.fc2.bias)
+            w.w_fc2, w.b_fc2 = self.f16(w2), self.f32(b2)
         self.keep.append(arr)
         return arr
 

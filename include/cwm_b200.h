@@ -264,7 +264,8 @@ int cwm_cross_block_forward(const cwm_cross_block_weights* w, float* x, float* s
  * Conventions of the reference: masks are bytes with non-zero = masked; `active` is a mask whose ZERO entries are
  * the patches to move; tokens are ordered (t, h, w); pt == 1; videos are logical [B, T, C, H, W].
  * Integer work (masks) is bit-exact; pixels are bit-exact too: the blend `x_shift*(1-m) + x*m` (perturbation.py:
- * 278-282) is evaluated literally in fp32 (one rounding per multiply and add, no fused multiply-add). */
+ * 278-282) is evaluated literally in fp32 (one rounding per multiply and add, no fused multiply-add), for FINITE
+ * pixel values (signed zeros included; an inf/NaN pixel that the reference would spread through `0 * inf` is not). */
 
 /* Masks of S samples in one launch.
  *   passive, active  [S, T*n_h*n_w] bytes   (`masks`, `active_patches` after 'b n s -> (b s) n', segmentation.py:313-314)

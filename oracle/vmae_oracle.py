@@ -76,7 +76,7 @@ def _linear(x, w, b, operand_dtype):
 
 
 def block_forward(x, sd, prefix, num_heads, eps, operand_dtype=None, taps=None):
-    """VideoMAE/utils.py:146-153 with gamma_* = None; Attention :87-121; Mlp :47-54."""
+    """VideoMAE/utils.py:146-153 (gamma_* optional); Attention :87-121; Mlp :47-54."""
     B, N, C = x.shape
     h = F.layer_norm(x, (C,), sd[prefix + "norm1.weight"], sd[prefix + "norm1.bias"], eps)
     qkv_bias = None
@@ -95,11 +95,15 @@ def block_forward(x, sd, prefix, num_heads, eps, operand_dtype=None, taps=None):
     if taps is not None:
         taps[prefix + "attn.core"] = a
     a = _linear(a, sd[prefix + "attn.proj.weight"], sd[prefix + "attn.proj.bias"], operand_dtype)  # :119
+    if (prefix + "gamma_1") in sd:                                                  # layer scale, utils.py:151
+        a = sd[prefix + "gamma_1"] * a
     x = x + a                                                                       # utils.py:148
     h = F.layer_norm(x, (C,), sd[prefix + "norm2.weight"], sd[prefix + "norm2.bias"], eps)
     h = _linear(h, sd[prefix + "mlp.fc1.weight"], sd[prefix + "mlp.fc1.bias"], operand_dtype)      # :48
     h = F.gelu(h)                                                                   # utils.py:49 (erf GELU)
     h = _linear(h, sd[prefix + "mlp.fc2.weight"], sd[prefix + "mlp.fc2.bias"], operand_dtype)      # :52
+    if (prefix + "gamma_2") in sd:                                                  # utils.py:152
+        h = sd[prefix + "gamma_2"] * h
     x = x + h                                                                       # utils.py:149
     return x
 
@@ -122,7 +126,10 @@ def vmae_forward(sd, x, mask, cfg, operand_dtype=None, taps=None, dtype=torch.fl
                    stride=(pt, ph, pw))
     tok = tok.flatten(2).transpose(1, 2)                                            # [B, Ntot, Ce], order (t,h,w)
     Ntot = tok.shape[1]
-    pos_e = sinusoid_table_cached(Ntot, Ce).to(dtype)                               # vmae.py:75,162
+    if "encoder.pos_embed" in sd:                                                   # use_learnable_pos_emb, vmae.py:68-70
+        pos_e = sd["encoder.pos_embed"]
+    else:
+        pos_e = sinusoid_table_cached(Ntot, Ce).to(dtype)                           # vmae.py:75,162
     tok = tok + pos_e                                                               # vmae.py:165
     if taps is not None:
         taps["tokens"] = tok

@@ -47,7 +47,7 @@ def golden_case_inputs(case):
     from counterfactualworldmodels_b200 import synthetic
     import make_golden
     cfg_name, B, style, wseed, dseed, _ = make_golden.CASES[case]
-    x = synthetic.make_video(B, synthetic.image_hw(cfg_name), seed=dseed)
+    x = synthetic.make_video(B, synthetic.image_hw(cfg_name), seed=dseed, T=synthetic.CONFIGS[cfg_name]["num_frames"])
     return cfg_name, B, style, wseed, x
 
 

@@ -14,6 +14,7 @@ DEV = "cuda:0"
 MAX_ABS, MEAN_ABS = 2e-2, 2e-3
 
 ALL_CASES = ["tiny_4x4_b2", "tiny_8x8_b3", "small_4x4_b2", "small_4x4_allvisible_frame1half",
+             "tiny_4x4_tube2_b2", "tiny_8x8_layerscale_learnpos_b2",  # tubelet 2 / layer scale + learnable pos-embed
              "base_8x8_b1_factual", "base_8x8_b2_counterfactual", "base_4x4_b1", "large_4x4_b1_factual"]
 
 
@@ -43,7 +44,8 @@ def test_forward_matches_reference_fixture(case):
     assert np.array_equal(perm.cpu().numpy(), perm_o) and n_vis == int(nvis_o[0])
 
 
-@pytest.mark.parametrize("case", ["tiny_4x4_b2", "small_4x4_b2", "base_8x8_b2_counterfactual"])
+@pytest.mark.parametrize("case", ["tiny_4x4_b2", "small_4x4_b2", "base_8x8_b2_counterfactual", "tiny_4x4_tube2_b2",
+                                  "tiny_8x8_layerscale_learnpos_b2"])
 def test_predict_wrapper_matches_reference_video(case):
     """`PredictorBasedGenerator.predict(x, mask, frame=None)` with raw [0,1] input (fused normalisation)."""
     g = load_golden(case)

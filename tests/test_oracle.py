@@ -10,7 +10,8 @@ import vmae_oracle as oracle
 from conftest import golden_case_inputs, load_golden
 from counterfactualworldmodels_b200 import synthetic, vmae
 
-FAST_CASES = ["tiny_4x4_b2", "tiny_8x8_b3", "small_4x4_b2", "small_4x4_allvisible_frame1half", "base_8x8_b1_factual"]
+FAST_CASES = ["tiny_4x4_b2", "tiny_8x8_b3", "small_4x4_b2", "small_4x4_allvisible_frame1half", "base_8x8_b1_factual",
+              "tiny_4x4_tube2_b2", "tiny_8x8_layerscale_learnpos_b2"]
 
 
 def _our_state_dict(cfg_name, wseed, style):

@@ -37,7 +37,79 @@ CASES = {
     "attn_dec_large": ("attn", 32, 6272, 8),
     "attn_dec_large_b6": ("attn", 6, 6272, 8),
     "ln_base_enc": ("ln", 50432, 768),
+    # HBM-bound pixel <-> token kernels at base 8x8 batch 64 / large 4x4 batch 32 (a1+a2, a10, a12) and the
+    # materialising counterfactual-construction kernel
+    "gather_base": ("gather", 64, 8, 788),
+    "gather_4x4": ("gather", 32, 4, 3140),
+    "fillmask_base": ("fillmask", 64, 1568, 788, 384),
+    "fillmask_large": ("fillmask", 32, 6272, 3140, 512),
+    "unpatchify_base": ("unpatch", 64, 8, 788),
+    "unpatchify_4x4": ("unpatch", 32, 4, 3140),
+    "cf_build_256": ("cfbuild", 256, 8),
 }
+
+
+def pixel_case(name):
+    """The HBM-bound kernels, called through the C ABI on rotating buffers (> 126 MB in total)."""
+    import ctypes
+    from counterfactualworldmodels_b200 import perturbation, synthetic
+    from counterfactualworldmodels_b200.vmae import compact_mask
+    lib = _lib.load()
+    kind = CASES[name][0]
+    stream = lambda: torch.cuda.current_stream().cuda_stream
+    if kind == "fillmask":
+        _, B, Ntot, Nvis, C = CASES[name]
+        mask = torch.ones(B, Ntot, dtype=torch.bool, device=DEV)
+        mask[:, :Nvis] = False
+        perm, _, _ = compact_mask(mask)
+        tok, pos = torch.randn(C, device=DEV), torch.randn(Ntot, C, device=DEV)
+        nbuf = max(2, int(300e6 // (B * Ntot * C * 4)) + 1)
+        outs = [torch.empty(B, Ntot, C, device=DEV) for _ in range(nbuf)]
+        def call(i):
+            _lib.check(lib.cwm_fill_mask_tokens(tok.data_ptr(), pos.data_ptr(), perm.data_ptr(), B, Ntot, Nvis, C,
+                                                outs[i % nbuf].data_ptr(), stream()))
+        return call, 0.0, B * (Ntot - Nvis) * C * 4
+    if kind == "cfbuild":
+        _, S, P = CASES[name]
+        h = 224 // P
+        x = synthetic.make_video(1, (224, 224), seed=0).to(DEV)
+        active = torch.ones(S, 2, h, h, dtype=torch.bool, device=DEV)
+        active[:, 1, 5:7, 9:11] = False
+        passive = torch.zeros(S, 2, h, h, dtype=torch.bool, device=DEV)
+        passive[:, 1] = True
+        video, _ = perturbation.shift_patches_and_masks(x, passive.reshape(S, -1), active.reshape(S, -1),
+                                                        [[1, -2]] * S, (1, P, P), frame=1, static_frame=0)
+        src, keep = video.c_struct()
+        outs = [torch.empty(S, 2, 3, 224, 224, device=DEV) for _ in range(2)]
+        def call(i, keep=keep):
+            _lib.check(lib.cwm_cf_build_videos(ctypes.byref(src), S, 2, 3, 224, 224, P, P, outs[i % 2].data_ptr(),
+                                               stream()))
+        return call, 0.0, S * 2 * 3 * 224 * 224 * 4
+    _, B, P, Nvis = CASES[name]
+    n = (224 // P) ** 2
+    nbuf = max(2, int(300e6 // (B * 2 * 3 * 224 * 224 * 4)) + 1)
+    xs = [torch.rand(B, 2, 3, 224, 224, device=DEV) for _ in range(nbuf)]
+    mask = torch.ones(B, 2 * n, dtype=torch.bool, device=DEV)
+    mask[:, :n] = False
+    mask[:, n + 7:n + 7 + (Nvis - n)] = False
+    perm, inv, _ = compact_mask(mask)
+    K = 3 * P * P
+    mean, std = _lib.float_array((0.485, 0.456, 0.406)), _lib.float_array((0.229, 0.224, 0.225))
+    if kind == "gather":
+        outs = [torch.empty(B * Nvis, K, device=DEV, dtype=torch.float16) for _ in range(nbuf)]
+        def call(i):
+            xv = xs[i % nbuf].transpose(1, 2)  # the [B, C, T, H, W] view the reference hands over
+            _lib.check(lib.cwm_patch_gather(xv.data_ptr(), _lib.strides5(xv), B, 3, 2, 224, 224, 1, P, P, perm.data_ptr(),
+                                            2 * n, Nvis, mean, std, outs[i % nbuf].data_ptr(), stream()))
+        return call, 0.0, B * Nvis * K * 6
+    Nmask = 2 * n - Nvis
+    ys = [torch.randn(B, Nmask, K, device=DEV) for _ in range(nbuf)]
+    outs = [torch.empty(B, 2, 3, 224, 224, device=DEV) for _ in range(nbuf)]
+    def call(i):
+        x = xs[i % nbuf]
+        _lib.check(lib.cwm_unpatchify_scatter(ys[i % nbuf].data_ptr(), x.data_ptr(), _lib.strides5(x), inv.data_ptr(), B,
+                                              2, 3, 224, 224, 1, P, P, Nvis, outs[i % nbuf].data_ptr(), stream()))
+    return call, 0.0, B * 2 * 3 * 224 * 224 * 8
 
 
 def run_case(name, iters=5):
@@ -63,6 +135,8 @@ def run_case(name, iters=5):
         def call(i):
             ops.attention_f16(qkv[i % nbuf], B, N, H)
         flops, byts = 4.0 * B * H * N * N * 64, B * N * H * 64 * 2 * 4
+    elif kind in ("gather", "unpatch", "fillmask", "cfbuild"):
+        call, flops, byts = pixel_case(name)
     else:
         _, M, C = CASES[name]
         nbuf = max(2, int(200e6 // (M * C * 4)) + 1)
