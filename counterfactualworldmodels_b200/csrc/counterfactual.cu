@@ -253,13 +253,12 @@ extern "C" int cwm_cf_build_videos(const cwm_cf_source* src, int S, int T, int C
   const long long blocks = (total + threads - 1) / threads;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ProfileScope prof(st, "cf_build_videos", 0.0, static_cast<double>(total) * 16.0);
-  if (C == 3 && S <= 65535) {
+  if (C == 3 && S <= 65535 && W / 4 <= 256) {
     UnpatchGeom g;
     g.y = nullptr; g.inv_perm = nullptr; g.T = T; g.H = H; g.W = W; g.pt = 1; g.ph = ph; g.pw = pw; g.n_h = s.n_h;
     g.n_w = s.n_w; g.Ntot = T * s.n_h * s.n_w; g.Nvis = g.Ntot; g.D = ph * pw * C; g.per_sample = T * H * (W / 4);
     g.out = out;
-    dim3 grid((g.per_sample + threads - 1) / threads, S);
-    unpatchify2_kernel<CfSrc, 3><<<grid, threads, 0, st>>>(s, g);
+    launch_unpatchify2(s, g, S, st);
     CWM_LAUNCH_CHECK();
     return CWM_OK;
   }
@@ -353,13 +352,12 @@ extern "C" int cwm_unpatchify_scatter_cf(const float* y, const cwm_cf_source* sr
   const long long blocks = (p.total + threads - 1) / threads;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ProfileScope prof(st, "unpatchify_scatter", 0.0, static_cast<double>(p.total) * 4 * 8.0);
-  if (C == 3 && S <= 65535 && (y == nullptr || (reinterpret_cast<uintptr_t>(y) % 16 == 0 && p.D % 4 == 0)) &&
+  if (C == 3 && S <= 65535 && W / 4 <= 256 && (y == nullptr || (reinterpret_cast<uintptr_t>(y) % 16 == 0 && p.D % 4 == 0)) &&
       reinterpret_cast<uintptr_t>(out) % 16 == 0) {
     UnpatchGeom g;
     g.y = y; g.inv_perm = inv_perm; g.T = T; g.H = H; g.W = W; g.pt = pt; g.ph = ph; g.pw = pw; g.n_h = p.s.n_h;
     g.n_w = p.s.n_w; g.Ntot = p.Ntot; g.Nvis = Nvis; g.D = p.D; g.per_sample = T * H * (W / 4); g.out = out;
-    dim3 grid((g.per_sample + threads - 1) / threads, S);
-    unpatchify2_kernel<CfSrc, 3><<<grid, threads, 0, st>>>(p.s, g);
+    launch_unpatchify2(p.s, g, S, st);
     CWM_LAUNCH_CHECK();
     return CWM_OK;
   }

@@ -488,7 +488,7 @@ extern "C" int cwm_unpatchify_scatter(const float* y, const float* x_raw, const 
   const long long blocks = (p.total + threads - 1) / threads;
   ProfileScope prof(static_cast<cudaStream_t>(stream), "unpatchify_scatter", 0.0,
                     static_cast<double>(p.total) * 4 * 8.0);
-  if (C == 3 && B <= 65535 && (y == nullptr || (reinterpret_cast<uintptr_t>(y) % 16 == 0 && p.D % 4 == 0)) &&
+  if (C == 3 && B <= 65535 && W / 4 <= 256 && (y == nullptr || (reinterpret_cast<uintptr_t>(y) % 16 == 0 && p.D % 4 == 0)) &&
       reinterpret_cast<uintptr_t>(out) % 16 == 0) {
     // v2: one thread per 4 pixels x all channels, contiguous 16-byte reads of the prediction rows (pixelsrc.cuh)
     TensorSrc src;
@@ -496,8 +496,7 @@ extern "C" int cwm_unpatchify_scatter(const float* y, const float* x_raw, const 
     UnpatchGeom g;
     g.y = y; g.inv_perm = inv_perm; g.T = T; g.H = H; g.W = W; g.pt = pt; g.ph = ph; g.pw = pw; g.n_h = p.n_h;
     g.n_w = p.n_w; g.Ntot = p.Ntot; g.Nvis = Nvis; g.D = p.D; g.per_sample = T * H * (W / 4); g.out = out;
-    dim3 grid((g.per_sample + threads - 1) / threads, B);
-    unpatchify2_kernel<TensorSrc, 3><<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(src, g);
+    launch_unpatchify2(src, g, B, static_cast<cudaStream_t>(stream));
     CWM_LAUNCH_CHECK();
     return CWM_OK;
   }

@@ -57,29 +57,54 @@ __device__ __forceinline__ float block_max(float v, float* sh) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// per-sample statistics: one CTA per (b, s).
+// per-sample statistics: kStatChunks CTAs per (b, s), each streaming a slice of the image (16-byte loads when the
+// rows are contiguous), combined with order-independent atomics -- a pixel COUNT (exact in fp32 up to 2^24) and
+// min / max on the bit patterns of the non-negative magnitudes -- so the result is deterministic.  Chunk 0 also
+// evaluates the few active patches and the corners.  acc[b, s, :] = {patch sum, patch count, pixels above the
+// threshold, corners, min bits, max bits} (zero / +inf-initialised by the host wrapper); flow_stats_finalize_kernel
+// turns it into
 //   stats[b, s, 0] = patch_flow_mag   (sampling.py:189-200: bilinear-downsampled magnitude averaged over the active
 //                                       patches of frame 2; align_corners=False source index like ATen)
 //   stats[b, s, 1] = flow_area        (:222-223: fraction of pixels with magnitude > threshold)
 //   stats[b, s, 2] = num_corners      (:232-247)
 //   stats[b, s, 3] = min magnitude, stats[b, s, 4] = max magnitude (per-sample normalisation, segmentation.py:252-254)
 // ---------------------------------------------------------------------------------------------
+constexpr int kStatChunks = 8;
+
 __global__ void __launch_bounds__(256)
 flow_sample_stats_kernel(FlowView f, const uint8_t* __restrict__ active, int64_t ab, int64_t an, int64_t as_, int n_h,
-                         int n_w, float thr, float* __restrict__ stats) {
+                         int n_w, float thr, int vec_ok, float* __restrict__ acc) {
   __shared__ float sh[8];
   const int s = blockIdx.x % f.S, b = blockIdx.x / f.S;
+  const int chunk = blockIdx.y;
   const int HW = f.H * f.W;
-  float cnt = 0.f, mn = INFINITY, mx = -INFINITY;
-  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
-    const int y = i / f.W, x = i - y * f.W;
-    const float m = f.mag(b, y, x, s);
-    cnt += (m > thr) ? 1.f : 0.f;
-    mn = fminf(mn, m);
-    mx = fmaxf(mx, m);
+  float cnt = 0.f, mn = INFINITY, mx = 0.f;
+  if (vec_ok) {  // sw == 1, W % 4 == 0, 16-byte aligned rows
+    const int W4 = f.W >> 2, n4 = HW >> 2;
+    const float* base = f.p + b * f.sb + s * f.ss;
+    for (int i = chunk * blockDim.x + threadIdx.x; i < n4; i += blockDim.x * kStatChunks) {
+      const int y = i / W4, x4 = i - y * W4;
+      const float4 u = __ldg(reinterpret_cast<const float4*>(base + y * f.sh) + x4);
+      const float4 v = __ldg(reinterpret_cast<const float4*>(base + f.sc + y * f.sh) + x4);
+      const float m0 = __fsqrt_rn(__fadd_rn(__fmul_rn(u.x, u.x), __fmul_rn(v.x, v.x)));
+      const float m1 = __fsqrt_rn(__fadd_rn(__fmul_rn(u.y, u.y), __fmul_rn(v.y, v.y)));
+      const float m2 = __fsqrt_rn(__fadd_rn(__fmul_rn(u.z, u.z), __fmul_rn(v.z, v.z)));
+      const float m3 = __fsqrt_rn(__fadd_rn(__fmul_rn(u.w, u.w), __fmul_rn(v.w, v.w)));
+      cnt += ((m0 > thr) ? 1.f : 0.f) + ((m1 > thr) ? 1.f : 0.f) + ((m2 > thr) ? 1.f : 0.f) + ((m3 > thr) ? 1.f : 0.f);
+      mn = fminf(fminf(mn, m0), fminf(m1, fminf(m2, m3)));
+      mx = fmaxf(fmaxf(mx, m0), fmaxf(m1, fmaxf(m2, m3)));
+    }
+  } else {
+    for (int i = chunk * blockDim.x + threadIdx.x; i < HW; i += blockDim.x * kStatChunks) {
+      const int y = i / f.W, x = i - y * f.W;
+      const float m = f.mag(b, y, x, s);
+      cnt += (m > thr) ? 1.f : 0.f;
+      mn = fminf(mn, m);
+      mx = fmaxf(mx, m);
+    }
   }
   float psum = 0.f, pcnt = 0.f;
-  if (active != nullptr) {
+  if (chunk == 0 && active != nullptr) {
     const float sy = static_cast<float>(f.H) / n_h, sx = static_cast<float>(f.W) / n_w;
     const int n = n_h * n_w;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -98,20 +123,45 @@ flow_sample_stats_kernel(FlowView f, const uint8_t* __restrict__ active, int64_t
     }
   }
   const float t_cnt = block_sum(cnt, sh);
-  const float t_psum = block_sum(psum, sh);
-  const float t_pcnt = block_sum(pcnt, sh);
   const float t_mn = -block_max(-mn, sh);
   const float t_mx = block_max(mx, sh);
-  if (threadIdx.x == 0) {
-    float* o = stats + (static_cast<long long>(b) * f.S + s) * 5;
-    o[0] = t_psum / (t_pcnt + 1e-12f);
-    o[1] = t_cnt / static_cast<float>(HW);
-    const float c = ((f.mag(b, 0, 0, s) > thr) ? 1.f : 0.f) + ((f.mag(b, 0, f.W - 1, s) > thr) ? 1.f : 0.f) +
-                    ((f.mag(b, f.H - 1, 0, s) > thr) ? 1.f : 0.f) + ((f.mag(b, f.H - 1, f.W - 1, s) > thr) ? 1.f : 0.f);
-    o[2] = c;
-    o[3] = t_mn;
-    o[4] = t_mx;
+  float* o = acc + (static_cast<long long>(b) * f.S + s) * 6;
+  if (chunk == 0) {  // block-uniform branch: the patch sums are written by exactly one CTA (deterministic order)
+    const float t_psum = block_sum(psum, sh);
+    const float t_pcnt = block_sum(pcnt, sh);
+    if (threadIdx.x == 0) {
+      o[0] = t_psum;
+      o[1] = t_pcnt;
+      o[3] = ((f.mag(b, 0, 0, s) > thr) ? 1.f : 0.f) + ((f.mag(b, 0, f.W - 1, s) > thr) ? 1.f : 0.f) +
+             ((f.mag(b, f.H - 1, 0, s) > thr) ? 1.f : 0.f) + ((f.mag(b, f.H - 1, f.W - 1, s) > thr) ? 1.f : 0.f);
+    }
   }
+  if (threadIdx.x == 0) {
+    atomicAdd(o + 2, t_cnt);  // integer-valued: exact and order-independent
+    atomicMin(reinterpret_cast<int*>(o + 4), __float_as_int(t_mn));  // magnitudes are >= 0: bit order == value order
+    atomicMax(reinterpret_cast<int*>(o + 5), __float_as_int(t_mx));
+  }
+}
+
+__global__ void flow_stats_finalize_kernel(const float* __restrict__ acc, int n, float hw, float* __restrict__ stats) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* a = acc + static_cast<long long>(i) * 6;
+  float* o = stats + static_cast<long long>(i) * 5;
+  o[0] = a[0] / (a[1] + 1e-12f);
+  o[1] = a[2] / hw;
+  o[2] = a[3];
+  o[3] = a[4];
+  o[4] = a[5];
+}
+
+__global__ void flow_stats_init_kernel(float* __restrict__ acc, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float* a = acc + static_cast<long long>(i) * 6;
+  a[0] = a[1] = a[2] = a[3] = 0.f;
+  a[4] = INFINITY;
+  a[5] = 0.f;
 }
 
 // filter mask [B, S] from the statistics (sampling.py:202-247, :266-279); methods bit 0 = patch_magnitude,
@@ -145,20 +195,23 @@ flow_zero_filtered_kernel(float* p, int64_t sb, int64_t sc, int64_t sh_, int64_t
   if (filt[b * S + s]) p[b * sb + c * sc + y * sh_ + x * sw + s * ss] = 0.f;
 }
 
-// sum over samples of the (optionally per-sample normalised, optionally filtered) magnitude: one thread per pixel.
-//   out[b, y, x] (+)= sum_s w_s * g_s(mag),  g_s(m) = normalize_per_sample ? (m - min_s) / max(max_s - min_s, eps) : m
-// `accumulate` adds to out (multi-chunk / multi-rank partial sums).
+// sum over samples of the (optionally per-sample normalised, optionally filtered) magnitude.  One thread per pixel
+// and sample slice (grid.y slices keep > 100k threads in flight for any S); the slice sums go to `partial`
+// [slices, B*H*W] and flow_partial_reduce_kernel adds them in slice order (deterministic).
+//   g_s(m) = normalize_per_sample ? (m - min_s) / max(max_s - min_s, eps) : m
 __global__ void __launch_bounds__(256)
 flow_magnitude_sum_kernel(FlowView f, const uint8_t* __restrict__ filt, const float* __restrict__ stats,
-                          int normalize_per_sample, float eps, int accumulate, long long total, float* __restrict__ out) {
+                          int normalize_per_sample, float eps, int per_slice, long long total, float* __restrict__ partial) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int x = static_cast<int>(i % f.W);
   long long r = i / f.W;
   const int y = static_cast<int>(r % f.H);
   const int b = static_cast<int>(r / f.H);
+  const int s0 = blockIdx.y * per_slice, s1 = min(f.S, s0 + per_slice);
   float acc = 0.f;
-  for (int s = 0; s < f.S; ++s) {
+#pragma unroll 4
+  for (int s = s0; s < s1; ++s) {
     const bool dropped = filt != nullptr && filt[b * f.S + s];
     float m = dropped ? 0.f : f.mag(b, y, x, s);
     if (normalize_per_sample) {
@@ -169,7 +222,17 @@ flow_magnitude_sum_kernel(FlowView f, const uint8_t* __restrict__ filt, const fl
     }
     acc += m;
   }
-  out[i] = accumulate ? out[i] + acc : acc;
+  partial[blockIdx.y * total + i] = acc;
+}
+
+__global__ void __launch_bounds__(256)
+flow_partial_reduce_kernel(const float* __restrict__ partial, int slices, long long total, int accumulate,
+                           float* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  float acc = accumulate ? out[i] : 0.f;
+  for (int k = 0; k < slices; ++k) acc += partial[k * total + i];
+  out[i] = acc;
 }
 
 // motion_map = sums / count (`flow_mags.mean(-1)`); then (optional) minus its min over (H, W), divided by max.clamp(eps)
@@ -212,19 +275,40 @@ static int make_view(const float* flows, const int64_t fs[5], int B, int H, int 
 
 using namespace cwm;
 
+extern "C" size_t cwm_flow_stats_workspace_bytes(int B, int H, int W, int S) {
+  if (B < 0 || H <= 0 || W <= 0 || S < 0) return 0;
+  const size_t acc = static_cast<size_t>(B) * S * 6 * sizeof(float);
+  const size_t partial = static_cast<size_t>(32) * B * H * W * sizeof(float);
+  return (acc > partial ? acc : partial) + 256;
+}
+
 extern "C" int cwm_flow_sample_stats(const float* flows, const int64_t fs[5], int B, int H, int W, int S,
                                      const uint8_t* active, const int64_t as[3], int n_h, int n_w,
-                                     float magnitude_threshold, float* stats, cwm_stream_t stream) {
+                                     float magnitude_threshold, float* stats, void* workspace, size_t workspace_bytes,
+                                     cwm_stream_t stream) {
   FlowView v;
   int rc = make_view(flows, fs, B, H, W, S, &v, "cwm_flow_sample_stats");
   if (rc != CWM_OK) return rc;
-  CWM_REQUIRE(stats, "cwm_flow_sample_stats: null pointer");
+  CWM_REQUIRE(stats && workspace, "cwm_flow_sample_stats: null pointer");
   CWM_REQUIRE(active == nullptr || (as && n_h > 0 && n_w > 0), "cwm_flow_sample_stats: active patches need strides and a grid");
-  if (B * S == 0) return CWM_OK;
+  if (workspace_bytes < static_cast<size_t>(B) * S * 6 * sizeof(float))
+    return fail(CWM_ERR_WORKSPACE, "cwm_flow_sample_stats: workspace %zu bytes too small", workspace_bytes);
+  const int n = B * S;
+  if (n == 0) return CWM_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  ProfileScope prof(st, "flow_sample_stats", 0.0, static_cast<double>(B) * S * H * W * 8.0);
-  flow_sample_stats_kernel<<<B * S, 256, 0, st>>>(v, active, active ? as[0] : 0, active ? as[1] : 0, active ? as[2] : 0,
-                                                  n_h, n_w, magnitude_threshold, stats);
+  float* acc = reinterpret_cast<float*>(workspace);
+  const int vec_ok = (fs[3] == 1) && (W % 4 == 0) && (reinterpret_cast<uintptr_t>(flows) % 16 == 0) && (fs[0] % 4 == 0) &&
+                     (fs[1] % 4 == 0) && (fs[2] % 4 == 0) && (fs[4] % 4 == 0);
+  flow_stats_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(acc, n);
+  CWM_LAUNCH_CHECK();
+  {
+    ProfileScope prof(st, "flow_sample_stats", 0.0, static_cast<double>(B) * S * H * W * 8.0);
+    flow_sample_stats_kernel<<<dim3(n, kStatChunks), 256, 0, st>>>(v, active, active ? as[0] : 0, active ? as[1] : 0,
+                                                                   active ? as[2] : 0, n_h, n_w, magnitude_threshold,
+                                                                   vec_ok, acc);
+    CWM_LAUNCH_CHECK();
+  }
+  flow_stats_finalize_kernel<<<(n + 255) / 256, 256, 0, st>>>(acc, n, static_cast<float>(H) * W, stats);
   CWM_LAUNCH_CHECK();
   return CWM_OK;
 }
@@ -261,19 +345,34 @@ extern "C" int cwm_flow_zero_filtered(float* flows, const int64_t fs[5], int B, 
 
 extern "C" int cwm_flow_magnitude_sum(const float* flows, const int64_t fs[5], int B, int H, int W, int S,
                                       const uint8_t* filter_mask, const float* stats, int normalize_per_sample,
-                                      float eps, int accumulate, float* sums, cwm_stream_t stream) {
+                                      float eps, int accumulate, float* sums, void* workspace, size_t workspace_bytes,
+                                      cwm_stream_t stream) {
   FlowView v;
   int rc = make_view(flows, fs, B, H, W, S, &v, "cwm_flow_magnitude_sum");
   if (rc != CWM_OK) return rc;
-  CWM_REQUIRE(sums, "cwm_flow_magnitude_sum: null pointer");
+  CWM_REQUIRE(sums && workspace, "cwm_flow_magnitude_sum: null pointer");
   CWM_REQUIRE(!normalize_per_sample || stats, "cwm_flow_magnitude_sum: per-sample normalisation needs the statistics");
   const long long total = static_cast<long long>(B) * H * W;
   if (total == 0) return CWM_OK;
+  // enough sample slices for ~300k threads in flight, at most 32, at least 4 samples per slice
+  int slices = static_cast<int>((300000 + total - 1) / total);
+  if (slices > 32) slices = 32;
+  if (slices > (S + 3) / 4) slices = (S + 3) / 4;
+  if (slices < 1) slices = 1;
+  const int per_slice = S > 0 ? (S + slices - 1) / slices : 1;
+  slices = S > 0 ? (S + per_slice - 1) / per_slice : 1;
+  if (workspace_bytes < static_cast<size_t>(slices) * total * sizeof(float))
+    return fail(CWM_ERR_WORKSPACE, "cwm_flow_magnitude_sum: workspace %zu bytes too small", workspace_bytes);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  ProfileScope prof(st, "flow_magnitude_sum", 0.0, static_cast<double>(total) * (8.0 * S + 4.0));
-  flow_magnitude_sum_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(v, filter_mask, stats,
-                                                                                        normalize_per_sample, eps,
-                                                                                        accumulate, total, sums);
+  float* partial = reinterpret_cast<float*>(workspace);
+  {
+    ProfileScope prof(st, "flow_magnitude_sum", 0.0, static_cast<double>(total) * (8.0 * S + 4.0));
+    flow_magnitude_sum_kernel<<<dim3(static_cast<unsigned>((total + 255) / 256), slices), 256, 0, st>>>(
+        v, filter_mask, stats, normalize_per_sample, eps, per_slice, total, partial);
+    CWM_LAUNCH_CHECK();
+  }
+  flow_partial_reduce_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(partial, slices, total, accumulate,
+                                                                                         sums);
   CWM_LAUNCH_CHECK();
   return CWM_OK;
 }

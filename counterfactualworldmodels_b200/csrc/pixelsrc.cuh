@@ -30,6 +30,26 @@ struct TensorSrc {
   }
 };
 
+// Per-(sample, frame, row, 4-pixel column) context: everything that does not depend on the channel is computed once.
+struct TensorCtx {
+  const float* base;
+};
+__device__ __forceinline__ TensorCtx src_begin(const TensorSrc& s, long long b, int t, int y, int x0) {
+  TensorCtx c;
+  c.base = s.x + b * s.sb + t * s.st + y * s.sh + x0 * s.sw;
+  return c;
+}
+__device__ __forceinline__ float4 src_load4(const TensorSrc& s, const TensorCtx& k, int c) {
+  const float* src = k.base + c * s.sc;
+  float4 v;
+  if (s.vec_ok) {
+    v = __ldg(reinterpret_cast<const float4*>(src));
+  } else {
+    v.x = __ldg(src); v.y = __ldg(src + s.sw); v.z = __ldg(src + 2 * s.sw); v.w = __ldg(src + 3 * s.sw);
+  }
+  return v;
+}
+
 struct CfSrc {
   const float* x;
   int64_t sb, st, sc, sh, sw;  // logical [B_img, T, C, H, W]
@@ -80,6 +100,68 @@ struct CfSrc {
     return r;
   }
 };
+
+struct CfCtx {
+  const float* o;   // original pixel row position (channel 0)
+  const float* v;   // shifted source position (channel 0); only read when blend != 0
+  float m;
+  int blend;        // 0: the pixel is the original one; 1: evaluate the blend
+  int vmask;        // bit e set: shifted pixel e is inside the image
+  int vvec;         // the 4 shifted pixels can be read with one aligned 16-byte load
+};
+__device__ __forceinline__ CfCtx src_begin(const CfSrc& s, long long i, int t, int y, int x0) {
+  CfCtx k;
+  const int b = s.sample_image ? s.sample_image[i] : 0;
+  const int ts = s.static_frame >= 0 ? s.static_frame : t;
+  const float* img = s.x + b * s.sb + ts * s.st;
+  k.o = img + y * s.sh + x0 * s.sw;
+  k.v = k.o;
+  k.m = 1.f;
+  k.blend = 0;
+  k.vmask = 0;
+  k.vvec = 0;
+  if (t != s.frame) return k;
+  k.blend = 1;
+  k.m = s.shifted_active[i * (s.n_h * s.n_w) + (y / s.ph) * s.n_w + x0 / s.pw] ? 1.f : 0.f;
+  const int sy = s.shift_px[2 * i], sx = s.shift_px[2 * i + 1];
+  const int ys = y - sy, xs = x0 - sx;
+  if (ys >= 0 && ys < s.H) {
+    k.v = img + ys * s.sh + xs * s.sw;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) k.vmask |= (xs + e >= 0 && xs + e < s.W) ? (1 << e) : 0;
+    k.vvec = s.vec_ok && (sx & 3) == 0 && k.vmask == 15;
+  }
+  return k;
+}
+__device__ __forceinline__ float4 src_load4(const CfSrc& s, const CfCtx& k, int c) {
+  const float* src = k.o + c * s.sc;
+  float4 o;
+  if (s.vec_ok) {
+    o = __ldg(reinterpret_cast<const float4*>(src));
+  } else {
+    o.x = __ldg(src); o.y = __ldg(src + s.sw); o.z = __ldg(src + 2 * s.sw); o.w = __ldg(src + 3 * s.sw);
+  }
+  if (!k.blend) return o;
+  // fast path (see CfSrc::load4): x_shift * 0 + x * 1 == x bit for bit unless x is a (signed) zero
+  if (k.m != 0.f && o.x != 0.f && o.y != 0.f && o.z != 0.f && o.w != 0.f) return o;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);  // F.pad(..., value=0) (perturbation.py:258)
+  const float* sp = k.v + c * s.sc;
+  if (k.vvec) {
+    v = __ldg(reinterpret_cast<const float4*>(sp));
+  } else {
+    if (k.vmask & 1) v.x = __ldg(sp);
+    if (k.vmask & 2) v.y = __ldg(sp + s.sw);
+    if (k.vmask & 4) v.z = __ldg(sp + 2 * s.sw);
+    if (k.vmask & 8) v.w = __ldg(sp + 3 * s.sw);
+  }
+  const float om = __fsub_rn(1.f, k.m);
+  float4 r;
+  r.x = __fadd_rn(__fmul_rn(v.x, om), __fmul_rn(o.x, k.m));
+  r.y = __fadd_rn(__fmul_rn(v.y, om), __fmul_rn(o.y, k.m));
+  r.z = __fadd_rn(__fmul_rn(v.z, om), __fmul_rn(o.z, k.m));
+  r.w = __fadd_rn(__fmul_rn(v.w, om), __fmul_rn(o.w, k.m));
+  return r;
+}
 
 // ---------------------------------------------------------------------------------------------
 // patch gather v2: A[m, (c,kt,kh,kw)] = norm(v[b, tt*pt+kt, c, hh*ph+kh, ww*pw+kw]) for the visible token m.
@@ -202,29 +284,30 @@ struct UnpatchGeom {
   const int32_t* inv_perm;
   int T, H, W, pt, ph, pw, n_h, n_w, Ntot, Nvis, D;
   int per_sample;  // T * H * W / 4
+  int ph_shift, pw_shift;  // log2 of the patch sides when both are powers of two, else -1
   float* out;
 };
 
 template <class Src, int C>
 __global__ void __launch_bounds__(256) unpatchify2_kernel(Src s, UnpatchGeom p) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= p.per_sample) return;
-  const long long b = blockIdx.y;
-  const int W4 = p.W >> 2;
-  const int x4 = idx % W4;
-  const int r = idx / W4;
-  const int yy = r % p.H;
-  const int t = r / p.H;
+  // blockDim = (W/4, rows per block): no division to find the pixel; grid = (row blocks, T, samples)
+  const int x4 = threadIdx.x;
+  const int yy = blockIdx.x * blockDim.y + threadIdx.y;
+  if (yy >= p.H) return;
+  const int t = blockIdx.y;
+  const long long b = blockIdx.z;
   const int xx = x4 << 2;
   const int tt = t / p.pt, kt = t - tt * p.pt;
-  const int hh = yy / p.ph, kh = yy - hh * p.ph;
-  const int ww = xx / p.pw, kw = xx - ww * p.pw;
+  int hh, ww;
+  if (p.ph_shift >= 0) { hh = yy >> p.ph_shift; ww = xx >> p.pw_shift; } else { hh = yy / p.ph; ww = xx / p.pw; }
+  const int kh = yy - hh * p.ph, kw = xx - ww * p.pw;
   const int tok = (tt * p.n_h + hh) * p.n_w + ww;
   const int pos = p.inv_perm ? p.inv_perm[b * p.Ntot + tok] : 0;
   float4 v[C];
   if (pos < p.Nvis) {
+    const auto ctx = src_begin(s, b, t, yy, xx);
 #pragma unroll
-    for (int c = 0; c < C; ++c) v[c] = s.load4(b, t, c, yy, xx);
+    for (int c = 0; c < C; ++c) v[c] = src_load4(s, ctx, c);
   } else {
     const int Nmask = p.Ntot - p.Nvis;
     const float4* src = reinterpret_cast<const float4*>(p.y + (b * Nmask + (pos - p.Nvis)) * p.D +
@@ -242,6 +325,26 @@ __global__ void __launch_bounds__(256) unpatchify2_kernel(Src s, UnpatchGeom p) 
   float* o = p.out + ((b * p.T + t) * C) * plane + static_cast<long long>(yy) * p.W + xx;
 #pragma unroll
   for (int c = 0; c < C; ++c) *reinterpret_cast<float4*>(o + c * plane) = v[c];
+}
+
+static inline int log2_exact(int v) {
+  for (int k = 0; k < 31; ++k)
+    if ((1 << k) == v) return k;
+  return -1;
+}
+
+// host-side launch shared by cwm_unpatchify_scatter, cwm_unpatchify_scatter_cf and cwm_cf_build_videos.
+// Requires W / 4 <= 256 and B <= 65535 (checked by the callers).
+template <class Src>
+static inline void launch_unpatchify2(const Src& src, UnpatchGeom g, int B, cudaStream_t st) {
+  g.ph_shift = log2_exact(g.ph);
+  g.pw_shift = log2_exact(g.pw);
+  if (g.ph_shift < 0 || g.pw_shift < 0) g.ph_shift = g.pw_shift = -1;
+  const int W4 = g.W / 4;
+  const int rows = 256 / W4 > 0 ? 256 / W4 : 1;
+  dim3 block(W4, rows);
+  dim3 grid((g.H + rows - 1) / rows, g.T, B);
+  unpatchify2_kernel<Src, 3><<<grid, block, 0, st>>>(src, g);
 }
 
 }  // namespace cwm

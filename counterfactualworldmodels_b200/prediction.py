@@ -221,13 +221,21 @@ class PredictorBasedGenerator(nn.Module):
         num_visible = kwargs.pop('_num_visible', None)
         self.inp_shape = x.shape
         self.set_image_size(x.shape[-2:])
+        plain_vmae = isinstance(self.predictor, PretrainVisionTransformer) and not isinstance(
+            self.predictor, (ConjoinedPretrainVisionTransformer, PaddedVisionTransformer))
+        if num_visible is None and plain_vmae and x.size(0) > 1 and mask.device.type == "cuda" and \
+                self.mask_rectangularizer._mode == 'min':
+            # One device->host read serves both the rectangulariser and the forward: the compaction kernel counts
+            # the visible tokens of every row; when they agree (every sweep whose prompts are well formed) the
+            # rectangulariser is the identity and draws nothing from the RNG (masking.py:117-128).
+            counts = compact_mask(mask.reshape(x.size(0), -1))[2].cpu()
+            if bool((counts == counts[0]).all()):
+                num_visible = int(counts[0])
         if num_visible is None:
             mask = mask if (x.size(0) == 1) else self.mask_rectangularizer(mask)
         elif isinstance(self.predictor, PretrainVisionTransformer) and \
                 not isinstance(self.predictor, PaddedVisionTransformer):
             kwargs['num_visible'] = num_visible
-        plain_vmae = isinstance(self.predictor, PretrainVisionTransformer) and not isinstance(
-            self.predictor, (ConjoinedPretrainVisionTransformer, PaddedVisionTransformer))
         if isinstance(x, CounterfactualVideo) and not (plain_vmae and self.t_dim == 2):
             x = x.materialize()  # other predictors take the materialised prompts (still one kernel, not a loop)
         if isinstance(self.predictor, (ConjoinedPretrainVisionTransformer, PaddedVisionTransformer)):

@@ -15,6 +15,18 @@ from .masking import EnergySamplingMaskingGenerator, RotatedTableEnergyMaskingGe
 _METHOD_BITS = {'patch_magnitude': 1, 'flow_area': 2, 'num_corners': 4}
 
 
+_WS = {}
+
+
+def _workspace(B, H, W, S, device):
+    """Scratch of the two reductions (per device, grown on demand)."""
+    need = int(_lib.load().cwm_flow_stats_workspace_bytes(B, H, W, S))
+    ws = _WS.get(str(device))
+    if ws is None or ws.numel() < need:
+        ws = _WS[str(device)] = torch.empty(need, dtype=torch.uint8, device=device)
+    return ws
+
+
 def _strides(t, n):
     assert t.dim() == n, t.shape
     return (ctypes.c_int64 * n)(*t.stride())
@@ -40,9 +52,11 @@ def flow_sample_stats(flow_samples, active_patches=None, magnitude_threshold=0.0
         a = a.view(torch.uint8) if a.dtype == torch.bool else (a != 0).view(torch.uint8)
         a_ptr, a_str = a.data_ptr(), _strides(a, 3)
     with torch.cuda.device(flow_samples.device):
+        ws = _workspace(B, H, W, S, flow_samples.device)
         stream = torch.cuda.current_stream(flow_samples.device).cuda_stream
         _lib.check(lib.cwm_flow_sample_stats(flow_samples.data_ptr(), _strides(flow_samples, 5), B, H, W, S, a_ptr, a_str,
-                                             h, w, float(magnitude_threshold), stats.data_ptr(), stream))
+                                             h, w, float(magnitude_threshold), stats.data_ptr(), ws.data_ptr(),
+                                             ws.numel(), stream))
     return stats
 
 
@@ -130,12 +144,13 @@ def flow_magnitude_sum(flow_samples, filter_mask=None, stats=None, normalize_per
     if out is None:
         out = torch.empty(B, H, W, dtype=torch.float32, device=flow_samples.device)
     with torch.cuda.device(flow_samples.device):
+        ws = _workspace(B, H, W, S, flow_samples.device)
         stream = torch.cuda.current_stream(flow_samples.device).cuda_stream
         _lib.check(lib.cwm_flow_magnitude_sum(
             flow_samples.data_ptr(), _strides(flow_samples, 5), B, H, W, S,
             None if filter_mask is None else filter_mask.contiguous().data_ptr(),
             None if stats is None else stats.contiguous().data_ptr(), int(bool(normalize_per_sample)), float(eps),
-            int(accumulate), out.data_ptr(), stream))
+            int(accumulate), out.data_ptr(), ws.data_ptr(), ws.numel(), stream))
     return out
 
 

@@ -324,9 +324,10 @@ int cwm_unpatchify_scatter_cf(const float* y, const cwm_cf_source* src, const in
  *   [1] flow_area: fraction of pixels whose magnitude exceeds magnitude_threshold (sampling.py:214-224)
  *   [2] num_corners: image corners whose magnitude exceeds magnitude_threshold (sampling.py:226-247)
  *   [3], [4] min / max magnitude over the image (`compute_flow_samples_magnitude`, segmentation.py:250-255) */
+size_t cwm_flow_stats_workspace_bytes(int B, int H, int W, int S); /* scratch for the two reductions below */
 int cwm_flow_sample_stats(const float* flows, const int64_t fs[5], int B, int H, int W, int S, const uint8_t* active,
                           const int64_t as[3], int n_h, int n_w, float magnitude_threshold, float* stats,
-                          cwm_stream_t stream);
+                          void* workspace, size_t workspace_bytes, cwm_stream_t stream);
 /* filter_mask[b, s] = OR over the enabled methods (bit 0 patch_magnitude: stats[0] < magnitude_threshold; bit 1
  * flow_area: stats[1] > area_threshold; bit 2 num_corners: stats[2] >= corners_threshold) -- sampling.py:266-279. */
 int cwm_flow_filter_mask(const float* stats, int B, int S, int methods, float magnitude_threshold, float area_threshold,
@@ -340,7 +341,7 @@ int cwm_flow_zero_filtered(float* flows, const int64_t fs[5], int B, int H, int 
  * (chunks of a sweep; partial sums of the ranks are combined with one all-reduce). */
 int cwm_flow_magnitude_sum(const float* flows, const int64_t fs[5], int B, int H, int W, int S,
                            const uint8_t* filter_mask, const float* stats, int normalize_per_sample, float eps,
-                           int accumulate, float* sums, cwm_stream_t stream);
+                           int accumulate, float* sums, void* workspace, size_t workspace_bytes, cwm_stream_t stream);
 /* motion_map[b] = sums[b] / count, then (normalize != 0) minus its minimum and divided by its maximum clamped at eps
  * (`compute_mean_motion_map`, segmentation.py:268-276).  sums / motion_map fp32 [B, H, W]. */
 int cwm_motion_map_finalize(const float* sums, int B, int H, int W, float count, int normalize, float eps,

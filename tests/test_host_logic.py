@@ -64,11 +64,25 @@ def test_forward_refuses_cpu_tensors():
 def test_unsupported_constructor_options_raise():
     kw = synthetic.model_kwargs("tiny_4x4")
     with pytest.raises(NotImplementedError):
-        vmae.PretrainVisionTransformer(**dict(kw, init_values=0.1))
-    with pytest.raises(NotImplementedError):
-        vmae.PretrainVisionTransformer(**dict(kw, use_learnable_pos_emb=True))
-    with pytest.raises(NotImplementedError):
         vmae.PretrainVisionTransformer(**dict(kw, decoder_depth=0))
+    with pytest.raises(NotImplementedError):
+        vmae.PretrainVisionTransformer(**dict(kw, embed_per_frame=True))
+    with pytest.raises(NotImplementedError):
+        vmae.PretrainVisionTransformer(**dict(kw, drop_path_rate=0.1))
+
+
+def test_supported_constructor_options_add_the_reference_parameters():
+    """layer scale and learnable positional embeddings create the same state_dict entries as the reference
+    (VideoMAE/utils.py:140-144, vmae.py:68-70)."""
+    kw = synthetic.model_kwargs("tiny_4x4")
+    m = vmae.PretrainVisionTransformer(**dict(kw, init_values=0.1, use_learnable_pos_emb=True))
+    keys = set(m.state_dict().keys())
+    assert {"encoder.blocks.0.gamma_1", "encoder.blocks.1.gamma_2", "decoder.blocks.0.gamma_1",
+            "encoder.pos_embed"} <= keys
+    assert m.state_dict()["encoder.pos_embed"].shape == (1, 128, 128)
+    assert float(m.state_dict()["decoder.blocks.0.gamma_2"][0]) == pytest.approx(0.1)
+    plain = set(vmae.PretrainVisionTransformer(**kw).state_dict().keys())
+    assert not any("gamma" in k or k.endswith("pos_embed") for k in plain)
 
 
 def test_engine_signature_tracks_weight_changes():
