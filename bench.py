@@ -77,6 +77,25 @@ def measured_peaks():
     return dict(hbm_gbs=6650.0, tflops_burst=1590.0, tflops_sustained=1400.0, source="fallback")
 
 
+def bind_to_gpu_numa_node(device_index):
+    """One process per GPU: keep the rank's host threads (and therefore its pinned staging buffers, first-touch) on the
+    CPUs NVML reports as local to its GPU, so that the e2e host<->device copies of different ranks do not cross sockets."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        n_words = (os.cpu_count() + 63) // 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        return None
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -291,6 +310,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback; use --impl reference)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    affinity = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
@@ -475,7 +495,8 @@ def main():
                        "global_batch": r["B"] * world, "visible_tokens": r["n_vis"],
                        "parallelism": f"dp{world} replicas, samples sharded, NCCL gather of predicted frames",
                        "l2": "3 rotating 77 MB input batches; > 1 GB of workspace is rewritten every step (>> 126 MB L2)",
-                       "gflop_per_frame": round(r["flops_frame"] / 1e9, 1)},
+                       "gflop_per_frame": round(r["flops_frame"] / 1e9, 1),
+                       "cpus_bound_per_rank": affinity},
             "tensor_frac_of_sustained_peak": round(r["fps"] / world * r["flops_frame"] / 1e12 /
                                                    peaks["tflops_sustained"], 4),
             "tensor_frac_of_burst_peak": round(r["fps"] / world * r["flops_frame"] / 1e12 / peaks["tflops_burst"], 4),

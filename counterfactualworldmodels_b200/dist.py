@@ -63,3 +63,71 @@ def sharded_predict(generator, x, mask, frame=-1, batch_size=None, gather=True, 
         T = 1 if frame is not None else x.shape[1]
         y = x.new_zeros((0, T) + tuple(x.shape[2:]), dtype=torch.float32)
     return gather_samples(y, S) if gather else y
+
+
+def sharded_counterfactual_videos(generator, x, active_patches, passive_patches=None, shifts=None, num_samples=8,
+                                  sample_batch_size=8, fix_passive=True, frame=1, gather=True, dst=None, **kwargs):
+    """``FlowGenerator.predict_counterfactual_videos`` (cwm/models/segmentation.py:345-430) with the S samples of the
+    sweep sharded over the ranks (SURVEY.md section 8e + 8f rank 1).
+
+    Every rank holds the image and the (tiny) patch descriptors.  Rank 0 builds and rectangularises the masks of the
+    whole sweep -- the rectangulariser draws from a global RNG (masking.py:119-128), so it must see all rows once --
+    and broadcasts them (S*N bytes); each rank then predicts its contiguous slice from the *virtual* counterfactual
+    video (nothing but descriptors is ever sent) and the predicted movies are gathered once.
+    Returns ``[S, T, C, H, W]`` on every rank (``dst=None``), on rank ``dst`` only, or the local slice (``gather=False``)."""
+    G = generator
+    multi = dist.is_initialized() and dist.get_world_size() > 1
+    rank = dist.get_rank() if multi else 0
+    world = dist.get_world_size() if multi else 1
+    if len(x.shape) == 3:
+        x = x.unsqueeze(0).unsqueeze(1).expand(-1, 2, -1, -1, -1)
+        fix_passive = True
+    elif len(x.shape) == 4:
+        x = x.unsqueeze(1).expand(-1, 2, -1, -1, -1)
+        fix_passive = True
+    elif len(x.shape) == 5 and x.size(1) == 1:
+        x = x.expand(-1, 2, -1, -1, -1)
+    x = x[:, 0:2]
+    G.set_input(x)
+    G.reset_shifts()
+    if passive_patches is None:
+        passive_patches = G.get_zeros_mask().unsqueeze(-1)
+    elif len(passive_patches.shape) == 2:
+        passive_patches = passive_patches.unsqueeze(-1)
+    if len(active_patches.shape) == 2:
+        active_patches = active_patches.unsqueeze(-1)
+    S = max(active_patches.size(-1), passive_patches.size(-1))
+    if S == 1 and num_samples > 1:
+        S = num_samples
+    G.shifter.set_shapes(x, mask=active_patches[..., 0])
+    G.shifter.set_num_shifts(S if shifts is None else (len(shifts) if not hasattr(shifts, 'shape') else shifts.shape[-1]))
+    shifts = G.shifter._preprocess_shifts_sequence(shifts, is_mask_shift=True)
+    if multi and rank == 0:
+        obj = [[list(map(int, s)) for s in shifts]]
+    else:
+        obj = [None]
+    if multi:  # randomly drawn shifts (shifts=None) must be the same sweep on every rank
+        dist.broadcast_object_list(obj, src=0)
+        shifts = obj[0]
+    S = len(shifts)
+    if active_patches.size(-1) == 1 and S > 1:
+        active_patches = active_patches.expand(-1, -1, S)
+    if passive_patches.size(-1) == 1 and S > 1:
+        passive_patches = passive_patches.expand(-1, -1, S)
+    video, masks = G.create_motion_counterfactuals(x, masks=passive_patches, active_patches=active_patches,
+                                                   shifts=shifts, num_samples=S, fix_passive=fix_passive,
+                                                   reset_shifts=False, frame=frame, virtual=True)
+    if multi:
+        m8 = masks.contiguous().view(torch.uint8)
+        dist.broadcast(m8, src=0)
+        masks = m8.view(torch.bool)
+    n_total = masks.shape[0]
+    lo, hi = shard_bounds(n_total, rank, world)
+    if hi > lo:
+        y = G.batch_predict_per_sample(video[lo:hi], masks=masks[lo:hi], frame=None,
+                                       batch_size=(sample_batch_size or (hi - lo)), sample_dim=0, **kwargs)
+    else:
+        y = x.new_zeros((0,) + tuple(x.shape[1:]), dtype=torch.float32)
+    if not gather:
+        return y
+    return gather_samples(y, n_total, dst=dst)

@@ -55,3 +55,36 @@ def test_struct_layout_matches_header():
     assert ctypes.sizeof(_lib.BlockWeights) == 12 * 8
     assert ctypes.sizeof(_lib.VmaeModel) == 16 * 4 + 3 * 4 + 4 + 14 * 8
     assert ctypes.sizeof(_lib.GemmEpilogue) == 80
+
+
+def test_argument_validation_of_the_counterfactual_and_flow_entry_points():
+    """SURVEY 8(f) entry points reject bad arguments on the host, before any CUDA call."""
+    lib = _lib.load()
+    rc = lib.cwm_cf_shift_masks(None, None, None, 4, 2, 8, 8, 1, None, None, None)
+    assert rc == -1 and b"null pointer" in lib.cwm_last_error()
+    rc = lib.cwm_cf_shift_masks(1, 1, 1, 4, 2, 8, 8, 2, 1, 1, None)      # frame out of range
+    assert rc == -1 and b"frame" in lib.cwm_last_error()
+    src = _lib.CfSource()
+    rc = lib.cwm_cf_build_videos(ctypes.byref(src), 1, 2, 3, 32, 32, 4, 4, 16, None)
+    assert rc == -1 and b"cwm_cf_source" in lib.cwm_last_error()
+    src.x, src.shift_px, src.shifted_active, src.frame, src.static_frame = 16, 16, 16, 1, -1
+    rc = lib.cwm_cf_build_videos(ctypes.byref(src), 1, 2, 3, 30, 32, 4, 4, 16, None)   # 30 % 4 != 0
+    assert rc == -1 and b"divisible" in lib.cwm_last_error()
+    rc = lib.cwm_cf_build_videos(ctypes.byref(src), 1, 2, 3, 32, 36, 4, 6, 16, None)   # patch width 6
+    assert rc == -3 and b"multiple of 4" in lib.cwm_last_error()
+    rc = lib.cwm_patch_gather_cf(ctypes.byref(src), 1, 3, 2, 32, 32, 2, 4, 4, 16, 128, 70, None, None, 16, None)
+    assert rc == -1 and b"temporal patch size" in lib.cwm_last_error()
+    fs = (ctypes.c_int64 * 5)(0, 0, 0, 0, 0)
+    rc = lib.cwm_flow_sample_stats(None, fs, 1, 8, 8, 2, None, None, 0, 0, 5.0, 16, 16, 1024, None)
+    assert rc == -1 and b"null pointer" in lib.cwm_last_error()
+    rc = lib.cwm_flow_sample_stats(16, fs, 1, 8, 8, 4, None, None, 0, 0, 5.0, 16, 16, 8, None)   # workspace too small
+    assert rc == -4 and b"workspace" in lib.cwm_last_error()
+    rc = lib.cwm_flow_magnitude_sum(16, fs, 1, 8, 8, 4, None, None, 1, 0.01, 0, 16, 16, 1 << 20, None)
+    assert rc == -1 and b"statistics" in lib.cwm_last_error()
+    rc = lib.cwm_motion_map_finalize(16, 1, 8, 8, 0.0, 1, 0.01, 16, None)
+    assert rc == -1
+    assert lib.cwm_flow_stats_workspace_bytes(1, 224, 224, 64) >= 32 * 224 * 224 * 4
+
+
+def test_cf_source_struct_layout():
+    assert ctypes.sizeof(_lib.CfSource) == 8 + 5 * 8 + 3 * 8 + 2 * 4
