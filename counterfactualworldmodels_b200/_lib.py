@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = (
     "cwm_cross_block_forward", "cwm_launch_count_reset", "cwm_vmae_forward_cf", "cwm_cf_shift_masks",
     "cwm_cf_build_videos", "cwm_cf_make_static", "cwm_patch_gather_cf", "cwm_unpatchify_scatter_cf",
     "cwm_flow_sample_stats", "cwm_flow_filter_mask", "cwm_flow_zero_filtered", "cwm_flow_magnitude_sum",
-    "cwm_motion_map_finalize", "cwm_flow_stats_workspace_bytes",
+    "cwm_motion_map_finalize", "cwm_flow_stats_workspace_bytes", "cwm_flow_corrs_workspace_bytes", "cwm_flow_corrs",
 )
 
 
@@ -127,6 +127,10 @@ def _declare(lib):
     lib.cwm_unpatchify_scatter_cf.argtypes = [c_void_p, POINTER(CfSource), c_void_p] + [c_int] * 9 + [c_void_p,
                                                                                                    c_void_p]
     i64x3 = POINTER(c_int64)
+    lib.cwm_flow_corrs_workspace_bytes.argtypes = [c_int] * 5
+    lib.cwm_flow_corrs_workspace_bytes.restype = c_size_t
+    lib.cwm_flow_corrs.argtypes = [c_void_p, i64x5, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                   c_size_t, c_void_p]
     lib.cwm_flow_stats_workspace_bytes.argtypes = [c_int] * 4
     lib.cwm_flow_stats_workspace_bytes.restype = c_size_t
     lib.cwm_flow_sample_stats.argtypes = [c_void_p, i64x5, c_int, c_int, c_int, c_int, c_void_p, i64x3, c_int, c_int,

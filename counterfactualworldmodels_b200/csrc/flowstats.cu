@@ -262,6 +262,116 @@ motion_map_finalize_kernel(const float* __restrict__ sums, int HW, float count, 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// motion covariance / correlation between image locations over the samples of a sweep
+// (`FlowGenerator.compute_flow_corrs`, segmentation.py:478-547, default options):
+//   X[n, s]  = sqrt(mean_c(avg_pool_ds(flow)[c, n, s]^2))          (ChannelMSE against zeros, utils.py:510-513)
+//   C        = (X - mean_s X)(X - mean_s X)^T / (S - 1)             (torch.cov), or
+//   R[i, j]  = clamp(C[i, j] / sqrt(C[i, i]) / sqrt(C[j, j]), -1, 1) (torch.corrcoef);   NaN -> 0
+// Kernel 1 writes the centred features Xc [B, N, S] and the row standard deviations; kernel 2 is an fp32
+// outer-product GEMM with K = S (tiny), i.e. bound by the N^2 * 4 bytes it writes.
+// ---------------------------------------------------------------------------------------------
+// one thread per (location, sample)
+__global__ void __launch_bounds__(256)
+flow_corr_features_kernel(FlowView f, int ds, int n_h, int n_w, int K, long long total, float* __restrict__ xc) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  // location fastest: neighbouring threads read neighbouring ds-pixel groups of one flow sample (coalesced reads of
+  // the 8*H*W bytes per sample); the 4-byte writes into xc[b, n, s] are strided but 1/(2*ds*ds) of the traffic
+  const int N = n_h * n_w;
+  const int n = static_cast<int>(i % N);
+  long long r = i / N;
+  const int s = static_cast<int>(r % K);
+  const int b = static_cast<int>(r / K);
+  const int py = n / n_w, px = n - py * n_w;
+  const float* q = f.p + b * f.sb + s * f.ss;
+  float su = 0.f, sv = 0.f;
+  for (int dy = 0; dy < ds; ++dy)
+    for (int dx = 0; dx < ds; ++dx) {
+      const float* e = q + (py * ds + dy) * f.sh + (px * ds + dx) * f.sw;
+      su += __ldg(e);
+      sv += __ldg(e + f.sc);
+    }
+  const float area = static_cast<float>(ds * ds);
+  const float u = __fdiv_rn(su, area), v = __fdiv_rn(sv, area);
+  xc[(static_cast<long long>(b) * N + n) * K + s] = __fsqrt_rn(__fdiv_rn(__fadd_rn(__fmul_rn(u, u), __fmul_rn(v, v)), 2.f));
+}
+
+// one warp per location: centre the K samples and record the standard deviation
+__global__ void __launch_bounds__(256)
+flow_corr_center_kernel(float* __restrict__ xc, int K, long long rows, float* __restrict__ stdev) {
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float* x = xc + row * K;
+  float sum = 0.f;
+  for (int s = lane; s < K; s += 32) sum += x[s];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = __fdiv_rn(sum, static_cast<float>(K));
+  float ss = 0.f;
+  for (int s = lane; s < K; s += 32) {
+    const float c = x[s] - mean;
+    x[s] = c;
+    ss += c * c;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (lane == 0) stdev[row] = __fsqrt_rn(__fdiv_rn(ss, static_cast<float>(K - 1)));
+}
+
+// C tile 64 x 64 per CTA, 4 x 4 outputs per thread, K (= samples) streamed through shared memory in chunks of 32
+__global__ void __launch_bounds__(256)
+flow_cov_kernel(const float* __restrict__ xc, const float* __restrict__ stdev, int N, int K, int use_covariance,
+                float* __restrict__ out) {
+  __shared__ float a_s[32][65], b_s[32][65];
+  const int b = blockIdx.z;
+  const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+  const float* xb = xc + static_cast<long long>(b) * N * K;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    for (int e = threadIdx.x; e < 64 * 32; e += 256) {
+      const int r = e >> 5, k = e & 31;
+      a_s[k][r] = (i0 + r < N && k0 + k < K) ? xb[static_cast<long long>(i0 + r) * K + k0 + k] : 0.f;
+      b_s[k][r] = (j0 + r < N && k0 + k < K) ? xb[static_cast<long long>(j0 + r) * K + k0 + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { av[u] = a_s[k][ty * 4 + u]; bv[u] = b_s[k][tx * 4 + u]; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(av[u], bv[v], acc[u][v]);
+    }
+    __syncthreads();
+  }
+  const float norm = static_cast<float>(K - 1);
+  const float* sd = stdev + static_cast<long long>(b) * N;
+  float* ob = out + static_cast<long long>(b) * N * N;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int i = i0 + ty * 4 + u;
+    if (i >= N) continue;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int j = j0 + tx * 4 + v;
+      if (j >= N) continue;
+      float c = __fdiv_rn(acc[u][v], norm);
+      if (!use_covariance) {
+        c = __fdiv_rn(__fdiv_rn(c, sd[i]), sd[j]);
+        c = fminf(fmaxf(c, -1.f), 1.f);  // fminf/fmaxf drop a NaN operand, so test it first
+        if (!(acc[u][v] == acc[u][v]) || !(sd[i] > 0.f) || !(sd[j] > 0.f)) c = __int_as_float(0x7fc00000);
+      }
+      if (c != c) c = 0.f;  // flow_corrs_b[isnan] = 0 (segmentation.py:541)
+      ob[static_cast<long long>(i) * N + j] = c;
+    }
+  }
+}
+
 static int make_view(const float* flows, const int64_t fs[5], int B, int H, int W, int S, FlowView* v, const char* who) {
   if (!flows || !fs) return fail(CWM_ERR_INVALID, "%s: null pointer", who);
   if (B < 0 || H <= 0 || W <= 0 || S < 0) return fail(CWM_ERR_INVALID, "%s: bad shape B=%d H=%d W=%d S=%d", who, B, H, W, S);
@@ -386,5 +496,46 @@ extern "C" int cwm_motion_map_finalize(const float* sums, int B, int H, int W, f
   ProfileScope prof(st, "motion_map_finalize", 0.0, static_cast<double>(B) * H * W * 12.0);
   motion_map_finalize_kernel<<<B, 1024, 0, st>>>(sums, H * W, count, normalize, eps, motion_map);
   CWM_LAUNCH_CHECK();
+  return CWM_OK;
+}
+
+extern "C" size_t cwm_flow_corrs_workspace_bytes(int B, int H, int W, int S, int downsample) {
+  if (B < 0 || H <= 0 || W <= 0 || S < 0 || downsample <= 0) return 0;
+  const size_t N = static_cast<size_t>(H / downsample) * (W / downsample);
+  return (static_cast<size_t>(B) * N * (S + 1)) * sizeof(float) + 256;
+}
+
+extern "C" int cwm_flow_corrs(const float* flows, const int64_t fs[5], int B, int H, int W, int S, int downsample,
+                              int use_covariance, float* out, void* workspace, size_t workspace_bytes,
+                              cwm_stream_t stream) {
+  FlowView v;
+  int rc = make_view(flows, fs, B, H, W, S, &v, "cwm_flow_corrs");
+  if (rc != CWM_OK) return rc;
+  CWM_REQUIRE(out && workspace, "cwm_flow_corrs: null pointer");
+  CWM_REQUIRE(downsample > 0 && H % downsample == 0 && W % downsample == 0,
+              "cwm_flow_corrs: image (%d,%d) not divisible by downsample %d", H, W, downsample);
+  CWM_REQUIRE(S >= 1, "cwm_flow_corrs: needs at least one sample (the caller substitutes a zero sample, segmentation.py:494-497)");
+  const int n_h = H / downsample, n_w = W / downsample, N = n_h * n_w;
+  if (workspace_bytes < cwm_flow_corrs_workspace_bytes(B, H, W, S, downsample))
+    return fail(CWM_ERR_WORKSPACE, "cwm_flow_corrs: workspace %zu bytes too small", workspace_bytes);
+  if (B == 0) return CWM_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* xc = reinterpret_cast<float*>(workspace);
+  float* sd = xc + static_cast<size_t>(B) * N * S;
+  {
+    ProfileScope prof(st, "flow_corr_features", 0.0, static_cast<double>(B) * S * H * W * 8.0);
+    const long long total = static_cast<long long>(B) * N * S;
+    flow_corr_features_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(v, downsample, n_h, n_w, S, total,
+                                                                                          xc);
+    CWM_LAUNCH_CHECK();
+    const long long rows = static_cast<long long>(B) * N;
+    flow_corr_center_kernel<<<static_cast<unsigned>((rows * 32 + 255) / 256), 256, 0, st>>>(xc, S, rows, sd);
+    CWM_LAUNCH_CHECK();
+  }
+  {
+    ProfileScope prof(st, "flow_cov", 2.0 * B * static_cast<double>(N) * N * S, static_cast<double>(B) * N * N * 4.0);
+    flow_cov_kernel<<<dim3((N + 63) / 64, (N + 63) / 64, B), 256, 0, st>>>(xc, sd, N, S, use_covariance, out);
+    CWM_LAUNCH_CHECK();
+  }
   return CWM_OK;
 }

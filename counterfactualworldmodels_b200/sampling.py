@@ -165,3 +165,25 @@ def motion_map_finalize(sums, count, normalize=True, eps=1e-2):
         _lib.check(lib.cwm_motion_map_finalize(sums.data_ptr(), B, H, W, float(count), int(bool(normalize)), float(eps),
                                                out.data_ptr(), stream))
     return out
+
+
+def flow_corrs(flow_samples, downsample=1, use_covariance=False):
+    """``FlowGenerator.compute_flow_corrs`` with default options (segmentation.py:478-547) ->
+    float32 [B, 1, H/ds, W/ds, H/ds, W/ds]."""
+    lib = _lib.load()
+    if flow_samples.device.type != "cuda":
+        raise RuntimeError("flow statistics: tensors must live on a CUDA (B200) device; there is no CPU fallback")
+    if flow_samples.dtype != torch.float32:
+        flow_samples = flow_samples.float()
+    B, C, H, W, S = flow_samples.shape
+    assert C == 2, flow_samples.shape
+    ds = int(downsample)
+    n_h, n_w = H // ds, W // ds
+    out = torch.empty(B, n_h * n_w, n_h * n_w, dtype=torch.float32, device=flow_samples.device)
+    with torch.cuda.device(flow_samples.device):
+        ws = torch.empty(int(lib.cwm_flow_corrs_workspace_bytes(B, H, W, S, ds)), dtype=torch.uint8,
+                         device=flow_samples.device)
+        stream = torch.cuda.current_stream(flow_samples.device).cuda_stream
+        _lib.check(lib.cwm_flow_corrs(flow_samples.data_ptr(), _strides(flow_samples, 5), B, H, W, S, ds,
+                                      int(bool(use_covariance)), out.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+    return out.view(B, 1, n_h, n_w, n_h, n_w)

@@ -166,6 +166,25 @@ class FlowGenerator(PredictorBasedGenerator):
             sums, count, normalize = flows[:, 0].float(), 1, True
         return sampling.motion_map_finalize(sums, count, normalize=normalize, eps=eps)
 
+    @staticmethod
+    def compute_flow_corrs(flow_samples, flow_samples_swap=None, downsample=1, take_top_k=None, do_spearman=False,
+                           distance_func=None, thresh=None, use_covariance=False, eps=1e-12, binarize=False,
+                           normalize=False, zscore=False, range_thresh=None):
+        """segmentation.py:478-547: covariance / correlation of the flow magnitude between image locations over the
+        samples.  The options the reference's only caller uses (interface.py:27-29, :466-493: ``downsample``,
+        ``use_covariance``, ``take_top_k``) run on device; the others raise."""
+        custom_distance = distance_func is not None and type(distance_func).__name__ != "ChannelMSE"
+        if flow_samples_swap is not None or do_spearman or custom_distance or thresh is not None or \
+                binarize or normalize or zscore or range_thresh is not None:
+            raise NotImplementedError("compute_flow_corrs: only the default feature pipeline (ChannelMSE magnitude, "
+                                      "no thresholding / ranking) is implemented on B200")
+        B, C, H, W, S = flow_samples.shape
+        if S == 0:  # segmentation.py:494-497
+            flow_samples = torch.zeros(list(flow_samples.shape)[:-1] + [1], device=flow_samples.device).float()
+        if take_top_k is not None:
+            flow_samples = flow_samples[..., :take_top_k]
+        return sampling.flow_corrs(flow_samples, downsample=downsample, use_covariance=use_covariance)
+
     def filter_flow_samples(self, flows, active_patches, do_filter=True):
         """The tail of ``sample_counterfactual_motion_map`` (segmentation.py:470-476): flows [(b s), T, 2, H, W] or
         [(b s), 2, H, W] from the flow network -> [B, 2, H, W, S] view with the rejected samples zeroed."""

@@ -342,6 +342,12 @@ int cwm_flow_zero_filtered(float* flows, const int64_t fs[5], int B, int H, int 
 int cwm_flow_magnitude_sum(const float* flows, const int64_t fs[5], int B, int H, int W, int S,
                            const uint8_t* filter_mask, const float* stats, int normalize_per_sample, float eps,
                            int accumulate, float* sums, void* workspace, size_t workspace_bytes, cwm_stream_t stream);
+/* `FlowGenerator.compute_flow_corrs` with its default options (segmentation.py:478-547): per image the covariance
+ * (use_covariance != 0, `torch.cov`) or correlation (`torch.corrcoef`, clamped to [-1, 1]) between the image locations
+ * of the downsampled flow-magnitude samples, NaN -> 0.   out fp32 [B, N, N], N = (H/downsample)*(W/downsample). */
+size_t cwm_flow_corrs_workspace_bytes(int B, int H, int W, int S, int downsample);
+int cwm_flow_corrs(const float* flows, const int64_t fs[5], int B, int H, int W, int S, int downsample,
+                   int use_covariance, float* out, void* workspace, size_t workspace_bytes, cwm_stream_t stream);
 /* motion_map[b] = sums[b] / count, then (normalize != 0) minus its minimum and divided by its maximum clamped at eps
  * (`compute_mean_motion_map`, segmentation.py:268-276).  sums / motion_map fp32 [B, H, W]. */
 int cwm_motion_map_finalize(const float* sums, int B, int H, int W, float count, int normalize, float eps,

@@ -107,3 +107,19 @@ def mean_motion_map(flows, normalize_per_sample=False, normalize=True, eps=1e-2)
         mm = mm - mm.amin((-2, -1), True)
         mm = mm / mm.amax((-2, -1), True).clamp(min=eps)
     return mm
+
+
+def flow_corrs(flow_samples, downsample=1, take_top_k=None, use_covariance=False):
+    """``FlowGenerator.compute_flow_corrs`` with its default options (segmentation.py:478-547)."""
+    B, C, H, W, S = flow_samples.shape
+    K = S if take_top_k is None else take_top_k
+    ds = downsample
+    inp = F.avg_pool3d(flow_samples[..., :K].permute(0, 1, 4, 2, 3), (1, ds, ds), stride=(1, ds, ds)).permute(0, 1, 3, 4, 2)
+    inp = torch.sqrt((inp - torch.zeros_like(inp)).square().mean(1, True).float())   # ChannelMSE(dim=1), utils.py:510-513
+    inp = inp.reshape(B, -1, inp.size(-1))
+    out = []
+    for b in range(B):
+        c = torch.cov(inp[b]) if use_covariance else torch.corrcoef(inp[b])
+        c[torch.isnan(c)] = 0
+        out.append(c)
+    return torch.stack(out, 0).view(B, 1, H // ds, W // ds, H // ds, W // ds)

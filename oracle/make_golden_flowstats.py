@@ -53,6 +53,17 @@ def main():
         mm4 = G.compute_mean_motion_map(flows.norm(dim=1, p=2).mean(-1)[:, None])
         assert torch.equal(fso.mean_motion_map(flows.norm(dim=1, p=2).mean(-1)[:, None]), mm4)
         out["motion_map_from_distribution"] = mm4.numpy()
+        # motion covariance / correlation (segmentation.py:478-547), stored for the small cases
+        if side <= 64:
+            ds = 4 if side == 32 else 8
+            for cov in (True, False):
+                c_ref = ref_seg.FlowGenerator.compute_flow_corrs(flows, downsample=ds, use_covariance=cov)
+                c_or = fso.flow_corrs(flows, downsample=ds, use_covariance=cov)
+                assert torch.equal(c_or, c_ref), (name, cov)
+                out[f"flow_{'cov' if cov else 'corr'}_ds{ds}"] = c_ref.numpy().astype(np.float32)
+            c_ref = ref_seg.FlowGenerator.compute_flow_corrs(flows, downsample=ds, use_covariance=True, take_top_k=3)
+            assert torch.equal(fso.flow_corrs(flows, downsample=ds, use_covariance=True, take_top_k=3), c_ref)
+            out[f"flow_cov_ds{ds}_top3"] = c_ref.numpy().astype(np.float32)
         path = os.path.join(GOLDEN_DIR, name + ".npz")
         np.savez_compressed(path, **out)
         print(f"{name}: filtered {ref_mask_bs.int().tolist()} oracle == reference | {os.path.getsize(path) / 1e3:.0f} KB")

@@ -115,3 +115,34 @@ def test_no_cpu_fallback():
     from counterfactualworldmodels_b200 import sampling
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         sampling.flow_sample_stats(torch.zeros(1, 2, 8, 8, 2))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,ds", [("fs_b2_s6_32px", 4), ("fs_b1_s12_64px", 8)])
+def test_gpu_flow_corrs_match_reference_fixture(case, ds):
+    """Motion covariance / correlation between image locations (segmentation.py:478-547)."""
+    from counterfactualworldmodels_b200 import segmentation
+    d = load_fs(case)
+    flows = fso.batch_to_samples(d["flows_bs"].to(DEV), d["B"])
+    for cov, key in ((True, f"flow_cov_ds{ds}"), (False, f"flow_corr_ds{ds}")):
+        got = segmentation.FlowGenerator.compute_flow_corrs(flows, downsample=ds, use_covariance=cov)
+        assert got.shape == d[key].shape
+        np.testing.assert_allclose(got.cpu().numpy(), d[key], rtol=2e-4, atol=2e-5, err_msg=key)
+    got = segmentation.FlowGenerator.compute_flow_corrs(flows, downsample=ds, use_covariance=True, take_top_k=3)
+    np.testing.assert_allclose(got.cpu().numpy(), d[f"flow_cov_ds{ds}_top3"], rtol=2e-4, atol=2e-5)
+    # properties that hold at any size: symmetric, unit diagonal of the correlation wherever the variance is non-zero
+    r = segmentation.FlowGenerator.compute_flow_corrs(flows, downsample=ds, use_covariance=False)
+    n = r.shape[2] * r.shape[3]
+    r2 = r.reshape(-1, n, n)
+    assert torch.allclose(r2, r2.transpose(1, 2), atol=1e-6)
+    diag = torch.diagonal(r2, dim1=1, dim2=2)
+    assert bool(((diag - 1).abs() < 1e-5).logical_or(diag == 0).all())
+    with pytest.raises(NotImplementedError):
+        segmentation.FlowGenerator.compute_flow_corrs(flows, do_spearman=True)
+
+
+def test_oracle_flow_corrs_matches_reference_fixture():
+    d = load_fs("fs_b2_s6_32px")
+    flows = fso.batch_to_samples(d["flows_bs"], d["B"])
+    assert np.array_equal(fso.flow_corrs(flows, downsample=4, use_covariance=True).numpy(), d["flow_cov_ds4"])
+    assert np.array_equal(fso.flow_corrs(flows, downsample=4, use_covariance=False).numpy(), d["flow_corr_ds4"])

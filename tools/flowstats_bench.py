@@ -56,6 +56,16 @@ def main():
     out["motion_map_GBps"] = nbytes / t / 1e6
     t = timed(lambda: filt(nxt(), active))
     out["filter_forward_inplace_ms"] = t
+    # motion covariance between image locations (segmentation.py:478-547) at downsample 4: N = 3136, 39 MB output
+    Sc = min(S, 64)
+    cview = fso.batch_to_samples(bufs[0][:Sc], 1)
+    t = timed(lambda: sampling.flow_corrs(cview, downsample=4, use_covariance=True))
+    out["flow_cov_ds4_ms"] = t
+    out["flow_cov_ds4_samples"] = Sc
+    out["flow_cov_ds4_GBps_written"] = 3136 * 3136 * 4 / t / 1e6
+    t0 = time.perf_counter()
+    fso.flow_corrs(fso.batch_to_samples(bufs[0][:Sc].cpu(), 1), downsample=4, use_covariance=True)
+    out["flow_cov_ds4_cpu_oracle_ms"] = (time.perf_counter() - t0) * 1e3
     # CPU oracle (the reference's own torch ops, all host threads) on a bounded sample
     n = min(S, 32)
     fl = fso.batch_to_samples(bufs[0][:n].cpu(), 1)
