@@ -17,6 +17,8 @@
 //
 // Roofline: tensor bound for K >= 768; the fp32-residual GEMMs with K <= 512 are HBM bound (8 bytes of residual
 // traffic per output element) -- see DESIGN.md.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace cwm {
@@ -106,7 +108,64 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-template <int BN, bool kRes>
+// ---- CTA-pair (cta_group::2) variants: two CTAs of a cluster on the two SMs of one TPC share a 256 x BN tile.
+//      Each CTA stages its own 128 rows of A and HALF of the W tile (BN/2 rows); the leader's single
+//      tcgen05.mma.cta_group::2 reads both shared memories, so the smem fill per CTA drops from (128 + BN) to
+//      (128 + BN/2) rows per k-step for the same tensor work.  Barriers: the TMA loads of both CTAs complete on
+//      the LEADER's full barrier (peer bit of the shared::cluster address cleared), the leader's commits are
+//      multicast to the empty / accumulator-full barriers of both CTAs, and the epilogue warps of both CTAs
+//      arrive on the leader's accumulator-empty barrier.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_ss2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives (count 1) on the mbarrier at this offset in BOTH CTAs of the pair when the prior MMAs complete
+__device__ __forceinline__ void umma_commit2(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+
+template <int BN, bool kRes, bool kCta2>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w,
                 const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_res, int M, int N,
@@ -128,7 +187,12 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
 
-  const int tiles_m = (M + BM - 1) / BM;
+  // a (pair) tile covers TM rows; in CTA-pair mode this CTA owns rows [cta_rank * 128, +128) of it
+  constexpr int TM = kCta2 ? 2 * BM : BM;
+  const int cta_rank = kCta2 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int tile_first = kCta2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_stride = kCta2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int tiles_m = (M + TM - 1) / TM;
   const int tiles_n = (N + BN - 1) / BN;
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (K + BK - 1) / BK;
@@ -147,17 +211,22 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], kEpiWarps);
+      mbar_init(&tempty_bar[a], kCta2 ? 2 * kEpiWarps : kEpiWarps);
     }
     for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    if constexpr (kCta2) {
+      tmem_alloc2(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kCta2) cluster_sync_all(); else __syncthreads();  // barrier inits visible to the peer CTA as well
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -169,15 +238,23 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = tile_first; tile < num_tiles; tile += tile_stride) {
       const int m_blk = tile / tiles_n;
       const int n_blk = tile - m_blk * tiles_n;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_2d(smem_a + stage * Cfg::kABytes, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
-          tma_load_2d(smem_b + stage * Cfg::kBBytes, &tma_w, &full_bar[stage], kb * BK, n_blk * BN);
+          if constexpr (kCta2) {
+            // the leader expects the bytes of BOTH CTAs; both CTAs' loads complete on the leader's barrier
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (Cfg::kABytes + Cfg::kBBytes / 2));
+            tma_load_2d_2sm(smem_a + stage * Cfg::kABytes, &tma_a, &full_bar[stage], kb * BK, m_blk * TM + cta_rank * BM);
+            tma_load_2d_2sm(smem_b + stage * Cfg::kBBytes, &tma_w, &full_bar[stage], kb * BK,
+                            n_blk * BN + cta_rank * (BN / 2));
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_2d(smem_a + stage * Cfg::kABytes, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
+            tma_load_2d(smem_b + stage * Cfg::kBBytes, &tma_w, &full_bar[stage], kb * BK, n_blk * BN);
+          }
         }
         __syncwarp();
         if (++stage == Cfg::kStages) {
@@ -186,16 +263,16 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = umma_idesc_f16(BM, BN, 0, 0);
+  } else if (warp == 1 && cta_rank == 0) {
+    // ===================== MMA issuer (the leader CTA only in CTA-pair mode) =====================
+    constexpr uint32_t idesc = umma_idesc_f16(TM, BN, 0, 0);
     const uint64_t adesc0 = umma_desc_kmajor_sw128(smem_u32(smem_a));
     const uint64_t bdesc0 = umma_desc_kmajor_sw128(smem_u32(smem_b));
     int stage = 0;
     uint32_t phase = 0;
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = tile_first; tile < num_tiles; tile += tile_stride) {
       mbar_wait(&tempty_bar[as], aphase ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + as * BN;
@@ -206,10 +283,17 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         const uint64_t adesc = adesc0 + static_cast<uint64_t>(stage * (Cfg::kABytes >> 4));
         const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(stage * (Cfg::kBBytes >> 4));
         if (elect_one()) {
+          if constexpr (kCta2) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) umma_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when the MMAs above have read it
-          if (kb == num_kb - 1) umma_commit(&tfull_bar[as]);  // accumulator complete
+            for (int k = 0; k < BK / 16; ++k) umma_ss2(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit2(&empty_bar[stage]);                      // frees the slot in both CTAs
+            if (kb == num_kb - 1) umma_commit2(&tfull_bar[as]);   // accumulator complete, both CTAs
+          } else {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) umma_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit(&empty_bar[stage]);  // frees the smem slot when the MMAs above have read it
+            if (kb == num_kb - 1) umma_commit(&tfull_bar[as]);  // accumulator complete
+          }
         }
         __syncwarp();
         if (++stage == Cfg::kStages) {
@@ -238,13 +322,13 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       // ---------------- f16 output: 64-column chunks, TMA store ----------------
       constexpr int kChunks = BN / 64;
       const bool gelu = (ep.mode == CWM_EPI_GELU_F16);
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile_first; tile < num_tiles; tile += tile_stride) {
         const int m_blk = tile / tiles_n;
         const int n_blk = tile - m_blk * tiles_n;
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
         const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
-        const int row0 = m_blk * BM + quad * 32;
+        const int row0 = m_blk * TM + cta_rank * BM + quad * 32;
         for (int c = half; c < kChunks; c += 2) {
           const int n0 = n_blk * BN + c * 64;
           // bias of the 64 columns -> per-warp smem (broadcast reads below)
@@ -263,7 +347,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
           const bool last_chunk = (c + 2 >= kChunks);
           if (last_chunk) {  // all TMEM reads of this tile by this warp are complete -> release the stage early
             tc_fence_before();
-            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            if (lane == 0) { if constexpr (kCta2) mbar_arrive_leader(&tempty_bar[as]); else mbar_arrive(&tempty_bar[as]); }
           }
           __syncwarp();
           if (elect_one()) bulk_wait_read0();  // the previous TMA store has finished reading the buffer
@@ -295,7 +379,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         }
         if (half >= kChunks) {  // this warp had no chunk in this tile (BN == 64): still release the stage
           tc_fence_before();
-          if (lane == 0) mbar_arrive(&tempty_bar[as]);
+          if (lane == 0) { if constexpr (kCta2) mbar_arrive_leader(&tempty_bar[as]); else mbar_arrive(&tempty_bar[as]); }
         }
         if (++as == 2) {
           as = 0;
@@ -311,18 +395,16 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       uint64_t* my_res_bar = res_bar + ew * 2;
       // flat list of this warp's work items: (tile, chunk) with chunk = half, half+2, ...
       const int my_chunks = (kChunks - half + 1) / 2;
-      const int my_tiles = (num_tiles > static_cast<int>(blockIdx.x))
-                               ? (num_tiles - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1
-                               : 0;
+      const int my_tiles = (num_tiles > tile_first) ? (num_tiles - 1 - tile_first) / tile_stride + 1 : 0;
       const int n_items = my_tiles * my_chunks;
       auto item_coords = [&](int it, int& row0, int& n0, int& c, bool& first, bool& last) {
         const int ti = it / my_chunks;
         const int ci = it - ti * my_chunks;
-        const int tile = blockIdx.x + ti * gridDim.x;
+        const int tile = tile_first + ti * tile_stride;
         const int m_blk = tile / tiles_n;
         const int n_blk = tile - m_blk * tiles_n;
         c = half + 2 * ci;
-        row0 = m_blk * BM + quad * 32;
+        row0 = m_blk * TM + cta_rank * BM + quad * 32;
         n0 = n_blk * BN + c * 32;
         first = (ci == 0);
         last = (ci == my_chunks - 1);
@@ -353,7 +435,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         tmem_ld_wait();
         if (last) {
           tc_fence_before();
-          if (lane == 0) mbar_arrive(&tempty_bar[as]);
+          if (lane == 0) { if constexpr (kCta2) mbar_arrive_leader(&tempty_bar[as]); else mbar_arrive(&tempty_bar[as]); }
         }
         __syncwarp();
         if (elect_one()) {
@@ -405,13 +487,13 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       //                  padded smem transpose, coalesced direct global accesses ----------------
       constexpr int kChunks = BN / 32;
       const uint32_t stg = buf0;  // 32 x 33 words = 4224 bytes <= 2 * kChunkBytes
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile_first; tile < num_tiles; tile += tile_stride) {
         const int m_blk = tile / tiles_n;
         const int n_blk = tile - m_blk * tiles_n;
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
         const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
-        const int row0 = m_blk * BM + quad * 32;
+        const int row0 = m_blk * TM + cta_rank * BM + quad * 32;
         for (int c = half; c < kChunks; c += 2) {
           const int n0 = n_blk * BN + c * 32;
           uint32_t acc[32];
@@ -442,7 +524,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
           __syncwarp();
         }
         tc_fence_before();
-        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        if (lane == 0) { if constexpr (kCta2) mbar_arrive_leader(&tempty_bar[as]); else mbar_arrive(&tempty_bar[as]); }
         if (++as == 2) {
           as = 0;
           aphase ^= 1;
@@ -452,28 +534,58 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kCta2) cluster_sync_all(); else __syncthreads();  // the peer may not exit while its smem / TMEM is in use
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if constexpr (kCta2) tmem_dealloc2(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+static int g_gemm_cta2 = 1;  // CTA-pair kernels: on by default (cwm_debug_gemm_cta2(0) / CWM_GEMM_CTA2=0 switch them off)
+
+template <int BN, bool kRes, bool kCta2>
+static int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const CUtensorMap& tr,
+                            int M, int N, int K, const EpiDev& ep, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, kRes>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CWM_CUDA_CHECK(cudaFuncSetAttribute(gemm_f16_kernel<BN, kRes, kCta2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  if constexpr (kCta2) {
+    const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
+    int pairs = num_sms() / 2;
+    if (tiles < pairs) pairs = tiles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CWM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_f16_kernel<BN, kRes, true>, ta, tw, to, tr, M, N, K, ep));
+    count_launch();
+    return CWM_OK;
+  } else {
+    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    gemm_f16_kernel<BN, kRes, false><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tw, to, tr, M, N, K, ep);
+    CWM_LAUNCH_CHECK();
+    return CWM_OK;
   }
 }
 
 template <int BN, bool kRes>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const CUtensorMap& tr, int M,
-                       int N, int K, const EpiDev& ep, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, kRes>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CWM_CUDA_CHECK(cudaFuncSetAttribute(gemm_f16_kernel<BN, kRes>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        Cfg::kSmemBytes));
-    attr_set = true;
-  }
-  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_f16_kernel<BN, kRes><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tw, to, tr, M, N, K, ep);
-  CWM_LAUNCH_CHECK();
-  return CWM_OK;
+                       int N, int K, const EpiDev& ep, cudaStream_t stream, bool cta2) {
+  if (cta2) return launch_gemm_impl<BN, kRes, true>(ta, tw, to, tr, M, N, K, ep, stream);
+  return launch_gemm_impl<BN, kRes, false>(ta, tw, to, tr, M, N, K, ep, stream);
 }
 
 int pick_bn(int N) {
@@ -509,12 +621,21 @@ extern "C" int cwm_gemm_f16(const uint16_t* A, const uint16_t* W, int M, int N, 
   ep.res = e->res; ep.ldr = e->ldr; ep.res_gather = e->res_gather; ep.gather_stride = e->gather_stride;
   ep.grp_rows = e->grp_rows; ep.grp_out_stride = e->grp_out_stride; ep.out = e->out; ep.ldo = e->ldo;
   const int bn = pick_bn(N);
+  const bool remap = e->grp_rows > 0;
+  // CTA pairs: non-remapped epilogues, BN >= 128 (each CTA stages BN/2 rows of W, a multiple of 8-row swizzle atoms),
+  // enough rows for 256-row pair tiles
+  static bool env_checked = false;
+  if (!env_checked) {
+    env_checked = true;
+    const char* v = getenv("CWM_GEMM_CTA2");
+    if (v != nullptr) g_gemm_cta2 = atoi(v);
+  }
+  const bool cta2 = g_gemm_cta2 != 0 && !remap && bn >= 128 && M >= 2 * BM;
   CUtensorMap ta, tw, to, tr;
   int rc = make_tmap_2d(&ta, A, CWM_TMAP_F16, M, K, K, BM, BK);
   if (rc) return rc;
-  rc = make_tmap_2d(&tw, W, CWM_TMAP_F16, N, K, K, bn, BK);
+  rc = make_tmap_2d(&tw, W, CWM_TMAP_F16, N, K, K, cta2 ? bn / 2 : bn, BK);
   if (rc) return rc;
-  const bool remap = e->grp_rows > 0;
   if (f16_out) {
     rc = make_tmap_2d(&to, e->out, CWM_TMAP_F16, M, N, e->ldo, 32, 64);
     tr = to;
@@ -540,16 +661,21 @@ extern "C" int cwm_gemm_f16(const uint16_t* A, const uint16_t* W, int M, int N, 
                     (static_cast<double>(M) * K + static_cast<double>(N) * K) * 2.0 + out_bytes);
   if (f16_out) {
     switch (bn) {
-      case 64: return launch_gemm<64, false>(ta, tw, to, tr, M, N, K, ep, s);
-      case 128: return launch_gemm<128, false>(ta, tw, to, tr, M, N, K, ep, s);
-      case 192: return launch_gemm<192, false>(ta, tw, to, tr, M, N, K, ep, s);
-      default: return launch_gemm<256, false>(ta, tw, to, tr, M, N, K, ep, s);
+      case 64: return launch_gemm<64, false>(ta, tw, to, tr, M, N, K, ep, s, cta2);
+      case 128: return launch_gemm<128, false>(ta, tw, to, tr, M, N, K, ep, s, cta2);
+      case 192: return launch_gemm<192, false>(ta, tw, to, tr, M, N, K, ep, s, cta2);
+      default: return launch_gemm<256, false>(ta, tw, to, tr, M, N, K, ep, s, cta2);
     }
   }
   switch (bn) {
-    case 64: return launch_gemm<64, true>(ta, tw, to, tr, M, N, K, ep, s);
-    case 128: return launch_gemm<128, true>(ta, tw, to, tr, M, N, K, ep, s);
-    case 192: return launch_gemm<192, true>(ta, tw, to, tr, M, N, K, ep, s);
-    default: return launch_gemm<256, true>(ta, tw, to, tr, M, N, K, ep, s);
+    case 64: return launch_gemm<64, true>(ta, tw, to, tr, M, N, K, ep, s, cta2);
+    case 128: return launch_gemm<128, true>(ta, tw, to, tr, M, N, K, ep, s, cta2);
+    case 192: return launch_gemm<192, true>(ta, tw, to, tr, M, N, K, ep, s, cta2);
+    default: return launch_gemm<256, true>(ta, tw, to, tr, M, N, K, ep, s, cta2);
   }
+}
+
+extern "C" int cwm_debug_gemm_cta2(int enable) {
+  g_gemm_cta2 = enable;
+  return CWM_OK;
 }

@@ -95,7 +95,10 @@ def _gemm_ref(a, w):
 
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (1, 64, 16), (300, 768, 192), (1000, 2304, 768), (257, 384, 384),
                                    (513, 1152, 384), (130, 48, 512), (129, 192, 384), (1584, 1024, 48),
-                                   (777, 3072, 768), (50688, 768, 3072)])
+                                   (777, 3072, 768), (50688, 768, 3072),
+                                   # CTA-pair (cta_group::2) tiles with ragged N / M: W rows beyond N are zero-filled
+                                   # in the second CTA's half, the last pair tile has rows in one CTA only
+                                   (300, 200, 128), (520, 136, 64), (257, 256, 64), (256, 512, 1024)])
 def test_gemm_f32_bias(M, N, K):
     g = torch.Generator().manual_seed(M * 7 + N)
     a = (torch.randn(M, K, generator=g)).to(torch.float16).to(DEV)
@@ -345,3 +348,27 @@ def test_fill_pad_rows():
             sel = perm[:, off:off + rows] >= first_pad
             want[sel] = 0.0 if value is None else value
             assert torch.equal(got, want)
+
+
+def test_gemm_cta_pair_equals_single_cta():
+    """The cta_group::2 kernels (two CTAs share a 256-row tile, each stages half of W) give bit-identical results to
+    the single-CTA kernels: same MMA shapes along K, same accumulation order."""
+    import ctypes
+    lib = _lib.load()
+    lib.cwm_debug_gemm_cta2.argtypes = [ctypes.c_int]
+    g = torch.Generator().manual_seed(5)
+    try:
+        for (M, N, K, mode) in [(1000, 2304, 768, _lib.EPI_F16), (777, 3072, 768, _lib.EPI_GELU_F16),
+                                (1300, 768, 3072, _lib.EPI_RES_F32), (513, 1152, 384, _lib.EPI_F32)]:
+            a = torch.randn(M, K, generator=g).to(torch.float16).to(DEV)
+            w = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.float16).to(DEV)
+            bias = torch.randn(N, generator=g).to(DEV)
+            res = torch.randn(M, N, generator=g).to(DEV) if mode == _lib.EPI_RES_F32 else None
+            outs = []
+            for flag in (0, 1):
+                lib.cwm_debug_gemm_cta2(flag)
+                outs.append(ops.gemm_f16(a, w, mode, bias=bias, scale=0.125, scale_cols=N // 3 if mode == _lib.EPI_F16 else 0,
+                                         res=None if res is None else res.clone()).clone())
+            assert torch.equal(outs[0], outs[1]), (M, N, K, mode)
+    finally:
+        lib.cwm_debug_gemm_cta2(1)
