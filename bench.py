@@ -405,20 +405,25 @@ def main():
                 e2e_step(i)
             pipe.finish()
             barrier()
-            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            f0.record()
-            for i in range(steps):
-                e2e_step(i)
-            pipe.finish()
-            f1.record()
-            barrier()
-            t2 = torch.tensor([f0.elapsed_time(f1)], device=dev)
-            if world > 1:
-                dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-            e2e_ms = float(t2.item())
+            # host-side copies are exposed to host jitter (one 2.5x outlier was seen in ~15 runs): three passes of
+            # exactly K steps each, the median pass is reported and all three are listed
+            runs = []
+            for _ in range(3):
+                f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                f0.record()
+                for i in range(steps):
+                    e2e_step(i)
+                pipe.finish()
+                f1.record()
+                barrier()
+                t2 = torch.tensor([f0.elapsed_time(f1)], device=dev)
+                if world > 1:
+                    dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+                runs.append(float(t2.item()))
+            e2e_ms = sorted(runs)[1]
             e2e = {"value": world * B * steps / (e2e_ms * 1e-3), "unit": "frames/s",
                    "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
-                   "ms_per_step": e2e_ms / steps,
+                   "ms_per_step": e2e_ms / steps, "passes_ms_per_step": [round(r / steps, 3) for r in runs],
                    "api": "prediction.HostPipeline.submit(x_host, mask_host, out_host) per step (3 streams, 2 slots)"}
             # the pipelined result is bit-identical to a plain predict of the same batch
             chk = G.predict(xs_dev[(steps - 1) % n_rot], ms_dev[(steps - 1) % n_rot], frame=None, **pred_kwargs)

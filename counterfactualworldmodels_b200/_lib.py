@@ -24,6 +24,7 @@ EXPORTED_SYMBOLS = (
     "cwm_cf_build_videos", "cwm_cf_make_static", "cwm_patch_gather_cf", "cwm_unpatchify_scatter_cf",
     "cwm_flow_sample_stats", "cwm_flow_filter_mask", "cwm_flow_zero_filtered", "cwm_flow_magnitude_sum",
     "cwm_motion_map_finalize", "cwm_flow_stats_workspace_bytes", "cwm_flow_corrs_workspace_bytes", "cwm_flow_corrs",
+    "cwm_gemm_ln_parts", "cwm_rowstats_f16",
 )
 
 
@@ -36,13 +37,16 @@ class GemmEpilogue(Structure):
         ("mode", c_int32), ("bias", c_void_p), ("scale", c_float), ("scale_cols", c_int32),
         ("res", c_void_p), ("ldr", c_int32), ("res_gather", c_void_p), ("gather_stride", c_int32),
         ("grp_rows", c_int32), ("grp_out_stride", c_int32), ("out", c_void_p), ("ldo", c_int32),
+        # LayerNorm fusion (optional; zero = off)
+        ("ln_x16", c_void_p), ("ln_ldx16", c_int32), ("ln_stats_out", c_void_p), ("ln_stats_in", c_void_p),
+        ("ln_parts", c_int32), ("ln_colsum", c_void_p), ("ln_width", c_int32), ("ln_eps", c_float),
     ]
 
 
 class BlockWeights(Structure):
     _fields_ = [(n, c_void_p) for n in (
         "ln1_g", "ln1_b", "w_qkv", "b_qkv", "w_proj", "b_proj", "ln2_g", "ln2_b", "w_fc1", "b_fc1", "w_fc2",
-        "b_fc2")]
+        "b_fc2", "w_qkv_ln", "s_qkv", "c_qkv", "w_fc1_ln", "s_fc1", "c_fc1")]
 
 
 class CrossBlockWeights(Structure):
@@ -92,6 +96,8 @@ def _declare(lib):
     lib.cwm_layernorm_f16.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_int,
                                       c_void_p, c_void_p]
     lib.cwm_gemm_f16.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, POINTER(GemmEpilogue), c_void_p]
+    lib.cwm_gemm_ln_parts.argtypes = [c_int]
+    lib.cwm_rowstats_f16.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
     lib.cwm_attention_f16.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]
     lib.cwm_fill_mask_tokens.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                                          c_void_p]

@@ -54,22 +54,23 @@ static PFN_encodeTiled get_encode() {
 }
 
 int make_tmap_2d(CUtensorMap* map, const void* base, int dtype, uint64_t rows, uint64_t cols, uint64_t ld,
-                 uint32_t box_rows, uint32_t box_cols) {
+                 uint32_t box_rows, uint32_t box_cols, int swizzle_bytes) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return fail(CWM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   const uint64_t elt = (dtype == CWM_TMAP_F32) ? 4 : 2;
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * elt) % 16 != 0)
     return fail(CWM_ERR_INVALID, "TMA operand must be 16-byte aligned (base %p, ld %llu)", base,
                 (unsigned long long)ld);
-  if (box_cols * elt > 128 || box_rows > 256)
-    return fail(CWM_ERR_INVALID, "TMA box [%u, %u] too large for 128B swizzle", box_rows, box_cols);
+  if (box_cols * elt > static_cast<uint64_t>(swizzle_bytes) || box_rows > 256 || (swizzle_bytes != 128 && swizzle_bytes != 64))
+    return fail(CWM_ERR_INVALID, "TMA box [%u, %u] too large for %dB swizzle", box_rows, box_cols, swizzle_bytes);
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstride[1] = {ld * elt};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, dtype == CWM_TMAP_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
                    const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(CWM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box=[%u,%u]", (int)r,
                 (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows, box_cols);

@@ -45,7 +45,7 @@ void reset_launches();
 // 128-byte swizzle (box_cols * element size must be <= 128).
 enum { CWM_TMAP_F16 = 0, CWM_TMAP_F32 = 1 };
 int make_tmap_2d(CUtensorMap* map, const void* base, int dtype, uint64_t rows, uint64_t cols, uint64_t ld,
-                 uint32_t box_rows, uint32_t box_cols);
+                 uint32_t box_rows, uint32_t box_cols, int swizzle_bytes = 128);
 int num_sms();
 
 // Optional per-launch CUDA-event timing (cwm_profile_begin/end).  No-op (one branch) when profiling is off.

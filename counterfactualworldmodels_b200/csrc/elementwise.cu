@@ -165,6 +165,33 @@ layernorm_f16_kernel(const float* __restrict__ x, int M, const float* __restrict
 }
 
 
+// First LayerNorm of a stream when the LayerNorm is fused into the consumer GEMM (gemm.cu): f16 copy of the rows and
+// per-row (sum, sum of squares) in the same format the residual-GEMM epilogues emit (one partial plane).
+__global__ void __launch_bounds__(256)
+rowstats_f16_kernel(const float* __restrict__ x, int M, int C4, __half* __restrict__ x16, float2* __restrict__ stats) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const float4* xr = reinterpret_cast<const float4*>(x) + static_cast<long long>(warp) * C4;
+  uint2* orow = reinterpret_cast<uint2*>(x16) + static_cast<long long>(warp) * C4;
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = lane; i < C4; i += 32) {
+    const float4 v = xr[i];
+    s1 += (v.x + v.y) + (v.z + v.w);
+    s2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    uint2 o;
+    o.x = pack_half2(v.x, v.y);
+    o.y = pack_half2(v.z, v.w);
+    orow[i] = o;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if (lane == 0) stats[warp] = make_float2(s1, s2);
+}
+
 // Same algorithm for widths that are not a multiple of 128 (context-stream widths 64 / 192, conjoined_vmae.py:
 // 1198-1204): C % 4 == 0, C <= 1024; lanes beyond the row end hold zeros and are excluded from the statistics.
 __global__ void __launch_bounds__(256)
@@ -422,6 +449,20 @@ extern "C" int cwm_layernorm_f16(const float* x, int M, int C, const float* gamm
       return fail(CWM_ERR_UNSUPPORTED, "cwm_layernorm_f16: unsupported C=%d", C);
   }
 #undef LN_CASE
+  CWM_LAUNCH_CHECK();
+  return CWM_OK;
+}
+
+extern "C" int cwm_rowstats_f16(const float* x, int M, int C, uint16_t* x16, float* stats, cwm_stream_t stream) {
+  CWM_REQUIRE(x && x16 && stats, "cwm_rowstats_f16: null pointer");
+  CWM_REQUIRE(C % 4 == 0 && C >= 4, "cwm_rowstats_f16: C=%d must be a multiple of 4", C);
+  if (M == 0) return CWM_OK;
+  const int threads = 256;
+  const unsigned blocks = (M + 7) / 8;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  ProfileScope prof(s, "rowstats_f16", 0.0, static_cast<double>(M) * C * 6.0);
+  rowstats_f16_kernel<<<blocks, threads, 0, s>>>(x, M, C / 4, reinterpret_cast<__half*>(x16),
+                                                 reinterpret_cast<float2*>(stats));
   CWM_LAUNCH_CHECK();
   return CWM_OK;
 }

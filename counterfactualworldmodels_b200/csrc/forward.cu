@@ -10,8 +10,9 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 struct Plan {
   int Ntot, Nvis, Nmask, out_rows, Kp;
   long long Me, Md, Mo;
-  size_t off_xe, off_xd, off_a16, off_qkv, off_attn, off_h16, total;
+  size_t off_xe, off_xd, off_a16, off_qkv, off_attn, off_h16, off_stats, total;
 };
+constexpr int kMaxLnParts = 16;  // partial-statistics planes of a LayerNorm-producer GEMM (2 per N tile, N <= 1024)
 
 static int make_plan(const cwm_vmae_model* m, int B, int Nvis, Plan* p) {
   if (!m) return fail(CWM_ERR_INVALID, "cwm_vmae: null model");
@@ -42,6 +43,7 @@ static int make_plan(const cwm_vmae_model* m, int B, int Nvis, Plan* p) {
   p->off_qkv = off; off = align_up(off + mx(p->Me * 3 * m->enc_dim, p->Md * 3 * m->dec_dim) * 2, 1024);
   p->off_attn = off; off = align_up(off + mx(p->Me * m->enc_dim, p->Md * m->dec_dim) * 2, 1024);
   p->off_h16 = off; off = align_up(off + mx(p->Me * m->enc_hidden, p->Md * m->dec_hidden) * 2, 1024);
+  p->off_stats = off; off = align_up(off + mx(p->Me, p->Md) * kMaxLnParts * 8, 1024);
   p->total = off + 1024;
   return CWM_OK;
 }
@@ -70,11 +72,53 @@ static cwm_gemm_epilogue epi_res(const float* bias, float* x, int ld) {
 
 // x += Attn(LN1(x)); x += Mlp(LN2(x))   (cwm/models/VideoMAE/utils.py:146-153, gamma_* = None)
 // inner attention width A = heads * head_dim; `attn` may alias `a16` (the LN output is dead once qkv is computed).
+//
+// Fused-LayerNorm path (folded weights present, a statistics buffer, attn != a16): no LayerNorm kernel at all.
+// `a16` then holds f16(x) written by the epilogue of the GEMM that last updated x (or by the row-statistics kernel
+// for the first block of a stream) together with per-row partial statistics in `stats`; the qkv / fc1 epilogues
+// normalise.  *x16_valid says whether a16 / stats describe the current x on entry; emit_for_next asks fc2 to produce
+// them for the following block.
 static int run_block(const cwm_block_weights& w, float* x, int Bn, int N, int C, int heads, int head_dim, int hidden,
                      float eps, float qk_scale, uint16_t* a16, uint16_t* qkv, uint16_t* attn, uint16_t* h16,
-                     cwm_stream_t st) {
+                     cwm_stream_t st, float* stats = nullptr, bool* x16_valid = nullptr, bool emit_for_next = false) {
   const int M = Bn * N;
   const int A = heads * head_dim;
+  const bool fused = w.w_qkv_ln != nullptr && w.w_fc1_ln != nullptr && stats != nullptr && x16_valid != nullptr &&
+                     attn != a16 && C % 32 == 0 && cwm_gemm_ln_parts(C) <= kMaxLnParts;
+  if (fused) {
+    const int parts_c = cwm_gemm_ln_parts(C);
+    int parts = parts_c;
+    if (!*x16_valid) {
+      CWM_TRY(cwm_rowstats_f16(x, M, C, a16, stats, st));
+      parts = 1;
+    }
+    auto with_ln = [&](cwm_gemm_epilogue e, const float* colsum, int n_parts) {
+      e.ln_stats_in = stats; e.ln_parts = n_parts; e.ln_colsum = colsum; e.ln_width = C; e.ln_eps = eps;
+      return e;
+    };
+    auto with_emit = [&](cwm_gemm_epilogue e) {
+      e.ln_x16 = a16; e.ln_ldx16 = C; e.ln_stats_out = stats;
+      return e;
+    };
+    cwm_gemm_epilogue e = with_ln(epi_f16(w.c_qkv, qk_scale, A, qkv, 3 * A), w.s_qkv, parts);
+    CWM_TRY(cwm_gemm_f16(a16, w.w_qkv_ln, M, 3 * A, C, &e, st));
+    if (head_dim == 64) {
+      CWM_TRY(cwm_attention_f16(qkv, Bn, N, heads, 64, attn, st));
+    } else {
+      CWM_TRY(cwm_attention_generic_f16(qkv, qkv + A, qkv + 2 * A, 3 * A, 3 * A, 3 * A, head_dim, head_dim, head_dim, Bn,
+                                        N, N, heads, head_dim, attn, A, nullptr, 0, st));
+    }
+    e = with_emit(epi_res(w.b_proj, x, C));
+    CWM_TRY(cwm_gemm_f16(attn, w.w_proj, M, C, A, &e, st));
+    e = with_ln(epi_gelu(w.c_fc1, h16, hidden), w.s_fc1, parts_c);
+    CWM_TRY(cwm_gemm_f16(a16, w.w_fc1_ln, M, hidden, C, &e, st));
+    e = epi_res(w.b_fc2, x, C);
+    if (emit_for_next) e = with_emit(e);
+    CWM_TRY(cwm_gemm_f16(h16, w.w_fc2, M, C, hidden, &e, st));
+    *x16_valid = emit_for_next;
+    return CWM_OK;
+  }
+  if (x16_valid != nullptr) *x16_valid = false;
   CWM_TRY(cwm_layernorm_f16(x, M, C, w.ln1_g, w.ln1_b, eps, 0, 0, 0, a16, st));
   cwm_gemm_epilogue e = epi_f16(w.b_qkv, qk_scale, A, qkv, 3 * A);  // (xW + [q_bias,0,v_bias]); q *= scale
   CWM_TRY(cwm_gemm_f16(a16, w.w_qkv, M, 3 * A, C, &e, st));
@@ -156,6 +200,7 @@ static int vmae_forward_impl(const cwm_vmae_model* m, const float* x, const int6
   uint16_t* qkv = reinterpret_cast<uint16_t*>(ws + p.off_qkv);
   uint16_t* attn = reinterpret_cast<uint16_t*>(ws + p.off_attn);
   uint16_t* h16 = reinterpret_cast<uint16_t*>(ws + p.off_h16);
+  float* stats = reinterpret_cast<float*>(ws + p.off_stats);
   const int Ce = m->enc_dim, Cd = m->dec_dim;
 
   if (Nvis > 0) {
@@ -172,9 +217,10 @@ static int vmae_forward_impl(const cwm_vmae_model* m, const float* x, const int6
     e.gather_stride = p.Ntot; e.grp_rows = Nvis; e.grp_out_stride = Nvis; e.out = xe; e.ldo = Ce;
     CWM_TRY(cwm_gemm_f16(a16, m->w_patch, static_cast<int>(p.Me), Ce, p.Kp, &e, st));
     // a5-a7: encoder blocks
+    bool x16_valid = false;
     for (int l = 0; l < m->enc_depth; ++l)
       CWM_TRY(run_block(m->enc_blocks[l], xe, B, Nvis, Ce, m->enc_heads, 64, m->enc_hidden, m->ln_eps, m->enc_qk_scale,
-                        a16, qkv, attn, h16, st));
+                        a16, qkv, attn, h16, st, stats, &x16_valid, l + 1 < m->enc_depth));
     // a8-a10: final norm, encoder_to_decoder (no bias) written at the visible rows of the decoder sequence with
     // the positional embedding of each visible token added
     CWM_TRY(cwm_layernorm_f16(xe, static_cast<int>(p.Me), Ce, m->enc_norm_g, m->enc_norm_b, m->ln_eps, 0, 0, 0, a16, st));
@@ -185,9 +231,10 @@ static int vmae_forward_impl(const cwm_vmae_model* m, const float* x, const int6
   }
   CWM_TRY(cwm_fill_mask_tokens(m->mask_token, m->pos_dec, perm, B, p.Ntot, Nvis, Cd, xd, st));
   // a11: decoder blocks over all Ntot tokens, then head(norm(last Nmask tokens))
+  bool xd16_valid = false;
   for (int l = 0; l < m->dec_depth; ++l)
     CWM_TRY(run_block(m->dec_blocks[l], xd, B, p.Ntot, Cd, m->dec_heads, 64, m->dec_hidden, m->ln_eps, m->dec_qk_scale, a16,
-                      qkv, attn, h16, st));
+                      qkv, attn, h16, st, stats, &xd16_valid, l + 1 < m->dec_depth));
   if (p.Nmask > 0) {
     CWM_TRY(cwm_layernorm_f16(xd, static_cast<int>(p.Mo), Cd, m->dec_norm_g, m->dec_norm_b, m->ln_eps, p.Nmask, p.Ntot,
                               Nvis, a16, st));

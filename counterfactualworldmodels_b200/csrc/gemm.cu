@@ -32,8 +32,12 @@ constexpr int kChunkBytes = 32 * 128;  // one epilogue chunk: 32 rows x 128 byte
 template <int BN, bool kRes>
 struct GemmCfg {
   // epilogue smem: kRes (fp32 out, optional residual): 2 buffers / warp, else 1 buffer / warp
-  static constexpr int kEpiBytes = kEpiWarps * kChunkBytes * (kRes ? 2 : 1);
-  static constexpr int kBiasBytes = kEpiWarps * 64 * 4;
+  // (+ 2 KB per warp for the f16 copy the LayerNorm-producer epilogue emits: 32 rows x 64 bytes, 64B-swizzled)
+  static constexpr int kX16Bytes = 32 * 64;
+  static constexpr int kEpiBytes = kEpiWarps * (kChunkBytes * (kRes ? 2 : 1) + (kRes ? kX16Bytes : 0));
+  // per warp: f16-out epilogues stage 64 bias values + 64 LayerNorm column sums, fp32 epilogues 32 bias values
+  static constexpr int kBiasWarpBytes = kRes ? 128 : 512;
+  static constexpr int kBiasBytes = kEpiWarps * kBiasWarpBytes;
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
@@ -58,6 +62,19 @@ struct EpiDev {
   int grp_out_stride;
   void* out;
   int ldo;
+  // ---- LayerNorm fusion ----
+  // producer side (fp32 residual epilogue): f16 copy of the updated residual rows (the A operand of the next GEMM) and
+  // per-row partial statistics (sum, sum of squares) of this CTA's columns: ln_stats_out[(n_blk * 2 + half) * M + row]
+  __half* x16;
+  int ldx16;
+  float2* ln_stats_out;
+  // consumer side (f16 epilogues): out = rstd_m * (acc - mean_m * ln_s[n]) + bias[n], with mean / rstd of row m
+  // rebuilt from ln_parts partial statistics; the LayerNorm affine is folded into W (gamma), ln_s and bias (beta)
+  const float2* ln_stats_in;
+  int ln_parts;
+  const float* ln_s;
+  float ln_inv_c;
+  float ln_eps;
 };
 
 // GELU(x) = 0.5 x (1 + erf(x / sqrt 2)), branch-free with one MUFU:
@@ -73,6 +90,58 @@ __device__ __forceinline__ float gelu_erf(float x) {
   float p;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(z * q));
   return fmaf(0.5f * ax, 1.0f - p, 0.5f * x);
+}
+
+// ---- packed dual-fp32 math (Blackwell fma/mul/add .f32x2: one issue slot for two lanes).  The f16-out epilogues
+//      are issue-bound for K <= 1024 (8 epilogue warps have ~6k cycles per 128x256 tile), so bias / LayerNorm / GELU
+//      run on register pairs; every lane computes exactly what the scalar formulas above compute. ----
+__device__ __forceinline__ uint64_t pk2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t pk2u(uint32_t a, uint32_t b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// gelu_erf on a pair (same operations, lane for lane)
+__device__ __forceinline__ uint64_t gelu_erf2(uint64_t x) {
+  float x0, x1;
+  upk2(x, x0, x1);
+  const uint64_t ax = pk2(fabsf(x0), fabsf(x1));
+  float z0, z1;
+  upk2(mul2(ax, pk2(0.70710678118654752440f, 0.70710678118654752440f)), z0, z1);
+  const uint64_t z = pk2(fminf(z0, 4.0f), fminf(z1, 4.0f));
+  uint64_t q = fma2(pk2(-0.0029442342929542065f, -0.0029442342929542065f), z, pk2(0.029590291902422905f, 0.029590291902422905f));
+  q = fma2(q, z, pk2(-0.1486659049987793f, -0.1486659049987793f));
+  q = fma2(q, z, pk2(-0.9185092449188232f, -0.9185092449188232f));
+  q = fma2(q, z, pk2(-1.6278890371322632f, -1.6278890371322632f));
+  float t0, t1, p0, p1;
+  upk2(mul2(z, q), t0, t1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(t0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(t1));
+  const uint64_t omp = fma2(pk2(p0, p1), pk2(-1.0f, -1.0f), pk2(1.0f, 1.0f));  // 1 - p
+  const uint64_t half2 = pk2(0.5f, 0.5f);
+  return fma2(mul2(ax, half2), omp, mul2(x, half2));
 }
 
 // ---- explicit shared-space accesses (the smem pointers are carved from a uintptr_t, keep them out of the
@@ -168,8 +237,8 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
 template <int BN, bool kRes, bool kCta2>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w,
-                const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_res, int M, int N,
-                int K, EpiDev ep) {
+                const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_res,
+                const __grid_constant__ CUtensorMap tma_x16, int M, int N, int K, EpiDev ep) {
   using Cfg = GemmCfg<BN, kRes>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_a = smem;
@@ -312,7 +381,9 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     const int quad = ew & 3;   // TMEM lane quadrant == warp % 4
     const int half = ew >> 2;  // which column chunks this warp takes
     const uint32_t buf0 = smem_u32(smem_epi) + ew * kChunkBytes * (kRes ? 2 : 1);
-    const uint32_t bias_s = smem_u32(smem_bias) + ew * 256;
+    const uint32_t x16_s = smem_u32(smem_epi) + kEpiWarps * kChunkBytes * 2 + ew * Cfg::kX16Bytes;  // kRes only
+    const uint32_t bias_s = smem_u32(smem_bias) + ew * Cfg::kBiasWarpBytes;
+    const uint32_t lns_s = bias_s + 256;
     const uint32_t row_s = lane * 128;      // this thread's row inside a chunk buffer
     const uint32_t sw = lane & 7;           // 128B swizzle: 16-byte unit index ^= row % 8
     int as = 0;
@@ -322,20 +393,58 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       // ---------------- f16 output: 64-column chunks, TMA store ----------------
       constexpr int kChunks = BN / 64;
       const bool gelu = (ep.mode == CWM_EPI_GELU_F16);
+      const bool ln = (ep.ln_stats_in != nullptr);
+      float2 ln_t[8];  // partial statistics of this thread's row in the tile being prepared (all loads back to back:
+                       // a rolled loop serialises one L2 round trip per plane, measured +30 us per launch)
+      auto load_ln_stats = [&](int row) {
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp)
+          ln_t[pp] = (pp < ep.ln_parts && row < M) ? __ldg(ep.ln_stats_in + static_cast<long long>(pp) * M + row)
+                                                   : make_float2(0.f, 0.f);
+      };
+      if (ln && tile_first < num_tiles) load_ln_stats((tile_first / tiles_n) * TM + cta_rank * BM + quad * 32 + lane);
       for (int tile = tile_first; tile < num_tiles; tile += tile_stride) {
         const int m_blk = tile / tiles_n;
         const int n_blk = tile - m_blk * tiles_n;
-        mbar_wait(&tfull_bar[as], aphase);
-        tc_fence_after();
         const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
         const int row0 = m_blk * TM + cta_rank * BM + quad * 32;
+        // fused LayerNorm: statistics of this thread's row from the producer's partial sums, summed in plane order
+        // (deterministic).  The loads for the NEXT tile are issued here, one tile ahead, so that their L2 round trip
+        // never sits on the epilogue's critical path.
+        float ln_mean = 0.f, ln_rstd = 1.f;
+        if (ln) {
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+          for (int pp = 0; pp < 8; ++pp) {
+            s1 += ln_t[pp].x;
+            s2 += ln_t[pp].y;
+          }
+          const int row = row0 + lane;
+          for (int pp = 8; pp < ep.ln_parts; ++pp) {  // (more than 4 N tiles: not reached by any CWM model)
+            if (row < M) {
+              const float2 u = __ldg(ep.ln_stats_in + static_cast<long long>(pp) * M + row);
+              s1 += u.x;
+              s2 += u.y;
+            }
+          }
+          ln_mean = s1 * ep.ln_inv_c;
+          ln_rstd = rsqrtf(fmaxf(s2 * ep.ln_inv_c - ln_mean * ln_mean, 0.f) + ep.ln_eps);
+          const int next_tile = tile + tile_stride;
+          if (next_tile < num_tiles) load_ln_stats((next_tile / tiles_n) * TM + cta_rank * BM + quad * 32 + lane);
+        }
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
         for (int c = half; c < kChunks; c += 2) {
           const int n0 = n_blk * BN + c * 64;
           // bias of the 64 columns -> per-warp smem (broadcast reads below)
-          float b_lo = 0.f, b_hi = 0.f;
+          float b_lo = 0.f, b_hi = 0.f, s_lo = 0.f, s_hi = 0.f;
           if (ep.bias != nullptr) {
             if (n0 + lane < N) b_lo = __ldg(ep.bias + n0 + lane);
             if (n0 + 32 + lane < N) b_hi = __ldg(ep.bias + n0 + 32 + lane);
+          }
+          if (ln) {
+            if (n0 + lane < N) s_lo = __ldg(ep.ln_s + n0 + lane);
+            if (n0 + 32 + lane < N) s_hi = __ldg(ep.ln_s + n0 + 32 + lane);
           }
           uint32_t acc[64];
           tmem_ld_x32(tmem_acc + c * 64, acc);
@@ -343,6 +452,10 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
           __syncwarp();  // previous chunk's broadcast reads of bias_s are done
           sts32(bias_s + lane * 4, __float_as_uint(b_lo));
           sts32(bias_s + 128 + lane * 4, __float_as_uint(b_hi));
+          if (ln) {
+            sts32(lns_s + lane * 4, __float_as_uint(s_lo));
+            sts32(lns_s + 128 + lane * 4, __float_as_uint(s_hi));
+          }
           tmem_ld_wait();
           const bool last_chunk = (c + 2 >= kChunks);
           if (last_chunk) {  // all TMEM reads of this tile by this warp are complete -> release the stage early
@@ -352,20 +465,46 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
           __syncwarp();
           if (elect_one()) bulk_wait_read0();  // the previous TMA store has finished reading the buffer
           __syncwarp();
+          // chunk-uniform q-scale (the boundary is a multiple of 64 for every model: heads * 64); a chunk that
+          // straddles it falls back to per-element selection
+          const bool sc_all = !gelu && (n0 + 64 <= ep.scale_cols);
+          const bool sc_mixed = !gelu && !sc_all && (n0 < ep.scale_cols);
+          const uint64_t sc2 = pk2(ep.scale, ep.scale);
+          const uint64_t rstd2 = pk2(ln_rstd, ln_rstd);
+          const uint64_t nmr2 = pk2(-ln_mean * ln_rstd, -ln_mean * ln_rstd);
 #pragma unroll
           for (int u = 0; u < 8; ++u) {  // 16-byte unit u = columns 8u .. 8u+7
             uint32_t bb[8];
             lds128(bias_s + u * 32, bb[0], bb[1], bb[2], bb[3]);
             lds128(bias_s + u * 32 + 16, bb[4], bb[5], bb[6], bb[7]);
+            uint64_t v2[4];
+            if (ln) {  // rstd * acc + (c - rstd * mean * s)
+              uint32_t ss[8];
+              lds128(lns_s + u * 32, ss[0], ss[1], ss[2], ss[3]);
+              lds128(lns_s + u * 32 + 16, ss[4], ss[5], ss[6], ss[7]);
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                v2[q] = fma2(rstd2, pk2u(acc[u * 8 + 2 * q], acc[u * 8 + 2 * q + 1]),
+                             fma2(nmr2, pk2u(ss[2 * q], ss[2 * q + 1]), pk2u(bb[2 * q], bb[2 * q + 1])));
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                v2[q] = add2(pk2u(acc[u * 8 + 2 * q], acc[u * 8 + 2 * q + 1]), pk2u(bb[2 * q], bb[2 * q + 1]));
+            }
             float v[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              v[q] = __uint_as_float(acc[u * 8 + q]) + __uint_as_float(bb[q]);
+            for (int q = 0; q < 4; ++q) {
               if (gelu) {
-                v[q] = gelu_erf(v[q]);
-              } else if (n0 + u * 8 + q < ep.scale_cols) {
-                v[q] *= ep.scale;
+                v2[q] = gelu_erf2(v2[q]);
+              } else if (sc_all) {
+                v2[q] = mul2(v2[q], sc2);
               }
+              upk2(v2[q], v[2 * q], v[2 * q + 1]);
+            }
+            if (sc_mixed) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                if (n0 + u * 8 + q < ep.scale_cols) v[q] *= ep.scale;
             }
             sts128(buf0 + row_s + ((u ^ sw) << 4), pack_half2(v[0], v[1]), pack_half2(v[2], v[3]),
                    pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
@@ -409,6 +548,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         first = (ci == 0);
         last = (ci == my_chunks - 1);
       };
+      const bool emit = (ep.x16 != nullptr);  // LayerNorm fusion: f16 copy + partial row statistics
+      float ps1 = 0.f, ps2 = 0.f;
       if (has_res && n_items > 0 && elect_one()) {  // prefetch the residual chunk of the first item
         int row0, n0, c;
         bool f, l;
@@ -452,6 +593,9 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         }
         if (has_res) mbar_wait(&my_res_bar[it & 1], (it >> 1) & 1);
         __syncwarp();
+        if (first) ps1 = ps2 = 0.f;
+        uint64_t acc1 = pk2(0.f, 0.f), acc2 = pk2(0.f, 0.f);  // packed partial sums of this chunk
+        uint32_t h16[16];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {  // 16-byte unit u = columns 4u .. 4u+3
           uint32_t bb[4];
@@ -467,11 +611,36 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
             for (int q = 0; q < 4; ++q) v[q] += __uint_as_float(r[q]);
           }
           sts128(addr, __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+          if (emit) {
+            const uint64_t a2 = pk2(v[0], v[1]), b2 = pk2(v[2], v[3]);
+            acc1 = add2(acc1, add2(a2, b2));
+            acc2 = fma2(a2, a2, fma2(b2, b2, acc2));
+            h16[2 * u] = pack_half2(v[0], v[1]);
+            h16[2 * u + 1] = pack_half2(v[2], v[3]);
+          }
+        }
+        if (emit) {
+          float e0, e1;
+          upk2(acc1, e0, e1);
+          ps1 += e0 + e1;
+          upk2(acc2, e0, e1);
+          ps2 += e0 + e1;
+          const int row = row0 + lane;
+          // f16 copy: 64-byte rows in shared memory, 64B swizzle (16-byte unit ^= (row >> 1) & 3), one TMA store per chunk
+          // (its buffer is free: the bulk_wait_read0 of this item also covered the previous chunk's f16 store)
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            sts128(x16_s + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4), h16[4 * q], h16[4 * q + 1], h16[4 * q + 2], h16[4 * q + 3]);
+          if (last && row < M) {
+            const int n_blk_t = n0 / BN;
+            ep.ln_stats_out[static_cast<long long>(n_blk_t * 2 + half) * M + row] = make_float2(ps1, ps2);
+          }
         }
         fence_proxy_async_smem();
         __syncwarp();
         if (elect_one()) {
           tma_store_2d(&tma_out, buf, n0, row0);
+          if (emit) tma_store_2d(&tma_x16, x16_s, n0, row0);
           bulk_commit();
         }
         if (last) {
@@ -545,7 +714,7 @@ static int g_gemm_cta2 = 1;  // CTA-pair kernels: on by default (cwm_debug_gemm_
 
 template <int BN, bool kRes, bool kCta2>
 static int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const CUtensorMap& tr,
-                            int M, int N, int K, const EpiDev& ep, cudaStream_t stream) {
+                            const CUtensorMap& tx, int M, int N, int K, const EpiDev& ep, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, kRes>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -569,23 +738,23 @@ static int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tw, const 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CWM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_f16_kernel<BN, kRes, true>, ta, tw, to, tr, M, N, K, ep));
+    CWM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_f16_kernel<BN, kRes, true>, ta, tw, to, tr, tx, M, N, K, ep));
     count_launch();
     return CWM_OK;
   } else {
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    gemm_f16_kernel<BN, kRes, false><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tw, to, tr, M, N, K, ep);
+    gemm_f16_kernel<BN, kRes, false><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tw, to, tr, tx, M, N, K, ep);
     CWM_LAUNCH_CHECK();
     return CWM_OK;
   }
 }
 
 template <int BN, bool kRes>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const CUtensorMap& tr, int M,
-                       int N, int K, const EpiDev& ep, cudaStream_t stream, bool cta2) {
-  if (cta2) return launch_gemm_impl<BN, kRes, true>(ta, tw, to, tr, M, N, K, ep, stream);
-  return launch_gemm_impl<BN, kRes, false>(ta, tw, to, tr, M, N, K, ep, stream);
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const CUtensorMap& tr,
+                       const CUtensorMap& tx, int M, int N, int K, const EpiDev& ep, cudaStream_t stream, bool cta2) {
+  if (cta2) return launch_gemm_impl<BN, kRes, true>(ta, tw, to, tr, tx, M, N, K, ep, stream);
+  return launch_gemm_impl<BN, kRes, false>(ta, tw, to, tr, tx, M, N, K, ep, stream);
 }
 
 int pick_bn(int N) {
@@ -620,6 +789,23 @@ extern "C" int cwm_gemm_f16(const uint16_t* A, const uint16_t* W, int M, int N, 
   ep.mode = e->mode; ep.bias = e->bias; ep.scale = e->scale; ep.scale_cols = (e->mode == CWM_EPI_F16) ? e->scale_cols : 0;
   ep.res = e->res; ep.ldr = e->ldr; ep.res_gather = e->res_gather; ep.gather_stride = e->gather_stride;
   ep.grp_rows = e->grp_rows; ep.grp_out_stride = e->grp_out_stride; ep.out = e->out; ep.ldo = e->ldo;
+  ep.x16 = nullptr; ep.ldx16 = 0; ep.ln_stats_out = nullptr;
+  ep.ln_stats_in = nullptr; ep.ln_parts = 0; ep.ln_s = nullptr; ep.ln_inv_c = 0.f; ep.ln_eps = 0.f;
+  if (e->ln_x16 != nullptr) {
+    CWM_REQUIRE(e->mode == CWM_EPI_RES_F32 && e->grp_rows <= 0 && e->ln_stats_out != nullptr && N % 32 == 0 &&
+                    reinterpret_cast<uintptr_t>(e->ln_x16) % 16 == 0 && e->ln_ldx16 % 8 == 0 && e->ln_ldx16 >= N,
+                "cwm_gemm_f16: LayerNorm-producer outputs need the plain fp32-residual epilogue, N %% 32 == 0 and a "
+                "16-byte aligned f16 copy");
+    ep.x16 = reinterpret_cast<__half*>(e->ln_x16); ep.ldx16 = e->ln_ldx16;
+    ep.ln_stats_out = reinterpret_cast<float2*>(e->ln_stats_out);
+  }
+  if (e->ln_stats_in != nullptr) {
+    CWM_REQUIRE((e->mode == CWM_EPI_F16 || e->mode == CWM_EPI_GELU_F16) && e->ln_parts > 0 && e->ln_colsum != nullptr &&
+                    e->ln_width > 0,
+                "cwm_gemm_f16: the fused-LayerNorm epilogue needs an f16 output mode, partial statistics and column sums");
+    ep.ln_stats_in = reinterpret_cast<const float2*>(e->ln_stats_in); ep.ln_parts = e->ln_parts; ep.ln_s = e->ln_colsum;
+    ep.ln_inv_c = 1.0f / static_cast<float>(e->ln_width); ep.ln_eps = e->ln_eps;
+  }
   const int bn = pick_bn(N);
   const bool remap = e->grp_rows > 0;
   // CTA pairs: non-remapped epilogues, BN >= 128 (each CTA stages BN/2 rows of W, a multiple of 8-row swizzle atoms),
@@ -654,6 +840,11 @@ extern "C" int cwm_gemm_f16(const uint16_t* A, const uint16_t* W, int M, int N, 
     tr = ta;
   }
   if (rc) return rc;
+  CUtensorMap tx = to;  // f16 copy of the output rows (LayerNorm-producer epilogue): 32 x 32 boxes, 64B swizzle
+  if (ep.x16 != nullptr) {
+    rc = make_tmap_2d(&tx, ep.x16, CWM_TMAP_F16, M, N, ep.ldx16, 32, 32, 64);
+    if (rc) return rc;
+  }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   static const char* kNames[4] = {"gemm_f16_out", "gemm_gelu_f16_out", "gemm_residual_f32", "gemm_f32_out"};
   const double out_bytes = static_cast<double>(M) * N * (f16_out ? 2.0 : (e->mode == CWM_EPI_RES_F32 ? 8.0 : 4.0));
@@ -661,21 +852,27 @@ extern "C" int cwm_gemm_f16(const uint16_t* A, const uint16_t* W, int M, int N, 
                     (static_cast<double>(M) * K + static_cast<double>(N) * K) * 2.0 + out_bytes);
   if (f16_out) {
     switch (bn) {
-      case 64: return launch_gemm<64, false>(ta, tw, to, tr, M, N, K, ep, s, cta2);
-      case 128: return launch_gemm<128, false>(ta, tw, to, tr, M, N, K, ep, s, cta2);
-      case 192: return launch_gemm<192, false>(ta, tw, to, tr, M, N, K, ep, s, cta2);
-      default: return launch_gemm<256, false>(ta, tw, to, tr, M, N, K, ep, s, cta2);
+      case 64: return launch_gemm<64, false>(ta, tw, to, tr, tx, M, N, K, ep, s, cta2);
+      case 128: return launch_gemm<128, false>(ta, tw, to, tr, tx, M, N, K, ep, s, cta2);
+      case 192: return launch_gemm<192, false>(ta, tw, to, tr, tx, M, N, K, ep, s, cta2);
+      default: return launch_gemm<256, false>(ta, tw, to, tr, tx, M, N, K, ep, s, cta2);
     }
   }
   switch (bn) {
-    case 64: return launch_gemm<64, true>(ta, tw, to, tr, M, N, K, ep, s, cta2);
-    case 128: return launch_gemm<128, true>(ta, tw, to, tr, M, N, K, ep, s, cta2);
-    case 192: return launch_gemm<192, true>(ta, tw, to, tr, M, N, K, ep, s, cta2);
-    default: return launch_gemm<256, true>(ta, tw, to, tr, M, N, K, ep, s, cta2);
+    case 64: return launch_gemm<64, true>(ta, tw, to, tr, tx, M, N, K, ep, s, cta2);
+    case 128: return launch_gemm<128, true>(ta, tw, to, tr, tx, M, N, K, ep, s, cta2);
+    case 192: return launch_gemm<192, true>(ta, tw, to, tr, tx, M, N, K, ep, s, cta2);
+    default: return launch_gemm<256, true>(ta, tw, to, tr, tx, M, N, K, ep, s, cta2);
   }
 }
 
 extern "C" int cwm_debug_gemm_cta2(int enable) {
   g_gemm_cta2 = enable;
   return CWM_OK;
+}
+
+// number of partial-statistics planes a LayerNorm-producer GEMM with N output columns writes (2 per N tile)
+extern "C" int cwm_gemm_ln_parts(int N) {
+  const int bn = pick_bn(N);
+  return 2 * ((N + bn - 1) / bn);
 }

@@ -10,6 +10,7 @@ Reference citations are relative to /root/reference.
 """
 import ctypes
 import math
+import os
 from functools import partial
 
 import numpy as np
@@ -238,7 +239,10 @@ class _Packer:
         self.keep.append(t)
         return t.data_ptr()
 
-    def block_array(self, blocks):
+    def block_array(self, blocks, fold_ln=False):
+        """``fold_ln``: also pack the LayerNorm-folded qkv / fc1 weights that let the library run the block without
+        LayerNorm kernels (``cwm_block_weights.w_qkv_ln`` ...): W' = f16(W * gamma), s = row sums of W' (of the f16
+        values, so that the mean term cancels exactly what the tensor cores accumulate), c = W @ beta + bias."""
         arr = (_lib.BlockWeights * max(1, len(blocks)))()
         for i, blk in enumerate(blocks):
             w = arr[i]
@@ -263,6 +267,25 @@ class _Packer:
             w.ln2_g, w.ln2_b = self.f32(blk.norm2.weight), self.f32(blk.norm2.bias)
             w.w_fc1, w.b_fc1 = self.f16(blk.mlp.fc1.weight), self.f32(blk.mlp.fc1.bias)
             w.w_fc2, w.b_fc2 = self.f16(w2), self.f32(b2)
+            if fold_ln:
+                def fold(weight, bias, norm):
+                    wt = weight.detach().to(device=self.device, dtype=torch.float32)
+                    g = norm.weight.detach().to(device=self.device, dtype=torch.float32)
+                    b = norm.bias.detach().to(device=self.device, dtype=torch.float32)
+                    w16 = (wt * g[None, :]).to(torch.float16).contiguous()
+                    colsum = w16.float().sum(1).contiguous()
+                    c = wt @ b
+                    if bias is not None:
+                        c = c + bias.detach().to(device=self.device, dtype=torch.float32)
+                    c = c.contiguous()
+                    self.keep += [w16, colsum, c]
+                    return w16.data_ptr(), colsum.data_ptr(), c.data_ptr()
+                qkv_bias = None
+                if blk.attn.q_bias is not None:
+                    qkv_bias = torch.cat([blk.attn.q_bias.detach(), torch.zeros_like(blk.attn.v_bias),
+                                          blk.attn.v_bias.detach()])
+                w.w_qkv_ln, w.s_qkv, w.c_qkv = fold(blk.attn.qkv.weight, qkv_bias, blk.norm1)
+                w.w_fc1_ln, w.s_fc1, w.c_fc1 = fold(blk.mlp.fc1.weight, blk.mlp.fc1.bias, blk.norm2)
         self.keep.append(arr)
         return arr
 
@@ -317,13 +340,14 @@ class _Engine:
         s.w_patch = f16(pe.proj.weight.reshape(pe.proj.out_channels, -1))  # (c, kt, kh, kw) flattening
         s.b_patch = f32(pe.proj.bias)
         s.pos_enc = f32(enc.pos_embed[0])
-        enc_arr = block_array(enc.blocks)
+        fold = os.environ.get("CWM_FUSE_LN", "1") != "0"  # LayerNorm folded into the consumer GEMM epilogues
+        enc_arr = block_array(enc.blocks, fold_ln=fold)
         s.enc_blocks = ctypes.cast(enc_arr, ctypes.POINTER(_lib.BlockWeights))
         s.enc_norm_g, s.enc_norm_b = f32(enc.norm.weight), f32(enc.norm.bias)
         s.w_e2d = f16(m.encoder_to_decoder.weight)
         s.mask_token = f32(m.mask_token.reshape(-1))
         s.pos_dec = f32(m.pos_embed[0])
-        dec_arr = block_array(dec.blocks)
+        dec_arr = block_array(dec.blocks, fold_ln=fold)
         s.dec_blocks = ctypes.cast(dec_arr, ctypes.POINTER(_lib.BlockWeights))
         s.dec_norm_g, s.dec_norm_b = f32(dec.norm.weight), f32(dec.norm.bias)
         s.w_head, s.b_head = f16(dec.head.weight), f32(dec.head.bias)

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define CWM_B200_ABI_VERSION 3
+#define CWM_B200_ABI_VERSION 4
 
 typedef void* cwm_stream_t; /* cudaStream_t */
 
@@ -77,6 +77,10 @@ int cwm_patch_gather(const float* x, const int64_t xs[5], int B, int C, int T, i
 int cwm_layernorm_f16(const float* x, int M, int C, const float* gamma, const float* beta, float eps,
                       int grp_rows, int grp_stride, int grp_offset, uint16_t* out, cwm_stream_t stream);
 
+/* First LayerNorm of a stream when LayerNorm is fused into the consumer GEMM (see cwm_gemm_epilogue): x16 = f16(x)
+ * [M, C] and stats[m] = (sum, sum of squares) of row m (one partial plane, ln_parts = 1). */
+int cwm_rowstats_f16(const float* x, int M, int C, uint16_t* x16, float* stats, cwm_stream_t stream);
+
 /* ---- GEMM with fused epilogue (a2, a6, a7, a9, a11) ---------------------------------------------
  * Y[M,N] = epilogue(A[M,K] . W[N,K]^T), A and W f16 (K contiguous, like nn.Linear.weight), fp32
  * accumulation in tensor memory (tcgen05.mma kind::f16).  K % 16 == 0 and K >= 16; lda = K, ldw = K.  */
@@ -102,7 +106,25 @@ typedef struct cwm_gemm_epilogue {
   int32_t grp_out_stride;
   void* out;             /* f16 or fp32, leading dimension ldo */
   int32_t ldo;
+  /* ---- LayerNorm fusion (all optional, zero-initialise to switch off) -----------------------------------------
+   * `x + f(x)` followed by `LayerNorm` (cwm/models/VideoMAE/utils.py:146-153) without a LayerNorm kernel:
+   *  producer (CWM_EPI_RES_F32, no row remap, N % 32 == 0): additionally writes ln_x16 = f16(out) [M, ln_ldx16] and,
+   *    per row, partial (sum, sum of squares) of its columns: ln_stats_out[p * M + m], p < cwm_gemm_ln_parts(N);
+   *  consumer (CWM_EPI_F16 / CWM_EPI_GELU_F16) with A = ln_x16 and W = weight * gamma[None, :]:
+   *    out = act(rstd_m * (acc - mean_m * ln_colsum[n]) + bias[n]), mean / rstd over ln_width elements with eps ln_eps,
+   *    ln_colsum[n] = sum_k W[n, k] (of the f16 values), bias[n] = (weight @ beta)[n] + linear bias[n]. */
+  uint16_t* ln_x16;
+  int32_t ln_ldx16;
+  float* ln_stats_out;       /* [cwm_gemm_ln_parts(N), M, 2] fp32 */
+  const float* ln_stats_in;  /* [ln_parts, M, 2] fp32 */
+  int32_t ln_parts;
+  const float* ln_colsum;    /* [N] */
+  int32_t ln_width;
+  float ln_eps;
 } cwm_gemm_epilogue;
+
+/* Number of partial-statistics planes a LayerNorm-producer GEMM with N output columns writes. */
+int cwm_gemm_ln_parts(int N);
 
 int cwm_gemm_f16(const uint16_t* A, const uint16_t* W, int M, int N, int K, const cwm_gemm_epilogue* epi,
                  cwm_stream_t stream);
@@ -146,6 +168,17 @@ typedef struct cwm_block_weights {
   const float* b_fc1;
   const uint16_t* w_fc2;            /* mlp.fc2.weight    f16 [C, hidden] */
   const float* b_fc2;
+  /* Optional LayerNorm-folded copies (all six set, or all NULL = separate LayerNorm kernels).  With them the block
+   * runs without LayerNorm kernels: the residual GEMMs emit an f16 copy + row statistics, the qkv / fc1 GEMMs apply
+   * the normalisation in their epilogue (see cwm_gemm_epilogue):
+   *   w_qkv_ln = f16(qkv.weight * norm1.weight[None, :]);  s_qkv[n] = sum_k w_qkv_ln[n, k];
+   *   c_qkv    = qkv.weight @ norm1.bias + cat(q_bias, 0, v_bias);      likewise fc1 with norm2. */
+  const uint16_t* w_qkv_ln;
+  const float* s_qkv;
+  const float* c_qkv;
+  const uint16_t* w_fc1_ln;
+  const float* s_fc1;
+  const float* c_fc1;
 } cwm_block_weights;
 
 typedef struct cwm_vmae_model {

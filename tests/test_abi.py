@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_error_string():
     lib = _lib.load()
-    assert lib.cwm_abi_version() == 3
+    assert lib.cwm_abi_version() == 4
     assert isinstance(lib.cwm_last_error(), bytes)
 
 
@@ -52,9 +52,9 @@ def test_argument_validation_without_gpu():
 
 def test_struct_layout_matches_header():
     # sizes follow from the C declaration order: 16 int32 + 3 float + 14 pointers (8-byte aligned)
-    assert ctypes.sizeof(_lib.BlockWeights) == 12 * 8
+    assert ctypes.sizeof(_lib.BlockWeights) == 18 * 8
     assert ctypes.sizeof(_lib.VmaeModel) == 16 * 4 + 3 * 4 + 4 + 14 * 8
-    assert ctypes.sizeof(_lib.GemmEpilogue) == 80
+    assert ctypes.sizeof(_lib.GemmEpilogue) == 80 + 56
 
 
 def test_argument_validation_of_the_counterfactual_and_flow_entry_points():
