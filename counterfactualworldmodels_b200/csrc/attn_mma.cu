@@ -71,12 +71,12 @@ __device__ __forceinline__ void load_tile(__half* dst, const __half* src, long l
   }
 }
 
-template <int HD, int kWarps>
+template <int HD, int kWarps, int BN>  // BN = key tile (64, or 32 when there are at most 32 keys: half the MMA work)
 __global__ void __launch_bounds__(kWarps * 32)
 attn_mma_kernel(AttnMmaParams p) {
   constexpr int kThreads = kWarps * 32;
   constexpr int BM = kWarps * 16;
-  constexpr int BN = 64;
+  constexpr int NT = BN / 8;   // 8-key score tiles per warp row slab
   constexpr int kStride = HD + 8;
   extern __shared__ __align__(16) uint8_t smem_raw_mma[];
   __half* Qs = reinterpret_cast<__half*>(smem_raw_mma);
@@ -114,15 +114,15 @@ attn_mma_kernel(AttnMmaParams p) {
     __syncthreads();
 
     // ---- S = Q K^T (16 x 64 per warp) ----
-    float s[8][4];
+    float s[NT][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+    for (int i = 0; i < NT; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
 #pragma unroll
     for (int kk = 0; kk < HD / 16; ++kk) {
       uint32_t a0, a1, a2, a3;
       ldsm_x4(q_addr + kk * 32, a0, a1, a2, a3);
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {  // two 8-key tiles per ldmatrix.x4
+      for (int nt = 0; nt < NT / 2; ++nt) {  // two 8-key tiles per ldmatrix.x4
         uint32_t b0, b1, b2, b3;
         ldsm_x4(k_addr + (nt * 16 * kStride + kk * 16) * 2, b0, b1, b2, b3);
         mma16816(s[2 * nt], a0, a1, a2, a3, b0, b1);
@@ -133,7 +133,7 @@ attn_mma_kernel(AttnMmaParams p) {
     const int valid = kv_end - kv0;  // >= 1
     if (valid < BN) {
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
+      for (int nt = 0; nt < NT; ++nt) {
         const int c = nt * 8 + (lane & 3) * 2;
         if (c >= valid) s[nt][0] = s[nt][2] = -INFINITY;
         if (c + 1 >= valid) s[nt][1] = s[nt][3] = -INFINITY;
@@ -141,7 +141,7 @@ attn_mma_kernel(AttnMmaParams p) {
     }
     float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+    for (int nt = 0; nt < NT; ++nt) {
       mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
       mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
     }
@@ -160,7 +160,7 @@ attn_mma_kernel(AttnMmaParams p) {
     }
     float sum[2] = {0.f, 0.f};
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+    for (int nt = 0; nt < NT; ++nt) {
       s[nt][0] = ex2f(fmaf(s[nt][0], kLog2eMma, neg_m[0]));
       s[nt][1] = ex2f(fmaf(s[nt][1], kLog2eMma, neg_m[0]));
       s[nt][2] = ex2f(fmaf(s[nt][2], kLog2eMma, neg_m[1]));
@@ -179,7 +179,7 @@ attn_mma_kernel(AttnMmaParams p) {
     }
     // ---- O += P V ----
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {  // 16 keys per step
+    for (int kk = 0; kk < BN / 16; ++kk) {  // 16 keys per step
       const uint32_t a0 = pack_half2(s[2 * kk][0], s[2 * kk][1]);
       const uint32_t a1 = pack_half2(s[2 * kk][2], s[2 * kk][3]);
       const uint32_t a2 = pack_half2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
@@ -250,29 +250,39 @@ __global__ void attn_combine_kernel(const float* __restrict__ part_o, const floa
   }
 }
 
+static int g_attn_mma_wide = 1;
+static int g_attn_mma_split = 512;  // keys per CTA when few queries face a long key axis (multiple of 64)
+
 static void pick_splits(int Nq, int Nk, int* n_splits, int* kv_per_split) {
   // few query rows against a long key axis (cross-attention "src" direction): split the keys for parallelism
   if (Nq <= 64 && Nk >= 1024) {
-    *kv_per_split = 512;
-    *n_splits = (Nk + 511) / 512;
+    *kv_per_split = g_attn_mma_split;
+    *n_splits = (Nk + g_attn_mma_split - 1) / g_attn_mma_split;
   } else {
     *kv_per_split = ((Nk + 63) / 64) * 64;
     *n_splits = 1;
   }
 }
 
-template <int HD, int kWarps>
-static int launch_attn_mma(const AttnMmaParams& p, int B, cudaStream_t s) {
-  constexpr int smem = (kWarps * 16 + 128) * (HD + 8) * 2;
+template <int HD, int kWarps, int BN>
+static int launch_attn_mma_bn(const AttnMmaParams& p, int B, cudaStream_t s) {
+  constexpr int smem = (kWarps * 16 + 2 * BN) * (HD + 8) * 2;
   static bool attr_set = false;
   if (!attr_set) {
-    CWM_CUDA_CHECK(cudaFuncSetAttribute(attn_mma_kernel<HD, kWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CWM_CUDA_CHECK(cudaFuncSetAttribute(attn_mma_kernel<HD, kWarps, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
   dim3 grid((p.Nq + kWarps * 16 - 1) / (kWarps * 16), p.H, B * p.n_splits);
-  attn_mma_kernel<HD, kWarps><<<grid, kWarps * 32, smem, s>>>(p);
+  attn_mma_kernel<HD, kWarps, BN><<<grid, kWarps * 32, smem, s>>>(p);
   CWM_LAUNCH_CHECK();
   return CWM_OK;
+}
+
+template <int HD, int kWarps>
+static int launch_attn_mma(const AttnMmaParams& p, int B, cudaStream_t s) {
+  // at most 32 keys in total (the 25 IMU tokens of the encoder-side cross attention): 32-row key tile
+  if (p.Nk <= 32 && p.n_splits == 1) return launch_attn_mma_bn<HD, kWarps, 32>(p, B, s);
+  return launch_attn_mma_bn<HD, kWarps, 64>(p, B, s);
 }
 
 }  // namespace cwm
@@ -323,10 +333,14 @@ extern "C" int cwm_attention_generic_f16(const uint16_t* q, const uint16_t* k, c
   ProfileScope prof(s, "attention_small_mma", 4.0 * B * H * static_cast<double>(Nq) * Nk * head_dim,
                     (static_cast<double>(B) * (Nq * 2.0 + Nk * 2.0) * H * head_dim) * 2.0);
   const bool narrow = Nq <= 32;
+  // many query rows against a handful of keys (cross-attention "trg" direction): 8 warps share one K/V tile
+  // (head dims above 128 need > 160 registers per thread: one 8-warp CTA per SM would be slower -- measured)
+  const bool wide = Nq >= 1024 && Nk <= 64 && head_dim <= 128 && g_attn_mma_wide;
   int rc;
 #define CWM_MMA_CASE(HDV)                                                            \
   case HDV:                                                                          \
-    rc = narrow ? launch_attn_mma<HDV, 2>(p, B, s) : launch_attn_mma<HDV, 4>(p, B, s); \
+    rc = narrow ? launch_attn_mma<HDV, 2>(p, B, s)                                   \
+                : (wide ? launch_attn_mma<HDV, 8>(p, B, s) : launch_attn_mma<HDV, 4>(p, B, s)); \
     break;
   switch (head_dim) {
     CWM_MMA_CASE(32)
@@ -346,3 +360,6 @@ extern "C" int cwm_attention_generic_f16(const uint16_t* q, const uint16_t* k, c
   }
   return CWM_OK;
 }
+
+extern "C" void cwm_debug_attn_mma_wide(int on) { g_attn_mma_wide = on; }
+extern "C" void cwm_debug_attn_mma_split(int keys) { g_attn_mma_split = keys >= 64 ? (keys / 64) * 64 : 64; }

@@ -46,6 +46,11 @@ CASES = {
     "unpatchify_base": ("unpatch", 64, 8, 788),
     "unpatchify_4x4": ("unpatch", 32, 4, 3140),
     "cf_build_256": ("cfbuild", 256, 8),
+    # the small attentions of the IMU-conditioned model (config 5, batch 32): cross attention in both directions
+    "xattn_enc_trg": ("xattn", 32, 3140, 25, 4, 192),
+    "xattn_enc_src": ("xattn", 32, 25, 3140, 4, 192),
+    "xattn_dec_trg": ("xattn", 32, 6336, 50, 4, 96),
+    "xattn_dec_src": ("xattn", 32, 50, 6336, 4, 96),
 }
 
 
@@ -135,6 +140,14 @@ def run_case(name, iters=5):
         def call(i):
             ops.attention_f16(qkv[i % nbuf], B, N, H)
         flops, byts = 4.0 * B * H * N * N * 64, B * N * H * 64 * 2 * 4
+    elif kind == "xattn":
+        _, B, Nq, Nk, H, d = CASES[name]
+        q = (torch.randn(B * Nq, H * d, device=DEV) * d ** -0.25).half()
+        k = (torch.randn(B * Nk, H * d, device=DEV) * d ** -0.25).half()
+        v = torch.randn(B * Nk, H * d, device=DEV).half()
+        def call(i):
+            ops.attention_generic_f16(q, k, v, B, Nq, Nk, H, d)
+        flops, byts = 4.0 * B * H * Nq * Nk * d, (2.0 * B * Nq + 2.0 * B * Nk) * H * d * 2
     elif kind in ("gather", "unpatch", "fillmask", "cfbuild"):
         call, flops, byts = pixel_case(name)
     else:
@@ -172,6 +185,10 @@ if __name__ == "__main__":
     if os.environ.get("CWM_ATTN_MAP"):
         _lib.load().cwm_debug_attention_persist_map(int(os.environ["CWM_ATTN_MAP"]))
         print("attention persist map =", os.environ["CWM_ATTN_MAP"])
+    if os.environ.get("CWM_ATTN_MMA_WIDE"):
+        _lib.load().cwm_debug_attn_mma_wide(int(os.environ["CWM_ATTN_MMA_WIDE"]))
+    if os.environ.get("CWM_ATTN_MMA_SPLIT"):
+        _lib.load().cwm_debug_attn_mma_split(int(os.environ["CWM_ATTN_MMA_SPLIT"]))
     names = sys.argv[1:] or list(CASES)
     for n in names:
         run_case(n)
