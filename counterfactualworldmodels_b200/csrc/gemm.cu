@@ -652,45 +652,72 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       }
       if (elect_one()) bulk_wait_all();
     } else {
-      // ---------------- generic fp32 epilogue with row remap / gathered residual (two small GEMMs per forward):
-      //                  padded smem transpose, coalesced direct global accesses ----------------
+      // ---------------- fp32 epilogue with row remap / gathered residual (patch embed + pos[perm], and
+      //                  encoder_to_decoder written into the decoder sequence): one thread owns one output row; its
+      //                  destination / residual rows are resolved ONCE per tile (one division, one coalesced gather
+      //                  load), then every 32-column chunk is 8 x 16-byte residual loads + 8 x 16-byte stores ----
       constexpr int kChunks = BN / 32;
-      const uint32_t stg = buf0;  // 32 x 33 words = 4224 bytes <= 2 * kChunkBytes
+      const bool has_res = (ep.mode == CWM_EPI_RES_F32);
+      float* outp = reinterpret_cast<float*>(ep.out);
+      const bool vec_ok = (ep.ldo % 4 == 0) && (!has_res || ep.ldr % 4 == 0) &&
+                          (reinterpret_cast<uintptr_t>(ep.out) % 16 == 0) &&
+                          (!has_res || reinterpret_cast<uintptr_t>(ep.res) % 16 == 0);
       for (int tile = tile_first; tile < num_tiles; tile += tile_stride) {
         const int m_blk = tile / tiles_n;
         const int n_blk = tile - m_blk * tiles_n;
+        const int row0 = m_blk * TM + cta_rank * BM + quad * 32;
+        const int m = row0 + lane;
+        const bool valid = m < M;
+        long long orow = 0, rrow = 0;
+        if (valid) {
+          const int g = m / ep.grp_rows;
+          const int j = m - g * ep.grp_rows;
+          orow = static_cast<long long>(g) * ep.grp_out_stride + j;
+          rrow = orow;
+          if (has_res && ep.res_gather != nullptr) rrow = __ldg(ep.res_gather + static_cast<long long>(g) * ep.gather_stride + j);
+        }
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
         const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
-        const int row0 = m_blk * TM + cta_rank * BM + quad * 32;
         for (int c = half; c < kChunks; c += 2) {
           const int n0 = n_blk * BN + c * 32;
+          float b_lo = 0.f;
+          if (ep.bias != nullptr && n0 + lane < N) b_lo = __ldg(ep.bias + n0 + lane);
           uint32_t acc[32];
           tmem_ld_x32(tmem_acc + c * 32, acc);
+          __syncwarp();  // previous chunk's broadcast reads of bias_s are done
+          sts32(bias_s + lane * 4, __float_as_uint(b_lo));
           tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) sts32(stg + (lane * 33 + j) * 4, acc[j]);
           __syncwarp();
-          const int n = n0 + lane;
-          if (n < N) {
-            const float bias = ep.bias != nullptr ? __ldg(ep.bias + n) : 0.f;
-            float* outp = reinterpret_cast<float*>(ep.out);
-            for (int r = 0; r < 32; ++r) {
-              const int m = row0 + r;
-              if (m >= M) break;
-              const int g = m / ep.grp_rows;
-              const int j = m - g * ep.grp_rows;
-              const long long orow = static_cast<long long>(g) * ep.grp_out_stride + j;
-              float v = __uint_as_float(lds32(stg + (r * 33 + lane) * 4)) + bias;
-              if (ep.mode == CWM_EPI_RES_F32) {
-                long long rrow = orow;
-                if (ep.res_gather != nullptr) rrow = ep.res_gather[static_cast<long long>(g) * ep.gather_stride + j];
-                v += ep.res[rrow * ep.ldr + n];
+          if (!valid) continue;
+          if (vec_ok && n0 + 32 <= N) {
+            const float4* rp = has_res ? reinterpret_cast<const float4*>(ep.res + rrow * ep.ldr + n0) : nullptr;
+            float4* op = reinterpret_cast<float4*>(outp + orow * ep.ldo + n0);
+            float4 rr[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) rr[u] = has_res ? __ldg(rp + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              uint32_t bb[4];
+              lds128(bias_s + u * 16, bb[0], bb[1], bb[2], bb[3]);
+              float4 v;
+              v.x = __uint_as_float(acc[4 * u]) + __uint_as_float(bb[0]) + rr[u].x;
+              v.y = __uint_as_float(acc[4 * u + 1]) + __uint_as_float(bb[1]) + rr[u].y;
+              v.z = __uint_as_float(acc[4 * u + 2]) + __uint_as_float(bb[2]) + rr[u].z;
+              v.w = __uint_as_float(acc[4 * u + 3]) + __uint_as_float(bb[3]) + rr[u].w;
+              op[u] = v;
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+              const int n = n0 + q;
+              if (n < N) {
+                float v = __uint_as_float(acc[q]) + __uint_as_float(lds32(bias_s + q * 4));
+                if (has_res) v += __ldg(ep.res + rrow * ep.ldr + n);
+                outp[orow * ep.ldo + n] = v;
               }
-              outp[orow * ep.ldo + n] = v;
             }
           }
-          __syncwarp();
         }
         tc_fence_before();
         if (lane == 0) { if constexpr (kCta2) mbar_arrive_leader(&tempty_bar[as]); else mbar_arrive(&tempty_bar[as]); }

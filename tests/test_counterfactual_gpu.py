@@ -220,3 +220,22 @@ def test_error_behaviour():
     sh = perturbation.ShiftPatchesAndMask(patch_size=(1, 4, 4))
     with pytest.raises(AssertionError):  # pixel shifts must be multiples of the patch size (perturbation.py:251-252)
         sh(x, mask=masks[..., 0].clone(), shift=(3, 0))
+
+
+def test_sharded_sweep_single_process_equals_generator():
+    """`dist.sharded_counterfactual_videos` without a process group is the plain fused sweep (the multi-rank path is
+    checked by tools/dist_check.py under torchrun: bit-identical on 4 and 8 GPUs, profiles/r1_dist_check_*.log)."""
+    from counterfactualworldmodels_b200 import dist as cdist
+    d = load_cf("cf_tiny_8x8_s8_clump2")
+    m = _tiny_predictor(d["cfg"])
+    G = segmentation.FlowGenerator(predictor=m, imagenet_normalize_inputs=True, temporal_dim=2)
+    x = d["x"].to(DEV)
+    passive, active = torch.from_numpy(d["passive"]).to(DEV), torch.from_numpy(d["active"]).to(DEV)
+    shifts = d["shifts"].tolist()
+    torch.manual_seed(11)
+    a = cdist.sharded_counterfactual_videos(G, x, active, passive, shifts=shifts, sample_batch_size=3)
+    torch.manual_seed(11)
+    b = G.predict_counterfactual_videos(x, active, passive_patches=passive, shifts=shifts, sample_batch_size=3)
+    assert torch.equal(a, b)
+    local = cdist.sharded_counterfactual_videos(G, x[0, 0], active, passive, shifts=shifts, gather=False)
+    assert local.shape == a.shape
