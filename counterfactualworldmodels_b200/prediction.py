@@ -97,8 +97,9 @@ class PredictorBasedGenerator(nn.Module):
     """The slice of cwm/models/prediction.py:16-540 that brackets the predictor call."""
 
     def __init__(self, predictor=None, imagenet_normalize_inputs=False, temporal_dim=2, seed=0,
-                 mask_generator=None, max_shift_fraction=0.15, **kwargs):
+                 mask_generator=None, max_shift_fraction=0.15, error_func=nn.MSELoss(reduction='none'), **kwargs):
         super().__init__()
+        self.error_func = error_func
         if predictor is None:
             raise ValueError("There is no predictor set for this generator and no model to load to")
         self.predictor = predictor
@@ -299,6 +300,92 @@ class PredictorBasedGenerator(nn.Module):
 
     def forward(self, x, mask=None, frame=None, *args, **kwargs):
         return self.predict(x, mask, frame, *args, **kwargs)
+
+    # ---- helpers the GUI entry points call (cwm/interface.py: get_masked_pred_patches, predict_error,
+    #      generate_mask_from_patch_idx_list); mask bookkeeping and an elementwise error map around `predict` ----
+    @property
+    def inp_mask_shape(self):
+        return (self.x.shape[0], int(np.prod(self.mask_shape)))
+
+    def set_new_mask(self, x=None):
+        if x is None:
+            x = self.x
+        self.mask = self.generate_mask(x)
+
+    def get_mask_image(self, mask, upsample=False, invert=False, shape=None):
+        """prediction.py:357-365."""
+        if shape is None:
+            shape = self.mask_shape
+        mask = mask.view(-1, *shape)
+        if upsample:
+            from .masking import upsample_masks
+            mask = upsample_masks(mask, self.inp_shape[-2:])
+        if invert:
+            mask = 1 - mask
+        return mask
+
+    @staticmethod
+    def make_visible_from_patch_idx_list(mask, patch_idx_list, stride=1, b=0, t=-1):
+        """prediction.py:617-638: clears mask[b, t, h // stride, w // stride] for every listed (.., h, w)."""
+        if len(patch_idx_list) == 0:
+            return mask
+        if not isinstance(patch_idx_list, torch.Tensor):
+            patch_idx_list = torch.tensor(np.array(patch_idx_list), dtype=torch.long).to(mask.device)
+        inds = torch.unbind(patch_idx_list, -1)
+        inds_h = (inds[-2] // stride) % mask.size(-2)
+        inds_w = (inds[-1] // stride) % mask.size(-1)
+        if len(inds) == 2:
+            inds_b = b * torch.ones_like(inds_h)
+            inds_t = t * torch.ones_like(inds_b)
+        elif len(inds) == 3:
+            inds_b = b * torch.ones_like(inds_h)
+            inds_t = inds[0]
+        else:
+            assert len(inds) == 4, len(inds)
+            inds_b, inds_t = inds[0], inds[1]
+        mask[inds_b, inds_t, inds_h, inds_w] = 0
+        return mask
+
+    def generate_mask_from_patch_idx_list(self, patch_idx_list, stride=None, b=0, frame=-1):
+        """prediction.py:640-648.  NB (reference behaviour, kept): `get_zeros_mask` returns a batch-EXPANDED view, so
+        the indexed write below lands in every batch row whatever ``b`` says -- all rows share the listed patches."""
+        assert self.x is not None
+        m = self.get_mask_image(self.get_zeros_mask(frame=frame))
+        if stride is None:
+            stride = self.inp_shape[-1] // m.size(-1)
+        m = self.make_visible_from_patch_idx_list(m, patch_idx_list, stride=stride, b=b, t=frame)
+        return m.view(m.size(0), -1)
+
+    def get_masked_pred_patches(self, preds, mask, invert=False, fill_value=None):
+        """prediction.py:261-282: the video with the masked patches blanked (or filled) -- display helper."""
+        from .masking import upsample_masks
+        shape = preds.shape
+        pt, ph, pw = self.patch_size
+        mask_shape = (shape[1] // pt, shape[-2] // ph, shape[-1] // pw)
+        mask_vis = upsample_masks(self.get_mask_image(mask, shape=mask_shape), shape[-2:]).to(preds)
+        if invert:
+            mask_vis = 1.0 - mask_vis
+        out = preds * mask_vis.unsqueeze(2)
+        if isinstance(fill_value, torch.Tensor):
+            assert list(fill_value.shape) == list(out.shape)
+            out = out + (1 - mask_vis.unsqueeze(2)) * fill_value
+        elif fill_value is not None:
+            fill_value = torch.tensor(fill_value, dtype=torch.float32).to(out.device).to(out).view(1, 1, -1, 1, 1)
+            out = out + (1 - mask_vis.unsqueeze(2)) * fill_value
+        return out
+
+    def predict_error(self, x=None, mask=None, target=None, frame=None, dim=-3):
+        """prediction.py:331-343: `error_func(predict(x, mask), target).sum(dim)` (factual prediction error map)."""
+        if x is None:
+            x = self.x
+        if mask is None:
+            mask = self.generate_mask(x)
+        x_pred = self.predict(x, mask, frame=frame)
+        if target is None:
+            target = x
+        if frame is not None:
+            target = target[:, frame].unsqueeze(1)
+        return self.error_func(x_pred, target).sum(dim, True)
 
     # ---- counterfactual prompts (SURVEY 8(f) rank 1) ----
     def set_input(self, x, mask=None, make_mask=False, timestamps=None):

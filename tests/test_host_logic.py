@@ -139,3 +139,35 @@ def test_shard_and_gather_gloo_world2(n_samples):
         assert p.exitcode == 0
     results = dict(q.get(timeout=10) for _ in range(2))
     assert results == {0: True, 1: True}
+
+
+def test_gui_mask_helpers_match_reference_semantics():
+    """`generate_mask_from_patch_idx_list` / `get_mask_image` / `get_masked_pred_patches` (the helpers cwm/interface.py
+    calls): pure mask bookkeeping, checked against hand-computed values and, when mounted, the reference itself."""
+    m = vmae.PretrainVisionTransformer(**synthetic.model_kwargs("tiny_8x8"))
+    G = prediction.PredictorBasedGenerator(predictor=m, imagenet_normalize_inputs=True, temporal_dim=2)
+    x = synthetic.make_video(2, (64, 64), seed=0)
+    G.set_input(x)
+    mask = G.generate_mask_from_patch_idx_list([[17, 40], [63, 0]], b=1)   # pixel coordinates, stride 64 // 8 = 8
+    img = G.get_mask_image(mask)
+    assert img.shape == (2, 2, 8, 8) and not img[:, 0].any()
+    vis = (~img[1, 1]).nonzero().tolist()
+    # the reference writes through the batch-expanded zeros mask: every row gets the patches, whatever `b` is
+    assert vis == [[2, 5], [7, 0]] and (~img[0, 1]).nonzero().tolist() == vis
+    assert G.inp_mask_shape == (2, 128)
+    out = G.get_masked_pred_patches(torch.ones(2, 2, 3, 64, 64), mask, fill_value=[0.5, 0, 0])
+    assert out.shape == (2, 2, 3, 64, 64)
+    assert float(out[1, 1, 0, 16:24, 40:48].min()) == 0.5 and float(out[1, 1, 1, 16:24, 40:48].max()) == 0.0
+    assert float(out[1, 1, 0, 0, 0]) == 1.0 and float(out[0, 0].max()) == 0.5 and float(out[0, 0, 1].max()) == 0.0
+    if os.path.isdir("/root/reference"):
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import ref_loader
+        ref_vmae, ref_pred = ref_loader.import_reference()
+        R = ref_pred.PredictorBasedGenerator(
+            predictor=ref_vmae.PretrainVisionTransformer(**synthetic.model_kwargs("tiny_8x8")),
+            imagenet_normalize_inputs=True, temporal_dim=2)
+        R.set_input(x)
+        rmask = R.generate_mask_from_patch_idx_list([[17, 40], [63, 0]], b=1)
+        assert torch.equal(rmask, mask)
+        want = R.get_masked_pred_patches(torch.ones(2, 2, 3, 64, 64), rmask, fill_value=[0.5, 0, 0])
+        assert torch.equal(want, out)

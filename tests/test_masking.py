@@ -74,3 +74,25 @@ def test_properties():
     for _ in range(5):
         vis = ~g(e)[0, 64:].view(8, 8)
         assert int(vis.sum()) in (1, 2) and int(vis[2:4, 4:6].sum()) == int(vis.sum())
+
+
+def test_batched_patch_sampling_properties():
+    """The opt-in batched sampler (one multinomial call for the whole sweep): same shape / counts / support as the
+    sequential reference sampler."""
+    from counterfactualworldmodels_b200 import segmentation, synthetic, vmae
+    kw = synthetic.model_kwargs("tiny_4x4")
+    kw.update(encoder_depth=1, decoder_depth=1)
+    G = segmentation.FlowGenerator(predictor=vmae.PretrainVisionTransformer(**kw), seed=3)
+    x = synthetic.make_video(1, (32, 32), seed=1)
+    G.set_input(x)
+    e = torch.zeros(1, 1, 32, 32)
+    e[..., 8:16, 20:28] = 1.0                       # patches rows 2-3, cols 5-6 of the 8 x 8 grid
+    m = G.sample_patches_from_energy(e, num_samples=64, num_visible=2, batched=True)
+    ref = G.sample_patches_from_energy(e, num_samples=4, num_visible=2)
+    assert m.shape == (1, 128, 64) and m.dtype == torch.bool and ref.shape == (1, 128, 4)
+    assert not bool(m[:, :64].any())                # frame 0 fully visible
+    vis = ~m[0, 64:].view(8, 8, 64)
+    assert int(vis[2:4, 5:7].sum()) == int(vis.sum())          # every draw lands where the energy is
+    counts = vis.sum((0, 1))
+    assert int(counts.min()) >= 1 and int(counts.max()) <= 2    # 2 draws with replacement
+    assert len({tuple(vis[..., s].flatten().tolist()) for s in range(64)}) > 1   # samples differ
