@@ -19,6 +19,8 @@ import ctypes
 from functools import partial
 
 import numpy as np
+import os
+
 import torch
 import torch.nn as nn
 
@@ -54,8 +56,9 @@ class _StreamEngine:
         self.K = pe.proj.weight[0].numel()
         self.w_patch = pk.f16(pe.proj.weight.reshape(pe.proj.out_channels, -1))  # (c, kt, kh, kw) flattening
         self.b_patch = pk.f32(pe.proj.bias)
-        self.enc_blocks = pk.block_array(enc.blocks)
-        self.dec_blocks = pk.block_array(dec.blocks)
+        fold = os.environ.get("CWM_FUSE_LN", "1") != "0"  # second LayerNorm of every block folded into the fc1 epilogue
+        self.enc_blocks = pk.block_array(enc.blocks, fold_ln=fold)
+        self.dec_blocks = pk.block_array(dec.blocks, fold_ln=fold)
 
         def dims(blocks, C):
             if len(blocks) == 0:

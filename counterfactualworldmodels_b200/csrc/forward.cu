@@ -139,13 +139,17 @@ static int run_block(const cwm_block_weights& w, float* x, int Bn, int N, int C,
 }
 
 struct BlockPlan {
-  size_t off_a16, off_qkv, off_h16, total;
+  size_t off_a16, off_qkv, off_h16, off_attn, off_stats, total;
 };
 static void make_block_plan(long long M, int C, int A, int hidden, BlockPlan* p) {
   size_t off = 0;
   p->off_a16 = off; off = align_up(off + M * (C > A ? C : A) * 2, 1024);
   p->off_qkv = off; off = align_up(off + M * 3 * A * 2, 1024);
   p->off_h16 = off; off = align_up(off + M * hidden * 2, 1024);
+  // separate attention output + statistics planes: lets a block with LayerNorm-folded weights run without its second
+  // LayerNorm kernel (the first one becomes the row-statistics pass: a single block call cannot know who wrote x last)
+  p->off_attn = off; off = align_up(off + M * A * 2, 1024);
+  p->off_stats = off; off = align_up(off + M * kMaxLnParts * 8, 1024);
   p->total = off + 1024;
 }
 
@@ -286,8 +290,11 @@ extern "C" int cwm_block_forward(const cwm_block_weights* w, float* x, int B, in
   if (B == 0) return CWM_OK;
   uint8_t* ws = align_ws(workspace);
   uint16_t* a16 = reinterpret_cast<uint16_t*>(ws + p.off_a16);
+  bool x16_valid = false;
   return run_block(*w, x, B, N, C, heads, head_dim, hidden, ln_eps, qk_scale, a16,
-                   reinterpret_cast<uint16_t*>(ws + p.off_qkv), a16, reinterpret_cast<uint16_t*>(ws + p.off_h16), st);
+                   reinterpret_cast<uint16_t*>(ws + p.off_qkv), reinterpret_cast<uint16_t*>(ws + p.off_attn),
+                   reinterpret_cast<uint16_t*>(ws + p.off_h16), st, reinterpret_cast<float*>(ws + p.off_stats), &x16_valid,
+                   false);
 }
 
 extern "C" size_t cwm_cross_block_workspace_bytes(int B, int N, int M, int C, int Cs, int heads, int head_dim,
