@@ -317,6 +317,9 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     _lib.check(_lib.load().cwm_device_check())
+    if os.environ.get("CWM_ATTN_POLY"):  # tuning hook: eighths of the softmax exponentials evaluated on the FMA pipe
+        _lib.load().cwm_debug_attention_poly.argtypes = [ctypes.c_int]
+        _lib.load().cwm_debug_attention_poly(int(os.environ["CWM_ATTN_POLY"]))
     peaks = measured_peaks()
 
     def barrier():
