@@ -378,7 +378,8 @@ def main():
 
         for i in range(warmup):
             step(i, xs_dev[i % n_rot], ms_dev[i % n_rot])
-        launches_per_step = model.last_forward_launches + 1  # + unpatchify_scatter
+        # + unpatchify_scatter + the compaction `predict` runs to read the per-row visible counts (plain VMAE only)
+        launches_per_step = model.last_forward_launches + (2 if cfg_name != "imu400_base_4x4" else 1)
         barrier()
         sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
         if sampler:
