@@ -374,3 +374,56 @@ def test_gemm_cta_pair_equals_single_cta():
                 assert torch.equal(run(1), ref), (M, N, K, mode, rep)
     finally:
         lib.cwm_debug_gemm_cta2(1)
+
+
+@pytest.mark.parametrize("M,C,N2", [(1000, 768, 2304), (777, 384, 1536), (300, 1024, 4096)])
+def test_layernorm_folded_into_gemm_epilogues(M, C, N2):
+    """The LayerNorm-free block path at the kernel level: a residual GEMM (producer) emits f16 rows + partial row
+    statistics, the next GEMM (consumer, weights folded with gamma) normalises in its epilogue.  Checked against
+    LayerNorm -> Linear in fp32; and the row-statistics kernel (first block of a stream) against the producer's planes."""
+    import ctypes
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M + C)
+    K1 = 256
+    a = torch.randn(M, K1, generator=g).to(torch.float16).to(DEV)
+    w1 = (torch.randn(C, K1, generator=g) / K1 ** 0.5).to(torch.float16).to(DEV)
+    b1 = torch.randn(C, generator=g).to(DEV)
+    x0 = (torch.randn(M, C, generator=g) * 2 + 0.7).to(DEV)          # residual with a non-zero mean
+    gamma = (1 + 0.2 * torch.randn(C, generator=g)).to(DEV)
+    beta = (0.2 * torch.randn(C, generator=g)).to(DEV)
+    w2 = (torch.randn(N2, C, generator=g) / C ** 0.5).to(DEV)
+    b2 = torch.randn(N2, generator=g).to(DEV)
+    eps = 1e-6
+    # ---- producer: x = x0 + a w1^T + b1, plus f16 copy and statistics planes ----
+    parts = lib.cwm_gemm_ln_parts(C)
+    x = x0.clone()
+    x16 = torch.empty(M, C, dtype=torch.float16, device=DEV)
+    stats = torch.full((parts, M, 2), float("nan"), device=DEV)
+    e = _lib.GemmEpilogue()
+    e.mode, e.bias, e.res, e.ldr, e.out, e.ldo = _lib.EPI_RES_F32, b1.data_ptr(), x.data_ptr(), C, x.data_ptr(), C
+    e.ln_x16, e.ln_ldx16, e.ln_stats_out = x16.data_ptr(), C, stats.data_ptr()
+    stream = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.cwm_gemm_f16(a.data_ptr(), w1.data_ptr(), M, C, K1, ctypes.byref(e), stream))
+    want_x = x0 + a.float() @ w1.float().t() + b1
+    assert (x - want_x).abs().max().item() < 2e-3
+    assert torch.equal(x16, x.to(torch.float16))
+    s = stats.sum(0)
+    assert torch.allclose(s[:, 0], x.sum(1), rtol=1e-5, atol=1e-2) and torch.allclose(s[:, 1], (x * x).sum(1), rtol=1e-5, atol=1e-2)
+    # ---- row-statistics kernel: same information in one plane ----
+    x16b = torch.empty_like(x16)
+    st1 = torch.empty(M, 2, device=DEV)
+    _lib.check(lib.cwm_rowstats_f16(x.data_ptr(), M, C, x16b.data_ptr(), st1.data_ptr(), stream))
+    assert torch.equal(x16b, x16) and torch.allclose(st1, s, rtol=1e-5, atol=1e-2)
+    # ---- consumer: GELU(LN(x) w2^T + b2) with the LayerNorm folded into weights + epilogue ----
+    w2f = (w2 * gamma[None, :]).to(torch.float16).contiguous()
+    colsum = w2f.float().sum(1).contiguous()
+    c = (w2 @ beta + b2).contiguous()
+    for stats_in, n_parts in ((stats, parts), (st1, 1)):
+        out = torch.empty(M, N2, dtype=torch.float16, device=DEV)
+        e = _lib.GemmEpilogue()
+        e.mode, e.bias, e.out, e.ldo = _lib.EPI_GELU_F16, c.data_ptr(), out.data_ptr(), N2
+        e.ln_stats_in, e.ln_parts, e.ln_colsum, e.ln_width, e.ln_eps = stats_in.data_ptr(), n_parts, colsum.data_ptr(), C, eps
+        _lib.check(lib.cwm_gemm_f16(x16.data_ptr(), w2f.data_ptr(), M, N2, C, ctypes.byref(e), stream))
+        want = F.gelu(F.layer_norm(x, (C,), gamma, beta, eps) @ w2.t() + b2)
+        err = (out.float() - want).abs()
+        assert err.max().item() < 2e-2 and err.mean().item() < 1.5e-3, (err.max().item(), err.mean().item())
