@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = (
     "cwm_cf_build_videos", "cwm_cf_make_static", "cwm_patch_gather_cf", "cwm_unpatchify_scatter_cf",
     "cwm_flow_sample_stats", "cwm_flow_filter_mask", "cwm_flow_zero_filtered", "cwm_flow_magnitude_sum",
     "cwm_motion_map_finalize", "cwm_flow_stats_workspace_bytes", "cwm_flow_corrs_workspace_bytes", "cwm_flow_corrs",
-    "cwm_gemm_ln_parts", "cwm_rowstats_f16",
+    "cwm_gemm_ln_parts", "cwm_rowstats_f16", "cwm_raft_corr_pyramid", "cwm_raft_corr_lookup", "cwm_raft_upsample_flow",
 )
 
 
@@ -146,6 +146,11 @@ def _declare(lib):
     lib.cwm_flow_magnitude_sum.argtypes = [c_void_p, i64x5, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                                            c_float, c_int, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.cwm_motion_map_finalize.argtypes = [c_void_p, c_int, c_int, c_int, c_float, c_int, c_float, c_void_p, c_void_p]
+    lib.cwm_raft_corr_pyramid.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, POINTER(c_void_p),
+                                          c_void_p]
+    lib.cwm_raft_corr_lookup.argtypes = [POINTER(c_void_p), c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
+                                         c_void_p]
+    lib.cwm_raft_upsample_flow.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]
     lib.cwm_profile_begin.restype = c_int
     lib.cwm_profile_end.argtypes = [POINTER(ProfileEntry), c_int, POINTER(c_int)]
     for name in EXPORTED_SYMBOLS:

@@ -1,0 +1,395 @@
+// raftcorr.cu -- SURVEY.md section 8(f) rank 3, first slice: the RAFT-specific (non-convolution) stages of the flow
+// network that runs right after the VMAE path in every counterfactual (cwm/models/segmentation.py:431).
+//
+//   CorrBlock.corr / __init__   all-pairs correlation volume + average-pooled pyramid   cwm/models/raft/corr.py:12-28, 53-60
+//   CorrBlock.__call__          (2r+1)^2 bilinear window lookup at every level          cwm/models/raft/corr.py:30-51
+//   bilinear_sampler            pixel coords -> grid_sample(align_corners=True)         cwm/models/raft/utils.py:60-80
+//   RAFT.upsample_flow          convex 8x upsampling of the 1/8-resolution flow         cwm/models/raft/raft_model.py:175-186
+//
+// Everything is fp32 like the reference (RAFT calls `.float()` on the feature maps before the correlation,
+// raft_model.py:224-225).  The lookup repeats the reference's coordinate arithmetic operation by operation
+// (normalise to [-1, 1], un-normalise inside grid_sample, floor, corner weights, zero padding), so the only
+// differences left are summation order in the volume (fp32 FMA chain over the feature channels instead of a BLAS
+// order) and FMA contraction: tests hold 2e-5 relative to the volume's scale.
+//
+// Data layout in HBM: level l of the pyramid is fp32 [B*H*W, H>>l, W>>l] (the reference's `corr_pyramid[l]` without
+// its singleton channel); 3.25 MB per sample at 28x28 / 4 levels.  The lookup output is [B, L*(2r+1)^2, H, W].
+#include "common.cuh"
+
+namespace cwm {
+
+// ---------------------------------------------------------------------------------------------
+// all-pairs correlation: C[b, i, j] = sum_c f1[b, c, i] * f2[b, c, j] / sqrt(D).   fmaps are [B, D, HW] (NCHW), so
+// both operands are contiguous along the output index -> coalesced 16-byte loads with no transposition.
+// 64 x 64 outputs per CTA, 4 x 4 per thread, the channel axis streamed through shared memory 16 at a time with the
+// next slab prefetched into registers.  fp32 FMA pipe bound (2*HW^2*D FLOP against HW^2*4 bytes written).
+// ---------------------------------------------------------------------------------------------
+template <bool kVec>
+__global__ void __launch_bounds__(256)
+raft_corr_volume_kernel(const float* __restrict__ f1, const float* __restrict__ f2, int D, int HW, float div,
+                        float* __restrict__ out) {
+  __shared__ __align__(16) float a_s[16][64], b_s[16][64];
+  const int b = blockIdx.z;
+  const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+  const float* f1b = f1 + static_cast<size_t>(b) * D * HW;
+  const float* f2b = f2 + static_cast<size_t>(b) * D * HW;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  // loader mapping: thread -> (channel lk of the slab, 4 consecutive positions lr)
+  const int lk = threadIdx.x >> 4, lr = (threadIdx.x & 15) * 4;
+  float4 ra, rb;
+  auto fetch = [&](int k0) {
+    const int c = k0 + lk;
+    ra = make_float4(0.f, 0.f, 0.f, 0.f);
+    rb = ra;
+    if (c < D) {
+      const float* pa = f1b + static_cast<size_t>(c) * HW + i0 + lr;
+      const float* pb = f2b + static_cast<size_t>(c) * HW + j0 + lr;
+      if (kVec) {
+        if (i0 + lr < HW) ra = __ldg(reinterpret_cast<const float4*>(pa));
+        if (j0 + lr < HW) rb = __ldg(reinterpret_cast<const float4*>(pb));
+      } else {
+        float* va = reinterpret_cast<float*>(&ra);
+        float* vb = reinterpret_cast<float*>(&rb);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (i0 + lr + u < HW) va[u] = __ldg(pa + u);
+          if (j0 + lr + u < HW) vb[u] = __ldg(pb + u);
+        }
+      }
+    }
+  };
+  float acc[4][4] = {};
+  fetch(0);
+  for (int k0 = 0; k0 < D; k0 += 16) {
+    *reinterpret_cast<float4*>(&a_s[lk][lr]) = ra;
+    *reinterpret_cast<float4*>(&b_s[lk][lr]) = rb;
+    __syncthreads();
+    if (k0 + 16 < D) fetch(k0 + 16);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float4 av = *reinterpret_cast<const float4*>(&a_s[k][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&b_s[k][tx * 4]);
+      const float a[4] = {av.x, av.y, av.z, av.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(a[u], bb[v], acc[u][v]);
+    }
+    __syncthreads();
+  }
+  float* ob = out + static_cast<size_t>(b) * HW * HW;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int i = i0 + ty * 4 + u;
+    if (i >= HW) continue;
+    const int j = j0 + tx * 4;
+    // corr / torch.sqrt(torch.tensor(dim).float())  (corr.py:60): div = sqrtf(D)
+    float o[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) o[v] = __fdiv_rn(acc[u][v], div);
+    float* dst = ob + static_cast<size_t>(i) * HW + j;
+    if (kVec) {
+      if (j < HW) *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
+#pragma unroll
+      for (int v = 0; v < 4; ++v)
+        if (j + v < HW) dst[v] = o[v];
+    }
+  }
+}
+
+// F.avg_pool2d(corr, 2, stride=2) (corr.py:26-27): row-major sum of the 2 x 2 window divided by 4, odd trailing
+// row / column dropped.  One thread per output element; HBM-bound (reads 16 B, writes 4 B per element).
+__global__ void __launch_bounds__(256)
+raft_corr_pool_kernel(const float* __restrict__ in, float* __restrict__ out, long long total, int hi, int wi, int ho,
+                      int wo) {
+  const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int x = static_cast<int>(e % wo);
+  const long long t = e / wo;
+  const int y = static_cast<int>(t % ho);
+  const long long p = t / ho;
+  const float* src = in + (p * hi + 2 * y) * wi + 2 * x;
+  const float s = ((__ldg(src) + __ldg(src + 1)) + __ldg(src + wi)) + __ldg(src + wi + 1);
+  out[e] = __fdiv_rn(s, 4.f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// pyramid lookup.  One CTA = 32 consecutive query pixels (flat over b, y, x) x all channels of the output, so the
+// [B, L*(2r+1)^2, H, W] result is written as full 128-byte rows.  Work item = (pixel, level), one warp each:
+//   * 2r+1 lanes restate the reference's x arithmetic, 2r+1 lanes the y arithmetic (it is separable: the sample
+//     position of tap (a, b) is (cx + a - r, cy + b - r), corr.py:38-44 -- note the reference's meshgrid puts the
+//     FIRST window axis on x);
+//   * the warp stages the (2r+4)^2 source window that every tap of the item can touch in shared memory (zero-filled
+//     outside the map = grid_sample's zero padding), 144 loads instead of 4*81;
+//   * every lane then combines 4 corners per tap in ATen's order (nw, ne, sw, se).
+// HBM-bound on the output write (L*(2r+1)^2*4 bytes per pixel); the pyramid reads hit L2.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxLevels = 8;
+struct CorrLevels {
+  const float* p[kMaxLevels];
+  int h[kMaxLevels], w[kMaxLevels];
+};
+
+__device__ __forceinline__ void raft_axis(float c, int tap_off, int size, int* i0, float* w_lo, float* w_hi) {
+  // centroid_lvl + delta_lvl (corr.py:42-44)
+  const float pos = __fadd_rn(c, static_cast<float>(tap_off));
+  // bilinear_sampler: 2*x/(W-1) - 1 (utils.py:64-65)
+  const float g = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, pos), static_cast<float>(size - 1)), 1.f);
+  // grid_sampler_unnormalize, align_corners=True: ((g + 1) / 2) * (size - 1)
+  const float ix = __fmul_rn(__fdiv_rn(__fadd_rn(g, 1.f), 2.f), static_cast<float>(size - 1));
+  if (!(fabsf(ix) < 1.0e8f)) {  // NaN / inf / absurd coordinate: every corner is out of bounds
+    *i0 = -(1 << 28);
+    *w_lo = 0.f;
+    *w_hi = 0.f;
+    return;
+  }
+  const float fl = floorf(ix);
+  *i0 = static_cast<int>(fl);
+  *w_lo = __fsub_rn(__fadd_rn(fl, 1.f), ix);  // (ix_se - ix): weight of the low corner
+  *w_hi = __fsub_rn(ix, fl);                  // (ix - ix_nw): weight of the high corner
+}
+
+__global__ void __launch_bounds__(256)
+raft_corr_lookup_kernel(const __grid_constant__ CorrLevels lv, int L, int r, const float* __restrict__ coords, long long P, int HW,
+                        float* __restrict__ out) {
+  extern __shared__ float smem[];
+  const int n1 = 2 * r + 1, n2 = n1 * n1, nch = L * n2;
+  const int WS = 2 * r + 4;
+  float* tile = smem;                                   // [nch][33]
+  float* wbase = tile + static_cast<size_t>(nch) * 33;  // per warp: window WS*WS, then 6 arrays of n1
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per_warp = WS * WS + 6 * n1;
+  float* win = wbase + warp * per_warp;
+  int* xi = reinterpret_cast<int*>(win + WS * WS);
+  float* xlo = reinterpret_cast<float*>(xi + n1);
+  float* xhi = xlo + n1;
+  int* yi = reinterpret_cast<int*>(xhi + n1);
+  float* ylo = reinterpret_cast<float*>(yi + n1);
+  float* yhi = ylo + n1;
+  const long long p0 = static_cast<long long>(blockIdx.x) * 32;
+
+  for (int item = warp; item < 32 * L; item += 8) {
+    const int pix = item & 31, lvl = item >> 5;
+    const long long p = p0 + pix;
+    if (p >= P) continue;  // warp-uniform
+    const long long b = p / HW;
+    const int hw = static_cast<int>(p - b * HW);
+    const float scale = 1.f / static_cast<float>(1 << lvl);  // coords / 2**i (exact)
+    const float cx = __ldg(coords + (b * 2) * HW + hw) * scale;
+    const float cy = __ldg(coords + (b * 2 + 1) * HW + hw) * scale;
+    const int Hl = lv.h[lvl], Wl = lv.w[lvl];
+    const float* src = lv.p[lvl] + p * (static_cast<long long>(Hl) * Wl);
+    // window origin; clamped so absurd coordinates cannot overflow the int conversion
+    const int wx0 = static_cast<int>(floorf(fminf(fmaxf(cx, -1.0e6f), 1.0e6f))) - r - 1;
+    const int wy0 = static_cast<int>(floorf(fminf(fmaxf(cy, -1.0e6f), 1.0e6f))) - r - 1;
+    if (lane < n1) {
+      raft_axis(cx, lane - r, Wl, &xi[lane], &xlo[lane], &xhi[lane]);
+    } else if (lane >= 16 && lane < 16 + n1) {
+      const int t = lane - 16;
+      raft_axis(cy, t - r, Hl, &yi[t], &ylo[t], &yhi[t]);
+    }
+    for (int e = lane; e < WS * WS; e += 32) {
+      const int wy = e / WS, wx = e - wy * WS;
+      const int gy = wy0 + wy, gx = wx0 + wx;
+      win[e] = (gy >= 0 && gy < Hl && gx >= 0 && gx < Wl) ? __ldg(src + gy * Wl + gx) : 0.f;
+    }
+    __syncwarp();
+    auto at = [&](int gy, int gx) -> float {
+      const int ry = gy - wy0, rx = gx - wx0;
+      if (ry >= 0 && ry < WS && rx >= 0 && rx < WS) return win[ry * WS + rx];
+      // outside the staged window (only when |coords| is so large that fp32 rounding exceeds a pixel)
+      return (gy >= 0 && gy < Hl && gx >= 0 && gx < Wl) ? __ldg(src + gy * Wl + gx) : 0.f;
+    };
+    for (int k = lane; k < n2; k += 32) {
+      const int a = k / n1, bb = k - a * n1;  // a: x offset, bb: y offset
+      const int x0 = xi[a], y0 = yi[bb];
+      float acc = 0.f;
+      acc = fmaf(at(y0, x0), __fmul_rn(xlo[a], ylo[bb]), acc);          // nw
+      acc = fmaf(at(y0, x0 + 1), __fmul_rn(xhi[a], ylo[bb]), acc);      // ne
+      acc = fmaf(at(y0 + 1, x0), __fmul_rn(xlo[a], yhi[bb]), acc);      // sw
+      acc = fmaf(at(y0 + 1, x0 + 1), __fmul_rn(xhi[a], yhi[bb]), acc);  // se
+      tile[(lvl * n2 + k) * 33 + pix] = acc;
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  const long long p = p0 + lane;
+  if (p < P) {
+    const long long b = p / HW;
+    const int hw = static_cast<int>(p - b * HW);
+    float* dst = out + b * static_cast<long long>(nch) * HW + hw;
+    for (int ch = warp; ch < nch; ch += 8) dst[static_cast<long long>(ch) * HW] = tile[ch * 33 + lane];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// convex upsampling (raft_model.py:175-186): out[n, c, 8y+i, 8x+j] = sum_k softmax_k(mask[n, k*64 + i*8 + j, y, x]) *
+// 8*flow[n, c, y + k/3 - 1, x + k%3 - 1] (zero padded).  One CTA per (n, y, 32-column slab): the 576 mask rows of the
+// slab are staged in shared memory (pitch 36 keeps the j-fastest reads conflict-free), every thread produces
+// outputs with j fastest so each warp writes one 128-byte row segment.  HBM-bound: reads 576*4 B, writes 64*C*4 B per
+// 1/8-resolution pixel.
+// ---------------------------------------------------------------------------------------------
+constexpr int kUpPitch = 36;
+__global__ void __launch_bounds__(256)
+raft_upsample_kernel(const float* __restrict__ flow, const float* __restrict__ mask, int C, int H, int W,
+                     float* __restrict__ out) {
+  extern __shared__ float smem[];
+  float* m_s = smem;                   // [576][36]
+  float* f_s = smem + 576 * kUpPitch;  // [C][3][34]
+  const int n = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * 32;
+  const int XW = min(32, W - x0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t HWs = static_cast<size_t>(H) * W;
+  const float* mrow = mask + (static_cast<size_t>(n) * 576) * HWs + static_cast<size_t>(y) * W + x0;
+  if (lane < XW)
+    for (int row = warp; row < 576; row += 8) m_s[row * kUpPitch + lane] = __ldg(mrow + row * HWs + lane);
+  for (int e = threadIdx.x; e < C * 3 * 34; e += 256) {
+    const int xx = e % 34, t = e / 34, dy = t % 3, c = t / 3;
+    const int gy = y + dy - 1, gx = x0 + xx - 1;
+    float v = 0.f;
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W)
+      v = __fmul_rn(8.f, __ldg(flow + (static_cast<size_t>(n) * C + c) * HWs + static_cast<size_t>(gy) * W + gx));
+    f_s[e] = v;
+  }
+  __syncthreads();
+  const int per_row = 8 * XW;
+  for (int t = threadIdx.x; t < 8 * per_row; t += 256) {
+    const int i = t / per_row, rem = t - i * per_row;
+    const int x = rem >> 3, j = rem & 7;
+    float m[9];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      m[k] = m_s[(k * 64 + i * 8 + j) * kUpPitch + x];
+      mx = fmaxf(mx, m[k]);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      m[k] = expf(m[k] - mx);
+      sum += m[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) m[k] = __fdiv_rn(m[k], sum);
+    for (int c = 0; c < C; ++c) {
+      const float* fc = f_s + c * 3 * 34;
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) acc = fmaf(m[k], fc[(k / 3) * 34 + x + (k % 3)], acc);
+      out[((static_cast<size_t>(n) * C + c) * (8 * H) + 8 * y + i) * (8 * static_cast<size_t>(W)) + 8 * (x0 + x) + j] = acc;
+    }
+  }
+}
+
+static int level_dims(int H, int W, int L, int* hs, int* ws, const char* who) {
+  CWM_REQUIRE(L >= 1 && L <= kMaxLevels, "%s: num_levels %d not in [1, %d]", who, L, kMaxLevels);
+  hs[0] = H;
+  ws[0] = W;
+  for (int l = 1; l < L; ++l) {
+    hs[l] = hs[l - 1] / 2;
+    ws[l] = ws[l - 1] / 2;
+  }
+  // the reference divides by (size - 1) of every level (utils.py:64-65): a 1-pixel level would produce NaN there
+  CWM_REQUIRE(hs[L - 1] >= 2 && ws[L - 1] >= 2, "%s: level %d of a (%d,%d) map is smaller than 2x2", who, L - 1, H, W);
+  return CWM_OK;
+}
+
+}  // namespace cwm
+
+using namespace cwm;
+
+extern "C" int cwm_raft_corr_pyramid(const float* fmap1, const float* fmap2, int B, int D, int H, int W,
+                                     int num_levels, float* const* levels, cwm_stream_t stream) {
+  CWM_REQUIRE(B >= 0 && D >= 1 && H >= 1 && W >= 1, "cwm_raft_corr_pyramid: bad shape B=%d D=%d H=%d W=%d", B, D, H, W);
+  int hs[kMaxLevels], ws[kMaxLevels];
+  int rc = level_dims(H, W, num_levels, hs, ws, "cwm_raft_corr_pyramid");
+  if (rc != CWM_OK) return rc;
+  CWM_REQUIRE(levels, "cwm_raft_corr_pyramid: null level table");
+  if (B == 0) return CWM_OK;
+  CWM_REQUIRE(fmap1 && fmap2, "cwm_raft_corr_pyramid: null feature map");
+  for (int l = 0; l < num_levels; ++l) CWM_REQUIRE(levels[l], "cwm_raft_corr_pyramid: null level %d", l);
+  const int HW = H * W;
+  CWM_REQUIRE(B <= 65535, "cwm_raft_corr_pyramid: batch %d > 65535 (chunk the sweep)", B);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const float div = sqrtf(static_cast<float>(D));
+  {
+    ProfileScope prof(st, "raft_corr_volume", 2.0 * B * static_cast<double>(HW) * HW * D,
+                      static_cast<double>(B) * HW * (static_cast<double>(HW) + 2.0 * D) * 4.0);
+    const dim3 grid((HW + 63) / 64, (HW + 63) / 64, B);
+    const bool vec = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(fmap1) | reinterpret_cast<uintptr_t>(fmap2) |
+                                        reinterpret_cast<uintptr_t>(levels[0])) % 16 == 0);
+    if (vec)
+      raft_corr_volume_kernel<true><<<grid, 256, 0, st>>>(fmap1, fmap2, D, HW, div, levels[0]);
+    else
+      raft_corr_volume_kernel<false><<<grid, 256, 0, st>>>(fmap1, fmap2, D, HW, div, levels[0]);
+    CWM_LAUNCH_CHECK();
+  }
+  for (int l = 1; l < num_levels; ++l) {
+    const long long total = static_cast<long long>(B) * HW * hs[l] * ws[l];
+    ProfileScope prof(st, "raft_corr_pool", 0.0, static_cast<double>(total) * 20.0);
+    raft_corr_pool_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(levels[l - 1], levels[l], total,
+                                                                                      hs[l - 1], ws[l - 1], hs[l], ws[l]);
+    CWM_LAUNCH_CHECK();
+  }
+  return CWM_OK;
+}
+
+extern "C" int cwm_raft_corr_lookup(const float* const* levels, int num_levels, int radius, const float* coords, int B,
+                                    int H, int W, float* out, cwm_stream_t stream) {
+  CWM_REQUIRE(B >= 0 && H >= 1 && W >= 1, "cwm_raft_corr_lookup: bad shape B=%d H=%d W=%d", B, H, W);
+  CWM_REQUIRE(radius >= 0 && radius <= 7, "cwm_raft_corr_lookup: radius %d not in [0, 7]", radius);
+  CorrLevels lv;
+  int rc = level_dims(H, W, num_levels, lv.h, lv.w, "cwm_raft_corr_lookup");
+  if (rc != CWM_OK) return rc;
+  CWM_REQUIRE(levels, "cwm_raft_corr_lookup: null level table");
+  if (B == 0) return CWM_OK;
+  CWM_REQUIRE(coords && out, "cwm_raft_corr_lookup: null pointer");
+  for (int l = 0; l < num_levels; ++l) {
+    CWM_REQUIRE(levels[l], "cwm_raft_corr_lookup: null level %d", l);
+    lv.p[l] = levels[l];
+  }
+  const int n1 = 2 * radius + 1, nch = num_levels * n1 * n1, WS = 2 * radius + 4;
+  const size_t smem = (static_cast<size_t>(nch) * 33 + 8 * (WS * WS + 6 * n1)) * sizeof(float);
+  CWM_REQUIRE(smem <= 200 * 1024, "cwm_raft_corr_lookup: %d levels x radius %d needs %zu bytes of shared memory", num_levels,
+              radius, smem);
+  static size_t configured = 0;  // grow-only opt-in for > 48 KB of dynamic shared memory
+  if (smem > configured) {
+    CWM_CUDA_CHECK(cudaFuncSetAttribute(raft_corr_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(smem)));
+    configured = smem;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long P = static_cast<long long>(B) * H * W;
+  double pyr = 0.0;
+  for (int l = 0; l < num_levels; ++l) {
+    const int ws = min(WS, lv.w[l]), hs = min(WS, lv.h[l]);
+    pyr += static_cast<double>(ws) * hs;
+  }
+  ProfileScope prof(st, "raft_corr_lookup", 0.0, static_cast<double>(P) * (nch + pyr + 2.0) * 4.0);
+  raft_corr_lookup_kernel<<<static_cast<unsigned>((P + 31) / 32), 256, smem, st>>>(lv, num_levels, radius, coords, P, H * W,
+                                                                                  out);
+  CWM_LAUNCH_CHECK();
+  return CWM_OK;
+}
+
+extern "C" int cwm_raft_upsample_flow(const float* flow, const float* mask, int N, int C, int H, int W, float* out,
+                                      cwm_stream_t stream) {
+  CWM_REQUIRE(N >= 0 && C >= 1 && C <= 16 && H >= 1 && W >= 1, "cwm_raft_upsample_flow: bad shape N=%d C=%d H=%d W=%d", N, C,
+              H, W);
+  if (N == 0) return CWM_OK;
+  CWM_REQUIRE(flow && mask && out, "cwm_raft_upsample_flow: null pointer");
+  CWM_REQUIRE(N <= 65535 && H <= 65535, "cwm_raft_upsample_flow: N=%d / H=%d exceed the grid limits", N, H);
+  const size_t smem = (576 * kUpPitch + static_cast<size_t>(C) * 3 * 34) * sizeof(float);
+  static size_t configured = 0;
+  if (smem > configured) {
+    CWM_CUDA_CHECK(cudaFuncSetAttribute(raft_upsample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(smem)));
+    configured = smem;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfileScope prof(st, "raft_upsample", 0.0, static_cast<double>(N) * H * W * (576.0 + C + 64.0 * C) * 4.0);
+  raft_upsample_kernel<<<dim3((W + 31) / 32, H, N), 256, smem, st>>>(flow, mask, C, H, W, out);
+  CWM_LAUNCH_CHECK();
+  return CWM_OK;
+}

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define CWM_B200_ABI_VERSION 4
+#define CWM_B200_ABI_VERSION 5
 
 typedef void* cwm_stream_t; /* cudaStream_t */
 
@@ -385,6 +385,26 @@ int cwm_flow_corrs(const float* flows, const int64_t fs[5], int B, int H, int W,
  * (`compute_mean_motion_map`, segmentation.py:268-276).  sums / motion_map fp32 [B, H, W]. */
 int cwm_motion_map_finalize(const float* sums, int B, int H, int W, float count, int normalize, float eps,
                             float* motion_map, cwm_stream_t stream);
+
+/* ==== SURVEY.md section 8(f) rank 3, first slice: the RAFT-specific stages of the flow network ================
+ * (the convolutions of RAFT stay a caller-supplied torch module; these replace what is NOT a convolution.)
+ * All tensors fp32, contiguous, NCHW like the reference.
+ *
+ * `CorrBlock.__init__` (cwm/models/raft/corr.py:12-28, :53-60): levels[0] = fmap1^T fmap2 / sqrt(D) as
+ * [B*H*W, H, W]; levels[l] = avg_pool2d(levels[l-1], 2, stride=2) as [B*H*W, H>>l, W>>l].  `levels` is a HOST array
+ * of num_levels DEVICE pointers (the reference's `corr_pyramid` list); fmap1 / fmap2 are [B, D, H, W].  Every level
+ * must be at least 2x2 (the reference divides by size-1, cwm/models/raft/utils.py:64-65). */
+int cwm_raft_corr_pyramid(const float* fmap1, const float* fmap2, int B, int D, int H, int W, int num_levels,
+                          float* const* levels, cwm_stream_t stream);
+/* `CorrBlock.__call__` (corr.py:30-51) + `bilinear_sampler` (utils.py:60-80, grid_sample align_corners=True, zero
+ * padding): coords [B, 2, H, W] (channel 0 = x, 1 = y, in level-0 pixels) -> out [B, num_levels*(2r+1)^2, H, W];
+ * channel l*(2r+1)^2 + a*(2r+1) + b samples level l at (x/2^l + a - r, y/2^l + b - r). */
+int cwm_raft_corr_lookup(const float* const* levels, int num_levels, int radius, const float* coords, int B, int H,
+                         int W, float* out, cwm_stream_t stream);
+/* `RAFT.upsample_flow` (cwm/models/raft/raft_model.py:175-186): flow [N, C, H, W], mask [N, 576, H, W] (9 x 8 x 8
+ * logits per coarse pixel) -> out [N, C, 8H, 8W], the softmax-weighted combination of the 3x3 neighbours of 8*flow. */
+int cwm_raft_upsample_flow(const float* flow, const float* mask, int N, int C, int H, int W, float* out,
+                           cwm_stream_t stream);
 
 /* Number of kernel launches this thread enqueued through the library since the last cwm_vmae_forward began or
  * cwm_launch_count_reset() was called (for bench accounting). */

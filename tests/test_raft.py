@@ -1,0 +1,248 @@
+"""SURVEY.md section 8(f) rank 3, first slice -- RAFT's correlation block and convex upsampling.
+CPU: the numpy oracle against the fixtures the REAL reference produced (tests/golden/raft_*.npz); host-side validation.
+GPU: csrc/raftcorr.cu through the mirror (``raft.CorrBlock`` / ``raft.upsample_flow``) against the fixtures and the oracle.
+
+Tolerance: fp32 everywhere.  The volume sums D products in a different order than BLAS and the lookup contracts
+multiply-adds, so values agree to a few ulp of the largest term: 2e-5 of the output scale (max |reference|) is the
+bar; the oracle itself is pinned to the reference at 2e-6 of scale by oracle/make_golden_raft.py."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import raft_oracle as ro
+from conftest import GOLDEN_DIR
+
+CORR_CASES = ["raft_corr_l3_r2_8x12_b2", "raft_corr_l4_r4_16x24_b1", "raft_corr_l4_r3_17x19_b1"]
+UPSAMPLE_CASES = ["raft_upsample_n2_5x36", "raft_upsample_n1_c3_4x7"]
+DEV = "cuda:0"
+ORACLE_TOL, GPU_TOL = 2e-6, 2e-5
+
+
+def load(case):
+    path = os.path.join(GOLDEN_DIR, case + ".npz")
+    if not os.path.exists(path):
+        pytest.skip(f"golden fixture {case} missing")
+    z = np.load(path)
+    return {k: z[k] for k in z.files}
+
+
+def rel_err(got, want):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    return np.abs(got - want).max() / max(np.abs(want).max(), 1e-30)
+
+
+def stored_level(ref_l, lvl, n_rows):
+    return ref_l[::7] if lvl < 2 and n_rows > 200 else ref_l
+
+
+# ------------------------------------------------------------------------------------------------ CPU
+@pytest.mark.parametrize("case", CORR_CASES)
+def test_oracle_corr_block_matches_reference_fixture(case):
+    d = load(case)
+    B, D, H, W, L, r, seed, sy, sx = [int(v) for v in d["shape"]]
+    f1, f2 = ro.make_fmaps(B, D, H, W, seed)
+    pyr = ro.corr_pyramid(f1, f2, L)
+    for lvl in range(L):
+        assert pyr[lvl].shape == (B * H * W, H >> lvl, W >> lvl)
+        assert rel_err(stored_level(pyr[lvl], lvl, B * H * W), d[f"level{lvl}"]) <= ORACLE_TOL
+    for kind in ("grid", "random"):
+        out = ro.corr_lookup(pyr, ro.make_coords(B, H, W, seed, kind), r)
+        assert out.shape == (B, L * (2 * r + 1) ** 2, H, W)
+        assert rel_err(out[:, :, ::sy, ::sx], d[f"lookup_{kind}"]) <= ORACLE_TOL
+
+
+def test_oracle_matches_the_trace_of_the_reference_raft():
+    d = load("raft_trace_large_128px")
+    f1, f2 = d["fmap1"].astype(np.float32), d["fmap2"].astype(np.float32)
+    pyr = ro.corr_pyramid(f1, f2, 4)
+    for it in range(3):
+        out = ro.corr_lookup(pyr, d[f"coords{it}"], 4)
+        assert rel_err(out[:, :, ::2, ::2], d[f"lookup{it}"]) <= ORACLE_TOL
+    # iteration 0 looks up the exact integer grid: the centre tap of level 0 is the volume's own diagonal entry
+    centre = 4 * 9 + 4
+    diag = pyr[0].reshape(256, 256)[np.arange(256), np.arange(256)].reshape(1, 16, 16)
+    np.testing.assert_allclose(ro.corr_lookup(pyr, d["coords0"], 4)[:, centre], diag, rtol=0, atol=2e-5 * np.abs(diag).max())
+
+
+@pytest.mark.parametrize("case", UPSAMPLE_CASES)
+def test_oracle_upsample_matches_reference_fixture(case):
+    d = load(case)
+    N, C, H, W, seed, stride = [int(v) for v in d["shape"]]
+    flow, mask = ro.make_upsample_inputs(N, C, H, W, seed)
+    up = ro.upsample_flow(flow, mask)
+    assert up.shape == (N, C, 8 * H, 8 * W)
+    assert rel_err(up[:, :, ::stride], d["up"]) <= ORACLE_TOL
+
+
+def test_oracle_upsample_of_a_constant_flow_is_that_flow_times_8_inside():
+    flow = np.full((1, 2, 4, 5), 1.5, np.float32)
+    _, mask = ro.make_upsample_inputs(1, 2, 4, 5, 3)
+    up = ro.upsample_flow(flow, mask)
+    # away from the zero padding every convex combination of equal neighbours is the neighbour itself
+    np.testing.assert_allclose(up[:, :, 8:-8, 8:-8], 12.0, rtol=1e-6)
+    assert up[:, :, :8].max() <= 12.0 + 1e-5
+
+
+def test_mirror_has_no_cpu_fallback_and_the_abi_validates_arguments():
+    from counterfactualworldmodels_b200 import _lib, raft
+    f = torch.zeros(1, 4, 8, 8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        raft.CorrBlock(f, f)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        raft.upsample_flow(torch.zeros(1, 2, 4, 4), torch.zeros(1, 576, 4, 4))
+    g = raft.coords_grid(2, 3, 5, "cpu")
+    assert g.shape == (2, 2, 3, 5) and g[1, 0, 2, 4] == 4 and g[1, 1, 2, 4] == 2
+    lib = _lib.load()
+    table = (ctypes.c_void_p * 4)(1, 1, 1, 1)
+    assert lib.cwm_raft_corr_pyramid(1, 1, 1, 8, 8, 8, 4, table, None) == -1       # level 3 of 8x8 is 1x1
+    assert b"smaller than 2x2" in lib.cwm_last_error()
+    assert lib.cwm_raft_corr_pyramid(1, 1, 1, 8, 16, 16, 9, table, None) == -1 and b"num_levels" in lib.cwm_last_error()
+    assert lib.cwm_raft_corr_pyramid(None, None, 1, 8, 16, 16, 4, table, None) == -1
+    assert lib.cwm_raft_corr_lookup(table, 4, 9, 1, 1, 16, 16, 1, None) == -1 and b"radius" in lib.cwm_last_error()
+    assert lib.cwm_raft_corr_lookup(table, 4, 4, None, 1, 16, 16, None, None) == -1
+    assert lib.cwm_raft_upsample_flow(None, None, 1, 2, 4, 4, None, None) == -1
+    assert lib.cwm_raft_upsample_flow(1, 1, 1, 0, 4, 4, 1, None) == -1
+    assert lib.cwm_raft_corr_pyramid(None, None, 0, 8, 16, 16, 4, table, None) == 0  # empty batch is a no-op
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CORR_CASES)
+def test_gpu_corr_block_matches_reference_fixture(case):
+    from counterfactualworldmodels_b200 import raft
+    d = load(case)
+    B, D, H, W, L, r, seed, sy, sx = [int(v) for v in d["shape"]]
+    f1, f2 = ro.make_fmaps(B, D, H, W, seed)
+    block = raft.CorrBlock(torch.from_numpy(f1).to(DEV), torch.from_numpy(f2).to(DEV), num_levels=L, radius=r)
+    assert len(block.corr_pyramid) == L
+    pyr_o = ro.corr_pyramid(f1, f2, L)
+    for lvl in range(L):
+        got = block.corr_pyramid[lvl]
+        assert tuple(got.shape) == (B * H * W, 1, H >> lvl, W >> lvl)
+        got = got[:, 0].cpu().numpy()
+        assert rel_err(stored_level(got, lvl, B * H * W), d[f"level{lvl}"]) <= GPU_TOL
+        assert rel_err(got, pyr_o[lvl]) <= GPU_TOL
+    for kind in ("grid", "random"):
+        coords = ro.make_coords(B, H, W, seed, kind)
+        out = block(torch.from_numpy(coords).to(DEV))
+        assert out.dtype == torch.float32 and out.is_contiguous()
+        out = out.cpu().numpy()
+        assert rel_err(out[:, :, ::sy, ::sx], d[f"lookup_{kind}"]) <= GPU_TOL
+        assert rel_err(out, ro.corr_lookup(pyr_o, coords, r)) <= GPU_TOL
+
+
+@pytest.mark.gpu
+def test_gpu_corr_block_on_the_trace_of_the_reference_raft():
+    from counterfactualworldmodels_b200 import raft
+    d = load("raft_trace_large_128px")
+    f1, f2 = torch.from_numpy(d["fmap1"]).to(DEV), torch.from_numpy(d["fmap2"]).to(DEV)  # f16: the mirror casts
+    block = raft.CorrBlock(f1, f2, radius=4)
+    for it in range(3):
+        out = block(torch.from_numpy(d[f"coords{it}"]).to(DEV)).cpu().numpy()
+        assert rel_err(out[:, :, ::2, ::2], d[f"lookup{it}"]) <= GPU_TOL
+    vol = raft.CorrBlock.corr(f1, f2)
+    assert tuple(vol.shape) == (1, 16, 16, 1, 16, 16)
+    assert torch.equal(vol.reshape(256, 16, 16), block.corr_pyramid[0][:, 0])
+
+
+@pytest.mark.gpu
+def test_gpu_corr_block_at_the_sweep_shape_against_the_oracle():
+    """224 px input -> 28x28 maps, D = 256 (RAFT-large), 3 samples: full comparison with the oracle, integer grid
+    and far-out-of-bounds centres included; a non-default stream; NaN centres give zeros, not a fault."""
+    from counterfactualworldmodels_b200 import raft
+    B, D, H, W = 3, 256, 28, 28
+    f1, f2 = ro.make_fmaps(B, D, H, W, 5)
+    pyr_o = ro.corr_pyramid(f1, f2, 4)
+    s = torch.cuda.Stream(device=DEV)
+    with torch.cuda.stream(s):
+        block = raft.CorrBlock(torch.from_numpy(f1).to(DEV), torch.from_numpy(f2).to(DEV))
+        outs = [block(torch.from_numpy(ro.make_coords(B, H, W, 5, kind)).to(DEV)) for kind in ("grid", "random")]
+        bad = torch.from_numpy(ro.make_coords(B, H, W, 5, "grid")).to(DEV)
+        bad[0, 0, 3, 4] = float("nan")
+        bad[1, 1, 0, 0] = float("inf")
+        bad[2, :, 5, 5] = 3.0e9
+        out_bad = block(bad)
+    s.synchronize()
+    for lvl in range(4):
+        assert rel_err(block.corr_pyramid[lvl][:, 0].cpu().numpy(), pyr_o[lvl]) <= GPU_TOL
+    for kind, out in zip(("grid", "random"), outs):
+        assert rel_err(out.cpu().numpy(), ro.corr_lookup(pyr_o, ro.make_coords(B, H, W, 5, kind), 4)) <= GPU_TOL
+    assert torch.isfinite(out_bad).all()
+    assert out_bad[0, :, 3, 4].abs().max() == 0 and out_bad[1, :, 0, 0].abs().max() == 0
+    assert out_bad[2, :, 5, 5].abs().max() == 0
+    keep = torch.ones(B, H, W, dtype=torch.bool, device=DEV)
+    keep[0, 3, 4] = keep[1, 0, 0] = keep[2, 5, 5] = False
+    assert torch.equal(out_bad.permute(0, 2, 3, 1)[keep], outs[0].permute(0, 2, 3, 1)[keep])
+
+
+@pytest.mark.gpu
+def test_gpu_corr_lookup_properties_at_sweep_batch():
+    """64 samples at 28x28 (a sweep chunk; the oracle would take minutes): size-independent properties.
+    (i) the centre tap of level 0 at the integer grid is the volume's diagonal-by-construction entry;
+    (ii) a lookup shifted by one whole pixel is the neighbouring channel of the unshifted lookup;
+    (iii) the volume is linear in fmap2."""
+    from counterfactualworldmodels_b200 import raft
+    B, D, H, W, r = 64, 256, 28, 28, 4
+    g = torch.Generator(device=DEV).manual_seed(0)
+    f1 = torch.randn(B, D, H, W, device=DEV, generator=g)
+    f2 = torch.randn(B, D, H, W, device=DEV, generator=g)
+    block = raft.CorrBlock(f1, f2, radius=r)
+    grid = raft.coords_grid(B, H, W, DEV)
+    out = block(grid)
+    assert tuple(out.shape) == (B, 4 * 81, H, W)
+    vol = block.corr_pyramid[0].view(B, H * W, H * W)
+    diag = torch.diagonal(vol, dim1=1, dim2=2).reshape(B, H, W)
+    assert (out[:, 4 * 9 + 4] - diag).abs().max() <= 1e-5 * diag.abs().max()
+    shifted = block(grid + torch.tensor([1.0, 0.0], device=DEV).view(1, 2, 1, 1))   # x + 1
+    # channel a*9 + b samples x offset a - r: shifting the centre by +1 in x moves tap a to a + 1
+    lvl0, lvl0_s = out[:, :81].view(B, 9, 9, H, W), shifted[:, :81].view(B, 9, 9, H, W)
+    assert (lvl0_s[:, :-1] - lvl0[:, 1:]).abs().max() <= 1e-5 * vol.abs().max()
+    block2 = raft.CorrBlock(f1, 2.0 * f2, radius=r)
+    assert torch.equal(block2.corr_pyramid[0], 2.0 * block.corr_pyramid[0])
+    # pooling: every level is the 2x2 mean of the previous one
+    for lvl in range(1, 4):
+        want = torch.nn.functional.avg_pool2d(block.corr_pyramid[lvl - 1], 2, stride=2)
+        assert (block.corr_pyramid[lvl] - want).abs().max() <= 1e-6 * vol.abs().max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", UPSAMPLE_CASES)
+def test_gpu_upsample_matches_reference_fixture(case):
+    from counterfactualworldmodels_b200 import raft
+    d = load(case)
+    N, C, H, W, seed, stride = [int(v) for v in d["shape"]]
+    flow, mask = ro.make_upsample_inputs(N, C, H, W, seed)
+    up = raft.upsample_flow(torch.from_numpy(flow).to(DEV), torch.from_numpy(mask).to(DEV)).cpu().numpy()
+    assert rel_err(up[:, :, ::stride], d["up"]) <= GPU_TOL
+    assert rel_err(up, ro.upsample_flow(flow, mask)) <= GPU_TOL
+
+
+@pytest.mark.gpu
+def test_gpu_upsample_at_the_sweep_shape():
+    from counterfactualworldmodels_b200 import raft
+    flow, mask = ro.make_upsample_inputs(4, 2, 28, 28, 9)
+    up = raft.upsample_flow(torch.from_numpy(flow).to(DEV), torch.from_numpy(mask).to(DEV))
+    assert tuple(up.shape) == (4, 2, 224, 224)
+    assert rel_err(up.cpu().numpy(), ro.upsample_flow(flow, mask)) <= GPU_TOL
+    # convexity: every output lies inside the range of the 3x3 neighbourhood of 8*flow (zero padding included)
+    f8 = torch.nn.functional.pad(8 * torch.from_numpy(flow), (1, 1, 1, 1))
+    hi = torch.nn.functional.max_pool2d(f8, 3, stride=1).repeat_interleave(8, 2).repeat_interleave(8, 3)
+    lo = -torch.nn.functional.max_pool2d(-f8, 3, stride=1).repeat_interleave(8, 2).repeat_interleave(8, 3)
+    u = up.cpu()
+    assert (u <= hi + 1e-4).all() and (u >= lo - 1e-4).all()
+
+
+def test_torch_port_used_as_cpu_baseline_agrees_with_the_oracle():
+    f1, f2 = ro.make_fmaps(2, 16, 8, 12, 1)
+    coords = [ro.make_coords(2, 8, 12, 1, k) for k in ("grid", "random")]
+    outs = ro.torch_corr_block(torch.from_numpy(f1), torch.from_numpy(f2), [torch.from_numpy(c) for c in coords], 3, 2)
+    pyr = ro.corr_pyramid(f1, f2, 3)
+    for c, o in zip(coords, outs):
+        assert rel_err(o.numpy(), ro.corr_lookup(pyr, c, 2)) <= ORACLE_TOL
+    flow, mask = ro.make_upsample_inputs(1, 2, 4, 7, 2)
+    up = ro.torch_upsample_flow(torch.from_numpy(flow), torch.from_numpy(mask)).numpy()
+    assert rel_err(up, ro.upsample_flow(flow, mask)) <= ORACLE_TOL

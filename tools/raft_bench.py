@@ -1,0 +1,117 @@
+"""Timing of the RAFT correlation / upsampling kernels (first slice) on one B200 at the sweep
+shape: 224 px frames -> 28x28 maps, D = 256 (RAFT-large), S samples per chunk.  Per-kernel device times come from the
+library's CUDA-event profiler (events on the launching stream); buffers rotate so every pass reads / writes more than
+the 126 MB L2.  The reference's own ATen ops (oracle/raft_oracle.py torch port, all host threads) are timed beside them
+on a bounded sample.     python tools/raft_bench.py [S]"""
+import json
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import raft_oracle as ro  # noqa: E402
+from counterfactualworldmodels_b200 import _lib, raft  # noqa: E402
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return p["hbm_gbs"], "measured"
+    return 6650.0, "fallback"
+
+
+def profiled(fn, iters=6, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    _lib.profile_begin()
+    for _ in range(iters):
+        fn()
+    torch.cuda.synchronize()
+    return {e["name"]: dict(ms=e["ms"] / e["launches"] * (e["launches"] / iters), launches=e["launches"] // iters,
+                            flops=e["flops"] / iters, bytes=e["bytes"] / iters) for e in _lib.profile_end()}
+
+
+def main():
+    S = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+    dev = "cuda:0"
+    D, H, W, L, r = 256, 28, 28, 4, 4
+    hbm, src = peaks()
+    g = torch.Generator(device=dev).manual_seed(0)
+    fmaps = [(torch.randn(S, D, H, W, device=dev, generator=g), torch.randn(S, D, H, W, device=dev, generator=g))
+             for _ in range(2)]
+    grid = raft.coords_grid(S, H, W, dev)
+    coords = [grid + torch.randn(S, 2, H, W, device=dev, generator=g) * 2.5 for _ in range(2)]
+    out = {"S": S, "shape": [D, H, W, L, r], "hbm_peak_GBps": hbm, "peak_source": src, "kernels": {}}
+    i = [0]
+    if len(sys.argv) > 2 and sys.argv[2] == "ncu":   # one launch of every kernel, for `ncu -k regex:raft_`
+        block = raft.CorrBlock(*fmaps[0], num_levels=L, radius=r)
+        block(coords[0])
+        raft.upsample_flow(torch.randn(S, 2, H, W, device=dev), torch.randn(S, 576, H, W, device=dev))
+        torch.cuda.synchronize()
+        return
+
+    def build():
+        i[0] += 1
+        return raft.CorrBlock(*fmaps[i[0] % 2], num_levels=L, radius=r)
+
+    for name, e in profiled(build).items():
+        out["kernels"][name] = e
+    blocks = [build(), build()]   # 2 x 3.25 MB x S of pyramid: alternate so the lookups do not find their level in L2
+
+    def lookup():
+        i[0] += 1
+        return blocks[i[0] % 2](coords[i[0] % 2])
+
+    for name, e in profiled(lookup).items():
+        out["kernels"][name] = e
+    del blocks
+    ups = [(torch.randn(S, 2, H, W, device=dev, generator=g) * 3, torch.randn(S, 576, H, W, device=dev, generator=g) * 2)
+           for _ in range(2)]
+
+    def upsample():
+        i[0] += 1
+        return raft.upsample_flow(*ups[i[0] % 2])
+
+    for name, e in profiled(upsample).items():
+        out["kernels"][name] = e
+    for e in out["kernels"].values():
+        e["GBps"] = e["bytes"] / e["ms"] / 1e6
+        e["frac_of_hbm_peak"] = e["GBps"] / hbm
+        if e["flops"]:
+            e["TFLOPs"] = e["flops"] / e["ms"] / 1e9
+    k = out["kernels"]
+    pyr_ms = k["raft_corr_volume"]["ms"] + k["raft_corr_pool"]["ms"]
+    out["per_sample_us"] = {"pyramid": pyr_ms / S * 1e3, "lookup_x24": 24 * k["raft_corr_lookup"]["ms"] / S * 1e3,
+                            "upsample": k["raft_upsample"]["ms"] / S * 1e3}
+    out["per_sample_us"]["total_24_iters"] = sum(out["per_sample_us"].values())
+    # CPU: the reference's ATen ops, all host threads, bounded sample (n samples, 2 lookups scaled to 24)
+    n = min(S, 8)
+    f1, f2 = fmaps[0][0][:n].cpu(), fmaps[0][1][:n].cpu()
+    cl = [c[:n].cpu() for c in coords]
+    fl, mk = ups[0][0][:n].cpu(), ups[0][1][:n].cpu()
+    ro.torch_corr_block(f1[:1], f2[:1], [cl[0][:1]], L, r)
+    t0 = time.perf_counter()
+    ro.torch_corr_block(f1, f2, [], L, r)
+    t_build = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ro.torch_corr_block(f1, f2, cl, L, r)
+    t_look = (time.perf_counter() - t0 - t_build) / len(cl)
+    t0 = time.perf_counter()
+    ro.torch_upsample_flow(fl, mk)
+    t_up = time.perf_counter() - t0
+    out["cpu_reference_ops"] = {"threads": torch.get_num_threads(), "samples": n,
+                                "per_sample_us": {"pyramid": t_build / n * 1e6, "lookup_x24": 24 * t_look / n * 1e6,
+                                                  "upsample": t_up / n * 1e6}}
+    out["cpu_reference_ops"]["per_sample_us"]["total_24_iters"] = sum(out["cpu_reference_ops"]["per_sample_us"].values())
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
