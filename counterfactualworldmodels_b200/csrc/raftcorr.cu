@@ -18,6 +18,12 @@
 
 namespace cwm {
 
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------------------------
 // all-pairs correlation: C[b, i, j] = sum_c f1[b, c, i] * f2[b, c, j] / sqrt(D).   fmaps are [B, D, HW] (NCHW), so
 // both operands are contiguous along the output index -> coalesced 16-byte loads with no transposition.
@@ -121,129 +127,199 @@ raft_corr_pool_kernel(const float* __restrict__ in, float* __restrict__ out, lon
 //     position of tap (a, b) is (cx + a - r, cy + b - r), corr.py:38-44 -- note the reference's meshgrid puts the
 //     FIRST window axis on x);
 //   * the warp stages the (2r+4)^2 source window that every tap of the item can touch in shared memory (zero-filled
-//     outside the map = grid_sample's zero padding), 144 loads instead of 4*81;
-//   * every lane then combines 4 corners per tap in ATen's order (nw, ne, sw, se).
-// HBM-bound on the output write (L*(2r+1)^2*4 bytes per pixel); the pyramid reads hit L2.
+//     outside the map = grid_sample's zero padding), 144 loads instead of 4*81; the window of the NEXT item is
+//     already in flight (registers) while the taps of the current one are combined;
+//   * every lane then combines 4 corners per tap in ATen's order (nw, ne, sw, se): 4 LDS + 4 FMUL + 4 FFMA.
+// The radius is a template parameter for RAFT's two values (4: large, 3: small) so the window arithmetic is
+// constant-folded; R = -1 is the generic fallback.  The kernel is issue-bound, not HBM-bound (ncu: DESIGN.md 8).
 // ---------------------------------------------------------------------------------------------
 constexpr int kMaxLevels = 8;
+constexpr int kMaxMapSide = 4096;  // beyond |coord| ~ 2^21 fp32 rounding exceeds a pixel; maps are far smaller
 struct CorrLevels {
   const float* p[kMaxLevels];
   int h[kMaxLevels], w[kMaxLevels];
 };
 
-__device__ __forceinline__ void raft_axis(float c, int tap_off, int size, int* i0, float* w_lo, float* w_hi) {
+// One window offset along one axis -> index of the low corner RELATIVE to the staged window (w0 = its origin) and the
+// two corner weights.  A corner pair that falls outside the staged window can only be a sample far outside the map
+// (see kMaxMapSide), i.e. all zeros in the reference: it gets weight 0 at a harmless index.
+__device__ __forceinline__ void raft_axis(float c, int tap_off, int size, int w0, int ws, int* rel, float* w_lo,
+                                          float* w_hi) {
   // centroid_lvl + delta_lvl (corr.py:42-44)
   const float pos = __fadd_rn(c, static_cast<float>(tap_off));
   // bilinear_sampler: 2*x/(W-1) - 1 (utils.py:64-65)
   const float g = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, pos), static_cast<float>(size - 1)), 1.f);
   // grid_sampler_unnormalize, align_corners=True: ((g + 1) / 2) * (size - 1)
   const float ix = __fmul_rn(__fdiv_rn(__fadd_rn(g, 1.f), 2.f), static_cast<float>(size - 1));
-  if (!(fabsf(ix) < 1.0e8f)) {  // NaN / inf / absurd coordinate: every corner is out of bounds
-    *i0 = -(1 << 28);
-    *w_lo = 0.f;
-    *w_hi = 0.f;
-    return;
+  int r = 0;
+  float lo = 0.f, hi = 0.f;
+  if (fabsf(ix) < 1.0e8f) {  // false for NaN / inf / absurd coordinates: every corner out of bounds
+    const float fl = floorf(ix);
+    const int i0 = static_cast<int>(fl) - w0;
+    if (i0 >= 0 && i0 <= ws - 2) {
+      r = i0;
+      lo = __fsub_rn(__fadd_rn(fl, 1.f), ix);  // (ix_se - ix): weight of the low corner
+      hi = __fsub_rn(ix, fl);                  // (ix - ix_nw): weight of the high corner
+    }
   }
-  const float fl = floorf(ix);
-  *i0 = static_cast<int>(fl);
-  *w_lo = __fsub_rn(__fadd_rn(fl, 1.f), ix);  // (ix_se - ix): weight of the low corner
-  *w_hi = __fsub_rn(ix, fl);                  // (ix - ix_nw): weight of the high corner
+  *rel = r;
+  *w_lo = lo;
+  *w_hi = hi;
 }
 
+template <int R>
 __global__ void __launch_bounds__(256)
-raft_corr_lookup_kernel(const __grid_constant__ CorrLevels lv, int L, int r, const float* __restrict__ coords, long long P, int HW,
-                        float* __restrict__ out) {
-  extern __shared__ float smem[];
+raft_corr_lookup_kernel(const __grid_constant__ CorrLevels lv, int L, int r_rt, const float* __restrict__ coords,
+                        long long P, int HW, float* __restrict__ out) {
+  extern __shared__ __align__(16) float smem[];
+  const int r = (R >= 0) ? R : r_rt;
   const int n1 = 2 * r + 1, n2 = n1 * n1, nch = L * n2;
-  const int WS = 2 * r + 4;
-  float* tile = smem;                                   // [nch][33]
-  float* wbase = tile + static_cast<size_t>(nch) * 33;  // per warp: window WS*WS, then 6 arrays of n1
+  const int WS = 2 * r + 4, WW = WS * WS;
+  constexpr int kWinRounds = (R >= 0) ? ((2 * R + 4) * (2 * R + 4) + 31) / 32 : 11;  // r <= 7: 18*18 / 32
+  constexpr int kTapRounds = (R >= 0) ? ((2 * R + 1) * (2 * R + 1) + 31) / 32 : 8;   // r <= 7: 15*15 / 32
+  float* tile = smem;  // [nch][33]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int per_warp = WS * WS + 6 * n1;
-  float* win = wbase + warp * per_warp;
-  int* xi = reinterpret_cast<int*>(win + WS * WS);
-  float* xlo = reinterpret_cast<float*>(xi + n1);
-  float* xhi = xlo + n1;
-  int* yi = reinterpret_cast<int*>(xhi + n1);
-  float* ylo = reinterpret_cast<float*>(yi + n1);
-  float* yhi = ylo + n1;
+  // per warp: the staged window (WW floats, padded to 16 bytes), then 2 x 16 axis entries {rel index, w_lo, w_hi, -}
+  const int per_warp = ((WW + 3) & ~3) + 128;
+  float* win = smem + ((nch * 33 + 3) & ~3) + warp * per_warp;
+  float4* ax = reinterpret_cast<float4*>(win + ((WW + 3) & ~3));
   const long long p0 = static_cast<long long>(blockIdx.x) * 32;
 
-  for (int item = warp; item < 32 * L; item += 8) {
-    const int pix = item & 31, lvl = item >> 5;
-    const long long p = p0 + pix;
-    if (p >= P) continue;  // warp-uniform
-    const long long b = p / HW;
-    const int hw = static_cast<int>(p - b * HW);
-    const float scale = 1.f / static_cast<float>(1 << lvl);  // coords / 2**i (exact)
-    const float cx = __ldg(coords + (b * 2) * HW + hw) * scale;
-    const float cy = __ldg(coords + (b * 2 + 1) * HW + hw) * scale;
-    const int Hl = lv.h[lvl], Wl = lv.w[lvl];
-    const float* src = lv.p[lvl] + p * (static_cast<long long>(Hl) * Wl);
+  // lane-constant index arithmetic, done once: the pixel this lane owns in the write phase (and whose centre it
+  // broadcasts), the window elements it stages and the taps it combines
+  const long long my_p = p0 + lane;
+  const bool my_valid = my_p < P;
+  const long long my_b = my_valid ? my_p / HW : 0;
+  const int my_hw = static_cast<int>(my_p - my_b * HW);
+  float my_cx = 0.f, my_cy = 0.f;
+  if (my_valid) {
+    my_cx = __ldg(coords + (my_b * 2) * HW + my_hw);
+    my_cy = __ldg(coords + (my_b * 2 + 1) * HW + my_hw);
+  }
+  int win_yx[kWinRounds];  // (wy << 16) | wx; elements past the window get a row far outside any map
+#pragma unroll
+  for (int q = 0; q < kWinRounds; ++q) {
+    const int e = lane + 32 * q;
+    const int wy = e / WS;
+    win_yx[q] = (e < WW) ? ((wy << 16) | (e - wy * WS)) : (0x4000 << 16);
+  }
+  int tap_ab[kTapRounds];  // (a << 8) | b, a: x offset index, b: y offset index; -1 past the last tap
+#pragma unroll
+  for (int t = 0; t < kTapRounds; ++t) {
+    const int k = lane + 32 * t;
+    const int a = k / n1;
+    tap_ab[t] = (k < n2) ? ((a << 8) | (k - a * n1)) : -1;
+  }
+
+  // state of the item whose window is in flight: pixel warp + 8*f_q, level f_lvl
+  float pre[kWinRounds];
+  float f_cx = 0.f, f_cy = 0.f;
+  int f_wx0 = 0, f_wy0 = 0, f_Hl = 2, f_Wl = 2, f_q = 0, f_lvl = 0;
+  bool f_live = false;
+  auto prefetch = [&]() {
+    f_live = false;
+    if (f_q >= 4) return;
+    const int pix = warp + 8 * f_q;
+    if (p0 + pix >= P) return;  // warp-uniform
+    f_live = true;
+    const float scale = 1.f / static_cast<float>(1 << f_lvl);  // coords / 2**i (exact)
+    f_cx = __shfl_sync(0xffffffffu, my_cx, pix) * scale;
+    f_cy = __shfl_sync(0xffffffffu, my_cy, pix) * scale;
+    f_Hl = lv.h[f_lvl];
+    f_Wl = lv.w[f_lvl];
+    const float* src = lv.p[f_lvl] + (p0 + pix) * (static_cast<long long>(f_Hl) * f_Wl);
     // window origin; clamped so absurd coordinates cannot overflow the int conversion
-    const int wx0 = static_cast<int>(floorf(fminf(fmaxf(cx, -1.0e6f), 1.0e6f))) - r - 1;
-    const int wy0 = static_cast<int>(floorf(fminf(fmaxf(cy, -1.0e6f), 1.0e6f))) - r - 1;
-    if (lane < n1) {
-      raft_axis(cx, lane - r, Wl, &xi[lane], &xlo[lane], &xhi[lane]);
-    } else if (lane >= 16 && lane < 16 + n1) {
-      const int t = lane - 16;
-      raft_axis(cy, t - r, Hl, &yi[t], &ylo[t], &yhi[t]);
+    f_wx0 = static_cast<int>(floorf(fminf(fmaxf(f_cx, -1.0e6f), 1.0e6f))) - r - 1;
+    f_wy0 = static_cast<int>(floorf(fminf(fmaxf(f_cy, -1.0e6f), 1.0e6f))) - r - 1;
+#pragma unroll
+    for (int q = 0; q < kWinRounds; ++q) {
+      const int gy = f_wy0 + (win_yx[q] >> 16), gx = f_wx0 + (win_yx[q] & 0xffff);
+      const bool in = static_cast<unsigned>(gy) < static_cast<unsigned>(f_Hl) &&
+                      static_cast<unsigned>(gx) < static_cast<unsigned>(f_Wl);
+      pre[q] = in ? __ldg(src + gy * f_Wl + gx) : 0.f;
     }
-    for (int e = lane; e < WS * WS; e += 32) {
-      const int wy = e / WS, wx = e - wy * WS;
-      const int gy = wy0 + wy, gx = wx0 + wx;
-      win[e] = (gy >= 0 && gy < Hl && gx >= 0 && gx < Wl) ? __ldg(src + gy * Wl + gx) : 0.f;
+  };
+
+  prefetch();
+  for (int it = 0; it < 4 * L; ++it) {
+    const bool cur = f_live;
+    const int tile_off = f_lvl * n2 * 33 + warp + 8 * f_q;
+    if (cur) {
+#pragma unroll
+      for (int q = 0; q < kWinRounds; ++q)
+        if (lane + 32 * q < WW) win[lane + 32 * q] = pre[q];
+      // lanes 0..2r: the x arithmetic of the 2r+1 offsets, lanes 16..16+2r: the y arithmetic (one pass, no divergence)
+      const int sel = lane >> 4, t = lane & 15;
+      if (t < n1) {
+        int rel;
+        float lo, hi;
+        raft_axis(sel ? f_cy : f_cx, t - r, sel ? f_Hl : f_Wl, sel ? f_wy0 : f_wx0, WS, &rel, &lo, &hi);
+        ax[lane] = make_float4(__int_as_float(sel ? rel * WS : rel), lo, hi, 0.f);
+      }
     }
     __syncwarp();
-    auto at = [&](int gy, int gx) -> float {
-      const int ry = gy - wy0, rx = gx - wx0;
-      if (ry >= 0 && ry < WS && rx >= 0 && rx < WS) return win[ry * WS + rx];
-      // outside the staged window (only when |coords| is so large that fp32 rounding exceeds a pixel)
-      return (gy >= 0 && gy < Hl && gx >= 0 && gx < Wl) ? __ldg(src + gy * Wl + gx) : 0.f;
-    };
-    for (int k = lane; k < n2; k += 32) {
-      const int a = k / n1, bb = k - a * n1;  // a: x offset, bb: y offset
-      const int x0 = xi[a], y0 = yi[bb];
-      float acc = 0.f;
-      acc = fmaf(at(y0, x0), __fmul_rn(xlo[a], ylo[bb]), acc);          // nw
-      acc = fmaf(at(y0, x0 + 1), __fmul_rn(xhi[a], ylo[bb]), acc);      // ne
-      acc = fmaf(at(y0 + 1, x0), __fmul_rn(xlo[a], yhi[bb]), acc);      // sw
-      acc = fmaf(at(y0 + 1, x0 + 1), __fmul_rn(xhi[a], yhi[bb]), acc);  // se
-      tile[(lvl * n2 + k) * 33 + pix] = acc;
+    if (++f_lvl == L) {  // all levels of one pixel in a row, then the warp's next pixel
+      f_lvl = 0;
+      ++f_q;
+    }
+    prefetch();  // global loads of the next window overlap the taps below
+    if (cur) {
+#pragma unroll
+      for (int t = 0; t < kTapRounds; ++t) {
+        if (tap_ab[t] >= 0) {
+          const float4 X = ax[tap_ab[t] >> 8], Y = ax[16 + (tap_ab[t] & 0xff)];
+          const float* w = win + __float_as_int(Y.x) + __float_as_int(X.x);
+          float acc = 0.f;
+          acc = fmaf(w[0], __fmul_rn(X.y, Y.y), acc);       // nw
+          acc = fmaf(w[1], __fmul_rn(X.z, Y.y), acc);       // ne
+          acc = fmaf(w[WS], __fmul_rn(X.y, Y.z), acc);      // sw
+          acc = fmaf(w[WS + 1], __fmul_rn(X.z, Y.z), acc);  // se
+          tile[tile_off + (lane + 32 * t) * 33] = acc;
+        }
+      }
     }
     __syncwarp();
   }
   __syncthreads();
-  const long long p = p0 + lane;
-  if (p < P) {
-    const long long b = p / HW;
-    const int hw = static_cast<int>(p - b * HW);
-    float* dst = out + b * static_cast<long long>(nch) * HW + hw;
+  if (my_valid) {
+    float* dst = out + my_b * static_cast<long long>(nch) * HW + my_hw;
     for (int ch = warp; ch < nch; ch += 8) dst[static_cast<long long>(ch) * HW] = tile[ch * 33 + lane];
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // convex upsampling (raft_model.py:175-186): out[n, c, 8y+i, 8x+j] = sum_k softmax_k(mask[n, k*64 + i*8 + j, y, x]) *
-// 8*flow[n, c, y + k/3 - 1, x + k%3 - 1] (zero padded).  One CTA per (n, y, 32-column slab): the 576 mask rows of the
-// slab are staged in shared memory (pitch 36 keeps the j-fastest reads conflict-free), every thread produces
-// outputs with j fastest so each warp writes one 128-byte row segment.  HBM-bound: reads 576*4 B, writes 64*C*4 B per
-// 1/8-resolution pixel.
+// 8*flow[n, c, y + k/3 - 1, x + k%3 - 1] (zero padded).  One CTA per (n, y, 32-column slab, half of the 8 sub-rows):
+// its 288 mask rows are streamed into shared memory with 16-byte cp.async (no register staging, all in flight at
+// once; pitch 36 keeps the j-fastest reads conflict-free), every thread produces outputs with j fastest so each warp
+// writes one 128-byte row segment.  HBM-bound: reads 576*4 B, writes 64*C*4 B per 1/8-resolution pixel.
 // ---------------------------------------------------------------------------------------------
 constexpr int kUpPitch = 36;
+constexpr int kUpRows = 9 * 32;  // 9 neighbours x 4 sub-rows x 8 sub-columns
 __global__ void __launch_bounds__(256)
-raft_upsample_kernel(const float* __restrict__ flow, const float* __restrict__ mask, int C, int H, int W,
+raft_upsample_kernel(const float* __restrict__ flow, const float* __restrict__ mask, int C, int H, int W, int vec_ok,
                      float* __restrict__ out) {
-  extern __shared__ float smem[];
-  float* m_s = smem;                   // [576][36]
-  float* f_s = smem + 576 * kUpPitch;  // [C][3][34]
-  const int n = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * 32;
+  extern __shared__ __align__(16) float smem[];
+  float* m_s = smem;                       // [288][36]: row k*32 + il*8 + j
+  float* f_s = smem + kUpRows * kUpPitch;  // [C][3][34]
+  const int n = blockIdx.z, y = blockIdx.y, x0 = (blockIdx.x >> 1) * 32, ih = blockIdx.x & 1;
   const int XW = min(32, W - x0);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t HWs = static_cast<size_t>(H) * W;
   const float* mrow = mask + (static_cast<size_t>(n) * 576) * HWs + static_cast<size_t>(y) * W + x0;
-  if (lane < XW)
-    for (int row = warp; row < 576; row += 8) m_s[row * kUpPitch + lane] = __ldg(mrow + row * HWs + lane);
+  if (vec_ok) {  // W % 4 == 0 and 16-byte aligned base: XW % 4 == 0 too
+    const int cpr = XW >> 2, total = kUpRows * cpr;
+    for (int c = threadIdx.x; c < total; c += 256) {
+      const int row = c / cpr, col = c - row * cpr;
+      const int k = row >> 5, rest = row & 31;
+      cp_async_16(m_s + row * kUpPitch + col * 4, mrow + (k * 64 + ih * 32 + rest) * HWs + col * 4);
+    }
+    cp_async_commit();
+  } else {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane < XW)
+      for (int row = warp; row < kUpRows; row += 8)
+        m_s[row * kUpPitch + lane] = __ldg(mrow + ((row >> 5) * 64 + ih * 32 + (row & 31)) * HWs + lane);
+  }
   for (int e = threadIdx.x; e < C * 3 * 34; e += 256) {
     const int xx = e % 34, t = e / 34, dy = t % 3, c = t / 3;
     const int gy = y + dy - 1, gx = x0 + xx - 1;
@@ -252,16 +328,17 @@ raft_upsample_kernel(const float* __restrict__ flow, const float* __restrict__ m
       v = __fmul_rn(8.f, __ldg(flow + (static_cast<size_t>(n) * C + c) * HWs + static_cast<size_t>(gy) * W + gx));
     f_s[e] = v;
   }
+  if (vec_ok) cp_async_wait_all();
   __syncthreads();
   const int per_row = 8 * XW;
-  for (int t = threadIdx.x; t < 8 * per_row; t += 256) {
-    const int i = t / per_row, rem = t - i * per_row;
+  for (int t = threadIdx.x; t < 4 * per_row; t += 256) {
+    const int il = t / per_row, rem = t - il * per_row;
     const int x = rem >> 3, j = rem & 7;
     float m[9];
     float mx = -INFINITY;
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
-      m[k] = m_s[(k * 64 + i * 8 + j) * kUpPitch + x];
+      m[k] = m_s[(k * 32 + il * 8 + j) * kUpPitch + x];
       mx = fmaxf(mx, m[k]);
     }
     float sum = 0.f;
@@ -270,8 +347,10 @@ raft_upsample_kernel(const float* __restrict__ flow, const float* __restrict__ m
       m[k] = expf(m[k] - mx);
       sum += m[k];
     }
+    const float inv = __fdiv_rn(1.f, sum);
 #pragma unroll
-    for (int k = 0; k < 9; ++k) m[k] = __fdiv_rn(m[k], sum);
+    for (int k = 0; k < 9; ++k) m[k] *= inv;
+    const int i = ih * 4 + il;
     for (int c = 0; c < C; ++c) {
       const float* fc = f_s + c * 3 * 34;
       float acc = 0.f;
@@ -350,14 +429,16 @@ extern "C" int cwm_raft_corr_lookup(const float* const* levels, int num_levels, 
     lv.p[l] = levels[l];
   }
   const int n1 = 2 * radius + 1, nch = num_levels * n1 * n1, WS = 2 * radius + 4;
-  const size_t smem = (static_cast<size_t>(nch) * 33 + 8 * (WS * WS + 6 * n1)) * sizeof(float);
+  const size_t smem = (static_cast<size_t>((nch * 33 + 3) & ~3) + 8 * (((WS * WS + 3) & ~3) + 128)) * sizeof(float);
   CWM_REQUIRE(smem <= 200 * 1024, "cwm_raft_corr_lookup: %d levels x radius %d needs %zu bytes of shared memory", num_levels,
               radius, smem);
-  static size_t configured = 0;  // grow-only opt-in for > 48 KB of dynamic shared memory
-  if (smem > configured) {
-    CWM_CUDA_CHECK(cudaFuncSetAttribute(raft_corr_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(smem)));
-    configured = smem;
+  CWM_REQUIRE(H <= kMaxMapSide && W <= kMaxMapSide, "cwm_raft_corr_lookup: map (%d,%d) larger than %d", H, W, kMaxMapSide);
+  auto kernel = radius == 4 ? raft_corr_lookup_kernel<4> : radius == 3 ? raft_corr_lookup_kernel<3> : raft_corr_lookup_kernel<-1>;
+  static size_t configured[3] = {0, 0, 0};  // grow-only opt-in for > 48 KB of dynamic shared memory, per instantiation
+  size_t& conf = configured[radius == 4 ? 0 : radius == 3 ? 1 : 2];
+  if (smem > conf) {
+    CWM_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    conf = smem;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long P = static_cast<long long>(B) * H * W;
@@ -367,8 +448,7 @@ extern "C" int cwm_raft_corr_lookup(const float* const* levels, int num_levels, 
     pyr += static_cast<double>(ws) * hs;
   }
   ProfileScope prof(st, "raft_corr_lookup", 0.0, static_cast<double>(P) * (nch + pyr + 2.0) * 4.0);
-  raft_corr_lookup_kernel<<<static_cast<unsigned>((P + 31) / 32), 256, smem, st>>>(lv, num_levels, radius, coords, P, H * W,
-                                                                                  out);
+  kernel<<<static_cast<unsigned>((P + 31) / 32), 256, smem, st>>>(lv, num_levels, radius, coords, P, H * W, out);
   CWM_LAUNCH_CHECK();
   return CWM_OK;
 }
@@ -380,7 +460,7 @@ extern "C" int cwm_raft_upsample_flow(const float* flow, const float* mask, int 
   if (N == 0) return CWM_OK;
   CWM_REQUIRE(flow && mask && out, "cwm_raft_upsample_flow: null pointer");
   CWM_REQUIRE(N <= 65535 && H <= 65535, "cwm_raft_upsample_flow: N=%d / H=%d exceed the grid limits", N, H);
-  const size_t smem = (576 * kUpPitch + static_cast<size_t>(C) * 3 * 34) * sizeof(float);
+  const size_t smem = (kUpRows * kUpPitch + static_cast<size_t>(C) * 3 * 34) * sizeof(float);
   static size_t configured = 0;
   if (smem > configured) {
     CWM_CUDA_CHECK(cudaFuncSetAttribute(raft_upsample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -388,8 +468,9 @@ extern "C" int cwm_raft_upsample_flow(const float* flow, const float* mask, int 
     configured = smem;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int vec_ok = (W % 4 == 0) && (reinterpret_cast<uintptr_t>(mask) % 16 == 0);
   ProfileScope prof(st, "raft_upsample", 0.0, static_cast<double>(N) * H * W * (576.0 + C + 64.0 * C) * 4.0);
-  raft_upsample_kernel<<<dim3((W + 31) / 32, H, N), 256, smem, st>>>(flow, mask, C, H, W, out);
+  raft_upsample_kernel<<<dim3(2 * ((W + 31) / 32), H, N), 256, smem, st>>>(flow, mask, C, H, W, vec_ok, out);
   CWM_LAUNCH_CHECK();
   return CWM_OK;
 }
