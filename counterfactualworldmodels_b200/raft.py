@@ -106,3 +106,398 @@ def use_in_reference(raft_model_module):
     raft_model_module.CorrBlock = CorrBlock
     raft_model_module.RAFT.upsample_flow = lambda self, flow, mask: upsample_flow(flow, mask)
     return old
+
+
+# ======================================================================================================
+# The network around those stages.  RAFT's convolutions are cuDNN calls from torch (library code, like cuBLAS for a
+# plain GEMM); the module tree below only exists so that (a) the published ``raft-large.pth`` / ``raft-small.pth``
+# checkpoints load unchanged (same parameter names and shapes as cwm/models/raft/{extractor,update,raft_model}.py),
+# (b) seeded random init reproduces the reference's (same construction order; pinned by tests/golden/raft_e2e_*.npz),
+# and (c) ``FlowGenerator(flow_model=raft.RAFT(...))`` works on a B200 with the correlation block, the lookups of all
+# GRU iterations and the convex upsampling on the kernels above.
+# ======================================================================================================
+import argparse  # noqa: E402
+import os  # noqa: E402
+
+import torch.nn as nn  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+
+def _make_norm(kind, channels, groups):
+    if kind == 'group':
+        return nn.GroupNorm(num_groups=groups, num_channels=channels)
+    if kind == 'batch':
+        return nn.BatchNorm2d(channels)
+    if kind == 'instance':
+        return nn.InstanceNorm2d(channels)
+    assert kind == 'none', kind
+    return nn.Sequential()
+
+
+def _init_encoder(module):
+    """extractor.py:151-158 / :229-236: He-normal conv weights (biases keep torch's default draw), unit norms."""
+    for m in module.modules():
+        if isinstance(m, nn.Conv2d):
+            nn.init.kaiming_normal_(m.weight, mode='fan_out', nonlinearity='relu')
+        elif isinstance(m, (nn.BatchNorm2d, nn.InstanceNorm2d, nn.GroupNorm)):
+            if m.weight is not None:
+                nn.init.constant_(m.weight, 1)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+
+
+class _EncoderBlock(nn.Module):
+    """``ResidualBlock`` (widths (p, p), kernels (3, 3); extractor.py:6-56) and ``BottleneckBlock`` (widths
+    (p/4, p/4, p), kernels (1, 3, 1); :60-115) are the same pattern: conv-norm-relu chain, strided conv in the
+    position ``strided``, optional 1x1 strided shortcut whose norm is ALSO registered as ``norm<k+1>``."""
+
+    def __init__(self, in_planes, widths, kernels, strided, norm_fn, stride):
+        super().__init__()
+        planes = widths[-1]
+        chain = [in_planes] + list(widths)
+        for i, k in enumerate(kernels):
+            setattr(self, f"conv{i + 1}", nn.Conv2d(chain[i], chain[i + 1], kernel_size=k, padding=k // 2,
+                                                    stride=stride if i == strided else 1))
+        self.relu = nn.ReLU(inplace=True)
+        self.depth = len(kernels)
+        for i, w in enumerate(widths):
+            setattr(self, f"norm{i + 1}", _make_norm(norm_fn, w, planes // 8))
+        self.downsample = None
+        if stride != 1:
+            shortcut_norm = _make_norm(norm_fn, planes, planes // 8)
+            setattr(self, f"norm{self.depth + 1}", shortcut_norm)
+            self.downsample = nn.Sequential(nn.Conv2d(in_planes, planes, kernel_size=1, stride=stride), shortcut_norm)
+
+    def forward(self, x):
+        y = x
+        for i in range(1, self.depth + 1):
+            y = self.relu(getattr(self, f"norm{i}")(getattr(self, f"conv{i}")(y)))
+        if self.downsample is not None:
+            x = self.downsample(x)
+        return self.relu(x + y)
+
+
+class ResidualBlock(_EncoderBlock):
+    def __init__(self, in_planes, planes, norm_fn='group', stride=1):
+        super().__init__(in_planes, (planes, planes), (3, 3), 0, norm_fn, stride)
+
+
+class BottleneckBlock(_EncoderBlock):
+    def __init__(self, in_planes, planes, norm_fn='group', stride=1):
+        super().__init__(in_planes, (planes // 4, planes // 4, planes), (1, 3, 1), 1, norm_fn, stride)
+
+
+class _Encoder(nn.Module):
+    """1/8-resolution feature pyramid: 7x7/2 stem, three 2-block stages (strides 1, 2, 2), 1x1 projection.
+    ``BasicEncoder`` (extractor.py:117-190) and ``SmallEncoder`` (:193-267) differ in widths and block type."""
+
+    block = None
+    widths = None
+
+    def __init__(self, output_dim=128, norm_fn='batch', dropout=0.0):
+        super().__init__()
+        self.norm_fn = norm_fn
+        stem = self.widths[0]
+        self.norm1 = _make_norm(norm_fn, stem, 8)
+        self.conv1 = nn.Conv2d(3, stem, kernel_size=7, stride=2, padding=3)
+        self.relu1 = nn.ReLU(inplace=True)
+        self.in_planes = stem
+        for i, (w, s) in enumerate(zip(self.widths, (1, 2, 2))):
+            setattr(self, f"layer{i + 1}", self._make_layer(w, stride=s))
+        self.dropout = None
+        if type(self).dropout_first:
+            self.dropout = nn.Dropout2d(p=dropout) if dropout > 0 else None
+            self.conv2 = nn.Conv2d(self.widths[-1], output_dim, kernel_size=1)
+        else:
+            self.conv2 = nn.Conv2d(self.widths[-1], output_dim, kernel_size=1)
+            self.dropout = nn.Dropout2d(p=dropout) if dropout > 0 else None
+        _init_encoder(self)
+
+    def _make_layer(self, dim, stride=1):
+        blocks = (self.block(self.in_planes, dim, self.norm_fn, stride=stride), self.block(dim, dim, self.norm_fn, stride=1))
+        self.in_planes = dim
+        return nn.Sequential(*blocks)
+
+    def forward(self, x):
+        pair = isinstance(x, (tuple, list))  # both frames in one batch (raft_model.py:221-222)
+        if pair:
+            n = x[0].shape[0]
+            x = torch.cat(x, dim=0)
+        x = self.relu1(self.norm1(self.conv1(x)))
+        x = self.conv2(self.layer3(self.layer2(self.layer1(x))))
+        if self.training and self.dropout is not None:
+            x = self.dropout(x)
+        return torch.split(x, [n, n], dim=0) if pair else x
+
+
+class BasicEncoder(_Encoder):
+    block, widths, dropout_first = ResidualBlock, (64, 96, 128), False
+
+
+class SmallEncoder(_Encoder):
+    block, widths, dropout_first = BottleneckBlock, (32, 64, 96), True
+
+
+class FlowHead(nn.Module):
+    """update.py:6-14."""
+
+    def __init__(self, input_dim=128, hidden_dim=256):
+        super().__init__()
+        self.conv1 = nn.Conv2d(input_dim, hidden_dim, 3, padding=1)
+        self.conv2 = nn.Conv2d(hidden_dim, 2, 3, padding=1)
+        self.relu = nn.ReLU(inplace=True)
+
+    def forward(self, x):
+        return self.conv2(self.relu(self.conv1(x)))
+
+
+def _gru_step(h, x, convz, convr, convq):
+    hx = torch.cat([h, x], dim=1)
+    z = torch.sigmoid(convz(hx))
+    r = torch.sigmoid(convr(hx))
+    q = torch.tanh(convq(torch.cat([r * h, x], dim=1)))
+    return (1 - z) * h + z * q
+
+
+class ConvGRU(nn.Module):
+    """update.py:16-31."""
+
+    def __init__(self, hidden_dim=128, input_dim=192 + 128):
+        super().__init__()
+        for gate in "zrq":
+            setattr(self, "conv" + gate, nn.Conv2d(hidden_dim + input_dim, hidden_dim, 3, padding=1))
+
+    def forward(self, h, x):
+        return _gru_step(h, x, self.convz, self.convr, self.convq)
+
+
+class SepConvGRU(nn.Module):
+    """update.py:33-60: a horizontal (1x5) then a vertical (5x1) GRU step."""
+
+    def __init__(self, hidden_dim=128, input_dim=192 + 128):
+        super().__init__()
+        for idx, (k, p) in enumerate((((1, 5), (0, 2)), ((5, 1), (2, 0))), start=1):
+            for gate in "zrq":
+                setattr(self, f"conv{gate}{idx}", nn.Conv2d(hidden_dim + input_dim, hidden_dim, k, padding=p))
+
+    def forward(self, h, x):
+        h = _gru_step(h, x, self.convz1, self.convr1, self.convq1)
+        return _gru_step(h, x, self.convz2, self.convr2, self.convq2)
+
+
+class SmallMotionEncoder(nn.Module):
+    """update.py:62-77."""
+
+    def __init__(self, args):
+        super().__init__()
+        cor_planes = args.corr_levels * (2 * args.corr_radius + 1) ** 2
+        self.convc1 = nn.Conv2d(cor_planes, 96, 1, padding=0)
+        self.convf1 = nn.Conv2d(2, 64, 7, padding=3)
+        self.convf2 = nn.Conv2d(64, 32, 3, padding=1)
+        self.conv = nn.Conv2d(128, 80, 3, padding=1)
+
+    def forward(self, flow, corr):
+        cor = F.relu(self.convc1(corr))
+        flo = F.relu(self.convf2(F.relu(self.convf1(flow))))
+        return torch.cat([F.relu(self.conv(torch.cat([cor, flo], dim=1))), flow], dim=1)
+
+
+class BasicMotionEncoder(nn.Module):
+    """update.py:79-98."""
+
+    def __init__(self, args):
+        super().__init__()
+        cor_planes = args.corr_levels * (2 * args.corr_radius + 1) ** 2
+        self.convc1 = nn.Conv2d(cor_planes, 256, 1, padding=0)
+        self.convc2 = nn.Conv2d(256, 192, 3, padding=1)
+        self.convf1 = nn.Conv2d(2, 128, 7, padding=3)
+        self.convf2 = nn.Conv2d(128, 64, 3, padding=1)
+        self.conv = nn.Conv2d(64 + 192, 128 - 2, 3, padding=1)
+
+    def forward(self, flow, corr):
+        cor = F.relu(self.convc2(F.relu(self.convc1(corr))))
+        flo = F.relu(self.convf2(F.relu(self.convf1(flow))))
+        return torch.cat([F.relu(self.conv(torch.cat([cor, flo], dim=1))), flow], dim=1)
+
+
+class SmallUpdateBlock(nn.Module):
+    """update.py:100-113."""
+
+    def __init__(self, args, hidden_dim=96):
+        super().__init__()
+        self.encoder = SmallMotionEncoder(args)
+        self.gru = ConvGRU(hidden_dim=hidden_dim, input_dim=82 + 64)
+        self.flow_head = FlowHead(hidden_dim, hidden_dim=128)
+
+    def forward(self, net, inp, corr, flow):
+        net = self.gru(net, torch.cat([inp, self.encoder(flow, corr)], dim=1))
+        return net, None, self.flow_head(net)
+
+
+class BasicUpdateBlock(nn.Module):
+    """update.py:115-139; the upsampling logits are scaled by 0.25 ("to balance gradients", :137)."""
+
+    def __init__(self, args, hidden_dim=128, input_dim=128):
+        super().__init__()
+        self.args = args
+        self.encoder = BasicMotionEncoder(args)
+        self.gru = SepConvGRU(hidden_dim=hidden_dim, input_dim=128 + hidden_dim)
+        self.flow_head = FlowHead(hidden_dim, hidden_dim=256)
+        self.mask = nn.Sequential(nn.Conv2d(128, 256, 3, padding=1), nn.ReLU(inplace=True),
+                                  nn.Conv2d(256, 64 * 9, 1, padding=0))
+
+    def forward(self, net, inp, corr, flow, upsample=True):
+        net = self.gru(net, torch.cat([inp, self.encoder(flow, corr)], dim=1))
+        return net, (.25 * self.mask(net) if upsample else None), self.flow_head(net)
+
+
+def get_args(cmd=None):
+    """raft_model.py:36-51 (same option names and defaults)."""
+    parser = argparse.ArgumentParser()
+    parser.add_argument('--corr_levels', type=int, default=4)
+    parser.add_argument('--corr_radius', type=int, default=4)
+    parser.add_argument('--output_dim', type=int, default=None)
+    parser.add_argument('--iters', type=int, default=None)
+    parser.add_argument('--dropout', type=float, default=0.0)
+    parser.add_argument('--mixed_precision', action='store_true')
+    parser.add_argument('--small', action='store_true')
+    parser.add_argument('--gpus', type=int, nargs='+', default=[0])
+    return parser.parse_args() if cmd is None else parser.parse_args(cmd)
+
+
+def upflow8(flow, mode='bilinear'):
+    """utils.py:88-90 (RAFT-small has no upsampling mask)."""
+    return 8 * F.interpolate(flow, size=(8 * flow.shape[2], 8 * flow.shape[3]), mode=mode, align_corners=True)
+
+
+class RAFT(nn.Module):
+    """``cwm.models.raft.raft_model.RAFT`` (raft_model.py:114-301): same ``args``, attributes (``iters``,
+    ``multiframe``, ``scale_inputs``, ``hidden_dim``, ``context_dim``), parameter names and forward semantics.
+    The correlation pyramid, its per-iteration lookups and the convex upsampling run on ``csrc/raftcorr.cu``; in
+    ``test_mode`` only the last iteration is upsampled (the reference upsamples all of them and returns the last)."""
+
+    def __init__(self, args):
+        super().__init__()
+        self.args = args
+        self.multiframe = getattr(args, 'multiframe', True)
+        self.scale_inputs = getattr(args, 'scale_inputs', True)
+        self._iters = None
+        if getattr(args, 'iters', None) is not None:
+            self.iters = args.iters
+        small = bool(getattr(args, 'small', False))
+        self.hidden_dim = hdim = 96 if small else 128
+        self.context_dim = cdim = 64 if small else 128
+        args.corr_levels = 4
+        args.corr_radius = 3 if small else 4
+        for name, default in (('dropout', 0), ('alternate_corr', False), ('mixed_precision', False), ('output_dim', None)):
+            if not hasattr(args, name):
+                setattr(args, name, default)
+        if args.alternate_corr:
+            raise NotImplementedError("alternate_corr needs the reference's optional alt_cuda_corr extension "
+                                      "(corr.py:5-9); CorrBlock is the supported path")
+        if small:
+            self.fnet = SmallEncoder(output_dim=128, norm_fn='instance', dropout=args.dropout)
+            self.cnet = SmallEncoder(output_dim=hdim + cdim, norm_fn='none', dropout=args.dropout)
+            self.update_block = SmallUpdateBlock(args, hidden_dim=hdim)
+        else:
+            self.fnet = BasicEncoder(output_dim=256, norm_fn='instance', dropout=args.dropout)
+            self.cnet = BasicEncoder(output_dim=hdim + cdim, norm_fn='batch', dropout=args.dropout)
+            self.update_block = BasicUpdateBlock(args, hidden_dim=hdim)
+        self.output_block = None
+        if args.output_dim is not None:
+            self.output_block = nn.Sequential(nn.Conv2d(hdim, 192 if small else 256, 3, padding=1), nn.ReLU(inplace=True),
+                                              nn.Conv2d(192 if small else 256, args.output_dim, 1, padding=0))
+
+    @property
+    def iters(self):
+        return getattr(self, '_iters', None)
+
+    @iters.setter
+    def iters(self, value=None):
+        self._iters = value
+
+    def freeze_bn(self):
+        for m in self.modules():
+            if isinstance(m, nn.BatchNorm2d):
+                m.eval()
+
+    def initialize_flow(self, img):
+        N, _, H, W = img.shape
+        grid = coords_grid(N, H // 8, W // 8, device=img.device, dtype=img.dtype)
+        return grid, grid.clone()
+
+    def upsample_flow(self, flow, mask):
+        return upsample_flow(flow, mask)
+
+    def _forward_two_images(self, image1, image2, iters=24, flow_init=None, upsample=True, test_mode=True, **kwargs):
+        """raft_model.py:199-277."""
+        if self.iters is not None:
+            iters = self.iters
+        image1 = (2 * (image1 / 255.0) - 1.0).contiguous()
+        image2 = (2 * (image2 / 255.0) - 1.0).contiguous()
+        amp = self.args.mixed_precision or image1.dtype in (torch.float16, torch.bfloat16)
+        with torch.autocast("cuda", enabled=bool(amp)):
+            fmap1, fmap2 = self.fnet([image1, image2])
+        corr_fn = CorrBlock(fmap1.float(), fmap2.float(), num_levels=self.args.corr_levels, radius=self.args.corr_radius)
+        with torch.autocast("cuda", enabled=bool(amp)):
+            net, inp = torch.split(self.cnet(image1), [self.hidden_dim, self.context_dim], dim=1)
+            net, inp = torch.tanh(net), torch.relu(inp)
+        coords0, coords1 = self.initialize_flow(image1)
+        if flow_init is not None:
+            coords1 = coords1 + flow_init
+        predictions = []
+        flow_up = None
+        for itr in range(iters):
+            coords1 = coords1.detach()
+            corr = corr_fn(coords1)
+            with torch.autocast("cuda", enabled=bool(amp)):
+                net, up_mask, delta_flow = self.update_block(net, inp, corr, coords1 - coords0)
+            coords1 = coords1 + delta_flow
+            if test_mode and itr + 1 < iters:
+                continue
+            out = self.output_block(net) if self.output_block is not None else coords1 - coords0
+            flow_up = upflow8(out) if up_mask is None else self.upsample_flow(out, up_mask)
+            predictions.append(flow_up)
+        if test_mode:
+            return coords1 - coords0, flow_up
+        return predictions
+
+    def forward(self, *args, **kwargs):
+        """raft_model.py:279-301: ``[B, T, 3, H, W]`` frames in [0, 1] -> flows ``[B, T-1, 2, H, W]``."""
+        if not self.multiframe:
+            return self._forward_two_images(*args, **kwargs)
+        x = (args[0] * 255.0) if self.scale_inputs else args[0]
+        if x.dim() == 4:
+            x = x.unsqueeze(1)
+        assert x.dim() == 5, x.shape
+        if x.size(1) == 1:  # a single frame is repeated
+            x = x.repeat(1, 2, 1, 1, 1)
+        backward = kwargs.get('backward', False)
+        flows = []
+        for t in range(x.size(1) - 1):
+            pair = (x[:, t + 1], x[:, t]) if backward else (x[:, t], x[:, t + 1])
+            flow = self._forward_two_images(*pair, *args[1:], **kwargs)[-1]
+            if backward:
+                flows.insert(0, flow)
+            else:
+                flows.append(flow)
+        return torch.stack(flows, 1)
+
+
+def load_raft_model(load_path=None, ignore_prefix=None, multiframe=True, scale_inputs=True, output_dim=None, **kwargs):
+    """raft_model.py:55-99: builds a RAFT and loads a published checkpoint (``module.`` prefixes stripped)."""
+    if ((load_path is None) or (not os.path.exists(load_path))) and (output_dim is None):
+        raise ValueError(f"{load_path} is not a valid raft checkpoint (the reference fetches them with "
+                         "cwm/models/raft/download_raft_checkpoints.sh)")
+    args = get_args("")
+    for k, v in kwargs.items():
+        setattr(args, k, v)
+    args.multiframe, args.scale_inputs, args.output_dim = multiframe, scale_inputs, output_dim
+    model = RAFT(args)
+    if load_path is not None:
+        weights = torch.load(load_path, map_location=torch.device("cpu"))
+        weights = {k.replace('module.', ''): v for k, v in weights.items()}
+        if ignore_prefix is not None:
+            weights = {k.replace(ignore_prefix, ''): v for k, v in weights.items()}
+        print(model.load_state_dict(weights, strict=False), type(model).__name__, load_path)
+    return model

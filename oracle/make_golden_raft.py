@@ -122,6 +122,54 @@ def main():
     print(f"raft_trace_large_128px: {len(rec['coords'])} iterations, fmaps {tuple(f1.shape)}, oracle == reference within "
           f"{worst:.1e} of scale | {os.path.getsize(path) / 1e3:.0f} KB")
 
+    # ---- end to end: the reference's RAFT (seeded random init, eval) on a seeded frame pair ---------------------
+    from counterfactualworldmodels_b200 import raft as mirror
+    for small in (False, True):
+        name = "raft_e2e_small_128px" if small else "raft_e2e_large_128px"
+        torch.manual_seed(0)
+        args = ref_raft.get_args("")
+        args.multiframe, args.scale_inputs, args.output_dim, args.small = True, True, None, small
+        model = ref_raft.RAFT(args).eval().requires_grad_(False)
+        torch.manual_seed(0)
+        margs = mirror.get_args("")
+        margs.multiframe, margs.scale_inputs, margs.output_dim, margs.small = True, True, None, small
+        twin = mirror.RAFT(margs)
+        sd, sd_twin = model.state_dict(), twin.state_dict()
+        assert list(sd.keys()) == list(sd_twin.keys()) and all(torch.equal(sd[k], sd_twin[k]) for k in sd), name
+        x = e2e_frames(2, 128)
+        model.iters = E2E_ITERS
+        with torch.no_grad():
+            fwd = model(x)
+            bwd = model(x, backward=True)
+        assert fwd.shape == (2, 1, 2, 128, 128)
+        path = os.path.join(GOLDEN_DIR, name + ".npz")
+        np.savez_compressed(path, flow_fwd=fwd.numpy(), flow_bwd=bwd.numpy()[:, :, :, ::2, ::2],
+                            init_checksum=np.array(state_checksum(sd)), n_tensors=np.array(len(sd)),
+                            iters=np.array(E2E_ITERS))
+        print(f"{name}: |flow| max {fwd.abs().max():.3f} mean {fwd.abs().mean():.3f}; mirror init == reference init "
+              f"({len(sd)} tensors) | {os.path.getsize(path) / 1e3:.0f} KB")
+
+
+E2E_ITERS = 4
+
+
+def e2e_frames(B, side):
+    """Seeded [B, 2, 3, side, side] frame pair in [0, 1]: smooth random texture, second frame shifted by (3, -5) px."""
+    g = torch.Generator().manual_seed(21)
+    base = torch.rand(B, 3, side // 4, side // 4, generator=g)
+    f0 = torch.nn.functional.interpolate(base, size=(side, side), mode="bilinear", align_corners=False)
+    f0 = (f0 + 0.1 * torch.rand(B, 3, side, side, generator=g)).clamp(0, 1)
+    f1 = torch.roll(f0, shifts=(3, -5), dims=(2, 3))
+    return torch.stack([f0, f1], dim=1)
+
+
+def state_checksum(sd):
+    """Order-sensitive fp64 checksum of a state_dict (a different init order or draw changes it)."""
+    total = 0.0
+    for i, (k, v) in enumerate(sd.items()):
+        total += (i + 1) * float(v.double().abs().sum()) + float(v.double().sum())
+    return total
+
 
 if __name__ == "__main__":
     main()

@@ -246,3 +246,74 @@ def test_torch_port_used_as_cpu_baseline_agrees_with_the_oracle():
     flow, mask = ro.make_upsample_inputs(1, 2, 4, 7, 2)
     up = ro.torch_upsample_flow(torch.from_numpy(flow), torch.from_numpy(mask)).numpy()
     assert rel_err(up, ro.upsample_flow(flow, mask)) <= ORACLE_TOL
+
+
+# ------------------------------------------------------------------------------------------------ the network
+def _mirror(small):
+    from counterfactualworldmodels_b200 import raft
+    torch.manual_seed(0)
+    args = raft.get_args("")
+    args.multiframe, args.scale_inputs, args.output_dim, args.small = True, True, None, small
+    return raft.RAFT(args).eval().requires_grad_(False)
+
+
+@pytest.mark.parametrize("small", [False, True])
+def test_raft_mirror_reproduces_the_reference_parameters(small):
+    """Same parameter names / shapes / seeded init as the reference's RAFT: the fixture holds an order-sensitive
+    checksum of the REAL reference's state_dict under torch.manual_seed(0) (oracle/make_golden_raft.py)."""
+    import make_golden_raft as mg
+    d = load("raft_e2e_small_128px" if small else "raft_e2e_large_128px")
+    model = _mirror(small)
+    sd = model.state_dict()
+    assert len(sd) == int(d["n_tensors"])
+    assert mg.state_checksum(sd) == pytest.approx(float(d["init_checksum"]), rel=1e-12)
+    assert sum(p.numel() for p in model.parameters()) == (990162 if small else 5257536)   # RAFT-large: SURVEY 8(c)
+    for key in ("fnet.conv1.weight", "fnet.layer2.0.downsample.0.weight", "cnet.layer3.1.conv2.bias",
+                "update_block.encoder.convc1.weight", "update_block.flow_head.conv2.bias"):
+        assert key in sd
+    if not small:
+        assert "cnet.layer2.0.norm3.running_mean" in sd and "cnet.layer2.0.downsample.1.running_mean" in sd
+        assert tuple(sd["update_block.mask.2.weight"].shape) == (576, 256, 1, 1)
+        assert tuple(sd["update_block.gru.convz1.weight"].shape) == (128, 384, 1, 5)
+
+
+def test_raft_loader_and_flow_generator_wiring():
+    from counterfactualworldmodels_b200 import raft, segmentation, synthetic, vmae
+    with pytest.raises(ValueError, match="not a valid raft checkpoint"):
+        raft.load_raft_model(load_path="/nonexistent/raft-large.pth")
+    with pytest.raises(NotImplementedError):
+        a = raft.get_args("")
+        a.alternate_corr = True
+        raft.RAFT(a)
+    model = raft.load_raft_model(load_path=None, output_dim=3, small=True)     # reference: a new RAFT with an output head
+    assert model.output_block is not None and model.args.corr_radius == 3 and model.iters is None
+    model.iters = 7
+    assert model.iters == 7
+    kw = synthetic.model_kwargs("tiny_4x4")
+    G = segmentation.FlowGenerator(predictor=vmae.PretrainVisionTransformer(**kw), flow_model=_mirror(True))
+    assert isinstance(G.flow_model, raft.RAFT) and not G.flow_model.training
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("small", [False, True])
+def test_gpu_raft_end_to_end_matches_the_reference(small):
+    """The whole flow network (seeded init == the reference's, eval) on a seeded frame pair, forward and backward flow,
+    4 GRU iterations: cuDNN fp32 convolutions (TF32 off) + this repo's correlation / lookup / upsampling kernels against
+    the flows the REAL reference produced on CPU.  Tolerance 2e-3 of the flow scale: fp32 convolutions summed in a
+    different order, fed back through 4 recurrent iterations."""
+    import make_golden_raft as mg
+    d = load("raft_e2e_small_128px" if small else "raft_e2e_large_128px")
+    model = _mirror(small).to(DEV)
+    model.iters = int(d["iters"])
+    x = mg.e2e_frames(2, 128).to(DEV)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        fwd = model(x)
+        bwd = model(x, backward=True)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert tuple(fwd.shape) == (2, 1, 2, 128, 128)
+    e_f, e_b = rel_err(fwd.cpu().numpy(), d["flow_fwd"]), rel_err(bwd.cpu().numpy()[:, :, :, ::2, ::2], d["flow_bwd"])
+    print(f"raft e2e small={small}: fwd {e_f:.2e} bwd {e_b:.2e} of scale")
+    assert e_f <= 2e-3 and e_b <= 2e-3

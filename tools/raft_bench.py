@@ -38,8 +38,43 @@ def profiled(fn, iters=6, warmup=3):
                             flops=e["flops"] / iters, bytes=e["bytes"] / iters) for e in _lib.profile_end()}
 
 
+def e2e(S):
+    """The whole flow network (raft.RAFT, RAFT-large shapes, random init) on S frame pairs of 224 px, 24 iterations:
+    samples/s and how the step splits between this repo's kernels and torch's cuDNN convolutions."""
+    dev = "cuda:0"
+    torch.manual_seed(0)
+    args = raft.get_args("")
+    args.multiframe, args.scale_inputs, args.output_dim = True, True, None
+    model = raft.RAFT(args).eval().requires_grad_(False).to(dev)
+    g = torch.Generator(device=dev).manual_seed(0)
+    x = torch.rand(S, 2, 3, 224, 224, device=dev, generator=g)
+    out = {"mode": "e2e", "S": S, "iters": 24}
+    for name, tf32, amp in (("fp32", False, False), ("tf32_convs", True, False), ("f16_autocast_convs", True, True)):
+        torch.backends.cudnn.allow_tf32 = tf32
+        model.args.mixed_precision = amp
+        for _ in range(2):
+            model(x)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            model(x)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        _lib.profile_begin()
+        model(x)
+        torch.cuda.synchronize()
+        mine = sum(e["ms"] for e in _lib.profile_end())
+        out[name] = {"ms_per_call": ms, "flow_samples_per_s": S / ms * 1e3, "ms_in_libcwm_kernels": mine,
+                     "share_in_libcwm_kernels": mine / ms}
+    print(json.dumps(out))
+
+
 def main():
     S = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+    if len(sys.argv) > 2 and sys.argv[2] == "e2e":
+        return e2e(S)
     dev = "cuda:0"
     D, H, W, L, r = 256, 28, 28, 4, 4
     hbm, src = peaks()
