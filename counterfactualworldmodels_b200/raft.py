@@ -430,30 +430,43 @@ class RAFT(nn.Module):
         return upsample_flow(flow, mask)
 
     def _forward_two_images(self, image1, image2, iters=24, flow_init=None, upsample=True, test_mode=True, **kwargs):
-        """raft_model.py:199-277."""
+        """raft_model.py:199-277.  One of the two images may have batch 1 while the other has N (a counterfactual
+        sweep shares its first frame): that image goes through the encoders once and is broadcast -- same result,
+        the per-sample instance norm makes the encoders independent of what else is in the batch."""
         if self.iters is not None:
             iters = self.iters
         image1 = (2 * (image1 / 255.0) - 1.0).contiguous()
         image2 = (2 * (image2 / 255.0) - 1.0).contiguous()
-        amp = self.args.mixed_precision or image1.dtype in (torch.float16, torch.bfloat16)
-        with torch.autocast("cuda", enabled=bool(amp)):
-            fmap1, fmap2 = self.fnet([image1, image2])
-        corr_fn = CorrBlock(fmap1.float(), fmap2.float(), num_levels=self.args.corr_levels, radius=self.args.corr_radius)
-        with torch.autocast("cuda", enabled=bool(amp)):
+        n1, n2 = image1.shape[0], image2.shape[0]
+        N = max(n1, n2)
+        assert n1 in (1, N) and n2 in (1, N), (image1.shape, image2.shape)
+        amp = bool(self.args.mixed_precision or image1.dtype in (torch.float16, torch.bfloat16))
+        with torch.autocast("cuda", enabled=amp):
+            fmaps = self.fnet(torch.cat([image1, image2], dim=0))  # both frames in one batch (raft_model.py:221-222)
+        fmap1 = fmaps[:n1].float().expand(N, -1, -1, -1)
+        fmap2 = fmaps[n1:].float().expand(N, -1, -1, -1)
+        corr_fn = CorrBlock(fmap1, fmap2, num_levels=self.args.corr_levels, radius=self.args.corr_radius)
+        with torch.autocast("cuda", enabled=amp):
             net, inp = torch.split(self.cnet(image1), [self.hidden_dim, self.context_dim], dim=1)
-            net, inp = torch.tanh(net), torch.relu(inp)
-        coords0, coords1 = self.initialize_flow(image1)
+            net = torch.tanh(net).expand(N, -1, -1, -1)
+            inp = torch.relu(inp).expand(N, -1, -1, -1)
+        coords0, coords1 = self.initialize_flow(image1 if n1 == N else image2)
         if flow_init is not None:
             coords1 = coords1 + flow_init
+        has_mask_head = isinstance(self.update_block, BasicUpdateBlock)
         predictions = []
         flow_up = None
         for itr in range(iters):
             coords1 = coords1.detach()
             corr = corr_fn(coords1)
-            with torch.autocast("cuda", enabled=bool(amp)):
-                net, up_mask, delta_flow = self.update_block(net, inp, corr, coords1 - coords0)
+            emit = (not test_mode) or itr + 1 == iters  # test_mode only returns the last prediction
+            with torch.autocast("cuda", enabled=amp):
+                if has_mask_head:  # the upsampling logits are only needed where a prediction is emitted
+                    net, up_mask, delta_flow = self.update_block(net, inp, corr, coords1 - coords0, upsample=emit)
+                else:
+                    net, up_mask, delta_flow = self.update_block(net, inp, corr, coords1 - coords0)
             coords1 = coords1 + delta_flow
-            if test_mode and itr + 1 < iters:
+            if not emit:
                 continue
             out = self.output_block(net) if self.output_block is not None else coords1 - coords0
             flow_up = upflow8(out) if up_mask is None else self.upsample_flow(out, up_mask)
@@ -463,7 +476,9 @@ class RAFT(nn.Module):
         return predictions
 
     def forward(self, *args, **kwargs):
-        """raft_model.py:279-301: ``[B, T, 3, H, W]`` frames in [0, 1] -> flows ``[B, T-1, 2, H, W]``."""
+        """raft_model.py:279-301: ``[B, T, 3, H, W]`` frames in [0, 1] -> flows ``[B, T-1, 2, H, W]``.
+        ``shared_frame=t`` (extension): frame t is identical across the batch and is encoded once."""
+        shared = kwargs.pop('shared_frame', None)
         if not self.multiframe:
             return self._forward_two_images(*args, **kwargs)
         x = (args[0] * 255.0) if self.scale_inputs else args[0]
@@ -473,9 +488,10 @@ class RAFT(nn.Module):
         if x.size(1) == 1:  # a single frame is repeated
             x = x.repeat(1, 2, 1, 1, 1)
         backward = kwargs.get('backward', False)
+        frame = lambda t: x[:1, t] if shared is not None and t == shared else x[:, t]  # noqa: E731
         flows = []
         for t in range(x.size(1) - 1):
-            pair = (x[:, t + 1], x[:, t]) if backward else (x[:, t], x[:, t + 1])
+            pair = (frame(t + 1), frame(t)) if backward else (frame(t), frame(t + 1))
             flow = self._forward_two_images(*pair, *args[1:], **kwargs)[-1]
             if backward:
                 flows.insert(0, flow)

@@ -84,6 +84,12 @@ class FlowGenerator(PredictorBasedGenerator):
                                "pass flow_model=<nn.Module> to the constructor)")
         if iters is not None and hasattr(self.flow_model, 'iters'):
             self.flow_model.iters = iters
+        from .raft import RAFT
+        if isinstance(self.flow_model, RAFT) and 'shared_frame' not in kwargs and vid.dim() == 5 and vid.size(0) > 1 \
+                and vid.size(1) == 2 and bool((vid[:, 0] == vid[:1, 0]).all()):
+            # a counterfactual sweep: every sample keeps the input's first frame (all of frame 0 is visible, so the
+            # predictor returns it bit for bit) -> RAFT encodes that frame once instead of once per sample
+            kwargs['shared_frame'] = 0
         return self.flow_model(vid, backward=backward, **kwargs).to(vid)
 
     # ---- which patches to move (host-side mask bookkeeping, reference RNG streams) ----
