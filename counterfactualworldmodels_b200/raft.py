@@ -374,7 +374,9 @@ class RAFT(nn.Module):
     """``cwm.models.raft.raft_model.RAFT`` (raft_model.py:114-301): same ``args``, attributes (``iters``,
     ``multiframe``, ``scale_inputs``, ``hidden_dim``, ``context_dim``), parameter names and forward semantics.
     The correlation pyramid, its per-iteration lookups and the convex upsampling run on ``csrc/raftcorr.cu``; in
-    ``test_mode`` only the last iteration is upsampled (the reference upsamples all of them and returns the last)."""
+    ``test_mode`` only the last iteration is upsampled (the reference upsamples all of them and returns the last).
+    ``args.mixed_precision`` (the reference's autocast option, raft_model.py:216-222): the encoders run under autocast
+    and the recurrent block on f16 channels-last tensors (``args.half_update=False`` restores plain autocast)."""
 
     def __init__(self, args):
         super().__init__()
@@ -429,6 +431,17 @@ class RAFT(nn.Module):
     def upsample_flow(self, flow, mask):
         return upsample_flow(flow, mask)
 
+    def _half_update_block(self):
+        """f16 channels-last twin of ``update_block``, rebuilt when the fp32 parameters change."""
+        import copy
+        key = tuple((p.data_ptr(), p._version) for p in self.update_block.parameters())
+        cached = getattr(self, '_half_ub', None)
+        if cached is None or cached[0] != key:
+            twin = copy.deepcopy(self.update_block).half().to(memory_format=torch.channels_last).eval().requires_grad_(False)
+            object.__setattr__(self, '_half_ub', (key, twin))  # not a submodule: keeps state_dict() the reference's
+            cached = self._half_ub
+        return cached[1]
+
     def _forward_two_images(self, image1, image2, iters=24, flow_init=None, upsample=True, test_mode=True, **kwargs):
         """raft_model.py:199-277.  One of the two images may have batch 1 while the other has N (a counterfactual
         sweep shares its first frame): that image goes through the encoders once and is broadcast -- same result,
@@ -454,18 +467,29 @@ class RAFT(nn.Module):
         if flow_init is not None:
             coords1 = coords1 + flow_init
         has_mask_head = isinstance(self.update_block, BasicUpdateBlock)
+        update_block = self.update_block
+        half_update = amp and bool(getattr(self.args, 'half_update', True))
+        if half_update:
+            # mixed precision without autocast's per-call casts and cuDNN's NCHW<->NHWC transforms: the recurrent
+            # block runs on f16 channels-last activations and an f16 channels-last copy of its weights
+            update_block = self._half_update_block()
+            to16 = lambda t: t.to(dtype=torch.float16, memory_format=torch.channels_last)  # noqa: E731
+            net, inp = to16(net), to16(inp)
         predictions = []
         flow_up = None
         for itr in range(iters):
             coords1 = coords1.detach()
             corr = corr_fn(coords1)
+            flow = coords1 - coords0
+            if half_update:
+                corr, flow = to16(corr), to16(flow)
             emit = (not test_mode) or itr + 1 == iters  # test_mode only returns the last prediction
-            with torch.autocast("cuda", enabled=amp):
+            with torch.autocast("cuda", enabled=amp and not half_update):
                 if has_mask_head:  # the upsampling logits are only needed where a prediction is emitted
-                    net, up_mask, delta_flow = self.update_block(net, inp, corr, coords1 - coords0, upsample=emit)
+                    net, up_mask, delta_flow = update_block(net, inp, corr, flow, upsample=emit)
                 else:
-                    net, up_mask, delta_flow = self.update_block(net, inp, corr, coords1 - coords0)
-            coords1 = coords1 + delta_flow
+                    net, up_mask, delta_flow = update_block(net, inp, corr, flow)
+            coords1 = coords1 + delta_flow.float()
             if not emit:
                 continue
             out = self.output_block(net) if self.output_block is not None else coords1 - coords0

@@ -351,3 +351,25 @@ def test_gpu_raft_shared_first_frame_is_the_same_flow():
         assert rel_err(auto.cpu().numpy(), model(x).cpu().numpy()) <= 1e-5
     finally:
         torch.backends.cudnn.allow_tf32 = old
+
+
+@pytest.mark.gpu
+def test_gpu_raft_mixed_precision_stays_close_to_the_fp32_reference():
+    """``mixed_precision=True`` (the reference's autocast option; here: autocast encoders + the recurrent block on f16
+    channels-last tensors): f16 convolutions with fp32 accumulation against the fp32 flows of the REAL reference.
+    Tolerance 1e-2 of the flow scale (measured 1.8e-3: f16 activations through 4 recurrent iterations)."""
+    import make_golden_raft as mg
+    d = load("raft_e2e_large_128px")
+    model = _mirror(False).to(DEV)
+    model.iters = int(d["iters"])
+    model.args.mixed_precision = True
+    x = mg.e2e_frames(2, 128).to(DEV)
+    errs = {}
+    for half_update in (True, False):
+        model.args.half_update = half_update
+        fwd = model(x)
+        assert fwd.dtype == torch.float32
+        errs[half_update] = rel_err(fwd.cpu().numpy(), d["flow_fwd"])
+    print(f"raft mixed precision: f16 update block {errs[True]:.2e}, autocast {errs[False]:.2e} of scale")
+    assert errs[True] <= 1e-2 and errs[False] <= 1e-2
+    assert "_half_ub" not in model.state_dict() and len(model.state_dict()) == int(d["n_tensors"])
