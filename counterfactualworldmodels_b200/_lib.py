@@ -25,6 +25,8 @@ EXPORTED_SYMBOLS = (
     "cwm_flow_sample_stats", "cwm_flow_filter_mask", "cwm_flow_zero_filtered", "cwm_flow_magnitude_sum",
     "cwm_motion_map_finalize", "cwm_flow_stats_workspace_bytes", "cwm_flow_corrs_workspace_bytes", "cwm_flow_corrs",
     "cwm_gemm_ln_parts", "cwm_rowstats_f16", "cwm_raft_corr_pyramid", "cwm_raft_corr_lookup", "cwm_raft_upsample_flow",
+    "cwm_raft_corr_lookup_f16", "cwm_raft_bias_act_f16", "cwm_raft_gru_gate_f16", "cwm_raft_gru_update_f16",
+    "cwm_raft_flow_update",
 )
 
 
@@ -151,6 +153,15 @@ def _declare(lib):
     lib.cwm_raft_corr_lookup.argtypes = [POINTER(c_void_p), c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
                                          c_void_p]
     lib.cwm_raft_upsample_flow.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]
+    c_ll = ctypes.c_longlong
+    lib.cwm_raft_corr_lookup_f16.argtypes = [POINTER(c_void_p), c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int,
+                                             c_void_p]
+    lib.cwm_raft_bias_act_f16.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_ll, c_void_p, c_int, c_void_p, c_int,
+                                          c_void_p, c_int, c_int, c_void_p]
+    lib.cwm_raft_gru_gate_f16.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_ll, c_void_p, c_void_p, c_int,
+                                          c_void_p]
+    lib.cwm_raft_gru_update_f16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_ll, c_void_p, c_void_p]
+    lib.cwm_raft_flow_update.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]
     lib.cwm_profile_begin.restype = c_int
     lib.cwm_profile_end.argtypes = [POINTER(ProfileEntry), c_int, POINTER(c_int)]
     for name in EXPORTED_SYMBOLS:

@@ -170,7 +170,7 @@ __device__ __forceinline__ void raft_axis(float c, int tap_off, int size, int w0
 template <int R>
 __global__ void __launch_bounds__(256)
 raft_corr_lookup_kernel(const __grid_constant__ CorrLevels lv, int L, int r_rt, const float* __restrict__ coords,
-                        long long P, int HW, float* __restrict__ out) {
+                        long long P, int HW, float* __restrict__ out, __half* __restrict__ out16, int ld16) {
   extern __shared__ __align__(16) float smem[];
   const int r = (R >= 0) ? R : r_rt;
   const int n1 = 2 * r + 1, n2 = n1 * n1, nch = L * n2;
@@ -281,7 +281,20 @@ raft_corr_lookup_kernel(const __grid_constant__ CorrLevels lv, int L, int r_rt, 
     __syncwarp();
   }
   __syncthreads();
-  if (my_valid) {
+  if (out16 != nullptr) {
+    // pixel-major f16 rows [P, ld16] (channels past nch are zero): the layout the f16 recurrent block consumes
+    for (int q = 0; q < 4; ++q) {
+      const int pix = warp + 8 * q;
+      if (p0 + pix >= P) break;
+      __half2* dst = reinterpret_cast<__half2*>(out16 + (p0 + pix) * ld16);
+      for (int c2 = lane; 2 * c2 < ld16; c2 += 32) {
+        const int ch = 2 * c2;
+        const float v0 = ch < nch ? tile[ch * 33 + pix] : 0.f;
+        const float v1 = ch + 1 < nch ? tile[(ch + 1) * 33 + pix] : 0.f;
+        dst[c2] = __floats2half2_rn(v0, v1);
+      }
+    }
+  } else if (my_valid) {
     float* dst = out + my_b * static_cast<long long>(nch) * HW + my_hw;
     for (int ch = warp; ch < nch; ch += 8) dst[static_cast<long long>(ch) * HW] = tile[ch * 33 + lane];
   }
@@ -361,6 +374,120 @@ raft_upsample_kernel(const float* __restrict__ flow, const float* __restrict__ m
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The elementwise half of RAFT-large's recurrent block (cwm/models/raft/update.py:33-60, :79-98, :115-139) for the
+// mixed-precision path.  The convolutions stay cuDNN calls WITHOUT bias on f16 pixel-major (channels-last) rows; these
+// kernels apply bias + activation to the raw convolution output and write it straight into its slot of the next
+// convolution's input (the reference's torch.cat / bias add / relu / sigmoid / tanh / gate arithmetic: ~55 eager
+// launches per iteration become 11).  All of them are HBM-bound streams of 16-byte vectors; math in fp32.
+// ---------------------------------------------------------------------------------------------
+union H8 {
+  uint4 u;
+  __half2 h2[4];
+};
+__device__ __forceinline__ void h8_to_f(const uint4& u, float* f) {
+  H8 v;
+  v.u = u;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __half22float2(v.h2[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 f_to_h8(const float* f) {
+  H8 v;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v.h2[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+  return v.u;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+
+// d1[m, c] (and d2[m, c]) = act(x[m, c] + bias[c]) for c < C; the last tail_cols columns are taken from tail[m, :]
+// instead (BasicMotionEncoder's `cat([out, flow])`, update.py:98).  act: 0 none, 1 relu.
+__global__ void __launch_bounds__(256)
+raft_bias_act_kernel(const __half* __restrict__ x, int ldx, const float* __restrict__ bias, int act, int C, long long M,
+                     __half* __restrict__ d1, int ld1, __half* __restrict__ d2, int ld2, const __half* __restrict__ tail,
+                     int ldt, int tail_cols) {
+  const int cv = C >> 3;
+  const long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (v >= M * cv) return;
+  const long long row = v / cv;
+  const int c8 = static_cast<int>(v - row * cv) << 3;
+  float f[8];
+  h8_to_f(*reinterpret_cast<const uint4*>(x + row * ldx + c8), f);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    f[i] += bias ? __ldg(bias + c8 + i) : 0.f;
+    if (act == 1) f[i] = fmaxf(f[i], 0.f);
+    if (tail != nullptr && c8 + i >= C - tail_cols) f[i] = __half2float(tail[row * ldt + (c8 + i - (C - tail_cols))]);
+  }
+  const uint4 o = f_to_h8(f);
+  *reinterpret_cast<uint4*>(d1 + row * ld1 + c8) = o;
+  if (d2 != nullptr) *reinterpret_cast<uint4*>(d2 + row * ld2 + c8) = o;
+}
+
+// z = sigmoid(zr[:, :C] + b), r = sigmoid(zr[:, C:] + b) (update.py:46-47 / :53-54); z -> z_out, r * h -> rh
+__global__ void __launch_bounds__(256)
+raft_gru_gate_kernel(const __half* __restrict__ zr, const float* __restrict__ bias, const __half* __restrict__ h, int ldh,
+                     int C, long long M, __half* __restrict__ z_out, __half* __restrict__ rh, int ldrh) {
+  const int cv = C >> 3;
+  const long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (v >= M * cv) return;
+  const long long row = v / cv;
+  const int c8 = static_cast<int>(v - row * cv) << 3;
+  float fz[8], fr[8], fh[8];
+  h8_to_f(*reinterpret_cast<const uint4*>(zr + row * (2 * C) + c8), fz);
+  h8_to_f(*reinterpret_cast<const uint4*>(zr + row * (2 * C) + C + c8), fr);
+  h8_to_f(*reinterpret_cast<const uint4*>(h + row * ldh + c8), fh);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    fz[i] = sigmoidf_(fz[i] + __ldg(bias + c8 + i));
+    fr[i] = sigmoidf_(fr[i] + __ldg(bias + C + c8 + i)) * fh[i];
+  }
+  *reinterpret_cast<uint4*>(z_out + row * C + c8) = f_to_h8(fz);
+  *reinterpret_cast<uint4*>(rh + row * ldrh + c8) = f_to_h8(fr);
+}
+
+// h <- (1 - z) * h + z * tanh(q + b) (update.py:48-49 / :55-56), in place in its slot and optionally to a dense copy
+__global__ void __launch_bounds__(256)
+raft_gru_update_kernel(const __half* __restrict__ q, const float* __restrict__ bias, const __half* __restrict__ z,
+                       __half* __restrict__ h, int ldh, int C, long long M, __half* __restrict__ h_dense) {
+  const int cv = C >> 3;
+  const long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (v >= M * cv) return;
+  const long long row = v / cv;
+  const int c8 = static_cast<int>(v - row * cv) << 3;
+  float fq[8], fz[8], fh[8];
+  h8_to_f(*reinterpret_cast<const uint4*>(q + row * C + c8), fq);
+  h8_to_f(*reinterpret_cast<const uint4*>(z + row * C + c8), fz);
+  h8_to_f(*reinterpret_cast<const uint4*>(h + row * ldh + c8), fh);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) fh[i] = (1.f - fz[i]) * fh[i] + fz[i] * tanhf(fq[i] + __ldg(bias + c8 + i));
+  const uint4 o = f_to_h8(fh);
+  *reinterpret_cast<uint4*>(h + row * ldh + c8) = o;
+  if (h_dense != nullptr) *reinterpret_cast<uint4*>(h_dense + row * C + c8) = o;
+}
+
+// coords1 += delta + b (raft_model.py:254), flow = coords1 - coords0 as the next iteration's f16 input row
+// [fx, fy, 0 x 6].  delta: raw flow-head output rows [M, ldd] (columns 0, 1), coords1: fp32 [B, 2, H, W].
+__global__ void __launch_bounds__(256)
+raft_flow_update_kernel(const __half* __restrict__ delta, int ldd, const float* __restrict__ bias, float* __restrict__ coords1,
+                        int HW, int W, long long M, __half* __restrict__ flow16) {
+  const long long m = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const long long b = m / HW;
+  const int hw = static_cast<int>(m - b * HW);
+  float* cx = coords1 + (b * 2) * HW + hw;
+  float* cy = cx + HW;
+  const float nx = *cx + (__half2float(delta[m * ldd]) + __ldg(bias));
+  const float ny = *cy + (__half2float(delta[m * ldd + 1]) + __ldg(bias + 1));
+  *cx = nx;
+  *cy = ny;
+  float f[8] = {nx - static_cast<float>(hw % W), ny - static_cast<float>(hw / W), 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  *reinterpret_cast<uint4*>(flow16 + m * 8) = f_to_h8(f);
+}
+
 static int level_dims(int H, int W, int L, int* hs, int* ws, const char* who) {
   CWM_REQUIRE(L >= 1 && L <= kMaxLevels, "%s: num_levels %d not in [1, %d]", who, L, kMaxLevels);
   hs[0] = H;
@@ -414,8 +541,8 @@ extern "C" int cwm_raft_corr_pyramid(const float* fmap1, const float* fmap2, int
   return CWM_OK;
 }
 
-extern "C" int cwm_raft_corr_lookup(const float* const* levels, int num_levels, int radius, const float* coords, int B,
-                                    int H, int W, float* out, cwm_stream_t stream) {
+static int corr_lookup_impl(const float* const* levels, int num_levels, int radius, const float* coords, int B, int H, int W,
+                            float* out, __half* out16, int ld16, cwm_stream_t stream) {
   CWM_REQUIRE(B >= 0 && H >= 1 && W >= 1, "cwm_raft_corr_lookup: bad shape B=%d H=%d W=%d", B, H, W);
   CWM_REQUIRE(radius >= 0 && radius <= 7, "cwm_raft_corr_lookup: radius %d not in [0, 7]", radius);
   CorrLevels lv;
@@ -423,7 +550,7 @@ extern "C" int cwm_raft_corr_lookup(const float* const* levels, int num_levels, 
   if (rc != CWM_OK) return rc;
   CWM_REQUIRE(levels, "cwm_raft_corr_lookup: null level table");
   if (B == 0) return CWM_OK;
-  CWM_REQUIRE(coords && out, "cwm_raft_corr_lookup: null pointer");
+  CWM_REQUIRE(coords && (out || out16), "cwm_raft_corr_lookup: null pointer");
   for (int l = 0; l < num_levels; ++l) {
     CWM_REQUIRE(levels[l], "cwm_raft_corr_lookup: null level %d", l);
     lv.p[l] = levels[l];
@@ -447,8 +574,92 @@ extern "C" int cwm_raft_corr_lookup(const float* const* levels, int num_levels, 
     const int ws = min(WS, lv.w[l]), hs = min(WS, lv.h[l]);
     pyr += static_cast<double>(ws) * hs;
   }
-  ProfileScope prof(st, "raft_corr_lookup", 0.0, static_cast<double>(P) * (nch + pyr + 2.0) * 4.0);
-  kernel<<<static_cast<unsigned>((P + 31) / 32), 256, smem, st>>>(lv, num_levels, radius, coords, P, H * W, out);
+  if (out16 != nullptr)
+    CWM_REQUIRE(ld16 >= nch && ld16 % 2 == 0 && reinterpret_cast<uintptr_t>(out16) % 4 == 0,
+                "cwm_raft_corr_lookup_f16: row length %d must be even and >= %d channels", ld16, nch);
+  ProfileScope prof(st, "raft_corr_lookup", 0.0,
+                    static_cast<double>(P) * ((out16 ? 0.5 * ld16 : static_cast<double>(nch)) + pyr + 2.0) * 4.0);
+  kernel<<<static_cast<unsigned>((P + 31) / 32), 256, smem, st>>>(lv, num_levels, radius, coords, P, H * W, out, out16, ld16);
+  CWM_LAUNCH_CHECK();
+  return CWM_OK;
+}
+
+extern "C" int cwm_raft_corr_lookup(const float* const* levels, int num_levels, int radius, const float* coords, int B,
+                                    int H, int W, float* out, cwm_stream_t stream) {
+  return corr_lookup_impl(levels, num_levels, radius, coords, B, H, W, out, nullptr, 0, stream);
+}
+
+extern "C" int cwm_raft_corr_lookup_f16(const float* const* levels, int num_levels, int radius, const float* coords, int B,
+                                        int H, int W, uint16_t* out16, int ld16, cwm_stream_t stream) {
+  return corr_lookup_impl(levels, num_levels, radius, coords, B, H, W, nullptr, reinterpret_cast<__half*>(out16), ld16, stream);
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static unsigned blocks_for(long long n) { return static_cast<unsigned>((n + 255) / 256); }
+
+extern "C" int cwm_raft_bias_act_f16(const uint16_t* x, int ldx, const float* bias, int act, int C, long long M, uint16_t* d1,
+                                     int ld1, uint16_t* d2, int ld2, const uint16_t* tail, int ldt, int tail_cols,
+                                     cwm_stream_t stream) {
+  CWM_REQUIRE(M >= 0 && C >= 8 && C % 8 == 0 && (act == 0 || act == 1), "cwm_raft_bias_act_f16: bad C=%d / act=%d", C, act);
+  if (M == 0) return CWM_OK;
+  CWM_REQUIRE(x && d1 && ldx >= C && ld1 >= C && ldx % 8 == 0 && ld1 % 8 == 0 && aligned16(x) && aligned16(d1),
+              "cwm_raft_bias_act_f16: rows must be 16-byte aligned and at least C wide");
+  CWM_REQUIRE(d2 == nullptr || (ld2 >= C && ld2 % 8 == 0 && aligned16(d2)), "cwm_raft_bias_act_f16: bad second destination");
+  CWM_REQUIRE(tail == nullptr || (tail_cols >= 1 && tail_cols <= C && ldt >= tail_cols), "cwm_raft_bias_act_f16: bad tail");
+  CWM_REQUIRE(M * (C / 8) < (1LL << 39), "cwm_raft_bias_act_f16: too many rows");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfileScope prof(st, "raft_bias_act", 0.0, static_cast<double>(M) * C * (d2 ? 6.0 : 4.0));
+  raft_bias_act_kernel<<<blocks_for(M * (C / 8)), 256, 0, st>>>(
+      reinterpret_cast<const __half*>(x), ldx, bias, act, C, M, reinterpret_cast<__half*>(d1), ld1,
+      reinterpret_cast<__half*>(d2), ld2, reinterpret_cast<const __half*>(tail), ldt, tail ? tail_cols : 0);
+  CWM_LAUNCH_CHECK();
+  return CWM_OK;
+}
+
+extern "C" int cwm_raft_gru_gate_f16(const uint16_t* zr, const float* bias, const uint16_t* h, int ldh, int C, long long M,
+                                     uint16_t* z_out, uint16_t* rh, int ldrh, cwm_stream_t stream) {
+  CWM_REQUIRE(M >= 0 && C >= 8 && C % 8 == 0, "cwm_raft_gru_gate_f16: bad C=%d", C);
+  if (M == 0) return CWM_OK;
+  CWM_REQUIRE(zr && bias && h && z_out && rh && ldh >= C && ldrh >= C && ldh % 8 == 0 && ldrh % 8 == 0 && aligned16(zr) &&
+                  aligned16(h) && aligned16(z_out) && aligned16(rh),
+              "cwm_raft_gru_gate_f16: null pointer or rows not 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfileScope prof(st, "raft_gru_gate", 0.0, static_cast<double>(M) * C * 10.0);
+  raft_gru_gate_kernel<<<blocks_for(M * (C / 8)), 256, 0, st>>>(reinterpret_cast<const __half*>(zr), bias,
+                                                               reinterpret_cast<const __half*>(h), ldh, C, M,
+                                                               reinterpret_cast<__half*>(z_out),
+                                                               reinterpret_cast<__half*>(rh), ldrh);
+  CWM_LAUNCH_CHECK();
+  return CWM_OK;
+}
+
+extern "C" int cwm_raft_gru_update_f16(const uint16_t* q, const float* bias, const uint16_t* z, uint16_t* h, int ldh, int C,
+                                       long long M, uint16_t* h_dense, cwm_stream_t stream) {
+  CWM_REQUIRE(M >= 0 && C >= 8 && C % 8 == 0, "cwm_raft_gru_update_f16: bad C=%d", C);
+  if (M == 0) return CWM_OK;
+  CWM_REQUIRE(q && bias && z && h && ldh >= C && ldh % 8 == 0 && aligned16(q) && aligned16(z) && aligned16(h) &&
+                  (h_dense == nullptr || aligned16(h_dense)),
+              "cwm_raft_gru_update_f16: null pointer or rows not 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfileScope prof(st, "raft_gru_update", 0.0, static_cast<double>(M) * C * (h_dense ? 10.0 : 8.0));
+  raft_gru_update_kernel<<<blocks_for(M * (C / 8)), 256, 0, st>>>(reinterpret_cast<const __half*>(q), bias,
+                                                                 reinterpret_cast<const __half*>(z),
+                                                                 reinterpret_cast<__half*>(h), ldh, C, M,
+                                                                 reinterpret_cast<__half*>(h_dense));
+  CWM_LAUNCH_CHECK();
+  return CWM_OK;
+}
+
+extern "C" int cwm_raft_flow_update(const uint16_t* delta, int ldd, const float* bias, float* coords1, int B, int H, int W,
+                                    uint16_t* flow16, cwm_stream_t stream) {
+  CWM_REQUIRE(B >= 0 && H >= 1 && W >= 1 && ldd >= 2, "cwm_raft_flow_update: bad shape B=%d H=%d W=%d ld=%d", B, H, W, ldd);
+  if (B == 0) return CWM_OK;
+  CWM_REQUIRE(delta && bias && coords1 && flow16 && aligned16(flow16), "cwm_raft_flow_update: null or misaligned pointer");
+  const long long M = static_cast<long long>(B) * H * W;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfileScope prof(st, "raft_flow_update", 0.0, static_cast<double>(M) * 36.0);
+  raft_flow_update_kernel<<<blocks_for(M), 256, 0, st>>>(reinterpret_cast<const __half*>(delta), ldd, bias, coords1, H * W, W, M,
+                                                        reinterpret_cast<__half*>(flow16));
   CWM_LAUNCH_CHECK();
   return CWM_OK;
 }

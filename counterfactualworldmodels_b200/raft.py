@@ -351,6 +351,130 @@ class BasicUpdateBlock(nn.Module):
         return net, (.25 * self.mask(net) if upsample else None), self.flow_head(net)
 
 
+class FusedBasicUpdate:
+    """``BasicUpdateBlock`` (update.py:115-139) for the mixed-precision path, on f16 pixel-major rows ``[M = N*H*W, C]``:
+    cuDNN convolutions WITHOUT bias on channels-last views of those rows, and everything between them -- bias, relu,
+    the ``torch.cat``s, the GRU gates, the flow update -- on the ``cwm_raft_*_f16`` kernels, which write each result
+    straight into its slot of the next convolution's input.  Per iteration: 1 lookup + 11 convolutions + 11 kernels
+    (the eager block: ~80 launches).  z|r and flow-head|mask-head convolutions are stacked along the output channels.
+
+    Row buffers (f16):  HX  [M, 384] = [h | inp | motion features (126) , flow (2)]   -> convz / convr input
+                        RHX [M, 384] = [r*h | inp | motion features, flow]             -> convq input
+                        CORFLO [M, 256] = [cor (192) | flo (64)]                       -> encoder.conv input
+    """
+    CORR_LD = 328   # 4 * 81 = 324 correlation channels padded to a multiple of 8 (16-byte rows)
+
+    def __init__(self, ub, device):
+        assert isinstance(ub, BasicUpdateBlock)
+
+        def cl(w, out_pad=None, in_pad=None):
+            w = w.detach().float()
+            if out_pad is not None or in_pad is not None:
+                full = torch.zeros(out_pad or w.shape[0], in_pad or w.shape[1], *w.shape[2:], device=w.device)
+                full[:w.shape[0], :w.shape[1]] = w
+                w = full
+            return w.to(device=device, dtype=torch.float16).contiguous(memory_format=torch.channels_last)
+
+        def f32(*bs, pad=None):
+            b = torch.cat([x.detach().float().reshape(-1) for x in bs])
+            if pad is not None:
+                b = torch.cat([b, b.new_zeros(pad - b.numel())])
+            return b.to(device).contiguous()
+
+        enc, gru, fh, mk = ub.encoder, ub.gru, ub.flow_head, ub.mask
+        self.C = gru.convz1.out_channels                       # hidden width (128)
+        assert enc.convc1.in_channels <= self.CORR_LD and self.C % 8 == 0
+        self.w_c1, self.b_c1 = cl(enc.convc1.weight, in_pad=self.CORR_LD), f32(enc.convc1.bias)
+        self.w_c2, self.b_c2 = cl(enc.convc2.weight), f32(enc.convc2.bias)
+        self.w_f1, self.b_f1 = cl(enc.convf1.weight, in_pad=8), f32(enc.convf1.bias)
+        self.w_f2, self.b_f2 = cl(enc.convf2.weight), f32(enc.convf2.bias)
+        self.w_cv, self.b_cv = cl(enc.conv.weight, out_pad=128), f32(enc.conv.bias, pad=128)
+        self.w_zr1, self.b_zr1 = cl(torch.cat([gru.convz1.weight, gru.convr1.weight])), f32(gru.convz1.bias, gru.convr1.bias)
+        self.w_zr2, self.b_zr2 = cl(torch.cat([gru.convz2.weight, gru.convr2.weight])), f32(gru.convz2.bias, gru.convr2.bias)
+        self.w_q1, self.b_q1 = cl(gru.convq1.weight), f32(gru.convq1.bias)
+        self.w_q2, self.b_q2 = cl(gru.convq2.weight), f32(gru.convq2.bias)
+        self.w_fh1, self.b_fh1 = cl(fh.conv1.weight), f32(fh.conv1.bias)
+        self.w_fh1m = cl(torch.cat([fh.conv1.weight, mk[0].weight]))
+        self.b_m0 = f32(mk[0].bias)
+        self.w_fh2, self.b_fh2 = cl(fh.conv2.weight, out_pad=8), f32(fh.conv2.bias)
+        self.w_m2 = cl(mk[2].weight)
+        self.b_m2 = mk[2].bias.detach().to(device=device, dtype=torch.float16)
+
+    class State:
+        pass
+
+    def begin(self, N, H, W, net, inp, flow_init=None):
+        """net / inp: [N or 1, C, H, W] (tanh / relu already applied, raft_model.py:236-237)."""
+        st, dev, C = self.State(), net.device, self.C
+        st.N, st.H, st.W, st.M = N, H, W, N * H * W
+        buf = lambda c, zero=False: (torch.zeros if zero else torch.empty)(st.M, c, dtype=torch.float16, device=dev)  # noqa: E731
+        st.HX, st.RHX, st.CORFLO = buf(3 * C), buf(3 * C), buf(256)
+        st.cor1, st.flo1, st.Z, st.Hd, st.fh1, st.mh = buf(256), buf(128), buf(C), buf(C), buf(256), buf(256)
+        st.corr16, st.flow16 = buf(self.CORR_LD), buf(8, zero=True)
+        rows = lambda t: t.expand(N, -1, -1, -1).permute(0, 2, 3, 1).reshape(st.M, -1)  # noqa: E731
+        st.HX[:, :C].copy_(rows(net))
+        st.HX[:, C:2 * C].copy_(rows(inp))
+        st.RHX[:, C:2 * C].copy_(st.HX[:, C:2 * C])
+        if flow_init is not None:
+            st.flow16[:, :2].copy_(rows(flow_init))
+        return st
+
+    @staticmethod
+    def _conv(st, rows, weight, padding):
+        x = rows.view(st.N, st.H, st.W, rows.shape[1]).permute(0, 3, 1, 2)
+        y = F.conv2d(x, weight, None, 1, padding)
+        if not y.is_contiguous(memory_format=torch.channels_last):
+            y = y.contiguous(memory_format=torch.channels_last)
+        return y.permute(0, 2, 3, 1).reshape(st.M, weight.shape[0])
+
+    def step(self, st, corr_fn, coords1, emit):
+        """One GRU iteration; ``coords1`` (fp32 [N, 2, H, W]) is updated in place.  Returns the upsampling logits
+        ``0.25 * mask(net)`` ([N, 576, H, W], f16) when ``emit`` else None."""
+        lib, M, C = _lib.load(), st.M, self.C
+        s = _stream(coords1)
+        p = lambda t: t.data_ptr()  # noqa: E731
+
+        def bias_act(raw, ldx, bias, C_, dst, ld, dst2=None, ld2=0, tail=None, x_ptr=None):
+            _lib.check(lib.cwm_raft_bias_act_f16(x_ptr or p(raw), ldx, p(bias), 1, C_, M, p(dst), ld,
+                                                 p(dst2) if dst2 is not None else None, ld2,
+                                                 p(tail) if tail is not None else None, 8, 2, s))
+
+        with torch.cuda.device(coords1.device):
+            _lib.check(lib.cwm_raft_corr_lookup_f16(_ptr_table(corr_fn.corr_pyramid), corr_fn.num_levels, corr_fn.radius,
+                                                    p(coords1), st.N, st.H, st.W, p(st.corr16), self.CORR_LD, s))
+            # BasicMotionEncoder (update.py:90-98)
+            raw = self._conv(st, st.corr16, self.w_c1, 0)
+            bias_act(raw, 256, self.b_c1, 256, st.cor1, 256)
+            raw = self._conv(st, st.cor1, self.w_c2, 1)
+            bias_act(raw, 192, self.b_c2, 192, st.CORFLO, 256)
+            raw = self._conv(st, st.flow16, self.w_f1, 3)
+            bias_act(raw, 128, self.b_f1, 128, st.flo1, 128)
+            raw = self._conv(st, st.flo1, self.w_f2, 1)
+            bias_act(raw, 64, self.b_f2, 64, st.CORFLO[:, 192:], 256)
+            raw = self._conv(st, st.CORFLO, self.w_cv, 1)
+            bias_act(raw, 128, self.b_cv, 128, st.HX[:, 2 * C:], 3 * C, st.RHX[:, 2 * C:], 3 * C, tail=st.flow16)
+            # SepConvGRU (update.py:43-60): horizontal then vertical
+            for w_zr, b_zr, w_q, b_q, pad, dense in ((self.w_zr1, self.b_zr1, self.w_q1, self.b_q1, (0, 2), None),
+                                                     (self.w_zr2, self.b_zr2, self.w_q2, self.b_q2, (2, 0), st.Hd)):
+                raw = self._conv(st, st.HX, w_zr, pad)
+                _lib.check(lib.cwm_raft_gru_gate_f16(p(raw), p(b_zr), p(st.HX), 3 * C, C, M, p(st.Z), p(st.RHX), 3 * C, s))
+                raw = self._conv(st, st.RHX, w_q, pad)
+                _lib.check(lib.cwm_raft_gru_update_f16(p(raw), p(b_q), p(st.Z), p(st.HX), 3 * C, C, M,
+                                                       p(dense) if dense is not None else None, s))
+            # FlowHead (update.py:13-14) and, where a prediction is emitted, the mask head (:131-137)
+            raw = self._conv(st, st.Hd, self.w_fh1m if emit else self.w_fh1, 1)
+            ldx = raw.shape[1]
+            bias_act(raw, ldx, self.b_fh1, 256, st.fh1, 256)
+            if emit:
+                bias_act(raw, ldx, self.b_m0, 256, st.mh, 256, x_ptr=p(raw[:, 256:]))
+            raw = self._conv(st, st.fh1, self.w_fh2, 1)
+            _lib.check(lib.cwm_raft_flow_update(p(raw), 8, p(self.b_fh2), p(coords1), st.N, st.H, st.W, p(st.flow16), s))
+            if not emit:
+                return None
+            mh = st.mh.view(st.N, st.H, st.W, 256).permute(0, 3, 1, 2)
+            return .25 * F.conv2d(mh, self.w_m2, self.b_m2)
+
+
 def get_args(cmd=None):
     """raft_model.py:36-51 (same option names and defaults)."""
     parser = argparse.ArgumentParser()
@@ -376,7 +500,8 @@ class RAFT(nn.Module):
     The correlation pyramid, its per-iteration lookups and the convex upsampling run on ``csrc/raftcorr.cu``; in
     ``test_mode`` only the last iteration is upsampled (the reference upsamples all of them and returns the last).
     ``args.mixed_precision`` (the reference's autocast option, raft_model.py:216-222): the encoders run under autocast
-    and the recurrent block on f16 channels-last tensors (``args.half_update=False`` restores plain autocast)."""
+    and the recurrent block on f16 channels-last tensors (``args.half_update=False`` restores plain autocast); for
+    RAFT-large inference that block is ``FusedBasicUpdate`` (``args.fused_update=False``: the same in eager torch ops)."""
 
     def __init__(self, args):
         super().__init__()
@@ -442,6 +567,15 @@ class RAFT(nn.Module):
             cached = self._half_ub
         return cached[1]
 
+    def _fused_update_block(self):
+        key = tuple((p.data_ptr(), p._version) for p in self.update_block.parameters())
+        cached = getattr(self, '_fused_ub', None)
+        if cached is None or cached[0] != key:
+            device = next(self.update_block.parameters()).device
+            object.__setattr__(self, '_fused_ub', (key, FusedBasicUpdate(self.update_block, device)))
+            cached = self._fused_ub
+        return cached[1]
+
     def _forward_two_images(self, image1, image2, iters=24, flow_init=None, upsample=True, test_mode=True, **kwargs):
         """raft_model.py:199-277.  One of the two images may have batch 1 while the other has N (a counterfactual
         sweep shares its first frame): that image goes through the encoders once and is broadcast -- same result,
@@ -475,6 +609,17 @@ class RAFT(nn.Module):
             update_block = self._half_update_block()
             to16 = lambda t: t.to(dtype=torch.float16, memory_format=torch.channels_last)  # noqa: E731
             net, inp = to16(net), to16(inp)
+        if (half_update and test_mode and has_mask_head and self.output_block is None and iters > 0
+                and bool(getattr(self.args, 'fused_update', True))):
+            # RAFT-large, inference: the recurrent block on cuDNN convolutions + the cwm_raft_*_f16 kernels
+            fused = self._fused_update_block()
+            st = fused.begin(N, coords0.shape[2], coords0.shape[3], net, inp, flow_init)
+            coords1 = coords1.float().contiguous().clone()
+            up_mask = None
+            for itr in range(iters):
+                up_mask = fused.step(st, corr_fn, coords1, emit=(itr + 1 == iters))
+            flow_low = coords1 - coords0
+            return flow_low, self.upsample_flow(flow_low, up_mask)
         predictions = []
         flow_up = None
         for itr in range(iters):

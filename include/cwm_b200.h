@@ -406,6 +406,30 @@ int cwm_raft_corr_lookup(const float* const* levels, int num_levels, int radius,
 int cwm_raft_upsample_flow(const float* flow, const float* mask, int N, int C, int H, int W, float* out,
                            cwm_stream_t stream);
 
+/* ---- mixed-precision recurrent block of RAFT-large (cwm/models/raft/update.py:33-60, :79-98, :115-139) --------
+ * The convolutions stay library calls WITHOUT bias on f16 pixel-major rows ([M = B*H*W, channels], "channels-last");
+ * these entry points are everything between them.  Row pointers / leading dimensions must be 16-byte aligned. */
+/* As cwm_raft_corr_lookup, but the result is written as f16 rows out16[M, ld16] (channels >= L*(2r+1)^2 zeroed):
+ * the input layout of the first motion-encoder convolution (update.py:93). */
+int cwm_raft_corr_lookup_f16(const float* const* levels, int num_levels, int radius, const float* coords, int B, int H,
+                             int W, uint16_t* out16, int ld16, cwm_stream_t stream);
+/* d1[m, c] (and d2[m, c] when d2 != NULL) = act(x[m, c] + bias[c]), c < C (C % 8 == 0; act 0 = none, 1 = relu); when
+ * tail != NULL the last tail_cols columns are copied from tail[m, 0..tail_cols) instead -- `cat([out, flow])`,
+ * update.py:98.  Replaces bias add + relu + torch.cat after a convolution. */
+int cwm_raft_bias_act_f16(const uint16_t* x, int ldx, const float* bias, int act, int C, long long M, uint16_t* d1, int ld1,
+                          uint16_t* d2, int ld2, const uint16_t* tail, int ldt, int tail_cols, cwm_stream_t stream);
+/* zr[M, 2C] raw output of the stacked z|r convolution, bias[2C]: z_out[M, C] = sigmoid(z), rh[m, c] = sigmoid(r) * h
+ * (update.py:46-47, :53-54); h / rh are slots (leading dimensions ldh / ldrh) of the GRU input rows. */
+int cwm_raft_gru_gate_f16(const uint16_t* zr, const float* bias, const uint16_t* h, int ldh, int C, long long M,
+                          uint16_t* z_out, uint16_t* rh, int ldrh, cwm_stream_t stream);
+/* h <- (1 - z) * h + z * tanh(q + bias) in place (update.py:48-49, :55-56); h_dense (optional) gets a packed copy. */
+int cwm_raft_gru_update_f16(const uint16_t* q, const float* bias, const uint16_t* z, uint16_t* h, int ldh, int C,
+                            long long M, uint16_t* h_dense, cwm_stream_t stream);
+/* coords1[B, 2, H, W] (fp32, in place) += delta[m, 0..1] + bias (raft_model.py:254); flow16[m, 0..7] = {coords1 - grid, 0..}
+ * = the next iteration's flow input (raft_model.py:249). */
+int cwm_raft_flow_update(const uint16_t* delta, int ldd, const float* bias, float* coords1, int B, int H, int W,
+                         uint16_t* flow16, cwm_stream_t stream);
+
 /* Number of kernel launches this thread enqueued through the library since the last cwm_vmae_forward began or
  * cwm_launch_count_reset() was called (for bench accounting). */
 int cwm_last_forward_launches(void);

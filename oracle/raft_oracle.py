@@ -152,3 +152,42 @@ def torch_upsample_flow(flow, mask):
     w = torch.softmax(mask.view(N, 1, 9, 8, 8, H, W), dim=2)
     nb = F.unfold(8 * flow, [3, 3], padding=1).view(N, C, 9, 1, 1, H, W)
     return torch.sum(w * nb, dim=2).permute(0, 1, 4, 2, 5, 3).reshape(N, C, 8 * H, 8 * W)
+
+
+# ---- elementwise half of the recurrent block (mixed-precision path): numpy fp32 on f16-rounded inputs ---------
+def _h(x):
+    """Round to f16 and back (what the kernels store between convolutions)."""
+    return np.asarray(x, F32).astype(np.float16).astype(F32)
+
+
+def bias_act(x, bias, relu=True, tail=None):
+    """conv output + bias (+ relu), last columns replaced by ``tail`` -- ``F.relu(conv(x))`` / ``cat([out, flow])``
+    (cwm/models/raft/update.py:90-98)."""
+    y = x.astype(F32) + (0 if bias is None else bias.astype(F32))
+    if relu:
+        y = np.maximum(y, 0)
+    if tail is not None:
+        y[:, y.shape[1] - tail.shape[1]:] = tail
+    return _h(y)
+
+
+def gru_gate(zr, bias, h):
+    """z = sigmoid(convz(hx)), r = sigmoid(convr(hx)) -> (z, r * h)  (update.py:46-47, :53-54); zr = [z | r] stacked."""
+    C = h.shape[1]
+    s = 1.0 / (1.0 + np.exp(-(zr.astype(F32) + bias.astype(F32))))
+    return _h(s[:, :C]), _h(s[:, C:] * h.astype(F32))
+
+
+def gru_update(q, bias, z, h):
+    """h = (1 - z) * h + z * tanh(convq(...))  (update.py:48-49, :55-56)."""
+    return _h((1 - z.astype(F32)) * h.astype(F32) + z.astype(F32) * np.tanh(q.astype(F32) + bias.astype(F32)))
+
+
+def flow_update(delta, bias, coords1):
+    """coords1 += delta_flow; flow = coords1 - coords0  (raft_model.py:249-254).  delta [M, >=2] rows, coords1
+    [B, 2, H, W] -> (new coords1, flow rows [M, 2])."""
+    B, _, H, W = coords1.shape
+    d = (delta[:, :2].astype(F32) + bias.astype(F32)).reshape(B, H, W, 2).transpose(0, 3, 1, 2)
+    new = (coords1.astype(F32) + d).astype(F32)
+    grid = make_coords(B, H, W, 0, "grid")
+    return new, _h((new - grid).transpose(0, 2, 3, 1).reshape(-1, 2))

@@ -373,3 +373,118 @@ def test_gpu_raft_mixed_precision_stays_close_to_the_fp32_reference():
     print(f"raft mixed precision: f16 update block {errs[True]:.2e}, autocast {errs[False]:.2e} of scale")
     assert errs[True] <= 1e-2 and errs[False] <= 1e-2
     assert "_half_ub" not in model.state_dict() and len(model.state_dict()) == int(d["n_tensors"])
+
+
+# ------------------------------------------------------------------------------------------------ recurrent block
+def test_oracle_gru_restatement_matches_torch_modules():
+    """The elementwise restatement (oracle) + plain convolutions == the mirror's SepConvGRU / BasicMotionEncoder tail."""
+    from counterfactualworldmodels_b200 import raft
+    torch.manual_seed(3)
+    gru = raft.SepConvGRU(hidden_dim=16, input_dim=24).eval().requires_grad_(False)
+    h, x = torch.randn(2, 16, 6, 7), torch.randn(2, 24, 6, 7)
+    want = gru(h, x)
+    rows = lambda t: t.permute(0, 2, 3, 1).reshape(-1, t.shape[1]).numpy()  # noqa: E731
+    unrows = lambda a, c: torch.from_numpy(a).reshape(2, 6, 7, c).permute(0, 3, 1, 2)  # noqa: E731
+    hh = h
+    for idx, pad in ((1, (0, 2)), (2, (2, 0))):
+        cz, cr, cq = (getattr(gru, f"conv{g}{idx}") for g in "zrq")
+        hx = torch.cat([hh, x], 1)
+        zr = torch.cat([torch.nn.functional.conv2d(hx, cz.weight, None, 1, pad),
+                        torch.nn.functional.conv2d(hx, cr.weight, None, 1, pad)], 1)
+        z, rh = ro.gru_gate(rows(zr), torch.cat([cz.bias, cr.bias]).detach().numpy(), rows(hh))
+        q = torch.nn.functional.conv2d(torch.cat([unrows(rh, 16), x], 1), cq.weight, None, 1, pad)
+        hh = unrows(ro.gru_update(rows(q), cq.bias.detach().numpy(), z, rows(hh)), 16)
+    assert (hh - want).abs().max() <= 5e-3          # f16 storage of z / r*h / h between the convolutions
+
+
+def _rows16(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).half()
+
+
+@pytest.mark.gpu
+def test_gpu_recurrent_block_kernels_match_the_oracle():
+    from counterfactualworldmodels_b200 import _lib
+    lib = _lib.load()
+    s = torch.cuda.current_stream().cuda_stream
+    M, C = 3 * 28 * 28 + 5, 128
+    tol = dict(rtol=2e-3, atol=2e-3)                 # one f16 ulp of O(1) values
+    # bias + relu into a slot of a wider buffer, second destination, flow tail
+    x, bias, tail = _rows16((M, 136), 1, 2.0), torch.randn(128, generator=torch.Generator().manual_seed(2)), _rows16((M, 8), 3)
+    d1 = torch.zeros(M, 384, dtype=torch.float16, device=DEV)
+    d2 = torch.zeros(M, 384, dtype=torch.float16, device=DEV)
+    xd, bd, td = x.to(DEV), bias.to(DEV), tail.to(DEV)
+    _lib.check(lib.cwm_raft_bias_act_f16(xd.data_ptr(), 136, bd.data_ptr(), 1, 128, M, d1[:, 256:].data_ptr(), 384,
+                                         d2[:, 128:].data_ptr(), 384, td.data_ptr(), 8, 2, s))
+    want = ro.bias_act(x[:, :128].float().numpy(), bias.numpy(), True, tail[:, :2].float().numpy())
+    np.testing.assert_allclose(d1[:, 256:].float().cpu().numpy(), want, **tol)
+    np.testing.assert_allclose(d2[:, 128:256].float().cpu().numpy(), want, **tol)
+    assert d1[:, :256].abs().max() == 0 and d2[:, :128].abs().max() == 0 and d2[:, 256:].abs().max() == 0
+    # GRU gates and update
+    zr, b2, hx = _rows16((M, 2 * C), 4, 2.0), torch.randn(2 * C, generator=torch.Generator().manual_seed(5)), _rows16((M, 384), 6)
+    z_out = torch.empty(M, C, dtype=torch.float16, device=DEV)
+    rhx = torch.zeros(M, 384, dtype=torch.float16, device=DEV)
+    hxd = hx.to(DEV)
+    _lib.check(lib.cwm_raft_gru_gate_f16(zr.to(DEV).data_ptr(), b2.to(DEV).data_ptr(), hxd.data_ptr(), 384, C, M,
+                                         z_out.data_ptr(), rhx.data_ptr(), 384, s))
+    z_w, rh_w = ro.gru_gate(zr.float().numpy(), b2.numpy(), hx[:, :C].float().numpy())
+    np.testing.assert_allclose(z_out.float().cpu().numpy(), z_w, **tol)
+    np.testing.assert_allclose(rhx[:, :C].float().cpu().numpy(), rh_w, **tol)
+    q, bq = _rows16((M, C), 7, 2.0), torch.randn(C, generator=torch.Generator().manual_seed(8))
+    dense = torch.empty(M, C, dtype=torch.float16, device=DEV)
+    _lib.check(lib.cwm_raft_gru_update_f16(q.to(DEV).data_ptr(), bq.to(DEV).data_ptr(), z_out.data_ptr(), hxd.data_ptr(), 384,
+                                           C, M, dense.data_ptr(), s))
+    h_w = ro.gru_update(q.float().numpy(), bq.numpy(), z_out.float().cpu().numpy(), hx[:, :C].float().numpy())
+    np.testing.assert_allclose(hxd[:, :C].float().cpu().numpy(), h_w, **tol)
+    assert torch.equal(dense, hxd[:, :C]) and torch.equal(hxd[:, C:].cpu(), hx[:, C:])
+    # flow update
+    B, H, W = 3, 28, 28
+    delta, bf = _rows16((B * H * W, 8), 9), torch.tensor([0.25, -0.5])
+    coords = torch.from_numpy(ro.make_coords(B, H, W, 4, "random"))
+    cd = coords.to(DEV).clone()
+    flow16 = torch.full((B * H * W, 8), 7.0, dtype=torch.float16, device=DEV)
+    _lib.check(lib.cwm_raft_flow_update(delta.to(DEV).data_ptr(), 8, bf.to(DEV).data_ptr(), cd.data_ptr(), B, H, W,
+                                        flow16.data_ptr(), s))
+    c_w, f_w = ro.flow_update(delta.float().numpy(), bf.numpy(), coords.numpy())
+    np.testing.assert_allclose(cd.cpu().numpy(), c_w, rtol=1e-6, atol=1e-5)
+    ok = np.abs(f_w) < 100                          # the far-out-of-bounds centres exceed f16 resolution
+    np.testing.assert_allclose(flow16[:, :2].float().cpu().numpy()[ok], f_w[ok], rtol=2e-3, atol=2e-3)
+    assert flow16[:, 2:].abs().max() == 0
+    # f16 pixel-major lookup == the fp32 lookup rounded
+    from counterfactualworldmodels_b200 import raft
+    f1, f2 = ro.make_fmaps(2, 64, 28, 28, 6)
+    block = raft.CorrBlock(torch.from_numpy(f1).to(DEV), torch.from_numpy(f2).to(DEV))
+    c2 = torch.from_numpy(ro.make_coords(2, 28, 28, 6, "random")).to(DEV)
+    out32 = block(c2)
+    out16 = torch.full((2 * 784, 328), 9.0, dtype=torch.float16, device=DEV)
+    _lib.check(lib.cwm_raft_corr_lookup_f16(raft._ptr_table(block.corr_pyramid), 4, 4, c2.data_ptr(), 2, 28, 28,
+                                            out16.data_ptr(), 328, s))
+    assert torch.equal(out16[:, :324], out32.permute(0, 2, 3, 1).reshape(-1, 324).half()) and out16[:, 324:].abs().max() == 0
+
+
+@pytest.mark.gpu
+def test_gpu_raft_fused_update_block_matches_eager_and_reference():
+    """RAFT-large, mixed precision, 4 iterations: the fused recurrent block (cuDNN convolutions + cwm_raft_*_f16 kernels)
+    against the same block in eager torch ops (f16-level agreement) and against the fp32 flows of the REAL reference."""
+    import make_golden_raft as mg
+    d = load("raft_e2e_large_128px")
+    model = _mirror(False).to(DEV)
+    model.iters = int(d["iters"])
+    model.args.mixed_precision = True
+    x = mg.e2e_frames(2, 128).to(DEV)
+    model.args.fused_update = True
+    fused, fused_b = model(x), model(x, backward=True)
+    model.args.fused_update = False
+    eager = model(x)
+    e_ref = rel_err(fused.cpu().numpy(), d["flow_fwd"])
+    e_ref_b = rel_err(fused_b.cpu().numpy()[:, :, :, ::2, ::2], d["flow_bwd"])
+    e_eager = rel_err(fused.cpu().numpy(), eager.cpu().numpy())
+    print(f"raft fused update: vs reference fp32 {e_ref:.2e} / {e_ref_b:.2e}, vs eager f16 {e_eager:.2e} of scale")
+    assert e_ref <= 1e-2 and e_ref_b <= 1e-2 and e_eager <= 5e-3
+    # flow_init and the shared first frame go through the same path
+    init = torch.full((2, 2, 16, 16), 0.5, device=DEV)
+    model.args.fused_update = True
+    a = model._forward_two_images(x[:, 0] * 255, x[:, 1] * 255, flow_init=init)[1]
+    model.args.fused_update = False
+    b = model._forward_two_images(x[:, 0] * 255, x[:, 1] * 255, flow_init=init)[1]
+    assert rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 5e-3

@@ -60,11 +60,13 @@ def e2e(S):
     variants = (("fp32", False, False, False, None), ("tf32_convs", True, False, False, None),
                 ("f16_autocast_convs", True, True, False, None),
                 ("f16_shared_frame0", True, True, False, 0), ("fp32_shared_frame0", False, False, False, 0),
-                ("f16_half_update_shared_frame0", True, True, True, 0))
+                ("f16_half_update_shared_frame0", True, True, True, 0),
+                ("f16_fused_update_shared_frame0", True, True, "fused", 0), ("f16_fused_update", True, True, "fused", None))
     for name, tf32, amp, half_update, shared in variants:
         torch.backends.cudnn.allow_tf32 = tf32
         model.args.mixed_precision = amp
-        model.args.half_update = half_update
+        model.args.half_update = bool(half_update)
+        model.args.fused_update = half_update == "fused"
         inp = xs if shared is not None else x
         kw = {} if shared is None else {"shared_frame": shared}
         for _ in range(2):
