@@ -239,6 +239,41 @@ def measure_cf_sweep(dev, workload, peaks, with_cpu):
            "tensor_frac_of_sustained_peak": round(S / ms * 1e3 * flops_per_frame(cfg_name, n_vis) / 1e12 /
                                                   peaks["tflops_sustained"], 4),
            "api": "segmentation.FlowGenerator.predict_counterfactual_videos(image, active, passive, shifts)"}
+    # the same sweep continued through the flow network (raft.RAFT, RAFT-large shapes, random
+    # init, mixed precision: cuDNN convolutions + the repo's correlation / lookup / fused recurrent-block kernels), the
+    # flow-sample filter and the mean motion map.  Reported beside the headline, never part of it.
+    try:
+        from counterfactualworldmodels_b200 import raft
+        torch.manual_seed(0)
+        rargs = raft.get_args("")
+        rargs.multiframe, rargs.scale_inputs, rargs.output_dim, rargs.mixed_precision = True, True, None, True
+        G.flow_model = raft.RAFT(rargs).to(dev).eval().requires_grad_(False)
+
+        def flow_step():
+            x = x_host.to(dev, non_blocking=True)
+            a, p_ = a_host.to(dev, non_blocking=True), p_host.to(dev, non_blocking=True)
+            G.set_input(x)
+            ys, flows = G.predict_counterfactual_videos_and_flows(x, a, passive_patches=p_, shifts=shifts,
+                                                                  sample_batch_size=S, raft_iters=24)
+            return G.compute_mean_motion_map(G.filter_flow_samples(flows, a))
+
+        for _ in range(2):
+            flow_step()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            mm = flow_step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_f = e0.elapsed_time(e1) / 3
+        out["with_flow_and_statistics"] = {
+            "value": round(S / ms_f * 1e3, 2), "unit": "counterfactuals/s", "ms_per_step": round(ms_f, 3),
+            "motion_map_finite": bool(torch.isfinite(mm).all()),
+            "api": "FlowGenerator.predict_counterfactual_videos_and_flows -> filter_flow_samples -> compute_mean_motion_map",
+            "flow_model": "raft.RAFT (RAFT-large, 24 iterations, mixed precision, fused recurrent block, shared frame 0)"}
+        G.flow_model = None
+    except Exception as exc:  # the extra line must never take the headline down
+        out["with_flow_and_statistics"] = {"error": repr(exc)[:300]}
     if with_cpu:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import counterfactual_oracle as cfo
