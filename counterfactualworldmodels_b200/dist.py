@@ -131,3 +131,42 @@ def sharded_counterfactual_videos(generator, x, active_patches, passive_patches=
     if not gather:
         return y
     return gather_samples(y, n_total, dst=dst)
+
+
+def sharded_counterfactual_motion_map(generator, x, active_patches, passive_patches=None, shifts=None, num_samples=8,
+                                      sample_batch_size=8, fix_passive=True, frame=1, raft_iters=None, backward=False,
+                                      do_filter=True, normalize_per_sample=False, return_local=False, **kwargs):
+    """One iteration of ``sample_counterfactual_motion_map`` (cwm/models/segmentation.py:434-476) with the S samples of
+    the sweep sharded over the ranks: every rank predicts its slice of the counterfactual videos, runs the flow network
+    and the flow-sample filter on it, sums its flow magnitudes, and the ranks exchange ONE ``[B, H, W]`` all-reduce
+    ("only a final NCCL gather of the predicted frames and flow-derived statistics").
+    Returns the normalised mean motion map ``[B, H, W]`` on every rank (plus the local videos / flows with
+    ``return_local``).  Needs B == 1 like the reference's sweep (segmentation.py:329)."""
+    G = generator
+    multi = dist.is_initialized() and dist.get_world_size() > 1
+    rank = dist.get_rank() if multi else 0
+    world = dist.get_world_size() if multi else 1
+    y_local = sharded_counterfactual_videos(G, x, active_patches, passive_patches, shifts=shifts, num_samples=num_samples,
+                                            sample_batch_size=sample_batch_size, fix_passive=fix_passive, frame=frame,
+                                            gather=False, **kwargs)
+    from . import sampling
+    if len(active_patches.shape) == 2:
+        active_patches = active_patches.unsqueeze(-1)
+    S = len(G.shifts)  # create_motion_counterfactuals records one shift per sample of the WHOLE sweep on every rank
+    lo, hi = shard_bounds(S, rank, world)
+    assert y_local.shape[0] == hi - lo, (y_local.shape, lo, hi)
+    H, W = y_local.shape[-2:]
+    if hi > lo:
+        step = sample_batch_size or (hi - lo)
+        flows = torch.cat([G.predict_flow(y_local[i:i + step], backward=backward, iters=raft_iters)
+                           for i in range(0, hi - lo, step)], 0)
+        active_local = active_patches[..., lo:hi] if active_patches.size(-1) > 1 else active_patches.expand(-1, -1, hi - lo)
+        view = G.filter_flow_samples(flows, active_local, do_filter=do_filter)
+        sums = sampling.flow_magnitude_sum(view, normalize_per_sample=normalize_per_sample)
+    else:  # a rank without samples still joins the all-reduce
+        flows = y_local.new_zeros((0, 1, 2, H, W))
+        sums = torch.zeros(G.x.size(0), H, W, dtype=torch.float32, device=y_local.device)
+    if multi:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    mm = sampling.motion_map_finalize(sums, S)
+    return (mm, y_local, flows) if return_local else mm

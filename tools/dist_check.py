@@ -57,12 +57,35 @@ def main():
     full = sampling.motion_map_finalize(sampling.flow_magnitude_sum(flows_all.reshape(1, S, 2, 224, 224).permute(0, 2, 3, 4, 1)), S)
     err = float((mm - full).abs().max())
     ok = ok and err < 1e-5
+    # the whole iteration sharded: predict -> RAFT flow (fp32, same seeded weights on every rank) -> filter -> ONE
+    # all-reduce of the magnitude sums; against the same sweep run on rank 0 alone
+    from counterfactualworldmodels_b200 import raft
+    torch.manual_seed(0)
+    rargs = raft.get_args("")
+    rargs.multiframe, rargs.scale_inputs, rargs.output_dim = True, True, None
+    G.flow_model = raft.RAFT(rargs).to(dev).eval().requires_grad_(False)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(7)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    mm_sharded = cdist.sharded_counterfactual_motion_map(G, x, a, p, shifts=shifts, sample_batch_size=16, raft_iters=6)
+    ev1.record()
+    torch.cuda.synchronize()
+    sweep_ms = ev0.elapsed_time(ev1)
+    err_sweep = 0.0
+    if rank == 0:
+        flows = torch.cat([G.predict_flow(ref[i:i + 16], iters=6) for i in range(0, S, 16)], 0)
+        G.set_input(x[:, None])
+        mm_single = G.compute_mean_motion_map(G.filter_flow_samples(flows, a))
+        err_sweep = float((mm_sharded - mm_single).abs().max())
+        ok = ok and err_sweep < 1e-4 and bool(torch.isfinite(mm_sharded).all())
     flag = torch.tensor([1 if ok else 0], device=dev)
     if world > 1:
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(json.dumps({"world": world, "samples": S, "sharded_equals_single_gpu": bool(flag.item()),
-                          "motion_map_max_abs_diff": err}))
+                          "motion_map_max_abs_diff": err, "sharded_sweep_with_flow_motion_map_max_abs_diff": err_sweep,
+                          "sharded_sweep_with_flow_ms": round(sweep_ms, 2)}))
     if world > 1:
         dist.destroy_process_group()
     sys.exit(0 if flag.item() else 1)
