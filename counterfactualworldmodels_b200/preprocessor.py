@@ -1,7 +1,7 @@
 """Stream preprocessors of the conjoined models (``cwm/models/preprocessor.py``): which frames of the input video a
 stream sees and how the IMU sequence is shaped.  Pure index-select / reshape -- no arithmetic -- so they stay on the
-host side.  The RAFT-based ``FramePairFlow`` family is out of scope (SURVEY.md section 2,
-rows 5 and 14): ``flowback_rgb01`` & co. need a caller-supplied flow network, see ``FramePairFlow``.
+host side.  The RAFT-based ``FramePairFlow`` family (``flowback_rgb01`` & co.) runs on a
+``raft.RAFT`` (or any RAFT-like module) handed in by the caller or loaded from a checkpoint path, see ``FramePairFlow``.
 """
 import copy
 from functools import partial
@@ -130,16 +130,31 @@ class IMU(Preprocessor):
 
 
 class FramePairFlow(Preprocessor):
-    """preprocessor.py:208-285 computes RAFT optical flow inside the model (out of scope: SURVEY.md section 2 row 14).
-    This holder keeps the frame / channel bookkeeping (2 flow channels, +2 backward, +3 rgb; one output frame) and
-    delegates the image -> stream-input map to a caller-supplied ``flow_model`` callable
-    ``flow_model(x [B,C,T,H,W]) -> [B, num_channels, 1, H, W]`` (e.g. the reference's own FlowBackRGB01 module)."""
+    """preprocessor.py:208-285: the stream input is RAFT optical flow between the two selected frames, optionally with
+    the backward flow and the second frame's RGB appended -- ``flowback_rgb01`` (7 channels, one output frame) is the
+    main stream of the flow2imu model.
+
+    ``flow_model``: a RAFT-like ``nn.Module`` (``counterfactualworldmodels_b200.raft.RAFT`` or the reference's:
+    ``flow_model([B, T, 3, H, W] in [0, 1], iters=, backward=) -> [B, T-1, 2, H, W]``), or ``flow_model_ckpt`` = path of
+    a published RAFT checkpoint (the reference's only way in, :263-264).  The pipeline is the reference's:
+    unnormalise -> cat([flow, backward flow, normalised rgb of frame 1]) -> flow / (size / 2).
+    A plain callable (not an ``nn.Module``) keeps the older contract of this mirror: it receives the selected frames and
+    returns the finished ``[B, num_channels, 1, H, W]`` stream input."""
     num_channels = 2
 
-    def __init__(self, flow_model=None, concat_backward=False, concat_rgb=False, frames_list=None, temporal_dim=2,
-                 **kwargs):
+    def __init__(self, iters=24, backward=False, unnormalize_rgb=True, normalize_flow=True, concat_backward=False,
+                 concat_rgb=False, flow_model_ckpt=None, flow_model=None, frames_list=None, temporal_dim=2, **kwargs):
         super().__init__(frames_list=frames_list, temporal_dim=temporal_dim)
-        self.flow_model = flow_model
+        if flow_model is None and flow_model_ckpt is not None:
+            from .raft import load_raft_model
+            flow_model = load_raft_model(flow_model_ckpt).eval().requires_grad_(False)
+        if isinstance(flow_model, nn.Module):
+            self.flow_model = flow_model.eval().requires_grad_(False)
+        else:
+            object.__setattr__(self, 'flow_model', flow_model)
+        self.iters, self.backward = iters, backward
+        self.unnormalize_rgb, self.normalize_flow = unnormalize_rgb, normalize_flow
+        self._concat_backward, self._concat_rgb = concat_backward, concat_rgb
         self.num_channels = 2 + (2 if concat_backward else 0) + (3 if concat_rgb else 0)
         self.unnormalize = False
         if self.frames_list is not None:
@@ -150,14 +165,54 @@ class FramePairFlow(Preprocessor):
             return len(self.frames_list) - 1 if self.frames_list is not None else None
         return self.num_frames
 
+    def _imagenet(self, x, inverse):
+        shape = [1] * x.dim()
+        shape[self.c_dim] = 3
+        mean = torch.as_tensor(IMAGENET_DEFAULT_MEAN, device=x.device, dtype=x.dtype).view(shape)
+        std = torch.as_tensor(IMAGENET_DEFAULT_STD, device=x.device, dtype=x.dtype).view(shape)
+        return x * std + mean if inverse else (x - mean) / std      # models/utils.py:15-31
+
+    def get_flow(self, x, **kwargs):
+        """preprocessor.py:279-285: the flow network takes [B, T, C, H, W]."""
+        if self.t_dim == 2 and self.c_dim == 1:
+            return self.flow_model(x.transpose(self.t_dim, self.c_dim), **kwargs).transpose(self.t_dim, self.c_dim)
+        return self.flow_model(x, **kwargs)
+
+    def _normalize_flow(self, flow):
+        """preprocessor.py:266-277: flow in units of half the image size; the rgb channels are left alone."""
+        h, w = flow.shape[-2:]
+        size = torch.as_tensor([w, h]).to(flow).view(1, 2, 1, 1, 1)
+        if self._concat_backward:
+            size = torch.cat([size, size], 1)
+        if self._concat_rgb:
+            size = torch.cat([size, 2 * torch.ones((1, 3, 1, 1, 1)).to(flow)], 1)
+        if self.c_dim == 2:
+            size = size.transpose(self.t_dim, self.c_dim)
+        return flow / (size / 2.0)
+
     def forward(self, x, *args, **kwargs):
         if self.flow_model is None:
             raise NotImplementedError(
-                "flow-based stream inputs need an optical-flow network (RAFT is out of scope of the B200 path): pass "
-                "main_input_kwargs={'flow_model': callable} producing the [B, %d, 1, H, W] stream input" %
-                self.num_channels)
+                "flow-based stream inputs need an optical-flow network: pass main_input_kwargs={'flow_model': "
+                "raft.RAFT(...)} or {'flow_model_ckpt': '<raft-large.pth>'} (a plain callable producing the "
+                "[B, %d, 1, H, W] stream input is accepted too)" % self.num_channels)
         self.set_input_dims(x)
-        y = self.flow_model(self.get_input_frames(x))
+        x = self.get_input_frames(x)
+        if not isinstance(self.flow_model, nn.Module):
+            y = self.flow_model(x)
+        else:
+            if self.unnormalize_rgb:
+                x = self._imagenet(x, inverse=True)
+            parts = [self.get_flow(x, iters=self.iters, backward=self.backward)]
+            if self._concat_backward:
+                parts.append(self.get_flow(x, iters=self.iters, backward=(not self.backward)))
+            if self._concat_rgb:
+                rgb = self._imagenet(x, inverse=False) if self.unnormalize_rgb else x
+                idx = torch.tensor(self.frames_list[1:]).long().to(x.device)
+                parts.append(torch.index_select(rgb, dim=self.t_dim, index=idx))
+            y = torch.cat(parts, self.c_dim)
+            if self.normalize_flow:
+                y = self._normalize_flow(y)
         self.set_output_dims(y)
         return y
 

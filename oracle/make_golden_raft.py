@@ -149,6 +149,28 @@ def main():
         print(f"{name}: |flow| max {fwd.abs().max():.3f} mean {fwd.abs().mean():.3f}; mirror init == reference init "
               f"({len(sd)} tensors) | {os.path.getsize(path) / 1e3:.0f} KB")
 
+    # ---- FlowBackRGB01 (preprocessor.py:208-285, :340-345): the flow2imu main-stream input -----------------------
+    import tempfile
+    import cwm.models.preprocessor as ref_pre
+    torch.manual_seed(0)
+    args = ref_raft.get_args("")
+    args.multiframe, args.scale_inputs, args.output_dim = True, True, None
+    with tempfile.TemporaryDirectory() as tmp:
+        ckpt = os.path.join(tmp, "raft-large.pth")
+        torch.save(ref_raft.RAFT(args).state_dict(), ckpt)      # the reference can only load RAFT from a file
+        pre = ref_pre.get_preprocessor('flowback_rgb01', temporal_dim=2, iters=3, flow_model_ckpt=ckpt)
+    frames = e2e_frames(2, 128)                                  # [B, T, C, H, W] in [0, 1]
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1, 1)
+    x = (frames.transpose(1, 2) - mean) / std                    # the predictor's input: [B, C, T, H, W], normalised
+    with torch.no_grad():
+        y = pre(x)
+    assert y.shape == (2, 7, 1, 128, 128) and pre.get_num_frames() == 1 and pre.num_channels == 7
+    path = os.path.join(GOLDEN_DIR, "raft_flowback_rgb01_128px.npz")
+    np.savez_compressed(path, y=y.numpy()[:, :, :, ::2, ::2], iters=np.array(3))
+    print(f"raft_flowback_rgb01_128px: {tuple(y.shape)} |flow ch| max {y[:, :4].abs().max():.4f} | "
+          f"{os.path.getsize(path) / 1e3:.0f} KB")
+
 
 E2E_ITERS = 4
 

@@ -488,3 +488,61 @@ def test_gpu_raft_fused_update_block_matches_eager_and_reference():
     model.args.fused_update = False
     b = model._forward_two_images(x[:, 0] * 255, x[:, 1] * 255, flow_init=init)[1]
     assert rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 5e-3
+
+
+# ------------------------------------------------------------------------------------------------ FlowBackRGB01
+class _StubFlow(torch.nn.Module):
+    """RAFT-like call signature; flow = (mean colour difference, its negative), doubled for the backward direction."""
+
+    def forward(self, x, iters=None, backward=False):
+        d = (x[:, 1:] - x[:, :-1]).mean(2, keepdim=True) * (2.0 if backward else 1.0)
+        return torch.cat([d, -d], 2)
+
+
+def test_frame_pair_flow_pipeline_with_a_stub_flow_network():
+    """preprocessor.py:208-285 restated by hand: unnormalise -> [flow, backward flow, normalised rgb of frame 1] ->
+    flow / (size / 2)."""
+    from counterfactualworldmodels_b200 import preprocessor
+    pre = preprocessor.get_preprocessor('flowback_rgb01', temporal_dim=2, iters=5, flow_model=_StubFlow())
+    assert pre.num_channels == 7 and pre.get_num_frames() == 1
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 3, 3, 8, 12, generator=g)                       # [B, C, T = 3, H, W], normalised
+    y = pre(x)
+    assert y.shape == (2, 7, 1, 8, 12)
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1, 1)
+    raw = x[:, :, :2] * std + mean
+    d = (raw[:, :, 1:] - raw[:, :, :1]).mean(1, keepdim=True)
+    size = torch.tensor([12.0, 8.0]).view(1, 2, 1, 1, 1) / 2
+    torch.testing.assert_close(y[:, 0:2], torch.cat([d, -d], 1) / size)
+    torch.testing.assert_close(y[:, 2:4], 2 * torch.cat([d, -d], 1) / size)
+    torch.testing.assert_close(y[:, 4:7], (raw[:, :, 1:2] - mean) / std)
+    with pytest.raises(NotImplementedError, match="flow_model"):
+        preprocessor.get_preprocessor('flow01')(x)
+    with pytest.raises(ValueError, match="not a valid raft checkpoint"):
+        preprocessor.get_preprocessor('flow01', flow_model_ckpt="/nonexistent/raft-large.pth")
+    legacy = preprocessor.get_preprocessor('flow01', flow_model=lambda frames: frames[:, :2, :1] * 0 + 1.0)
+    assert legacy(x).shape == (2, 2, 1, 8, 12)                          # a plain callable returns the finished input
+
+
+@pytest.mark.gpu
+def test_gpu_flowback_rgb01_matches_the_reference_preprocessor():
+    """`get_preprocessor('flowback_rgb01')` (the flow2imu main-stream input) with raft.RAFT under the
+    reference's seeded init against the output of the REAL reference preprocessor + RAFT (3 iterations, fp32)."""
+    import make_golden_raft as mg
+    from counterfactualworldmodels_b200 import preprocessor
+    d = load("raft_flowback_rgb01_128px")
+    pre = preprocessor.get_preprocessor('flowback_rgb01', temporal_dim=2, iters=int(d["iters"]),
+                                        flow_model=_mirror(False).to(DEV))
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1, 1)
+    x = ((mg.e2e_frames(2, 128).transpose(1, 2) - mean) / std).to(DEV)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        y = pre(x).cpu().numpy()[:, :, :, ::2, ::2]
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert y.shape == d["y"].shape
+    assert rel_err(y[:, :4], d["y"][:, :4]) <= 1e-4          # forward + backward flow, in units of half the image
+    assert rel_err(y[:, 4:], d["y"][:, 4:]) <= 1e-6          # the rgb channels only go through normalise / unnormalise
