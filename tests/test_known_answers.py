@@ -64,3 +64,21 @@ def test_weights_regenerate_identically():
     m = vmae.PretrainVisionTransformer(**synthetic.model_kwargs("tiny_4x4"))
     synthetic.init_weights_(m, seed=1, style="perturbed")
     assert synthetic.weights_checksum(m) == pytest.approx(float(g["weights_checksum"][0]), rel=0, abs=1e-9)
+
+
+def test_flow2imu_parameter_count_with_raft_inside_the_preprocessor():
+    """ipynb:355-364: the flow2imu model reports `Total: 135730048` (main 92,956,480 / ctx 23,272,512 / conj 19,501,056)
+    trainable parameters; the frozen RAFT-large inside its `flowback_rgb01` preprocessor (preprocessor.py:263-264; here
+    `raft.RAFT` handed in through `main_input_kwargs`) adds 5,257,536 more to the module and its state_dict."""
+    from counterfactualworldmodels_b200 import conjoined_vmae as conj
+    from counterfactualworldmodels_b200 import raft
+    args = raft.get_args("")
+    args.multiframe, args.scale_inputs, args.output_dim = True, True, None
+    m = conj.imu400_8x8patch_2frames_1tube_flowbackrgb01(main_input_kwargs={'flow_model': raft.RAFT(args)})
+    count = lambda mod: sum(p.numel() for p in mod.parameters())  # noqa: E731
+    assert count(m.get_main_input.flow_model) == 5257536
+    assert count(m.main_stream) == 92956480 and count(m.context_stream) == 23272512
+    assert sum(p.numel() for p in m.parameters() if p.requires_grad) == 135730048
+    assert count(m) == 135730048 + 5257536
+    assert any(k.startswith("get_main_input.flow_model.fnet.") for k in m.state_dict())
+    assert m.get_main_input.num_channels == 7 and m.get_main_input.get_num_frames() == 1
