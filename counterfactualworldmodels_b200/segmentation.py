@@ -3,9 +3,9 @@ SURVEY.md section 8(f): the callers right above the VMAE hot path.
 
 Built so far (rank 1): ``create_motion_counterfactuals`` (:279-343) and ``predict_counterfactual_videos_and_flows``
 (:345-432) -- the per-sample Python loop over ``ShiftPatchesAndMask`` becomes one mask kernel plus a *virtual* video
-the VMAE forward reads directly, so the S prompts ``x_mocos`` (1.2 MB each) are never written to HBM.  RAFT stays out
-of scope: ``flow_model`` is a caller-supplied ``nn.Module`` (the reference's own constructor accepts one, :70-78);
-without it the flow entry points raise.
+the VMAE forward reads directly, so the S prompts ``x_mocos`` (1.2 MB each) are never written to HBM.  The flow
+network is ``raft.RAFT`` (rank 3) or any ``nn.Module`` the caller hands in (the reference's own constructor accepts one,
+:70-78), or RAFT loaded from ``flow_model_load_path``; without one the flow entry points raise.
 
 Same method names, argument meaning and error behaviour as the reference.
 """
@@ -40,7 +40,8 @@ class FlowGenerator(PredictorBasedGenerator):
         'resize': False
     }
 
-    def __init__(self, *args, flow_model=None, raft_iters=24, flow_sample_filter=None,
+    def __init__(self, *args, flow_model=None, flow_model_load_path=None, flow_model_kwargs={}, raft_iters=24,
+                 flow_sample_filter=None,
                  patch_sampling_func=RotatedTableEnergyMaskingGenerator,
                  patch_sampling_kwargs=default_patch_sampling_kwargs, **kwargs):
         super().__init__(*args, **kwargs)
@@ -52,12 +53,12 @@ class FlowGenerator(PredictorBasedGenerator):
         self.set_patch_sampler()
         self.flow_sample_filter = flow_sample_filter if flow_sample_filter is not None else \
             FlowSampleFilter(**self.default_flow_filter_params)
-        if flow_model is not None:
-            assert isinstance(flow_model, nn.Module)
-            self.flow_model = flow_model.eval().requires_grad_(False)
+        if flow_model is not None or flow_model_load_path is not None:
+            self.set_flow_model(flow_model=flow_model, flow_model_load_path=flow_model_load_path, **flow_model_kwargs)
         else:
-            self.flow_model = None  # the reference would load RAFT here (:70-75); RAFT is SURVEY 8(f) rank 3
+            self.flow_model = None  # the reference insists on a checkpoint here (:70-75); this mirror defers the error
         self.raft_iters = raft_iters
+        self.set_raft_iters(raft_iters)
         self.shifts = None
 
     # ---- small helpers (segmentation.py:130-140, :247-248) ----
@@ -80,8 +81,8 @@ class FlowGenerator(PredictorBasedGenerator):
     def predict_flow(self, vid, backward=False, iters=None, **kwargs):
         """segmentation.py:142-153."""
         if self.flow_model is None:
-            raise RuntimeError("FlowGenerator.predict_flow needs a flow_model (RAFT is outside the B200 hot path; "
-                               "pass flow_model=<nn.Module> to the constructor)")
+            raise RuntimeError("FlowGenerator.predict_flow needs a flow_model: pass flow_model=raft.RAFT(...) / any "
+                               "nn.Module, or flow_model_load_path=<raft-large.pth>, to the constructor")
         if iters is not None and hasattr(self.flow_model, 'iters'):
             self.flow_model.iters = iters
         from .raft import RAFT
@@ -91,6 +92,72 @@ class FlowGenerator(PredictorBasedGenerator):
             # predictor returns it bit for bit) -> RAFT encodes that frame once instead of once per sample
             kwargs['shared_frame'] = 0
         return self.flow_model(vid, backward=backward, **kwargs).to(vid)
+
+    def set_flow_model(self, flow_model=None, flow_model_load_path=None, **kwargs):
+        """segmentation.py:71-84: a given module, or RAFT loaded from a published checkpoint."""
+        if flow_model is None:
+            from .raft import load_raft_model
+            flow_model = load_raft_model(load_path=flow_model_load_path, multiframe=True, scale_inputs=True, **kwargs)
+        else:
+            assert isinstance(flow_model, nn.Module)
+        self.flow_model = flow_model.eval().requires_grad_(False)
+
+    def set_raft_iters(self, iters=None):
+        """segmentation.py:86-90."""
+        from .raft import RAFT
+        for m in self.modules():
+            if isinstance(m, RAFT) or type(m).__name__ == 'RAFT':
+                m.iters = iters
+
+    def predict_video_and_flow(self, x=None, mask=None, backward=False, propagate_error=False, **kwargs):
+        """segmentation.py:170-197: roll the predictor over the movie, then the flow of (frame t, predicted t+1)."""
+        x = self.x if x is None else x
+        mask = self.mask if mask is None else mask
+        num_frames, dt = x.size(1), self.sequence_length
+        x_pred = [x[:, 0:1]]
+        for t in range(num_frames - dt + 1):
+            x_pred.append(self.predict(x[:, t:t + dt], mask, frame=1, **kwargs))
+        x_pred = torch.cat(x_pred, 1)
+        if propagate_error:
+            return x_pred, self.predict_flow(x_pred, backward, **kwargs)
+        f_pred = []
+        for t in range(num_frames - dt + 1):
+            _x = torch.cat([x[:, t:t + 1], x_pred[:, t + 1:t + 2], x[:, t + 2:t + dt]], 1)
+            f_pred.append(self.predict_flow(_x, backward, **kwargs))
+        return x_pred, torch.cat(f_pred, 1)
+
+    def predict_flow_per_sample(self, x, masks, x_context=None, mask_context=None, timestamps=None, backward=False,
+                                **kwargs):
+        """segmentation.py:199-208: flows of the S sample predictions as [B, T-1, 2, H, W, S]."""
+        S = masks.size(-1)
+        x_preds = self.predict_per_sample(x, masks, x_context=x_context, mask_context=mask_context,
+                                          timestamps=timestamps, frame=None, split_samples=False)
+        flow = self.predict_flow(x_preds, backward, **kwargs)
+        p_dims = tuple(range(2, len(flow.shape) + 1))
+        return flow.view(-1, S, *flow.shape[1:]).permute(0, *p_dims, 1)
+
+    def predict_video_and_flow_per_sample(self, x, masks, x_context=None, mask_context=None, timestamps=None,
+                                          backward=False, **kwargs):
+        """segmentation.py:210-245."""
+        assert len(masks.shape) == 3
+        B, _, S = masks.shape
+        tile = lambda z: self.sample_tile(z, S) if (z is not None and z.size(0) != B * S) else z  # noqa: E731
+        ys = self.predict_per_sample(x, masks, x_context=tile(x_context), mask_context=tile(mask_context),
+                                     timestamps=tile(timestamps), frame=None, split_samples=False, **kwargs)
+        flows = self.predict_flow(ys, backward)
+        p_dims = tuple(range(2, len(flows.shape) + 1))
+        ys = ys.view(-1, S, *ys.shape[1:]).permute(0, *p_dims, 1)
+        flows = flows.view(-1, S, *flows.shape[1:]).permute(0, *p_dims, 1)
+        return ys, flows
+
+    def compute_flow_samples_magnitude(self, flows, normalize=True, dim=-4, eps=1e-2):
+        """segmentation.py:250-255 (the per-sample normalised magnitudes themselves; the mean motion map fuses this
+        into ``cwm_flow_magnitude_sum`` instead of materialising it)."""
+        flow_mags = flows.square().sum(dim, True).sqrt().to(flows.dtype)
+        if normalize:
+            flow_mags = flow_mags - flow_mags.amin((-3, -2), True)
+            flow_mags = flow_mags / flow_mags.amax((-3, -2), True).clamp(min=eps)
+        return flow_mags
 
     # ---- SURVEY 8(f) rank 4: which patches to move (host-side mask bookkeeping, reference RNG streams) ----
     def set_patch_sampler(self, num_visible=1, mask_ratio=None, **kwargs):

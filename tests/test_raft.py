@@ -546,3 +546,33 @@ def test_gpu_flowback_rgb01_matches_the_reference_preprocessor():
     assert y.shape == d["y"].shape
     assert rel_err(y[:, :4], d["y"][:, :4]) <= 1e-4          # forward + backward flow, in units of half the image
     assert rel_err(y[:, 4:], d["y"][:, 4:]) <= 1e-6          # the rgb channels only go through normalise / unnormalise
+
+
+@pytest.mark.gpu
+def test_gpu_flow_generator_video_and_flow_entry_points():
+    """`predict_video_and_flow`, `predict_flow_per_sample`, `predict_video_and_flow_per_sample` (segmentation.py:170-245)
+    are compositions of `predict` and `predict_flow`: shapes, the sample axis, and consistency with doing it by hand."""
+    from counterfactualworldmodels_b200 import segmentation, synthetic, vmae
+    cfg = "base_8x8"                                        # 224 px: RAFT's 4-level pyramid needs >= 128 px frames
+    model = vmae.PretrainVisionTransformer(**synthetic.model_kwargs(cfg))
+    synthetic.init_weights_(model, seed=0)
+    flow_model = _mirror(True).to(DEV)                      # RAFT-small keeps the test light
+    G = segmentation.FlowGenerator(predictor=model.to(DEV).eval(), imagenet_normalize_inputs=True, temporal_dim=2,
+                                   flow_model=flow_model, raft_iters=2)
+    assert flow_model.iters == 2
+    H, W = synthetic.image_hw(cfg)
+    x = synthetic.make_video(2, (H, W), seed=1).to(DEV)
+    S = 3
+    masks = torch.stack([synthetic.make_mask(2, model.mask_size, num_clumps=2, seed=s) for s in range(S)], -1).to(DEV)
+    G.set_input(x)
+    ys, flows = G.predict_video_and_flow_per_sample(x, masks)
+    assert tuple(ys.shape) == (2, 2, 3, H, W, S) and tuple(flows.shape) == (2, 1, 2, H, W, S)
+    only = G.predict_flow_per_sample(x, masks)
+    assert torch.equal(only, flows)
+    by_hand = G.predict_flow(G.predict(x, masks[..., 1], frame=None))
+    assert (flows[..., 1] - by_hand).abs().max() <= 1e-4 * max(1.0, float(by_hand.abs().max()))
+    x_pred, f_pred = G.predict_video_and_flow(x, masks[..., 0])
+    assert tuple(x_pred.shape) == (2, 2, 3, H, W) and tuple(f_pred.shape) == (2, 1, 2, H, W)
+    assert torch.equal(x_pred[:, 0], x[:, 0])
+    mags = G.compute_flow_samples_magnitude(flows[:, 0])
+    assert float(mags.amin()) == 0.0 and float(mags.amax()) <= 1.0 + 1e-6
