@@ -565,13 +565,22 @@ def test_gpu_flow_generator_video_and_flow_entry_points():
     S = 3
     masks = torch.stack([synthetic.make_mask(2, model.mask_size, num_clumps=2, seed=s) for s in range(S)], -1).to(DEV)
     G.set_input(x)
-    ys, flows = G.predict_video_and_flow_per_sample(x, masks)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False          # TF32 convolutions pick batch-size dependent algorithms
+    try:
+        ys, flows = G.predict_video_and_flow_per_sample(x, masks)
+        only = G.predict_flow_per_sample(x, masks)
+        y1 = G.predict(x, masks[..., 1], frame=None)
+        by_hand = G.predict_flow(y1)
+        x_pred, f_pred = G.predict_video_and_flow(x, masks[..., 0])
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
     assert tuple(ys.shape) == (2, 2, 3, H, W, S) and tuple(flows.shape) == (2, 1, 2, H, W, S)
-    only = G.predict_flow_per_sample(x, masks)
-    assert torch.equal(only, flows)
-    by_hand = G.predict_flow(G.predict(x, masks[..., 1], frame=None))
-    assert (flows[..., 1] - by_hand).abs().max() <= 1e-4 * max(1.0, float(by_hand.abs().max()))
-    x_pred, f_pred = G.predict_video_and_flow(x, masks[..., 0])
+    assert torch.equal(ys[..., 1], y1)               # the predictor is batch-invariant bit for bit
+    assert rel_err(only.cpu().numpy(), flows.cpu().numpy()) <= 1e-5
+    e = rel_err(flows[..., 1].cpu().numpy(), by_hand.cpu().numpy())
+    print(f"per-sample flow vs by hand: {e:.2e} of scale (|flow| max {float(by_hand.abs().max()):.2f})")
+    assert e <= 1e-4
     assert tuple(x_pred.shape) == (2, 2, 3, H, W) and tuple(f_pred.shape) == (2, 1, 2, H, W)
     assert torch.equal(x_pred[:, 0], x[:, 0])
     mags = G.compute_flow_samples_magnitude(flows[:, 0])
