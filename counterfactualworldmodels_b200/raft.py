@@ -603,12 +603,6 @@ class RAFT(nn.Module):
         has_mask_head = isinstance(self.update_block, BasicUpdateBlock)
         update_block = self.update_block
         half_update = amp and bool(getattr(self.args, 'half_update', True))
-        if half_update:
-            # mixed precision without autocast's per-call casts and cuDNN's NCHW<->NHWC transforms: the recurrent
-            # block runs on f16 channels-last activations and an f16 channels-last copy of its weights
-            update_block = self._half_update_block()
-            to16 = lambda t: t.to(dtype=torch.float16, memory_format=torch.channels_last)  # noqa: E731
-            net, inp = to16(net), to16(inp)
         if (half_update and test_mode and has_mask_head and self.output_block is None and iters > 0
                 and bool(getattr(self.args, 'fused_update', True))):
             # RAFT-large, inference: the recurrent block on cuDNN convolutions + the cwm_raft_*_f16 kernels
@@ -620,6 +614,12 @@ class RAFT(nn.Module):
                 up_mask = fused.step(st, corr_fn, coords1, emit=(itr + 1 == iters))
             flow_low = coords1 - coords0
             return flow_low, self.upsample_flow(flow_low, up_mask)
+        if half_update:
+            # mixed precision without autocast's per-call casts and cuDNN's NCHW<->NHWC transforms: the recurrent
+            # block runs on f16 channels-last activations and an f16 channels-last copy of its weights
+            update_block = self._half_update_block()
+            to16 = lambda t: t.to(dtype=torch.float16, memory_format=torch.channels_last)  # noqa: E731
+            net, inp = to16(net), to16(inp)
         predictions = []
         flow_up = None
         for itr in range(iters):
@@ -637,7 +637,7 @@ class RAFT(nn.Module):
             coords1 = coords1 + delta_flow.float()
             if not emit:
                 continue
-            out = self.output_block(net) if self.output_block is not None else coords1 - coords0
+            out = self.output_block(net.float()) if self.output_block is not None else coords1 - coords0
             flow_up = upflow8(out) if up_mask is None else self.upsample_flow(out, up_mask)
             predictions.append(flow_up)
         if test_mode:
