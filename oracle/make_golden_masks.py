@@ -61,6 +61,19 @@ def draw_all(masking, sampling, seg_cls, vmae_mod):
     out["flowgen_energy_beta_s4_vis2"] = G.sample_patches_from_energy(energy_map(1, 32, 32, 2), num_samples=4,
                                                                       num_visible=2, beta=0.5)
     out["flowgen_zero_visible"] = G.sample_patches_from_energy(None, num_samples=2, num_visible=0)
+    # IMU token masks (masking.py:402-476): missing-data tokens forced masked, full-mask / full-visible draws
+    miss = torch.zeros(4, 25, dtype=torch.bool)
+    miss[1, :7] = True
+    miss[3, 20:] = True
+    gen = masking.MissingDataImuMaskGenerator(input_size=25, mask_ratio=0.4, full_mask_prob=0, full_vis_prob=0,
+                                              truncation_mode='none', create_on_cpu=True, seed=8)
+    out["imu_missing_none_r40_seed8"] = gen(miss)
+    gen = masking.MissingDataImuMaskGenerator(input_size=25, mask_ratio=0.4, full_mask_prob=0.3, full_vis_prob=0.2,
+                                              truncation_mode='max', seed=9)
+    out["imu_missing_max_fullprob_seed9"] = torch.stack([gen(miss.clone()) for _ in range(4)], 0)
+    gen = masking.ImuFullMaskGenerator(input_size=(5, 5), mask_ratio=0.5, clumping_factor=5, full_mask_prob=0.5,
+                                       full_mask_per_example=True, seed=10)
+    out["imu_full_per_example_seed10"] = gen(miss)
     return out
 
 
