@@ -68,7 +68,7 @@ def mask_size(name):
     return (kw["num_frames"] // kw["tubelet_size"], h // kw["patch_size"][0], w // kw["patch_size"][1])
 
 
-def init_weights_(model, seed=0, style="reference"):
+def init_weights_(model, seed=0, style="reference", skip=("get_main_input.flow_model.",)):
     """Overwrites every parameter of ``model`` (ours or the reference's) deterministically.
 
     ``style="reference"`` follows the reference's initialisation *distributions* (vmae.py:100-107, :371): xavier
@@ -79,6 +79,8 @@ def init_weights_(model, seed=0, style="reference"):
     sd = model.state_dict()
     with torch.no_grad():
         for name in sorted(sd.keys()):
+            if name.startswith(tuple(skip)):  # a RAFT inside a flow preprocessor keeps its own (seeded) init
+                continue
             t = sd[name]
             if name.endswith(("mask_token", "null_token_enc", "null_token_dec", "dummy_token")):
                 v = torch.empty(t.shape).normal_(0, 0.02, generator=g).clamp_(-0.02, 0.02)
@@ -160,6 +162,16 @@ CONJOINED = {
         kind="padded", img_size=32, patch_size=(4, 4), enc=(256, 4, 4), dec=(128, 2, 2), ctx_enc_dim=128,
         ctx_dec_dim=64, seq_len=80, main_pad=8, ctx_pad=5, enc_layers=[0, 3], dec_layers=True, main_chans=3,
         main_frames=[0, 1]),
+    # the pair an ImuConditionedFlowGenerator drives, at 128 px so that RAFT's 4-level pyramid exists: an IMU-conditioned
+    # padded predictor and a flow2imu model whose main-stream input is the real 'flowback_rgb01' preprocessor
+    "conj_padded_128": dict(
+        kind="padded", img_size=128, patch_size=(4, 4), enc=(256, 4, 4), dec=(128, 2, 2), ctx_enc_dim=128,
+        ctx_dec_dim=64, seq_len=80, main_pad=8, ctx_pad=5, enc_layers=[0, 3], dec_layers=True, main_chans=3,
+        main_frames=[0, 1]),
+    "conj_flow2imu_128": dict(
+        kind="full", img_size=128, patch_size=(8, 8), enc=(256, 3, 4), dec=(128, 2, 2), ctx_enc_dim=128,
+        ctx_dec_dim=64, seq_len=80, main_pad=0, ctx_pad=0, enc_layers=[0, -1], dec_layers=True, main_chans=7,
+        main_frames=[1], main_input='flowback_rgb01'),
     # non-padded, dummy-token IMU context, 7-channel single-frame main stream (the flow2imu topology, a17)
     "conj_flow2imu_small": dict(
         kind="full", img_size=32, patch_size=(8, 8), enc=(256, 3, 4), dec=(128, 2, 2), ctx_enc_dim=128,
@@ -168,7 +180,7 @@ CONJOINED = {
 }
 
 
-def build_conjoined(ns, name, preproc_ns=None):
+def build_conjoined(ns, name, preproc_ns=None, main_input_kwargs=None):
     """Builds the conjoined model `name` from the classes of module `ns` (ours: counterfactualworldmodels_b200.
     conjoined_vmae; or the reference's cwm.models.VideoMAE.conjoined_vmae -- same constructor signatures)."""
     import copy
@@ -190,7 +202,9 @@ def build_conjoined(ns, name, preproc_ns=None):
         import importlib
         preproc_ns = importlib.import_module(ns.__name__.rsplit(".", 1)[0] + ".preprocessor") \
             if ns.__name__.startswith("counterfactualworldmodels_b200") else importlib.import_module("cwm.models.preprocessor")
-    if c["main_chans"] == 3:
+    if c.get("main_input"):  # a named preprocessor (e.g. 'flowback_rgb01': needs flow_model / flow_model_ckpt kwargs)
+        main_input, main_input_kwargs = c["main_input"], dict(main_input_kwargs or {})
+    elif c["main_chans"] == 3:
         main_input, main_input_kwargs = 'rgb01', {'unnormalize': False}
     else:  # a pass-through of frame 1 of a 7-channel input stands in for the RAFT-based 'flowback_rgb01' preprocessor
         main_input = partial(preproc_ns.Preprocessor, num_channels=c["main_chans"], frames_list=c["main_frames"])
