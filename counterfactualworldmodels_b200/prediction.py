@@ -97,9 +97,11 @@ class PredictorBasedGenerator(nn.Module):
     """The slice of cwm/models/prediction.py:16-540 that brackets the predictor call."""
 
     def __init__(self, predictor=None, imagenet_normalize_inputs=False, temporal_dim=2, seed=0,
-                 mask_generator=None, max_shift_fraction=0.15, error_func=nn.MSELoss(reduction='none'), **kwargs):
+                 mask_generator=None, max_shift_fraction=0.15, error_func=nn.MSELoss(reduction='none'),
+                 keypoint_predictor=None, **kwargs):
         super().__init__()
         self.error_func = error_func
+        self.keypoint_predictor = keypoint_predictor  # prediction.py:66-71 (any module: video -> [B, 1, 1, H, W] logits)
         if predictor is None:
             raise ValueError("There is no predictor set for this generator and no model to load to")
         self.predictor = predictor
@@ -297,6 +299,20 @@ class PredictorBasedGenerator(nn.Module):
         if not bool((counts == counts[0]).all()):
             raise RuntimeError("shape mismatch: rows of the mask have different numbers of masked tokens")
         return unpatchify_scatter(y, _x, inv, int(counts[0]), patch_size)
+
+    def predict_keypoints_map(self, x, *args, **kwargs):
+        """prediction.py:815-820."""
+        assert len(x.shape) == 5, x.shape
+        if self.keypoint_predictor is None:
+            return torch.ones_like(x[:, 0:1, 0:1])
+        return self.keypoint_predictor(x, *args, **kwargs)
+
+    def predict_keypoints_distribution(self, x, power=8, eps=1e-3):
+        """prediction.py:822-827: sigmoid(logits)^power, rescaled to [0, 1] over the image."""
+        value = self.predict_keypoints_map(x).squeeze(-3)
+        value = (value.sigmoid()) ** power
+        value = value - value.amin((-2, -1))
+        return value / value.amax((-2, -1)).clamp(min=eps)
 
     def forward(self, x, mask=None, frame=None, *args, **kwargs):
         return self.predict(x, mask, frame, *args, **kwargs)

@@ -577,11 +577,17 @@ class ImuConditionedFlowGenerator(FlowGenerator):
     sweep: the IMU of the static movie is predicted ONCE per image, then all S counterfactuals are conditioned on it."""
     default_imu_generator_kwargs = {'head_mask_ratio': 1}
 
-    def __init__(self, *args, predictor, head_motion_predictor, head_motion_load_path=None,
+    def __init__(self, *args, predictor, head_motion_predictor=None, head_motion_load_path=None,
                  head_motion_generator=ImuGenerator, head_motion_kwargs=default_imu_generator_kwargs,
                  head_motion_mask_generator=None, flow_model=None, flow_model_load_path=None, **kwargs):
         super().__init__(*args, predictor=predictor, flow_model=flow_model, flow_model_load_path=flow_model_load_path,
                          **kwargs)
+        if head_motion_predictor is None:
+            # extension: a predictor that is NOT conditioned on head motion (the plain VMAEs of BASELINE configs 1-4)
+            # -- the reference's docstring promises this works (movability.py:18-20) but its constructor cannot be
+            # called without a head-motion model; here the sweep then runs unconditioned
+            self.head_motion_generator = None
+            return
         head_motion_kwargs = copy.deepcopy(head_motion_kwargs)
         self._update_head_motion_kwargs(head_motion_load_path, head_motion_kwargs)
         if not isinstance(head_motion_predictor, nn.Module):
@@ -664,6 +670,8 @@ class ImuConditionedFlowGenerator(FlowGenerator):
     def predict_counterfactual_videos_and_flows(self, x, *args, head_motion=None, timestamps=None,
                                                 mask_head_motion=False, static_head_motion=True, **kwargs):
         """segmentation.py:931-963: head motion once per image, then the conditioned counterfactual sweep."""
+        if self.head_motion_generator is None:
+            return super().predict_counterfactual_videos_and_flows(x, *args, **kwargs)
         self.set_input(x)
         # like the reference, the sweep's own arguments are forwarded: the first positional one (the active patches)
         # lands in ``mask`` and the call returns the head motion before anything else is used
