@@ -352,3 +352,39 @@ class MissingDataImuMaskGenerator(ImuFullMaskGenerator):
         assert list(missing.shape) == list(masks.shape), (missing.shape, masks.shape)
         merged = torch.maximum(masks, missing.to(masks.device))
         return merged if self.mode in ['none', None] else self.rect(merged)
+
+
+# ---- patch neighbourhoods (masking.py:32-71): used by the GUI helpers get_nearby_patches / generate_cutout_mask ------
+def patch_distance_transform(masks, self_mask=True):
+    """For each patch the L-inf distance to the nearest visible patch, in units of half the grid (masking.py:32-56).
+    masks bool [B, T, H, W] (True = masked) -> float [B, T, H, W]."""
+    B, T, H, W = masks.shape
+    flat = masks.view(B * T, H, W)
+    hh, ww = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    grid = torch.stack([hh, ww], -1).to(masks.device)                                      # [H, W, 2]
+    scale = torch.tensor([(H - 1) // 2, (W - 1) // 2], dtype=torch.float32, device=masks.device)
+    dists = []
+    for b in range(B * T):
+        vis = torch.nonzero(~flat[b]).float()                                             # [N, 2]
+        if vis.shape[0] == 0:
+            dists.append(torch.zeros([H, W], dtype=torch.float32, device=masks.device))
+            continue
+        d = ((grid[None] - vis.view(-1, 1, 1, 2)) / scale).abs().amax(-1).amin(0)         # [H, W]
+        if self_mask:
+            d[~flat[b]] = d.amax()
+        dists.append(d)
+    return torch.stack(dists, 0).view(B, T, H, W)
+
+
+def patches_adjacent_to_visible(masks, radius=1, size=None):
+    """masking.py:58-71: patches within ``radius`` (L-inf, in patches) of a visible one; radius 0 -> a soft proximity."""
+    if size is not None:
+        masks = masks.view(-1, 1, *size)
+    if radius is None:
+        return masks
+    H, W = masks.shape[-2:]
+    dists = patch_distance_transform(masks)
+    if radius != 0:
+        return dists <= ((1 / ((min(H, W) - 1) // 2)) * radius)
+    rmax = dists.amax((-1, -2), keepdim=True)
+    return (rmax - dists) / rmax.clip(min=1.0)

@@ -300,6 +300,176 @@ class PredictorBasedGenerator(nn.Module):
             raise RuntimeError("shape mismatch: rows of the mask have different numbers of masked tokens")
         return unpatchify_scatter(y, _x, inv, int(counts[0]), patch_size)
 
+    # ---- host-side helpers of the reference wrapper that involve no forward pass of their own ---------------------
+    def load_predictor(self, load_path=None, model=None, map_location='cpu'):
+        """prediction.py:81-107: load a checkpoint (``{'model': state_dict}`` or a bare state_dict) into the predictor."""
+        if (getattr(self, 'predictor', None) is None) and (model is None):
+            raise ValueError("There is no predictor set for this generator and no model to load to")
+        if load_path is None:
+            return
+        weights = torch.load(load_path, map_location=torch.device(map_location))
+        if 'model' in weights.keys():
+            weights = weights['model']
+        target = self.predictor if model is None else model
+        print(target.load_state_dict(weights), load_path)
+        if model is None:
+            self._predictor_load_path = load_path
+
+    def get_fully_visible_mask(self, x=None):
+        x = self.x if x is None else x
+        return torch.zeros(self.mask_shape, device=x.device, dtype=torch.bool)
+
+    def mask_complement(self, mask1, mask2, frame=-1):
+        """prediction.py:231-243: visible exactly where mask1 is masked and mask2 is not (in ``frame``)."""
+        mask1, mask2 = self.get_mask_image(mask1), self.get_mask_image(mask2)
+        mask_diff = mask1 & (~mask2)
+        if frame is None:
+            return (~mask_diff).view(mask_diff.shape[0], -1)
+        frame = frame % mask1.shape[1]
+        return torch.cat([mask1[:, :frame], ~mask_diff[:, frame, None], mask1[:, (frame + 1):]], 1).view(
+            mask_diff.shape[0], -1)
+
+    def patchify_energy_density(self, density, mode='min', beta=None):
+        """prediction.py:284-302: Boltzmann-weight an energy map and pool it to the patch grid."""
+        import torch.nn.functional as F
+        from .masking import boltzmann
+        rank = len(density.shape)
+        assert rank in [4, 5], rank
+        density = boltzmann(density, beta=beta)
+        pool = {(5, 'mean'): F.avg_pool3d, (4, 'mean'): F.avg_pool2d, (5, 'max'): F.max_pool3d, (4, 'max'): F.max_pool2d,
+                (5, 'min'): lambda v, **kw: -F.max_pool3d(-v, **kw),
+                (4, 'min'): lambda v, **kw: -F.max_pool2d(-v, **kw)}[(rank, mode)]
+        ps = tuple(self.patch_size) if rank == 5 else tuple(self.patch_size[-2:])
+        pooled = pool((density.transpose(1, 2) if rank == 5 else density), kernel_size=ps, stride=ps)
+        return pooled.squeeze(1) if rank == 5 else pooled
+
+    def _get_frames(self, x, frames=0):
+        assert len(x.shape) == 5, x.shape
+        return torch.index_select(x, dim=1, index=torch.tensor(frames).long().to(x.device))
+
+    def _get_target(self, x):
+        assert len(x.shape) == 5 and x.shape[1] == 2, x.shape
+        return self._get_frames(x, frames=[1])
+
+    def _get_error(self, pred, gt, dim=-3, frame=None):
+        return self.error_func(pred[:, -gt.shape[1]:], gt).sum(dim, True)
+
+    def get_nearby_patches(self, mask, radius=1, upsample=False, shape=None):
+        """prediction.py:345-351."""
+        from . import masking
+        nearby = masking.patches_adjacent_to_visible(self.get_mask_image(mask, shape=shape), radius=radius, size=None)
+        return masking.upsample_masks(nearby, size=self.inp_shape[-2:]) if upsample else nearby
+
+    @staticmethod
+    def invert_mask_frame(mask, size, frame=-1):
+        """prediction.py:371-381."""
+        shape = mask.shape
+        mask = mask.view(shape[0], -1, *size)
+        frame = frame % mask.size(1)
+        return torch.cat([mask[:, :frame], ~mask[:, frame:frame + 1], mask[:, (frame + 1):]], 1).view(*shape)
+
+    def _invert_mask(self, mask, frame=-1):
+        return self.invert_mask_frame(mask, self.mask_shape[-2:], frame)
+
+    def _sample_random_patches(self, batch_size=1, t_idx=None):
+        """prediction.py:386-394 (two draws of ``self.rng`` per batch element)."""
+        patches = []
+        for b_idx in range(batch_size):
+            if t_idx is None:
+                t_idx = self.mask_shape[0] - 1
+            patches.append([b_idx, t_idx, self.rng.randint(self.mask_shape[1]), self.rng.randint(self.mask_shape[2])])
+        return patches
+
+    def predict_with_mask(self, mask, invert_mask=False, *args, **kwargs):
+        assert self.x is not None
+        return self.predict(self.x, (~mask if invert_mask else mask).view(*self.inp_mask_shape), *args, **kwargs)
+
+    def error_with_mask(self, mask, invert_mask=False, frame=-1, *args, **kwargs):
+        x_pred = self.predict_with_mask(mask, invert_mask, *args, **kwargs)
+        return self._get_error(x_pred[:, frame].unsqueeze(1), self.x[:, frame].unsqueeze(1), dim=-3)
+
+    def get_error_on_target_region(self, x, mask, target_mask, target=None, average_error=True, frame=-1,
+                                   aggregate_over_patches=True, patch_size=None, **kwargs):
+        """prediction.py:553-574: prediction error pooled to patches and restricted to the visible part of target_mask."""
+        import torch.nn.functional as F
+        target = x if target is None else target
+        if len(target_mask.shape) == 2:
+            target_region = 1 - target_mask.view(x.shape[0], -1, *self.mask_shape[-2:]).to(x)
+        else:
+            target_region = 1 - target_mask.to(x)
+        error = self._get_error(self.predict(x, mask, frame=frame, **kwargs), target)
+        if not aggregate_over_patches:
+            return error
+        patch_size = patch_size or self.patch_size
+        error = F.avg_pool3d(error.transpose(1, 2), patch_size, stride=patch_size).squeeze(1) * target_region.to(x)
+        if not average_error:
+            return error
+        return error.sum((1, 2, 3)) / target_region.sum((1, 2, 3)).clamp(min=1)
+
+    def get_initial_mask(self, x):
+        raise NotImplementedError("Need to specify how to get the initial mask")
+
+    @staticmethod
+    def unmask_one_patch(mask, idx=None, mask_shape=None, inplace=False, frame=0):
+        """prediction.py:580-607: make the patch at ``idx`` visible (flat index, or (t, h, w) / (b, t, h, w))."""
+        shape = mask.shape
+        if not inplace:
+            mask = mask.clone()
+        if mask_shape is None:
+            assert len(shape) == 2, "If you don't pass a mask shape, it must be [B,N]"
+            mask[:, idx] = torch.zeros_like(mask[:, 0])
+            return mask
+        if len(idx) == 2 and isinstance(idx, (list, tuple)):
+            idx = [frame] + list(idx)
+        assert (len(idx) == len(mask_shape)) or (len(idx) == (len(mask_shape) + 1)), (idx, mask_shape)
+        idx = [int(i) for i in idx]
+        mask = mask.view(-1, *mask_shape)
+        if len(idx) == len(mask_shape):
+            mask[(slice(None),) + tuple(idx)] = False
+        else:
+            mask[tuple(idx)] = False
+        return mask.view(*shape)
+
+    @staticmethod
+    def patch_idx_list_from_mask(mask):
+        """prediction.py:609-615: [b, t, h, w] of every visible patch of a [B, T, H, W] mask."""
+        assert len(mask.shape) == 4, mask.shape
+        return [list(p) for p in torch.nonzero(~mask).cpu().numpy()]
+
+    def generate_cutout_mask(self, patch_idx_list, radius=1, stride=None, b=0, frame=-1):
+        """prediction.py:649-659 (declared @staticmethod with a ``self`` argument there): the listed patches plus
+        their neighbourhood of ``radius`` patches are visible in ``frame``."""
+        from . import masking
+        mask = self.get_mask_image(self.generate_mask_from_patch_idx_list(patch_idx_list, stride=stride, b=b, frame=frame))
+        cutout = masking.patches_adjacent_to_visible(mask[:, frame:frame + 1], radius=radius)
+        cutout = torch.maximum(cutout, ~mask[:, frame:frame + 1])
+        mask[:, frame] = cutout[:, 0]
+        return mask.flatten(1)
+
+    def get_frame_pairs(self, x, frame=None):
+        """prediction.py:691-701: every frame paired with the target frame."""
+        assert len(x.shape) == 5, x.shape
+        T = x.shape[1]
+        self.num_frame_pairs = T - 1
+        self.target_frame = frame if frame is not None else (T // 2)
+        frames = torch.unbind(x, 1)
+        return [torch.stack([frames[t], frames[self.target_frame]], 1) for t in range(T) if t != self.target_frame]
+
+    def sample_random_masks(self, num_samples=10, num_visible=1, mask_ratio=None):
+        """prediction.py:741-758: S draws of the wrapper's mask generator, stacked on a trailing sample axis."""
+        assert self.mask_generator is not None
+        _num_vis = self.mask_generator.num_visible
+        if mask_ratio is None:
+            self.mask_generator.num_visible = num_visible
+        else:
+            self.mask_generator.mask_ratio = mask_ratio
+        x = self.x if self.x is not None else None
+        masks = torch.stack([self.mask_generator(x) for _ in range(num_samples)], -1)
+        if self.x is not None:
+            masks = masks.to(x.device)
+        self.mask_generator.num_visible = _num_vis
+        return masks
+
     def predict_keypoints_map(self, x, *args, **kwargs):
         """prediction.py:815-820."""
         assert len(x.shape) == 5, x.shape
