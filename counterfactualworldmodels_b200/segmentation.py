@@ -283,18 +283,72 @@ class FlowGenerator(PredictorBasedGenerator):
                            normalize=False, zscore=False, range_thresh=None):
         """segmentation.py:478-547: covariance / correlation of the flow magnitude between image locations over the
         samples.  The options the reference's only caller uses (interface.py:27-29, :466-493: ``downsample``,
-        ``use_covariance``, ``take_top_k``) run on device; the others raise."""
+        ``use_covariance``, ``take_top_k``) run on the hand-written kernels; the other options take the torch-op route of
+        ``_flow_corrs_general``."""
         custom_distance = distance_func is not None and type(distance_func).__name__ != "ChannelMSE"
         if flow_samples_swap is not None or do_spearman or custom_distance or thresh is not None or \
                 binarize or normalize or zscore or range_thresh is not None:
-            raise NotImplementedError("compute_flow_corrs: only the default feature pipeline (ChannelMSE magnitude, "
-                                      "no thresholding / ranking) is implemented on B200")
+            # the options the reference's only caller never sets: the same feature transforms as torch ops on the
+            # device tensors, then torch.cov / torch.corrcoef (library calls; no hand-written kernel for these)
+            if flow_samples.device.type != "cuda":
+                raise RuntimeError("compute_flow_corrs: tensors must live on a CUDA (B200) device; there is no CPU fallback")
+            return FlowGenerator._flow_corrs_general(
+                flow_samples, flow_samples_swap=flow_samples_swap, downsample=downsample, take_top_k=take_top_k,
+                do_spearman=do_spearman, distance_func=distance_func, thresh=thresh, use_covariance=use_covariance,
+                eps=eps, binarize=binarize, normalize=normalize, zscore=zscore, range_thresh=range_thresh)
         B, C, H, W, S = flow_samples.shape
         if S == 0:  # segmentation.py:494-497
             flow_samples = torch.zeros(list(flow_samples.shape)[:-1] + [1], device=flow_samples.device).float()
         if take_top_k is not None:
             flow_samples = flow_samples[..., :take_top_k]
         return sampling.flow_corrs(flow_samples, downsample=downsample, use_covariance=use_covariance)
+
+    @staticmethod
+    def _flow_corrs_general(flow_samples, flow_samples_swap=None, downsample=1, take_top_k=None, do_spearman=False,
+                            distance_func=None, thresh=None, use_covariance=False, eps=1e-12, binarize=False,
+                            normalize=False, zscore=False, range_thresh=None):
+        """segmentation.py:478-547 with every option, as device-agnostic torch ops (pinned against the live reference in
+        tests/test_flowstats.py)."""
+        import torch.nn.functional as F
+        B, C, H, W, S = flow_samples.shape
+        if S == 0:
+            flow_samples = torch.zeros(list(flow_samples.shape)[:-1] + [1]).to(flow_samples.device).float()
+            S = 1
+        if flow_samples_swap is not None:
+            assert list(flow_samples_swap.shape) == [B, C, H, W, S]
+        K = S if take_top_k is None else take_top_k
+        ds = downsample
+
+        def _ds(fs):
+            return F.avg_pool3d(fs[..., :K].permute(0, 1, 4, 2, 3), (1, ds, ds), stride=(1, ds, ds)).permute(0, 1, 3, 4, 2)
+
+        flow_inp = _ds(flow_samples)
+        if flow_samples_swap is not None:
+            flow_inp = torch.cat([flow_inp, _ds(flow_samples_swap)], -1)
+        if distance_func is None or type(distance_func).__name__ == "ChannelMSE":
+            flow_inp = torch.sqrt(flow_inp.square().mean(1, True).float())      # ChannelMSE(dim=1), utils.py:510-521
+        else:
+            flow_inp = distance_func(flow_inp, torch.zeros_like(flow_inp))
+        flow_inp = flow_inp.reshape(B, -1, flow_inp.size(-1))
+        flow_corrs = []
+        for b in range(B):
+            f = torch.argsort(flow_inp[b], -1).float() if do_spearman else flow_inp[b]
+            if (thresh is not None) and (binarize is False):
+                f = f * (f > thresh).float()
+            elif thresh is not None:
+                f = (f > thresh).float()
+            elif range_thresh is not None:
+                f = f - f.amin(0, True)
+                f = (f > (range_thresh * f.amax(0, True))).float()
+            if normalize:
+                f = f / f.amax(0, True).clamp(min=eps)
+            if zscore:
+                mn, std = f.mean(0), f.std(0).clamp(min=eps)
+                f = (f - mn[None]) / std[None]
+            c = torch.cov(f) if use_covariance else torch.corrcoef(f)
+            c[torch.isnan(c)] = 0
+            flow_corrs.append(c)
+        return torch.stack(flow_corrs, 0).view(B, 1, H // ds, W // ds, H // ds, W // ds)
 
     def filter_flow_samples(self, flows, active_patches, do_filter=True):
         """The tail of ``sample_counterfactual_motion_map`` (segmentation.py:470-476): flows [(b s), T, 2, H, W] or

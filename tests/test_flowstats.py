@@ -137,8 +137,12 @@ def test_gpu_flow_corrs_match_reference_fixture(case, ds):
     assert torch.allclose(r2, r2.transpose(1, 2), atol=1e-6)
     diag = torch.diagonal(r2, dim1=1, dim2=2)
     assert bool(((diag - 1).abs() < 1e-5).logical_or(diag == 0).all())
-    with pytest.raises(NotImplementedError):
-        segmentation.FlowGenerator.compute_flow_corrs(flows, do_spearman=True)
+    # the options the reference's caller never sets take the torch-op route (pinned bit for bit against the live
+    # reference on CPU, test_flow_corrs_general_options_match_the_live_reference); here: it runs on device tensors
+    sp = segmentation.FlowGenerator.compute_flow_corrs(flows, downsample=ds, do_spearman=True)
+    assert sp.shape == r.shape and bool(torch.isfinite(sp).all())
+    sp2 = sp.reshape(-1, n, n)
+    assert torch.allclose(sp2, sp2.transpose(1, 2), atol=1e-5)
 
 
 def test_oracle_flow_corrs_matches_reference_fixture():
@@ -146,3 +150,28 @@ def test_oracle_flow_corrs_matches_reference_fixture():
     flows = fso.batch_to_samples(d["flows_bs"], d["B"])
     assert np.array_equal(fso.flow_corrs(flows, downsample=4, use_covariance=True).numpy(), d["flow_cov_ds4"])
     assert np.array_equal(fso.flow_corrs(flows, downsample=4, use_covariance=False).numpy(), d["flow_corr_ds4"])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="live reference not mounted")
+def test_flow_corrs_general_options_match_the_live_reference():
+    """The options of compute_flow_corrs the reference's only caller never sets (segmentation.py:478-547): the torch-op
+    route reproduces the reference bit for bit on CPU (the public method only accepts device tensors)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLDEN_DIR), "..", "oracle"))
+    import ref_loader
+    ref_loader.import_reference()
+    import cwm.models.segmentation as ref_seg
+    import cwm.models.utils as ref_utils
+    from counterfactualworldmodels_b200 import segmentation
+    flows_bs, _ = fso.make_flows(2, 6, 32, 32, 4)
+    flows = fso.batch_to_samples(flows_bs, 2)
+    swap = fso.batch_to_samples(fso.make_flows(2, 6, 32, 32, 5)[0], 2)
+    cases = [dict(do_spearman=True), dict(thresh=1.0), dict(thresh=1.0, binarize=True), dict(range_thresh=0.5),
+             dict(normalize=True, use_covariance=True), dict(zscore=True), dict(flow_samples_swap=swap, take_top_k=4),
+             dict(distance_func=ref_utils.ChannelL1Error(dim=1), use_covariance=True)]
+    for kw in cases:
+        want = ref_seg.FlowGenerator.compute_flow_corrs(flows, downsample=4, **kw)
+        got = segmentation.FlowGenerator._flow_corrs_general(flows, downsample=4, **kw)
+        assert torch.equal(got, want), kw
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        segmentation.FlowGenerator.compute_flow_corrs(flows, downsample=4, zscore=True)
