@@ -26,7 +26,10 @@ EXPORTED_SYMBOLS = (
     "cwm_motion_map_finalize", "cwm_flow_stats_workspace_bytes", "cwm_flow_corrs_workspace_bytes", "cwm_flow_corrs",
     "cwm_gemm_ln_parts", "cwm_rowstats_f16", "cwm_raft_corr_pyramid", "cwm_raft_corr_lookup", "cwm_raft_upsample_flow",
     "cwm_raft_corr_lookup_f16", "cwm_raft_bias_act_f16", "cwm_raft_gru_gate_f16", "cwm_raft_gru_update_f16",
-    "cwm_raft_flow_update",
+    "cwm_raft_flow_update", "cwm_total_launches",
+    # tuning hooks (header section "tuning hooks")
+    "cwm_debug_attention_poly", "cwm_debug_attention_war_safe", "cwm_debug_attention_persistent",
+    "cwm_debug_attention_persist_map", "cwm_debug_attn_mma_wide", "cwm_debug_attn_mma_split", "cwm_debug_gemm_cta2",
 )
 
 
@@ -111,6 +114,12 @@ def _declare(lib):
                                      POINTER(c_float), c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.cwm_last_forward_launches.restype = c_int
     lib.cwm_launch_count_reset.restype = c_int
+    lib.cwm_total_launches.restype = ctypes.c_longlong
+    for name in ("cwm_debug_attention_poly", "cwm_debug_attention_war_safe", "cwm_debug_attention_persistent",
+                 "cwm_debug_attention_persist_map", "cwm_debug_attn_mma_wide", "cwm_debug_attn_mma_split"):
+        getattr(lib, name).argtypes = [c_int]
+        getattr(lib, name).restype = None
+    lib.cwm_debug_gemm_cta2.argtypes = [c_int]
     lib.cwm_attention_generic_workspace_bytes.argtypes = [c_int] * 5
     lib.cwm_attention_generic_workspace_bytes.restype = c_size_t
     lib.cwm_attention_generic_f16.argtypes = [c_void_p, c_void_p, c_void_p] + [c_int] * 11 + [c_void_p, c_int, c_void_p,
@@ -164,10 +173,8 @@ def _declare(lib):
     lib.cwm_raft_flow_update.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]
     lib.cwm_profile_begin.restype = c_int
     lib.cwm_profile_end.argtypes = [POINTER(ProfileEntry), c_int, POINTER(c_int)]
-    for name in EXPORTED_SYMBOLS:
-        fn = getattr(lib, name)
-        if fn.restype is c_int and name not in ("cwm_abi_version", "cwm_last_forward_launches"):
-            pass
+    for name in EXPORTED_SYMBOLS:   # a missing export fails here, at load time, not at first use
+        getattr(lib, name)
     return lib
 
 

@@ -13,6 +13,7 @@ namespace cwm {
 
 static thread_local char g_err[512] = "";
 static thread_local int g_launches = 0;
+static thread_local long long g_total_launches = 0;
 
 void set_last_error(const char* fmt, ...) {
   va_list ap;
@@ -29,7 +30,7 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
-void count_launch() { ++g_launches; }
+void count_launch() { ++g_launches; ++g_total_launches; }
 int launches() { return g_launches; }
 void reset_launches() { g_launches = 0; }
 
@@ -174,6 +175,8 @@ int cwm_device_check(void) {
 }
 
 int cwm_last_forward_launches(void) { return cwm::g_launches; }
+
+long long cwm_total_launches(void) { return cwm::g_total_launches; }
 
 int cwm_launch_count_reset(void) {
   cwm::g_launches = 0;

@@ -29,23 +29,33 @@ def shard_samples(x, mask, rank=None, world_size=None):
 
 def gather_samples(y_local, num_samples, dst=None):
     """Inverse of ``shard_samples`` along dim 0.  ``dst=None`` -> all ranks get the full tensor (all_gather),
-    otherwise only rank ``dst`` does (others get None).  Shards may differ in size by one sample, so every rank
-    pads to the largest shard before the collective."""
+    otherwise only rank ``dst`` does (others get None).  Equal shards land directly in their slice of the result
+    (no staging copy); shards that differ in size by one sample are padded to the largest before the collective."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return y_local
     world = dist.get_world_size()
     rank = dist.get_rank()
-    sizes = [shard_bounds(num_samples, r, world)[1] - shard_bounds(num_samples, r, world)[0] for r in range(world)]
+    bounds = [shard_bounds(num_samples, r, world) for r in range(world)]
+    sizes = [hi - lo for lo, hi in bounds]
     max_n = max(sizes)
+    receives = dst is None or rank == dst
+    if min(sizes) == max_n:
+        y_local = y_local.contiguous()
+        full = y_local.new_empty((num_samples,) + tuple(y_local.shape[1:])) if receives else None
+        out = [full[lo:hi] for lo, hi in bounds] if receives else None
+        if dst is None:
+            dist.all_gather(out, y_local)
+        else:
+            dist.gather(y_local, out, dst=dst)
+        return full
     pad = y_local
     if y_local.shape[0] < max_n:
         pad = torch.cat([y_local, y_local.new_zeros((max_n - y_local.shape[0],) + tuple(y_local.shape[1:]))], 0)
     pad = pad.contiguous()
+    out = [torch.empty_like(pad) for _ in range(world)] if receives else None
     if dst is None:
-        out = [torch.empty_like(pad) for _ in range(world)]
         dist.all_gather(out, pad)
     else:
-        out = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
         dist.gather(pad, out, dst=dst)
         if rank != dst:
             return None
@@ -66,7 +76,8 @@ def sharded_predict(generator, x, mask, frame=-1, batch_size=None, gather=True, 
 
 
 def sharded_counterfactual_videos(generator, x, active_patches, passive_patches=None, shifts=None, num_samples=8,
-                                  sample_batch_size=8, fix_passive=True, frame=1, gather=True, dst=None, **kwargs):
+                                  sample_batch_size=8, fix_passive=True, frame=1, gather=True, dst=None,
+                                  predict_frame=None, **kwargs):
     """``FlowGenerator.predict_counterfactual_videos`` (cwm/models/segmentation.py:345-430) with the S samples of the
     sweep sharded over the ranks (SURVEY.md section 8e + 8f rank 1).
 
@@ -74,7 +85,9 @@ def sharded_counterfactual_videos(generator, x, active_patches, passive_patches=
     whole sweep -- the rectangulariser draws from a global RNG (masking.py:119-128), so it must see all rows once --
     and broadcasts them (S*N bytes); each rank then predicts its contiguous slice from the *virtual* counterfactual
     video (nothing but descriptors is ever sent) and the predicted movies are gathered once.
-    Returns ``[S, T, C, H, W]`` on every rank (``dst=None``), on rank ``dst`` only, or the local slice (``gather=False``)."""
+    Returns ``[S, T, C, H, W]`` on every rank (``dst=None``), on rank ``dst`` only, or the local slice (``gather=False``).
+    ``predict_frame`` (extension) keeps only that frame of every predicted movie (``-1``: the counterfactual frame,
+    ``[S, 1, C, H, W]``) so that the gather moves the predicted frames and not the prompts' frame 0 with them."""
     G = generator
     multi = dist.is_initialized() and dist.get_world_size() > 1
     rank = dist.get_rank() if multi else 0
@@ -124,10 +137,11 @@ def sharded_counterfactual_videos(generator, x, active_patches, passive_patches=
     n_total = masks.shape[0]
     lo, hi = shard_bounds(n_total, rank, world)
     if hi > lo:
-        y = G.batch_predict_per_sample(video[lo:hi], masks=masks[lo:hi], frame=None,
+        y = G.batch_predict_per_sample(video[lo:hi], masks=masks[lo:hi], frame=predict_frame,
                                        batch_size=(sample_batch_size or (hi - lo)), sample_dim=0, **kwargs)
     else:
-        y = x.new_zeros((0,) + tuple(x.shape[1:]), dtype=torch.float32)
+        T = x.shape[1] if predict_frame is None else 1
+        y = x.new_zeros((0, T) + tuple(x.shape[2:]), dtype=torch.float32)
     if not gather:
         return y
     return gather_samples(y, n_total, dst=dst)

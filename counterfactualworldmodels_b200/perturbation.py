@@ -149,128 +149,83 @@ def shift_patches_and_masks(x, passive, active, mask_shifts, patch_size, frame=1
     return video, mask_out
 
 
-class PatchPerturbation(nn.Module):
-    """cwm/models/perturbation.py:13-112."""
+class _Geometry:
+    """Shape record of one ``[B, T, C, H, W]`` video batch and its patch grid (what the reference keeps as a dozen
+    attributes and properties on ``PatchPerturbation``, perturbation.py:13-72)."""
+    __slots__ = ("batch", "frames", "channels", "height", "width", "grid")
 
-    def __init__(self, patch_size, seed=0, frame=None, use_image_coordinates=True, **kwargs):
+    def __init__(self, video_shape, patch_size):
+        if len(video_shape) != 5:
+            raise AssertionError(tuple(video_shape))
+        self.batch, self.frames, self.channels, self.height, self.width = (int(v) for v in video_shape)
+        pt, ph, pw = patch_size
+        self.grid = (self.frames // pt, self.height // ph, self.width // pw)
+
+    def frame_masks(self, mask):
+        """[B, N] -> [B, frames_in_mask, h, w] (the mask may cover fewer frames than the video)."""
+        return mask.reshape(self.batch, -1, self.grid[1], self.grid[2])
+
+
+class _Perturbation(nn.Module):
+    """State shared by the two perturbations the counterfactual path uses: patch size, the seeded host RNG the
+    reference draws random shifts from, and the geometry of the last input."""
+
+    def __init__(self, patch_size, seed=0, **unused):
         super().__init__()
         self.patch_size = tuple(patch_size)
-        self.frame = frame
         self.seed = seed
         self.rng = np.random.RandomState(seed=seed)
-        self.use_image_coordinates = use_image_coordinates
+        self.geometry = None
+        self.inp_mask_shape = None
 
-    @property
-    def T(self):
-        return self.sequence_length
-
-    @property
-    def C(self):
-        return self.num_channels
-
-    @property
-    def H(self):
-        return self.image_size[0]
-
-    @property
-    def W(self):
-        return self.image_size[1]
-
-    @property
-    def mask_shape(self):
-        return (self.sequence_length // self.patch_size[0], self.image_size[0] // self.patch_size[1],
-                self.image_size[1] // self.patch_size[2])
-
-    @property
-    def mask_image_size(self):
-        return self.mask_shape[-2:]
-
-    def _check_shapes(self, x, mask):
+    def set_shapes(self, x, mask):
+        self.geometry = _Geometry(x.shape, self.patch_size)
         if mask is not None:
             self.inp_mask_shape = mask.shape
 
-    def set_shapes(self, x, mask):
-        assert len(x.shape) == 5, x.shape
-        self.inp_shape = x.shape
-        self.B = self.inp_shape[0]
-        self.image_size = self.inp_shape[-2:]
-        self.sequence_length = self.inp_shape[1]
-        self.num_channels = self.inp_shape[2]
-        self.num_patches = np.prod(self.mask_shape)
-        self._check_shapes(x, mask)
+    # the names other modules read
+    @property
+    def image_size(self):
+        return (self.geometry.height, self.geometry.width)
 
-    def reshape_mask_to_video(self, mask):
-        mask = mask.view(self.B, -1, *self.mask_image_size)
-        self.T_mask = mask.size(1)
-        return mask
-
-    def sample_random_patch(self, batch_size, frames=[0]):
-        patch_idx_list = []
-        if frames is None:
-            frames = list(range(self.T))
-        elif not isinstance(frames, (list, tuple)):
-            frames = [frames]
-        for b_idx in range(batch_size):
-            t_idx = self.rng.choice(frames)
-            h_idx = self.rng.randint(self.mask_image_size[0])
-            w_idx = self.rng.randint(self.mask_image_size[1])
-            patch_idx_list.append([b_idx, t_idx, h_idx, w_idx])
-        return patch_idx_list
-
-    def image_to_patch_inds(self, inds):
-        return [inds[-i] // self.patch_size[-i] for i in range(1, len(inds) + 1)]
-
-    def perturb(self, x, mask, **kwargs):
-        raise NotImplementedError("Do the perturbation")
-
-    def forward(self, x, mask=None, perturbation_points=None, **kwargs):
-        self.set_shapes(x, mask)
-        mask = mask.clone()
-        if perturbation_points is None:
-            perturbation_mask = mask
-        else:  # remove the visible patches in common between mask and perturbation mask
-            mask[perturbation_points] = 1
-            perturbation_mask = torch.logical_not(perturbation_points)
-        x_perturbed, mask_perturbed = self.perturb(x, perturbation_mask, **kwargs)
-        if perturbation_points is not None:
-            mask_perturbed = torch.minimum(mask, mask_perturbed)
-        return x_perturbed, mask_perturbed
+    @property
+    def mask_shape(self):
+        return self.geometry.grid
 
 
-class NullPerturbation(PatchPerturbation):
+class MakeStatic(_Perturbation):
+    """Copies frame 0 into every visible patch of the later frames (cwm/models/perturbation.py:120-150): one launch of
+    ``cwm_cf_make_static`` on the strided input, no Patchify round trip.  Returns ``(video, mask)``, the mask as given."""
 
-    def perturb(self, x, mask, **kwargs):
-        return (x, mask)
-
-
-class MakeStatic(PatchPerturbation):
-    """Make the visible patches in frames t > 0 identical to the spatially equivalent patches in frame t = 0
-    (perturbation.py:120-150)."""
-
-    def _check_shapes(self, x, mask):
-        assert self.T > 1
-
-    def perturb(self, x, mask):
+    def forward(self, x, mask=None, **unused):
         lib = _lib.load()
         _require_cuda(x, "MakeStatic")
-        m = self.reshape_mask_to_video(mask.to(x.device))
-        if self.T_mask != self.T:  # assume all other frames are masked, so they won't be altered (:137-141)
-            T_vis = self.T - self.T_mask
-            m_vis = torch.ones((self.B, T_vis, *self.mask_image_size), dtype=m.dtype, device=m.device)
-            m = torch.cat([m_vis, m[:, -1:]], 1)
-        if x.dtype != torch.float32:
-            x = x.float()
-        out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
-        with torch.cuda.device(x.device):
-            stream = torch.cuda.current_stream(x.device).cuda_stream
-            _lib.check(lib.cwm_cf_make_static(x.data_ptr(), _lib.strides5(x), _as_u8(m).data_ptr(), self.B, self.T,
-                                              self.C, self.H, self.W, self.patch_size[-2], self.patch_size[-1],
-                                              out.data_ptr(), stream))
-        return (out, mask)  # original mask is unaltered
+        self.set_shapes(x, mask)
+        g = self.geometry
+        if g.frames < 2:
+            raise AssertionError("MakeStatic needs at least two frames")
+        per_frame = g.frame_masks(mask.to(x.device))
+        if per_frame.shape[1] != g.frames:
+            # a mask that only covers the last frame: the earlier frames count as masked, i.e. are left alone
+            lead = torch.ones((g.batch, g.frames - per_frame.shape[1]) + g.grid[1:], dtype=per_frame.dtype,
+                              device=per_frame.device)
+            per_frame = torch.cat([lead, per_frame[:, -1:]], 1)
+        src = x if x.dtype == torch.float32 else x.float()
+        out = torch.empty(src.shape, dtype=torch.float32, device=src.device)
+        with torch.cuda.device(src.device):
+            _lib.check(lib.cwm_cf_make_static(src.data_ptr(), _lib.strides5(src), _as_u8(per_frame).data_ptr(),
+                                              g.batch, g.frames, g.channels, g.height, g.width, self.patch_size[-2],
+                                              self.patch_size[-1], out.data_ptr(),
+                                              torch.cuda.current_stream(src.device).cuda_stream))
+        return out, mask
 
 
-class ShiftPatchesAndMask(PatchPerturbation):
-    """Shift the visible patches and mask in a target frame by some 2D vector (perturbation.py:152-289)."""
+class ShiftPatchesAndMask(_Perturbation):
+    """Moves the patches selected by a mask, and the mask with them, by a 2-D vector inside one frame
+    (cwm/models/perturbation.py:152-289), for a whole batch in one mask kernel + one (virtual) video.
+
+    Shifts are ``(dy, dx)``; ``mask_shift`` counts patches, ``shift`` pixels (multiples of the patch size).
+    Only what ``prediction.py:53-58`` configures is supported: constant padding, whole-patch shifts."""
 
     def __init__(self, patch_size, max_shift_fraction=0.15, padding_mode='constant', allow_fractional_shifts=False,
                  **kwargs):
@@ -280,97 +235,77 @@ class ShiftPatchesAndMask(PatchPerturbation):
         if allow_fractional_shifts:
             raise NotImplementedError("allow_fractional_shifts=True belongs to MultiShiftPatchesAndMask")
         self.max_shift_fraction = max_shift_fraction
-        self.padding_mode = padding_mode
-        self.allow_fractional_shifts = allow_fractional_shifts
-        self.set_num_shifts()
+        self.num_shifts = 1
+        self.shift = None
 
     def set_num_shifts(self, num_shifts=None):
-        self._num_shifts = 1 if num_shifts is None else num_shifts
-
-    @property
-    def num_shifts(self):
-        if getattr(self, '_num_shifts', None) is None:
-            self.set_num_shifts()
-        return self._num_shifts
-
-    def _check_shapes(self, x, mask):
-        self.inp_mask_shape = mask.shape
-
-    def _preprocess_shifts_sequence(self, shifts_sequence, is_mask_shift=False):
-        """perturbation.py:184-216."""
-        if shifts_sequence is None:
-            return [self.get_random_shift(is_mask_shift) for _ in range(self.num_shifts)]
-        if hasattr(shifts_sequence, 'shape'):
-            assert len(shifts_sequence.shape) == 2, shifts_sequence.shape
-            D, S = shifts_sequence.shape
-            assert D == 2, D
-            assert S in (self.num_shifts, 1), (S, self.num_shifts)
-            if isinstance(shifts_sequence, torch.Tensor):
-                shifts_sequence = [shifts_sequence[..., s].detach().cpu().numpy() for s in range(S)]
-            else:
-                shifts_sequence = [shifts_sequence[..., s] for s in range(S)]
-        if isinstance(shifts_sequence, (list, tuple)):
-            if not isinstance(shifts_sequence[0], (list, tuple)):
-                shifts_sequence = [shifts_sequence]
-            assert all((len(s) == 2 for s in shifts_sequence))
-            if len(shifts_sequence) == 1:  # all have same shift
-                return shifts_sequence * self.num_shifts
-            else:
-                assert len(shifts_sequence) == self.num_shifts, (len(shifts_sequence), self.num_shifts)
-        return shifts_sequence
+        self.num_shifts = num_shifts or 1
 
     def get_random_shift(self, is_mask_shift=False):
-        """perturbation.py:218-234: same draws from the same ``np.random.RandomState(seed)``."""
-        def rect(s, p):
-            q = 1 if is_mask_shift else p
-            return int(s // p) * q
+        """One non-zero-sum shift drawn like perturbation.py:218-234 (two ``randint`` per attempt from the seeded
+        stream, floored to whole patches): pixel units, or patch units with ``is_mask_shift``."""
+        limits = [int(self.max_shift_fraction * extent) for extent in self.image_size]
+        patch = self.patch_size[-2:]
+        while True:
+            draw = [self.rng.randint(-lim, lim + 1) for lim in limits]
+            whole = [int(d // p) for d, p in zip(draw, patch)]
+            out = tuple(whole) if is_mask_shift else tuple(n * p for n, p in zip(whole, patch))
+            if sum(out) != 0:
+                return out
 
-        max_shift = [int(self.max_shift_fraction * s) for s in self.image_size]
-        random_shift = (0, 0)
-        while sum(random_shift) == 0:
-            random_shift = (
-                rect(self.rng.randint(-max_shift[0], max_shift[0] + 1), self.patch_size[-2]),
-                rect(self.rng.randint(-max_shift[1], max_shift[1] + 1), self.patch_size[-1]))
-        return random_shift
+    def _preprocess_shifts_sequence(self, shifts_sequence, is_mask_shift=False):
+        """One shift per sample from whatever the caller passed (perturbation.py:184-216): ``None`` -> random draws;
+        one pair -> repeated; a list of ``num_shifts`` pairs -> itself; a ``[2, S]`` array -> its columns, which then
+        go through the list rules (so, exactly like the reference, only S == 2 survives the pair check)."""
+        count = self.num_shifts
+        if shifts_sequence is None:
+            return [self.get_random_shift(is_mask_shift) for _ in range(count)]
+        seq = shifts_sequence
+        if hasattr(seq, 'shape'):
+            if len(seq.shape) != 2 or seq.shape[0] != 2 or seq.shape[1] not in (count, 1):
+                raise AssertionError((tuple(seq.shape), count))
+            cols = seq.detach().cpu().numpy() if isinstance(seq, torch.Tensor) else np.asarray(seq)
+            seq = [cols[:, j] for j in range(cols.shape[1])]
+        if not isinstance(seq, (list, tuple)):
+            return seq
+        pairs = seq if isinstance(seq[0], (list, tuple)) else [seq]
+        if any(len(pair) != 2 for pair in pairs):
+            raise AssertionError("every shift must be a (dy, dx) pair")
+        if len(pairs) == 1:
+            return list(pairs) * count
+        if len(pairs) != count:
+            raise AssertionError((len(pairs), count))
+        return pairs
 
-    def perturb(self, x, mask, shift=None, mask_shift=None, frame=-1, passive=None, virtual=False):
-        """perturbation.py:245-289.  ``mask`` is the perturbation mask (False = patch to move).  Extensions:
-        ``passive`` (the mask `minimum`-ed in by ``forward``) and ``virtual`` (return a CounterfactualVideo)."""
-        frame = (frame % self.T)
+    def _resolve_shift(self, shift, mask_shift):
+        ph, pw = self.patch_size[-2:]
         if shift is not None:
-            assert len(shift) == 2, shift
-            assert (shift[0] % self.patch_size[-2]) == 0, shift
-            assert (shift[1] % self.patch_size[-1]) == 0, shift
-        elif mask_shift is not None:
-            assert len(mask_shift) == 2, mask_shift
-            shift = (mask_shift[0] * self.patch_size[-2], mask_shift[1] * self.patch_size[-1])
-        else:
-            shift = self.get_random_shift()
-        self.shift = shift
-        mask = self.reshape_mask_to_video(mask).reshape(self.B, -1)
-        if self.T_mask != self.T:
-            raise RuntimeError(f"shape '{list(self.inp_mask_shape)}' is invalid: the mask must cover all {self.T} "
-                               "frames (the reference fails at perturbation.py:287)")
-        if passive is None:
-            passive = torch.ones_like(mask)
-        ms = [[int(shift[0]) // self.patch_size[-2], int(shift[1]) // self.patch_size[-1]]] * self.B
-        video, mask_shift_out = shift_patches_and_masks(
-            x, passive, mask, ms, self.patch_size, frame=frame, static_frame=-1,
-            sample_image=torch.arange(self.B, dtype=torch.int32, device=x.device))
-        mask_shift_out = mask_shift_out.view(*self.inp_mask_shape)
-        return (video if virtual else video.materialize(), mask_shift_out)
+            if len(shift) != 2 or shift[0] % ph or shift[1] % pw:
+                raise AssertionError(f"pixel shift {tuple(shift)} is not a pair of multiples of the patch size")
+            return (shift[0], shift[1])
+        if mask_shift is not None:
+            if len(mask_shift) != 2:
+                raise AssertionError(mask_shift)
+            return (mask_shift[0] * ph, mask_shift[1] * pw)
+        return self.get_random_shift()
 
-    def forward(self, x, mask=None, perturbation_points=None, **kwargs):
-        """``PatchPerturbation.forward`` (perturbation.py:99-112) with the final ``minimum`` fused into the mask
-        kernel: (mask | points) & shifted(~points)."""
+    def forward(self, x, mask=None, perturbation_points=None, shift=None, mask_shift=None, frame=-1, virtual=False):
+        """``(x_shifted, mask_shifted)`` for the batch.  With ``perturbation_points`` (True = patch to move) the
+        result mask is ``(mask | points) & shifted(~points)`` -- the reference's clone / index-assign / ``minimum``
+        sequence (perturbation.py:99-112) folded into the mask kernel; without them ``mask`` itself (False = move)
+        selects the patches.  ``virtual=True`` returns the prompts as a ``CounterfactualVideo``."""
         self.set_shapes(x, mask)
-        if perturbation_points is None:
-            return self.perturb(x, mask, **kwargs)
-        return self.perturb(x, torch.logical_not(perturbation_points), passive=mask, **kwargs)
-
-
-class ShiftPatches(ShiftPatchesAndMask):
-    """Only shift the patches (perturbation.py:291-...): not on the counterfactual path."""
-
-    def perturb(self, *args, **kwargs):
-        raise NotImplementedError("ShiftPatches is not used by the counterfactual path")
+        g = self.geometry
+        moving = mask if perturbation_points is None else torch.logical_not(perturbation_points)
+        if g.frame_masks(moving).shape[1] != g.frames:
+            raise RuntimeError(f"shape '{list(self.inp_mask_shape)}' is invalid: the mask must cover all {g.frames} "
+                               "frames (the reference fails at perturbation.py:287)")
+        moving = moving.reshape(g.batch, -1)
+        held = torch.ones_like(moving) if perturbation_points is None else mask.reshape(g.batch, -1)
+        self.shift = self._resolve_shift(shift, mask_shift)
+        ph, pw = self.patch_size[-2:]
+        per_sample = [[int(self.shift[0]) // ph, int(self.shift[1]) // pw]] * g.batch
+        video, shifted = shift_patches_and_masks(
+            x, held, moving, per_sample, self.patch_size, frame=frame % g.frames, static_frame=-1,
+            sample_image=torch.arange(g.batch, dtype=torch.int32, device=x.device))
+        return (video if virtual else video.materialize()), shifted.view(*self.inp_mask_shape)

@@ -231,9 +231,11 @@ class PredictorBasedGenerator(nn.Module):
             # One device->host read serves both the rectangulariser and the forward: the compaction kernel counts
             # the visible tokens of every row; when they agree (every sweep whose prompts are well formed) the
             # rectangulariser is the identity and draws nothing from the RNG (masking.py:117-128).
-            counts = compact_mask(mask.reshape(x.size(0), -1))[2].cpu()
+            compaction = compact_mask(mask.reshape(x.size(0), -1))
+            counts = compaction[2].cpu()
             if bool((counts == counts[0]).all()):
                 num_visible = int(counts[0])
+                kwargs['compaction'] = compaction   # the forward reuses it: one compaction launch per call
         if num_visible is None:
             mask = mask if (x.size(0) == 1) else self.mask_rectangularizer(mask)
         elif isinstance(self.predictor, PretrainVisionTransformer) and \
@@ -300,7 +302,7 @@ class PredictorBasedGenerator(nn.Module):
             raise RuntimeError("shape mismatch: rows of the mask have different numbers of masked tokens")
         return unpatchify_scatter(y, _x, inv, int(counts[0]), patch_size)
 
-    # ---- host-side helpers of the reference wrapper that involve no forward pass of their own ---------------------
+    # ---- checkpoint loading and the `interface.py` entry points around `predict` ----
     def load_predictor(self, load_path=None, model=None, map_location='cpu'):
         """prediction.py:81-107: load a checkpoint (``{'model': state_dict}`` or a bare state_dict) into the predictor."""
         if (getattr(self, 'predictor', None) is None) and (model is None):
@@ -315,303 +317,48 @@ class PredictorBasedGenerator(nn.Module):
         if model is None:
             self._predictor_load_path = load_path
 
-    def get_fully_visible_mask(self, x=None):
-        x = self.x if x is None else x
-        return torch.zeros(self.mask_shape, device=x.device, dtype=torch.bool)
-
-    def mask_complement(self, mask1, mask2, frame=-1):
-        """prediction.py:231-243: visible exactly where mask1 is masked and mask2 is not (in ``frame``)."""
-        mask1, mask2 = self.get_mask_image(mask1), self.get_mask_image(mask2)
-        mask_diff = mask1 & (~mask2)
-        if frame is None:
-            return (~mask_diff).view(mask_diff.shape[0], -1)
-        frame = frame % mask1.shape[1]
-        return torch.cat([mask1[:, :frame], ~mask_diff[:, frame, None], mask1[:, (frame + 1):]], 1).view(
-            mask_diff.shape[0], -1)
-
-    def patchify_energy_density(self, density, mode='min', beta=None):
-        """prediction.py:284-302: Boltzmann-weight an energy map and pool it to the patch grid."""
-        import torch.nn.functional as F
-        from .masking import boltzmann
-        rank = len(density.shape)
-        assert rank in [4, 5], rank
-        density = boltzmann(density, beta=beta)
-        pool = {(5, 'mean'): F.avg_pool3d, (4, 'mean'): F.avg_pool2d, (5, 'max'): F.max_pool3d, (4, 'max'): F.max_pool2d,
-                (5, 'min'): lambda v, **kw: -F.max_pool3d(-v, **kw),
-                (4, 'min'): lambda v, **kw: -F.max_pool2d(-v, **kw)}[(rank, mode)]
-        ps = tuple(self.patch_size) if rank == 5 else tuple(self.patch_size[-2:])
-        pooled = pool((density.transpose(1, 2) if rank == 5 else density), kernel_size=ps, stride=ps)
-        return pooled.squeeze(1) if rank == 5 else pooled
-
-    def _get_frames(self, x, frames=0):
-        assert len(x.shape) == 5, x.shape
-        return torch.index_select(x, dim=1, index=torch.tensor(frames).long().to(x.device))
-
-    def _get_target(self, x):
-        assert len(x.shape) == 5 and x.shape[1] == 2, x.shape
-        return self._get_frames(x, frames=[1])
-
-    def _get_error(self, pred, gt, dim=-3, frame=None):
-        return self.error_func(pred[:, -gt.shape[1]:], gt).sum(dim, True)
-
-    def get_nearby_patches(self, mask, radius=1, upsample=False, shape=None):
-        """prediction.py:345-351."""
-        from . import masking
-        nearby = masking.patches_adjacent_to_visible(self.get_mask_image(mask, shape=shape), radius=radius, size=None)
-        return masking.upsample_masks(nearby, size=self.inp_shape[-2:]) if upsample else nearby
-
-    @staticmethod
-    def invert_mask_frame(mask, size, frame=-1):
-        """prediction.py:371-381."""
-        shape = mask.shape
-        mask = mask.view(shape[0], -1, *size)
-        frame = frame % mask.size(1)
-        return torch.cat([mask[:, :frame], ~mask[:, frame:frame + 1], mask[:, (frame + 1):]], 1).view(*shape)
-
-    def _invert_mask(self, mask, frame=-1):
-        return self.invert_mask_frame(mask, self.mask_shape[-2:], frame)
-
-    def _sample_random_patches(self, batch_size=1, t_idx=None):
-        """prediction.py:386-394 (two draws of ``self.rng`` per batch element)."""
-        patches = []
-        for b_idx in range(batch_size):
-            if t_idx is None:
-                t_idx = self.mask_shape[0] - 1
-            patches.append([b_idx, t_idx, self.rng.randint(self.mask_shape[1]), self.rng.randint(self.mask_shape[2])])
-        return patches
-
-    def predict_with_mask(self, mask, invert_mask=False, *args, **kwargs):
-        assert self.x is not None
-        return self.predict(self.x, (~mask if invert_mask else mask).view(*self.inp_mask_shape), *args, **kwargs)
-
-    def error_with_mask(self, mask, invert_mask=False, frame=-1, *args, **kwargs):
-        x_pred = self.predict_with_mask(mask, invert_mask, *args, **kwargs)
-        return self._get_error(x_pred[:, frame].unsqueeze(1), self.x[:, frame].unsqueeze(1), dim=-3)
-
-    def get_error_on_target_region(self, x, mask, target_mask, target=None, average_error=True, frame=-1,
-                                   aggregate_over_patches=True, patch_size=None, **kwargs):
-        """prediction.py:553-574: prediction error pooled to patches and restricted to the visible part of target_mask."""
-        import torch.nn.functional as F
-        target = x if target is None else target
-        if len(target_mask.shape) == 2:
-            target_region = 1 - target_mask.view(x.shape[0], -1, *self.mask_shape[-2:]).to(x)
-        else:
-            target_region = 1 - target_mask.to(x)
-        error = self._get_error(self.predict(x, mask, frame=frame, **kwargs), target)
-        if not aggregate_over_patches:
-            return error
-        patch_size = patch_size or self.patch_size
-        error = F.avg_pool3d(error.transpose(1, 2), patch_size, stride=patch_size).squeeze(1) * target_region.to(x)
-        if not average_error:
-            return error
-        return error.sum((1, 2, 3)) / target_region.sum((1, 2, 3)).clamp(min=1)
-
-    def get_initial_mask(self, x):
-        raise NotImplementedError("Need to specify how to get the initial mask")
-
-    @staticmethod
-    def unmask_one_patch(mask, idx=None, mask_shape=None, inplace=False, frame=0):
-        """prediction.py:580-607: make the patch at ``idx`` visible (flat index, or (t, h, w) / (b, t, h, w))."""
-        shape = mask.shape
-        if not inplace:
-            mask = mask.clone()
-        if mask_shape is None:
-            assert len(shape) == 2, "If you don't pass a mask shape, it must be [B,N]"
-            mask[:, idx] = torch.zeros_like(mask[:, 0])
-            return mask
-        if len(idx) == 2 and isinstance(idx, (list, tuple)):
-            idx = [frame] + list(idx)
-        assert (len(idx) == len(mask_shape)) or (len(idx) == (len(mask_shape) + 1)), (idx, mask_shape)
-        idx = [int(i) for i in idx]
-        mask = mask.view(-1, *mask_shape)
-        if len(idx) == len(mask_shape):
-            mask[(slice(None),) + tuple(idx)] = False
-        else:
-            mask[tuple(idx)] = False
-        return mask.view(*shape)
-
-    @staticmethod
-    def patch_idx_list_from_mask(mask):
-        """prediction.py:609-615: [b, t, h, w] of every visible patch of a [B, T, H, W] mask."""
-        assert len(mask.shape) == 4, mask.shape
-        return [list(p) for p in torch.nonzero(~mask).cpu().numpy()]
-
-    def generate_cutout_mask(self, patch_idx_list, radius=1, stride=None, b=0, frame=-1):
-        """prediction.py:649-659 (declared @staticmethod with a ``self`` argument there): the listed patches plus
-        their neighbourhood of ``radius`` patches are visible in ``frame``."""
-        from . import masking
-        mask = self.get_mask_image(self.generate_mask_from_patch_idx_list(patch_idx_list, stride=stride, b=b, frame=frame))
-        cutout = masking.patches_adjacent_to_visible(mask[:, frame:frame + 1], radius=radius)
-        cutout = torch.maximum(cutout, ~mask[:, frame:frame + 1])
-        mask[:, frame] = cutout[:, 0]
-        return mask.flatten(1)
-
-    def get_frame_pairs(self, x, frame=None):
-        """prediction.py:691-701: every frame paired with the target frame."""
-        assert len(x.shape) == 5, x.shape
-        T = x.shape[1]
-        self.num_frame_pairs = T - 1
-        self.target_frame = frame if frame is not None else (T // 2)
-        frames = torch.unbind(x, 1)
-        return [torch.stack([frames[t], frames[self.target_frame]], 1) for t in range(T) if t != self.target_frame]
-
-    def sample_random_masks(self, num_samples=10, num_visible=1, mask_ratio=None):
-        """prediction.py:741-758: S draws of the wrapper's mask generator, stacked on a trailing sample axis."""
-        assert self.mask_generator is not None
-        _num_vis = self.mask_generator.num_visible
-        if mask_ratio is None:
-            self.mask_generator.num_visible = num_visible
-        else:
-            self.mask_generator.mask_ratio = mask_ratio
-        x = self.x if self.x is not None else None
-        masks = torch.stack([self.mask_generator(x) for _ in range(num_samples)], -1)
-        if self.x is not None:
-            masks = masks.to(x.device)
-        self.mask_generator.num_visible = _num_vis
-        return masks
-
-    def predict_keypoints_map(self, x, *args, **kwargs):
-        """prediction.py:815-820."""
-        assert len(x.shape) == 5, x.shape
-        if self.keypoint_predictor is None:
-            return torch.ones_like(x[:, 0:1, 0:1])
-        return self.keypoint_predictor(x, *args, **kwargs)
-
-    def predict_keypoints_distribution(self, x, power=8, eps=1e-3):
-        """prediction.py:822-827: sigmoid(logits)^power, rescaled to [0, 1] over the image."""
-        value = self.predict_keypoints_map(x).squeeze(-3)
-        value = (value.sigmoid()) ** power
-        value = value - value.amin((-2, -1))
-        return value / value.amax((-2, -1)).clamp(min=eps)
-
     def forward(self, x, mask=None, frame=None, *args, **kwargs):
         return self.predict(x, mask, frame, *args, **kwargs)
 
-    # ---- helpers the GUI entry points call (cwm/interface.py: get_masked_pred_patches, predict_error,
-    #      generate_mask_from_patch_idx_list); mask bookkeeping and an elementwise error map around `predict` ----
-    @property
-    def inp_mask_shape(self):
-        return (self.x.shape[0], int(np.prod(self.mask_shape)))
-
-    def set_new_mask(self, x=None):
-        if x is None:
-            x = self.x
-        self.mask = self.generate_mask(x)
-
-    def get_mask_image(self, mask, upsample=False, invert=False, shape=None):
-        """prediction.py:357-365."""
-        if shape is None:
-            shape = self.mask_shape
-        mask = mask.view(-1, *shape)
-        if upsample:
-            from .masking import upsample_masks
-            mask = upsample_masks(mask, self.inp_shape[-2:])
-        if invert:
-            mask = 1 - mask
-        return mask
-
-    @staticmethod
-    def make_visible_from_patch_idx_list(mask, patch_idx_list, stride=1, b=0, t=-1):
-        """prediction.py:617-638: clears mask[b, t, h // stride, w // stride] for every listed (.., h, w)."""
-        if len(patch_idx_list) == 0:
-            return mask
-        if not isinstance(patch_idx_list, torch.Tensor):
-            patch_idx_list = torch.tensor(np.array(patch_idx_list), dtype=torch.long).to(mask.device)
-        inds = torch.unbind(patch_idx_list, -1)
-        inds_h = (inds[-2] // stride) % mask.size(-2)
-        inds_w = (inds[-1] // stride) % mask.size(-1)
-        if len(inds) == 2:
-            inds_b = b * torch.ones_like(inds_h)
-            inds_t = t * torch.ones_like(inds_b)
-        elif len(inds) == 3:
-            inds_b = b * torch.ones_like(inds_h)
-            inds_t = inds[0]
-        else:
-            assert len(inds) == 4, len(inds)
-            inds_b, inds_t = inds[0], inds[1]
-        mask[inds_b, inds_t, inds_h, inds_w] = 0
-        return mask
-
-    def generate_mask_from_patch_idx_list(self, patch_idx_list, stride=None, b=0, frame=-1):
-        """prediction.py:640-648.  NB (reference behaviour, kept): `get_zeros_mask` returns a batch-EXPANDED view, so
-        the indexed write below lands in every batch row whatever ``b`` says -- all rows share the listed patches."""
-        assert self.x is not None
-        m = self.get_mask_image(self.get_zeros_mask(frame=frame))
-        if stride is None:
-            stride = self.inp_shape[-1] // m.size(-1)
-        m = self.make_visible_from_patch_idx_list(m, patch_idx_list, stride=stride, b=b, t=frame)
-        return m.view(m.size(0), -1)
-
-    def get_masked_pred_patches(self, preds, mask, invert=False, fill_value=None):
-        """prediction.py:261-282: the video with the masked patches blanked (or filled) -- display helper."""
-        from .masking import upsample_masks
-        shape = preds.shape
-        pt, ph, pw = self.patch_size
-        mask_shape = (shape[1] // pt, shape[-2] // ph, shape[-1] // pw)
-        mask_vis = upsample_masks(self.get_mask_image(mask, shape=mask_shape), shape[-2:]).to(preds)
-        if invert:
-            mask_vis = 1.0 - mask_vis
-        out = preds * mask_vis.unsqueeze(2)
-        if isinstance(fill_value, torch.Tensor):
-            assert list(fill_value.shape) == list(out.shape)
-            out = out + (1 - mask_vis.unsqueeze(2)) * fill_value
-        elif fill_value is not None:
-            fill_value = torch.tensor(fill_value, dtype=torch.float32).to(out.device).to(out).view(1, 1, -1, 1, 1)
-            out = out + (1 - mask_vis.unsqueeze(2)) * fill_value
-        return out
-
     def predict_error(self, x=None, mask=None, target=None, frame=None, dim=-3):
-        """prediction.py:331-343: `error_func(predict(x, mask), target).sum(dim)` (factual prediction error map)."""
-        if x is None:
-            x = self.x
-        if mask is None:
-            mask = self.generate_mask(x)
-        x_pred = self.predict(x, mask, frame=frame)
-        if target is None:
-            target = x
+        """Factual prediction error map (prediction.py:331-343, `interface.py`'s entry point): `error_func` between
+        `predict(x, mask)` and the target (default: the input itself), summed over ``dim`` (channels)."""
+        x = self.x if x is None else x
+        mask = self.generate_mask(x) if mask is None else mask
+        prediction = self.predict(x, mask, frame=frame)
+        target = x if target is None else target
         if frame is not None:
             target = target[:, frame].unsqueeze(1)
-        return self.error_func(x_pred, target).sum(dim, True)
+        return self.error_func(prediction, target).sum(dim, True)
 
     # ---- counterfactual prompts (SURVEY 8(f) rank 1) ----
     def set_input(self, x, mask=None, make_mask=False, timestamps=None):
-        """prediction.py:703-724."""
-        shape = x.shape
-        if len(shape) == 4:
+        """Remembers the movie the following calls work on (prediction.py:703-724): a single frame ``[B, C, H, W]``
+        becomes a one-frame movie; ``mask`` / ``timestamps`` are stored when given, ``make_mask`` draws a fresh mask."""
+        if x.dim() == 4:
             x = x.unsqueeze(1)
-        else:
-            assert len(shape) == 5, \
-                "Input must be a movie of shape [B,T,C,H,W]" + \
-                "or a single frame of shape [B,C,H,W]"
-        self.inp_shape = x.shape
-        self.x = x
-        self.B = self.inp_shape[0]
-        self.T = self.inp_shape[1]
-        self.C = self.inp_shape[2]
+        elif x.dim() != 5:
+            raise AssertionError("Input must be a movie of shape [B,T,C,H,W] or a single frame of shape [B,C,H,W]")
+        self.x, self.inp_shape = x, x.shape
+        self.B, self.T, self.C = (int(v) for v in x.shape[:3])
         if mask is not None:
             self.mask = mask
         elif make_mask:
-            assert self.mask_generator is not None, "You need to have a mask generator to set a new mask"
-            self.mask = self.generate_mask(self.x)
+            if self.mask_generator is None:
+                raise AssertionError("You need to have a mask generator to set a new mask")
+            self.mask = self.generate_mask(x)
         if timestamps is not None:
             self.timestamps = timestamps
 
-    def get_static_input(self, x=None):
-        """prediction.py:726-729."""
-        if x is None:
-            x = self.x
-        return torch.tile(x[:, 0:1], (1, x.size(1), 1, 1, 1))
-
     def make_static_movie(self, x=None, T=None, frame=0):
-        """prediction.py:731-740."""
-        if x is None:
-            x = self.x
-        if T is None:
-            T = getattr(self.predictor, 'num_frames', 2)
-        if len(x.shape) == 4:
-            x = x[:, None]
-        assert len(x.shape) == 5, "x must be of shape [B,C,H,W] or [B,T,C,H,W], but is %s" % x.shape
-        return torch.tile(x[:, frame % x.size(1), None], (1, T, 1, 1, 1))
+        """``T`` copies of one frame of ``x`` as a ``[B, T, C, H, W]`` movie (prediction.py:731-740)."""
+        x = self.x if x is None else x
+        T = getattr(self.predictor, 'num_frames', 2) if T is None else T
+        if x.dim() == 4:
+            x = x.unsqueeze(1)
+        if x.dim() != 5:
+            raise AssertionError("x must be of shape [B,C,H,W] or [B,T,C,H,W], but is %s" % (tuple(x.shape),))
+        return x[:, frame % x.size(1)].unsqueeze(1).repeat(1, T, 1, 1, 1)
 
     def _shift(self, x, mask, active_patches=None, shift=None, frame=1, virtual=False):
         """prediction.py:756-779: ``shift`` is a mask shift (patch units)."""

@@ -508,13 +508,15 @@ class PretrainVisionTransformer(nn.Module):
         return (x, mask)  # vmae.py:466-469 with main_input=None
 
     @torch.no_grad()
-    def forward(self, x, mask, timestamps=None, *args, input_norm=None, num_visible=None, **kwargs):
+    def forward(self, x, mask, timestamps=None, *args, input_norm=None, num_visible=None, compaction=None, **kwargs):
         """``x`` float [B, C, T, H, W] (any strides), ``mask`` bool [B, Ntot] (True = masked) ->
         float32 [B, Nmask, D] predicted patches of the masked tokens in ascending token order (vmae.py:539-560).
 
         Extensions (keyword-only, not in the reference): ``input_norm=(mean, std)`` fuses ``imagenet_normalize``
         of the raw input into the patch gather; ``num_visible`` skips the device->host read of the per-row
-        visible count (the caller vouches that every row has exactly that many visible tokens)."""
+        visible count (the caller vouches that every row has exactly that many visible tokens); ``compaction`` is the
+        ``(perm, inv_perm, counts)`` triple ``compact_mask`` already returned for exactly this mask (the wrapper runs
+        the compaction once to read the counts for its rectangulariser and hands the result on)."""
         lib = _lib.load()
         if x.device.type != "cuda":
             raise RuntimeError(
@@ -546,7 +548,11 @@ class PretrainVisionTransformer(nn.Module):
         with torch.cuda.device(x.device):
             model = self._engine.ensure(self, x.device)
             aux = self._engine.get_aux(B, Ntot, x.device)
-            perm, inv, nvis = compact_mask(mask, out=aux)
+            if compaction is not None:
+                perm, inv, nvis = compaction
+                assert perm.shape == (B, Ntot) and perm.device == x.device, (perm.shape, perm.device)
+            else:
+                perm, inv, nvis = compact_mask(mask, out=aux)
             if num_visible is None:
                 counts = nvis.cpu()
                 n_vis = int(counts[0]) if B > 0 else 0
@@ -576,7 +582,8 @@ class PretrainVisionTransformer(nn.Module):
                 _lib.check(lib.cwm_vmae_forward(ctypes.byref(model), x.data_ptr(), _lib.strides5(x), B, mean, std,
                                                 perm.data_ptr(), n_vis, y.data_ptr(), ws.data_ptr(), ws.numel(),
                                                 stream))
-            self.last_forward_launches = lib.cwm_last_forward_launches() + 1  # + the compaction kernel
+            # + the compaction kernel when it ran here
+            self.last_forward_launches = lib.cwm_last_forward_launches() + (1 if compaction is None else 0)
             self.last_aux = (perm, inv, n_vis)
         return y
 

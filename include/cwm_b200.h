@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define CWM_B200_ABI_VERSION 5
+#define CWM_B200_ABI_VERSION 6
 
 typedef void* cwm_stream_t; /* cudaStream_t */
 
@@ -434,6 +434,21 @@ int cwm_raft_flow_update(const uint16_t* delta, int ldd, const float* bias, floa
  * cwm_launch_count_reset() was called (for bench accounting). */
 int cwm_last_forward_launches(void);
 int cwm_launch_count_reset(void);
+/* Monotonic count of every kernel launch this thread ever enqueued through the library (never reset): the difference
+ * of two reads brackets a region, e.g. bench.py's timed steps. */
+long long cwm_total_launches(void);
+
+/* ---- tuning hooks -------------------------------------------------------------------------------------------------
+ * Process-wide switches used by tools/kernel_bench.py and the A/B tests; they select between result-identical kernel
+ * variants (or, for the polynomial share, variants inside the same tolerance) and are not part of the reference-facing
+ * boundary. */
+void cwm_debug_attention_poly(int eighths);        /* share (in 1/8) of the softmax exponentials evaluated on the FMA pipe */
+void cwm_debug_attention_war_safe(int on);         /* conservative score-buffer reuse (debug) */
+void cwm_debug_attention_persistent(int mode);     /* 1 = persistent CTAs (default), 3 = one work item per CTA; 2 / 4 = the same with watchdog waits */
+void cwm_debug_attention_persist_map(int m);       /* work-item map of the persistent kernel: -1 auto, 0 ranges, 1 strided */
+void cwm_debug_attn_mma_wide(int on);              /* small-attention kernel: 8 warps per K/V tile */
+void cwm_debug_attn_mma_split(int keys);           /* small-attention kernel: key-axis split */
+int cwm_debug_gemm_cta2(int enable);               /* CTA-pair GEMM kernels on (default) / off; returns CWM_OK */
 
 /* ---- per-kernel timing (bench.py's roofline numbers) -------------------------------------------------
  * Between cwm_profile_begin() and cwm_profile_end() every launch made through this library is bracketed by two

@@ -1,19 +1,40 @@
 """TEST INFRASTRUCTURE ONLY -- loader for the *real* reference (read-only mount at /root/reference).
 
-Only usable in the build container (the GPU box has no /root/reference).  It is used by
-``oracle/make_golden.py`` to (a) pin ``oracle/vmae_oracle.py`` against the reference module and
-(b) generate the fixtures under ``tests/golden/``.  Nothing in the product package imports this.
+In the build container the reference is the read-only mount at /root/reference; on the GPU box (no mount) it is
+the unmodified copy that ``baseline/stage_reference.py`` staged under the git-ignored ``baseline/_ref/`` (it travels
+with the gpurun snapshot).  Used by ``oracle/make_golden*.py`` to (a) pin the oracles against the reference modules and
+(b) generate the fixtures under ``tests/golden/``; by the reference-wrapper GPU tests (the reference's OWN
+``PredictorBasedGenerator`` / ``FlowGenerator`` driving the drop-in predictor); and by ``bench.py --impl reference``.
+Nothing in the product package imports this.
 
 The reference needs three pip packages that are absent here: ``timm`` (five
 symbols: vmae.py:12-15, VideoMAE/utils.py:6-9), ``kornia`` and ``matplotlib`` (import-only on this
 path).  We register in-process stubs in ``sys.modules`` before importing ``cwm``.
 """
+import os
 import sys
 import types
 
 import torch
 
-REFERENCE_ROOT = "/root/reference"
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# the staged copy first: the GPU tests and bench.py then import the same files on both boxes and never touch the mount
+_CANDIDATES = (os.path.join(os.path.dirname(_HERE), "baseline", "_ref"), "/root/reference")
+
+
+def reference_root():
+    """The first location that holds the reference's ``cwm`` package (None if neither does)."""
+    for root in _CANDIDATES:
+        if os.path.isfile(os.path.join(root, "cwm", "models", "VideoMAE", "vmae.py")):
+            return root
+    return None
+
+
+REFERENCE_ROOT = reference_root() or _CANDIDATES[1]
+
+
+def available():
+    return reference_root() is not None
 
 
 def _stub(name):

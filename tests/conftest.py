@@ -13,6 +13,16 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
 
+def reference_available():
+    """True when the real reference can be imported: the staged copy under baseline/_ref (travels to the GPU box) or,
+    in the build container, the /root/reference mount (oracle/ref_loader.py)."""
+    import ref_loader
+    return ref_loader.available()
+
+
+needs_reference = pytest.mark.skipif(not reference_available(), reason="real reference neither staged nor mounted")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA sm_100 (B200) device")
     config.addinivalue_line("markers", "slow: CPU-heavy (large oracle runs)")

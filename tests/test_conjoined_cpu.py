@@ -9,7 +9,7 @@ import torch
 
 import conjoined_oracle as co
 import make_golden_conjoined as mgc
-from conftest import load_golden_conjoined
+from conftest import load_golden_conjoined, needs_reference
 from counterfactualworldmodels_b200 import conjoined_vmae as C
 from counterfactualworldmodels_b200 import preprocessor, synthetic, transformer
 
@@ -137,7 +137,7 @@ def test_pos_embedding_and_preprocessors():
         preprocessor.get_preprocessor('flowback_rgb01')(torch.zeros(1, 3, 2, 8, 8))
 
 
-@pytest.mark.skipif(not os.path.isdir("/root/reference/cwm"), reason="reference mount absent (GPU box)")
+@needs_reference
 def test_state_dict_keys_match_reference_live():
     import sys
     import ref_loader

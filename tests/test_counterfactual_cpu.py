@@ -9,7 +9,7 @@ import pytest
 import torch
 
 import counterfactual_oracle as cfo
-from conftest import GOLDEN_DIR
+from conftest import GOLDEN_DIR, needs_reference
 from counterfactualworldmodels_b200 import perturbation, synthetic
 
 CF_CASES = ["cf_tiny_4x4_s6", "cf_tiny_8x8_s8_clump2", "cf_small_4x4_s8_moving_input", "cf_base_8x8_s8_preset"]
@@ -93,7 +93,7 @@ def test_no_cpu_fallback():
     assert "oracle" not in src.replace("SURVEY", "")
 
 
-@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="needs the reference mount (build container only)")
+@needs_reference
 def test_oracle_matches_live_reference():
     import ref_loader
     ref_vmae, _ = ref_loader.import_reference()

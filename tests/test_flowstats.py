@@ -9,7 +9,7 @@ import pytest
 import torch
 
 import flowstats_oracle as fso
-from conftest import GOLDEN_DIR
+from conftest import GOLDEN_DIR, needs_reference
 
 FS_CASES = ["fs_b2_s6_32px", "fs_b1_s12_64px", "fs_b1_s8_224px"]
 FILTER = dict(filter_methods=['patch_magnitude', 'flow_area', 'num_corners'], flow_magnitude_threshold=5.0,
@@ -146,7 +146,7 @@ def test_oracle_flow_corrs_matches_reference_fixture():
     assert np.array_equal(fso.flow_corrs(flows, downsample=4, use_covariance=False).numpy(), d["flow_corr_ds4"])
 
 
-@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="live reference not mounted")
+@needs_reference
 def test_flow_corrs_general_options_match_the_live_reference():
     """The options of compute_flow_corrs the reference's only caller never sets (segmentation.py:478-547): the torch-op
     route reproduces the reference bit for bit on CPU (the public method only accepts device tensors)."""

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 import vmae_oracle as oracle
-from conftest import golden_case_inputs, load_golden
+from conftest import golden_case_inputs, load_golden, needs_reference
 from counterfactualworldmodels_b200 import synthetic, vmae
 
 FAST_CASES = ["tiny_4x4_b2", "tiny_8x8_b3", "small_4x4_b2", "small_4x4_allvisible_frame1half", "base_8x8_b1_factual",
@@ -69,7 +69,7 @@ def test_fp16_operand_emulation_is_within_tolerance_small():
     assert err.max().item() < 2e-2 and err.mean().item() < 2e-3
 
 
-@pytest.mark.skipif(not os.path.isdir("/root/reference/cwm"), reason="reference mount absent (GPU box)")
+@needs_reference
 def test_oracle_matches_reference_module_live():
     import ref_loader
     ref_vmae, ref_pred = ref_loader.import_reference()
