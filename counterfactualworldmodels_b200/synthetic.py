@@ -108,7 +108,43 @@ def init_weights_(model, seed=0, style="reference", skip=("get_main_input.flow_m
             else:
                 raise ValueError(f"unexpected parameter {name} {tuple(t.shape)}")
             t.copy_(v.to(t.dtype))
+        if style == "trained_like":      # massive-activation channels + a mild drift of the token mean
+            _add_trained_like_statistics_(sd, g)
+        elif style == "mean_drift":      # stress: no outliers, the token mean runs away to several sigma
+            _add_trained_like_statistics_(sd, g, mean_step=None, outliers=0)
     return model
+
+
+def _add_trained_like_statistics_(sd, g, mean_step=0.9, outliers=4, outlier_scale=60.0):
+    """Makes the residual streams look like a TRAINED ViT's instead of a freshly initialised one: every
+    producer of the residual stream (patch embedding, each block's proj / fc2, the encoder->decoder map's input norm)
+    gets a common per-channel offset so that the token mean drifts away from zero layer after layer (|mean| of a row
+    reaches several of its standard deviations), and a handful of channels carry "massive activations" two orders of
+    magnitude above the rest.  LayerNorm affine parameters are spread out as well.  On top of style="reference"."""
+    def randn(shape):
+        return torch.empty(shape).normal_(0, 1, generator=g)
+
+    for stream in ("encoder", "decoder"):
+        bias_names = sorted(n for n in sd if n.startswith(stream + ".blocks.") and
+                            (n.endswith("attn.proj.bias") or n.endswith("mlp.fc2.bias")))
+        if not bias_names:
+            continue
+        C = sd[bias_names[0]].numel()
+        step = mean_step if mean_step is not None else 22.0 / len(bias_names)   # ends near 9 sigma at any depth
+        big = torch.randperm(C, generator=g)[:outliers]
+        sign = torch.where(torch.rand(outliers, generator=g) < 0.5, -1.0, 1.0)
+        for n in bias_names:
+            b = sd[n]
+            b.add_(step + 0.1 * randn(b.shape))            # common drift: the row mean grows with depth
+            if outliers:
+                b[big] += sign * outlier_scale * (0.5 + torch.rand(outliers, generator=g))
+        for n in sorted(n for n in sd if n.startswith(stream + ".") and n.endswith(("norm1.weight", "norm2.weight",
+                                                                                    "norm.weight"))):
+            sd[n].mul_(torch.empty(sd[n].shape).uniform_(0.5, 1.5, generator=g))
+            sd[n.replace("weight", "bias")].add_(0.1 * randn(sd[n].shape))
+    pe = "encoder.patch_embed.proj.bias"
+    if pe in sd:
+        sd[pe].add_(2.0 if outliers else 3.0)
 
 
 def weights_checksum(model):

@@ -1,6 +1,7 @@
 """GPU parity of the padded / conjoined (IMU-conditioned) predictors (BASELINE
 config 5) through the C ABI against the fixtures the REAL reference produced and against the CPU oracle.
 Tolerance (BASELINE.json north_star): index work bit-exact; predicted values max-abs <= 2e-2, mean-abs <= 2e-3."""
+import os
 from functools import partial
 
 import numpy as np
@@ -10,7 +11,7 @@ import torch
 import conjoined_oracle as co
 import make_golden_conjoined as mgc
 import vmae_oracle as oracle
-from conftest import load_golden_conjoined
+from conftest import GOLDEN_DIR, load_golden_conjoined
 from counterfactualworldmodels_b200 import conjoined_vmae as C
 from counterfactualworldmodels_b200 import prediction, synthetic
 
@@ -141,3 +142,34 @@ def test_conjoined_batch_invariance():
         alone = m(xs[i:i + 1], masks[i:i + 1], x_context=imus[i:i + 1], mask_context=mcs[i:i + 1])
         m._reset_padding_mask()
         assert torch.equal(alone[0], full[i])
+
+
+def test_flow2imu_full_size_matches_reference_fixture():
+    """a17 at FULL size: the factory `imu400_8x8patch_2frames_1tube_flowbackrgb01` (conjoined_vmae.py:1218-1228; ViT-base,
+    784 tokens of the 7-channel flow | flow-back | rgb input its preprocessor builds with RAFT, 25 masked IMU tokens + the
+    dummy token), called like `ImuConditionedFlowGenerator.predict_imu_from_video` does (segmentation.py:834-846).
+    Fixture: the REAL reference on CPU, seeded RAFT-large in the preprocessor (oracle/make_golden_flow2imu.py).
+    The flow network runs in fp32 here (the parity configuration), so its 2.7e-6-of-scale error is invisible next to the
+    f16-operand error of the ViT; bars: predicted IMU tokens within 2e-2 max-abs / 2e-3 mean-abs."""
+    import make_golden_flow2imu as mgf
+    from counterfactualworldmodels_b200 import raft
+    path = os.path.join(GOLDEN_DIR, "flow2imu_full_b2.npz")
+    if not os.path.exists(path):
+        pytest.skip("fixture flow2imu_full_b2 missing")
+    g = np.load(path)
+    torch.manual_seed(0)
+    rargs = raft.get_args("")
+    rargs.multiframe, rargs.scale_inputs, rargs.output_dim = True, True, None
+    flow_model = raft.RAFT(rargs).eval().requires_grad_(False)
+    m = mgf.build(C, 'flow_model', flow_model).to(DEV)
+    assert sum(p.numel() for p in m.parameters()) == mgf.PARAMS == int(g["num_params"][0])
+    assert synthetic.weights_checksum(m) == pytest.approx(float(g["weights_checksum"][0]), rel=1e-9)
+    x, mask, imu, mc = mgf.inputs()
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        y = m(oracle.preprocess(x).to(DEV), mask=mask.to(DEV), x_context=imu.to(DEV), mask_context=mc.to(DEV),
+              output_main=False, output_context=True)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    _check(y, torch.from_numpy(g["y_ctx"]), "flow2imu full size, IMU tokens")

@@ -87,3 +87,20 @@ def test_oracle_matches_reference_module_live():
     ours = vmae.PretrainVisionTransformer(**synthetic.model_kwargs("tiny_8x8"))
     missing = ours.load_state_dict(ref.state_dict())
     assert not missing.missing_keys and not missing.unexpected_keys
+
+
+@pytest.mark.parametrize("case", ["tiny_8x8_b2_trained_like", "base_8x8_b1_trained_like", "base_8x8_b1_mean_drift"])
+def test_oracle_reproduces_the_trained_like_fixtures(case):
+    """oracle/make_golden_stats.py: the reference under trained-like activation statistics (outlier channels, token
+    means of several sigma); the fixture records the statistics the reference actually reached."""
+    import make_golden_stats as mgs
+    g = load_golden(case)
+    cfg_name, B, wseed, x, mask, style = mgs.case_inputs(case)
+    m, sd = _our_state_dict(cfg_name, wseed, style)
+    assert torch.equal(mask, g["mask"])
+    y = oracle.vmae_forward(sd, oracle.preprocess(x), mask, synthetic.oracle_cfg(cfg_name))
+    assert (y - g["y"]).abs().max().item() <= 2e-5 * max(1.0, g["y"].abs().max().item())
+    if style == "mean_drift":
+        assert g["enc_mean_over_sigma"].max() >= 3.0 and g["dec_mean_over_sigma"].max() >= 3.0
+    else:
+        assert g["enc_max_over_median"].max() >= 30.0

@@ -109,6 +109,9 @@ def test_reference_flow_generator_sweep_over_the_dropin_predictor(flow_model_kin
         raft_dev = our_raft.RAFT(our_raft.get_args("")).eval().requires_grad_(False)
         raft_dev.args.multiframe = raft_dev.multiframe = True
         raft_dev.args.scale_inputs = raft_dev.scale_inputs = True
+        # the reference's `set_raft_iters` (segmentation.py:86-90) only finds instances of ITS RAFT class, so the
+        # iteration count of a drop-in flow network is set on the module itself
+        raft_dev.iters = 4
     raft_dev.load_state_dict(raft_cpu.state_dict())
     raft_dev = raft_dev.to(DEV)
     x = synthetic.make_video(1, hw, seed=41)[:, 0]
