@@ -27,6 +27,8 @@ EXPORTED_SYMBOLS = (
     "cwm_gemm_ln_parts", "cwm_rowstats_f16", "cwm_raft_corr_pyramid", "cwm_raft_corr_lookup", "cwm_raft_upsample_flow",
     "cwm_raft_corr_lookup_f16", "cwm_raft_bias_act_f16", "cwm_raft_gru_gate_f16", "cwm_raft_gru_update_f16",
     "cwm_raft_flow_update", "cwm_total_launches",
+    "cwm_philox4x32_10", "cwm_mask_uniform", "cwm_mask_energy_table", "cwm_mask_energy_sample",
+    "cwm_mask_rectangularize_workspace_bytes", "cwm_mask_rectangularize",
     # tuning hooks (header section "tuning hooks")
     "cwm_debug_attention_poly", "cwm_debug_attention_war_safe", "cwm_debug_attention_persistent",
     "cwm_debug_attention_persist_map", "cwm_debug_attn_mma_wide", "cwm_debug_attn_mma_split", "cwm_debug_gemm_cta2",
@@ -171,6 +173,15 @@ def _declare(lib):
                                           c_void_p]
     lib.cwm_raft_gru_update_f16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_ll, c_void_p, c_void_p]
     lib.cwm_raft_flow_update.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]
+    c_u64, c_u32p = ctypes.c_uint64, POINTER(ctypes.c_uint32)
+    lib.cwm_philox4x32_10.argtypes = [c_u32p, c_u32p, c_u32p]
+    lib.cwm_mask_uniform.argtypes = [c_u64] + [c_int] * 8 + [c_void_p, c_void_p]
+    lib.cwm_mask_energy_table.argtypes = [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p]
+    lib.cwm_mask_energy_sample.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_u64, c_int, c_int, c_int, c_int,
+                                           c_void_p, c_void_p]
+    lib.cwm_mask_rectangularize_workspace_bytes.argtypes = [c_int]
+    lib.cwm_mask_rectangularize_workspace_bytes.restype = c_size_t
+    lib.cwm_mask_rectangularize.argtypes = [c_void_p, c_int, c_int, c_int, c_u64, c_int, c_void_p, c_size_t, c_void_p]
     lib.cwm_profile_begin.restype = c_int
     lib.cwm_profile_end.argtypes = [POINTER(ProfileEntry), c_int, POINTER(c_int)]
     for name in EXPORTED_SYMBOLS:   # a missing export fails here, at load time, not at first use

@@ -130,7 +130,9 @@ def sharded_counterfactual_videos(generator, x, active_patches, passive_patches=
     video, masks = G.create_motion_counterfactuals(x, masks=passive_patches, active_patches=active_patches,
                                                    shifts=shifts, num_samples=S, fix_passive=fix_passive,
                                                    reset_shifts=False, frame=frame, virtual=True)
-    if multi:
+    if multi and not getattr(G, 'device_masks', False):
+        # host rectangulariser: global RNG, so rank 0's result is THE result.  With device_masks=True the rectangulariser
+        # is a pure function of (seed, row): every rank already holds the same masks and nothing is exchanged.
         m8 = masks.contiguous().view(torch.uint8)
         dist.broadcast(m8, src=0)
         masks = m8.view(torch.bool)

@@ -117,11 +117,21 @@ class FlowSampleFilter(nn.Module):
 
     def forward(self, flow_samples, active_patches):
         """flow_samples [B, 2, H, W, S], active_patches [B, num_patches, S] -> (flow_samples with the rejected samples
-        set to zero IN PLACE, filter mask expanded to the shape of flow_samples) -- sampling.py:252-286."""
+        set to zero IN PLACE, filter mask expanded to the shape of flow_samples) -- sampling.py:252-286.
+
+        Stride contract (differs from the reference): the reference returns ``flow_samples.contiguous()``,
+        a 411 MB copy for a 1024-sample sweep because its input is the permuted ``'(b s) c h w -> b c h w s'`` view;
+        here the SAME strided view comes back (every kernel downstream takes strides).  Call ``.contiguous()`` on the
+        result before ``.view()``-ing it."""
         lib = _lib.load()
         B, _, H, W, S = flow_samples.shape
+        if flow_samples.dtype != torch.float32:
+            # e.g. fp16 flows from an autocast flow network: the statistics run on an fp32 copy, the rejected samples
+            # are zeroed in the caller's tensor (the reference accepts any float dtype, sampling.py:252-286)
+            mask, _ = self.filter_mask(flow_samples.float(), active_patches)
+            flow_samples.mul_((~mask).view(B, 1, 1, 1, S).to(flow_samples.dtype))
+            return flow_samples, mask.view(B, 1, 1, 1, S).expand_as(flow_samples)
         mask, _ = self.filter_mask(flow_samples, active_patches)
-        assert flow_samples.dtype == torch.float32, flow_samples.dtype
         with torch.cuda.device(flow_samples.device):
             stream = torch.cuda.current_stream(flow_samples.device).cuda_stream
             _lib.check(lib.cwm_flow_zero_filtered(flow_samples.data_ptr(), _strides(flow_samples, 5), B, H, W, S,

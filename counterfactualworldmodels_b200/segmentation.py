@@ -22,6 +22,9 @@ from .prediction import PredictorBasedGenerator
 from .sampling import FlowSampleFilter
 
 
+_DEFAULT_FILTER = object()   # sentinel: "build the default FlowSampleFilter"
+
+
 class FlowGenerator(PredictorBasedGenerator):
     """A wrapper for masked predictors that builds motion counterfactuals and (with a caller-supplied flow network)
     runs the counterfactual movies through it (segmentation.py:23-41)."""
@@ -41,18 +44,30 @@ class FlowGenerator(PredictorBasedGenerator):
     }
 
     def __init__(self, *args, flow_model=None, flow_model_load_path=None, flow_model_kwargs={}, raft_iters=24,
-                 flow_sample_filter=None,
+                 flow_sample_filter=_DEFAULT_FILTER,
                  patch_sampling_func=RotatedTableEnergyMaskingGenerator,
-                 patch_sampling_kwargs=default_patch_sampling_kwargs, **kwargs):
+                 patch_sampling_kwargs=default_patch_sampling_kwargs, device_masks=False, **kwargs):
         super().__init__(*args, **kwargs)
+        # device_masks=True (extension): patches are sampled and masks rectangularised on the device
+        # from a counter-based RNG (device_masks.py) -- reproducible for any number of GPUs, but not the reference's
+        # host RNG streams, hence opt-in
+        self.device_masks = bool(device_masks)
+        if self.device_masks:
+            from .device_masks import DeterministicRectangularizeMasks, DeviceEnergyMaskingGenerator
+            if patch_sampling_func is RotatedTableEnergyMaskingGenerator:
+                patch_sampling_func = DeviceEnergyMaskingGenerator
+            self.mask_rectangularizer = DeterministicRectangularizeMasks(seed=self.seed)
+        self._sweep_counter = 0
         # submodule for sampling patches (segmentation.py:65-69): consumes one draw of self.rng like the reference
         self._patch_sampling_func = patch_sampling_func
         self._patch_sampling_kwargs = copy.deepcopy(self.default_patch_sampling_kwargs)
         self._patch_sampling_kwargs.update(patch_sampling_kwargs)
         self.patch_sampler = None
         self.set_patch_sampler()
-        self.flow_sample_filter = flow_sample_filter if flow_sample_filter is not None else \
-            FlowSampleFilter(**self.default_flow_filter_params)
+        # the reference's default argument is a filter instance and an explicit None means "no filtering"
+        # (segmentation.py:48,63)
+        self.flow_sample_filter = FlowSampleFilter(**self.default_flow_filter_params) \
+            if flow_sample_filter is _DEFAULT_FILTER else flow_sample_filter
         if flow_model is not None or flow_model_load_path is not None:
             self.set_flow_model(flow_model=flow_model, flow_model_load_path=flow_model_load_path, **flow_model_kwargs)
         else:
@@ -195,6 +210,11 @@ class FlowGenerator(PredictorBasedGenerator):
             energy = torch.ones_like(self.x[:, 0, 0:1])
         energy = boltzmann(energy, beta)
         torch.manual_seed(self.rng.randint(99999))
+        if self.device_masks and hasattr(self.patch_sampler, 'sample'):
+            # one table + one sampling launch for the whole sweep; sample s of sweep k is global sample (k << 20) + s
+            masks = self.patch_sampler.sample(energy, num_samples, sample_offset=self._sweep_counter << 20)
+            self._sweep_counter += 1
+            return masks
         if batched:
             return self._sample_patches_batched(energy, num_samples)
         return torch.stack([self.patch_sampler(energy) for _ in range(num_samples)], -1)
@@ -285,7 +305,7 @@ class FlowGenerator(PredictorBasedGenerator):
         samples.  The options the reference's only caller uses (interface.py:27-29, :466-493: ``downsample``,
         ``use_covariance``, ``take_top_k``) run on the hand-written kernels; the other options take the torch-op route of
         ``_flow_corrs_general``."""
-        custom_distance = distance_func is not None and type(distance_func).__name__ != "ChannelMSE"
+        custom_distance = distance_func is not None and not FlowGenerator._is_channel_rms(distance_func)
         if flow_samples_swap is not None or do_spearman or custom_distance or thresh is not None or \
                 binarize or normalize or zscore or range_thresh is not None:
             # the options the reference's only caller never sets: the same feature transforms as torch ops on the
@@ -302,6 +322,12 @@ class FlowGenerator(PredictorBasedGenerator):
         if take_top_k is not None:
             flow_samples = flow_samples[..., :take_top_k]
         return sampling.flow_corrs(flow_samples, downsample=downsample, use_covariance=use_covariance)
+
+    @staticmethod
+    def _is_channel_rms(distance_func):
+        """True only for the reference's default ``ChannelMSE(dim=1)`` (utils.py:510-521): the channel-RMS the kernels
+        hard-code.  Any other class, or the same class reducing another dim, takes the general route."""
+        return type(distance_func).__name__ == "ChannelMSE" and getattr(distance_func, 'dim', 1) in (1, -4)
 
     @staticmethod
     def _flow_corrs_general(flow_samples, flow_samples_swap=None, downsample=1, take_top_k=None, do_spearman=False,
@@ -325,7 +351,7 @@ class FlowGenerator(PredictorBasedGenerator):
         flow_inp = _ds(flow_samples)
         if flow_samples_swap is not None:
             flow_inp = torch.cat([flow_inp, _ds(flow_samples_swap)], -1)
-        if distance_func is None or type(distance_func).__name__ == "ChannelMSE":
+        if distance_func is None or FlowGenerator._is_channel_rms(distance_func):
             flow_inp = torch.sqrt(flow_inp.square().mean(1, True).float())      # ChannelMSE(dim=1), utils.py:510-521
         else:
             flow_inp = distance_func(flow_inp, torch.zeros_like(flow_inp))

@@ -430,6 +430,38 @@ int cwm_raft_gru_update_f16(const uint16_t* q, const float* bias, const uint16_t
 int cwm_raft_flow_update(const uint16_t* delta, int ldd, const float* bias, float* coords1, int B, int H, int W,
                          uint16_t* flow16, cwm_stream_t stream);
 
+/* ---- masks on device with a counter-based RNG (csrc/masks.cu) --------------------------------------
+ * Opt-in stand-ins for the reference's host-side mask generation (cwm/models/masking.py:347-401 MaskingGenerator.
+ * sample_mask_per_frame, :478-545 RotatedTableUniformMaskingGenerator; sampling.py:63-90 EnergySamplingMaskingGenerator;
+ * utils.py:152-213 sample_from_energy; masking.py:100-132 RectangularizeMasks).  Draws come from Philox4x32-10 keyed by
+ * `seed` with the counter (draw, GLOBAL sample index, stream, sub-stream): a sample's mask does not depend on the batch
+ * split or the number of GPUs.  Masks are uint8 rows [frames * h * w], 1 = masked. */
+
+/* Host-side reference point of the generator (no device work): out = Philox4x32-10(counter, key). */
+int cwm_philox4x32_10(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]);
+
+/* rows masks [rows, (visible_frames + mask_frames) * h * w]: the first `visible_frames` frames fully visible, in every
+ * masked frame `n_visible_cells` of the (h/clump) x (w/clump) clump cells visible, uniformly without replacement.
+ * Row r is global sample row0 + r. */
+int cwm_mask_uniform(uint64_t seed, int row0, int rows, int visible_frames, int mask_frames, int h, int w, int clump,
+                     int n_visible_cells, uint8_t* masks, cwm_stream_t stream);
+
+/* probs [B, n] (fp32 weights of the n clump cells of each image) -> inclusive integer cumulative table [B, n] of
+ * floor(relu(p - min p + eps) / max * 2^24) (utils.py:160-163 with normalize=True, quantised). */
+int cwm_mask_energy_table(const float* probs, int B, int n, float eps, uint64_t* table, cwm_stream_t stream);
+
+/* masks [B * S, (visible_frames + 1) * h * w]: for image b and sample s (global index sample0 + s), `points` clump cells
+ * drawn WITH replacement from table[b] are visible in the last frame (duplicates collapse, as in the reference). */
+int cwm_mask_energy_sample(const uint64_t* table, int B, int h, int w, int clump, uint64_t seed, int sample0, int S,
+                           int points, int visible_frames, uint8_t* masks, cwm_stream_t stream);
+
+/* RectangularizeMasks('min') in place on masks [rows, N]: every row keeps `target_masked` masked tokens (< 0: the minimum
+ * over the rows given); the revealed tokens of row r are the masked ones with the smallest Philox keys of global row
+ * row0 + r.  Pass the global minimum as `target_masked` when the rows are a shard of a larger batch. */
+size_t cwm_mask_rectangularize_workspace_bytes(int rows);
+int cwm_mask_rectangularize(uint8_t* masks, int rows, int N, int row0, uint64_t seed, int target_masked, void* workspace,
+                            size_t workspace_bytes, cwm_stream_t stream);
+
 /* Number of kernel launches this thread enqueued through the library since the last cwm_vmae_forward began or
  * cwm_launch_count_reset() was called (for bench accounting). */
 int cwm_last_forward_launches(void);
