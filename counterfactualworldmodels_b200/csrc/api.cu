@@ -78,6 +78,29 @@ int make_tmap_2d(CUtensorMap* map, const void* base, int dtype, uint64_t rows, u
   return CWM_OK;
 }
 
+int make_tmap_nhwc(CUtensorMap* map, const void* base, uint64_t S, uint64_t H, uint64_t W, uint64_t C, uint64_t ld,
+                   uint32_t box_h, uint32_t box_w, uint32_t box_c) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return fail(CWM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 2) % 16 != 0 || ld < C)
+    return fail(CWM_ERR_INVALID, "TMA operand must be 16-byte aligned with ld >= C (base %p, ld %llu, C %llu)", base,
+                (unsigned long long)ld, (unsigned long long)C);
+  if (box_c * 2 > 128 || box_w > 256 || box_h > 256)
+    return fail(CWM_ERR_INVALID, "TMA box [%u, %u, %u] too large", box_h, box_w, box_c);
+  cuuint64_t gdim[4] = {C, W, H, S};
+  cuuint64_t gstride[3] = {ld * 2, W * ld * 2, H * W * ld * 2};
+  cuuint32_t box[4] = {box_c, box_w, box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(CWM_ERR_CUDA, "cuTensorMapEncodeTiled (NHWC) failed (%d) S=%llu H=%llu W=%llu C=%llu ld=%llu box=[%u,%u,%u]",
+                (int)r, (unsigned long long)S, (unsigned long long)H, (unsigned long long)W, (unsigned long long)C,
+                (unsigned long long)ld, box_h, box_w, box_c);
+  return CWM_OK;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {

@@ -46,6 +46,11 @@ void reset_launches();
 enum { CWM_TMAP_F16 = 0, CWM_TMAP_F32 = 1 };
 int make_tmap_2d(CUtensorMap* map, const void* base, int dtype, uint64_t rows, uint64_t cols, uint64_t ld,
                  uint32_t box_rows, uint32_t box_cols, int swizzle_bytes = 128);
+// 4-D NHWC f16 tensor [S, H, W, C] whose pixel rows are `ld` elements apart, box [1, box_h, box_w, box_c], 128B swizzle:
+// the implicit-GEMM convolution loads one (tap, channel slab) A tile with it -- coordinates may be negative or run past
+// the image, out-of-range elements are zero-filled by the TMA unit (= the convolution's zero padding).
+int make_tmap_nhwc(CUtensorMap* map, const void* base, uint64_t S, uint64_t H, uint64_t W, uint64_t C, uint64_t ld,
+                   uint32_t box_h, uint32_t box_w, uint32_t box_c);
 int num_sms();
 
 // Optional per-launch CUDA-event timing (cwm_profile_begin/end).  No-op (one branch) when profiling is off.
@@ -133,6 +138,13 @@ __device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorM
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, "
       "{%3, %4}], [%2], %5;" ::"r"(smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 // L2 cache policies (same encodings CUTLASS uses for TMA::CacheHintSm90)

@@ -75,6 +75,21 @@ struct EpiDev {
   const float* ln_s;
   float ln_inv_c;
   float ln_eps;
+  int relu;  // f16-out epilogues: max(v, 0) after the bias (convolution + relu)
+};
+
+// Implicit-GEMM convolution mode (stride 1, "same" zero padding, NHWC f16 rows; cwm_conv2d_f16).  The A operand of
+// k-step kb = (tap, 64-channel slab) is ONE 4-D TMA box [1, hb, wb, 64] of the input image at the tap's spatial offset:
+// nothing is ever im2col-ed, and the zero padding is the TMA unit's out-of-bounds fill.  A 128-row tile is hb image rows of
+// wb pixel slots (wb = 16 or 32 >= image width; slots beyond the width are computed and clipped by the 4-D TMA store).
+struct ConvDev {
+  int taps;           // kh * kw; 0 = plain GEMM
+  int kw;
+  int pad_h, pad_w;
+  int cin_slabs;      // 64-channel slabs per tap (K = taps * cin_slabs * 64, weights zero-padded to that)
+  int tiles_per_img;  // ceil(H / hb)
+  int hb;             // image rows per 128-row tile
+  int rows_per_warp;  // image rows per 32-row epilogue chunk (32 / wb)
 };
 
 // GELU(x) = 0.5 x (1 + erf(x / sqrt 2)), branch-free with one MUFU:
@@ -230,6 +245,20 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMa
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d_2sm(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                                int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+      "%6}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
@@ -238,7 +267,7 @@ template <int BN, bool kRes, bool kCta2>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w,
                 const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_res,
-                const __grid_constant__ CUtensorMap tma_x16, int M, int N, int K, EpiDev ep) {
+                const __grid_constant__ CUtensorMap tma_x16, int M, int N, int K, EpiDev ep, ConvDev cv) {
   using Cfg = GemmCfg<BN, kRes>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_a = smem;
@@ -310,20 +339,41 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     for (int tile = tile_first; tile < num_tiles; tile += tile_stride) {
       const int m_blk = tile / tiles_n;
       const int n_blk = tile - m_blk * tiles_n;
+      // convolution mode: this CTA's 128-row tile = image rows [cy0, cy0 + hb) of sample cs
+      const int ct = m_blk * (kCta2 ? 2 : 1) + cta_rank;
+      const int cs = cv.taps ? ct / cv.tiles_per_img : 0;
+      const int cy0 = cv.taps ? (ct - cs * cv.tiles_per_img) * cv.hb : 0;
+      int tap = 0, slab = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one()) {
           if constexpr (kCta2) {
             // the leader expects the bytes of BOTH CTAs; both CTAs' loads complete on the leader's barrier
             if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (Cfg::kABytes + Cfg::kBBytes / 2));
-            tma_load_2d_2sm(smem_a + stage * Cfg::kABytes, &tma_a, &full_bar[stage], kb * BK, m_blk * TM + cta_rank * BM);
+            if (cv.taps) {
+              const int dy = tap / cv.kw;
+              tma_load_4d_2sm(smem_a + stage * Cfg::kABytes, &tma_a, &full_bar[stage], slab * BK,
+                              tap - dy * cv.kw - cv.pad_w, cy0 + dy - cv.pad_h, cs);
+            } else {
+              tma_load_2d_2sm(smem_a + stage * Cfg::kABytes, &tma_a, &full_bar[stage], kb * BK, m_blk * TM + cta_rank * BM);
+            }
             tma_load_2d_2sm(smem_b + stage * Cfg::kBBytes, &tma_w, &full_bar[stage], kb * BK,
                             n_blk * BN + cta_rank * (BN / 2));
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            tma_load_2d(smem_a + stage * Cfg::kABytes, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
+            if (cv.taps) {
+              const int dy = tap / cv.kw;
+              tma_load_4d(smem_a + stage * Cfg::kABytes, &tma_a, &full_bar[stage], slab * BK, tap - dy * cv.kw - cv.pad_w,
+                          cy0 + dy - cv.pad_h, cs);
+            } else {
+              tma_load_2d(smem_a + stage * Cfg::kABytes, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
+            }
             tma_load_2d(smem_b + stage * Cfg::kBBytes, &tma_w, &full_bar[stage], kb * BK, n_blk * BN);
           }
+        }
+        if (++slab == cv.cin_slabs) {
+          slab = 0;
+          ++tap;
         }
         __syncwarp();
         if (++stage == Cfg::kStages) {
@@ -506,13 +556,23 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
               for (int q = 0; q < 8; ++q)
                 if (n0 + u * 8 + q < ep.scale_cols) v[q] *= ep.scale;
             }
+            if (ep.relu) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
+            }
             sts128(buf0 + row_s + ((u ^ sw) << 4), pack_half2(v[0], v[1]), pack_half2(v[2], v[3]),
                    pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
           }
           fence_proxy_async_smem();
           __syncwarp();
           if (elect_one()) {
-            tma_store_2d(&tma_out, buf0, n0, row0);
+            if (cv.taps) {  // this warp's 32 rows = rows_per_warp image rows of wb pixel slots; slots past the width are clipped
+              const int ct = m_blk * (kCta2 ? 2 : 1) + cta_rank;
+              const int cs = ct / cv.tiles_per_img;
+              tma_store_4d(&tma_out, buf0, n0, 0, (ct - cs * cv.tiles_per_img) * cv.hb + quad * cv.rows_per_warp, cs);
+            } else {
+              tma_store_2d(&tma_out, buf0, n0, row0);
+            }
             bulk_commit();
           }
         }
@@ -741,7 +801,8 @@ static int g_gemm_cta2 = 1;  // CTA-pair kernels: on by default (cwm_debug_gemm_
 
 template <int BN, bool kRes, bool kCta2>
 static int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const CUtensorMap& tr,
-                            const CUtensorMap& tx, int M, int N, int K, const EpiDev& ep, cudaStream_t stream) {
+                            const CUtensorMap& tx, int M, int N, int K, const EpiDev& ep, cudaStream_t stream,
+                            const ConvDev& cv) {
   using Cfg = GemmCfg<BN, kRes>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -765,13 +826,13 @@ static int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tw, const 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CWM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_f16_kernel<BN, kRes, true>, ta, tw, to, tr, tx, M, N, K, ep));
+    CWM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_f16_kernel<BN, kRes, true>, ta, tw, to, tr, tx, M, N, K, ep, cv));
     count_launch();
     return CWM_OK;
   } else {
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    gemm_f16_kernel<BN, kRes, false><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tw, to, tr, tx, M, N, K, ep);
+    gemm_f16_kernel<BN, kRes, false><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tw, to, tr, tx, M, N, K, ep, cv);
     CWM_LAUNCH_CHECK();
     return CWM_OK;
   }
@@ -779,9 +840,10 @@ static int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tw, const 
 
 template <int BN, bool kRes>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const CUtensorMap& tr,
-                       const CUtensorMap& tx, int M, int N, int K, const EpiDev& ep, cudaStream_t stream, bool cta2) {
-  if (cta2) return launch_gemm_impl<BN, kRes, true>(ta, tw, to, tr, tx, M, N, K, ep, stream);
-  return launch_gemm_impl<BN, kRes, false>(ta, tw, to, tr, tx, M, N, K, ep, stream);
+                       const CUtensorMap& tx, int M, int N, int K, const EpiDev& ep, cudaStream_t stream, bool cta2,
+                       const ConvDev& cv = ConvDev{0, 1, 0, 0, 1 << 30, 1, 1, 1}) {
+  if (cta2) return launch_gemm_impl<BN, kRes, true>(ta, tw, to, tr, tx, M, N, K, ep, stream, cv);
+  return launch_gemm_impl<BN, kRes, false>(ta, tw, to, tr, tx, M, N, K, ep, stream, cv);
 }
 
 int pick_bn(int N) {
@@ -817,7 +879,7 @@ extern "C" int cwm_gemm_f16(const uint16_t* A, const uint16_t* W, int M, int N, 
   ep.res = e->res; ep.ldr = e->ldr; ep.res_gather = e->res_gather; ep.gather_stride = e->gather_stride;
   ep.grp_rows = e->grp_rows; ep.grp_out_stride = e->grp_out_stride; ep.out = e->out; ep.ldo = e->ldo;
   ep.x16 = nullptr; ep.ldx16 = 0; ep.ln_stats_out = nullptr;
-  ep.ln_stats_in = nullptr; ep.ln_parts = 0; ep.ln_s = nullptr; ep.ln_inv_c = 0.f; ep.ln_eps = 0.f;
+  ep.ln_stats_in = nullptr; ep.ln_parts = 0; ep.ln_s = nullptr; ep.ln_inv_c = 0.f; ep.ln_eps = 0.f; ep.relu = 0;
   if (e->ln_x16 != nullptr) {
     CWM_REQUIRE(e->mode == CWM_EPI_RES_F32 && e->grp_rows <= 0 && e->ln_stats_out != nullptr && N % 32 == 0 &&
                     reinterpret_cast<uintptr_t>(e->ln_x16) % 16 == 0 && e->ln_ldx16 % 8 == 0 && e->ln_ldx16 >= N,
@@ -890,6 +952,52 @@ extern "C" int cwm_gemm_f16(const uint16_t* A, const uint16_t* W, int M, int N, 
     case 128: return launch_gemm<128, true>(ta, tw, to, tr, tx, M, N, K, ep, s, cta2);
     case 192: return launch_gemm<192, true>(ta, tw, to, tr, tx, M, N, K, ep, s, cta2);
     default: return launch_gemm<256, true>(ta, tw, to, tr, tx, M, N, K, ep, s, cta2);
+  }
+}
+
+// ---- convolution as an implicit GEMM on the same kernel (RAFT's recurrent block) ----
+extern "C" int cwm_conv2d_weight_k(int Cin, int kh, int kw) { return kh * kw * ((Cin + BK - 1) / BK) * BK; }
+
+extern "C" int cwm_conv2d_f16(const uint16_t* x, int ldx, int S, int H, int W, int Cin, const uint16_t* w_packed, int Cout,
+                              int kh, int kw, int pad_h, int pad_w, const float* bias, int relu, uint16_t* out, int ldo,
+                              cwm_stream_t stream) {
+  CWM_REQUIRE(x && w_packed && out, "cwm_conv2d_f16: null pointer");
+  CWM_REQUIRE(S >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && kh > 0 && kw > 0, "cwm_conv2d_f16: bad shape");
+  CWM_REQUIRE(W <= 32, "cwm_conv2d_f16: image width %d > 32 (one 128-row tile holds whole image rows of <= 32 pixels)", W);
+  CWM_REQUIRE(kh == 2 * pad_h + 1 && kw == 2 * pad_w + 1, "cwm_conv2d_f16: only stride-1 'same' convolutions (k = 2 pad + 1)");
+  CWM_REQUIRE(Cin % 8 == 0 && ldx % 8 == 0 && ldx >= Cin && ldo % 8 == 0 && ldo >= Cout && Cout % 8 == 0,
+              "cwm_conv2d_f16: channel counts and row strides must be multiples of 8 (16-byte rows)");
+  if (S == 0) return CWM_OK;
+  const int wb = W <= 16 ? 16 : 32, hb = BM / wb;
+  ConvDev cv;
+  cv.taps = kh * kw; cv.kw = kw; cv.pad_h = pad_h; cv.pad_w = pad_w; cv.cin_slabs = (Cin + BK - 1) / BK;
+  cv.tiles_per_img = (H + hb - 1) / hb; cv.hb = hb; cv.rows_per_warp = 32 / wb;
+  const int K = cv.taps * cv.cin_slabs * BK;
+  const long long Mp = static_cast<long long>(S) * cv.tiles_per_img * BM;
+  CWM_REQUIRE(Mp < (1ll << 31), "cwm_conv2d_f16: too many rows");
+  const int M = static_cast<int>(Mp);
+  EpiDev ep;
+  ep.mode = CWM_EPI_F16; ep.bias = bias; ep.scale = 1.f; ep.scale_cols = 0; ep.res = nullptr; ep.ldr = 0;
+  ep.res_gather = nullptr; ep.gather_stride = 0; ep.grp_rows = 0; ep.grp_out_stride = 0; ep.out = out; ep.ldo = ldo;
+  ep.x16 = nullptr; ep.ldx16 = 0; ep.ln_stats_out = nullptr; ep.ln_stats_in = nullptr; ep.ln_parts = 0; ep.ln_s = nullptr;
+  ep.ln_inv_c = 0.f; ep.ln_eps = 0.f; ep.relu = relu ? 1 : 0;
+  const int bn = pick_bn(Cout);
+  const bool cta2 = g_gemm_cta2 != 0 && bn >= 128 && M >= 2 * BM;
+  CUtensorMap ta, tw, to;
+  int rc = make_tmap_nhwc(&ta, x, S, H, W, Cin, ldx, hb, wb, BK);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tw, w_packed, CWM_TMAP_F16, Cout, K, K, cta2 ? bn / 2 : bn, BK);
+  if (rc) return rc;
+  rc = make_tmap_nhwc(&to, out, S, H, W, Cout, ldo, cv.rows_per_warp, wb, 64);
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  ProfileScope prof(s, "conv2d_f16", 2.0 * S * H * W * static_cast<double>(Cout) * cv.taps * Cin,
+                    static_cast<double>(S) * H * W * (Cin + Cout) * 2.0 + static_cast<double>(Cout) * K * 2.0);
+  switch (bn) {
+    case 64: return launch_gemm<64, false>(ta, tw, to, to, to, M, Cout, K, ep, s, cta2, cv);
+    case 128: return launch_gemm<128, false>(ta, tw, to, to, to, M, Cout, K, ep, s, cta2, cv);
+    case 192: return launch_gemm<192, false>(ta, tw, to, to, to, M, Cout, K, ep, s, cta2, cv);
+    default: return launch_gemm<256, false>(ta, tw, to, to, to, M, Cout, K, ep, s, cta2, cv);
   }
 }
 

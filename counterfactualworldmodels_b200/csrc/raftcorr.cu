@@ -664,6 +664,45 @@ extern "C" int cwm_raft_flow_update(const uint16_t* delta, int ldd, const float*
   return CWM_OK;
 }
 
+// im2col of the 2-channel flow field for BasicMotionEncoder.convf1 (7x7, padding 3; update.py:85): row m of `out` holds
+// the 49 taps x 2 channels of pixel m's neighbourhood in (ky, kx, c) order (zero outside the image), padded to `ldo`
+// columns -- a K = 98 convolution becomes one plain K = 128 GEMM instead of 49 nearly empty 64-channel k-steps.
+namespace cwm {
+__global__ void raft_im2col_flow_kernel(const __half* __restrict__ flow16, int ldf, int H, int W, long long M, int k,
+                                        __half* __restrict__ out, int ldo) {
+  const int units = ldo / 2;   // one thread writes one (tap) pair of channels = 4 bytes
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= M * units) return;
+  const long long m = idx / units;
+  const int tap = static_cast<int>(idx - m * units);
+  __half2 v = __floats2half2_rn(0.f, 0.f);
+  if (tap < k * k) {
+    const int hw = H * W;
+    const int pix = static_cast<int>(m % hw);
+    const int y = pix / W + tap / k - k / 2, x = pix % W + tap % k - k / 2;
+    if (y >= 0 && y < H && x >= 0 && x < W)
+      v = *reinterpret_cast<const __half2*>(flow16 + (m - pix + static_cast<long long>(y) * W + x) * ldf);
+  }
+  *reinterpret_cast<__half2*>(out + m * ldo + 2 * tap) = v;
+}
+}  // namespace cwm
+
+extern "C" int cwm_raft_im2col_flow(const uint16_t* flow16, int ldf, int B, int H, int W, int k, uint16_t* out, int ldo,
+                                    cwm_stream_t stream) {
+  CWM_REQUIRE(B >= 0 && H >= 1 && W >= 1 && k >= 1 && (k & 1) && ldf >= 2 && ldf % 2 == 0 && ldo % 2 == 0 && ldo >= 2 * k * k,
+              "cwm_raft_im2col_flow: bad shape B=%d H=%d W=%d k=%d ldf=%d ldo=%d", B, H, W, k, ldf, ldo);
+  if (B == 0) return CWM_OK;
+  CWM_REQUIRE(flow16 && out, "cwm_raft_im2col_flow: null pointer");
+  const long long M = static_cast<long long>(B) * H * W;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfileScope prof(st, "raft_im2col_flow", 0.0, static_cast<double>(M) * (ldo * 2.0 + 4.0 * k * k));
+  const long long threads = M * (ldo / 2);
+  cwm::raft_im2col_flow_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(
+      reinterpret_cast<const __half*>(flow16), ldf, H, W, M, k, reinterpret_cast<__half*>(out), ldo);
+  CWM_LAUNCH_CHECK();
+  return CWM_OK;
+}
+
 extern "C" int cwm_raft_upsample_flow(const float* flow, const float* mask, int N, int C, int H, int W, float* out,
                                       cwm_stream_t stream) {
   CWM_REQUIRE(N >= 0 && C >= 1 && C <= 16 && H >= 1 && W >= 1, "cwm_raft_upsample_flow: bad shape N=%d C=%d H=%d W=%d", N, C,

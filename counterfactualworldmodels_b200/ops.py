@@ -115,3 +115,42 @@ def fill_pad_rows(x, perm, perm_offset, first_pad_token, value=None):
                                      int(first_pad_token), value.data_ptr() if value is not None else None,
                                      _stream(x)))
     return x
+
+
+def pack_conv_weight(w):
+    """nn.Conv2d weight [Cout, Cin, kh, kw] -> f16 [Cout, kh*kw*cin_pad] (tap-major, channels padded to 64 with zeros):
+    the layout ``cwm_conv2d_f16`` reads (include/cwm_b200.h)."""
+    Cout, Cin, kh, kw = w.shape
+    cin_pad = (Cin + 63) // 64 * 64
+    p = torch.zeros(Cout, kh, kw, cin_pad, dtype=torch.float16, device=w.device)
+    p[..., :Cin] = w.detach().permute(0, 2, 3, 1).to(torch.float16)
+    return p.reshape(Cout, kh * kw * cin_pad).contiguous()
+
+
+def conv2d_f16(x_rows, S, H, W, weight, bias=None, relu=False, ldo=None, out=None, packed=None):
+    """Stride-1 'same' convolution of NHWC f16 rows ``x_rows [S*H*W, Cin]`` (may be a column slice of a wider buffer) with
+    an nn.Conv2d weight ``[Cout, Cin, kh, kw]`` on the tcgen05 implicit-GEMM kernel -> f16 rows ``[S*H*W, Cout]``
+    (``out``: optional destination, may be a column slice)."""
+    _req_cuda(x_rows, weight, bias, out)
+    lib = _lib.load()
+    Cout, Cin, kh, kw = weight.shape
+    assert x_rows.dtype == torch.float16 and x_rows.shape == (S * H * W, Cin) and x_rows.stride(1) == 1, x_rows.shape
+    if packed is None:
+        packed = pack_conv_weight(weight)
+    assert packed.shape[1] == lib.cwm_conv2d_weight_k(Cin, kh, kw)
+    if out is None:
+        out = torch.empty(S * H * W, ldo or Cout, dtype=torch.float16, device=x_rows.device)[:, :Cout]
+    assert out.dtype == torch.float16 and out.shape == (S * H * W, Cout) and out.stride(1) == 1
+    _lib.check(lib.cwm_conv2d_f16(x_rows.data_ptr(), x_rows.stride(0), S, H, W, Cin, packed.data_ptr(), Cout, kh, kw, kh // 2,
+                                  kw // 2, None if bias is None else bias.data_ptr(), int(bool(relu)), out.data_ptr(),
+                                  out.stride(0), _stream(x_rows)))
+    return out
+
+
+def raft_im2col_flow(flow16, S, H, W, k, ldo):
+    """flow16 f16 [S*H*W, >= 2] -> f16 [S*H*W, ldo]: the k x k neighbourhood of the 2 flow channels, (ky, kx, c) order."""
+    _req_cuda(flow16)
+    out = torch.empty(S * H * W, ldo, dtype=torch.float16, device=flow16.device)
+    _lib.check(_lib.load().cwm_raft_im2col_flow(flow16.data_ptr(), flow16.stride(0), S, H, W, k, out.data_ptr(), ldo,
+                                                _stream(flow16)))
+    return out

@@ -364,8 +364,13 @@ class FusedBasicUpdate:
     """
     CORR_LD = 328   # 4 * 81 = 324 correlation channels padded to a multiple of 8 (16-byte rows)
 
-    def __init__(self, ub, device):
+    def __init__(self, ub, device, conv_impl=None):
         assert isinstance(ub, BasicUpdateBlock)
+        # 'tcgen05' (default): every convolution is an implicit GEMM on the repo's tensor-core kernel (cwm_conv2d_f16);
+        # 'cudnn': the library convolutions of round 1, kept as the A/B reference (CWM_RAFT_CONV=cudnn)
+        self.conv_impl = conv_impl or os.environ.get("CWM_RAFT_CONV", "tcgen05")
+        assert self.conv_impl in ("tcgen05", "cudnn"), self.conv_impl
+        self._packed = {}
 
         def cl(w, out_pad=None, in_pad=None):
             w = w.detach().float()
@@ -373,7 +378,14 @@ class FusedBasicUpdate:
                 full = torch.zeros(out_pad or w.shape[0], in_pad or w.shape[1], *w.shape[2:], device=w.device)
                 full[:w.shape[0], :w.shape[1]] = w
                 w = full
-            return w.to(device=device, dtype=torch.float16).contiguous(memory_format=torch.channels_last)
+            out = w.to(device=device, dtype=torch.float16).contiguous(memory_format=torch.channels_last)
+            if self.conv_impl == "tcgen05":
+                Cout, Cin, kh, kw = out.shape
+                cin_pad = (Cin + 63) // 64 * 64
+                pk = torch.zeros(Cout, kh, kw, cin_pad, dtype=torch.float16, device=device)
+                pk[..., :Cin] = out.permute(0, 2, 3, 1)
+                self._packed[id(out)] = (pk.reshape(Cout, -1).contiguous(), Cout, Cin, kh, kw)
+            return out
 
         def f32(*bs, pad=None):
             b = torch.cat([x.detach().float().reshape(-1) for x in bs])
@@ -387,6 +399,11 @@ class FusedBasicUpdate:
         self.w_c1, self.b_c1 = cl(enc.convc1.weight, in_pad=self.CORR_LD), f32(enc.convc1.bias)
         self.w_c2, self.b_c2 = cl(enc.convc2.weight), f32(enc.convc2.bias)
         self.w_f1, self.b_f1 = cl(enc.convf1.weight, in_pad=8), f32(enc.convf1.bias)
+        # the 7x7 convolution of the 2-channel flow as ONE K = 128 GEMM over im2col-ed rows (49 taps x 2 channels = 98)
+        k7 = enc.convf1.kernel_size[0]
+        wk = torch.zeros(enc.convf1.out_channels, 128, device=enc.convf1.weight.device)
+        wk[:, :2 * k7 * k7] = enc.convf1.weight.detach().float().permute(0, 2, 3, 1).reshape(enc.convf1.out_channels, -1)
+        self.w_f1k, self.k_f1 = cl(wk.view(-1, 128, 1, 1)), k7
         self.w_f2, self.b_f2 = cl(enc.convf2.weight), f32(enc.convf2.bias)
         self.w_cv, self.b_cv = cl(enc.conv.weight, out_pad=128), f32(enc.conv.bias, pad=128)
         self.w_zr1, self.b_zr1 = cl(torch.cat([gru.convz1.weight, gru.convr1.weight])), f32(gru.convz1.bias, gru.convr1.bias)
@@ -399,6 +416,7 @@ class FusedBasicUpdate:
         self.w_fh2, self.b_fh2 = cl(fh.conv2.weight, out_pad=8), f32(fh.conv2.bias)
         self.w_m2 = cl(mk[2].weight)
         self.b_m2 = mk[2].bias.detach().to(device=device, dtype=torch.float16)
+        self.w_m2q, self.b_m2q = cl(0.25 * mk[2].weight), f32(0.25 * mk[2].bias)   # .25 * mask(net), update.py:137
 
     class State:
         pass
@@ -411,6 +429,9 @@ class FusedBasicUpdate:
         st.HX, st.RHX, st.CORFLO = buf(3 * C), buf(3 * C), buf(256)
         st.cor1, st.flo1, st.Z, st.Hd, st.fh1, st.mh = buf(256), buf(128), buf(C), buf(C), buf(256), buf(256)
         st.corr16, st.flow16 = buf(self.CORR_LD), buf(8, zero=True)
+        # the implicit-GEMM kernel tiles whole image rows of <= 32 pixels (224 px frames: 28); wider maps use cuDNN
+        st.tc = self.conv_impl == "tcgen05" and W <= 32
+        st.flowcols = buf(128) if st.tc else None
         rows = lambda t: t.expand(N, -1, -1, -1).permute(0, 2, 3, 1).reshape(st.M, -1)  # noqa: E731
         st.HX[:, :C].copy_(rows(net))
         st.HX[:, C:2 * C].copy_(rows(inp))
@@ -419,8 +440,17 @@ class FusedBasicUpdate:
             st.flow16[:, :2].copy_(rows(flow_init))
         return st
 
-    @staticmethod
-    def _conv(st, rows, weight, padding):
+    def _conv(self, st, rows, weight, padding):
+        """f16 rows [M, Cin] (a column slice is fine) -> raw convolution output rows [M, Cout], no bias."""
+        if st.tc:
+            packed, Cout, Cin, kh, kw = self._packed[id(weight)]
+            rows = rows[:, :Cin] if rows.shape[1] > Cin else rows
+            assert rows.shape[1] == Cin and (kh // 2, kw // 2) == tuple(padding if isinstance(padding, tuple) else (padding, padding))
+            out = torch.empty(st.M, Cout, dtype=torch.float16, device=rows.device)
+            _lib.check(_lib.load().cwm_conv2d_f16(rows.data_ptr(), rows.stride(0), st.N, st.H, st.W, Cin, packed.data_ptr(),
+                                                  Cout, kh, kw, kh // 2, kw // 2, None, 0, out.data_ptr(), Cout,
+                                                  _stream(rows)))
+            return out
         x = rows.view(st.N, st.H, st.W, rows.shape[1]).permute(0, 3, 1, 2)
         y = F.conv2d(x, weight, None, 1, padding)
         if not y.is_contiguous(memory_format=torch.channels_last):
@@ -447,7 +477,11 @@ class FusedBasicUpdate:
             bias_act(raw, 256, self.b_c1, 256, st.cor1, 256)
             raw = self._conv(st, st.cor1, self.w_c2, 1)
             bias_act(raw, 192, self.b_c2, 192, st.CORFLO, 256)
-            raw = self._conv(st, st.flow16, self.w_f1, 3)
+            if st.tc:
+                _lib.check(lib.cwm_raft_im2col_flow(p(st.flow16), 8, st.N, st.H, st.W, self.k_f1, p(st.flowcols), 128, s))
+                raw = self._conv(st, st.flowcols, self.w_f1k, 0)
+            else:
+                raw = self._conv(st, st.flow16, self.w_f1, 3)
             bias_act(raw, 128, self.b_f1, 128, st.flo1, 128)
             raw = self._conv(st, st.flo1, self.w_f2, 1)
             bias_act(raw, 64, self.b_f2, 64, st.CORFLO[:, 192:], 256)
@@ -471,6 +505,13 @@ class FusedBasicUpdate:
             _lib.check(lib.cwm_raft_flow_update(p(raw), 8, p(self.b_fh2), p(coords1), st.N, st.H, st.W, p(st.flow16), s))
             if not emit:
                 return None
+            if st.tc:
+                # mask head's 1x1 convolution with its bias in the epilogue; 0.25 is folded into weights and bias (exact)
+                packed, Cout, Cin, _, _ = self._packed[id(self.w_m2q)]
+                out = torch.empty(st.M, Cout, dtype=torch.float16, device=st.mh.device)
+                _lib.check(lib.cwm_conv2d_f16(p(st.mh), 256, st.N, st.H, st.W, Cin, packed.data_ptr(), Cout, 1, 1, 0, 0,
+                                              p(self.b_m2q), 0, p(out), Cout, s))
+                return out.view(st.N, st.H, st.W, Cout).permute(0, 3, 1, 2)
             mh = st.mh.view(st.N, st.H, st.W, 256).permute(0, 3, 1, 2)
             return .25 * F.conv2d(mh, self.w_m2, self.b_m2)
 

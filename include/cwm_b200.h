@@ -430,6 +430,25 @@ int cwm_raft_gru_update_f16(const uint16_t* q, const float* bias, const uint16_t
 int cwm_raft_flow_update(const uint16_t* delta, int ldd, const float* bias, float* coords1, int B, int H, int W,
                          uint16_t* flow16, cwm_stream_t stream);
 
+/* ---- convolutions of RAFT's recurrent block as implicit GEMMs on the tcgen05 kernel -------------------
+ * Replaces the nn.Conv2d calls of cwm/models/raft/update.py:16-60 (SepConvGRU), :79-97 (BasicMotionEncoder), :6-14
+ * (FlowHead) and :121-137 (the mask head) on f16 pixel-major rows.
+ *
+ * out[s, y, x, 0:Cout] = act(bias + sum over (ky, kx, c) of x[s, y + ky - pad_h, x + kx - pad_w, c] * w[n, ky, kx, c]),
+ * stride 1, zero padding, kh = 2 pad_h + 1, kw = 2 pad_w + 1, image width <= 32.  `x` / `out` are NHWC f16 with pixel rows
+ * ldx / ldo elements apart (so a convolution can read / write a column slice of a wider row buffer).  `w_packed` is
+ * [Cout, kh, kw, cin_pad] f16 with cin_pad = Cin rounded up to 64 and zeros in the padding: cwm_conv2d_weight_k() columns.
+ * The A tile of each (tap, 64-channel slab) k-step is one 4-D TMA box at the tap's offset; the padding is the TMA unit's
+ * out-of-bounds zero fill, nothing is im2col-ed.  bias may be NULL; relu != 0 applies max(., 0). */
+int cwm_conv2d_weight_k(int Cin, int kh, int kw);
+int cwm_conv2d_f16(const uint16_t* x, int ldx, int S, int H, int W, int Cin, const uint16_t* w_packed, int Cout, int kh,
+                   int kw, int pad_h, int pad_w, const float* bias, int relu, uint16_t* out, int ldo, cwm_stream_t stream);
+
+/* im2col of the 2-channel flow rows for the k x k convolution of BasicMotionEncoder.convf1 (update.py:85): out[m, 2 tap + c],
+ * taps in (ky, kx) order, zero outside the image and in the columns >= 2 k^2. */
+int cwm_raft_im2col_flow(const uint16_t* flow16, int ldf, int B, int H, int W, int k, uint16_t* out, int ldo,
+                         cwm_stream_t stream);
+
 /* ---- masks on device with a counter-based RNG (csrc/masks.cu) --------------------------------------
  * Opt-in stand-ins for the reference's host-side mask generation (cwm/models/masking.py:347-401 MaskingGenerator.
  * sample_mask_per_frame, :478-545 RotatedTableUniformMaskingGenerator; sampling.py:63-90 EnergySamplingMaskingGenerator;

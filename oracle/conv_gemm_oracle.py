@@ -1,66 +1,72 @@
-"""TEST INFRASTRUCTURE ONLY -- the formulation DESIGN.md section 10 (1) proposes for RAFT's convolutions on the tcgen05
-GEMM, restated in numpy so that the index arithmetic is pinned before any kernel exists:
+"""TEST INFRASTRUCTURE ONLY -- numpy restatement of the implicit-GEMM convolution in csrc/gemm.cu (`cwm_conv2d_f16`,
+SURVEY 8f rank 3: the nn.Conv2d calls of cwm/models/raft/update.py:6-14, :16-60, :79-97, :121-137).
 
-  * activations live as zero-padded pixel-major rows  X[(s, y, x), c],  y in [0, H + 2P), x in [0, Wp), Wp >= W + 2P
-    (the valid pixels sit at y, x in [P, P + H) x [P, P + W); every other row is zero);
-  * a kh x kw convolution (stride 1, 'same' padding, kh//2, kw//2 <= P) is ONE GEMM  out[m, n] = sum_k A[m, k] W[n, k]
-    with K = kh*kw*C, where K-slab (tap t = ky*kw + kx, channels c0..c0+63) of the virtual A is the plain 2-D tile
-    X[m + off_t, c0:c0+64],  off_t = (ky - kh//2) * Wp + (kx - kw//2)  -- a TMA load at a shifted row coordinate (rows
-    before the first / after the last row read as zero, which is TMA's out-of-bounds fill);
-  * the epilogue writes zeros to the border rows, so the output is again a valid zero-padded buffer for the next layer.
-
-``tests/test_conv_as_gemm.py`` checks this against ``torch.nn.functional.conv2d`` for RAFT's kernel shapes (1x1, 3x3, 1x5,
-5x1, 7x7) and for two chained layers.
+Formulation (what the kernel does, step for step):
+  * activations are NHWC rows  X[(s, y, x), c]  with a row pitch `ldx` >= C (a convolution may read a column slice);
+  * one 128-row M tile = `hb` image rows of `wb` pixel slots, wb = 16 or 32 >= W, hb = 128 / wb: tile row r is pixel
+    (y0 + r // wb, r % wb) of sample s;
+  * k-step (tap t = ky*kw + kx, channel slab j) loads the A tile as ONE box [hb, wb, 64] of the image at
+    (y0 + ky - pad_h, kx - pad_w, 64 j): every element outside [0,H) x [0,W) x [0,C) is ZERO (the TMA unit's
+    out-of-bounds fill) -- that is the convolution's zero padding, and nothing is ever im2col-ed;
+  * weights are packed [Cout, kh, kw, cin_pad], cin_pad = ceil(C / 64) * 64, zero in the padding;
+  * the store writes the box [rows, wb, 64] back clipped to [0,H) x [0,W) x [0,Cout).
+`tests/test_conv_as_gemm.py` checks this against torch.nn.functional.conv2d for RAFT's kernel shapes on CPU and the CUDA
+kernel against conv2d of the same f16-rounded operands on the GPU.
 """
 import numpy as np
 
-
-def to_rows(x, P, Wp=None):
-    """x [S, C, H, W] -> zero-padded pixel-major rows [S * (H + 2P) * Wp, C]."""
-    S, C, H, W = x.shape
-    Wp = Wp or (W + 2 * P)
-    buf = np.zeros((S, H + 2 * P, Wp, C), x.dtype)
-    buf[:, P:P + H, P:P + W] = x.transpose(0, 2, 3, 1)
-    return buf.reshape(-1, C), (S, H, W, P, Wp)
-
-
-def from_rows(rows, geom):
-    S, H, W, P, Wp = geom
-    return rows.reshape(S, H + 2 * P, Wp, -1)[:, P:P + H, P:P + W].transpose(0, 3, 1, 2)
+BK = 64
 
 
 def pack_weight(w):
-    """w [N, C, kh, kw] -> [N, kh*kw*C]: K index = (ky*kw + kx) * C + c, matching the slab order of the virtual A."""
+    """w [Cout, C, kh, kw] -> [Cout, kh*kw*cin_pad]: K index = ((ky*kw + kx) * cin_pad + c)."""
     N, C, kh, kw = w.shape
-    return w.transpose(0, 2, 3, 1).reshape(N, kh * kw * C)
+    cin_pad = (C + BK - 1) // BK * BK
+    out = np.zeros((N, kh, kw, cin_pad), w.dtype)
+    out[..., :C] = w.transpose(0, 2, 3, 1)
+    return out.reshape(N, kh * kw * cin_pad)
 
 
-def tap_offsets(kh, kw, Wp):
-    return [(ky - kh // 2) * Wp + (kx - kw // 2) for ky in range(kh) for kx in range(kw)]
+def load_box(x, s, y0, x0, c0, hb, wb):
+    """The 4-D box [hb, wb, 64] of NHWC tensor x at (s, y0, x0, c0) with zero fill outside the tensor."""
+    S, H, W, C = x.shape
+    box = np.zeros((hb, wb, BK), x.dtype)
+    if not (0 <= s < S):
+        return box
+    ys, xs, cs = np.arange(y0, y0 + hb), np.arange(x0, x0 + wb), np.arange(c0, c0 + BK)
+    vy, vx, vc = (ys >= 0) & (ys < H), (xs >= 0) & (xs < W), (cs >= 0) & (cs < C)
+    if vy.any() and vx.any() and vc.any():
+        box[np.ix_(vy, vx, vc)] = x[s][np.ix_(ys[vy], xs[vx], cs[vc])]
+    return box
 
 
-def border_mask(geom):
-    """True for the rows the epilogue must write as zero."""
-    S, H, W, P, Wp = geom
-    m = np.ones((S, H + 2 * P, Wp), bool)
-    m[:, P:P + H, P:P + W] = False
-    return m.reshape(-1)
-
-
-def conv_as_gemm(rows, geom, w, bias=None):
-    """One GEMM over the virtual A (tap-shifted row tiles, zero fill outside the buffer), border rows zeroed."""
-    N, C, kh, kw = w.shape
-    S, H, W, P, Wp = geom
-    assert kh // 2 <= P and kw // 2 <= P and rows.shape[1] == C
-    M = rows.shape[0]
-    wp = pack_weight(w)
-    out = np.zeros((M, N), np.float64)
-    for t, off in enumerate(tap_offsets(kh, kw, Wp)):
-        shifted = np.zeros_like(rows)                     # rows m + off, zero where that leaves the buffer (TMA OOB fill)
-        lo, hi = max(0, -off), min(M, M - off)
-        shifted[lo:hi] = rows[lo + off:hi + off]
-        out += shifted.astype(np.float64) @ wp[:, t * C:(t + 1) * C].astype(np.float64).T
-    if bias is not None:
-        out += bias
-    out[border_mask(geom)] = 0
-    return out.astype(rows.dtype)
+def conv_as_gemm(x, w, bias=None, relu=False):
+    """x [S, H, W, C] (NHWC), w [Cout, C, kh, kw] -> [S, H, W, Cout]: the tile / k-step walk of the kernel in float64."""
+    S, H, W, C = x.shape
+    N, _, kh, kw = w.shape
+    pad_h, pad_w = kh // 2, kw // 2
+    wb = 16 if W <= 16 else 32
+    assert W <= 32
+    hb = 128 // wb
+    slabs = (C + BK - 1) // BK
+    wp = pack_weight(w).astype(np.float64)
+    out = np.zeros((S, H, W, N), np.float64)
+    tiles = (H + hb - 1) // hb
+    for s in range(S):
+        for yt in range(tiles):
+            y0 = yt * hb
+            acc = np.zeros((hb * wb, N), np.float64)
+            kb = 0
+            for tap in range(kh * kw):
+                for j in range(slabs):
+                    a = load_box(x, s, y0 + tap // kw - pad_h, tap % kw - pad_w, j * BK, hb, wb).reshape(hb * wb, BK)
+                    acc += a.astype(np.float64) @ wp[:, kb * BK:(kb + 1) * BK].T
+                    kb += 1
+            if bias is not None:
+                acc += bias
+            if relu:
+                acc = np.maximum(acc, 0)
+            tile = acc.reshape(hb, wb, N)
+            ye = min(H, y0 + hb)
+            out[s, y0:ye, :, :] = tile[:ye - y0, :W]              # the clipped store
+    return out

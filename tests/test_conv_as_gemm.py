@@ -1,5 +1,9 @@
-"""Pins the index arithmetic of DESIGN.md section 10 (1) -- RAFT's convolutions as one tcgen05 GEMM over a zero-padded
-pixel-major buffer with tap-shifted TMA row coordinates -- against torch's conv2d, before the kernel exists."""
+"""RAFT's convolutions as implicit GEMMs (csrc/gemm.cu `cwm_conv2d_f16`).
+
+CPU: the numpy restatement of the kernel's tile / k-step walk (4-D boxes with zero fill, packed weights) against torch's
+conv2d for every kernel shape of the recurrent block.  GPU: the CUDA kernel against conv2d of the same f16-rounded
+operands -- fp32 accumulation of f16 products, so the bar is the f16 rounding of the OUTPUT (2^-11 relative) plus the
+accumulation-order noise of K up to 1920 terms."""
 import numpy as np
 import pytest
 import torch
@@ -7,31 +11,84 @@ import torch.nn.functional as F
 
 import conv_gemm_oracle as cg
 
+DEV = "cuda:0"
+
 
 @pytest.mark.parametrize("kh,kw", [(1, 1), (3, 3), (1, 5), (5, 1), (7, 7)])
-def test_convolution_equals_one_gemm_with_shifted_row_tiles(kh, kw):
-    g = torch.Generator().manual_seed(kh * 10 + kw)
-    S, C, H, W, N, P = 2, 8, 7, 9, 5, 3
+@pytest.mark.parametrize("H,W,C", [(7, 9, 8), (28, 28, 72), (5, 20, 130)])
+def test_convolution_equals_the_box_walk(kh, kw, H, W, C):
+    g = torch.Generator().manual_seed(kh * 10 + kw + H)
+    S, N = 2, 5
     x = torch.randn(S, C, H, W, generator=g, dtype=torch.float64)
     w = torch.randn(N, C, kh, kw, generator=g, dtype=torch.float64)
     b = torch.randn(N, generator=g, dtype=torch.float64)
-    want = F.conv2d(x, w, b, 1, (kh // 2, kw // 2)).numpy()
-    rows, geom = cg.to_rows(x.numpy(), P, Wp=16)            # Wp wider than W + 2P: a power-of-two pitch like 32 for 28
-    out = cg.conv_as_gemm(rows, geom, w.numpy(), b.numpy())
-    np.testing.assert_allclose(cg.from_rows(out, geom), want, rtol=1e-12, atol=1e-12)
-    assert np.abs(out[cg.border_mask(geom)]).max() == 0     # the result is a valid padded buffer again
+    want = F.conv2d(x, w, b, 1, (kh // 2, kw // 2)).permute(0, 2, 3, 1).numpy()
+    got = cg.conv_as_gemm(x.permute(0, 2, 3, 1).numpy(), w.numpy(), b.numpy())
+    np.testing.assert_allclose(got, want, rtol=1e-11, atol=1e-11)
 
 
-def test_two_chained_layers_keep_the_padding_invariant():
-    """SepConvGRU-like chain: 1x5 then 5x1, with a relu between; the zeroed border of layer 1 is layer 2's padding."""
-    g = torch.Generator().manual_seed(3)
-    x = torch.randn(1, 4, 28, 28, generator=g, dtype=torch.float64)
-    w1 = torch.randn(6, 4, 1, 5, generator=g, dtype=torch.float64)
-    w2 = torch.randn(3, 6, 5, 1, generator=g, dtype=torch.float64)
-    want = F.conv2d(F.relu(F.conv2d(x, w1, None, 1, (0, 2))), w2, None, 1, (2, 0)).numpy()
-    rows, geom = cg.to_rows(x.numpy(), 2, Wp=32)            # 28 + 2*2 = 32: the pitch the recurrent block would use
-    assert rows.shape[0] == 32 * 32
-    h = np.maximum(cg.conv_as_gemm(rows, geom, w1.numpy()), 0)
-    out = cg.conv_as_gemm(h, geom, w2.numpy())
-    np.testing.assert_allclose(cg.from_rows(out, geom), want, rtol=1e-12, atol=1e-12)
-    assert cg.tap_offsets(1, 5, 32) == [-2, -1, 0, 1, 2] and cg.tap_offsets(5, 1, 32) == [-64, -32, 0, 32, 64]
+def test_packed_weight_layout_and_relu():
+    w = np.arange(2 * 3 * 1 * 5, dtype=np.float64).reshape(2, 3, 1, 5)
+    p = cg.pack_weight(w)
+    assert p.shape == (2, 5 * 64) and p[1, 2 * 64 + 1] == w[1, 1, 0, 2] and p[0, 3:64].max() == 0
+    x = -np.ones((1, 4, 4, 3))
+    assert cg.conv_as_gemm(x, np.abs(w), relu=True).max() == 0
+
+
+def _conv_gpu(x_rows, S, H, W, w, bias, relu, ldo=None, out=None):
+    from counterfactualworldmodels_b200 import ops
+    return ops.conv2d_f16(x_rows, S, H, W, w, bias=bias, relu=relu, ldo=ldo, out=out)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,Cin,Cout,kh,kw", [
+    ("convc1", 328, 256, 1, 1), ("convc2", 256, 192, 3, 3), ("convf2", 128, 64, 3, 3), ("conv", 256, 128, 3, 3),
+    ("convz1|r1", 384, 256, 1, 5), ("convq2", 384, 128, 5, 1), ("flow_head.conv1|mask.0", 128, 512, 3, 3),
+    ("flow_head.conv2", 256, 8, 3, 3), ("mask.2", 256, 576, 1, 1), ("7x7", 64, 128, 7, 7)])
+@pytest.mark.parametrize("S,H,W", [(3, 28, 28), (2, 16, 16), (1, 9, 30)])
+def test_gpu_conv2d_matches_torch(name, Cin, Cout, kh, kw, S, H, W):
+    g = torch.Generator().manual_seed(Cin + Cout + kh + S)
+    x = (torch.randn(S, H, W, Cin, generator=g) * 0.7).half()
+    w = (torch.randn(Cout, Cin, kh, kw, generator=g) / (Cin * kh * kw) ** 0.5).half()
+    b = torch.randn(Cout, generator=g)
+    want = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, 1, (kh // 2, kw // 2)).permute(0, 2, 3, 1)
+    got = _conv_gpu(x.reshape(-1, Cin).to(DEV), S, H, W, w.to(DEV), b.to(DEV), False).cpu().float().view(S, H, W, Cout)
+    err = (got - want).abs().max().item()
+    assert err <= 2e-3 * max(1.0, want.abs().max().item()), (name, err)
+    got_relu = _conv_gpu(x.reshape(-1, Cin).to(DEV), S, H, W, w.to(DEV), None, True).cpu().float().view(S, H, W, Cout)
+    want_relu = F.relu(want - b)
+    assert (got_relu - want_relu).abs().max().item() <= 2e-3 * max(1.0, want.abs().max().item())
+
+
+@pytest.mark.gpu
+def test_gpu_conv2d_reads_and_writes_column_slices():
+    """The recurrent block's buffers: a convolution reads a slice of a wider row buffer and writes into a slice of the
+    next convolution's input (HX = [h | inp | motion]); the neighbouring columns must stay untouched."""
+    g = torch.Generator().manual_seed(5)
+    S, H, W = 2, 28, 28
+    buf = (torch.randn(S * H * W, 384, generator=g) * 0.5).half().to(DEV)
+    w = (torch.randn(64, 128, 3, 3, generator=g) / 34).half().to(DEV)
+    dst = torch.full((S * H * W, 256), 7.0, dtype=torch.float16, device=DEV)
+    _conv_gpu(buf[:, 128:256], S, H, W, w, None, False, out=dst[:, 192:])
+    want = F.conv2d(buf[:, 128:256].float().view(S, H, W, 128).permute(0, 3, 1, 2), w.float(), None, 1, 1).permute(0, 2, 3, 1)
+    assert (dst[:, 192:].float().view(S, H, W, 64) - want).abs().max().item() <= 2e-3 * want.abs().max().item()
+    assert bool((dst[:, :192] == 7.0).all())
+
+
+@pytest.mark.gpu
+def test_gpu_im2col_flow_and_7x7_as_one_gemm():
+    from counterfactualworldmodels_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    S, H, W = 2, 28, 28
+    flow = torch.zeros(S * H * W, 8, dtype=torch.float16)
+    flow[:, :2] = (torch.randn(S * H * W, 2, generator=g) * 3).half()
+    w = (torch.randn(128, 2, 7, 7, generator=g) / 10).half()
+    cols = ops.raft_im2col_flow(flow.to(DEV), S, H, W, 7, 128)
+    want_cols = F.unfold(flow[:, :2].float().view(S, H, W, 2).permute(0, 3, 1, 2), 7, padding=3)   # [S, 2*49, HW], (c, tap)
+    want_cols = want_cols.view(S, 2, 49, H * W).permute(0, 3, 2, 1).reshape(S * H * W, 98)
+    assert torch.equal(cols[:, :98].cpu().float(), want_cols) and float(cols[:, 98:].abs().max()) == 0
+    wk = torch.zeros(128, 128, dtype=torch.float16)
+    wk[:, :98] = w.permute(0, 2, 3, 1).reshape(128, 98)
+    got = _conv_gpu(cols, S, H, W, wk.view(128, 128, 1, 1).to(DEV), None, False).cpu().float().view(S, H, W, 128)
+    want = F.conv2d(flow[:, :2].float().view(S, H, W, 2).permute(0, 3, 1, 2), w.float(), None, 1, 3).permute(0, 2, 3, 1)
+    assert (got - want).abs().max().item() <= 2e-3 * want.abs().max().item()

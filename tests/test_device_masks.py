@@ -121,7 +121,7 @@ def test_gpu_energy_sampling_equals_the_oracle():
     g.num_visible = 1
     flat = g.sample(torch.ones(1, 1, 8, 12, device=DEV), 512)
     vis = (~flat[0]).view(2, 8, 12, 512)
-    assert not vis[0].any() and (vis[1].sum((0, 1)) == 4).all()
+    assert vis[0].all() and (vis[1].sum((0, 1)) == 4).all()     # frame 0 visible, one 2x2 clump in frame 1
     per_cell = vis[1].view(4, 2, 6, 2, 512).all(1).all(2).sum(-1).flatten()
     assert per_cell.sum() == 512 and per_cell.max() <= 45 and per_cell.min() >= 5
 

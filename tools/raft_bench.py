@@ -57,12 +57,20 @@ def e2e(S):
         return
     xs = x.clone()
     xs[:, 0] = xs[:1, 0]                                   # a sweep: frame 0 shared by all samples
-    variants = (("fp32", False, False, False, None), ("tf32_convs", True, False, False, None),
-                ("f16_autocast_convs", True, True, False, None),
-                ("f16_shared_frame0", True, True, False, 0), ("fp32_shared_frame0", False, False, False, 0),
-                ("f16_half_update_shared_frame0", True, True, True, 0),
-                ("f16_fused_update_shared_frame0", True, True, "fused", 0), ("f16_fused_update", True, True, "fused", None))
-    for name, tf32, amp, half_update, shared in variants:
+    variants = [("fp32", False, False, False, None, None), ("tf32_convs", True, False, False, None, None),
+                ("f16_autocast_convs", True, True, False, None, None),
+                ("f16_shared_frame0", True, True, False, 0, None), ("fp32_shared_frame0", False, False, False, 0, None),
+                ("f16_half_update_shared_frame0", True, True, True, 0, None),
+                ("f16_fused_update_shared_frame0_cudnn_convs", True, True, "fused", 0, "cudnn"),
+                ("f16_fused_update_shared_frame0", True, True, "fused", 0, "tcgen05"),
+                ("f16_fused_update_cudnn_convs", True, True, "fused", None, "cudnn"),
+                ("f16_fused_update", True, True, "fused", None, "tcgen05")]
+    if os.environ.get("RAFT_BENCH_ONLY"):     # e.g. RAFT_BENCH_ONLY=fused: only the variants whose name contains it
+        variants = [v for v in variants if os.environ["RAFT_BENCH_ONLY"] in v[0]]
+    for name, tf32, amp, half_update, shared, conv in variants:
+        if conv is not None:   # which convolutions the fused recurrent block uses: the repo's implicit GEMMs or cuDNN
+            os.environ["CWM_RAFT_CONV"] = conv
+            object.__setattr__(model, '_fused_ub', None)
         torch.backends.cudnn.allow_tf32 = tf32
         model.args.mixed_precision = amp
         model.args.half_update = bool(half_update)
