@@ -90,7 +90,18 @@ struct ConvDev {
   int tiles_per_img;  // ceil(H / hb)
   int hb;             // image rows per 128-row tile
   int rows_per_warp;  // image rows per 32-row epilogue chunk (32 / wb)
+  // halo mode (W + 2 pad_w <= wb): per channel slab ONE box of hb + kh - 1 image rows is staged, each row laid out as
+  // [2 pad_w zero slots | W pixels | zero slots]; tap (ky, kx) then reads the SAME smem through an A descriptor whose start
+  // is shifted by ky * wb + kx + pad_w rows (a read past a row's end lands on the next row's leading zeros), so the
+  // shared-memory fill per tile drops from taps x 16 KB to one halo per slab.
+  int halo;           // 0 = one A box per (tap, slab) k-step
+  int halo_rows;      // hb + kh - 1 (+ 1, see cwm_conv2d_f16)
+  int wb;
+  int w_stages;       // depth of the weight-tile ring in halo mode
+  int w_stride;       // bytes between its stages (a CTA of a pair holds half a tile)
+  int base_off;       // 1: set the descriptor's base-offset field for the row-shifted starts
 };
+constexpr int kHaloStageBytes = 33 * 1024;  // 256 rows x 128 B + slack for the shifted reads of discarded output rows
 
 // GELU(x) = 0.5 x (1 + erf(x / sqrt 2)), branch-free with one MUFU:
 //   erfc(z) = 2^(z * Q(z)) for z = min(|x| / sqrt 2, 4), Q = degree-4 minimax fit (max |erf error| 6.8e-7, max
@@ -275,12 +286,18 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   uint8_t* smem_epi = smem + Cfg::kStages * Cfg::kStageBytes;
   uint8_t* smem_bias = smem_epi + Cfg::kEpiBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_bias + Cfg::kBiasBytes);
-  uint64_t* full_bar = bars;                        // kStages
-  uint64_t* empty_bar = bars + Cfg::kStages;        // kStages
-  uint64_t* tfull_bar = bars + 2 * Cfg::kStages;    // 2
+  constexpr int kBarSlots = 8;                      // >= kStages; the convolution halo mode uses up to 8 weight stages
+  static_assert(Cfg::kStages <= kBarSlots, "barrier slots");
+  uint64_t* full_bar = bars;                        // kBarSlots
+  uint64_t* empty_bar = bars + kBarSlots;           // kBarSlots
+  uint64_t* tfull_bar = bars + 2 * kBarSlots;       // 2
   uint64_t* tempty_bar = tfull_bar + 2;             // 2
   uint64_t* res_bar = tempty_bar + 2;               // kEpiWarps * 2 (residual chunk landed)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2 * kEpiWarps);
+  uint64_t* halo_full = res_bar + 2 * kEpiWarps + 1;   // 2 (convolution halo mode)
+  uint64_t* halo_empty = halo_full + 2;                // 2
+  uint8_t* smem_halo = smem;                           // halo mode: 2 halo stages, then the weight-tile ring
+  uint8_t* smem_wring = smem + 2 * kHaloStageBytes;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
@@ -303,7 +320,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     if (kRes) tma_prefetch_desc(&tma_res);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < Cfg::kStages; ++s) {
+    for (int s = 0; s < kBarSlots; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
@@ -312,6 +329,10 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       mbar_init(&tempty_bar[a], kCta2 ? 2 * kEpiWarps : kEpiWarps);
     }
     for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&halo_full[i], 1);
+      mbar_init(&halo_empty[i], 1);
+    }
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -332,7 +353,53 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   // only the TMA / tcgen05 instructions themselves are issued by one elected lane.  Running the whole role under
   // `if (lane == 0)` makes every operand thread-private and the compiler wraps each TMA / MMA instruction in a
   // per-lane "waterfall" loop (R2UR + BRA.U.ANY), ~100 cycles of issue per instruction.
-  if (warp == 0) {
+  if (warp == 0 && cv.halo) {
+    // ===================== TMA producer, convolution halo mode =====================
+    int stage = 0, hcount = 0;
+    uint32_t phase = 0;
+    const uint32_t halo_bytes = static_cast<uint32_t>(cv.halo_rows * cv.wb) * 128u;
+    for (int tile = tile_first; tile < num_tiles; tile += tile_stride) {
+      const int m_blk = tile / tiles_n;
+      const int n_blk = tile - m_blk * tiles_n;
+      const int ct = m_blk * (kCta2 ? 2 : 1) + cta_rank;
+      const int cs = ct / cv.tiles_per_img;
+      const int cy0 = (ct - cs * cv.tiles_per_img) * cv.hb;
+      for (int slab = 0; slab < cv.cin_slabs; ++slab, ++hcount) {
+        const int hs = hcount & 1;
+        mbar_wait(&halo_empty[hs], ((hcount >> 1) & 1) ^ 1);
+        if (elect_one()) {
+          if constexpr (kCta2) {
+            if (cta_rank == 0) mbar_arrive_expect_tx(&halo_full[hs], 2 * halo_bytes);
+            tma_load_4d_2sm(smem_halo + hs * kHaloStageBytes, &tma_a, &halo_full[hs], slab * BK, -2 * cv.pad_w,
+                            cy0 - cv.pad_h, cs);
+          } else {
+            mbar_arrive_expect_tx(&halo_full[hs], halo_bytes);
+            tma_load_4d(smem_halo + hs * kHaloStageBytes, &tma_a, &halo_full[hs], slab * BK, -2 * cv.pad_w, cy0 - cv.pad_h, cs);
+          }
+        }
+        __syncwarp();
+        for (int tap = 0; tap < cv.taps; ++tap) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (elect_one()) {
+            const int kcol = (tap * cv.cin_slabs + slab) * BK;
+            if constexpr (kCta2) {
+              if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], Cfg::kBBytes);
+              tma_load_2d_2sm(smem_wring + stage * cv.w_stride, &tma_w, &full_bar[stage], kcol,
+                              n_blk * BN + cta_rank * (BN / 2));
+            } else {
+              mbar_arrive_expect_tx(&full_bar[stage], Cfg::kBBytes);
+              tma_load_2d(smem_wring + stage * cv.w_stride, &tma_w, &full_bar[stage], kcol, n_blk * BN);
+            }
+          }
+          __syncwarp();
+          if (++stage == cv.w_stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 0) {
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
@@ -380,6 +447,67 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
           stage = 0;
           phase ^= 1;
         }
+      }
+    }
+  } else if (warp == 1 && cta_rank == 0 && cv.halo) {
+    // ===================== MMA issuer, convolution halo mode =====================
+    constexpr uint32_t idesc = umma_idesc_f16(TM, BN, 0, 0);
+    const uint64_t bdesc0 = umma_desc_kmajor_sw128(smem_u32(smem_wring));
+    const uint32_t halo_addr0 = smem_u32(smem_halo);
+    int stage = 0, hcount = 0, as = 0;
+    uint32_t phase = 0, aphase = 0;
+    for (int tile = tile_first; tile < num_tiles; tile += tile_stride) {
+      mbar_wait(&tempty_bar[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + as * BN;
+      uint32_t accumulate = 0;
+      for (int slab = 0; slab < cv.cin_slabs; ++slab, ++hcount) {
+        const int hs = hcount & 1;
+        mbar_wait(&halo_full[hs], (hcount >> 1) & 1);
+        tc_fence_after();
+        int ky = 0, kx = 0;
+        for (int tap = 0; tap < cv.taps; ++tap) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          // the A operand of this tap: the halo, read from (ky * wb + kx + pad_w) rows further down.  The start is a
+          // multiple of 128 B but not of the 1024-byte swizzle atom; the tensor core applies the 128B-swizzle XOR to the
+          // absolute shared-memory address (like the TMA write did), so the descriptor's base-offset field stays 0
+          // (tests/test_conv_as_gemm.py fails with the field set: CWM_CONV_BASEOFF=1).
+          const uint32_t a_addr = halo_addr0 + hs * kHaloStageBytes + static_cast<uint32_t>(ky * cv.wb + kx + cv.pad_w) * 128u;
+          const uint64_t adesc = umma_desc_kmajor_sw128(a_addr) |
+                                 (cv.base_off ? (static_cast<uint64_t>((a_addr >> 7) & 7u) << 49) : 0ull);
+          const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(stage * (cv.w_stride >> 4));
+          const bool last = (slab == cv.cin_slabs - 1) && (tap == cv.taps - 1);
+          if (elect_one()) {
+            if constexpr (kCta2) {
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) umma_ss2(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (accumulate | k) != 0 ? 1u : 0u);
+              umma_commit2(&empty_bar[stage]);
+              if (tap == cv.taps - 1) umma_commit2(&halo_empty[hs]);
+              if (last) umma_commit2(&tfull_bar[as]);
+            } else {
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) umma_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (accumulate | k) != 0 ? 1u : 0u);
+              umma_commit(&empty_bar[stage]);
+              if (tap == cv.taps - 1) umma_commit(&halo_empty[hs]);
+              if (last) umma_commit(&tfull_bar[as]);
+            }
+          }
+          __syncwarp();
+          accumulate = 1;
+          if (++kx == cv.kw) {
+            kx = 0;
+            ++ky;
+          }
+          if (++stage == cv.w_stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
       }
     }
   } else if (warp == 1 && cta_rank == 0) {
@@ -802,13 +930,20 @@ static int g_gemm_cta2 = 1;  // CTA-pair kernels: on by default (cwm_debug_gemm_
 template <int BN, bool kRes, bool kCta2>
 static int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const CUtensorMap& tr,
                             const CUtensorMap& tx, int M, int N, int K, const EpiDev& ep, cudaStream_t stream,
-                            const ConvDev& cv) {
+                            const ConvDev& cv_in) {
   using Cfg = GemmCfg<BN, kRes>;
   static bool attr_set = false;
   if (!attr_set) {
     CWM_CUDA_CHECK(cudaFuncSetAttribute(gemm_f16_kernel<BN, kRes, kCta2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::kSmemBytes));
     attr_set = true;
+  }
+  ConvDev cv = cv_in;
+  if (cv.halo) {  // carve the operand ring into 2 halo stages + as many weight stages as fit
+    cv.w_stride = kCta2 ? Cfg::kBBytes / 2 : Cfg::kBBytes;
+    const int ws = (Cfg::kStages * Cfg::kStageBytes - 2 * kHaloStageBytes) / cv.w_stride;
+    cv.w_stages = ws > 8 ? 8 : ws;
+    if (cv.w_stages < 2) return fail(CWM_ERR_INVALID, "convolution halo mode: no room for the weight ring (BN=%d)", BN);
   }
   if constexpr (kCta2) {
     const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
@@ -841,7 +976,7 @@ static int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tw, const 
 template <int BN, bool kRes>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const CUtensorMap& tr,
                        const CUtensorMap& tx, int M, int N, int K, const EpiDev& ep, cudaStream_t stream, bool cta2,
-                       const ConvDev& cv = ConvDev{0, 1, 0, 0, 1 << 30, 1, 1, 1}) {
+                       const ConvDev& cv = ConvDev{0, 1, 0, 0, 1 << 30, 1, 1, 1, 0, 0, 32, 1, 0, 0}) {
   if (cta2) return launch_gemm_impl<BN, kRes, true>(ta, tw, to, tr, tx, M, N, K, ep, stream, cv);
   return launch_gemm_impl<BN, kRes, false>(ta, tw, to, tr, tx, M, N, K, ep, stream, cv);
 }
@@ -972,6 +1107,24 @@ extern "C" int cwm_conv2d_f16(const uint16_t* x, int ldx, int S, int H, int W, i
   ConvDev cv;
   cv.taps = kh * kw; cv.kw = kw; cv.pad_h = pad_h; cv.pad_w = pad_w; cv.cin_slabs = (Cin + BK - 1) / BK;
   cv.tiles_per_img = (H + hb - 1) / hb; cv.hb = hb; cv.rows_per_warp = 32 / wb;
+  const int bn = pick_bn(Cout);
+  // halo mode: every image row with its zero padding fits one row of wb pixel slots, and there is more than one tap
+  static int halo_env = -1;
+  if (halo_env < 0) {
+    const char* v = getenv("CWM_CONV_HALO");
+    halo_env = (v == nullptr) ? 1 : atoi(v);
+  }
+  cv.wb = wb;
+  // one more row when the right-most taps of the right-most pixels read past their row's end (slot W - 1 + kw - 1 + pad_w
+  // >= wb): they land on the NEXT row's leading zero slots, which must exist for the last row of the box too
+  cv.halo_rows = hb + kh - 1 + ((W + 3 * pad_w > wb) ? 1 : 0);
+  cv.halo = (halo_env != 0 && cv.taps > 1 && W + 2 * pad_w <= wb && cv.halo_rows * wb * 128 <= kHaloStageBytes) ? 1 : 0;
+  cv.w_stages = 2;
+  cv.w_stride = 0;
+  {
+    const char* v = getenv("CWM_CONV_BASEOFF");
+    cv.base_off = (v == nullptr) ? 0 : atoi(v);  // measured: the swizzle XOR follows the ABSOLUTE smem address, so 0
+  }
   const int K = cv.taps * cv.cin_slabs * BK;
   const long long Mp = static_cast<long long>(S) * cv.tiles_per_img * BM;
   CWM_REQUIRE(Mp < (1ll << 31), "cwm_conv2d_f16: too many rows");
@@ -981,10 +1134,9 @@ extern "C" int cwm_conv2d_f16(const uint16_t* x, int ldx, int S, int H, int W, i
   ep.res_gather = nullptr; ep.gather_stride = 0; ep.grp_rows = 0; ep.grp_out_stride = 0; ep.out = out; ep.ldo = ldo;
   ep.x16 = nullptr; ep.ldx16 = 0; ep.ln_stats_out = nullptr; ep.ln_stats_in = nullptr; ep.ln_parts = 0; ep.ln_s = nullptr;
   ep.ln_inv_c = 0.f; ep.ln_eps = 0.f; ep.relu = relu ? 1 : 0;
-  const int bn = pick_bn(Cout);
   const bool cta2 = g_gemm_cta2 != 0 && bn >= 128 && M >= 2 * BM;
   CUtensorMap ta, tw, to;
-  int rc = make_tmap_nhwc(&ta, x, S, H, W, Cin, ldx, hb, wb, BK);
+  int rc = make_tmap_nhwc(&ta, x, S, H, W, Cin, ldx, cv.halo ? cv.halo_rows : hb, wb, BK);
   if (rc) return rc;
   rc = make_tmap_2d(&tw, w_packed, CWM_TMAP_F16, Cout, K, K, cta2 ? bn / 2 : bn, BK);
   if (rc) return rc;

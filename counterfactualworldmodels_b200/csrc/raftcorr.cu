@@ -670,33 +670,39 @@ extern "C" int cwm_raft_flow_update(const uint16_t* delta, int ldd, const float*
 namespace cwm {
 __global__ void raft_im2col_flow_kernel(const __half* __restrict__ flow16, int ldf, int H, int W, long long M, int k,
                                         __half* __restrict__ out, int ldo) {
-  const int units = ldo / 2;   // one thread writes one (tap) pair of channels = 4 bytes
+  const int units = ldo / 8;   // one thread writes four taps x two channels = one 16-byte store
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= M * units) return;
   const long long m = idx / units;
-  const int tap = static_cast<int>(idx - m * units);
-  __half2 v = __floats2half2_rn(0.f, 0.f);
-  if (tap < k * k) {
-    const int hw = H * W;
-    const int pix = static_cast<int>(m % hw);
-    const int y = pix / W + tap / k - k / 2, x = pix % W + tap % k - k / 2;
-    if (y >= 0 && y < H && x >= 0 && x < W)
-      v = *reinterpret_cast<const __half2*>(flow16 + (m - pix + static_cast<long long>(y) * W + x) * ldf);
+  const int tap0 = static_cast<int>(idx - m * units) * 4;
+  const int hw = H * W;
+  const int pix = static_cast<int>(m % hw);
+  const int py = pix / W - k / 2, px = pix % W - k / 2;
+  const __half* img = flow16 + (m - pix) * ldf;
+  uint32_t v[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int tap = tap0 + t;
+    v[t] = 0u;
+    if (tap < k * k) {
+      const int y = py + tap / k, x = px + tap % k;
+      if (y >= 0 && y < H && x >= 0 && x < W) v[t] = *reinterpret_cast<const uint32_t*>(img + (static_cast<long long>(y) * W + x) * ldf);
+    }
   }
-  *reinterpret_cast<__half2*>(out + m * ldo + 2 * tap) = v;
+  *reinterpret_cast<uint4*>(out + m * ldo + 2 * tap0) = make_uint4(v[0], v[1], v[2], v[3]);
 }
 }  // namespace cwm
 
 extern "C" int cwm_raft_im2col_flow(const uint16_t* flow16, int ldf, int B, int H, int W, int k, uint16_t* out, int ldo,
                                     cwm_stream_t stream) {
-  CWM_REQUIRE(B >= 0 && H >= 1 && W >= 1 && k >= 1 && (k & 1) && ldf >= 2 && ldf % 2 == 0 && ldo % 2 == 0 && ldo >= 2 * k * k,
+  CWM_REQUIRE(B >= 0 && H >= 1 && W >= 1 && k >= 1 && (k & 1) && ldf >= 2 && ldf % 2 == 0 && ldo % 8 == 0 && ldo >= 2 * k * k,
               "cwm_raft_im2col_flow: bad shape B=%d H=%d W=%d k=%d ldf=%d ldo=%d", B, H, W, k, ldf, ldo);
   if (B == 0) return CWM_OK;
-  CWM_REQUIRE(flow16 && out, "cwm_raft_im2col_flow: null pointer");
+  CWM_REQUIRE(flow16 && out && aligned16(out), "cwm_raft_im2col_flow: null or misaligned pointer");
   const long long M = static_cast<long long>(B) * H * W;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ProfileScope prof(st, "raft_im2col_flow", 0.0, static_cast<double>(M) * (ldo * 2.0 + 4.0 * k * k));
-  const long long threads = M * (ldo / 2);
+  const long long threads = M * (ldo / 8);
   cwm::raft_im2col_flow_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(
       reinterpret_cast<const __half*>(flow16), ldf, H, W, M, k, reinterpret_cast<__half*>(out), ldo);
   CWM_LAUNCH_CHECK();

@@ -413,6 +413,7 @@ class FusedBasicUpdate:
         self.w_fh1, self.b_fh1 = cl(fh.conv1.weight), f32(fh.conv1.bias)
         self.w_fh1m = cl(torch.cat([fh.conv1.weight, mk[0].weight]))
         self.b_m0 = f32(mk[0].bias)
+        self.b_fh1m = f32(fh.conv1.bias, mk[0].bias)
         self.w_fh2, self.b_fh2 = cl(fh.conv2.weight, out_pad=8), f32(fh.conv2.bias)
         self.w_m2 = cl(mk[2].weight)
         self.b_m2 = mk[2].bias.detach().to(device=device, dtype=torch.float16)
@@ -432,6 +433,7 @@ class FusedBasicUpdate:
         # the implicit-GEMM kernel tiles whole image rows of <= 32 pixels (224 px frames: 28); wider maps use cuDNN
         st.tc = self.conv_impl == "tcgen05" and W <= 32
         st.flowcols = buf(128) if st.tc else None
+        st.fhm = buf(512) if st.tc else None
         rows = lambda t: t.expand(N, -1, -1, -1).permute(0, 2, 3, 1).reshape(st.M, -1)  # noqa: E731
         st.HX[:, :C].copy_(rows(net))
         st.HX[:, C:2 * C].copy_(rows(inp))
@@ -440,16 +442,21 @@ class FusedBasicUpdate:
             st.flow16[:, :2].copy_(rows(flow_init))
         return st
 
-    def _conv(self, st, rows, weight, padding):
-        """f16 rows [M, Cin] (a column slice is fine) -> raw convolution output rows [M, Cout], no bias."""
+    def _conv(self, st, rows, weight, padding, bias=None, relu=False, out=None):
+        """f16 rows [M, Cin] (a column slice is fine) -> convolution output rows [M, Cout].  On the implicit-GEMM kernel
+        ``bias`` / ``relu`` run in the epilogue and ``out`` may be a column slice of the next convolution's input; the
+        cuDNN route returns the raw output (its callers apply bias / activation with the elementwise kernels)."""
         if st.tc:
             packed, Cout, Cin, kh, kw = self._packed[id(weight)]
             rows = rows[:, :Cin] if rows.shape[1] > Cin else rows
             assert rows.shape[1] == Cin and (kh // 2, kw // 2) == tuple(padding if isinstance(padding, tuple) else (padding, padding))
-            out = torch.empty(st.M, Cout, dtype=torch.float16, device=rows.device)
+            if out is None:
+                out = torch.empty(st.M, Cout, dtype=torch.float16, device=rows.device)
+            assert out.shape == (st.M, Cout) and out.stride(1) == 1
             _lib.check(_lib.load().cwm_conv2d_f16(rows.data_ptr(), rows.stride(0), st.N, st.H, st.W, Cin, packed.data_ptr(),
-                                                  Cout, kh, kw, kh // 2, kw // 2, None, 0, out.data_ptr(), Cout,
-                                                  _stream(rows)))
+                                                  Cout, kh, kw, kh // 2, kw // 2,
+                                                  None if bias is None else bias.data_ptr(), int(bool(relu)),
+                                                  out.data_ptr(), out.stride(0), _stream(rows)))
             return out
         x = rows.view(st.N, st.H, st.W, rows.shape[1]).permute(0, 3, 1, 2)
         y = F.conv2d(x, weight, None, 1, padding)
@@ -473,18 +480,22 @@ class FusedBasicUpdate:
             _lib.check(lib.cwm_raft_corr_lookup_f16(_ptr_table(corr_fn.corr_pyramid), corr_fn.num_levels, corr_fn.radius,
                                                     p(coords1), st.N, st.H, st.W, p(st.corr16), self.CORR_LD, s))
             # BasicMotionEncoder (update.py:90-98)
-            raw = self._conv(st, st.corr16, self.w_c1, 0)
-            bias_act(raw, 256, self.b_c1, 256, st.cor1, 256)
-            raw = self._conv(st, st.cor1, self.w_c2, 1)
-            bias_act(raw, 192, self.b_c2, 192, st.CORFLO, 256)
             if st.tc:
+                # bias + relu in the convolution epilogues, every result written straight into its consumer's input slot
+                self._conv(st, st.corr16, self.w_c1, 0, self.b_c1, True, st.cor1)
+                self._conv(st, st.cor1, self.w_c2, 1, self.b_c2, True, st.CORFLO[:, :192])
                 _lib.check(lib.cwm_raft_im2col_flow(p(st.flow16), 8, st.N, st.H, st.W, self.k_f1, p(st.flowcols), 128, s))
-                raw = self._conv(st, st.flowcols, self.w_f1k, 0)
+                self._conv(st, st.flowcols, self.w_f1k, 0, self.b_f1, True, st.flo1)
+                self._conv(st, st.flo1, self.w_f2, 1, self.b_f2, True, st.CORFLO[:, 192:])
             else:
+                raw = self._conv(st, st.corr16, self.w_c1, 0)
+                bias_act(raw, 256, self.b_c1, 256, st.cor1, 256)
+                raw = self._conv(st, st.cor1, self.w_c2, 1)
+                bias_act(raw, 192, self.b_c2, 192, st.CORFLO, 256)
                 raw = self._conv(st, st.flow16, self.w_f1, 3)
-            bias_act(raw, 128, self.b_f1, 128, st.flo1, 128)
-            raw = self._conv(st, st.flo1, self.w_f2, 1)
-            bias_act(raw, 64, self.b_f2, 64, st.CORFLO[:, 192:], 256)
+                bias_act(raw, 128, self.b_f1, 128, st.flo1, 128)
+                raw = self._conv(st, st.flo1, self.w_f2, 1)
+                bias_act(raw, 64, self.b_f2, 64, st.CORFLO[:, 192:], 256)
             raw = self._conv(st, st.CORFLO, self.w_cv, 1)
             bias_act(raw, 128, self.b_cv, 128, st.HX[:, 2 * C:], 3 * C, st.RHX[:, 2 * C:], 3 * C, tail=st.flow16)
             # SepConvGRU (update.py:43-60): horizontal then vertical
@@ -496,22 +507,28 @@ class FusedBasicUpdate:
                 _lib.check(lib.cwm_raft_gru_update_f16(p(raw), p(b_q), p(st.Z), p(st.HX), 3 * C, C, M,
                                                        p(dense) if dense is not None else None, s))
             # FlowHead (update.py:13-14) and, where a prediction is emitted, the mask head (:131-137)
-            raw = self._conv(st, st.Hd, self.w_fh1m if emit else self.w_fh1, 1)
-            ldx = raw.shape[1]
-            bias_act(raw, ldx, self.b_fh1, 256, st.fh1, 256)
-            if emit:
-                bias_act(raw, ldx, self.b_m0, 256, st.mh, 256, x_ptr=p(raw[:, 256:]))
-            raw = self._conv(st, st.fh1, self.w_fh2, 1)
+            if st.tc:
+                if emit:   # flow head conv1 | mask head conv0 stacked: one convolution, both biases + relu in the epilogue
+                    self._conv(st, st.Hd, self.w_fh1m, 1, self.b_fh1m, True, st.fhm)
+                    fh1, mh = st.fhm[:, :256], st.fhm[:, 256:]
+                else:
+                    fh1, mh = self._conv(st, st.Hd, self.w_fh1, 1, self.b_fh1, True, st.fh1), None
+                raw = self._conv(st, fh1, self.w_fh2, 1)
+            else:
+                raw = self._conv(st, st.Hd, self.w_fh1m if emit else self.w_fh1, 1)
+                ldx = raw.shape[1]
+                bias_act(raw, ldx, self.b_fh1, 256, st.fh1, 256)
+                if emit:
+                    bias_act(raw, ldx, self.b_m0, 256, st.mh, 256, x_ptr=p(raw[:, 256:]))
+                mh = st.mh
+                raw = self._conv(st, st.fh1, self.w_fh2, 1)
             _lib.check(lib.cwm_raft_flow_update(p(raw), 8, p(self.b_fh2), p(coords1), st.N, st.H, st.W, p(st.flow16), s))
             if not emit:
                 return None
             if st.tc:
                 # mask head's 1x1 convolution with its bias in the epilogue; 0.25 is folded into weights and bias (exact)
-                packed, Cout, Cin, _, _ = self._packed[id(self.w_m2q)]
-                out = torch.empty(st.M, Cout, dtype=torch.float16, device=st.mh.device)
-                _lib.check(lib.cwm_conv2d_f16(p(st.mh), 256, st.N, st.H, st.W, Cin, packed.data_ptr(), Cout, 1, 1, 0, 0,
-                                              p(self.b_m2q), 0, p(out), Cout, s))
-                return out.view(st.N, st.H, st.W, Cout).permute(0, 3, 1, 2)
+                out = self._conv(st, mh, self.w_m2q, 0, self.b_m2q, False)
+                return out.view(st.N, st.H, st.W, out.shape[1]).permute(0, 3, 1, 2)
             mh = st.mh.view(st.N, st.H, st.W, 256).permute(0, 3, 1, 2)
             return .25 * F.conv2d(mh, self.w_m2, self.b_m2)
 

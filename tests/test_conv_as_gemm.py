@@ -45,7 +45,7 @@ def _conv_gpu(x_rows, S, H, W, w, bias, relu, ldo=None, out=None):
     ("convc1", 328, 256, 1, 1), ("convc2", 256, 192, 3, 3), ("convf2", 128, 64, 3, 3), ("conv", 256, 128, 3, 3),
     ("convz1|r1", 384, 256, 1, 5), ("convq2", 384, 128, 5, 1), ("flow_head.conv1|mask.0", 128, 512, 3, 3),
     ("flow_head.conv2", 256, 8, 3, 3), ("mask.2", 256, 576, 1, 1), ("7x7", 64, 128, 7, 7)])
-@pytest.mark.parametrize("S,H,W", [(3, 28, 28), (2, 16, 16), (1, 9, 30)])
+@pytest.mark.parametrize("S,H,W", [(3, 28, 28), (2, 16, 16), (1, 9, 30), (5, 20, 12), (67, 28, 28)])
 def test_gpu_conv2d_matches_torch(name, Cin, Cout, kh, kw, S, H, W):
     g = torch.Generator().manual_seed(Cin + Cout + kh + S)
     x = (torch.randn(S, H, W, Cin, generator=g) * 0.7).half()
