@@ -27,7 +27,8 @@ EXPORTED_SYMBOLS = (
     "cwm_gemm_ln_parts", "cwm_rowstats_f16", "cwm_raft_corr_pyramid", "cwm_raft_corr_lookup", "cwm_raft_upsample_flow",
     "cwm_raft_corr_lookup_f16", "cwm_raft_bias_act_f16", "cwm_raft_gru_gate_f16", "cwm_raft_gru_update_f16",
     "cwm_raft_flow_update", "cwm_total_launches",
-    "cwm_conv2d_weight_k", "cwm_conv2d_f16", "cwm_raft_im2col_flow",
+    "cwm_conv2d_weight_k", "cwm_conv2d_f16", "cwm_raft_im2col_flow", "cwm_conv2d_gru_gate_f16",
+    "cwm_conv2d_gru_update_f16",
     "cwm_philox4x32_10", "cwm_mask_uniform", "cwm_mask_energy_table", "cwm_mask_energy_sample",
     "cwm_mask_rectangularize_workspace_bytes", "cwm_mask_rectangularize",
     # tuning hooks (header section "tuning hooks")
@@ -177,6 +178,10 @@ def _declare(lib):
     lib.cwm_conv2d_weight_k.argtypes = [c_int] * 3
     lib.cwm_conv2d_f16.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                    c_void_p, c_int, c_void_p, c_int, c_void_p]
+    lib.cwm_conv2d_gru_gate_f16.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
+                                            c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]
+    lib.cwm_conv2d_gru_update_f16.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
+                                              c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]
     lib.cwm_raft_im2col_flow.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]
     c_u64, c_u32p = ctypes.c_uint64, POINTER(ctypes.c_uint32)
     lib.cwm_philox4x32_10.argtypes = [c_u32p, c_u32p, c_u32p]

@@ -76,7 +76,29 @@ struct EpiDev {
   float ln_inv_c;
   float ln_eps;
   int relu;  // f16-out epilogues: max(v, 0) after the bias (convolution + relu)
+  // convolution post-ops of RAFT's ConvGRU (cwm/models/raft/update.py:43-60), evaluated on the fp32 accumulators:
+  //   1 = gate:   columns [0, C): z = sigmoid(v) -> out;  columns [C, 2C): sigmoid(v) * h -> out2 (column n - C)
+  //   2 = update: h + z * (tanh(v) - h) -> out (h's own slot, in place) and, when out2 is given, a dense copy
+  // h / z are f16 pixel rows (aux_h, aux_z); out2 is the kernel's second output tensor map.
+  int post;
+  int post_c;
+  const __half* aux_h;
+  int ld_h;
+  const __half* aux_z;
+  int ld_z;
+  int has_out2;
+  int img_h, img_w, img_s;
 };
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ void h8_unpack(const uint4& u, float* f) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
 
 // Implicit-GEMM convolution mode (stride 1, "same" zero padding, NHWC f16 rows; cwm_conv2d_f16).  The A operand of
 // k-step kb = (tap, 64-channel slab) is ONE 4-D TMA box [1, hb, wb, 64] of the input image at the tap's spatial offset:
@@ -610,6 +632,16 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
           const int next_tile = tile + tile_stride;
           if (next_tile < num_tiles) load_ln_stats((next_tile / tiles_n) * TM + cta_rank * BM + quad * 32 + lane);
         }
+        // convolution post-ops: the pixel row this thread's tile row stands for (-1: a padding slot / beyond the image)
+        long long post_row = -1;
+        if (ep.post) {
+          const int ct = m_blk * (kCta2 ? 2 : 1) + cta_rank;
+          const int cs = ct / cv.tiles_per_img;
+          const int tr = quad * 32 + lane;
+          const int py = (ct - cs * cv.tiles_per_img) * cv.hb + tr / cv.wb, px = tr % cv.wb;
+          if (cs < ep.img_s && py < ep.img_h && px < ep.img_w)
+            post_row = (static_cast<long long>(cs) * ep.img_h + py) * ep.img_w + px;
+        }
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
         for (int c = half; c < kChunks; c += 2) {
@@ -688,6 +720,29 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
 #pragma unroll
               for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
             }
+            if (ep.post == 1) {          // GRU gate
+              const bool is_r = n0 >= ep.post_c;
+              float hh[8];
+              if (is_r && post_row >= 0) {
+                h8_unpack(__ldg(reinterpret_cast<const uint4*>(ep.aux_h + post_row * ep.ld_h + (n0 - ep.post_c) + u * 8)), hh);
+              } else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) hh[q] = is_r ? 0.f : 1.f;
+              }
+#pragma unroll
+              for (int q = 0; q < 8; ++q) v[q] = sigmoid_fast(v[q]) * hh[q];
+            } else if (ep.post == 2) {   // GRU update
+              float hh[8], zz[8];
+              if (post_row >= 0) {
+                h8_unpack(__ldg(reinterpret_cast<const uint4*>(ep.aux_h + post_row * ep.ld_h + n0 + u * 8)), hh);
+                h8_unpack(__ldg(reinterpret_cast<const uint4*>(ep.aux_z + post_row * ep.ld_z + n0 + u * 8)), zz);
+              } else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) hh[q] = zz[q] = 0.f;
+              }
+#pragma unroll
+              for (int q = 0; q < 8; ++q) v[q] = (1.f - zz[q]) * hh[q] + zz[q] * tanhf(v[q]);
+            }
             sts128(buf0 + row_s + ((u ^ sw) << 4), pack_half2(v[0], v[1]), pack_half2(v[2], v[3]),
                    pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
           }
@@ -697,7 +752,13 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
             if (cv.taps) {  // this warp's 32 rows = rows_per_warp image rows of wb pixel slots; slots past the width are clipped
               const int ct = m_blk * (kCta2 ? 2 : 1) + cta_rank;
               const int cs = ct / cv.tiles_per_img;
-              tma_store_4d(&tma_out, buf0, n0, 0, (ct - cs * cv.tiles_per_img) * cv.hb + quad * cv.rows_per_warp, cs);
+              const int sy = (ct - cs * cv.tiles_per_img) * cv.hb + quad * cv.rows_per_warp;
+              if (ep.post == 1 && n0 >= ep.post_c) {
+                tma_store_4d(&tma_res, buf0, n0 - ep.post_c, 0, sy, cs);      // r * h -> the q convolution's input slot
+              } else {
+                tma_store_4d(&tma_out, buf0, n0, 0, sy, cs);
+                if (ep.post == 2 && ep.has_out2) tma_store_4d(&tma_res, buf0, n0, 0, sy, cs);   // dense copy of h
+              }
             } else {
               tma_store_2d(&tma_out, buf0, n0, row0);
             }
@@ -1015,6 +1076,8 @@ extern "C" int cwm_gemm_f16(const uint16_t* A, const uint16_t* W, int M, int N, 
   ep.grp_rows = e->grp_rows; ep.grp_out_stride = e->grp_out_stride; ep.out = e->out; ep.ldo = e->ldo;
   ep.x16 = nullptr; ep.ldx16 = 0; ep.ln_stats_out = nullptr;
   ep.ln_stats_in = nullptr; ep.ln_parts = 0; ep.ln_s = nullptr; ep.ln_inv_c = 0.f; ep.ln_eps = 0.f; ep.relu = 0;
+  ep.post = 0; ep.post_c = 0; ep.aux_h = nullptr; ep.ld_h = 0; ep.aux_z = nullptr; ep.ld_z = 0; ep.has_out2 = 0;
+  ep.img_h = ep.img_w = ep.img_s = 0;
   if (e->ln_x16 != nullptr) {
     CWM_REQUIRE(e->mode == CWM_EPI_RES_F32 && e->grp_rows <= 0 && e->ln_stats_out != nullptr && N % 32 == 0 &&
                     reinterpret_cast<uintptr_t>(e->ln_x16) % 16 == 0 && e->ln_ldx16 % 8 == 0 && e->ln_ldx16 >= N,
@@ -1093,14 +1156,26 @@ extern "C" int cwm_gemm_f16(const uint16_t* A, const uint16_t* W, int M, int N, 
 // ---- convolution as an implicit GEMM on the same kernel (RAFT's recurrent block) ----
 extern "C" int cwm_conv2d_weight_k(int Cin, int kh, int kw) { return kh * kw * ((Cin + BK - 1) / BK) * BK; }
 
-extern "C" int cwm_conv2d_f16(const uint16_t* x, int ldx, int S, int H, int W, int Cin, const uint16_t* w_packed, int Cout,
-                              int kh, int kw, int pad_h, int pad_w, const float* bias, int relu, uint16_t* out, int ldo,
-                              cwm_stream_t stream) {
+struct ConvPost {
+  int post = 0;            // 0 none, 1 GRU gate, 2 GRU update
+  int C = 0;
+  const uint16_t* h = nullptr;
+  int ldh = 0;
+  const uint16_t* z = nullptr;
+  int ldz = 0;
+  uint16_t* out2 = nullptr;
+  int ldo2 = 0;
+  int out2_cols = 0;
+};
+
+static int conv2d_impl(const uint16_t* x, int ldx, int S, int H, int W, int Cin, const uint16_t* w_packed, int Cout, int kh,
+                       int kw, int pad_h, int pad_w, const float* bias, int relu, uint16_t* out, int ldo, int out_cols,
+                       const ConvPost& post, cwm_stream_t stream) {
   CWM_REQUIRE(x && w_packed && out, "cwm_conv2d_f16: null pointer");
   CWM_REQUIRE(S >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && kh > 0 && kw > 0, "cwm_conv2d_f16: bad shape");
   CWM_REQUIRE(W <= 32, "cwm_conv2d_f16: image width %d > 32 (one 128-row tile holds whole image rows of <= 32 pixels)", W);
   CWM_REQUIRE(kh == 2 * pad_h + 1 && kw == 2 * pad_w + 1, "cwm_conv2d_f16: only stride-1 'same' convolutions (k = 2 pad + 1)");
-  CWM_REQUIRE(Cin % 8 == 0 && ldx % 8 == 0 && ldx >= Cin && ldo % 8 == 0 && ldo >= Cout && Cout % 8 == 0,
+  CWM_REQUIRE(Cin % 8 == 0 && ldx % 8 == 0 && ldx >= Cin && ldo % 8 == 0 && ldo >= out_cols && Cout % 8 == 0,
               "cwm_conv2d_f16: channel counts and row strides must be multiples of 8 (16-byte rows)");
   if (S == 0) return CWM_OK;
   const int wb = W <= 16 ? 16 : 32, hb = BM / wb;
@@ -1134,23 +1209,58 @@ extern "C" int cwm_conv2d_f16(const uint16_t* x, int ldx, int S, int H, int W, i
   ep.res_gather = nullptr; ep.gather_stride = 0; ep.grp_rows = 0; ep.grp_out_stride = 0; ep.out = out; ep.ldo = ldo;
   ep.x16 = nullptr; ep.ldx16 = 0; ep.ln_stats_out = nullptr; ep.ln_stats_in = nullptr; ep.ln_parts = 0; ep.ln_s = nullptr;
   ep.ln_inv_c = 0.f; ep.ln_eps = 0.f; ep.relu = relu ? 1 : 0;
+  ep.post = post.post; ep.post_c = post.C; ep.aux_h = reinterpret_cast<const __half*>(post.h); ep.ld_h = post.ldh;
+  ep.aux_z = reinterpret_cast<const __half*>(post.z); ep.ld_z = post.ldz; ep.has_out2 = post.out2 != nullptr;
+  ep.img_h = H; ep.img_w = W; ep.img_s = S;
   const bool cta2 = g_gemm_cta2 != 0 && bn >= 128 && M >= 2 * BM;
   CUtensorMap ta, tw, to;
   int rc = make_tmap_nhwc(&ta, x, S, H, W, Cin, ldx, cv.halo ? cv.halo_rows : hb, wb, BK);
   if (rc) return rc;
   rc = make_tmap_2d(&tw, w_packed, CWM_TMAP_F16, Cout, K, K, cta2 ? bn / 2 : bn, BK);
   if (rc) return rc;
-  rc = make_tmap_nhwc(&to, out, S, H, W, Cout, ldo, cv.rows_per_warp, wb, 64);
+  rc = make_tmap_nhwc(&to, out, S, H, W, out_cols, ldo, cv.rows_per_warp, wb, 64);
   if (rc) return rc;
+  CUtensorMap to2 = to;
+  if (post.out2 != nullptr) {
+    rc = make_tmap_nhwc(&to2, post.out2, S, H, W, post.out2_cols, post.ldo2, cv.rows_per_warp, wb, 64);
+    if (rc) return rc;
+  }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  ProfileScope prof(s, "conv2d_f16", 2.0 * S * H * W * static_cast<double>(Cout) * cv.taps * Cin,
+  ProfileScope prof(s, post.post == 1 ? "conv2d_gru_gate" : (post.post == 2 ? "conv2d_gru_update" : "conv2d_f16"),
+                    2.0 * S * H * W * static_cast<double>(Cout) * cv.taps * Cin,
                     static_cast<double>(S) * H * W * (Cin + Cout) * 2.0 + static_cast<double>(Cout) * K * 2.0);
   switch (bn) {
-    case 64: return launch_gemm<64, false>(ta, tw, to, to, to, M, Cout, K, ep, s, cta2, cv);
-    case 128: return launch_gemm<128, false>(ta, tw, to, to, to, M, Cout, K, ep, s, cta2, cv);
-    case 192: return launch_gemm<192, false>(ta, tw, to, to, to, M, Cout, K, ep, s, cta2, cv);
-    default: return launch_gemm<256, false>(ta, tw, to, to, to, M, Cout, K, ep, s, cta2, cv);
+    case 64: return launch_gemm<64, false>(ta, tw, to, to2, to, M, Cout, K, ep, s, cta2, cv);
+    case 128: return launch_gemm<128, false>(ta, tw, to, to2, to, M, Cout, K, ep, s, cta2, cv);
+    case 192: return launch_gemm<192, false>(ta, tw, to, to2, to, M, Cout, K, ep, s, cta2, cv);
+    default: return launch_gemm<256, false>(ta, tw, to, to2, to, M, Cout, K, ep, s, cta2, cv);
   }
+}
+
+extern "C" int cwm_conv2d_f16(const uint16_t* x, int ldx, int S, int H, int W, int Cin, const uint16_t* w_packed, int Cout,
+                              int kh, int kw, int pad_h, int pad_w, const float* bias, int relu, uint16_t* out, int ldo,
+                              cwm_stream_t stream) {
+  return conv2d_impl(x, ldx, S, H, W, Cin, w_packed, Cout, kh, kw, pad_h, pad_w, bias, relu, out, ldo, Cout, ConvPost(), stream);
+}
+
+extern "C" int cwm_conv2d_gru_gate_f16(const uint16_t* x, int ldx, int S, int H, int W, int Cin, const uint16_t* w_zr, int C,
+                                       int kh, int kw, int pad_h, int pad_w, const float* bias_zr, const uint16_t* h, int ldh,
+                                       uint16_t* z_out, int ldz, uint16_t* rh_out, int ldrh, cwm_stream_t stream) {
+  CWM_REQUIRE(h && z_out && rh_out && C % 64 == 0 && ldh % 8 == 0 && ldh >= C && ldz % 8 == 0 && ldrh % 8 == 0,
+              "cwm_conv2d_gru_gate_f16: null pointer, or C not a multiple of 64 / rows not 16-byte aligned");
+  ConvPost p;
+  p.post = 1; p.C = C; p.h = h; p.ldh = ldh; p.out2 = rh_out; p.ldo2 = ldrh; p.out2_cols = C;
+  return conv2d_impl(x, ldx, S, H, W, Cin, w_zr, 2 * C, kh, kw, pad_h, pad_w, bias_zr, 0, z_out, ldz, C, p, stream);
+}
+
+extern "C" int cwm_conv2d_gru_update_f16(const uint16_t* x, int ldx, int S, int H, int W, int Cin, const uint16_t* w_q, int C,
+                                         int kh, int kw, int pad_h, int pad_w, const float* bias_q, const uint16_t* z, int ldz,
+                                         uint16_t* h, int ldh, uint16_t* h_dense, cwm_stream_t stream) {
+  CWM_REQUIRE(h && z && C % 64 == 0 && ldh % 8 == 0 && ldh >= C && ldz % 8 == 0 && ldz >= C,
+              "cwm_conv2d_gru_update_f16: null pointer, or C not a multiple of 64 / rows not 16-byte aligned");
+  ConvPost p;
+  p.post = 2; p.C = C; p.h = h; p.ldh = ldh; p.z = z; p.ldz = ldz; p.out2 = h_dense; p.ldo2 = C; p.out2_cols = C;
+  return conv2d_impl(x, ldx, S, H, W, Cin, w_q, C, kh, kw, pad_h, pad_w, bias_q, 0, h, ldh, C, p, stream);
 }
 
 extern "C" int cwm_debug_gemm_cta2(int enable) {

@@ -370,6 +370,7 @@ class FusedBasicUpdate:
         # 'cudnn': the library convolutions of round 1, kept as the A/B reference (CWM_RAFT_CONV=cudnn)
         self.conv_impl = conv_impl or os.environ.get("CWM_RAFT_CONV", "tcgen05")
         assert self.conv_impl in ("tcgen05", "cudnn"), self.conv_impl
+        self.fuse_gru = os.environ.get("CWM_RAFT_FUSE_GRU", "1") != "0" and ub.gru.convz1.out_channels % 64 == 0
         self._packed = {}
 
         def cl(w, out_pad=None, in_pad=None):
@@ -501,6 +502,17 @@ class FusedBasicUpdate:
             # SepConvGRU (update.py:43-60): horizontal then vertical
             for w_zr, b_zr, w_q, b_q, pad, dense in ((self.w_zr1, self.b_zr1, self.w_q1, self.b_q1, (0, 2), None),
                                                      (self.w_zr2, self.b_zr2, self.w_q2, self.b_q2, (2, 0), st.Hd)):
+                if st.tc and self.fuse_gru:
+                    # gate / update arithmetic in the epilogues of the two convolutions: no raw tensors, no extra launches
+                    pk_zr, pk_q = self._packed[id(w_zr)][0], self._packed[id(w_q)][0]
+                    kh, kw = 2 * pad[0] + 1, 2 * pad[1] + 1
+                    _lib.check(lib.cwm_conv2d_gru_gate_f16(p(st.HX), 3 * C, st.N, st.H, st.W, 3 * C, p(pk_zr), C, kh, kw,
+                                                           pad[0], pad[1], p(b_zr), p(st.HX), 3 * C, p(st.Z), C,
+                                                           p(st.RHX), 3 * C, s))
+                    _lib.check(lib.cwm_conv2d_gru_update_f16(p(st.RHX), 3 * C, st.N, st.H, st.W, 3 * C, p(pk_q), C, kh, kw,
+                                                             pad[0], pad[1], p(b_q), p(st.Z), C, p(st.HX), 3 * C,
+                                                             p(dense) if dense is not None else None, s))
+                    continue
                 raw = self._conv(st, st.HX, w_zr, pad)
                 _lib.check(lib.cwm_raft_gru_gate_f16(p(raw), p(b_zr), p(st.HX), 3 * C, C, M, p(st.Z), p(st.RHX), 3 * C, s))
                 raw = self._conv(st, st.RHX, w_q, pad)

@@ -444,6 +444,18 @@ int cwm_conv2d_weight_k(int Cin, int kh, int kw);
 int cwm_conv2d_f16(const uint16_t* x, int ldx, int S, int H, int W, int Cin, const uint16_t* w_packed, int Cout, int kh,
                    int kw, int pad_h, int pad_w, const float* bias, int relu, uint16_t* out, int ldo, cwm_stream_t stream);
 
+/* The two convolutions of one ConvGRU half-step with the gate arithmetic in their epilogues (update.py:43-60):
+ *   gate:    [z | r] = sigmoid(conv(x, w_zr) + bias_zr), 2C output channels; z -> z_out [., C], r * h -> rh_out [., C]
+ *            (the first C columns of the q convolution's input rows);
+ *   update:  h <- (1 - z) * h + z * tanh(conv(x, w_q) + bias_q), in place in h's slot and, when h_dense != NULL, also to a
+ *            dense [., C] copy.  h / z / outputs are f16 pixel rows with the given row strides; C % 64 == 0. */
+int cwm_conv2d_gru_gate_f16(const uint16_t* x, int ldx, int S, int H, int W, int Cin, const uint16_t* w_zr, int C, int kh,
+                            int kw, int pad_h, int pad_w, const float* bias_zr, const uint16_t* h, int ldh, uint16_t* z_out,
+                            int ldz, uint16_t* rh_out, int ldrh, cwm_stream_t stream);
+int cwm_conv2d_gru_update_f16(const uint16_t* x, int ldx, int S, int H, int W, int Cin, const uint16_t* w_q, int C, int kh,
+                              int kw, int pad_h, int pad_w, const float* bias_q, const uint16_t* z, int ldz, uint16_t* h,
+                              int ldh, uint16_t* h_dense, cwm_stream_t stream);
+
 /* im2col of the 2-channel flow rows for the k x k convolution of BasicMotionEncoder.convf1 (update.py:85): out[m, 2 tap + c],
  * taps in (ky, kx) order, zero outside the image and in the columns >= 2 k^2. */
 int cwm_raft_im2col_flow(const uint16_t* flow16, int ldf, int B, int H, int W, int k, uint16_t* out, int ldo,

@@ -92,3 +92,45 @@ def test_gpu_im2col_flow_and_7x7_as_one_gemm():
     got = _conv_gpu(cols, S, H, W, wk.view(128, 128, 1, 1).to(DEV), None, False).cpu().float().view(S, H, W, 128)
     want = F.conv2d(flow[:, :2].float().view(S, H, W, 2).permute(0, 3, 1, 2), w.float(), None, 1, 3).permute(0, 2, 3, 1)
     assert (got - want).abs().max().item() <= 2e-3 * want.abs().max().item()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kh,kw", [(1, 5), (5, 1), (3, 3)])
+@pytest.mark.parametrize("S,H,W", [(3, 28, 28), (2, 16, 16)])
+def test_gpu_gru_gate_and_update_in_the_conv_epilogues(kh, kw, S, H, W):
+    """One ConvGRU half-step (update.py:43-60) as two convolutions with the gate arithmetic in their epilogues, against
+    the same step in torch fp32 on the f16-rounded operands."""
+    from counterfactualworldmodels_b200 import _lib, ops
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(kh * 7 + kw + S)
+    C, M = 128, S * H * W
+    HX = (torch.randn(M, 3 * C, generator=g) * 0.6).half()
+    w_zr = (torch.randn(2 * C, 3 * C, kh, kw, generator=g) / (3 * C * kh * kw) ** 0.5 * 2).half()
+    w_q = (torch.randn(C, 3 * C, kh, kw, generator=g) / (3 * C * kh * kw) ** 0.5 * 2).half()
+    b_zr, b_q = torch.randn(2 * C, generator=g) * 0.3, torch.randn(C, generator=g) * 0.3
+    pad = (kh // 2, kw // 2)
+    nchw = lambda rows: rows.float().view(S, H, W, -1).permute(0, 3, 1, 2)          # noqa: E731
+    rows = lambda t: t.permute(0, 2, 3, 1).reshape(M, -1)                            # noqa: E731
+    h = HX[:, :C].float()
+    zr = torch.sigmoid(rows(F.conv2d(nchw(HX), w_zr.float(), b_zr, 1, pad)))
+    z, r = zr[:, :C], zr[:, C:]
+    RHX = torch.cat([(r * h).half(), HX[:, C:]], 1)
+    q = torch.tanh(rows(F.conv2d(nchw(RHX), w_q.float(), b_q, 1, pad)))
+    h_new = (1 - z.half().float()) * h + z.half().float() * q
+
+    d = lambda t: t.to(DEV).contiguous()                                             # noqa: E731
+    HXd, RHXd = d(HX), d(torch.cat([torch.zeros(M, C).half(), HX[:, C:]], 1))
+    Zd = torch.empty(M, C, dtype=torch.float16, device=DEV)
+    Hd = torch.empty(M, C, dtype=torch.float16, device=DEV)
+    pzr, pq, bzr, bq = ops.pack_conv_weight(d(w_zr)), ops.pack_conv_weight(d(w_q)), d(b_zr), d(b_q)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.cwm_conv2d_gru_gate_f16(HXd.data_ptr(), 3 * C, S, H, W, 3 * C, pzr.data_ptr(), C, kh, kw, pad[0], pad[1],
+                                           bzr.data_ptr(), HXd.data_ptr(), 3 * C, Zd.data_ptr(), C, RHXd.data_ptr(), 3 * C, st))
+    assert (Zd.cpu().float() - z).abs().max().item() <= 2e-3
+    assert (RHXd[:, :C].cpu().float() - r * h).abs().max().item() <= 4e-3
+    assert torch.equal(RHXd[:, C:].cpu(), HX[:, C:])                                 # the other slots are untouched
+    _lib.check(lib.cwm_conv2d_gru_update_f16(RHXd.data_ptr(), 3 * C, S, H, W, 3 * C, pq.data_ptr(), C, kh, kw, pad[0], pad[1],
+                                             bq.data_ptr(), Zd.data_ptr(), C, HXd.data_ptr(), 3 * C, Hd.data_ptr(), st))
+    got = HXd[:, :C].cpu().float()
+    assert (got - h_new).abs().max().item() <= 8e-3, (got - h_new).abs().max().item()
+    assert torch.equal(Hd.cpu(), HXd[:, :C].cpu()) and torch.equal(HXd[:, C:].cpu(), HX[:, C:])
