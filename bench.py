@@ -366,7 +366,7 @@ def measure_flow_sweep(dev, cfg_name, S, peaks, with_cpu):
     return out
 
 
-def run_reference_arm(args):
+def run_reference_arm(args, out):
     """`--impl reference`: the reference's own CPU implementation of the path on the box's host cores, same workload,
     metric and unit; every step is a bounded sample (--ref-sample frames) of the workload.  Rank 0 alone runs."""
     rank = int(os.environ.get("RANK", "0"))
@@ -393,10 +393,36 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    out.emit(line)
+
+
+class OneLineStdout:
+    """stdout carries exactly ONE JSON line: everything else any library prints on fd 1 (NCCL's version banner, the
+    reference's own progress prints) is diverted to stderr for the duration of the run."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, obj):
+        sys.stdout.flush()
+        os.write(self.real, (json.dumps(obj) + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.real, 1)
+        os.close(self.real)
+        return False
 
 
 def main():
+    with OneLineStdout() as out:
+        _main(out)
+
+
+def _main(out):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -416,7 +442,7 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
 
     if args.impl == "reference":
-        run_reference_arm(args)
+        run_reference_arm(args, out)
         return
 
     import torch.distributed as dist
@@ -816,7 +842,7 @@ def main():
             "clocks": r["clocks"], "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels,
             "also": also,
         }
-        print(json.dumps(line), flush=True)
+        out.emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -114,12 +114,10 @@ def sharded_counterfactual_videos(generator, x, active_patches, passive_patches=
         S = num_samples
     G.shifter.set_shapes(x, mask=active_patches[..., 0])
     G.shifter.set_num_shifts(S if shifts is None else (len(shifts) if not hasattr(shifts, 'shape') else shifts.shape[-1]))
+    drawn = shifts is None
     shifts = G.shifter._preprocess_shifts_sequence(shifts, is_mask_shift=True)
-    if multi and rank == 0:
-        obj = [[list(map(int, s)) for s in shifts]]
-    else:
-        obj = [None]
-    if multi:  # randomly drawn shifts (shifts=None) must be the same sweep on every rank
+    if multi and drawn:  # randomly drawn shifts must be the same sweep on every rank (caller-given ones already are)
+        obj = [[list(map(int, s)) for s in shifts]] if rank == 0 else [None]
         dist.broadcast_object_list(obj, src=0)
         shifts = obj[0]
     S = len(shifts)
