@@ -296,7 +296,10 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
 
-template <int BN, bool kRes, bool kCta2>
+// kConv: the convolution instantiation (4-D TMA operands, halo mode, relu / ConvGRU post-ops).  It is a template flag and not
+// a run-time mode because the f16-out epilogue of the plain GEMMs is issue-bound: the extra branches per 16-byte unit cost
+// the qkv / fc1 GEMMs 15 % when they were run-time (measured: 1173 -> 996 TFLOP/s inside a large-4x4 step).
+template <int BN, bool kRes, bool kCta2, bool kConv>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w,
                 const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_res,
@@ -375,7 +378,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   // only the TMA / tcgen05 instructions themselves are issued by one elected lane.  Running the whole role under
   // `if (lane == 0)` makes every operand thread-private and the compiler wraps each TMA / MMA instruction in a
   // per-lane "waterfall" loop (R2UR + BRA.U.ANY), ~100 cycles of issue per instruction.
-  if (warp == 0 && cv.halo) {
+  if (kConv && warp == 0 && cv.halo) {
     // ===================== TMA producer, convolution halo mode =====================
     int stage = 0, hcount = 0;
     uint32_t phase = 0;
@@ -430,8 +433,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       const int n_blk = tile - m_blk * tiles_n;
       // convolution mode: this CTA's 128-row tile = image rows [cy0, cy0 + hb) of sample cs
       const int ct = m_blk * (kCta2 ? 2 : 1) + cta_rank;
-      const int cs = cv.taps ? ct / cv.tiles_per_img : 0;
-      const int cy0 = cv.taps ? (ct - cs * cv.tiles_per_img) * cv.hb : 0;
+      const int cs = (kConv && cv.taps) ? ct / cv.tiles_per_img : 0;
+      const int cy0 = (kConv && cv.taps) ? (ct - cs * cv.tiles_per_img) * cv.hb : 0;
       int tap = 0, slab = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -439,7 +442,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
           if constexpr (kCta2) {
             // the leader expects the bytes of BOTH CTAs; both CTAs' loads complete on the leader's barrier
             if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (Cfg::kABytes + Cfg::kBBytes / 2));
-            if (cv.taps) {
+            if (kConv && cv.taps) {
               const int dy = tap / cv.kw;
               tma_load_4d_2sm(smem_a + stage * Cfg::kABytes, &tma_a, &full_bar[stage], slab * BK,
                               tap - dy * cv.kw - cv.pad_w, cy0 + dy - cv.pad_h, cs);
@@ -450,7 +453,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
                             n_blk * BN + cta_rank * (BN / 2));
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            if (cv.taps) {
+            if (kConv && cv.taps) {
               const int dy = tap / cv.kw;
               tma_load_4d(smem_a + stage * Cfg::kABytes, &tma_a, &full_bar[stage], slab * BK, tap - dy * cv.kw - cv.pad_w,
                           cy0 + dy - cv.pad_h, cs);
@@ -460,7 +463,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
             tma_load_2d(smem_b + stage * Cfg::kBBytes, &tma_w, &full_bar[stage], kb * BK, n_blk * BN);
           }
         }
-        if (++slab == cv.cin_slabs) {
+        if (kConv && ++slab == cv.cin_slabs) {
           slab = 0;
           ++tap;
         }
@@ -471,7 +474,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         }
       }
     }
-  } else if (warp == 1 && cta_rank == 0 && cv.halo) {
+  } else if (kConv && warp == 1 && cta_rank == 0 && cv.halo) {
     // ===================== MMA issuer, convolution halo mode =====================
     constexpr uint32_t idesc = umma_idesc_f16(TM, BN, 0, 0);
     const uint64_t bdesc0 = umma_desc_kmajor_sw128(smem_u32(smem_wring));
@@ -634,7 +637,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         }
         // convolution post-ops: the pixel row this thread's tile row stands for (-1: a padding slot / beyond the image)
         long long post_row = -1;
-        if (ep.post) {
+        if (kConv && ep.post) {
           const int ct = m_blk * (kCta2 ? 2 : 1) + cta_rank;
           const int cs = ct / cv.tiles_per_img;
           const int tr = quad * 32 + lane;
@@ -716,11 +719,11 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
               for (int q = 0; q < 8; ++q)
                 if (n0 + u * 8 + q < ep.scale_cols) v[q] *= ep.scale;
             }
-            if (ep.relu) {
+            if (kConv && ep.relu) {
 #pragma unroll
               for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
             }
-            if (ep.post == 1) {          // GRU gate
+            if (kConv && ep.post == 1) {          // GRU gate
               const bool is_r = n0 >= ep.post_c;
               float hh[8];
               if (is_r && post_row >= 0) {
@@ -731,7 +734,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
               }
 #pragma unroll
               for (int q = 0; q < 8; ++q) v[q] = sigmoid_fast(v[q]) * hh[q];
-            } else if (ep.post == 2) {   // GRU update
+            } else if (kConv && ep.post == 2) {   // GRU update
               float hh[8], zz[8];
               if (post_row >= 0) {
                 h8_unpack(__ldg(reinterpret_cast<const uint4*>(ep.aux_h + post_row * ep.ld_h + n0 + u * 8)), hh);
@@ -749,7 +752,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
           fence_proxy_async_smem();
           __syncwarp();
           if (elect_one()) {
-            if (cv.taps) {  // this warp's 32 rows = rows_per_warp image rows of wb pixel slots; slots past the width are clipped
+            if (kConv && cv.taps) {  // this warp's 32 rows = rows_per_warp image rows of wb pixel slots; slots past the width are clipped
               const int ct = m_blk * (kCta2 ? 2 : 1) + cta_rank;
               const int cs = ct / cv.tiles_per_img;
               const int sy = (ct - cs * cv.tiles_per_img) * cv.hb + quad * cv.rows_per_warp;
@@ -988,14 +991,14 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
 
 static int g_gemm_cta2 = 1;  // CTA-pair kernels: on by default (cwm_debug_gemm_cta2(0) / CWM_GEMM_CTA2=0 switch them off)
 
-template <int BN, bool kRes, bool kCta2>
+template <int BN, bool kRes, bool kCta2, bool kConv>
 static int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const CUtensorMap& tr,
                             const CUtensorMap& tx, int M, int N, int K, const EpiDev& ep, cudaStream_t stream,
                             const ConvDev& cv_in) {
   using Cfg = GemmCfg<BN, kRes>;
   static bool attr_set = false;
   if (!attr_set) {
-    CWM_CUDA_CHECK(cudaFuncSetAttribute(gemm_f16_kernel<BN, kRes, kCta2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CWM_CUDA_CHECK(cudaFuncSetAttribute(gemm_f16_kernel<BN, kRes, kCta2, kConv>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::kSmemBytes));
     attr_set = true;
   }
@@ -1022,24 +1025,24 @@ static int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tw, const 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CWM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_f16_kernel<BN, kRes, true>, ta, tw, to, tr, tx, M, N, K, ep, cv));
+    CWM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_f16_kernel<BN, kRes, true, kConv>, ta, tw, to, tr, tx, M, N, K, ep, cv));
     count_launch();
     return CWM_OK;
   } else {
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    gemm_f16_kernel<BN, kRes, false><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tw, to, tr, tx, M, N, K, ep, cv);
+    gemm_f16_kernel<BN, kRes, false, kConv><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tw, to, tr, tx, M, N, K, ep, cv);
     CWM_LAUNCH_CHECK();
     return CWM_OK;
   }
 }
 
-template <int BN, bool kRes>
+template <int BN, bool kRes, bool kConv = false>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const CUtensorMap& tr,
                        const CUtensorMap& tx, int M, int N, int K, const EpiDev& ep, cudaStream_t stream, bool cta2,
                        const ConvDev& cv = ConvDev{0, 1, 0, 0, 1 << 30, 1, 1, 1, 0, 0, 32, 1, 0, 0}) {
-  if (cta2) return launch_gemm_impl<BN, kRes, true>(ta, tw, to, tr, tx, M, N, K, ep, stream, cv);
-  return launch_gemm_impl<BN, kRes, false>(ta, tw, to, tr, tx, M, N, K, ep, stream, cv);
+  if (cta2) return launch_gemm_impl<BN, kRes, true, kConv>(ta, tw, to, tr, tx, M, N, K, ep, stream, cv);
+  return launch_gemm_impl<BN, kRes, false, kConv>(ta, tw, to, tr, tx, M, N, K, ep, stream, cv);
 }
 
 int pick_bn(int N) {
@@ -1230,10 +1233,10 @@ static int conv2d_impl(const uint16_t* x, int ldx, int S, int H, int W, int Cin,
                     2.0 * S * H * W * static_cast<double>(Cout) * cv.taps * Cin,
                     static_cast<double>(S) * H * W * (Cin + Cout) * 2.0 + static_cast<double>(Cout) * K * 2.0);
   switch (bn) {
-    case 64: return launch_gemm<64, false>(ta, tw, to, to2, to, M, Cout, K, ep, s, cta2, cv);
-    case 128: return launch_gemm<128, false>(ta, tw, to, to2, to, M, Cout, K, ep, s, cta2, cv);
-    case 192: return launch_gemm<192, false>(ta, tw, to, to2, to, M, Cout, K, ep, s, cta2, cv);
-    default: return launch_gemm<256, false>(ta, tw, to, to2, to, M, Cout, K, ep, s, cta2, cv);
+    case 64: return launch_gemm<64, false, true>(ta, tw, to, to2, to, M, Cout, K, ep, s, cta2, cv);
+    case 128: return launch_gemm<128, false, true>(ta, tw, to, to2, to, M, Cout, K, ep, s, cta2, cv);
+    case 192: return launch_gemm<192, false, true>(ta, tw, to, to2, to, M, Cout, K, ep, s, cta2, cv);
+    default: return launch_gemm<256, false, true>(ta, tw, to, to2, to, M, Cout, K, ep, s, cta2, cv);
   }
 }
 
