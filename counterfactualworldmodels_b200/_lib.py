@@ -29,11 +29,12 @@ EXPORTED_SYMBOLS = (
     "cwm_raft_flow_update", "cwm_total_launches",
     "cwm_conv2d_weight_k", "cwm_conv2d_f16", "cwm_raft_im2col_flow", "cwm_conv2d_gru_gate_f16",
     "cwm_conv2d_gru_update_f16",
+    "cwm_raft_corr_tc_workspace_bytes", "cwm_raft_corr_volume_tc", "cwm_raft_corr_pyramid_tc",
     "cwm_philox4x32_10", "cwm_mask_uniform", "cwm_mask_energy_table", "cwm_mask_energy_sample",
     "cwm_mask_rectangularize_workspace_bytes", "cwm_mask_rectangularize",
     # tuning hooks (header section "tuning hooks")
     "cwm_debug_attention_poly", "cwm_debug_attention_war_safe", "cwm_debug_attention_persistent",
-    "cwm_debug_attention_persist_map", "cwm_debug_attn_mma_wide", "cwm_debug_attn_mma_split", "cwm_debug_gemm_cta2",
+    "cwm_debug_attention_persist_map", "cwm_debug_attention_stale_max", "cwm_debug_attn_mma_wide", "cwm_debug_attn_mma_split", "cwm_debug_gemm_cta2",
 )
 
 
@@ -120,7 +121,7 @@ def _declare(lib):
     lib.cwm_launch_count_reset.restype = c_int
     lib.cwm_total_launches.restype = ctypes.c_longlong
     for name in ("cwm_debug_attention_poly", "cwm_debug_attention_war_safe", "cwm_debug_attention_persistent",
-                 "cwm_debug_attention_persist_map", "cwm_debug_attn_mma_wide", "cwm_debug_attn_mma_split"):
+                 "cwm_debug_attention_persist_map", "cwm_debug_attention_stale_max", "cwm_debug_attn_mma_wide", "cwm_debug_attn_mma_split"):
         getattr(lib, name).argtypes = [c_int]
         getattr(lib, name).restype = None
     lib.cwm_debug_gemm_cta2.argtypes = [c_int]
@@ -163,6 +164,12 @@ def _declare(lib):
     lib.cwm_motion_map_finalize.argtypes = [c_void_p, c_int, c_int, c_int, c_float, c_int, c_float, c_void_p, c_void_p]
     lib.cwm_raft_corr_pyramid.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, POINTER(c_void_p),
                                           c_void_p]
+    lib.cwm_raft_corr_tc_workspace_bytes.argtypes = [c_int] * 4
+    lib.cwm_raft_corr_tc_workspace_bytes.restype = c_size_t
+    lib.cwm_raft_corr_volume_tc.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t,
+                                            c_void_p]
+    lib.cwm_raft_corr_pyramid_tc.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, POINTER(c_void_p),
+                                             c_void_p, c_size_t, c_void_p]
     lib.cwm_raft_corr_lookup.argtypes = [POINTER(c_void_p), c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
                                          c_void_p]
     lib.cwm_raft_upsample_flow.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]

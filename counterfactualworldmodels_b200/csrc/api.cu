@@ -78,6 +78,26 @@ int make_tmap_2d(CUtensorMap* map, const void* base, int dtype, uint64_t rows, u
   return CWM_OK;
 }
 
+int make_tmap_3d_f32(CUtensorMap* map, const void* base, uint64_t S, uint64_t R, uint64_t C, uint32_t box_rows,
+                     uint32_t box_cols) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return fail(CWM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (C * 4) % 16 != 0 || box_cols * 4 > 128 || box_rows > 256)
+    return fail(CWM_ERR_INVALID, "TMA operand (3-D fp32) misaligned or box too large (base %p, C %llu, box [%u, %u])", base,
+                (unsigned long long)C, box_rows, box_cols);
+  cuuint64_t gdim[3] = {C, R, S};
+  cuuint64_t gstride[2] = {C * 4, R * C * 4};
+  cuuint32_t box[3] = {box_cols, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(CWM_ERR_CUDA, "cuTensorMapEncodeTiled (3-D fp32) failed (%d) S=%llu R=%llu C=%llu", (int)r,
+                (unsigned long long)S, (unsigned long long)R, (unsigned long long)C);
+  return CWM_OK;
+}
+
 int make_tmap_nhwc(CUtensorMap* map, const void* base, uint64_t S, uint64_t H, uint64_t W, uint64_t C, uint64_t ld,
                    uint32_t box_h, uint32_t box_w, uint32_t box_c) {
   PFN_encodeTiled enc = get_encode();

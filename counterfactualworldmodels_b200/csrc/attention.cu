@@ -155,7 +155,7 @@ __device__ __forceinline__ ItemCoord decode_item(int item, int nq, int H, int N)
 template <int kPoly, bool kDbg>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attention_persist_kernel(const __grid_constant__ CUtensorMap tma_qkv, int N, int H, int B, __half* __restrict__ out,
-                         float scale_log2, int strided, int war_safe) {
+                         float scale_log2, int strided, int war_safe, int stale_max) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_q = smem;                               // 2 buffers x 2 tiles
@@ -427,78 +427,104 @@ attention_persist_kernel(const __grid_constant__ CUtensorMap tma_qkv, int N, int
           for (int i = 0; i < 128; ++i)
             if (i >= kv_valid) s[i] = 0xff800000u;  // -inf
         }
-        float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]);
-        float mx2 = __uint_as_float(s[2]), mx3 = __uint_as_float(s[3]);
+        // Row maximum of this tile.  Only the FIRST tile of an item needs it before the exponentials; afterwards the
+        // exponentials use the running reference m_ref as it stands (the lazy rescale keeps it within 2^8 of the true
+        // maximum in all but rare tiles), the tile maximum is reduced in the same instruction stream (ALU pipe, beside the
+        // MUFU / FMA work), and only if it turns out to exceed m_ref by more than the threshold the tile is redone with
+        // the new reference.  This removes the serialised "load everything -> max -> exp" phase during which a warp keeps
+        // the XU pipe idle.
+        auto tile_max = [&]() {
+          float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]);
+          float mx2 = __uint_as_float(s[2]), mx3 = __uint_as_float(s[3]);
 #pragma unroll
-        for (int i = 4; i < 128; i += 4) {
-          mx0 = fmaxf(mx0, __uint_as_float(s[i]));
-          mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
-          mx2 = fmaxf(mx2, __uint_as_float(s[i + 2]));
-          mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
-        }
-        const float row_max = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+          for (int i = 4; i < 128; i += 4) {
+            mx0 = fmaxf(mx0, __uint_as_float(s[i]));
+            mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
+            mx2 = fmaxf(mx2, __uint_as_float(s[i + 2]));
+            mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
+          }
+          return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        };
+        // exp2((s - m_ref) * scale) for the whole tile -> f16 P over S in tensor memory; returns the fp32 row sum
+        auto exp_tile = [&](float neg_m) {
+          float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (c * 32 < ncols) {
+              uint32_t p[16];  // 32 kv elements as packed f16 pairs; P aliases S columns that are already in registers
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const int el = c * 32 + i;
+                float x0, x1, x2, x3, p0, p1, p2, p3;
+                ffma2(x0, x1, __uint_as_float(s[el]), __uint_as_float(s[el + 1]), scale_log2, neg_m);
+                ffma2(x2, x3, __uint_as_float(s[el + 2]), __uint_as_float(s[el + 3]), scale_log2, neg_m);
+                if (pair_poly(kPoly, el)) {
+                  ex2_poly2(p0, p1, x0, x1);
+                } else {
+                  p0 = ex2(x0);
+                  p1 = ex2(x1);
+                }
+                if (pair_poly(kPoly, el + 2)) {
+                  ex2_poly2(p2, p3, x2, x3);
+                } else {
+                  p2 = ex2(x2);
+                  p3 = ex2(x3);
+                }
+                fadd2(sum0, sum1, sum0, sum1, p0, p1);
+                fadd2(sum2, sum3, sum2, sum3, p2, p3);
+                p[(i >> 1)] = pack_half2(p0, p1);
+                p[(i >> 1) + 1] = pack_half2(p2, p3);
+              }
+              tmem_st_x16(tm_s + c * 16, p);
+            }
+          }
+          return (sum0 + sum1) + (sum2 + sum3);
+        };
+        // O_t *= f, l *= f for the rows whose reference maximum moved (all lanes take part: the TMEM accesses are warp-wide)
+        auto rescale = [&](float row_max, bool need) {
+          const float f = need ? ex2((m_ref - row_max) * scale_log2) : 1.0f;
+          if (need) m_ref = row_max;
+          l_sum *= f;
+          // O_t is quiescent once PV_t of the previous step has completed (PV_t of this step is not issued before
+          // this warpgroup signals p_full[t]).  pv_done alternates between two barriers by step parity: this warp
+          // does not observe every completion (the wait is lazy), and a warp may be a full step ahead of the
+          // slowest warp of its group, so on a single barrier "PV(gt-2) still pending" and "PV(gt-1) done" would
+          // have the same parity.  On barrier (gt-1)&1 the previous completion is PV(gt-3), which is known to be
+          // complete because S(gt-1) -- issued after it and already consumed by this warp -- has completed.
+          WAIT(&pv_done[2 * t + ((gt - 1) & 1)], ((gt - 1) >> 1) & 1, 13 + t, gt);
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            tmem_ld_x32(tm_o + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+            tmem_st_x32(tm_o + c * 32, o);
+          }
+          tmem_st_wait();
+        };
+        float tile_sum;
         if (j == 0) {
-          m_ref = row_max;
-        } else {
+          m_ref = tile_max();
+          tile_sum = exp_tile(-m_ref * scale_log2);
+        } else if (stale_max) {
+          tile_sum = exp_tile(-m_ref * scale_log2);
+          const float row_max = tile_max();
           const bool need = (row_max - m_ref) * scale_log2 > kRescaleThreshold;
-          if (__any_sync(0xffffffffu, need)) {
-            const float f = need ? ex2((m_ref - row_max) * scale_log2) : 1.0f;
-            if (need) m_ref = row_max;
-            l_sum *= f;
-            // O_t is quiescent once PV_t of the previous step has completed (PV_t of this step is not issued before
-            // this warpgroup signals p_full[t]).  pv_done alternates between two barriers by step parity: this warp
-            // does not observe every completion (the wait is lazy), and a warp may be a full step ahead of the
-            // slowest warp of its group, so on a single barrier "PV(gt-2) still pending" and "PV(gt-1) done" would
-            // have the same parity.  On barrier (gt-1)&1 the previous completion is PV(gt-3), which is known to be
-            // complete because S(gt-1) -- issued after it and already consumed by this warp -- has completed.
-            WAIT(&pv_done[2 * t + ((gt - 1) & 1)], ((gt - 1) >> 1) & 1, 13 + t, gt);
-            tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              uint32_t o[32];
-              tmem_ld_x32(tm_o + c * 32, o);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-              tmem_st_x32(tm_o + c * 32, o);
-            }
+          if (__any_sync(0xffffffffu, need)) {   // rare: the tile's exponentials were taken against a stale reference
             tmem_st_wait();
+            rescale(row_max, need);
+            tile_sum = exp_tile(-m_ref * scale_log2);
           }
-        }
-        const float neg_m = -m_ref * scale_log2;
-        float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (c * 32 < ncols) {
-            uint32_t p[16];  // 32 kv elements as packed f16 pairs; P aliases S columns that are already in registers
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const int el = c * 32 + i;
-              float x0, x1, x2, x3, p0, p1, p2, p3;
-              ffma2(x0, x1, __uint_as_float(s[el]), __uint_as_float(s[el + 1]), scale_log2, neg_m);
-              ffma2(x2, x3, __uint_as_float(s[el + 2]), __uint_as_float(s[el + 3]), scale_log2, neg_m);
-              if (pair_poly(kPoly, el)) {
-                ex2_poly2(p0, p1, x0, x1);
-              } else {
-                p0 = ex2(x0);
-                p1 = ex2(x1);
-              }
-              if (pair_poly(kPoly, el + 2)) {
-                ex2_poly2(p2, p3, x2, x3);
-              } else {
-                p2 = ex2(x2);
-                p3 = ex2(x3);
-              }
-              fadd2(sum0, sum1, sum0, sum1, p0, p1);
-              fadd2(sum2, sum3, sum2, sum3, p2, p3);
-              p[(i >> 1)] = pack_half2(p0, p1);
-              p[(i >> 1) + 1] = pack_half2(p2, p3);
-            }
-            tmem_st_x16(tm_s + c * 16, p);
-          }
+        } else {
+          const float row_max = tile_max();
+          const bool need = (row_max - m_ref) * scale_log2 > kRescaleThreshold;
+          if (__any_sync(0xffffffffu, need)) rescale(row_max, need);
+          tile_sum = exp_tile(-m_ref * scale_log2);
         }
         tmem_st_wait();
-        l_sum += (sum0 + sum1) + (sum2 + sum3);
+        l_sum += tile_sum;
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[2 * t + (gt & 1)]);
@@ -552,6 +578,8 @@ extern "C" void cwm_debug_attention_poly(int eighths) {
 static int g_attn_mode = 1;
 static int g_attn_persist_map = -1;  // -1 = automatic, 0 = contiguous ranges, 1 = strided
 static int g_attn_war_safe = 1;
+static int g_attn_stale_max = 1;  // exponentials against the running reference, tile maximum checked afterwards
+extern "C" void cwm_debug_attention_stale_max(int on) { g_attn_stale_max = on; }
 extern "C" void cwm_debug_attention_war_safe(int on) { g_attn_war_safe = on; }
 extern "C" void cwm_debug_attention_persistent(int mode) { g_attn_mode = (mode <= 0) ? 3 : mode; }
 extern "C" void cwm_debug_attention_persist_map(int m) { g_attn_persist_map = m; }
@@ -568,7 +596,7 @@ extern "C" int cwm_attention_f16(const uint16_t* qkv, int B, int N, int H, int h
   if (B == 0) return CWM_OK;
   const long long n_items = static_cast<long long>((N + 255) / 256) * H * B;
   CWM_REQUIRE(n_items < (1ll << 31), "cwm_attention_f16: too many work items");
-  using KernelFn = void (*)(const CUtensorMap, int, int, int, __half*, float, int, int);
+  using KernelFn = void (*)(const CUtensorMap, int, int, int, __half*, float, int, int, int);
   static const KernelFn kernels[6] = {attention_persist_kernel<0, false>, attention_persist_kernel<1, false>,
                                       attention_persist_kernel<2, false>, attention_persist_kernel<3, false>,
                                       attention_persist_kernel<4, false>, attention_persist_kernel<kDefaultPoly, true>};
@@ -592,7 +620,7 @@ extern "C" int cwm_attention_f16(const uint16_t* qkv, int B, int N, int H, int h
   const int strided = !multi ? 1 : (g_attn_persist_map >= 0) ? g_attn_persist_map : (kv_resident > 48e6 ? 1 : 0);
   kernels[(g_attn_mode == 2 || g_attn_mode == 4) ? 5 : g_attn_poly]<<<grid, kAttnThreads, kPersistSmemBytes,
                                                                       static_cast<cudaStream_t>(stream)>>>(
-      tm, N, H, B, reinterpret_cast<__half*>(out), kLog2e, strided, g_attn_war_safe);
+      tm, N, H, B, reinterpret_cast<__half*>(out), kLog2e, strided, g_attn_war_safe, g_attn_stale_max);
   CWM_LAUNCH_CHECK();
   return CWM_OK;
 }

@@ -51,6 +51,9 @@ int make_tmap_2d(CUtensorMap* map, const void* base, int dtype, uint64_t rows, u
 // the image, out-of-range elements are zero-filled by the TMA unit (= the convolution's zero padding).
 int make_tmap_nhwc(CUtensorMap* map, const void* base, uint64_t S, uint64_t H, uint64_t W, uint64_t C, uint64_t ld,
                    uint32_t box_h, uint32_t box_w, uint32_t box_c);
+// 3-D fp32 tensor [S, R, C] (C contiguous), box [1, box_rows, box_cols], 128B swizzle (box_cols * 4 <= 128).
+int make_tmap_3d_f32(CUtensorMap* map, const void* base, uint64_t S, uint64_t R, uint64_t C, uint32_t box_rows,
+                     uint32_t box_cols);
 int num_sms();
 
 // Optional per-launch CUDA-event timing (cwm_profile_begin/end).  No-op (one branch) when profiling is off.
@@ -138,6 +141,12 @@ __device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorM
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, "
       "{%3, %4}], [%2], %5;" ::"r"(smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,

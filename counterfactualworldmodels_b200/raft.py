@@ -13,6 +13,7 @@ argument meaning, on the hand-written kernels of ``csrc/raftcorr.cu``:
 section 7).  There is no CPU fallback: CPU tensors raise.
 """
 import ctypes
+import os
 
 import torch
 
@@ -55,9 +56,20 @@ class CorrBlock:
         for _ in range(num_levels):
             self.corr_pyramid.append(torch.empty(batch * ht * wd, 1, h, w, dtype=torch.float32, device=fmap1.device))
             h, w = h // 2, w // 2
+        lib = _lib.load()
+        # level 0 on the tensor cores (3xTF32 split, fp32 accuracy) when the channel count allows the 32-wide k-slabs;
+        # CWM_RAFT_CORR=simt keeps round 1's fp32 SIMT kernel (the A/B reference)
+        tensor_cores = dim % 32 == 0 and os.environ.get("CWM_RAFT_CORR", "tc") != "simt"
         with torch.cuda.device(fmap1.device):
-            _lib.check(_lib.load().cwm_raft_corr_pyramid(fmap1.data_ptr(), fmap2.data_ptr(), batch, dim, ht, wd,
-                                                         num_levels, _ptr_table(self.corr_pyramid), _stream(fmap1)))
+            if tensor_cores:
+                ws = torch.empty(lib.cwm_raft_corr_tc_workspace_bytes(batch, dim, ht, wd), dtype=torch.uint8,
+                                 device=fmap1.device)
+                _lib.check(lib.cwm_raft_corr_pyramid_tc(fmap1.data_ptr(), fmap2.data_ptr(), batch, dim, ht, wd, num_levels,
+                                                        _ptr_table(self.corr_pyramid), ws.data_ptr(), ws.numel(),
+                                                        _stream(fmap1)))
+            else:
+                _lib.check(lib.cwm_raft_corr_pyramid(fmap1.data_ptr(), fmap2.data_ptr(), batch, dim, ht, wd, num_levels,
+                                                     _ptr_table(self.corr_pyramid), _stream(fmap1)))
 
     def __call__(self, coords):
         coords = _req(coords, "CorrBlock coords", 4)

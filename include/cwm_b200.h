@@ -396,6 +396,15 @@ int cwm_motion_map_finalize(const float* sums, int B, int H, int W, float count,
  * must be at least 2x2 (the reference divides by size-1, cwm/models/raft/utils.py:64-65). */
 int cwm_raft_corr_pyramid(const float* fmap1, const float* fmap2, int B, int D, int H, int W, int num_levels,
                           float* const* levels, cwm_stream_t stream);
+
+/* The same pyramid with level 0 (the all-pairs volume) on the tensor cores: every operand is split into tf32(x) and
+ * tf32(x - tf32(x)) and hi*hi + hi*lo + lo*hi is accumulated in fp32 by tcgen05.mma.kind::tf32 -- fp32 accuracy (the
+ * dropped lo*lo term is 2^-22 of a product), corr.py:53-60.  D % 32 == 0; workspace: cwm_raft_corr_tc_workspace_bytes. */
+size_t cwm_raft_corr_tc_workspace_bytes(int B, int D, int H, int W);
+int cwm_raft_corr_volume_tc(const float* fmap1, const float* fmap2, int B, int D, int H, int W, float* out, void* workspace,
+                            size_t workspace_bytes, cwm_stream_t stream);
+int cwm_raft_corr_pyramid_tc(const float* fmap1, const float* fmap2, int B, int D, int H, int W, int num_levels,
+                             float* const* levels, void* workspace, size_t workspace_bytes, cwm_stream_t stream);
 /* `CorrBlock.__call__` (corr.py:30-51) + `bilinear_sampler` (utils.py:60-80, grid_sample align_corners=True, zero
  * padding): coords [B, 2, H, W] (channel 0 = x, 1 = y, in level-0 pixels) -> out [B, num_levels*(2r+1)^2, H, W];
  * channel l*(2r+1)^2 + a*(2r+1) + b samples level l at (x/2^l + a - r, y/2^l + b - r). */
@@ -507,6 +516,7 @@ long long cwm_total_launches(void);
  * boundary. */
 void cwm_debug_attention_poly(int eighths);        /* share (in 1/8) of the softmax exponentials evaluated on the FMA pipe */
 void cwm_debug_attention_war_safe(int on);         /* conservative score-buffer reuse (debug) */
+void cwm_debug_attention_stale_max(int on);        /* 1 (default): exponentials first, tile maximum checked afterwards */
 void cwm_debug_attention_persistent(int mode);     /* 1 = persistent CTAs (default), 3 = one work item per CTA; 2 / 4 = the same with watchdog waits */
 void cwm_debug_attention_persist_map(int m);       /* work-item map of the persistent kernel: -1 auto, 0 ranges, 1 strided */
 void cwm_debug_attn_mma_wide(int on);              /* small-attention kernel: 8 warps per K/V tile */

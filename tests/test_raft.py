@@ -658,3 +658,25 @@ def test_gpu_imu_conditioned_sweep_matches_the_reference():
     assert np.abs(err).max() <= 2e-2 and np.abs(err).mean() <= 2e-3
     assert torch.isfinite(flows).all()
     assert not hasattr(G.predictor, 'padding_mask')            # the wrappers reset the padding masks after every call
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,D,H,W", [(2, 256, 28, 28), (1, 128, 16, 16), (3, 32, 9, 13), (2, 64, 30, 17)])
+def test_gpu_corr_volume_on_tensor_cores_keeps_fp32_accuracy(B, D, H, W, monkeypatch):
+    """`cwm_raft_corr_pyramid_tc`: the all-pairs volume as 3 TF32 products per k-step (hi*hi + hi*lo + lo*hi) on
+    tcgen05.mma.kind::tf32 against the float64 product of the same fp32 operands, on feature maps whose channels span four
+    orders of magnitude.  Bar: 5e-6 of the volume's scale (measured 3e-7 ... 2.5e-6: the tensor core's fp32 accumulation
+    over 256 channels; a single TF32 product would be at ~5e-4), the round-1 fp32 SIMT kernel 1e-6 (measured <= 6e-7)."""
+    from counterfactualworldmodels_b200 import raft
+    g = torch.Generator().manual_seed(B * 100 + D)
+    f1 = torch.randn(B, D, H, W, generator=g) * torch.logspace(-2, 2, D).view(1, D, 1, 1)[:, torch.randperm(D, generator=g)]
+    f2 = torch.randn(B, D, H, W, generator=g)
+    want = torch.einsum("bdi,bdj->bij", f1.double().flatten(2), f2.double().flatten(2)) / (float(D) ** 0.5)
+    scale = want.abs().max().item()
+    monkeypatch.setenv("CWM_RAFT_CORR", "tc")
+    tc = raft.CorrBlock(f1.to(DEV), f2.to(DEV), num_levels=1, radius=1).corr_pyramid[0].view(B, H * W, H * W).cpu()
+    monkeypatch.setenv("CWM_RAFT_CORR", "simt")
+    simt = raft.CorrBlock(f1.to(DEV), f2.to(DEV), num_levels=1, radius=1).corr_pyramid[0].view(B, H * W, H * W).cpu()
+    e_tc, e_simt = (tc.double() - want).abs().max().item() / scale, (simt.double() - want).abs().max().item() / scale
+    print(f"corr volume B={B} D={D} {H}x{W}: tensor cores {e_tc:.2e} of scale, fp32 SIMT {e_simt:.2e}")
+    assert e_tc <= 5e-6 and e_simt <= 1e-6

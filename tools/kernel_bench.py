@@ -182,6 +182,9 @@ if __name__ == "__main__":
         lib = _lib.load()
         lib.cwm_debug_attention_persistent(int(os.environ["CWM_ATTN_PERSIST"]))
         print("attention mode (3 = one item per CTA, 1 = experimental multi-item) =", os.environ["CWM_ATTN_PERSIST"])
+    if os.environ.get("CWM_ATTN_STALE"):
+        _lib.load().cwm_debug_attention_stale_max(int(os.environ["CWM_ATTN_STALE"]))
+        print("attention stale-max =", os.environ["CWM_ATTN_STALE"])
     if os.environ.get("CWM_ATTN_MAP"):
         _lib.load().cwm_debug_attention_persist_map(int(os.environ["CWM_ATTN_MAP"]))
         print("attention persist map =", os.environ["CWM_ATTN_MAP"])
