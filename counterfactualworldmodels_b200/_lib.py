@@ -30,6 +30,7 @@ EXPORTED_SYMBOLS = (
     "cwm_conv2d_weight_k", "cwm_conv2d_f16", "cwm_raft_im2col_flow", "cwm_conv2d_gru_gate_f16",
     "cwm_conv2d_gru_update_f16",
     "cwm_raft_corr_tc_workspace_bytes", "cwm_raft_corr_volume_tc", "cwm_raft_corr_pyramid_tc",
+    "cwm_instnorm_workspace_bytes", "cwm_instnorm_f16",
     "cwm_philox4x32_10", "cwm_mask_uniform", "cwm_mask_energy_table", "cwm_mask_energy_sample",
     "cwm_mask_rectangularize_workspace_bytes", "cwm_mask_rectangularize",
     # tuning hooks (header section "tuning hooks")
@@ -190,6 +191,10 @@ def _declare(lib):
     lib.cwm_conv2d_gru_update_f16.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
                                               c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]
     lib.cwm_raft_im2col_flow.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]
+    lib.cwm_instnorm_workspace_bytes.argtypes = [c_int, c_int]
+    lib.cwm_instnorm_workspace_bytes.restype = c_size_t
+    lib.cwm_instnorm_f16.argtypes = [c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p, c_int, c_void_p, c_void_p,
+                                     c_size_t, c_void_p]
     c_u64, c_u32p = ctypes.c_uint64, POINTER(ctypes.c_uint32)
     lib.cwm_philox4x32_10.argtypes = [c_u32p, c_u32p, c_u32p]
     lib.cwm_mask_uniform.argtypes = [c_u64] + [c_int] * 8 + [c_void_p, c_void_p]

@@ -1,0 +1,163 @@
+// norm.cu -- instance normalisation of NHWC f16 feature maps for RAFT's feature encoder (cwm/models/raft/extractor.py:
+// 118-190, `norm_fn='instance'`: nn.InstanceNorm2d, no affine, eps 1e-5, biased variance), fused with what follows it:
+//   y = relu?( (x - mean[s, c]) * rstd[s, c] )        and, at the end of a residual block,   out = relu( shortcut + y ).
+// In eager PyTorch every norm is a statistics kernel + a transform kernel on NCHW tensors, plus cuDNN's NCHW <-> NHWC
+// transforms around the neighbouring convolutions, a bias add and a relu: 4.5 of the 20.4 ms of a 64-sample flow call.
+// Here the activations stay NHWC f16 (what the tensor-core convolutions consume), statistics are fp32:
+//   instnorm_stats_kernel   grid (slabs, S): per (sample, pixel slab) partial sum / sum of squares of every channel
+//   instnorm_apply_kernel   grid (pixel blocks, S): sums the slab partials in a fixed order (deterministic), then streams
+// Both are HBM bound: 2 bytes read per element for the statistics, 2 (+2) read + 2 written for the transform.
+#include "common.cuh"
+
+namespace cwm {
+
+constexpr int kNormThreads = 256;
+
+__device__ __forceinline__ void h8_to_f32(const uint4& u, float* f) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+
+__global__ void __launch_bounds__(kNormThreads)
+instnorm_stats_kernel(const __half* __restrict__ x, int HW, int C, int nslab, float2* __restrict__ partial) {
+  extern __shared__ float2 red[];   // [pixel lanes][C]
+  const int s = blockIdx.y, slab = blockIdx.x;
+  const int groups = C >> 3;                       // 8-channel groups per pixel
+  const int lanes = kNormThreads / groups;         // pixels in flight
+  const int cg = threadIdx.x % groups, pl = threadIdx.x / groups;
+  const int per = (HW + nslab - 1) / nslab;
+  const int p0 = slab * per, p1 = min(HW, p0 + per);
+  float s1[8], s2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
+  if (pl < lanes) {
+    const __half* xs = x + (static_cast<size_t>(s) * HW) * C + cg * 8;
+    for (int p = p0 + pl; p < p1; p += lanes) {
+      float f[8];
+      h8_to_f32(__ldg(reinterpret_cast<const uint4*>(xs + static_cast<size_t>(p) * C)), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s1[i] += f[i];
+        s2[i] = fmaf(f[i], f[i], s2[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[pl * C + cg * 8 + i] = make_float2(s1[i], s2[i]);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += kNormThreads) {
+    float a = 0.f, b = 0.f;
+    for (int l = 0; l < lanes; ++l) {
+      const float2 v = red[l * C + c];
+      a += v.x;
+      b += v.y;
+    }
+    partial[(static_cast<size_t>(s) * nslab + slab) * C + c] = make_float2(a, b);
+  }
+}
+
+__global__ void __launch_bounds__(kNormThreads)
+instnorm_apply_kernel(const __half* __restrict__ x, const float2* __restrict__ partial, int nslab, int HW, int C, float eps,
+                      int relu_inner, const __half* __restrict__ add, int relu_outer, int pixels_per_block,
+                      __half* __restrict__ out) {
+  extern __shared__ float2 stat[];   // [C]: (mean, rstd)
+  const int s = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += kNormThreads) {
+    float a = 0.f, b = 0.f;
+    for (int l = 0; l < nslab; ++l) {
+      const float2 v = partial[(static_cast<size_t>(s) * nslab + l) * C + c];
+      a += v.x;
+      b += v.y;
+    }
+    const float mean = a / static_cast<float>(HW);
+    const float var = fmaxf(b / static_cast<float>(HW) - mean * mean, 0.f);
+    stat[c] = make_float2(mean, rsqrtf(var + eps));
+  }
+  __syncthreads();
+  const int groups = C >> 3;
+  const int p0 = blockIdx.x * pixels_per_block, p1 = min(HW, p0 + pixels_per_block);
+  const size_t base = static_cast<size_t>(s) * HW * C;
+  for (int u = p0 * groups + threadIdx.x; u < p1 * groups; u += kNormThreads) {
+    const int p = u / groups, cg = u - p * groups;
+    const size_t off = base + static_cast<size_t>(p) * C + cg * 8;
+    float f[8], g[8];
+    h8_to_f32(__ldg(reinterpret_cast<const uint4*>(x + off)), f);
+    if (add != nullptr) h8_to_f32(__ldg(reinterpret_cast<const uint4*>(add + off)), g);
+    uint32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+      const float2 st0 = stat[cg * 8 + i], st1 = stat[cg * 8 + i + 1];
+      float y0 = (f[i] - st0.x) * st0.y, y1 = (f[i + 1] - st1.x) * st1.y;
+      if (relu_inner) {
+        y0 = fmaxf(y0, 0.f);
+        y1 = fmaxf(y1, 0.f);
+      }
+      if (add != nullptr) {
+        y0 += g[i];
+        y1 += g[i + 1];
+      }
+      if (relu_outer) {
+        y0 = fmaxf(y0, 0.f);
+        y1 = fmaxf(y1, 0.f);
+      }
+      o[i >> 1] = pack_half2(y0, y1);
+    }
+    *reinterpret_cast<uint4*>(out + off) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+}  // namespace cwm
+
+using namespace cwm;
+
+extern "C" size_t cwm_instnorm_workspace_bytes(int S, int C) { return static_cast<size_t>(S) * 16 * C * sizeof(float2); }
+
+// out[s, p, c] = post((x[s, p, c] - mean[s, c]) / sqrt(var[s, c] + eps)), statistics over the HW pixels of sample s;
+// post: optional relu, then optional `+ add[s, p, c]`, then optional relu.  x / add / out: NHWC f16 [S, HW, C], C % 8 == 0.
+extern "C" int cwm_instnorm_f16(const uint16_t* x, int S, int HW, int C, float eps, int relu_inner, const uint16_t* add,
+                                int relu_outer, uint16_t* out, void* workspace, size_t workspace_bytes, cwm_stream_t stream) {
+  CWM_REQUIRE(S >= 0 && HW >= 1 && C >= 8 && C % 8 == 0 && C <= 2048, "cwm_instnorm_f16: bad shape S=%d HW=%d C=%d (C %% 8 == 0)", S, HW, C);
+  if (S == 0) return CWM_OK;
+  CWM_REQUIRE(x && out && workspace, "cwm_instnorm_f16: null pointer");
+  CWM_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(add)) & 15) == 0,
+              "cwm_instnorm_f16: tensors must be 16-byte aligned");
+  CWM_REQUIRE(workspace_bytes >= cwm_instnorm_workspace_bytes(S, C), "cwm_instnorm_f16: workspace too small");
+  CWM_REQUIRE(S <= 65535, "cwm_instnorm_f16: batch %d > 65535", S);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // enough (sample, slab) CTAs to fill the machine, at most 16 slabs (the workspace holds 16)
+  int nslab = (2 * num_sms() + S - 1) / S;
+  nslab = nslab < 1 ? 1 : (nslab > 16 ? 16 : nslab);
+  if (nslab > HW) nslab = HW;
+  float2* partial = static_cast<float2*>(workspace);
+  const int groups = C / 8, lanes = kNormThreads / groups > 0 ? kNormThreads / groups : 1;
+  CWM_REQUIRE(groups <= kNormThreads, "cwm_instnorm_f16: C too large for one CTA row");
+  {
+    ProfileScope prof(st, "instnorm_stats", 0.0, static_cast<double>(S) * HW * C * 2.0);
+    const size_t smem = static_cast<size_t>(lanes) * C * sizeof(float2);
+    static size_t configured = 0;
+    if (smem > configured && smem > 48 * 1024) {
+      CWM_CUDA_CHECK(cudaFuncSetAttribute(instnorm_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      configured = smem;
+    }
+    instnorm_stats_kernel<<<dim3(nslab, S), kNormThreads, smem, st>>>(reinterpret_cast<const __half*>(x), HW, C, nslab, partial);
+    CWM_LAUNCH_CHECK();
+  }
+  {
+    ProfileScope prof(st, "instnorm_apply", 0.0, static_cast<double>(S) * HW * C * (add ? 6.0 : 4.0));
+    int blocks = (4 * num_sms() + S - 1) / S;
+    if (blocks < 1) blocks = 1;
+    int ppb = (HW + blocks - 1) / blocks;
+    if (ppb < 8) ppb = 8;
+    blocks = (HW + ppb - 1) / ppb;
+    instnorm_apply_kernel<<<dim3(blocks, S), kNormThreads, C * sizeof(float2), st>>>(
+        reinterpret_cast<const __half*>(x), partial, nslab, HW, C, eps, relu_inner, reinterpret_cast<const __half*>(add),
+        relu_outer, ppb, reinterpret_cast<__half*>(out));
+    CWM_LAUNCH_CHECK();
+  }
+  return CWM_OK;
+}

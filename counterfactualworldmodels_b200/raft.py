@@ -363,6 +363,66 @@ class BasicUpdateBlock(nn.Module):
         return net, (.25 * self.mask(net) if upsample else None), self.flow_head(net)
 
 
+class FusedFeatureEncoder:
+    """``BasicEncoder`` with ``norm_fn='instance'`` (RAFT's feature network, extractor.py:118-190) for the mixed-precision
+    inference path, on f16 channels-last activations: the convolutions are cuDNN's tensor-core kernels on NHWC tensors
+    (no layout transforms, no separate bias kernels -- a per-channel bias in front of an affine-free instance norm cancels
+    exactly and is dropped), and every ``norm -> relu [-> + shortcut -> relu]`` is one statistics + one transform launch
+    of ``cwm_instnorm_f16`` instead of autocast's norm / bias / relu / add / layout kernels.  Same arithmetic as the
+    module it wraps up to f16 rounding of the activations (which autocast applies as well)."""
+
+    def __init__(self, enc, device):
+        assert isinstance(enc, BasicEncoder) and enc.norm_fn == 'instance'
+
+        def w16(conv):
+            return conv.weight.detach().to(device=device, dtype=torch.float16).contiguous(memory_format=torch.channels_last)
+
+        self.stem = (w16(enc.conv1), enc.conv1.stride, enc.conv1.padding)
+        self.blocks = []
+        for layer in (enc.layer1, enc.layer2, enc.layer3):
+            for blk in layer:
+                down = None if blk.downsample is None else (w16(blk.downsample[0]), blk.downsample[0].stride)
+                self.blocks.append((w16(blk.conv1), blk.conv1.stride, w16(blk.conv2), down))
+        self.w_out = w16(enc.conv2)
+        self.b_out = enc.conv2.bias.detach().to(device=device, dtype=torch.float16)
+        self.eps = 1e-5
+        self._ws = None
+
+    def _norm(self, y, relu_inner, add=None, relu_outer=False):
+        """y: channels-last f16 [S, C, H, W] -> same layout."""
+        lib = _lib.load()
+        S, C, H, W = y.shape
+        assert y.is_contiguous(memory_format=torch.channels_last) and y.dtype == torch.float16
+        need = lib.cwm_instnorm_workspace_bytes(S, C)
+        if self._ws is None or self._ws.numel() < need or self._ws.device != y.device:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=y.device)
+        out = torch.empty_like(y)
+        if add is not None:
+            assert add.shape == y.shape and add.is_contiguous(memory_format=torch.channels_last)
+        _lib.check(lib.cwm_instnorm_f16(y.data_ptr(), S, H * W, C, self.eps, int(relu_inner),
+                                        None if add is None else add.data_ptr(), int(relu_outer), out.data_ptr(),
+                                        self._ws.data_ptr(), self._ws.numel(), _stream(y)))
+        return out
+
+    @staticmethod
+    def _cl(t):
+        return t if t.is_contiguous(memory_format=torch.channels_last) else t.contiguous(memory_format=torch.channels_last)
+
+    def __call__(self, x):
+        """x fp32 / f16 [S, 3, H, W] -> f16 [S, 256, H/8, W/8] (channels-last strides)."""
+        with torch.cuda.device(x.device):
+            w, stride, pad = self.stem
+            y = self._cl(F.conv2d(x.to(torch.float16).contiguous(memory_format=torch.channels_last), w, None, stride, pad))
+            y = self._norm(y, relu_inner=True)
+            for w1, s1, w2, down in self.blocks:
+                z = self._norm(self._cl(F.conv2d(y, w1, None, s1, 1)), relu_inner=True)
+                z = self._cl(F.conv2d(z, w2, None, 1, 1))
+                if down is not None:
+                    y = self._norm(self._cl(F.conv2d(y, down[0], None, down[1], 0)), relu_inner=False)
+                y = self._norm(z, relu_inner=True, add=y, relu_outer=True)     # relu(x + relu(norm2(conv2(.))))
+            return F.conv2d(y, self.w_out, self.b_out)
+
+
 class FusedBasicUpdate:
     """``BasicUpdateBlock`` (update.py:115-139) for the mixed-precision path, on f16 pixel-major rows ``[M = N*H*W, C]``:
     cuDNN convolutions WITHOUT bias on channels-last views of those rows, and everything between them -- bias, relu,
@@ -649,6 +709,15 @@ class RAFT(nn.Module):
             cached = self._half_ub
         return cached[1]
 
+    def _fused_feature_encoder(self):
+        key = tuple((p.data_ptr(), p._version) for p in self.fnet.parameters())
+        cached = getattr(self, '_fused_fnet', None)
+        if cached is None or cached[0] != key:
+            device = next(self.fnet.parameters()).device
+            object.__setattr__(self, '_fused_fnet', (key, FusedFeatureEncoder(self.fnet, device)))
+            cached = self._fused_fnet
+        return cached[1]
+
     def _fused_update_block(self):
         key = tuple((p.data_ptr(), p._version) for p in self.update_block.parameters())
         cached = getattr(self, '_fused_ub', None)
@@ -670,8 +739,14 @@ class RAFT(nn.Module):
         N = max(n1, n2)
         assert n1 in (1, N) and n2 in (1, N), (image1.shape, image2.shape)
         amp = bool(self.args.mixed_precision or image1.dtype in (torch.float16, torch.bfloat16))
-        with torch.autocast("cuda", enabled=amp):
-            fmaps = self.fnet(torch.cat([image1, image2], dim=0))  # both frames in one batch (raft_model.py:221-222)
+        fused_fnet = (amp and test_mode and isinstance(self.fnet, BasicEncoder) and self.fnet.norm_fn == 'instance'
+                      and bool(getattr(self.args, 'fused_encoder', True)) and os.environ.get("CWM_RAFT_ENCODER", "fused") != "eager")
+        if fused_fnet:
+            # f16 channels-last activations, cuDNN convolutions, instance norm + relu (+ shortcut) in cwm_instnorm_f16
+            fmaps = self._fused_feature_encoder()(torch.cat([image1, image2], dim=0))
+        else:
+            with torch.autocast("cuda", enabled=amp):
+                fmaps = self.fnet(torch.cat([image1, image2], dim=0))  # both frames in one batch (raft_model.py:221-222)
         fmap1 = fmaps[:n1].float().expand(N, -1, -1, -1)
         fmap2 = fmaps[n1:].float().expand(N, -1, -1, -1)
         corr_fn = CorrBlock(fmap1, fmap2, num_levels=self.args.corr_levels, radius=self.args.corr_radius)

@@ -470,6 +470,13 @@ int cwm_conv2d_gru_update_f16(const uint16_t* x, int ldx, int S, int H, int W, i
 int cwm_raft_im2col_flow(const uint16_t* flow16, int ldf, int B, int H, int W, int k, uint16_t* out, int ldo,
                          cwm_stream_t stream);
 
+/* Instance normalisation of NHWC f16 maps fused with what follows it in RAFT's feature encoder (extractor.py:118-190,
+ * nn.InstanceNorm2d: no affine, biased variance): out = relu_outer?( add? + relu_inner?( (x - mean[s,c]) * rstd[s,c] ) ).
+ * x / add / out: [S, HW, C] f16, C % 8 == 0; fp32 statistics over the HW pixels of every (sample, channel). */
+size_t cwm_instnorm_workspace_bytes(int S, int C);
+int cwm_instnorm_f16(const uint16_t* x, int S, int HW, int C, float eps, int relu_inner, const uint16_t* add, int relu_outer,
+                     uint16_t* out, void* workspace, size_t workspace_bytes, cwm_stream_t stream);
+
 /* ---- masks on device with a counter-based RNG (csrc/masks.cu) --------------------------------------
  * Opt-in stand-ins for the reference's host-side mask generation (cwm/models/masking.py:347-401 MaskingGenerator.
  * sample_mask_per_frame, :478-545 RotatedTableUniformMaskingGenerator; sampling.py:63-90 EnergySamplingMaskingGenerator;

@@ -680,3 +680,50 @@ def test_gpu_corr_volume_on_tensor_cores_keeps_fp32_accuracy(B, D, H, W, monkeyp
     e_tc, e_simt = (tc.double() - want).abs().max().item() / scale, (simt.double() - want).abs().max().item() / scale
     print(f"corr volume B={B} D={D} {H}x{W}: tensor cores {e_tc:.2e} of scale, fp32 SIMT {e_simt:.2e}")
     assert e_tc <= 5e-6 and e_simt <= 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("S,H,W,C", [(3, 28, 28, 128), (5, 56, 56, 96), (2, 112, 112, 64), (65, 9, 7, 8)])
+def test_gpu_instance_norm_kernel_matches_torch(S, H, W, C):
+    """`cwm_instnorm_f16`: nn.InstanceNorm2d (no affine, eps 1e-5) on NHWC f16 maps with the fused relu / shortcut add /
+    relu, against torch's fp32 instance norm of the same f16-rounded input."""
+    from counterfactualworldmodels_b200 import raft
+    g = torch.Generator().manual_seed(S + C)
+    x = (torch.randn(S, C, H, W, generator=g) * 2 + torch.randn(1, C, 1, 1, generator=g)).half()
+    add = torch.randn(S, C, H, W, generator=g).half()
+    enc = raft.FusedFeatureEncoder.__new__(raft.FusedFeatureEncoder)
+    enc.eps, enc._ws = 1e-5, None
+    cl = lambda t: t.to(DEV).contiguous(memory_format=torch.channels_last)            # noqa: E731
+    ref = torch.nn.functional.instance_norm(x.float(), eps=1e-5)
+    got = enc._norm(cl(x), relu_inner=False).float().cpu()
+    assert (got - ref).abs().max().item() <= 4e-3
+    got = enc._norm(cl(x), relu_inner=True).float().cpu()
+    assert (got - ref.relu()).abs().max().item() <= 4e-3
+    got = enc._norm(cl(x), relu_inner=True, add=cl(add), relu_outer=True).float().cpu()
+    assert (got - (add.float() + ref.relu()).relu()).abs().max().item() <= 6e-3
+    again = enc._norm(cl(x), relu_inner=True, add=cl(add), relu_outer=True).float().cpu()
+    assert torch.equal(got, again)                                                       # deterministic reduction order
+
+
+@pytest.mark.gpu
+def test_gpu_fused_feature_encoder_matches_the_autocast_encoder():
+    """`FusedFeatureEncoder` (f16 channels-last activations, cuDNN convolutions without bias, cwm_instnorm_f16) against
+    the module it wraps: fp32 reference, and no further from it than plain autocast is."""
+    from counterfactualworldmodels_b200 import raft
+    model = _mirror(False).to(DEV)
+    g = torch.Generator().manual_seed(1)
+    x = (2 * torch.rand(5, 3, 224, 224, generator=g) - 1).to(DEV)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        want = model.fnet(x).float()
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    with torch.autocast("cuda"):
+        amp = model.fnet(x).float()
+    got = raft.FusedFeatureEncoder(model.fnet, DEV)(x).float()
+    assert got.shape == want.shape == (5, 256, 28, 28)
+    scale = want.abs().max().item()
+    e_fused, e_amp = (got - want).abs().max().item() / scale, (amp - want).abs().max().item() / scale
+    print(f"feature encoder: fused {e_fused:.2e} of scale, autocast {e_amp:.2e}")
+    assert e_fused <= 1e-2 and e_fused <= 3 * e_amp + 1e-3
