@@ -30,7 +30,8 @@ EXPORTED_SYMBOLS = (
     "cwm_conv2d_weight_k", "cwm_conv2d_f16", "cwm_raft_im2col_flow", "cwm_conv2d_gru_gate_f16",
     "cwm_conv2d_gru_update_f16",
     "cwm_raft_corr_tc_workspace_bytes", "cwm_raft_corr_volume_tc", "cwm_raft_corr_pyramid_tc",
-    "cwm_instnorm_workspace_bytes", "cwm_instnorm_f16",
+    "cwm_instnorm_workspace_bytes", "cwm_instnorm_f16", "cwm_conv2d_strided_f16", "cwm_im2col_nchw_f16", "cwm_add_act_f16",
+    "cwm_conv2d_dual_f16", "cwm_raft_flow_update_taps",
     "cwm_philox4x32_10", "cwm_mask_uniform", "cwm_mask_energy_table", "cwm_mask_energy_sample",
     "cwm_mask_rectangularize_workspace_bytes", "cwm_mask_rectangularize",
     # tuning hooks (header section "tuning hooks")
@@ -190,6 +191,15 @@ def _declare(lib):
                                             c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]
     lib.cwm_conv2d_gru_update_f16.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
                                               c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]
+    lib.cwm_conv2d_strided_f16.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
+                                           c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]
+    lib.cwm_im2col_nchw_f16.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p,
+                                        c_int, c_void_p]
+    lib.cwm_add_act_f16.argtypes = [c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p]
+    lib.cwm_conv2d_dual_f16.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                        c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]
+    lib.cwm_raft_flow_update_taps.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                                              c_void_p, c_int, c_void_p]
     lib.cwm_raft_im2col_flow.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]
     lib.cwm_instnorm_workspace_bytes.argtypes = [c_int, c_int]
     lib.cwm_instnorm_workspace_bytes.restype = c_size_t

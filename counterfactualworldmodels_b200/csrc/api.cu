@@ -99,7 +99,7 @@ int make_tmap_3d_f32(CUtensorMap* map, const void* base, uint64_t S, uint64_t R,
 }
 
 int make_tmap_nhwc(CUtensorMap* map, const void* base, uint64_t S, uint64_t H, uint64_t W, uint64_t C, uint64_t ld,
-                   uint32_t box_h, uint32_t box_w, uint32_t box_c) {
+                   uint32_t box_h, uint32_t box_w, uint32_t box_c, uint32_t pixel_stride) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return fail(CWM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 2) % 16 != 0 || ld < C)
@@ -110,7 +110,7 @@ int make_tmap_nhwc(CUtensorMap* map, const void* base, uint64_t S, uint64_t H, u
   cuuint64_t gdim[4] = {C, W, H, S};
   cuuint64_t gstride[3] = {ld * 2, W * ld * 2, H * W * ld * 2};
   cuuint32_t box[4] = {box_c, box_w, box_h, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  cuuint32_t estr[4] = {1, pixel_stride, pixel_stride, 1};  // traversal stride: a box of b pixels loads ceil(b / stride)
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

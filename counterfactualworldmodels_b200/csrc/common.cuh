@@ -48,9 +48,11 @@ int make_tmap_2d(CUtensorMap* map, const void* base, int dtype, uint64_t rows, u
                  uint32_t box_rows, uint32_t box_cols, int swizzle_bytes = 128);
 // 4-D NHWC f16 tensor [S, H, W, C] whose pixel rows are `ld` elements apart, box [1, box_h, box_w, box_c], 128B swizzle:
 // the implicit-GEMM convolution loads one (tap, channel slab) A tile with it -- coordinates may be negative or run past
-// the image, out-of-range elements are zero-filled by the TMA unit (= the convolution's zero padding).
+// the image, out-of-range elements are zero-filled by the TMA unit (= the convolution's zero padding).  pixel_stride = 2
+// makes it a strided view (the map's traversal stride): box_h / box_w then count INPUT pixels and the box delivers every
+// second one (a stride-2 convolution's operand).
 int make_tmap_nhwc(CUtensorMap* map, const void* base, uint64_t S, uint64_t H, uint64_t W, uint64_t C, uint64_t ld,
-                   uint32_t box_h, uint32_t box_w, uint32_t box_c);
+                   uint32_t box_h, uint32_t box_w, uint32_t box_c, uint32_t pixel_stride = 1);
 // 3-D fp32 tensor [S, R, C] (C contiguous), box [1, box_rows, box_cols], 128B swizzle (box_cols * 4 <= 128).
 int make_tmap_3d_f32(CUtensorMap* map, const void* base, uint64_t S, uint64_t R, uint64_t C, uint32_t box_rows,
                      uint32_t box_cols);

@@ -79,6 +79,8 @@ struct EpiDev {
   // convolution post-ops of RAFT's ConvGRU (cwm/models/raft/update.py:43-60), evaluated on the fp32 accumulators:
   //   1 = gate:   columns [0, C): z = sigmoid(v) -> out;  columns [C, 2C): sigmoid(v) * h -> out2 (column n - C)
   //   2 = update: h + z * (tanh(v) - h) -> out (h's own slot, in place) and, when out2 is given, a dense copy
+  //   3 = tail:   the last two output columns are replaced by the 2 f16 at aux_h[row * ld_h] (the flow columns that close
+  //               the GRU input rows; out2 = the second row buffer)
   // h / z are f16 pixel rows (aux_h, aux_z); out2 is the kernel's second output tensor map.
   int post;
   int post_c;
@@ -89,7 +91,14 @@ struct EpiDev {
   int has_out2;
   int img_h, img_w, img_s;
 };
-__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+// one MUFU each: tanh.approx.f32 (max relative error 2^-11, the rounding of the f16 the result is stored as) and
+// sigmoid(x) = 0.5 tanh(x / 2) + 0.5
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
 __device__ __forceinline__ void h8_unpack(const uint4& u, float* f) {
   const __half2* h = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
@@ -109,7 +118,11 @@ struct ConvDev {
   int kw;
   int pad_h, pad_w;
   int cin_slabs;      // 64-channel slabs per tap (K = taps * cin_slabs * 64, weights zero-padded to that)
-  int tiles_per_img;  // ceil(H / hb)
+  int tiles_per_img;  // tiles_x * ceil(Hout / hb)
+  int tiles_x;        // column blocks of wb pixel slots per image row (1 for maps of <= 32 pixels; the encoders' 56 / 112
+                      // pixel maps are tiled in both directions)
+  int stride;         // 1 or 2: output pixel (y, x) reads input (stride * y + ky - pad_h, stride * x + kx - pad_w); the A
+                      // tensor map then carries the traversal stride (one box still loads hb x wb pixels)
   int hb;             // image rows per 128-row tile
   int rows_per_warp;  // image rows per 32-row epilogue chunk (32 / wb)
   // halo mode (W + 2 pad_w <= wb): per channel slab ONE box of hb + kh - 1 image rows is staged, each row laid out as
@@ -434,7 +447,10 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       // convolution mode: this CTA's 128-row tile = image rows [cy0, cy0 + hb) of sample cs
       const int ct = m_blk * (kCta2 ? 2 : 1) + cta_rank;
       const int cs = (kConv && cv.taps) ? ct / cv.tiles_per_img : 0;
-      const int cy0 = (kConv && cv.taps) ? (ct - cs * cv.tiles_per_img) * cv.hb : 0;
+      const int cti = (kConv && cv.taps) ? ct - cs * cv.tiles_per_img : 0;
+      const int cty = (kConv && cv.taps) ? cti / cv.tiles_x : 0;
+      const int cy0 = cty * cv.hb * cv.stride - cv.pad_h;                 // input coordinates of the tile's first pixel
+      const int cx0 = (cti - cty * cv.tiles_x) * cv.wb * cv.stride - cv.pad_w;
       int tap = 0, slab = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -445,7 +461,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
             if (kConv && cv.taps) {
               const int dy = tap / cv.kw;
               tma_load_4d_2sm(smem_a + stage * Cfg::kABytes, &tma_a, &full_bar[stage], slab * BK,
-                              tap - dy * cv.kw - cv.pad_w, cy0 + dy - cv.pad_h, cs);
+                              cx0 + tap - dy * cv.kw, cy0 + dy, cs);
             } else {
               tma_load_2d_2sm(smem_a + stage * Cfg::kABytes, &tma_a, &full_bar[stage], kb * BK, m_blk * TM + cta_rank * BM);
             }
@@ -455,8 +471,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
             if (kConv && cv.taps) {
               const int dy = tap / cv.kw;
-              tma_load_4d(smem_a + stage * Cfg::kABytes, &tma_a, &full_bar[stage], slab * BK, tap - dy * cv.kw - cv.pad_w,
-                          cy0 + dy - cv.pad_h, cs);
+              tma_load_4d(smem_a + stage * Cfg::kABytes, &tma_a, &full_bar[stage], slab * BK, cx0 + tap - dy * cv.kw,
+                          cy0 + dy, cs);
             } else {
               tma_load_2d(smem_a + stage * Cfg::kABytes, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
             }
@@ -641,7 +657,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
           const int ct = m_blk * (kCta2 ? 2 : 1) + cta_rank;
           const int cs = ct / cv.tiles_per_img;
           const int tr = quad * 32 + lane;
-          const int py = (ct - cs * cv.tiles_per_img) * cv.hb + tr / cv.wb, px = tr % cv.wb;
+          const int cti = ct - cs * cv.tiles_per_img, cty = cti / cv.tiles_x;
+          const int py = cty * cv.hb + tr / cv.wb, px = (cti - cty * cv.tiles_x) * cv.wb + tr % cv.wb;
           if (cs < ep.img_s && py < ep.img_h && px < ep.img_w)
             post_row = (static_cast<long long>(cs) * ep.img_h + py) * ep.img_w + px;
         }
@@ -668,6 +685,26 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
           if (ln) {
             sts32(lns_s + lane * 4, __float_as_uint(s_lo));
             sts32(lns_s + 128 + lane * 4, __float_as_uint(s_hi));
+          }
+          // ConvGRU post-ops: h (and z) of this thread's pixel row for the chunk's 64 columns, fetched as a 4-deep ring of
+          // 16-byte loads that is primed here, before the accumulator wait, and refilled 4 units ahead in the loop
+          uint4 h_raw[4], z_raw[4];
+          const uint4* h_ptr = nullptr;
+          const uint4* z_ptr = nullptr;
+          bool post_ld_h = false;
+          if (kConv && (ep.post == 1 || ep.post == 2)) {
+            const int hc = (ep.post == 1) ? n0 - ep.post_c : n0;   // gate: only the r columns [C, 2C) read h
+            post_ld_h = post_row >= 0 && hc >= 0;
+            if (post_ld_h) {
+              h_ptr = reinterpret_cast<const uint4*>(ep.aux_h + post_row * ep.ld_h + hc);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) h_raw[q] = __ldg(h_ptr + q);
+              if (ep.post == 2) {
+                z_ptr = reinterpret_cast<const uint4*>(ep.aux_z + post_row * ep.ld_z + n0);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) z_raw[q] = __ldg(z_ptr + q);
+              }
+            }
           }
           tmem_ld_wait();
           const bool last_chunk = (c + 2 >= kChunks);
@@ -724,30 +761,36 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
               for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
             }
             if (kConv && ep.post == 1) {          // GRU gate
-              const bool is_r = n0 >= ep.post_c;
               float hh[8];
-              if (is_r && post_row >= 0) {
-                h8_unpack(__ldg(reinterpret_cast<const uint4*>(ep.aux_h + post_row * ep.ld_h + (n0 - ep.post_c) + u * 8)), hh);
+              if (post_ld_h) {
+                h8_unpack(h_raw[u & 3], hh);
+                if (u + 4 < 8) h_raw[u & 3] = __ldg(h_ptr + u + 4);   // 4 units ahead (the smem store below fences the compiler)
               } else {
 #pragma unroll
-                for (int q = 0; q < 8; ++q) hh[q] = is_r ? 0.f : 1.f;
+                for (int q = 0; q < 8; ++q) hh[q] = (n0 >= ep.post_c) ? 0.f : 1.f;
               }
 #pragma unroll
               for (int q = 0; q < 8; ++q) v[q] = sigmoid_fast(v[q]) * hh[q];
             } else if (kConv && ep.post == 2) {   // GRU update
               float hh[8], zz[8];
-              if (post_row >= 0) {
-                h8_unpack(__ldg(reinterpret_cast<const uint4*>(ep.aux_h + post_row * ep.ld_h + n0 + u * 8)), hh);
-                h8_unpack(__ldg(reinterpret_cast<const uint4*>(ep.aux_z + post_row * ep.ld_z + n0 + u * 8)), zz);
+              if (post_ld_h) {
+                h8_unpack(h_raw[u & 3], hh);
+                h8_unpack(z_raw[u & 3], zz);
+                if (u + 4 < 8) {
+                  h_raw[u & 3] = __ldg(h_ptr + u + 4);
+                  z_raw[u & 3] = __ldg(z_ptr + u + 4);
+                }
               } else {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) hh[q] = zz[q] = 0.f;
               }
 #pragma unroll
-              for (int q = 0; q < 8; ++q) v[q] = (1.f - zz[q]) * hh[q] + zz[q] * tanhf(v[q]);
+              for (int q = 0; q < 8; ++q) v[q] = fmaf(zz[q], tanh_fast(v[q]) - hh[q], hh[q]);   // (1 - z) h + z tanh(v)
             }
-            sts128(buf0 + row_s + ((u ^ sw) << 4), pack_half2(v[0], v[1]), pack_half2(v[2], v[3]),
-                   pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
+            uint32_t last2 = pack_half2(v[6], v[7]);
+            if (kConv && ep.post == 3 && n0 + u * 8 + 8 == N)   // tail: the last two columns carry 2 f16 of another row buffer
+              last2 = post_row >= 0 ? __ldg(reinterpret_cast<const uint32_t*>(ep.aux_h + post_row * ep.ld_h)) : 0u;
+            sts128(buf0 + row_s + ((u ^ sw) << 4), pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), last2);
           }
           fence_proxy_async_smem();
           __syncwarp();
@@ -755,12 +798,13 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
             if (kConv && cv.taps) {  // this warp's 32 rows = rows_per_warp image rows of wb pixel slots; slots past the width are clipped
               const int ct = m_blk * (kCta2 ? 2 : 1) + cta_rank;
               const int cs = ct / cv.tiles_per_img;
-              const int sy = (ct - cs * cv.tiles_per_img) * cv.hb + quad * cv.rows_per_warp;
+              const int cti = ct - cs * cv.tiles_per_img, cty = cti / cv.tiles_x;
+              const int sy = cty * cv.hb + quad * cv.rows_per_warp, sx = (cti - cty * cv.tiles_x) * cv.wb;
               if (ep.post == 1 && n0 >= ep.post_c) {
-                tma_store_4d(&tma_res, buf0, n0 - ep.post_c, 0, sy, cs);      // r * h -> the q convolution's input slot
+                tma_store_4d(&tma_res, buf0, n0 - ep.post_c, sx, sy, cs);      // r * h -> the q convolution's input slot
               } else {
-                tma_store_4d(&tma_out, buf0, n0, 0, sy, cs);
-                if (ep.post == 2 && ep.has_out2) tma_store_4d(&tma_res, buf0, n0, 0, sy, cs);   // dense copy of h
+                tma_store_4d(&tma_out, buf0, n0, sx, sy, cs);
+                if (ep.post != 1 && ep.has_out2) tma_store_4d(&tma_res, buf0, n0, sx, sy, cs);   // second destination (GRU update: the dense copy of h)
               }
             } else {
               tma_store_2d(&tma_out, buf0, n0, row0);
@@ -1040,7 +1084,7 @@ static int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tw, const 
 template <int BN, bool kRes, bool kConv = false>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const CUtensorMap& tr,
                        const CUtensorMap& tx, int M, int N, int K, const EpiDev& ep, cudaStream_t stream, bool cta2,
-                       const ConvDev& cv = ConvDev{0, 1, 0, 0, 1 << 30, 1, 1, 1, 0, 0, 32, 1, 0, 0}) {
+                       const ConvDev& cv = ConvDev{0, 1, 0, 0, 1 << 30, 1, 1, 1, 1, 1, 0, 0, 32, 1, 0, 0}) {
   if (cta2) return launch_gemm_impl<BN, kRes, true, kConv>(ta, tw, to, tr, tx, M, N, K, ep, stream, cv);
   return launch_gemm_impl<BN, kRes, false, kConv>(ta, tw, to, tr, tx, M, N, K, ep, stream, cv);
 }
@@ -1173,18 +1217,33 @@ struct ConvPost {
 
 static int conv2d_impl(const uint16_t* x, int ldx, int S, int H, int W, int Cin, const uint16_t* w_packed, int Cout, int kh,
                        int kw, int pad_h, int pad_w, const float* bias, int relu, uint16_t* out, int ldo, int out_cols,
-                       const ConvPost& post, cwm_stream_t stream) {
+                       const ConvPost& post, cwm_stream_t stream, int stride = 1) {
   CWM_REQUIRE(x && w_packed && out, "cwm_conv2d_f16: null pointer");
   CWM_REQUIRE(S >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && kh > 0 && kw > 0, "cwm_conv2d_f16: bad shape");
-  CWM_REQUIRE(W <= 32, "cwm_conv2d_f16: image width %d > 32 (one 128-row tile holds whole image rows of <= 32 pixels)", W);
-  CWM_REQUIRE(kh == 2 * pad_h + 1 && kw == 2 * pad_w + 1, "cwm_conv2d_f16: only stride-1 'same' convolutions (k = 2 pad + 1)");
+  CWM_REQUIRE(stride == 1 || stride == 2, "cwm_conv2d_f16: stride %d (1 or 2)", stride);
+  CWM_REQUIRE(kh == 2 * pad_h + 1 && kw == 2 * pad_w + 1, "cwm_conv2d_f16: only 'same'-padded convolutions (k = 2 pad + 1)");
   CWM_REQUIRE(Cin % 8 == 0 && ldx % 8 == 0 && ldx >= Cin && ldo % 8 == 0 && ldo >= out_cols && Cout % 8 == 0,
               "cwm_conv2d_f16: channel counts and row strides must be multiples of 8 (16-byte rows)");
   if (S == 0) return CWM_OK;
-  const int wb = W <= 16 ? 16 : 32, hb = BM / wb;
+  // output map (torch.nn.Conv2d with padding = k // 2): (H + 2 pad - k) / stride + 1 = (H - 1) / stride + 1
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  CWM_REQUIRE(post.post == 0 || (Wo <= 32 && stride == 1), "cwm_conv2d_gru_*: maps of at most 32 pixels, stride 1");
+  // a 128-row tile = hb image rows of wb pixel slots.  Maps of <= 32 pixels: one column block (wb = 16 / 32 >= Wo); wider
+  // maps are tiled in both directions with the wb in {8, 16, 32} that wastes the fewest slots (ties: the widest)
+  int wb = Wo <= 16 ? 16 : 32;
+  if (Wo > 32) {
+    long long best = -1;
+    for (int cand = 32; cand >= 8; cand >>= 1) {
+      const int hbc = BM / cand;
+      const long long area = static_cast<long long>((Wo + cand - 1) / cand) * cand * ((Ho + hbc - 1) / hbc) * hbc;
+      if (best < 0 || area < best) { best = area; wb = cand; }
+    }
+  }
+  const int hb = BM / wb;
   ConvDev cv;
   cv.taps = kh * kw; cv.kw = kw; cv.pad_h = pad_h; cv.pad_w = pad_w; cv.cin_slabs = (Cin + BK - 1) / BK;
-  cv.tiles_per_img = (H + hb - 1) / hb; cv.hb = hb; cv.rows_per_warp = 32 / wb;
+  cv.tiles_x = (Wo + wb - 1) / wb; cv.stride = stride;
+  cv.tiles_per_img = cv.tiles_x * ((Ho + hb - 1) / hb); cv.hb = hb; cv.rows_per_warp = 32 / wb;
   const int bn = pick_bn(Cout);
   // halo mode: every image row with its zero padding fits one row of wb pixel slots, and there is more than one tap
   static int halo_env = -1;
@@ -1196,7 +1255,8 @@ static int conv2d_impl(const uint16_t* x, int ldx, int S, int H, int W, int Cin,
   // one more row when the right-most taps of the right-most pixels read past their row's end (slot W - 1 + kw - 1 + pad_w
   // >= wb): they land on the NEXT row's leading zero slots, which must exist for the last row of the box too
   cv.halo_rows = hb + kh - 1 + ((W + 3 * pad_w > wb) ? 1 : 0);
-  cv.halo = (halo_env != 0 && cv.taps > 1 && W + 2 * pad_w <= wb && cv.halo_rows * wb * 128 <= kHaloStageBytes) ? 1 : 0;
+  cv.halo = (halo_env != 0 && cv.taps > 1 && stride == 1 && cv.tiles_x == 1 && W + 2 * pad_w <= wb &&
+             cv.halo_rows * wb * 128 <= kHaloStageBytes) ? 1 : 0;
   cv.w_stages = 2;
   cv.w_stride = 0;
   {
@@ -1214,24 +1274,27 @@ static int conv2d_impl(const uint16_t* x, int ldx, int S, int H, int W, int Cin,
   ep.ln_inv_c = 0.f; ep.ln_eps = 0.f; ep.relu = relu ? 1 : 0;
   ep.post = post.post; ep.post_c = post.C; ep.aux_h = reinterpret_cast<const __half*>(post.h); ep.ld_h = post.ldh;
   ep.aux_z = reinterpret_cast<const __half*>(post.z); ep.ld_z = post.ldz; ep.has_out2 = post.out2 != nullptr;
-  ep.img_h = H; ep.img_w = W; ep.img_s = S;
+  ep.img_h = Ho; ep.img_w = Wo; ep.img_s = S;
   const bool cta2 = g_gemm_cta2 != 0 && bn >= 128 && M >= 2 * BM;
   CUtensorMap ta, tw, to;
-  int rc = make_tmap_nhwc(&ta, x, S, H, W, Cin, ldx, cv.halo ? cv.halo_rows : hb, wb, BK);
+  // stride 2: the box spans 2 hb x 2 wb input pixels and the map's traversal stride picks every second one
+  int rc = make_tmap_nhwc(&ta, x, S, H, W, Cin, ldx, cv.halo ? cv.halo_rows : hb * stride, wb * stride, BK, stride);
   if (rc) return rc;
   rc = make_tmap_2d(&tw, w_packed, CWM_TMAP_F16, Cout, K, K, cta2 ? bn / 2 : bn, BK);
   if (rc) return rc;
-  rc = make_tmap_nhwc(&to, out, S, H, W, out_cols, ldo, cv.rows_per_warp, wb, 64);
+  rc = make_tmap_nhwc(&to, out, S, Ho, Wo, out_cols, ldo, cv.rows_per_warp, wb, 64);
   if (rc) return rc;
   CUtensorMap to2 = to;
   if (post.out2 != nullptr) {
-    rc = make_tmap_nhwc(&to2, post.out2, S, H, W, post.out2_cols, post.ldo2, cv.rows_per_warp, wb, 64);
+    rc = make_tmap_nhwc(&to2, post.out2, S, Ho, Wo, post.out2_cols, post.ldo2, cv.rows_per_warp, wb, 64);
     if (rc) return rc;
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  ProfileScope prof(s, post.post == 1 ? "conv2d_gru_gate" : (post.post == 2 ? "conv2d_gru_update" : "conv2d_f16"),
-                    2.0 * S * H * W * static_cast<double>(Cout) * cv.taps * Cin,
-                    static_cast<double>(S) * H * W * (Cin + Cout) * 2.0 + static_cast<double>(Cout) * K * 2.0);
+  ProfileScope prof(s, post.post == 1 ? "conv2d_gru_gate" : (post.post == 2 ? "conv2d_gru_update" :
+                                                                (Wo > 32 || stride > 1 ? "conv2d_f16_wide" : "conv2d_f16")),
+                    2.0 * S * Ho * Wo * static_cast<double>(Cout) * cv.taps * Cin,
+                    static_cast<double>(S) * (static_cast<double>(H) * W * Cin + static_cast<double>(Ho) * Wo * Cout) * 2.0 +
+                        static_cast<double>(Cout) * K * 2.0);
   switch (bn) {
     case 64: return launch_gemm<64, false, true>(ta, tw, to, to2, to, M, Cout, K, ep, s, cta2, cv);
     case 128: return launch_gemm<128, false, true>(ta, tw, to, to2, to, M, Cout, K, ep, s, cta2, cv);
@@ -1244,6 +1307,27 @@ extern "C" int cwm_conv2d_f16(const uint16_t* x, int ldx, int S, int H, int W, i
                               int kh, int kw, int pad_h, int pad_w, const float* bias, int relu, uint16_t* out, int ldo,
                               cwm_stream_t stream) {
   return conv2d_impl(x, ldx, S, H, W, Cin, w_packed, Cout, kh, kw, pad_h, pad_w, bias, relu, out, ldo, Cout, ConvPost(), stream);
+}
+
+extern "C" int cwm_conv2d_strided_f16(const uint16_t* x, int ldx, int S, int H, int W, int Cin, const uint16_t* w_packed,
+                                      int Cout, int kh, int kw, int pad_h, int pad_w, int stride, const float* bias, int relu,
+                                      uint16_t* out, int ldo, cwm_stream_t stream) {
+  return conv2d_impl(x, ldx, S, H, W, Cin, w_packed, Cout, kh, kw, pad_h, pad_w, bias, relu, out, ldo, Cout, ConvPost(), stream,
+                     stride);
+}
+
+extern "C" int cwm_conv2d_dual_f16(const uint16_t* x, int ldx, int S, int H, int W, int Cin, const uint16_t* w_packed, int Cout,
+                                   int kh, int kw, int pad_h, int pad_w, const float* bias, int relu, const uint16_t* tail,
+                                   int ld_tail, uint16_t* out, int ldo, uint16_t* out2, int ldo2, cwm_stream_t stream) {
+  CWM_REQUIRE(out2 == nullptr || (ldo2 % 8 == 0 && ldo2 >= Cout), "cwm_conv2d_dual_f16: bad second row stride %d", ldo2);
+  CWM_REQUIRE(tail == nullptr || (ld_tail >= 2 && ld_tail % 2 == 0 && (reinterpret_cast<uintptr_t>(tail) & 3) == 0),
+              "cwm_conv2d_dual_f16: tail rows must be 4-byte aligned (ld %d)", ld_tail);
+  ConvPost p;
+  p.out2 = out2; p.ldo2 = ldo2; p.out2_cols = Cout;
+  if (tail != nullptr) {
+    p.post = 3; p.C = Cout; p.h = tail; p.ldh = ld_tail;
+  }
+  return conv2d_impl(x, ldx, S, H, W, Cin, w_packed, Cout, kh, kw, pad_h, pad_w, bias, relu, out, ldo, Cout, p, stream);
 }
 
 extern "C" int cwm_conv2d_gru_gate_f16(const uint16_t* x, int ldx, int S, int H, int W, int Cin, const uint16_t* w_zr, int C,

@@ -111,6 +111,70 @@ instnorm_apply_kernel(const __half* __restrict__ x, const float2* __restrict__ p
   }
 }
 
+// im2col of a few-channel NCHW fp32 image for a strided k x k convolution (the encoders' 7x7 / 2 stem on 3 channels,
+// extractor.py:132): row m = (s, oy, ox) of `out` holds  scale * img[s, c, stride*oy + ky - pad, stride*ox + kx - pad] + shift
+// at column (ky * k + kx) * Cin + c, zeros outside the image (the padding of the already-normalised image) and in the
+// columns [k*k*Cin, ldo).  The convolution is then ONE plain GEMM with K = ldo on the tcgen05 kernel.  One thread = one
+// 16-byte store (8 columns).
+__global__ void __launch_bounds__(256)
+im2col_nchw_kernel(const float* __restrict__ img, int Cin, int H, int W, int Ho, int Wo, int k, int stride, int pad,
+                   float scale, float shift, long long M, __half* __restrict__ out, int ldo) {
+  const int units = ldo >> 3;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= M * units) return;
+  const long long m = idx / units;
+  const int col0 = static_cast<int>(idx - m * units) * 8;
+  const int hw = Ho * Wo;
+  const long long s = m / hw;
+  const int pix = static_cast<int>(m - s * hw);
+  const int y0 = (pix / Wo) * stride - pad, x0 = (pix % Wo) * stride - pad;
+  const float* im = img + s * Cin * static_cast<long long>(H) * W;
+  const int kk = k * k * Cin;
+  float v[8];
+  int tap = col0 / Cin, c = col0 - tap * Cin;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    v[i] = 0.f;
+    if (col0 + i < kk) {
+      const int ky = tap / k;
+      const int y = y0 + ky, x = x0 + tap - ky * k;
+      if (y >= 0 && y < H && x >= 0 && x < W) v[i] = fmaf(__ldg(im + (static_cast<long long>(c) * H + y) * W + x), scale, shift);
+    }
+    if (++c == Cin) {
+      c = 0;
+      ++tap;
+    }
+  }
+  const __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]), h2 = __floats2half2_rn(v[4], v[5]),
+                h3 = __floats2half2_rn(v[6], v[7]);
+  *reinterpret_cast<uint4*>(out + m * ldo + col0) =
+      make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
+                 *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
+}
+
+// out = relu?(a + b) on f16 rows (the residual joins of the batch-norm context encoder, whose norms are folded into the
+// convolution weights: extractor.py:46-56)
+__global__ void __launch_bounds__(256)
+add_act_f16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, long long n16, int relu, uint4* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n16) return;
+  float fa[8], fb[8];
+  h8_to_f32(__ldg(a + i), fa);
+  h8_to_f32(__ldg(b + i), fb);
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float x0 = fa[2 * j] + fb[2 * j], x1 = fa[2 * j + 1] + fb[2 * j + 1];
+    if (relu) {
+      x0 = fmaxf(x0, 0.f);
+      x1 = fmaxf(x1, 0.f);
+    }
+    const __half2 h = __floats2half2_rn(x0, x1);
+    o[j] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  out[i] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 }  // namespace cwm
 
 using namespace cwm;
@@ -159,5 +223,39 @@ extern "C" int cwm_instnorm_f16(const uint16_t* x, int S, int HW, int C, float e
         relu_outer, ppb, reinterpret_cast<__half*>(out));
     CWM_LAUNCH_CHECK();
   }
+  return CWM_OK;
+}
+
+extern "C" int cwm_im2col_nchw_f16(const float* img, int S, int Cin, int H, int W, int k, int stride, int pad, float scale,
+                                   float shift, uint16_t* out, int ldo, cwm_stream_t stream) {
+  CWM_REQUIRE(S >= 0 && Cin >= 1 && H >= 1 && W >= 1 && k >= 1 && stride >= 1 && pad >= 0 && ldo % 8 == 0 && ldo >= k * k * Cin,
+              "cwm_im2col_nchw_f16: bad shape S=%d Cin=%d H=%d W=%d k=%d stride=%d pad=%d ldo=%d", S, Cin, H, W, k, stride, pad, ldo);
+  if (S == 0) return CWM_OK;
+  CWM_REQUIRE(img && out && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "cwm_im2col_nchw_f16: null or misaligned pointer");
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  CWM_REQUIRE(Ho >= 1 && Wo >= 1, "cwm_im2col_nchw_f16: empty output");
+  const long long M = static_cast<long long>(S) * Ho * Wo;
+  const long long threads = M * (ldo / 8);
+  CWM_REQUIRE((threads + 255) / 256 < (1ll << 31), "cwm_im2col_nchw_f16: too many rows");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfileScope prof(st, "im2col_nchw", 0.0, static_cast<double>(M) * ldo * 2.0 + static_cast<double>(S) * Cin * H * W * 4.0);
+  cwm::im2col_nchw_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(
+      img, Cin, H, W, Ho, Wo, k, stride, pad, scale, shift, M, reinterpret_cast<__half*>(out), ldo);
+  CWM_LAUNCH_CHECK();
+  return CWM_OK;
+}
+
+extern "C" int cwm_add_act_f16(const uint16_t* a, const uint16_t* b, long long n, int relu, uint16_t* out, cwm_stream_t stream) {
+  CWM_REQUIRE(n >= 0 && n % 8 == 0, "cwm_add_act_f16: element count %lld must be a multiple of 8", n);
+  if (n == 0) return CWM_OK;
+  CWM_REQUIRE(a && b && out, "cwm_add_act_f16: null pointer");
+  CWM_REQUIRE(((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+              "cwm_add_act_f16: tensors must be 16-byte aligned");
+  const long long n16 = n / 8;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfileScope prof(st, "add_act_f16", 0.0, static_cast<double>(n) * 6.0);
+  cwm::add_act_f16_kernel<<<static_cast<unsigned>((n16 + 255) / 256), 256, 0, st>>>(
+      reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b), n16, relu, reinterpret_cast<uint4*>(out));
+  CWM_LAUNCH_CHECK();
   return CWM_OK;
 }

@@ -488,6 +488,47 @@ raft_flow_update_kernel(const __half* __restrict__ delta, int ldd, const float* 
   *reinterpret_cast<uint4*>(flow16 + m * 8) = f_to_h8(f);
 }
 
+// The same update with the flow head's last convolution (3x3, 256 -> 2; update.py:13-14) finished here: `taps` [M, ldt]
+// holds, per pixel q, the 18 per-tap products  w[co, :, ky, kx] . fh1[q, :]  at column (ky * 3 + kx) * 2 + co (one 1x1
+// GEMM with N = 18 instead of a 3x3 implicit GEMM whose 64-wide N tile would be 97 % padding), and
+//   delta[p, co] = bias[co] + sum over (ky, kx) of taps[p + (ky - 1, kx - 1)][(ky * 3 + kx) * 2 + co]   (zero outside the image).
+// The new flow is also written (2 f16) into up to two further row buffers: the flow slots of the GRU input rows.
+__global__ void __launch_bounds__(256)
+raft_flow_update_taps_kernel(const __half* __restrict__ taps, int ldt, const float* __restrict__ bias, float* __restrict__ coords1,
+                             int H, int W, long long M, __half* __restrict__ flow16, __half* __restrict__ dst1, int ld1,
+                             __half* __restrict__ dst2, int ld2) {
+  const long long m = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const int HW = H * W;
+  const long long b = m / HW;
+  const int hw = static_cast<int>(m - b * HW);
+  const int y = hw / W, x = hw - y * W;
+  float dx = __ldg(bias), dy = __ldg(bias + 1);
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int yy = y + ky - 1;
+    if (yy < 0 || yy >= H) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int xx = x + kx - 1;
+      if (xx < 0 || xx >= W) continue;
+      const float2 t = __half22float2(*reinterpret_cast<const __half2*>(taps + (b * HW + yy * W + xx) * ldt + (ky * 3 + kx) * 2));
+      dx += t.x;
+      dy += t.y;
+    }
+  }
+  float* cx = coords1 + (b * 2) * HW + hw;
+  float* cy = cx + HW;
+  const float nx = *cx + dx, ny = *cy + dy;
+  *cx = nx;
+  *cy = ny;
+  float f[8] = {nx - static_cast<float>(x), ny - static_cast<float>(y), 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const uint4 o = f_to_h8(f);
+  *reinterpret_cast<uint4*>(flow16 + m * 8) = o;
+  if (dst1 != nullptr) *reinterpret_cast<uint32_t*>(dst1 + m * ld1) = o.x;
+  if (dst2 != nullptr) *reinterpret_cast<uint32_t*>(dst2 + m * ld2) = o.x;
+}
+
 static int level_dims(int H, int W, int L, int* hs, int* ws, const char* who) {
   CWM_REQUIRE(L >= 1 && L <= kMaxLevels, "%s: num_levels %d not in [1, %d]", who, L, kMaxLevels);
   hs[0] = H;
@@ -687,6 +728,25 @@ extern "C" int cwm_raft_flow_update(const uint16_t* delta, int ldd, const float*
   ProfileScope prof(st, "raft_flow_update", 0.0, static_cast<double>(M) * 36.0);
   raft_flow_update_kernel<<<blocks_for(M), 256, 0, st>>>(reinterpret_cast<const __half*>(delta), ldd, bias, coords1, H * W, W, M,
                                                         reinterpret_cast<__half*>(flow16));
+  CWM_LAUNCH_CHECK();
+  return CWM_OK;
+}
+
+extern "C" int cwm_raft_flow_update_taps(const uint16_t* taps, int ldt, const float* bias, float* coords1, int B, int H, int W,
+                                         uint16_t* flow16, uint16_t* dst1, int ld1, uint16_t* dst2, int ld2,
+                                         cwm_stream_t stream) {
+  CWM_REQUIRE(B >= 0 && H >= 1 && W >= 1 && ldt >= 18 && ldt % 2 == 0 && ld1 % 2 == 0 && ld2 % 2 == 0,
+              "cwm_raft_flow_update_taps: bad shape B=%d H=%d W=%d ldt=%d ld1=%d ld2=%d", B, H, W, ldt, ld1, ld2);
+  if (B == 0) return CWM_OK;
+  CWM_REQUIRE(taps && bias && coords1 && flow16 && aligned16(flow16) && (reinterpret_cast<uintptr_t>(taps) & 3) == 0 &&
+                  (reinterpret_cast<uintptr_t>(dst1) & 3) == 0 && (reinterpret_cast<uintptr_t>(dst2) & 3) == 0,
+              "cwm_raft_flow_update_taps: null or misaligned pointer");
+  const long long M = static_cast<long long>(B) * H * W;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfileScope prof(st, "raft_flow_update_taps", 0.0, static_cast<double>(M) * (36.0 + 36.0 + 8.0));
+  raft_flow_update_taps_kernel<<<blocks_for(M), 256, 0, st>>>(reinterpret_cast<const __half*>(taps), ldt, bias, coords1, H, W, M,
+                                                             reinterpret_cast<__half*>(flow16), reinterpret_cast<__half*>(dst1),
+                                                             ld1, reinterpret_cast<__half*>(dst2), ld2);
   CWM_LAUNCH_CHECK();
   return CWM_OK;
 }

@@ -127,10 +127,10 @@ def pack_conv_weight(w):
     return p.reshape(Cout, kh * kw * cin_pad).contiguous()
 
 
-def conv2d_f16(x_rows, S, H, W, weight, bias=None, relu=False, ldo=None, out=None, packed=None):
-    """Stride-1 'same' convolution of NHWC f16 rows ``x_rows [S*H*W, Cin]`` (may be a column slice of a wider buffer) with
-    an nn.Conv2d weight ``[Cout, Cin, kh, kw]`` on the tcgen05 implicit-GEMM kernel -> f16 rows ``[S*H*W, Cout]``
-    (``out``: optional destination, may be a column slice)."""
+def conv2d_f16(x_rows, S, H, W, weight, bias=None, relu=False, ldo=None, out=None, packed=None, stride=1):
+    """'Same'-padded convolution (stride 1 or 2) of NHWC f16 rows ``x_rows [S*H*W, Cin]`` (may be a column slice of a wider
+    buffer) with an nn.Conv2d weight ``[Cout, Cin, kh, kw]`` on the tcgen05 implicit-GEMM kernel -> f16 rows
+    ``[S*Ho*Wo, Cout]`` (``out``: optional destination, may be a column slice)."""
     _req_cuda(x_rows, weight, bias, out)
     lib = _lib.load()
     Cout, Cin, kh, kw = weight.shape
@@ -138,12 +138,30 @@ def conv2d_f16(x_rows, S, H, W, weight, bias=None, relu=False, ldo=None, out=Non
     if packed is None:
         packed = pack_conv_weight(weight)
     assert packed.shape[1] == lib.cwm_conv2d_weight_k(Cin, kh, kw)
+    Mo = S * ((H - 1) // stride + 1) * ((W - 1) // stride + 1)
     if out is None:
-        out = torch.empty(S * H * W, ldo or Cout, dtype=torch.float16, device=x_rows.device)[:, :Cout]
-    assert out.dtype == torch.float16 and out.shape == (S * H * W, Cout) and out.stride(1) == 1
-    _lib.check(lib.cwm_conv2d_f16(x_rows.data_ptr(), x_rows.stride(0), S, H, W, Cin, packed.data_ptr(), Cout, kh, kw, kh // 2,
-                                  kw // 2, None if bias is None else bias.data_ptr(), int(bool(relu)), out.data_ptr(),
-                                  out.stride(0), _stream(x_rows)))
+        out = torch.empty(Mo, ldo or Cout, dtype=torch.float16, device=x_rows.device)[:, :Cout]
+    assert out.dtype == torch.float16 and out.shape == (Mo, Cout) and out.stride(1) == 1
+    args = (None if bias is None else bias.data_ptr(), int(bool(relu)), out.data_ptr(), out.stride(0), _stream(x_rows))
+    if stride == 1 and W <= 32:
+        _lib.check(lib.cwm_conv2d_f16(x_rows.data_ptr(), x_rows.stride(0), S, H, W, Cin, packed.data_ptr(), Cout, kh, kw,
+                                      kh // 2, kw // 2, *args))
+    else:
+        _lib.check(lib.cwm_conv2d_strided_f16(x_rows.data_ptr(), x_rows.stride(0), S, H, W, Cin, packed.data_ptr(), Cout, kh,
+                                              kw, kh // 2, kw // 2, stride, *args))
+    return out
+
+
+def im2col_nchw_f16(img, k, stride, pad, ldo, scale=1.0, shift=0.0):
+    """fp32 NCHW image ``[S, Cin, H, W]`` -> f16 rows ``[S*Ho*Wo, ldo]``: the k x k neighbourhood of every output pixel of a
+    strided convolution in (ky, kx, c) order, ``scale * v + shift`` applied inside the image, zeros outside."""
+    _req_cuda(img)
+    assert img.dtype == torch.float32 and img.is_contiguous() and img.dim() == 4
+    S, Cin, H, W = img.shape
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    out = torch.empty(S * Ho * Wo, ldo, dtype=torch.float16, device=img.device)
+    _lib.check(_lib.load().cwm_im2col_nchw_f16(img.data_ptr(), S, Cin, H, W, k, stride, pad, float(scale), float(shift),
+                                               out.data_ptr(), ldo, _stream(img)))
     return out
 
 

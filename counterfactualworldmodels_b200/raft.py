@@ -17,7 +17,7 @@ import os
 
 import torch
 
-from . import _lib
+from . import _lib, ops
 
 
 def _stream(t):
@@ -364,63 +364,135 @@ class BasicUpdateBlock(nn.Module):
 
 
 class FusedFeatureEncoder:
-    """``BasicEncoder`` with ``norm_fn='instance'`` (RAFT's feature network, extractor.py:118-190) for the mixed-precision
-    inference path, on f16 channels-last activations: the convolutions are cuDNN's tensor-core kernels on NHWC tensors
-    (no layout transforms, no separate bias kernels -- a per-channel bias in front of an affine-free instance norm cancels
-    exactly and is dropped), and every ``norm -> relu [-> + shortcut -> relu]`` is one statistics + one transform launch
-    of ``cwm_instnorm_f16`` instead of autocast's norm / bias / relu / add / layout kernels.  Same arithmetic as the
-    module it wraps up to f16 rounding of the activations (which autocast applies as well)."""
+    """``BasicEncoder`` (RAFT's feature network with ``norm_fn='instance'`` and its context network with ``'batch'``,
+    extractor.py:118-190) for the mixed-precision inference path, on f16 pixel-major rows ``[S*H*W, C]``:
 
-    def __init__(self, enc, device):
-        assert isinstance(enc, BasicEncoder) and enc.norm_fn == 'instance'
+    * every convolution is an implicit GEMM on the repo's tcgen05 kernel (``cwm_conv2d_strided_f16``: 2-D tiles for the
+      112 / 56 pixel maps, stride 2 through the tensor map's traversal stride); the 7x7 / 2 stem on the 3-channel frame is an
+      im2col (``cwm_im2col_nchw_f16``, K = 147 -> 152) followed by the same kernel as a 1x1 convolution;
+    * instance norm: a per-channel bias in front of an affine-free instance norm cancels exactly and is dropped; every
+      ``norm -> relu [-> + shortcut -> relu]`` is one statistics + one transform launch of ``cwm_instnorm_f16``;
+    * batch norm (inference: running statistics) is folded into the convolution weights and biases, relu runs in the
+      convolution epilogue and the residual join is one ``cwm_add_act_f16``.
 
-        def w16(conv):
-            return conv.weight.detach().to(device=device, dtype=torch.float16).contiguous(memory_format=torch.channels_last)
+    ``conv_impl='cudnn'`` (``CWM_RAFT_ENCODER_CONV=cudnn``) keeps round 1's route for A/B runs: cuDNN convolutions on
+    channels-last views of the same rows (instance norm only).  Same arithmetic as the module it wraps up to the f16
+    rounding of the activations (which autocast applies as well)."""
 
-        self.stem = (w16(enc.conv1), enc.conv1.stride, enc.conv1.padding)
+    K_STEM = 152   # 7 * 7 * 3 = 147 im2col columns padded to a multiple of 8 (16-byte rows)
+
+    def __init__(self, enc, device, conv_impl=None):
+        assert isinstance(enc, BasicEncoder) and enc.norm_fn in ('instance', 'batch')
+        self.norm = enc.norm_fn
+        self.conv_impl = conv_impl or (os.environ.get("CWM_RAFT_ENCODER_CONV", "tcgen05") if self.norm == 'instance' else "tcgen05")
+        assert self.conv_impl in ("tcgen05", "cudnn") and (self.conv_impl == "tcgen05" or self.norm == 'instance')
+        self.eps = 1e-5
+
+        def fold(conv, bn):
+            """-> (weight fp32 [Cout, Cin, kh, kw], bias fp32 [Cout] or None) with the batch norm folded in"""
+            w = conv.weight.detach().float()
+            if self.norm == 'instance':
+                return w, None
+            g = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+            return w * g.view(-1, 1, 1, 1), (conv.bias.detach().float() - bn.running_mean.detach().float()) * g + bn.bias.detach().float()
+
+        def pack(conv, bn):
+            w, b = fold(conv, bn)
+            w16 = w.to(device=device, dtype=torch.float16)
+            b = None if b is None else b.to(device).contiguous()
+            if self.conv_impl == "cudnn":
+                return w16.contiguous(memory_format=torch.channels_last), b, conv.kernel_size[0], conv.stride[0]
+            return ops.pack_conv_weight(w16), b, conv.kernel_size[0], conv.stride[0]
+
+        k = enc.conv1.kernel_size[0]
+        assert enc.conv1.in_channels * k * k <= self.K_STEM
+        w, b = fold(enc.conv1, enc.norm1)
+        wk = torch.zeros(w.shape[0], self.K_STEM, 1, 1)
+        wk[:, :w.shape[1] * k * k, 0, 0] = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).cpu()
+        self.stem_geom = (k, enc.conv1.stride[0], enc.conv1.padding[0])
+        self.stem_w = ops.pack_conv_weight(wk.to(device=device, dtype=torch.float16))
+        self.stem_b = None if b is None else b.to(device).contiguous()
+        self.stem_cudnn = w.to(device=device, dtype=torch.float16).contiguous(memory_format=torch.channels_last)
         self.blocks = []
         for layer in (enc.layer1, enc.layer2, enc.layer3):
             for blk in layer:
-                down = None if blk.downsample is None else (w16(blk.downsample[0]), blk.downsample[0].stride)
-                self.blocks.append((w16(blk.conv1), blk.conv1.stride, w16(blk.conv2), down))
-        self.w_out = w16(enc.conv2)
-        self.b_out = enc.conv2.bias.detach().to(device=device, dtype=torch.float16)
-        self.eps = 1e-5
+                down = None if blk.downsample is None else pack(blk.downsample[0], blk.downsample[1])
+                self.blocks.append((pack(blk.conv1, blk.norm1), pack(blk.conv2, blk.norm2), down))
+        self.out_conv = (ops.pack_conv_weight(enc.conv2.weight.detach().to(device=device, dtype=torch.float16)),
+                         enc.conv2.bias.detach().float().to(device).contiguous(), enc.conv2.out_channels)
+        self.out_cudnn = (enc.conv2.weight.detach().to(device=device, dtype=torch.float16),
+                          enc.conv2.bias.detach().to(device=device, dtype=torch.float16))
         self._ws = None
 
-    def _norm(self, y, relu_inner, add=None, relu_outer=False):
-        """y: channels-last f16 [S, C, H, W] -> same layout."""
+    def _inorm(self, rows, S, relu_inner, add=None, relu_outer=False):
+        """rows f16 [S*HW, C] -> instance-normalised rows (statistics per sample and channel)."""
         lib = _lib.load()
-        S, C, H, W = y.shape
-        assert y.is_contiguous(memory_format=torch.channels_last) and y.dtype == torch.float16
+        C = rows.shape[1]
         need = lib.cwm_instnorm_workspace_bytes(S, C)
-        if self._ws is None or self._ws.numel() < need or self._ws.device != y.device:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=y.device)
-        out = torch.empty_like(y)
-        if add is not None:
-            assert add.shape == y.shape and add.is_contiguous(memory_format=torch.channels_last)
-        _lib.check(lib.cwm_instnorm_f16(y.data_ptr(), S, H * W, C, self.eps, int(relu_inner),
+        if self._ws is None or self._ws.numel() < need or self._ws.device != rows.device:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=rows.device)
+        out = torch.empty_like(rows)
+        assert rows.is_contiguous() and rows.dtype == torch.float16 and (add is None or (add.shape == rows.shape and add.is_contiguous()))
+        _lib.check(lib.cwm_instnorm_f16(rows.data_ptr(), S, rows.shape[0] // S, C, self.eps, int(relu_inner),
                                         None if add is None else add.data_ptr(), int(relu_outer), out.data_ptr(),
-                                        self._ws.data_ptr(), self._ws.numel(), _stream(y)))
+                                        self._ws.data_ptr(), self._ws.numel(), _stream(rows)))
         return out
 
-    @staticmethod
-    def _cl(t):
-        return t if t.is_contiguous(memory_format=torch.channels_last) else t.contiguous(memory_format=torch.channels_last)
+    def _conv(self, rows, S, H, W, packed, relu):
+        """-> (output rows, Ho, Wo); bias / relu in the epilogue when the norm is folded (batch norm)."""
+        w, b, k, stride = packed
+        Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+        Cin = rows.shape[1]
+        if self.conv_impl == "cudnn":
+            y = F.conv2d(rows.view(S, H, W, Cin).permute(0, 3, 1, 2), w, None, stride, k // 2)
+            if not y.is_contiguous(memory_format=torch.channels_last):
+                y = y.contiguous(memory_format=torch.channels_last)
+            return y.permute(0, 2, 3, 1).reshape(S * Ho * Wo, -1), Ho, Wo
+        Cout = w.shape[0]
+        out = torch.empty(S * Ho * Wo, Cout, dtype=torch.float16, device=rows.device)
+        _lib.check(_lib.load().cwm_conv2d_strided_f16(rows.data_ptr(), rows.stride(0), S, H, W, Cin, w.data_ptr(), Cout, k, k,
+                                                      k // 2, k // 2, stride, None if b is None else b.data_ptr(),
+                                                      int(bool(relu and b is not None)), out.data_ptr(), Cout, _stream(rows)))
+        return out, Ho, Wo
 
     def __call__(self, x):
-        """x fp32 / f16 [S, 3, H, W] -> f16 [S, 256, H/8, W/8] (channels-last strides)."""
+        """x fp32 / f16 [S, 3, H, W] (already scaled to [-1, 1]) -> f16 [S, output_dim, H/8, W/8] (channels-last strides)."""
+        lib = _lib.load()
+        inst = self.norm == 'instance'
         with torch.cuda.device(x.device):
-            w, stride, pad = self.stem
-            y = self._cl(F.conv2d(x.to(torch.float16).contiguous(memory_format=torch.channels_last), w, None, stride, pad))
-            y = self._norm(y, relu_inner=True)
-            for w1, s1, w2, down in self.blocks:
-                z = self._norm(self._cl(F.conv2d(y, w1, None, s1, 1)), relu_inner=True)
-                z = self._cl(F.conv2d(z, w2, None, 1, 1))
+            S, _, H, W = x.shape
+            k, stride, pad = self.stem_geom
+            H1, W1 = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+            if self.conv_impl == "cudnn":
+                y = F.conv2d(x.to(torch.float16).contiguous(memory_format=torch.channels_last), self.stem_cudnn, None, stride, pad)
+                y = y.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1).reshape(S * H1 * W1, -1)
+            else:
+                cols = ops.im2col_nchw_f16(x.float().contiguous(), k, stride, pad, self.K_STEM)
+                y, _, _ = self._conv(cols, S, H1, W1, (self.stem_w, self.stem_b, 1, 1), relu=True)
+            if inst:
+                y = self._inorm(y, S, relu_inner=True)
+            H, W = H1, W1
+            for c1, c2, down in self.blocks:
+                z, Ho, Wo = self._conv(y, S, H, W, c1, relu=True)
+                if inst:
+                    z = self._inorm(z, S, relu_inner=True)
+                z, _, _ = self._conv(z, S, Ho, Wo, c2, relu=True)
                 if down is not None:
-                    y = self._norm(self._cl(F.conv2d(y, down[0], None, down[1], 0)), relu_inner=False)
-                y = self._norm(z, relu_inner=True, add=y, relu_outer=True)     # relu(x + relu(norm2(conv2(.))))
-            return F.conv2d(y, self.w_out, self.b_out)
+                    y, _, _ = self._conv(y, S, H, W, down, relu=False)
+                    if inst:
+                        y = self._inorm(y, S, relu_inner=False)
+                if inst:
+                    y = self._inorm(z, S, relu_inner=True, add=y, relu_outer=True)     # relu(x + relu(norm2(conv2(.))))
+                else:
+                    out = torch.empty_like(z)
+                    _lib.check(lib.cwm_add_act_f16(y.data_ptr(), z.data_ptr(), z.numel(), 1, out.data_ptr(), _stream(z)))
+                    y = out
+                H, W = Ho, Wo
+            if self.conv_impl == "cudnn":
+                return F.conv2d(y.view(S, H, W, -1).permute(0, 3, 1, 2), *self.out_cudnn)
+            w, b, Cout = self.out_conv
+            out, _, _ = self._conv(y, S, H, W, (w, b, 1, 1), relu=False)
+            return out.view(S, H, W, Cout).permute(0, 3, 1, 2)
 
 
 class FusedBasicUpdate:
@@ -488,6 +560,12 @@ class FusedBasicUpdate:
         self.b_m0 = f32(mk[0].bias)
         self.b_fh1m = f32(fh.conv1.bias, mk[0].bias)
         self.w_fh2, self.b_fh2 = cl(fh.conv2.weight, out_pad=8), f32(fh.conv2.bias)
+        # the flow head's 3x3 / 256 -> 2 convolution as a 1x1 GEMM to its 18 per-tap products (row (ky*3 + kx)*2 + co), summed
+        # over the 3x3 neighbourhood inside cwm_raft_flow_update_taps: a 3x3 implicit GEMM with N = 2 is 97 % padding
+        wt = fh.conv2.weight.detach().float().permute(2, 3, 0, 1).reshape(-1, fh.conv2.in_channels)     # [(ky, kx, co), c]
+        self.fuse_tail = (os.environ.get("CWM_RAFT_FUSE_TAIL", "1") != "0" and tuple(fh.conv2.kernel_size) == (3, 3)
+                          and fh.conv2.out_channels == 2 and enc.conv.out_channels == self.C - 2)
+        self.w_fh2t = cl(wt.view(wt.shape[0], -1, 1, 1), out_pad=24)
         self.w_m2 = cl(mk[2].weight)
         self.b_m2 = mk[2].bias.detach().to(device=device, dtype=torch.float16)
         self.w_m2q, self.b_m2q = cl(0.25 * mk[2].weight), f32(0.25 * mk[2].bias)   # .25 * mask(net), update.py:137
@@ -513,6 +591,7 @@ class FusedBasicUpdate:
         st.RHX[:, C:2 * C].copy_(st.HX[:, C:2 * C])
         if flow_init is not None:
             st.flow16[:, :2].copy_(rows(flow_init))
+        st.taps = buf(24) if st.tc else None
         return st
 
     def _conv(self, st, rows, weight, padding, bias=None, relu=False, out=None):
@@ -569,8 +648,14 @@ class FusedBasicUpdate:
                 bias_act(raw, 128, self.b_f1, 128, st.flo1, 128)
                 raw = self._conv(st, st.flo1, self.w_f2, 1)
                 bias_act(raw, 64, self.b_f2, 64, st.CORFLO[:, 192:], 256)
-            raw = self._conv(st, st.CORFLO, self.w_cv, 1)
-            bias_act(raw, 128, self.b_cv, 128, st.HX[:, 2 * C:], 3 * C, st.RHX[:, 2 * C:], 3 * C, tail=st.flow16)
+            if st.tc and self.fuse_tail:
+                # bias + relu in the epilogue, the 126 motion features + the flow stored into BOTH GRU input buffers
+                pk = self._packed[id(self.w_cv)][0]
+                _lib.check(lib.cwm_conv2d_dual_f16(p(st.CORFLO), 256, st.N, st.H, st.W, 256, p(pk), 128, 3, 3, 1, 1, p(self.b_cv), 1,
+                                                   p(st.flow16), 8, p(st.HX[:, 2 * C:]), 3 * C, p(st.RHX[:, 2 * C:]), 3 * C, s))
+            else:
+                raw = self._conv(st, st.CORFLO, self.w_cv, 1)
+                bias_act(raw, 128, self.b_cv, 128, st.HX[:, 2 * C:], 3 * C, st.RHX[:, 2 * C:], 3 * C, tail=st.flow16)
             # SepConvGRU (update.py:43-60): horizontal then vertical
             for w_zr, b_zr, w_q, b_q, pad, dense in ((self.w_zr1, self.b_zr1, self.w_q1, self.b_q1, (0, 2), None),
                                                      (self.w_zr2, self.b_zr2, self.w_q2, self.b_q2, (2, 0), st.Hd)):
@@ -597,7 +682,13 @@ class FusedBasicUpdate:
                     fh1, mh = st.fhm[:, :256], st.fhm[:, 256:]
                 else:
                     fh1, mh = self._conv(st, st.Hd, self.w_fh1, 1, self.b_fh1, True, st.fh1), None
-                raw = self._conv(st, fh1, self.w_fh2, 1)
+                if self.fuse_tail:
+                    self._conv(st, fh1, self.w_fh2t, 0, None, False, st.taps)
+                    _lib.check(lib.cwm_raft_flow_update_taps(p(st.taps), 24, p(self.b_fh2), p(coords1), st.N, st.H, st.W,
+                                                             p(st.flow16), None, 0, None, 0, s))
+                    raw = None
+                else:
+                    raw = self._conv(st, fh1, self.w_fh2, 1)
             else:
                 raw = self._conv(st, st.Hd, self.w_fh1m if emit else self.w_fh1, 1)
                 ldx = raw.shape[1]
@@ -606,7 +697,8 @@ class FusedBasicUpdate:
                     bias_act(raw, ldx, self.b_m0, 256, st.mh, 256, x_ptr=p(raw[:, 256:]))
                 mh = st.mh
                 raw = self._conv(st, st.fh1, self.w_fh2, 1)
-            _lib.check(lib.cwm_raft_flow_update(p(raw), 8, p(self.b_fh2), p(coords1), st.N, st.H, st.W, p(st.flow16), s))
+            if raw is not None:
+                _lib.check(lib.cwm_raft_flow_update(p(raw), 8, p(self.b_fh2), p(coords1), st.N, st.H, st.W, p(st.flow16), s))
             if not emit:
                 return None
             if st.tc:
@@ -709,14 +801,19 @@ class RAFT(nn.Module):
             cached = self._half_ub
         return cached[1]
 
-    def _fused_feature_encoder(self):
-        key = tuple((p.data_ptr(), p._version) for p in self.fnet.parameters())
-        cached = getattr(self, '_fused_fnet', None)
+    def _fused_encoder(self, which):
+        """Packed twin of ``fnet`` / ``cnet`` (rebuilt when its parameters or batch-norm statistics change)."""
+        enc = getattr(self, which)
+        key = tuple((p.data_ptr(), p._version) for p in list(enc.parameters()) + list(enc.buffers()))
+        cached = getattr(self, '_fused_' + which, None)
         if cached is None or cached[0] != key:
-            device = next(self.fnet.parameters()).device
-            object.__setattr__(self, '_fused_fnet', (key, FusedFeatureEncoder(self.fnet, device)))
-            cached = self._fused_fnet
+            device = next(enc.parameters()).device
+            object.__setattr__(self, '_fused_' + which, (key, FusedFeatureEncoder(enc, device)))
+            cached = getattr(self, '_fused_' + which)
         return cached[1]
+
+    def _fused_feature_encoder(self):
+        return self._fused_encoder('fnet')
 
     def _fused_update_block(self):
         key = tuple((p.data_ptr(), p._version) for p in self.update_block.parameters())
@@ -742,7 +839,7 @@ class RAFT(nn.Module):
         fused_fnet = (amp and test_mode and isinstance(self.fnet, BasicEncoder) and self.fnet.norm_fn == 'instance'
                       and bool(getattr(self.args, 'fused_encoder', True)) and os.environ.get("CWM_RAFT_ENCODER", "fused") != "eager")
         if fused_fnet:
-            # f16 channels-last activations, cuDNN convolutions, instance norm + relu (+ shortcut) in cwm_instnorm_f16
+            # f16 pixel-major rows, implicit-GEMM convolutions, instance norm + relu (+ shortcut) in cwm_instnorm_f16
             fmaps = self._fused_feature_encoder()(torch.cat([image1, image2], dim=0))
         else:
             with torch.autocast("cuda", enabled=amp):
@@ -750,8 +847,12 @@ class RAFT(nn.Module):
         fmap1 = fmaps[:n1].float().expand(N, -1, -1, -1)
         fmap2 = fmaps[n1:].float().expand(N, -1, -1, -1)
         corr_fn = CorrBlock(fmap1, fmap2, num_levels=self.args.corr_levels, radius=self.args.corr_radius)
+        # the context network: batch norm folded into its convolutions (inference statistics only)
+        fused_cnet = (fused_fnet and isinstance(self.cnet, BasicEncoder) and self.cnet.norm_fn == 'batch'
+                      and not self.cnet.training)
         with torch.autocast("cuda", enabled=amp):
-            net, inp = torch.split(self.cnet(image1), [self.hidden_dim, self.context_dim], dim=1)
+            ctx = self._fused_encoder('cnet')(image1) if fused_cnet else self.cnet(image1)
+            net, inp = torch.split(ctx, [self.hidden_dim, self.context_dim], dim=1)
             net = torch.tanh(net).expand(N, -1, -1, -1)
             inp = torch.relu(inp).expand(N, -1, -1, -1)
         coords0, coords1 = self.initialize_flow(image1 if n1 == N else image2)

@@ -453,6 +453,25 @@ int cwm_conv2d_weight_k(int Cin, int kh, int kw);
 int cwm_conv2d_f16(const uint16_t* x, int ldx, int S, int H, int W, int Cin, const uint16_t* w_packed, int Cout, int kh,
                    int kw, int pad_h, int pad_w, const float* bias, int relu, uint16_t* out, int ldo, cwm_stream_t stream);
 
+/* The same with a stride (1 or 2) and no limit on the image width: the convolutions of RAFT's two encoders
+ * (cwm/models/raft/extractor.py:6-56 ResidualBlock, :118-190 BasicEncoder: 3x3 / 1 and 3x3 / 2 convolutions and the 1x1 / 2
+ * shortcuts on 112, 56 and 28 pixel maps).  H / W are the INPUT size; the output map is ((H - 1) / stride + 1) x ((W - 1) /
+ * stride + 1) (nn.Conv2d with padding = k // 2) and `out` holds its pixel rows.  Maps wider than 32 pixels are tiled in both
+ * directions (a 128-row tile = 8 x 16, 16 x 8 or 4 x 32 pixels); for stride 2 the A boxes are loaded through a tensor map
+ * with traversal stride 2, so nothing is gathered or copied on the way either. */
+int cwm_conv2d_strided_f16(const uint16_t* x, int ldx, int S, int H, int W, int Cin, const uint16_t* w_packed, int Cout, int kh,
+                           int kw, int pad_h, int pad_w, int stride, const float* bias, int relu, uint16_t* out, int ldo,
+                           cwm_stream_t stream);
+
+/* cwm_conv2d_f16 writing its output rows to TWO row buffers (out2 may be NULL), with the last two output columns
+ * optionally replaced by the 2 f16 at tail[row * ld_tail] (tail may be NULL): the motion encoder's last convolution
+ * (126 features, update.py:96-98) feeds both GRU input buffers ([h | inp | motion, flow] and [r*h | inp | motion, flow],
+ * :52-58) and closes their rows with the current flow -- no copy / concatenation kernel.  Maps of <= 32 pixels when a
+ * tail is given. */
+int cwm_conv2d_dual_f16(const uint16_t* x, int ldx, int S, int H, int W, int Cin, const uint16_t* w_packed, int Cout, int kh,
+                        int kw, int pad_h, int pad_w, const float* bias, int relu, const uint16_t* tail, int ld_tail,
+                        uint16_t* out, int ldo, uint16_t* out2, int ldo2, cwm_stream_t stream);
+
 /* The two convolutions of one ConvGRU half-step with the gate arithmetic in their epilogues (update.py:43-60):
  *   gate:    [z | r] = sigmoid(conv(x, w_zr) + bias_zr), 2C output channels; z -> z_out [., C], r * h -> rh_out [., C]
  *            (the first C columns of the q convolution's input rows);
@@ -465,6 +484,13 @@ int cwm_conv2d_gru_update_f16(const uint16_t* x, int ldx, int S, int H, int W, i
                               int kw, int pad_h, int pad_w, const float* bias_q, const uint16_t* z, int ldz, uint16_t* h,
                               int ldh, uint16_t* h_dense, cwm_stream_t stream);
 
+/* cwm_raft_flow_update with the flow head's last convolution (3x3, 256 -> 2; update.py:13-14) finished inside: `taps`
+ * [B*H*W, ldt] holds per pixel the 18 per-tap products of a 1x1 GEMM (column (ky*3 + kx)*2 + co = w[co, :, ky, kx] . x[pixel]),
+ * delta = bias + the 3x3 stencil sum of the neighbours' taps (zero outside the image); coords1 += delta; the new flow goes to
+ * flow16 [., 8] and, as 2 f16, to dst1 / dst2 (the flow columns of the GRU input rows; either may be NULL). */
+int cwm_raft_flow_update_taps(const uint16_t* taps, int ldt, const float* bias, float* coords1, int B, int H, int W,
+                              uint16_t* flow16, uint16_t* dst1, int ld1, uint16_t* dst2, int ld2, cwm_stream_t stream);
+
 /* im2col of the 2-channel flow rows for the k x k convolution of BasicMotionEncoder.convf1 (update.py:85): out[m, 2 tap + c],
  * taps in (ky, kx) order, zero outside the image and in the columns >= 2 k^2. */
 int cwm_raft_im2col_flow(const uint16_t* flow16, int ldf, int B, int H, int W, int k, uint16_t* out, int ldo,
@@ -476,6 +502,17 @@ int cwm_raft_im2col_flow(const uint16_t* flow16, int ldf, int B, int H, int W, i
 size_t cwm_instnorm_workspace_bytes(int S, int C);
 int cwm_instnorm_f16(const uint16_t* x, int S, int HW, int C, float eps, int relu_inner, const uint16_t* add, int relu_outer,
                      uint16_t* out, void* workspace, size_t workspace_bytes, cwm_stream_t stream);
+
+/* im2col of a few-channel NCHW fp32 image for a strided k x k convolution -- the encoders' 7x7 / 2 stem on the 3-channel frame
+ * (extractor.py:132, :172): out[(s, oy, ox), (ky * k + kx) * Cin + c] = scale * img[s, c, stride oy + ky - pad, stride ox + kx
+ * - pad] + shift, zero outside the image and in the columns [k k Cin, ldo); the stem is then one cwm_gemm_f16 with K = ldo.
+ * scale / shift carry RAFT's input normalisation 2 (x / 255) - 1 (raft_model.py:205-206). */
+int cwm_im2col_nchw_f16(const float* img, int S, int Cin, int H, int W, int k, int stride, int pad, float scale, float shift,
+                        uint16_t* out, int ldo, cwm_stream_t stream);
+
+/* out = relu?(a + b) over n f16 elements (n % 8 == 0): the residual joins of the context encoder, whose batch norms are
+ * folded into the convolution weights at inference (extractor.py:46-56). */
+int cwm_add_act_f16(const uint16_t* a, const uint16_t* b, long long n, int relu, uint16_t* out, cwm_stream_t stream);
 
 /* ---- masks on device with a counter-based RNG (csrc/masks.cu) --------------------------------------
  * Opt-in stand-ins for the reference's host-side mask generation (cwm/models/masking.py:347-401 MaskingGenerator.

@@ -27,6 +27,31 @@ def test_convolution_equals_the_box_walk(kh, kw, H, W, C):
     np.testing.assert_allclose(got, want, rtol=1e-11, atol=1e-11)
 
 
+@pytest.mark.parametrize("kh,stride,H,W,C", [(3, 1, 40, 56, 24), (3, 2, 56, 56, 64), (1, 2, 56, 112, 96), (3, 2, 37, 45, 70),
+                                             (3, 1, 20, 112, 8), (3, 2, 18, 36, 8)])
+def test_strided_and_wide_convolutions_equal_the_box_walk(kh, stride, H, W, C):
+    """The encoders' shapes: 2-D tiles for maps wider than 32 pixels, traversal stride 2 (odd sizes included)."""
+    g = torch.Generator().manual_seed(kh * 10 + stride + H)
+    S, N = 2, 3
+    x = torch.randn(S, C, H, W, generator=g, dtype=torch.float64)
+    w = torch.randn(N, C, kh, kh, generator=g, dtype=torch.float64)
+    b = torch.randn(N, generator=g, dtype=torch.float64)
+    want = F.conv2d(x, w, b, stride, kh // 2).permute(0, 2, 3, 1).numpy()
+    got = cg.conv_as_gemm(x.permute(0, 2, 3, 1).numpy(), w.numpy(), b.numpy(), stride=stride)
+    np.testing.assert_allclose(got, want, rtol=1e-11, atol=1e-11)
+
+
+def test_stem_im2col_plus_gemm_equals_the_strided_convolution():
+    g = torch.Generator().manual_seed(5)
+    img = torch.rand(2, 3, 30, 38, generator=g, dtype=torch.float64) * 255
+    w = torch.randn(4, 3, 7, 7, generator=g, dtype=torch.float64)
+    want = F.conv2d(2 * (img / 255) - 1, w, None, 2, 3).permute(0, 2, 3, 1).reshape(-1, 4).numpy()
+    cols = cg.im2col_nchw(img.numpy(), 7, 2, 3, 152, scale=2 / 255, shift=-1.0)
+    wk = np.zeros((4, 152))
+    wk[:, :147] = w.permute(0, 2, 3, 1).reshape(4, -1).numpy()
+    np.testing.assert_allclose(cols @ wk.T, want, rtol=1e-10, atol=1e-10)
+
+
 def test_packed_weight_layout_and_relu():
     w = np.arange(2 * 3 * 1 * 5, dtype=np.float64).reshape(2, 3, 1, 5)
     p = cg.pack_weight(w)
@@ -134,3 +159,100 @@ def test_gpu_gru_gate_and_update_in_the_conv_epilogues(kh, kw, S, H, W):
     got = HXd[:, :C].cpu().float()
     assert (got - h_new).abs().max().item() <= 8e-3, (got - h_new).abs().max().item()
     assert torch.equal(Hd.cpu(), HXd[:, :C].cpu()) and torch.equal(HXd[:, C:].cpu(), HX[:, C:])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,Cin,Cout,k,stride,S,H,W", [
+    ("layer1 3x3", 64, 64, 3, 1, 3, 112, 112), ("layer2 3x3/2", 64, 96, 3, 2, 3, 112, 112), ("layer2 1x1/2", 64, 96, 1, 2, 2, 112, 112),
+    ("layer2 3x3", 96, 96, 3, 1, 5, 56, 56), ("layer3 3x3/2", 96, 128, 3, 2, 5, 56, 56), ("layer3 1x1/2", 96, 128, 1, 2, 2, 56, 56),
+    ("layer3 3x3", 128, 128, 3, 1, 3, 28, 28), ("conv2 1x1", 128, 256, 1, 1, 3, 28, 28),
+    ("odd sizes /2", 72, 40, 3, 2, 2, 37, 45), ("odd sizes", 24, 136, 3, 1, 2, 40, 50), ("1x1/2 odd", 16, 64, 1, 2, 1, 19, 75)])
+def test_gpu_encoder_convolutions_match_torch(name, Cin, Cout, k, stride, S, H, W):
+    """RAFT's encoder convolutions (extractor.py:6-56, :118-190): wide maps tiled in both directions, stride 2 through the
+    tensor map's traversal stride."""
+    from counterfactualworldmodels_b200 import ops
+    g = torch.Generator().manual_seed(Cin + Cout + k + S)
+    x = (torch.randn(S, H, W, Cin, generator=g) * 0.7).half()
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).half()
+    b = torch.randn(Cout, generator=g)
+    want = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, stride, k // 2).permute(0, 2, 3, 1)
+    got = ops.conv2d_f16(x.reshape(-1, Cin).to(DEV), S, H, W, w.to(DEV), bias=b.to(DEV), relu=False, stride=stride)
+    got = got.cpu().float().view(want.shape)
+    err = (got - want).abs().max().item()
+    assert err <= 2e-3 * max(1.0, want.abs().max().item()), (name, err)
+    got_relu = ops.conv2d_f16(x.reshape(-1, Cin).to(DEV), S, H, W, w.to(DEV), relu=True, stride=stride).cpu().float().view(want.shape)
+    assert (got_relu - F.relu(want - b)).abs().max().item() <= 2e-3 * max(1.0, want.abs().max().item())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("S,H,W", [(2, 224, 224), (3, 30, 38), (1, 17, 65)])
+def test_gpu_stem_im2col_matches_the_restatement(S, H, W):
+    from counterfactualworldmodels_b200 import ops
+    g = torch.Generator().manual_seed(S + H)
+    img = torch.rand(S, 3, H, W, generator=g) * 255
+    got = ops.im2col_nchw_f16(img.to(DEV), 7, 2, 3, 152, scale=2 / 255, shift=-1.0).cpu().float().numpy()
+    want = cg.im2col_nchw(img.numpy(), 7, 2, 3, 152, scale=2 / 255, shift=-1.0)
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-3)     # f16 rounding of values in [-1, 1]
+    assert np.array_equal(got == 0, np.abs(want) < 3e-8) or np.abs(got[np.abs(want) < 3e-8]).max() < 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("S,H,W", [(2, 28, 28), (3, 16, 16), (1, 9, 30)])
+def test_gpu_dual_destination_convolution_with_a_tail(S, H, W):
+    """`cwm_conv2d_dual_f16`: the motion encoder's last convolution writes its 126 features + the 2 flow columns into both
+    GRU input buffers; everything in front stays untouched."""
+    from counterfactualworldmodels_b200 import _lib, ops
+    g = torch.Generator().manual_seed(S + H)
+    M = S * H * W
+    x = (torch.randn(M, 256, generator=g) * 0.5).half().to(DEV)
+    w = torch.zeros(128, 256, 3, 3)
+    w[:126] = torch.randn(126, 256, 3, 3, generator=g) / 48
+    b = torch.zeros(128)
+    b[:126] = torch.randn(126, generator=g)
+    flow16 = torch.zeros(M, 8, dtype=torch.float16)
+    flow16[:, :2] = (torch.randn(M, 2, generator=g) * 4).half()
+    HX = torch.full((M, 384), 7.0, dtype=torch.float16, device=DEV)
+    RHX = torch.full((M, 384), -3.0, dtype=torch.float16, device=DEV)
+    pk = ops.pack_conv_weight(w.half().to(DEV))
+    bd, fd = b.to(DEV), flow16.to(DEV)
+    _lib.check(_lib.load().cwm_conv2d_dual_f16(x.data_ptr(), 256, S, H, W, 256, pk.data_ptr(), 128, 3, 3, 1, 1, bd.data_ptr(), 1,
+                                               fd.data_ptr(), 8, HX[:, 256:].data_ptr(), 384, RHX[:, 256:].data_ptr(), 384, None))
+    want = F.relu(F.conv2d(x.float().cpu().view(S, H, W, 256).permute(0, 3, 1, 2), w.half().float(), b, 1, 1)).permute(0, 2, 3, 1)
+    want = want.reshape(-1, 128)[:, :126]
+    for buf, fill in ((HX, 7.0), (RHX, -3.0)):
+        got = buf.cpu().float()
+        assert (got[:, 256:382] - want).abs().max().item() <= 2e-3 * max(1.0, want.abs().max().item())
+        assert bool((got[:, :256] == fill).all()) and torch.equal(got[:, 382:], flow16[:, :2].float())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("S,H,W", [(2, 28, 28), (3, 16, 16), (1, 9, 30)])
+def test_gpu_flow_head_as_tap_products_plus_stencil(S, H, W):
+    """The flow head's 3x3 / 256 -> 2 convolution as a 1x1 GEMM to 18 per-tap products + the stencil sum inside
+    `cwm_raft_flow_update_taps`, against conv2d; the new flow lands in flow16 and in both GRU input rows."""
+    from counterfactualworldmodels_b200 import _lib, ops
+    g = torch.Generator().manual_seed(S * 7 + W)
+    M = S * H * W
+    x = torch.relu(torch.randn(M, 256, generator=g)).half()
+    w = (torch.randn(2, 256, 3, 3, generator=g) / 48).half()
+    b = torch.randn(2, generator=g) * 0.1
+    coords = torch.randn(S, 2, H, W, generator=g) * 5
+    want_c = coords + F.conv2d(x.float().view(S, H, W, 256).permute(0, 3, 1, 2), w.float(), b, 1, 1)
+    wt = torch.zeros(24, 256, 1, 1, dtype=torch.float16)
+    wt[:18, :, 0, 0] = w.permute(2, 3, 0, 1).reshape(18, 256)
+    taps = ops.conv2d_f16(x.to(DEV), S, H, W, wt.to(DEV))
+    c1 = coords.clone().to(DEV)
+    flow16 = torch.zeros(M, 8, dtype=torch.float16, device=DEV)
+    HX = torch.full((M, 384), 7.0, dtype=torch.float16, device=DEV)
+    RHX = torch.full((M, 384), -3.0, dtype=torch.float16, device=DEV)
+    bd = b.to(DEV)
+    _lib.check(_lib.load().cwm_raft_flow_update_taps(taps.data_ptr(), taps.stride(0), bd.data_ptr(), c1.data_ptr(), S, H, W,
+                                                     flow16.data_ptr(), HX[:, 382:].data_ptr(), 384, RHX[:, 382:].data_ptr(), 384,
+                                                     None))   # (the two extra destinations are optional; raft.py passes NULL)
+    scale = (want_c - coords).abs().max().item()
+    assert (c1.cpu() - want_c).abs().max().item() <= 3e-3 * scale
+    ys, xs = torch.meshgrid(torch.arange(H).float(), torch.arange(W).float(), indexing="ij")
+    want_flow = (want_c - torch.stack([xs, ys])[None]).permute(0, 2, 3, 1).reshape(M, 2)
+    for got in (flow16[:, :2], HX[:, 382:], RHX[:, 382:]):
+        assert (got.cpu().float() - want_flow).abs().max().item() <= 3e-3 * scale + 2e-3 * want_flow.abs().max().item()
+    assert bool((HX[:, :382] == 7.0).all()) and bool((RHX[:, :382] == -3.0).all()) and float(flow16[:, 2:].abs().max()) == 0

@@ -693,37 +693,50 @@ def test_gpu_instance_norm_kernel_matches_torch(S, H, W, C):
     add = torch.randn(S, C, H, W, generator=g).half()
     enc = raft.FusedFeatureEncoder.__new__(raft.FusedFeatureEncoder)
     enc.eps, enc._ws = 1e-5, None
-    cl = lambda t: t.to(DEV).contiguous(memory_format=torch.channels_last)            # noqa: E731
+    rows = lambda t: t.to(DEV).permute(0, 2, 3, 1).reshape(-1, C).contiguous()         # noqa: E731  (pixel-major rows)
+    back = lambda r: r.float().cpu().view(S, H, W, C).permute(0, 3, 1, 2)              # noqa: E731
     ref = torch.nn.functional.instance_norm(x.float(), eps=1e-5)
-    got = enc._norm(cl(x), relu_inner=False).float().cpu()
+    got = back(enc._inorm(rows(x), S, relu_inner=False))
     assert (got - ref).abs().max().item() <= 4e-3
-    got = enc._norm(cl(x), relu_inner=True).float().cpu()
+    got = back(enc._inorm(rows(x), S, relu_inner=True))
     assert (got - ref.relu()).abs().max().item() <= 4e-3
-    got = enc._norm(cl(x), relu_inner=True, add=cl(add), relu_outer=True).float().cpu()
+    got = back(enc._inorm(rows(x), S, relu_inner=True, add=rows(add), relu_outer=True))
     assert (got - (add.float() + ref.relu()).relu()).abs().max().item() <= 6e-3
-    again = enc._norm(cl(x), relu_inner=True, add=cl(add), relu_outer=True).float().cpu()
+    again = back(enc._inorm(rows(x), S, relu_inner=True, add=rows(add), relu_outer=True))
     assert torch.equal(got, again)                                                       # deterministic reduction order
 
 
 @pytest.mark.gpu
-def test_gpu_fused_feature_encoder_matches_the_autocast_encoder():
-    """`FusedFeatureEncoder` (f16 channels-last activations, cuDNN convolutions without bias, cwm_instnorm_f16) against
-    the module it wraps: fp32 reference, and no further from it than plain autocast is."""
+@pytest.mark.parametrize("which,conv_impl,hw", [("fnet", "tcgen05", 224), ("fnet", "cudnn", 224), ("cnet", "tcgen05", 224),
+                                               ("fnet", "tcgen05", 136), ("cnet", "tcgen05", 200)])
+def test_gpu_fused_encoders_match_the_autocast_encoders(which, conv_impl, hw):
+    """`FusedFeatureEncoder` (f16 pixel-major rows; every convolution an implicit GEMM on the tcgen05 kernel -- 2-D tiles,
+    stride 2 through the tensor map, im2col stem --, instance norms in cwm_instnorm_f16 / batch norms folded into the
+    weights) against the module it wraps: the fp32 reference, and no further from it than plain autocast is.  The batch
+    norms get non-trivial running statistics and affines first (a fresh BatchNorm2d is the identity)."""
     from counterfactualworldmodels_b200 import raft
-    model = _mirror(False).to(DEV)
+    model = _mirror(False).to(DEV).eval()
     g = torch.Generator().manual_seed(1)
-    x = (2 * torch.rand(5, 3, 224, 224, generator=g) - 1).to(DEV)
+    for m in model.cnet.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            n = m.num_features
+            m.running_mean.copy_(torch.randn(n, generator=g) * 0.3)
+            m.running_var.copy_(torch.rand(n, generator=g) + 0.5)
+            m.weight.data.copy_(torch.rand(n, generator=g) + 0.5)
+            m.bias.data.copy_(torch.randn(n, generator=g) * 0.2)
+    enc = getattr(model, which)
+    x = (2 * torch.rand(5, 3, hw, hw + 16, generator=g) - 1).to(DEV)
     old = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = False
     try:
-        want = model.fnet(x).float()
+        want = enc(x).float()
     finally:
         torch.backends.cudnn.allow_tf32 = old
     with torch.autocast("cuda"):
-        amp = model.fnet(x).float()
-    got = raft.FusedFeatureEncoder(model.fnet, DEV)(x).float()
-    assert got.shape == want.shape == (5, 256, 28, 28)
+        amp = enc(x).float()
+    got = raft.FusedFeatureEncoder(enc, DEV, conv_impl=conv_impl)(x).float()
+    assert got.shape == want.shape == (5, 256, hw // 8, (hw + 16) // 8)
     scale = want.abs().max().item()
     e_fused, e_amp = (got - want).abs().max().item() / scale, (amp - want).abs().max().item() / scale
-    print(f"feature encoder: fused {e_fused:.2e} of scale, autocast {e_amp:.2e}")
+    print(f"{which} ({conv_impl}, {hw} px): fused {e_fused:.2e} of scale, autocast {e_amp:.2e}")
     assert e_fused <= 1e-2 and e_fused <= 3 * e_amp + 1e-3
