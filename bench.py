@@ -432,6 +432,8 @@ def _main(out):
     ap.add_argument("--ref-sample", type=int, default=0,
                     help="frames per step of the CPU reference arm / baseline leg (0 = 1 for 4x4-patch models, else 2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-operand-modes", action="store_true",
+                    help="skip the f16 / bf16 operand-mode parity report (two short subprocesses after the timed runs)")
     ap.add_argument("--also", default="base_8x8_b64_counterfactual,imu400_base_4x4_b32",
                     help="extra workloads measured briefly (comma separated, '' to skip)")
     ap.add_argument("--no-cf-sweep", dest="cf_sweep", action="store_false",
@@ -806,6 +808,23 @@ def _main(out):
     if world == 1 and args.cf_sweep:
         also.append(measure_flow_sweep(dev, "base_8x8", 64, peaks, not args.no_cpu_baseline))
 
+    # the bf16-operand build beside the f16 default: parity error of both on fixtures the REAL reference produced
+    # (tools/dtype_error.py in a subprocess per build -- a process binds to one library at import time)
+    operand_modes = None
+    if rank == 0 and world == 1 and not args.no_operand_modes:
+        operand_modes = {}
+        for mode in ("f16", "bf16"):
+            try:
+                pr = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "dtype_error.py"), "base_8x8_b2_counterfactual",
+                                     "large_4x4_b1_factual"], env=dict(os.environ, CWM_DTYPE=mode), capture_output=True,
+                                    text=True, timeout=600)
+                operand_modes[mode] = (json.loads(pr.stdout.strip().splitlines()[-1])["cases"] if pr.returncode == 0
+                                       else {"error": pr.stderr[-300:]})
+            except Exception as e:  # noqa: BLE001  (a report line, never fatal for the benchmark)
+                operand_modes[mode] = {"error": repr(e)}
+        operand_modes["note"] = ("max-abs / mean-abs of the predicted patches vs the real reference (fp32); bar 2e-2 / 2e-3. "
+                                 "f16 is the shipped default; bf16 = the same kernels built with -DCWM_ACT_BF16 (CWM_DTYPE=bf16)")
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -840,7 +859,7 @@ def _main(out):
             "tensor_frac_of_burst_peak": round(per_gpu_fps * r["flops_frame"] / 1e12 / peaks["tflops_burst"], 4),
             "e2e": r["e2e"], "gpu_launches": int(r["launches"]),
             "clocks": r["clocks"], "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels,
-            "also": also,
+            "also": also, "operand_modes": operand_modes,
         }
         out.emit(line)
     if world > 1:

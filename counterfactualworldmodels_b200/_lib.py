@@ -14,6 +14,8 @@ CWM_OK = 0
 EPI_F16, EPI_GELU_F16, EPI_RES_F32, EPI_F32 = 0, 1, 2, 3
 
 # every symbol include/cwm_b200.h declares (checked by tests/test_abi.py)
+ABI_VERSION = 7   # include/cwm_b200.h CWM_B200_ABI_VERSION
+
 EXPORTED_SYMBOLS = (
     "cwm_abi_version", "cwm_last_error", "cwm_device_check", "cwm_compact_mask", "cwm_patch_gather",
     "cwm_layernorm_f16", "cwm_gemm_f16", "cwm_attention_f16", "cwm_fill_mask_tokens",
@@ -31,7 +33,7 @@ EXPORTED_SYMBOLS = (
     "cwm_conv2d_gru_update_f16",
     "cwm_raft_corr_tc_workspace_bytes", "cwm_raft_corr_volume_tc", "cwm_raft_corr_pyramid_tc",
     "cwm_instnorm_workspace_bytes", "cwm_instnorm_f16", "cwm_conv2d_strided_f16", "cwm_im2col_nchw_f16", "cwm_add_act_f16",
-    "cwm_conv2d_dual_f16", "cwm_raft_flow_update_taps",
+    "cwm_conv2d_dual_f16", "cwm_raft_flow_update_taps", "cwm_act_dtype",
     "cwm_philox4x32_10", "cwm_mask_uniform", "cwm_mask_energy_table", "cwm_mask_energy_sample",
     "cwm_mask_rectangularize_workspace_bytes", "cwm_mask_rectangularize",
     # tuning hooks (header section "tuning hooks")
@@ -221,17 +223,39 @@ def _declare(lib):
     return lib
 
 
+def lib_path():
+    """The build this process uses: ``CWM_DTYPE=bf16`` selects the bf16-operand twin (same sources, -DCWM_ACT_BF16); the
+    default is the f16 build, the only one inside the parity bar."""
+    mode = os.environ.get("CWM_DTYPE", "f16").lower()
+    if mode not in ("f16", "fp16", "bf16"):
+        raise CwmError(f"CWM_DTYPE={mode!r}: expected f16 or bf16")
+    return LIB_PATH.replace("libcwm_b200.so", "libcwm_b200_bf16.so") if mode == "bf16" else LIB_PATH
+
+
 def load():
     """Loads (once) and returns the ctypes handle.  Raises if the library has not been built."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = lib_path()
+        if not os.path.exists(path):
             raise CwmError(
-                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(there is no CPU or PyTorch fallback for the CWM VMAE path)")
         import torch  # noqa: F401  -- makes sure libcudart.so.12 is already mapped (same SONAME is reused)
-        _lib = _declare(ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL))
+        _lib = _declare(ctypes.CDLL(path, mode=ctypes.RTLD_GLOBAL))
     return _lib
+
+
+def act_dtype():
+    """torch dtype of every 16-bit activation / weight tensor handed to the library (f16, or bf16 in the bf16 build)."""
+    import torch
+    return torch.bfloat16 if load().cwm_act_dtype() == 1 else torch.float16
+
+
+def require_f16(what):
+    """Paths that exist for f16 operands only (RAFT, the conjoined models) refuse the bf16 build instead of mis-reading it."""
+    if load().cwm_act_dtype() != 0:
+        raise CwmError(f"{what} is available in the f16 build only (unset CWM_DTYPE=bf16)")
 
 
 def check(rc):

@@ -204,6 +204,7 @@ int cwm_profile_end(cwm_profile_entry* out, int max_entries, int* n_entries) {
 }
 
 int cwm_abi_version(void) { return CWM_B200_ABI_VERSION; }
+int cwm_act_dtype(void) { return CWM_ACT_IS_BF16; }
 
 const char* cwm_last_error(void) { return cwm::g_err; }
 

@@ -383,6 +383,7 @@ class FusedFeatureEncoder:
 
     def __init__(self, enc, device, conv_impl=None):
         assert isinstance(enc, BasicEncoder) and enc.norm_fn in ('instance', 'batch')
+        _lib.require_f16("raft.FusedFeatureEncoder")
         self.norm = enc.norm_fn
         self.conv_impl = conv_impl or (os.environ.get("CWM_RAFT_ENCODER_CONV", "tcgen05") if self.norm == 'instance' else "tcgen05")
         assert self.conv_impl in ("tcgen05", "cudnn") and (self.conv_impl == "tcgen05" or self.norm == 'instance')
@@ -510,6 +511,7 @@ class FusedBasicUpdate:
 
     def __init__(self, ub, device, conv_impl=None):
         assert isinstance(ub, BasicUpdateBlock)
+        _lib.require_f16("raft.FusedBasicUpdate")
         # 'tcgen05' (default): every convolution is an implicit GEMM on the repo's tensor-core kernel (cwm_conv2d_f16);
         # 'cudnn': the library convolutions of round 1, kept as the A/B reference (CWM_RAFT_CONV=cudnn)
         self.conv_impl = conv_impl or os.environ.get("CWM_RAFT_CONV", "tcgen05")

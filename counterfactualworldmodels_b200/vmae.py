@@ -235,7 +235,7 @@ class _Packer:
         return t.data_ptr()
 
     def f16(self, t):
-        t = t.detach().to(device=self.device, dtype=torch.float32).contiguous().to(torch.float16)
+        t = t.detach().to(device=self.device, dtype=torch.float32).contiguous().to(_lib.act_dtype())   # f16 (bf16 build: bf16)
         self.keep.append(t)
         return t.data_ptr()
 
@@ -272,7 +272,7 @@ class _Packer:
                     wt = weight.detach().to(device=self.device, dtype=torch.float32)
                     g = norm.weight.detach().to(device=self.device, dtype=torch.float32)
                     b = norm.bias.detach().to(device=self.device, dtype=torch.float32)
-                    w16 = (wt * g[None, :]).to(torch.float16).contiguous()
+                    w16 = (wt * g[None, :]).to(_lib.act_dtype()).contiguous()
                     colsum = w16.float().sum(1).contiguous()
                     c = wt @ b
                     if bias is not None:

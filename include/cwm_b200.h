@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define CWM_B200_ABI_VERSION 6
+#define CWM_B200_ABI_VERSION 7
 
 typedef void* cwm_stream_t; /* cudaStream_t */
 
@@ -38,6 +38,9 @@ enum cwm_status {
 
 /* ---- library ------------------------------------------------------------------------------------- */
 int cwm_abi_version(void);
+/* Operand type of this build: 0 = IEEE f16 (libcwm_b200.so, the parity default), 1 = bf16 (libcwm_b200_bf16.so: the same
+ * sources compiled with -DCWM_ACT_BF16; every `uint16_t*` activation / weight tensor of this header then holds bf16). */
+int cwm_act_dtype(void);
 const char* cwm_last_error(void);
 /* 0 when the current device is compute capability 10.x (B200), CWM_ERR_ARCH otherwise. */
 int cwm_device_check(void);

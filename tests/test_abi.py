@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_error_string():
     lib = _lib.load()
-    assert lib.cwm_abi_version() == 6
+    assert lib.cwm_abi_version() == 7
     assert isinstance(lib.cwm_last_error(), bytes)
 
 
