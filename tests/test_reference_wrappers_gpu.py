@@ -141,3 +141,54 @@ def test_reference_flow_generator_sweep_over_the_dropin_predictor(flow_model_kin
     ferr = (f_our - f_ref).abs().max().item() / max(f_ref.abs().max().item(), 1e-6)
     print(f"sweep ({flow_model_kind}): flows differ by {ferr:.2e} of scale")
     assert ferr <= 2e-2
+
+
+def test_reference_imu_conditioned_generator_over_the_dropin_conjoined_predictors():
+    """BASELINE config 5's driver, the reference's OWN class (segmentation.py:756-967 `ImuConditionedFlowGenerator`, with the
+    `ImuGenerator` it builds inside, :549-754): flow2imu -- this repo's RAFT inside its preprocessor -- predicts the head
+    motion of the static movie once, then the S counterfactuals are predicted by the drop-in IMU-conditioned padded
+    predictor.  Compared with what the same class produced over the reference's predictors on the CPU
+    (tests/golden/imu_sweep_128px.npz, oracle/make_golden_imu_sweep.py)."""
+    import sys
+    _, _, ref_seg = _reference()
+    import make_golden_imu_sweep as mg
+    from counterfactualworldmodels_b200 import conjoined_vmae as conj
+    from counterfactualworldmodels_b200 import raft as our_raft
+
+    def flow_net():
+        torch.manual_seed(0)
+        args = our_raft.get_args("")
+        args.multiframe, args.scale_inputs, args.output_dim = True, True, None
+        net = our_raft.RAFT(args).eval().requires_grad_(False)
+        net.iters = mg.RAFT_ITERS          # the reference's set_raft_iters only finds ITS RAFT class (INTEGRATION.md)
+        return net
+
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "imu_sweep_128px.npz")
+    d = np.load(path)
+    pred, head = mg.build(conj, ref_seg, our_raft, 'flow_model', flow_net())
+    G = ref_seg.ImuConditionedFlowGenerator(predictor=pred.to(DEV), head_motion_predictor=head.to(DEV),
+                                            flow_model=flow_net().to(DEV), imagenet_normalize_inputs=True, temporal_dim=2,
+                                            raft_iters=mg.RAFT_ITERS, seed=0)
+    assert type(G).__module__ == "cwm.models.segmentation" and "cwm.models.segmentation" in sys.modules
+    x, active, passive = mg.sweep_inputs()
+    x, active, passive = x.to(DEV), active.to(DEV), passive.to(DEV)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            G.set_input(x)
+            h = G.get_static_imu()
+            G.reset_padding_masks()
+            ys, flows = G.predict_counterfactual_videos_and_flows(x, active, passive, shifts=mg.SHIFTS, sample_batch_size=2,
+                                                                  raft_iters=mg.RAFT_ITERS)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert tuple(h.shape) == (1, 5, 96) and tuple(ys.shape) == (4, 2, 3, 128, 128) and tuple(flows.shape) == (4, 1, 2, 128, 128)
+    want_h, want_y = d["head_motion"], d["ys_frame1"]
+    e_h = float(np.abs(h.cpu().numpy() - want_h).max() / np.abs(want_h).max())
+    err = np.abs(ys[:, 1, :, ::2, ::2].cpu().numpy() - want_y)
+    print(f"reference ImuConditionedFlowGenerator over the drop-ins: head motion {e_h:.2e} of scale, frame-1 pixels "
+          f"max-abs {err.max():.2e} mean-abs {err.mean():.2e}")
+    assert e_h <= 2e-2 and err.max() <= MAX_ABS and err.mean() <= MEAN_ABS
+    assert torch.isfinite(flows).all()
