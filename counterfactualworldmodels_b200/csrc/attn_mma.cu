@@ -12,6 +12,8 @@
 // One CTA = kWarps * 16 query rows of one (sample, head); K/V are streamed in 64-row tiles through shared memory
 // (rows padded by 16 bytes: conflict-free ldmatrix).  q is expected pre-scaled (the qkv GEMM epilogue applies the
 // softmax scale), like cwm_attention_f16.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace cwm {
@@ -71,7 +73,30 @@ __device__ __forceinline__ void load_tile(__half* dst, const __half* src, long l
   }
 }
 
-template <int HD, int kWarps, int BN>  // BN = key tile (64, or 32 when there are at most 32 keys: half the MMA work)
+// ---- cp.async helpers (16-byte copies; src_bytes = 0 zero-fills the destination) ----
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+template <int HD, int kThreads>
+__device__ __forceinline__ void load_tile_async(__half* dst, const __half* src, long long ld, int row0, int n_rows, int limit) {
+  constexpr int kVec = HD / 8;
+  constexpr int kStride = HD + 8;
+  for (int i = threadIdx.x; i < n_rows * kVec; i += kThreads) {
+    const int r = i / kVec, c = i - r * kVec;
+    const bool in = row0 + r < limit;
+    cp_async16(smem_u32(dst + r * kStride + c * 8), reinterpret_cast<const uint4*>(src + (in ? row0 + r : 0) * ld) + c, in ? 16 : 0);
+  }
+}
+
+// kPipe: K / V tiles are double-buffered with cp.async (the next tile is in flight while the current one is multiplied) --
+// the split-key "src" direction of the cross-attention, where a CTA streams 512 keys for a handful of queries and the
+// un-pipelined load -> sync -> compute loop left the memory system idle most of the time.
+template <int HD, int kWarps, int BN, bool kPipe = false>  // BN = key tile (64, or 32 when there are at most 32 keys: half the MMA work)
 __global__ void __launch_bounds__(kWarps * 32)
 attn_mma_kernel(AttnMmaParams p) {
   constexpr int kThreads = kWarps * 32;
@@ -81,7 +106,7 @@ attn_mma_kernel(AttnMmaParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw_mma[];
   __half* Qs = reinterpret_cast<__half*>(smem_raw_mma);
   __half* Ks = Qs + BM * kStride;
-  __half* Vs = Ks + BN * kStride;
+  __half* Vs = Ks + BN * kStride;           // kPipe: stage 1 = the same pair 2 * BN rows further
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.y;
@@ -95,7 +120,14 @@ attn_mma_kernel(AttnMmaParams p) {
   const __half* kb = p.k + static_cast<long long>(b) * p.Nk * p.ldk + h * p.k_hs;
   const __half* vb = p.v + static_cast<long long>(b) * p.Nk * p.ldv + h * p.v_hs;
 
-  load_tile<HD, kThreads>(Qs, qb, p.ldq, q0, BM, p.Nq);
+  if constexpr (kPipe) {
+    load_tile_async<HD, kThreads>(Qs, qb, p.ldq, q0, BM, p.Nq);
+    load_tile_async<HD, kThreads>(Ks, kb, p.ldk, kv_begin, BN, kv_end);
+    load_tile_async<HD, kThreads>(Vs, vb, p.ldv, kv_begin, BN, kv_end);
+    cp_async_commit();
+  } else {
+    load_tile<HD, kThreads>(Qs, qb, p.ldq, q0, BM, p.Nq);
+  }
 
   float o[HD / 8][4];
 #pragma unroll
@@ -104,14 +136,31 @@ attn_mma_kernel(AttnMmaParams p) {
   float l_run[2] = {0.f, 0.f};
 
   const uint32_t q_addr = smem_u32(Qs + (warp * 16 + (lane & 15)) * kStride + (lane >> 4) * 8);
-  const uint32_t k_addr = smem_u32(Ks + ((lane & 7) + ((lane >> 4) << 3)) * kStride + ((lane >> 3) & 1) * 8);
-  const uint32_t v_addr = smem_u32(Vs + ((lane & 7) + (((lane >> 3) & 1) << 3)) * kStride + (lane >> 4) * 8);
+  const uint32_t k_addr0 = smem_u32(Ks + ((lane & 7) + ((lane >> 4) << 3)) * kStride + ((lane >> 3) & 1) * 8);
+  const uint32_t v_addr0 = smem_u32(Vs + ((lane & 7) + (((lane >> 3) & 1) << 3)) * kStride + (lane >> 4) * 8);
+  constexpr uint32_t kStageBytes = 2 * BN * kStride * 2;
 
+  int stage = 0;
   for (int kv0 = kv_begin; kv0 < kv_end; kv0 += BN) {
-    __syncthreads();  // previous tile fully consumed (and Q visible on the first pass)
-    load_tile<HD, kThreads>(Ks, kb, p.ldk, kv0, BN, kv_end);
-    load_tile<HD, kThreads>(Vs, vb, p.ldv, kv0, BN, kv_end);
-    __syncthreads();
+    uint32_t k_addr = k_addr0, v_addr = v_addr0;
+    if constexpr (kPipe) {
+      __syncthreads();  // the other stage (tile - 1) is fully consumed
+      if (kv0 + BN < kv_end) {
+        load_tile_async<HD, kThreads>(Ks + (stage ^ 1) * 2 * BN * kStride, kb, p.ldk, kv0 + BN, BN, kv_end);
+        load_tile_async<HD, kThreads>(Vs + (stage ^ 1) * 2 * BN * kStride, vb, p.ldv, kv0 + BN, BN, kv_end);
+      }
+      cp_async_commit();
+      cp_async_wait<1>();   // this tile (and Q) landed
+      __syncthreads();
+      k_addr += stage * kStageBytes;
+      v_addr += stage * kStageBytes;
+      stage ^= 1;
+    } else {
+      __syncthreads();  // previous tile fully consumed (and Q visible on the first pass)
+      load_tile<HD, kThreads>(Ks, kb, p.ldk, kv0, BN, kv_end);
+      load_tile<HD, kThreads>(Vs, vb, p.ldv, kv0, BN, kv_end);
+      __syncthreads();
+    }
 
     // ---- S = Q K^T (16 x 64 per warp) ----
     float s[NT][4];
@@ -227,6 +276,142 @@ attn_mma_kernel(AttnMmaParams p) {
   }
 }
 
+// The "trg" direction of the bidirectional cross-attention (transformer.py:314-378): thousands of main-stream queries
+// against the <= 64 context keys of one (sample, head).  The generic kernel above gives every 64-row query tile its own CTA,
+// which re-stages K / V per tile and runs load -> sync -> compute -> store with nothing overlapped (measured 222-232 us =
+// 1.3 TB/s for 3140 x 25 / 6336 x 50).  Here a CTA keeps K and V resident, walks the query tiles q0 = blockIdx.x, +gridDim.x,
+// ... with the NEXT tile's Q in flight (cp.async, two buffers) while the current one is computed, and writes O through the
+// consumed Q buffer as full 16-byte row segments.  One kv tile means a plain (single-pass) softmax.
+template <int HD, int kWarps, int BN>
+__global__ void __launch_bounds__(kWarps * 32)
+attn_mma_trg_kernel(AttnMmaParams p) {
+  constexpr int kThreads = kWarps * 32;
+  constexpr int BM = kWarps * 16;
+  constexpr int NT = BN / 8;
+  constexpr int kStride = HD + 8;
+  extern __shared__ __align__(16) uint8_t smem_raw_mma[];
+  __half* Qs = reinterpret_cast<__half*>(smem_raw_mma);   // 2 x [BM][kStride]
+  __half* Ks = Qs + 2 * BM * kStride;
+  __half* Vs = Ks + BN * kStride;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const __half* qb = p.q + static_cast<long long>(b) * p.Nq * p.ldq + h * p.q_hs;
+  const __half* kb = p.k + static_cast<long long>(b) * p.Nk * p.ldk + h * p.k_hs;
+  const __half* vb = p.v + static_cast<long long>(b) * p.Nk * p.ldv + h * p.v_hs;
+  const int n_tiles = (p.Nq + BM - 1) / BM;
+
+  load_tile_async<HD, kThreads>(Ks, kb, p.ldk, 0, BN, p.Nk);
+  load_tile_async<HD, kThreads>(Vs, vb, p.ldv, 0, BN, p.Nk);
+  int tile = blockIdx.x;
+  if (tile < n_tiles) load_tile_async<HD, kThreads>(Qs, qb, p.ldq, tile * BM, BM, p.Nq);
+  cp_async_commit();
+
+  const uint32_t k_addr = smem_u32(Ks + ((lane & 7) + ((lane >> 4) << 3)) * kStride + ((lane >> 3) & 1) * 8);
+  const uint32_t v_addr = smem_u32(Vs + ((lane & 7) + (((lane >> 3) & 1) << 3)) * kStride + (lane >> 4) * 8);
+  const int valid = p.Nk;  // <= BN
+
+  for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
+    __half* Qc = Qs + (it & 1) * BM * kStride;
+    __syncthreads();   // everyone is done with the other buffer (tile it - 1: its O staging has been written out)
+    const int next = tile + gridDim.x;
+    if (next < n_tiles) load_tile_async<HD, kThreads>(Qs + ((it + 1) & 1) * BM * kStride, qb, p.ldq, next * BM, BM, p.Nq);
+    cp_async_commit();
+    cp_async_wait<1>();   // this tile's Q (and, the first time, K / V) have landed for this thread
+    __syncthreads();      // ... and for every other thread
+
+    const uint32_t q_addr = smem_u32(Qc + (warp * 16 + (lane & 15)) * kStride + (lane >> 4) * 8);
+    float s[NT][4];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < HD / 16; ++kk) {
+      uint32_t a0, a1, a2, a3;
+      ldsm_x4(q_addr + kk * 32, a0, a1, a2, a3);
+#pragma unroll
+      for (int nt = 0; nt < NT / 2; ++nt) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4(k_addr + (nt * 16 * kStride + kk * 16) * 2, b0, b1, b2, b3);
+        mma16816(s[2 * nt], a0, a1, a2, a3, b0, b1);
+        mma16816(s[2 * nt + 1], a0, a1, a2, a3, b2, b3);
+      }
+    }
+    if (valid < BN) {
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int c = nt * 8 + (lane & 3) * 2;
+        if (c >= valid) s[nt][0] = s[nt][2] = -INFINITY;
+        if (c + 1 >= valid) s[nt][1] = s[nt][3] = -INFINITY;
+      }
+    }
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
+    }
+    float sum[2] = {0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      mx[r] *= -kLog2eMma;
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      s[nt][0] = ex2f(fmaf(s[nt][0], kLog2eMma, mx[0]));
+      s[nt][1] = ex2f(fmaf(s[nt][1], kLog2eMma, mx[0]));
+      s[nt][2] = ex2f(fmaf(s[nt][2], kLog2eMma, mx[1]));
+      s[nt][3] = ex2f(fmaf(s[nt][3], kLog2eMma, mx[1]));
+      sum[0] += s[nt][0] + s[nt][1];
+      sum[1] += s[nt][2] + s[nt][3];
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 1);
+      sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 2);
+      sum[r] = 1.0f / sum[r];
+    }
+    float o[HD / 8][4];
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < BN / 16; ++kk) {
+      const uint32_t a0 = pack_half2(s[2 * kk][0], s[2 * kk][1]);
+      const uint32_t a1 = pack_half2(s[2 * kk][2], s[2 * kk][3]);
+      const uint32_t a2 = pack_half2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      const uint32_t a3 = pack_half2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+      for (int dt = 0; dt < HD / 16; ++dt) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4_t(v_addr + (kk * 16 * kStride + dt * 16) * 2, b0, b1, b2, b3);
+        mma16816(o[2 * dt], a0, a1, a2, a3, b0, b1);
+        mma16816(o[2 * dt + 1], a0, a1, a2, a3, b2, b3);
+      }
+    }
+    // ---- O through this warp's own 16 rows of the consumed Q buffer, then 16-byte row segments to global ----
+    __syncwarp();   // every lane's ldmatrix reads of these rows are done
+    {
+      __half* orow = Qc + (warp * 16 + (lane >> 2)) * kStride + (lane & 3) * 2;
+#pragma unroll
+      for (int i = 0; i < HD / 8; ++i) {
+        *reinterpret_cast<uint32_t*>(orow + i * 8) = pack_half2(o[i][0] * sum[0], o[i][1] * sum[0]);
+        *reinterpret_cast<uint32_t*>(orow + 8 * kStride + i * 8) = pack_half2(o[i][2] * sum[1], o[i][3] * sum[1]);
+      }
+    }
+    __syncwarp();
+    constexpr int kVec = HD / 8;
+    for (int i = lane; i < 16 * kVec; i += 32) {
+      const int r = i / kVec, c = i - r * kVec;
+      const int row = tile * BM + warp * 16 + r;
+      if (row < p.Nq)
+        *reinterpret_cast<uint4*>(p.out + (static_cast<long long>(b) * p.Nq + row) * p.ldo + h * HD + c * 8) =
+            *reinterpret_cast<const uint4*>(Qc + (warp * 16 + r) * kStride + c * 8);
+    }
+  }
+  cp_async_wait<0>();
+}
+
 // merge the split-KV partials: out = sum_s exp(m_s - m) O_s / sum_s exp(m_s - m) l_s.  One CTA per (row, h, b).
 __global__ void attn_combine_kernel(const float* __restrict__ part_o, const float* __restrict__ part_ml, int Nq,
                                     int H, int n_splits, int HD, __half* __restrict__ out, long long ldo) {
@@ -251,6 +436,7 @@ __global__ void attn_combine_kernel(const float* __restrict__ part_o, const floa
 }
 
 static int g_attn_mma_wide = 1;
+static int g_attn_mma_pipe = 1;   // CWM_XATTN_PIPE=0: the un-pipelined split-key loop
 static int g_attn_mma_split = 512;  // keys per CTA when few queries face a long key axis (multiple of 64)
 
 static void pick_splits(int Nq, int Nk, int* n_splits, int* kv_per_split) {
@@ -264,16 +450,16 @@ static void pick_splits(int Nq, int Nk, int* n_splits, int* kv_per_split) {
   }
 }
 
-template <int HD, int kWarps, int BN>
+template <int HD, int kWarps, int BN, bool kPipe = false>
 static int launch_attn_mma_bn(const AttnMmaParams& p, int B, cudaStream_t s) {
-  constexpr int smem = (kWarps * 16 + 2 * BN) * (HD + 8) * 2;
+  constexpr int smem = (kWarps * 16 + (kPipe ? 4 : 2) * BN) * (HD + 8) * 2;
   static bool attr_set = false;
   if (!attr_set) {
-    CWM_CUDA_CHECK(cudaFuncSetAttribute(attn_mma_kernel<HD, kWarps, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CWM_CUDA_CHECK(cudaFuncSetAttribute(attn_mma_kernel<HD, kWarps, BN, kPipe>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
   dim3 grid((p.Nq + kWarps * 16 - 1) / (kWarps * 16), p.H, B * p.n_splits);
-  attn_mma_kernel<HD, kWarps, BN><<<grid, kWarps * 32, smem, s>>>(p);
+  attn_mma_kernel<HD, kWarps, BN, kPipe><<<grid, kWarps * 32, smem, s>>>(p);
   CWM_LAUNCH_CHECK();
   return CWM_OK;
 }
@@ -282,7 +468,28 @@ template <int HD, int kWarps>
 static int launch_attn_mma(const AttnMmaParams& p, int B, cudaStream_t s) {
   // at most 32 keys in total (the 25 IMU tokens of the encoder-side cross attention): 32-row key tile
   if (p.Nk <= 32 && p.n_splits == 1) return launch_attn_mma_bn<HD, kWarps, 32>(p, B, s);
+  // split keys (few queries against a long key axis): 32-key tiles, double-buffered
+  if (p.n_splits > 1 && g_attn_mma_pipe) return launch_attn_mma_bn<HD, kWarps, 32, true>(p, B, s);
   return launch_attn_mma_bn<HD, kWarps, 64>(p, B, s);
+}
+
+template <int HD, int kWarps, int BN>
+static int launch_attn_trg(const AttnMmaParams& p, int B, cudaStream_t s) {
+  constexpr int smem = (2 * kWarps * 16 + 2 * BN) * (HD + 8) * 2;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CWM_CUDA_CHECK(cudaFuncSetAttribute(attn_mma_trg_kernel<HD, kWarps, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  // query tiles per (sample, head) are spread over gx CTAs so that the grid is ~4 CTAs per SM: each CTA then walks several
+  // tiles with K / V staged once and the next Q tile in flight
+  const int n_tiles = (p.Nq + kWarps * 16 - 1) / (kWarps * 16);
+  int gx = (4 * num_sms() + p.H * B - 1) / (p.H * B);
+  gx = gx < 1 ? 1 : (gx > n_tiles ? n_tiles : gx);
+  dim3 grid(gx, p.H, B);
+  attn_mma_trg_kernel<HD, kWarps, BN><<<grid, kWarps * 32, smem, s>>>(p);
+  CWM_LAUNCH_CHECK();
+  return CWM_OK;
 }
 
 }  // namespace cwm
@@ -337,6 +544,33 @@ extern "C" int cwm_attention_generic_f16(const uint16_t* q, const uint16_t* k, c
   // (head dims above 128 need > 160 registers per thread: one 8-warp CTA per SM would be slower -- measured)
   const bool wide = Nq >= 1024 && Nk <= 64 && head_dim <= 128 && g_attn_mma_wide;
   int rc;
+  static int trg_env = -1;
+  if (trg_env < 0) {
+    const char* e = getenv("CWM_XATTN_TRG");
+    trg_env = (e == nullptr) ? 1 : atoi(e);
+    e = getenv("CWM_XATTN_PIPE");
+    if (e != nullptr) g_attn_mma_pipe = atoi(e);
+  }
+  // many queries against one resident K / V tile (cross-attention "trg" direction): the tile-walking kernel
+  const bool trg = trg_env != 0 && Nq >= 512 && Nk <= 64 && p.n_splits == 1 && ldo % 8 == 0 &&
+                   reinterpret_cast<uintptr_t>(out) % 16 == 0;
+#define CWM_TRG_CASE(HDV)                                                                                   \
+  case HDV:                                                                                                 \
+    rc = Nk <= 32 ? launch_attn_trg<HDV, 4, 32>(p, B, s) : launch_attn_trg<HDV, 4, 64>(p, B, s);            \
+    break;
+  if (trg && B <= 65535) {
+    switch (head_dim) {
+      CWM_TRG_CASE(32)
+      CWM_TRG_CASE(64)
+      CWM_TRG_CASE(96)
+      CWM_TRG_CASE(128)
+      CWM_TRG_CASE(192)
+      default:
+        return fail(CWM_ERR_UNSUPPORTED, "cwm_attention_generic_f16: head_dim %d (supported: 32, 64, 96, 128, 192)", head_dim);
+    }
+    return rc;
+  }
+#undef CWM_TRG_CASE
 #define CWM_MMA_CASE(HDV)                                                            \
   case HDV:                                                                          \
     rc = narrow ? launch_attn_mma<HDV, 2>(p, B, s)                                   \

@@ -280,6 +280,9 @@ def _attn_ref3(q, k, v):
     (2, 788, 25, 4, 192), (2, 1600, 50, 4, 96), (1, 70, 5, 4, 64), (2, 100, 1, 4, 192),  # cross, trg direction
     (2, 25, 3140, 4, 192), (2, 50, 6336, 4, 96), (1, 5, 72, 4, 32), (2, 1, 784, 4, 192),  # cross, src direction
     (1, 300, 300, 2, 128),
+    # the tile-walking trg kernel (Nq >= 512, one resident K / V tile) at the model sizes and at ragged / minimal ones
+    (1, 3140, 25, 4, 192), (1, 6336, 50, 4, 96), (2, 512, 64, 4, 128), (3, 1000, 33, 2, 64), (1, 777, 7, 3, 32),
+    (40, 513, 32, 4, 96),
 ])
 def test_attention_generic(B, Nq, Nk, H, d):
     g = torch.Generator().manual_seed(Nq * 31 + Nk)
@@ -295,10 +298,11 @@ def test_attention_generic(B, Nq, Nk, H, d):
     assert err.max().item() <= 6e-3 and err.mean().item() <= 6e-4, (err.max().item(), err.mean().item())
 
 
-def test_attention_generic_cross_layout():
+@pytest.mark.parametrize("N", [300, 1500])
+def test_attention_generic_cross_layout(N):
     """The interleaved [qk | v] layout of BidirectionalCrossAttention (transformer.py:333-365): head h of qk owns
     columns [2*hd*h, 2*hd*(h+1)), first hd for the trg similarity, last hd for the src similarity."""
-    B, N, M, H, hd = 2, 300, 25, 4, 96
+    B, M, H, hd = 2, 25, 4, 96
     D = H * hd
     g = torch.Generator().manual_seed(5)
     qkv = (torch.randn(B * N, 3 * D, generator=g) * 0.3).to(torch.float16)
