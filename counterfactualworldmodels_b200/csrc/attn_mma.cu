@@ -554,9 +554,19 @@ extern "C" int cwm_attention_generic_f16(const uint16_t* q, const uint16_t* k, c
   // many queries against one resident K / V tile (cross-attention "trg" direction): the tile-walking kernel
   const bool trg = trg_env != 0 && Nq >= 512 && Nk <= 64 && p.n_splits == 1 && ldo % 8 == 0 &&
                    reinterpret_cast<uintptr_t>(out) % 16 == 0;
+  static int trg_warps = -1;
+  if (trg_warps < 0) {
+    const char* e = getenv("CWM_XATTN_TRG_WARPS");
+    trg_warps = (e == nullptr) ? 4 : atoi(e);
+  }
+  const bool trg8 = trg_warps == 8 && head_dim <= 128;
 #define CWM_TRG_CASE(HDV)                                                                                   \
   case HDV:                                                                                                 \
-    rc = Nk <= 32 ? launch_attn_trg<HDV, 4, 32>(p, B, s) : launch_attn_trg<HDV, 4, 64>(p, B, s);            \
+    if (trg8 && HDV <= 128)                                                                                 \
+      rc = Nk <= 32 ? launch_attn_trg<HDV, (HDV <= 128 ? 8 : 4), 32>(p, B, s)                               \
+                    : launch_attn_trg<HDV, (HDV <= 128 ? 8 : 4), 64>(p, B, s);                              \
+    else                                                                                                    \
+      rc = Nk <= 32 ? launch_attn_trg<HDV, 4, 32>(p, B, s) : launch_attn_trg<HDV, 4, 64>(p, B, s);          \
     break;
   if (trg && B <= 65535) {
     switch (head_dim) {
