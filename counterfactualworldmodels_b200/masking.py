@@ -294,67 +294,7 @@ class RotatedTableEnergyMaskingGenerator(EnergySamplingMaskingGenerator):
 
 
 # ---- IMU token masks (masking.py:402-476): the head-motion stream of the conjoined models ------------------------
-class FullMaskGenerator(MaskingGenerator):
-    """masking.py:402-431: the sampled mask, or -- with probability ``full_mask_prob`` / ``full_vis_prob`` -- an all-masked
-    / all-visible one.  Draw order on ``self.rng`` as in the reference: one ``rand`` for "partial?", a second only if not."""
 
-    def __init__(self, full_mask_prob=0.2, full_vis_prob=0.0, always_batch=True, full_mask_per_example=False, *args,
-                 **kwargs):
-        super().__init__(always_batch=always_batch, *args, **kwargs)
-        self.full_mask_prob = min(max(full_mask_prob, 0), 1)
-        self.full_vis_prob = min(max(full_vis_prob, 0), 1)
-        self.partial_prob = max(1 - self.full_mask_prob - self.full_vis_prob, 0)
-        self._final_full_mask_prob = self.full_mask_prob / max(self.full_mask_prob + self.full_vis_prob, 1e-6)
-        self._per_sample = full_mask_per_example
-
-    def forward(self, x=None, num_frames=None):
-        masks = super().forward(x=x, num_frames=num_frames)
-        if self._per_sample:
-            fully_masked = (torch.rand((masks.size(0), 1)).to(masks.device) < self.full_mask_prob).expand(-1, masks.size(-1))
-            return torch.maximum(masks, fully_masked)
-        if self.rng.rand() < self.partial_prob:
-            return masks
-        if self.rng.rand() < self._final_full_mask_prob:
-            return torch.ones_like(masks)
-        return torch.zeros_like(masks)
-
-
-class ImuFullMaskGenerator(FullMaskGenerator):
-    """masking.py:433-446: a 1 x 1 x num_tokens "image"."""
-
-    def __init__(self, input_size=10, clumping_factor=1, *args, **kwargs):
-        if not isinstance(input_size, int):
-            input_size = int(np.prod(input_size))
-        super().__init__(input_size=(1, 1, input_size), clumping_factor=(1, clumping_factor), *args, **kwargs)
-
-
-class MissingDataImuMaskGenerator(ImuFullMaskGenerator):
-    """masking.py:448-476: tokens whose IMU samples are missing are always masked; unless the mode is 'none' the rows
-    are then rectangularised (equal number of masked tokens per row)."""
-
-    def __init__(self, truncation_mode='max', *args, **kwargs):
-        super().__init__(*args, **kwargs)
-        from .prediction import RectangularizeMasks
-        self.rect = RectangularizeMasks(truncation_mode)
-
-    def set_mode(self, mode):
-        self.rect.set_mode(mode)
-
-    @property
-    def mode(self):
-        return self.rect._mode
-
-    def forward(self, missing=None):
-        masks = super().forward(x=missing)
-        if missing is None:
-            return masks
-        assert missing.dtype == torch.bool, missing.dtype
-        assert list(missing.shape) == list(masks.shape), (missing.shape, masks.shape)
-        merged = torch.maximum(masks, missing.to(masks.device))
-        return merged if self.mode in ['none', None] else self.rect(merged)
-
-
-# ---- patch neighbourhoods (masking.py:32-71): used by the GUI helpers get_nearby_patches / generate_cutout_mask ------
 def patch_distance_transform(masks, self_mask=True):
     """For each patch the L-inf distance to the nearest visible patch, in units of half the grid (masking.py:32-56).
     masks bool [B, T, H, W] (True = masked) -> float [B, T, H, W]."""

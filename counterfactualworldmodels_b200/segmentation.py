@@ -500,274 +500,4 @@ class FlowGenerator(PredictorBasedGenerator):
         return (y_mocos, flow_mocos)
 
 
-class ImuGenerator(FlowGenerator):
-    """Wraps predictors that take and predict IMU tokens beside the RGB video (segmentation.py:549-754): conjoined
-    VMAEs with an IMU context stream, e.g. flow2imu.  Host-side bookkeeping around ``self.predictor(...)``."""
-
-    def __init__(self, *args, head_mask_generator=None, head_mask_ratio=0, always_use_predicted=False,
-                 require_none_missing=False, **kwargs):
-        super().__init__(*args, **kwargs)
-        from . import masking
-        assert hasattr(self.predictor, 'context_stream')
-        self._is_padded = hasattr(self.predictor.context_stream, 'padding_mask')
-        self.num_head_tokens = self.predictor.context_stream.encoder.num_tokens
-        if self.mask_generator is None:  # all of the video visible (:566-571)
-            self.mask_generator = masking.MaskingGenerator(input_size=self.predictor.mask_size, mask_ratio=0,
-                                                           always_batch=True, create_on_cpu=False)
-        if head_mask_generator is not None:
-            self.head_mask_generator = head_mask_generator
-        else:
-            self.set_head_mask_generator()
-            self.set_head_mask_params(mask_ratio=head_mask_ratio)
-        self._always_use_predicted = always_use_predicted
-        self._require_none_missing = require_none_missing
-        self.missing_imu = None
-
-    def set_head_mask_generator(self):
-        from . import masking
-        self.head_mask_generator = masking.MissingDataImuMaskGenerator(
-            input_size=(self.num_head_tokens), mask_ratio=0, full_mask_prob=0, full_vis_prob=0, truncation_mode='none',
-            create_on_cpu=True)
-
-    def set_head_mask_params(self, **kwargs):
-        for k, v in kwargs.items():
-            setattr(self.head_mask_generator, k, v)
-
-    def set_mode(self, mode='output'):
-        if mode not in ('output', 'input'):
-            raise ValueError("%s is not a known mode" % mode)
-        self.set_head_mask_params(mask_ratio=1.0 if mode == 'output' else 0.0)
-
-    def input_mode(self):
-        self.set_mode('input')
-
-    def output_mode(self):
-        self.set_mode('output')
-
-    def _imagenet_unnormalize(self, x, c_dim):
-        from .vmae import IMAGENET_DEFAULT_MEAN, IMAGENET_DEFAULT_STD
-        shape = [1] * x.dim()
-        shape[c_dim] = 3
-        mean = torch.as_tensor(IMAGENET_DEFAULT_MEAN, device=x.device, dtype=x.dtype).view(shape)
-        std = torch.as_tensor(IMAGENET_DEFAULT_STD, device=x.device, dtype=x.dtype).view(shape)
-        return x * std + mean
-
-    def get_imu_input(self, inp_dict, imu_mode='input', missing_thresh=0.5, device=None):
-        """segmentation.py:612-639: a dataset dict (``video`` normalised [B, C, T, H, W], ``imu`` [B, L, 6],
-        ``imu_missing_data``, ``video_ts``) -> (raw video [B, T, C, H, W], imu [B, 6, L], missing, imu mask, timestamps)."""
-        if imu_mode is not None:
-            self.set_mode(imu_mode)
-        add_batch_dim = (len(inp_dict['imu'].shape) != 3)
-        _unsq = lambda v: (v.unsqueeze(0) if add_batch_dim else v)  # noqa: E731
-        video = _unsq(inp_dict['video'])
-        if self.t_dim == 2:
-            x = self._imagenet_unnormalize(video, c_dim=1).transpose(1, 2)
-        else:
-            x = self._imagenet_unnormalize(video, c_dim=2)
-        imu = _unsq(inp_dict['imu'])
-        if self.t_dim == 2:
-            imu = imu.transpose(1, 2)
-        missing_imu = _unsq(inp_dict['imu_missing_data'])
-        missing_imu = missing_imu.view(missing_imu.size(0), self.num_head_tokens, -1)
-        imu_mask = self.head_mask_generator(missing_imu.float().mean(-1) > missing_thresh)
-        out_list = [x, imu, missing_imu, imu_mask, _unsq(inp_dict['video_ts'])]
-        if device is not None:
-            out_list = [v.to(device) for v in out_list]
-        return out_list
-
-    def reshape_input(self, x, tubelet_size=None):
-        """'b c (t pt) -> b t (pt c)' (:641-644)."""
-        pt = self.predictor.context_stream.patch_size[0] if tubelet_size is None else tubelet_size
-        B, C, L = x.shape
-        return x.reshape(B, C, L // pt, pt).permute(0, 2, 3, 1).reshape(B, L // pt, pt * C)
-
-    def reshape_output(self, y, tubelet_size=None):
-        """'b t (pt c) -> b c (t pt)' (:646-650)."""
-        pt = self.predictor.context_stream.patch_size[0] if tubelet_size is None else tubelet_size
-        B, T, D = y.shape
-        return y.reshape(B, T, pt, D // pt).permute(0, 3, 1, 2).reshape(B, D // pt, T * pt)
-
-    def predict_imu(self, inp_dict, imu_mask_ratio=1, device=None, get_labels=True):
-        """segmentation.py:652-718."""
-        self.set_head_mask_params(mask_ratio=imu_mask_ratio)
-        x, imu, missing_imu, imu_mask, timestamps = self.get_imu_input(inp_dict, device=device, imu_mode=None)
-        self.missing_imu = missing_imu
-        self.mask = self.mask_generator(x).to(x.device)
-        if imu_mask_ratio == 1:
-            imu_mask = torch.ones_like(imu_mask)
-        elif not self._is_padded:
-            imu_mask = self.mask_rectangularizer(imu_mask)
-        main_out, imu_out = self.predictor(x=x.transpose(1, 2), mask=self.mask, timestamps=timestamps, x_context=imu,
-                                           mask_context=imu_mask, output_main=True, output_context=True)
-        imu_labels_orig = self.reshape_input(imu)
-        if imu_mask_ratio == 1 and (not self._is_padded):
-            imu_labels, imu_pred = imu_labels_orig, imu_out
-        elif self._is_padded:  # padded models: pick the non-padding tokens apart again
-            imu_labels = self.predictor.get_masked_imu(imu, torch.ones_like(imu_mask))
-            imu_pred = torch.zeros_like(imu_labels)
-            null_mask = self.predictor.context_stream.null_mask
-            imu_true = self.predictor.get_masked_imu(imu, ~imu_mask)
-            imu_pred[null_mask] = imu_true[null_mask]
-            imu_pred[~null_mask] = imu_out[~null_mask]
-            _imu_pred, _imu_labels = imu_pred[~null_mask], imu_labels[~null_mask]
-            imu_pred = torch.zeros(imu_out.size(0), self.num_head_tokens, _imu_pred.size(-1)).to(_imu_pred)
-            imu_pred[imu_mask] = _imu_pred
-            imu_pred[~imu_mask] = imu_labels_orig[~imu_mask]
-            imu_labels = torch.zeros_like(imu_pred)
-            imu_labels[imu_mask] = _imu_labels
-            imu_labels[~imu_mask] = imu_labels_orig[~imu_mask]
-            self.predictor.context_stream._reset_padding_mask()
-        else:
-            imu_labels = imu_labels_orig
-            imu_pred = torch.zeros_like(imu_labels)
-            imu_true = self.predictor.get_masked_imu(imu, ~imu_mask)
-            imu_pred[~imu_mask] = imu_true.view(-1, imu_pred.size(-1))
-            imu_pred[imu_mask] = imu_out.view(-1, imu_pred.size(-1))
-        if getattr(self.predictor, '_main_padded', False):
-            self.predictor.main_stream._reset_padding_mask()
-        return (imu_pred, imu_labels) if get_labels else imu_pred
-
-    @property
-    def any_imu(self):
-        return None if self.missing_imu is None else ~(torch.amin(self.missing_imu, (-2, -1)).bool())
-
-    @property
-    def full_imu(self):
-        return None if self.missing_imu is None else ~(torch.amax(self.missing_imu, (-2, -1)).bool())
-
-    def forward(self, inp_dict, imu_mask_ratio=1, device=None):
-        """The predicted IMU where the dataset has none and (optionally) the true IMU where it has (:731-754)."""
-        imu_pred, imu_labels = self.predict_imu(inp_dict, imu_mask_ratio=imu_mask_ratio, device=device, get_labels=True)
-        if self._always_use_predicted:
-            imu_out = imu_pred
-        elif self._require_none_missing:
-            imu_out = torch.where(self.full_imu[:, None, None], imu_labels, imu_pred)
-        else:
-            imu_out = torch.where(self.any_imu[:, None, None], imu_labels, imu_pred)
-        if self._always_use_predicted:
-            missing_imu = torch.zeros_like(self.missing_imu)
-        else:
-            missing_imu = torch.where(self.any_imu[:, None, None], self.missing_imu, torch.zeros_like(self.missing_imu))
-        return (imu_out, missing_imu)
-
-
-class ImuConditionedFlowGenerator(FlowGenerator):
-    """Two models (segmentation.py:756-967): (1) ``head_motion_predictor`` predicts ~2 s of IMU from a frame pair
-    (flow2imu), (2) ``predictor`` is a masked predictor conditioned on video patches and that IMU.  BASELINE config 5's
-    sweep: the IMU of the static movie is predicted ONCE per image, then all S counterfactuals are conditioned on it."""
-    default_imu_generator_kwargs = {'head_mask_ratio': 1}
-
-    def __init__(self, *args, predictor, head_motion_predictor=None, head_motion_load_path=None,
-                 head_motion_generator=ImuGenerator, head_motion_kwargs=default_imu_generator_kwargs,
-                 head_motion_mask_generator=None, flow_model=None, flow_model_load_path=None, **kwargs):
-        super().__init__(*args, predictor=predictor, flow_model=flow_model, flow_model_load_path=flow_model_load_path,
-                         **kwargs)
-        if head_motion_predictor is None:
-            # extension: a predictor that is NOT conditioned on head motion (the plain VMAEs of BASELINE configs 1-4)
-            # -- the reference's docstring promises this works (movability.py:18-20) but its constructor cannot be
-            # called without a head-motion model; here the sweep then runs unconditioned
-            self.head_motion_generator = None
-            return
-        head_motion_kwargs = copy.deepcopy(head_motion_kwargs)
-        self._update_head_motion_kwargs(head_motion_load_path, head_motion_kwargs)
-        if not isinstance(head_motion_predictor, nn.Module):
-            head_motion_predictor = head_motion_predictor()
-        self.head_motion_generator = head_motion_generator(
-            predictor=head_motion_predictor, mask_generator=head_motion_mask_generator, flow_model=self.flow_model,
-            **head_motion_kwargs)
-
-    def _update_head_motion_kwargs(self, load_path, kwargs):
-        kwargs['imagenet_normalize_inputs'] = kwargs.get('imagenet_normalize_inputs', self.imagenet_normalize_inputs)
-        kwargs['temporal_dim'] = kwargs.get('temporal_dim', self.predictor.t_dim)
-        if load_path is not None:
-            raise NotImplementedError("head_motion_load_path: load the checkpoint into head_motion_predictor yourself")
-
-    @property
-    def num_head_tokens(self):
-        return self.head_motion_generator.num_head_tokens
-
-    @property
-    def head_tubelet_size(self):
-        return self.head_motion_generator.predictor.context_stream.patch_size[0]
-
-    @property
-    def head_motion_channels(self):
-        return getattr(self.head_motion_generator.predictor.get_context_input, 'num_channels', 6)
-
-    def get_fake_head_motion(self, x):
-        """An all-zero IMU input and an all-masked IMU mask for the head-motion predictor (:818-832)."""
-        B = x.size(0)
-        head_motion = torch.zeros((B, self.head_tubelet_size * self.num_head_tokens, self.head_motion_channels),
-                                  device=x.device).to(x.dtype)
-        head_mask = torch.ones((B, self.num_head_tokens), device=x.device).bool()
-        if self.head_motion_generator.t_dim == 2:
-            head_motion = head_motion.transpose(self.head_motion_generator.t_dim, self.head_motion_generator.c_dim)
-        return (head_motion, head_mask)
-
-    def predict_imu_from_video(self, x, timestamps=None):
-        """segmentation.py:834-871.  (The reference's branch for a PADDED head-motion predictor calls methods that do
-        not exist -- ``reshape_imu``, ``torch.zeros_like(int, ...)`` -- so it can never have run; it raises here.)"""
-        fake_imu, imu_mask = self.get_fake_head_motion(x)
-        G = self.head_motion_generator
-        mask = G.mask_generator(x).to(x.device)
-        imu_out = G.predictor(G._preprocess(x), mask=mask, timestamps=timestamps, x_context=fake_imu,
-                              mask_context=imu_mask, output_main=False, output_context=True)
-        if G._is_padded:
-            raise NotImplementedError("padded head-motion predictors (the reference's own branch is broken, :850-869)")
-        return imu_out
-
-    def get_static_imu(self, x=None, timestamps=None):
-        x = self.x if x is None else x
-        return self.predict_imu_from_video(torch.tile(x[:, 0:1], (1, x.size(1), 1, 1, 1)), timestamps=timestamps)
-
-    def get_zeros_imu(self, x=None, timestamps=None):
-        x = self.x if x is None else x
-        return torch.zeros_like(self.predict_imu_from_video(x, timestamps=timestamps))
-
-    def predict_imu_video_and_flow(self, x, mask=None, timestamps=None, head_motion=None, mask_head_motion=False,
-                                   static_head_motion=False, return_flow=True, return_head_motion=False, *args,
-                                   **kwargs):
-        """segmentation.py:885-929."""
-        self.set_input(x)
-        self.mask = self.generate_mask(x) if mask is None else mask
-        if head_motion is not None:
-            h = head_motion
-        elif static_head_motion:
-            h = self.get_static_imu()
-        else:
-            h = self.predict_imu_from_video(x, timestamps=timestamps)
-        if return_head_motion:
-            return h
-        h_mask = torch.zeros(h.size(0), self.num_head_tokens).bool().to(h.device)
-        if mask_head_motion:
-            h_mask = ~h_mask
-        y, flow = self.predict_video_and_flow(x, mask=self.mask, timestamps=timestamps,
-                                              x_context=self.head_motion_generator.reshape_output(h),
-                                              mask_context=h_mask, *args, **kwargs)
-        self.reset_padding_masks()
-        return (y, flow)
-
-    def predict_counterfactual_videos_and_flows(self, x, *args, head_motion=None, timestamps=None,
-                                                mask_head_motion=False, static_head_motion=True, **kwargs):
-        """segmentation.py:931-963: head motion once per image, then the conditioned counterfactual sweep."""
-        if self.head_motion_generator is None:
-            return super().predict_counterfactual_videos_and_flows(x, *args, **kwargs)
-        self.set_input(x)
-        # like the reference, the sweep's own arguments are forwarded: the first positional one (the active patches)
-        # lands in ``mask`` and the call returns the head motion before anything else is used
-        h = self.predict_imu_video_and_flow(x, *args, head_motion=head_motion, static_head_motion=static_head_motion,
-                                            return_head_motion=True, **kwargs)
-        self.mask = None
-        self.reset_padding_masks()
-        h_mask = torch.zeros(h.size(0), self.num_head_tokens).bool().to(h.device)
-        if mask_head_motion:
-            h_mask = ~h_mask
-        h = self.head_motion_generator.reshape_output(h)
-        return super().predict_counterfactual_videos_and_flows(x, *args, timestamps=timestamps, x_context=h,
-                                                               mask_context=h_mask, **kwargs)
-
-    def forward(self, *args, **kwargs):
-        return self.predict_imu_video_and_flow(*args, **kwargs)
-
-
-__all__ = ["FlowGenerator", "ImuGenerator", "ImuConditionedFlowGenerator", "CounterfactualVideo"]
+__all__ = ["FlowGenerator", "CounterfactualVideo"]

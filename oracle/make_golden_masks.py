@@ -61,7 +61,11 @@ def draw_all(masking, sampling, seg_cls, vmae_mod):
     out["flowgen_energy_beta_s4_vis2"] = G.sample_patches_from_energy(energy_map(1, 32, 32, 2), num_samples=4,
                                                                       num_visible=2, beta=0.5)
     out["flowgen_zero_visible"] = G.sample_patches_from_energy(None, num_samples=2, num_visible=0)
-    # IMU token masks (masking.py:402-476): missing-data tokens forced masked, full-mask / full-visible draws
+    # IMU token masks (masking.py:402-476): missing-data tokens forced masked, full-mask / full-visible draws.  Drawn from
+    # the reference only: these generators belong to its ImuGenerator driver, which runs unchanged over the drop-in
+    # predictors and is not mirrored (tests/test_reference_wrappers_gpu.py)
+    if not hasattr(masking, "MissingDataImuMaskGenerator"):
+        return out
     miss = torch.zeros(4, 25, dtype=torch.bool)
     miss[1, :7] = True
     miss[3, 20:] = True

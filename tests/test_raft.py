@@ -588,78 +588,6 @@ def test_gpu_flow_generator_video_and_flow_entry_points():
 
 
 # ------------------------------------------------------------------------------------------------ IMU-conditioned sweep
-def test_imu_generators_host_logic():
-    """ImuGenerator / ImuConditionedFlowGenerator bookkeeping that needs no forward pass (segmentation.py:549-832)."""
-    import make_golden_imu_sweep as mg
-    from counterfactualworldmodels_b200 import conjoined_vmae as conj
-    from counterfactualworldmodels_b200 import raft, segmentation
-    pred, head = mg.build(conj, segmentation, raft, 'flow_model', _mirror(False))
-    G = segmentation.ImuConditionedFlowGenerator(predictor=pred, head_motion_predictor=head, flow_model=_mirror(False),
-                                                 imagenet_normalize_inputs=True, temporal_dim=2, raft_iters=3, seed=0)
-    H = G.head_motion_generator
-    assert isinstance(H, segmentation.ImuGenerator) and not H._is_padded
-    assert G.num_head_tokens == 5 and G.head_tubelet_size == 16 and G.head_motion_channels == 6
-    # constructing the inner generator (raft_iters defaults to 24) re-sets every RAFT it can see, the shared flow model
-    # included -- the reference does the same (segmentation.py:59, :86-90)
-    assert G.flow_model.iters == 24 and head.get_main_input.flow_model.iters == 24
-    fake, fmask = G.get_fake_head_motion(torch.zeros(2, 2, 3, 128, 128))
-    assert tuple(fake.shape) == (2, 6, 80) and fmask.dtype == torch.bool and bool(fmask.all()) and tuple(fmask.shape) == (2, 5)
-    imu = torch.arange(2 * 6 * 80, dtype=torch.float32).reshape(2, 6, 80)
-    tok = H.reshape_input(imu)
-    assert tuple(tok.shape) == (2, 5, 96) and torch.equal(H.reshape_output(tok), imu)
-    assert torch.equal(tok[0, 1, :6], imu[0, :, 16])                     # 'b c (t pt) -> b t (pt c)': c fastest
-    H.set_mode('output')
-    assert H.head_mask_generator.mask_ratio == 1.0
-    H.input_mode()
-    assert H.head_mask_generator.mask_ratio == 0.0
-    with pytest.raises(ValueError):
-        H.set_mode('sideways')
-    inp = {'video': torch.zeros(3, 2, 128, 128), 'imu': torch.zeros(80, 6), 'video_ts': torch.zeros(2),
-           'imu_missing_data': torch.cat([torch.ones(32), torch.zeros(48)])}
-    x, imu_in, missing, imu_mask, ts = H.get_imu_input(inp, imu_mode='input')
-    assert tuple(x.shape) == (1, 2, 3, 128, 128) and tuple(imu_in.shape) == (1, 6, 80) and tuple(missing.shape) == (1, 5, 16)
-    assert imu_mask.tolist() == [[True, True, False, False, False]]      # tokens with missing samples are masked
-    assert abs(float(x[0, 0, 0, 0, 0]) - 0.485) < 1e-6                   # imagenet_unnormalize of a zero video
-    H.missing_imu = missing
-    assert H.any_imu.tolist() == [True] and H.full_imu.tolist() == [False]
-
-
-@pytest.mark.gpu
-def test_gpu_imu_conditioned_sweep_matches_the_reference():
-    """BASELINE config 5's driver end to end on small models: flow2imu (RAFT inside its preprocessor) predicts the head
-    motion of the static movie once, then the S counterfactuals are predicted conditioned on it -- against the REAL
-    reference `ImuConditionedFlowGenerator` run on CPU (oracle/make_golden_imu_sweep.py).  Tolerances: the predictors run
-    f16 GEMMs with fp32 accumulation: pixels 2e-2 max-abs / 2e-3 mean-abs, head motion 2e-2 of its scale."""
-    import make_golden_imu_sweep as mg
-    from counterfactualworldmodels_b200 import conjoined_vmae as conj
-    from counterfactualworldmodels_b200 import raft, segmentation
-    d = load("imu_sweep_128px")
-    pred, head = mg.build(conj, segmentation, raft, 'flow_model', _mirror(False))
-    G = segmentation.ImuConditionedFlowGenerator(predictor=pred.to(DEV), head_motion_predictor=head.to(DEV),
-                                                 flow_model=_mirror(False).to(DEV), imagenet_normalize_inputs=True,
-                                                 temporal_dim=2, raft_iters=mg.RAFT_ITERS, seed=0)
-    x, active, passive = mg.sweep_inputs()
-    x, active, passive = x.to(DEV), active.to(DEV), passive.to(DEV)
-    old = torch.backends.cudnn.allow_tf32
-    torch.backends.cudnn.allow_tf32 = False
-    try:
-        G.set_input(x)
-        h = G.get_static_imu()
-        G.reset_padding_masks()
-        ys, flows = G.predict_counterfactual_videos_and_flows(x, active, passive, shifts=mg.SHIFTS, sample_batch_size=2,
-                                                              raft_iters=mg.RAFT_ITERS)
-    finally:
-        torch.backends.cudnn.allow_tf32 = old
-    assert tuple(h.shape) == (1, 5, 96) and tuple(ys.shape) == (4, 2, 3, 128, 128) and tuple(flows.shape) == (4, 1, 2, 128, 128)
-    e_h = rel_err(h.cpu().numpy(), d["head_motion"])
-    err = (ys[:, 1, :, ::2, ::2].cpu().numpy() - d["ys_frame1"])
-    print(f"imu sweep: head motion {e_h:.2e} of scale, frame-1 pixels max-abs {np.abs(err).max():.2e} mean-abs {np.abs(err).mean():.2e}")
-    assert e_h <= 2e-2
-    assert np.abs(err).max() <= 2e-2 and np.abs(err).mean() <= 2e-3
-    assert torch.isfinite(flows).all()
-    assert not hasattr(G.predictor, 'padding_mask')            # the wrappers reset the padding masks after every call
-
-
 @pytest.mark.gpu
 @pytest.mark.parametrize("B,D,H,W", [(2, 256, 28, 28), (1, 128, 16, 16), (3, 32, 9, 13), (2, 64, 30, 17)])
 def test_gpu_corr_volume_on_tensor_cores_keeps_fp32_accuracy(B, D, H, W, monkeypatch):

@@ -166,10 +166,15 @@ def test_reference_imu_conditioned_generator_over_the_dropin_conjoined_predictor
     import os
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "imu_sweep_128px.npz")
     d = np.load(path)
-    pred, head = mg.build(conj, ref_seg, our_raft, 'flow_model', flow_net())
+    head_flow = flow_net()
+    pred, head = mg.build(conj, ref_seg, our_raft, 'flow_model', head_flow)
     G = ref_seg.ImuConditionedFlowGenerator(predictor=pred.to(DEV), head_motion_predictor=head.to(DEV),
                                             flow_model=flow_net().to(DEV), imagenet_normalize_inputs=True, temporal_dim=2,
                                             raft_iters=mg.RAFT_ITERS, seed=0)
+    # reference quirk (segmentation.py:549-575): constructing the inner ImuGenerator re-sets every RAFT *of the reference's
+    # class* it can see to 24 iterations -- the one inside flow2imu's preprocessor included; a drop-in flow network is not
+    # found by that isinstance walk, so the same state is set by hand
+    head_flow.iters = 24
     assert type(G).__module__ == "cwm.models.segmentation" and "cwm.models.segmentation" in sys.modules
     x, active, passive = mg.sweep_inputs()
     x, active, passive = x.to(DEV), active.to(DEV), passive.to(DEV)
