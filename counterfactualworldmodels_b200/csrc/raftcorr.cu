@@ -14,6 +14,8 @@
 //
 // Data layout in HBM: level l of the pyramid is fp32 [B*H*W, H>>l, W>>l] (the reference's `corr_pyramid[l]` without
 // its singleton channel); 3.25 MB per sample at 28x28 / 4 levels.  The lookup output is [B, L*(2r+1)^2, H, W].
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace cwm {
@@ -529,6 +531,147 @@ raft_flow_update_taps_kernel(const __half* __restrict__ taps, int ldt, const flo
   if (dst2 != nullptr) *reinterpret_cast<uint32_t*>(dst2 + m * ld2) = o.x;
 }
 
+// ---- f16 lookup for the mixed-precision recurrent block (cwm_raft_corr_lookup_f16), radius 4, <= 4 levels ----
+// All (2r+1)^2 taps of a level are the centre plus INTEGER offsets, so they share one pair of bilinear fractions
+// (fx, fy): the 9x9 output window is the separable blend of a 10x10 source window,
+//   T[i][j] = W[i][j] + fx (W[i][j+1] - W[i][j]),   out[i][j] = T[i][j] + fy (T[i+1][j] - T[i][j]),
+// ~10 instructions per output instead of the ~120 of raft_corr_lookup_kernel, which restates the reference's normalise /
+// unnormalise coordinate arithmetic operation by operation for the fp32 parity path (issue-bound: 1240 warp instructions per
+// pixel).  The fractions here come from floor() directly; they differ from the reference's round trip by a few ulp, far
+// below the f16 rounding of the output.  Zero outside the map (grid_sample's zero padding); a non-finite centre gives zeros.
+// CTA = kFastPix pixels; phase 1: the 10x10 windows of every (pixel, level) are staged with coalesced loads (lanes run
+// along window rows); phase 2: one thread per (pixel, level, window row) blends its 9 outputs from shared memory and puts
+// them at channel l*81 + j*9 + i (x offset major, corr.py:37-47); phase 3: the rows leave as 16-byte segments.
+constexpr int kFastPix = 16;
+constexpr int kFastR = 4, kFastN1 = 9, kFastWin = 10, kFastPitch = 11;   // window rows padded to 11 floats: conflict-free
+constexpr int kFastWarps = 9;
+constexpr int kFastThreads = kFastWarps * 32;                              // 288 = half of the 16 x 4 x 9 blend tasks
+constexpr int kFastItems = kFastPix * 4;                                   // (pixel, level) windows per CTA
+
+struct FastItem {
+  const float* src;   // the (pixel, level) map; nullptr: nothing to load (level >= L, pixel >= P)
+  int gx0, gy0;       // map coordinates of window element (0, 0)
+  int Hl, Wl;
+  float fx, fy;
+};
+
+__global__ void __launch_bounds__(kFastThreads)
+raft_corr_lookup_fast_kernel(const __grid_constant__ CorrLevels lv, int L, const float* __restrict__ coords, long long P,
+                             int HW, __half* __restrict__ out16, int ld16) {
+  __shared__ float win[kFastItems * kFastWin * kFastPitch];     // [pix][lvl][10][11]
+  __shared__ __align__(16) __half rows[kFastPix * 328];         // [pix][ld <= 328]
+  __shared__ FastItem items[kFastItems];
+  const long long p0 = static_cast<long long>(blockIdx.x) * kFastPix;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < kFastItems) {
+    const int pix = tid >> 2, lvl = tid & 3;
+    const long long p = p0 + pix;
+    FastItem it;
+    it.src = nullptr;
+    it.gx0 = it.gy0 = 0;
+    it.Hl = it.Wl = 1;
+    it.fx = it.fy = 0.f;
+    if (p < P && lvl < L) {
+      const long long b = p / HW;
+      const int hw = static_cast<int>(p - b * HW);
+      float cx = __ldg(coords + (b * 2) * HW + hw);
+      float cy = __ldg(coords + (b * 2 + 1) * HW + hw);
+      // non-finite or absurd centres: every tap is out of bounds
+      if (!(fabsf(cx) < 1.0e6f) || !(fabsf(cy) < 1.0e6f)) cx = cy = -1.0e6f;
+      const float sc = 1.f / static_cast<float>(1 << lvl);      // coords / 2**lvl (exact)
+      const float x = cx * sc, y = cy * sc;
+      const float flx = floorf(x), fly = floorf(y);
+      it.Hl = lv.h[lvl];
+      it.Wl = lv.w[lvl];
+      it.src = lv.p[lvl] + p * (static_cast<long long>(it.Hl) * it.Wl);
+      it.gx0 = static_cast<int>(flx) - kFastR;
+      it.gy0 = static_cast<int>(fly) - kFastR;
+      it.fx = x - flx;
+      it.fy = y - fly;
+    }
+    items[tid] = it;
+  }
+  // pad columns [L*81, ld16)
+  for (int e = tid; e < kFastPix * (ld16 - L * 81); e += kFastThreads) {
+    const int pix = e / (ld16 - L * 81);
+    rows[pix * 328 + L * 81 + (e - pix * (ld16 - L * 81))] = __float2half_rn(0.f);
+  }
+  // lane-constant window positions of the four load rounds (elements lane, lane + 32, ... of the 10 x 10 window)
+  int wyx[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int e = lane + 32 * q;
+    const int wy = e / kFastWin;
+    wyx[q] = (e < kFastWin * kFastWin) ? ((wy << 8) | (e - wy * kFastWin)) : -1;
+  }
+  __syncthreads();
+  // ---- phase 1: a warp stages whole windows (coalesced along the window rows), two windows in flight ----
+  for (int i0 = warp; i0 < kFastItems; i0 += 2 * kFastWarps) {
+    float v[2][4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int item = i0 + h * kFastWarps;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v[h][q] = 0.f;
+      if (item < kFastItems) {
+        const FastItem it = items[item];
+        if (it.src != nullptr) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int gy = it.gy0 + (wyx[q] >> 8), gx = it.gx0 + (wyx[q] & 0xff);
+            if (wyx[q] >= 0 && static_cast<unsigned>(gx) < static_cast<unsigned>(it.Wl) &&
+                static_cast<unsigned>(gy) < static_cast<unsigned>(it.Hl))
+              v[h][q] = __ldg(it.src + gy * it.Wl + gx);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int item = i0 + h * kFastWarps;
+      if (item < kFastItems) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (wyx[q] >= 0) win[item * (kFastWin * kFastPitch) + (wyx[q] >> 8) * kFastPitch + (wyx[q] & 0xff)] = v[h][q];
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: separable blend, one task = (pixel, level, window row): 576 tasks = 2 rounds of 288 threads ----
+#pragma unroll
+  for (int round = 0; round < (kFastItems * kFastN1) / kFastThreads; ++round) {
+    const int task = tid + round * kFastThreads;
+    const int item = task / kFastN1;
+    const int i = task - item * kFastN1;
+    const int pix = item >> 2, lvl = item & 3;
+    if (lvl < L) {
+      const float fx = items[item].fx, fy = items[item].fy;
+      const float* w0 = win + item * (kFastWin * kFastPitch) + i * kFastPitch;
+      float t0[kFastN1], t1[kFastN1];
+      float a = w0[0], b = w0[kFastPitch];
+#pragma unroll
+      for (int j = 0; j < kFastN1; ++j) {
+        const float a1 = w0[j + 1], b1 = w0[kFastPitch + j + 1];
+        t0[j] = fmaf(fx, a1 - a, a);
+        t1[j] = fmaf(fx, b1 - b, b);
+        a = a1;
+        b = b1;
+      }
+      __half* dst = rows + pix * 328 + lvl * (kFastN1 * kFastN1) + i;
+#pragma unroll
+      for (int j = 0; j < kFastN1; ++j) dst[j * kFastN1] = __float2half_rn(fmaf(fy, t1[j] - t0[j], t0[j]));
+    }
+  }
+  __syncthreads();
+  // ---- phase 3: rows out ----
+  const int units = ld16 >> 3;   // ld16 % 8 == 0
+  for (int e = tid; e < kFastPix * units; e += kFastThreads) {
+    const int pix = e / units, u = e - pix * units;
+    if (p0 + pix < P)
+      *reinterpret_cast<uint4*>(out16 + (p0 + pix) * ld16 + u * 8) = *reinterpret_cast<const uint4*>(rows + pix * 328 + u * 8);
+  }
+}
+
 static int level_dims(int H, int W, int L, int* hs, int* ws, const char* who) {
   CWM_REQUIRE(L >= 1 && L <= kMaxLevels, "%s: num_levels %d not in [1, %d]", who, L, kMaxLevels);
   hs[0] = H;
@@ -628,6 +771,23 @@ static int corr_lookup_impl(const float* const* levels, int num_levels, int radi
   CWM_REQUIRE(smem <= 200 * 1024, "cwm_raft_corr_lookup: %d levels x radius %d needs %zu bytes of shared memory", num_levels,
               radius, smem);
   CWM_REQUIRE(H <= kMaxMapSide && W <= kMaxMapSide, "cwm_raft_corr_lookup: map (%d,%d) larger than %d", H, W, kMaxMapSide);
+  cudaStream_t st_fast = static_cast<cudaStream_t>(stream);
+  static int fast_env = -1;
+  if (fast_env < 0) {
+    const char* e = getenv("CWM_RAFT_LOOKUP");
+    fast_env = (e != nullptr && (e[0] == 'e' || e[0] == '0')) ? 0 : 1;   // CWM_RAFT_LOOKUP=exact: the reference-arithmetic kernel
+  }
+  if (out16 != nullptr && out == nullptr && fast_env && radius == kFastR && num_levels <= 4 && ld16 % 8 == 0 && ld16 <= 328 &&
+      ld16 >= num_levels * 81 && reinterpret_cast<uintptr_t>(out16) % 16 == 0) {
+    const long long Pf = static_cast<long long>(B) * H * W;
+    double pyr_f = 0.0;
+    for (int l = 0; l < num_levels; ++l) pyr_f += static_cast<double>(min(kFastWin, lv.w[l])) * min(kFastWin, lv.h[l]);
+    ProfileScope prof(st_fast, "raft_corr_lookup", 0.0, static_cast<double>(Pf) * (0.5 * ld16 + pyr_f + 2.0) * 4.0);
+    raft_corr_lookup_fast_kernel<<<static_cast<unsigned>((Pf + kFastPix - 1) / kFastPix), kFastThreads, 0, st_fast>>>(
+        lv, num_levels, coords, Pf, H * W, out16, ld16);
+    CWM_LAUNCH_CHECK();
+    return CWM_OK;
+  }
   auto kernel = radius == 4 ? raft_corr_lookup_kernel<4> : radius == 3 ? raft_corr_lookup_kernel<3> : raft_corr_lookup_kernel<-1>;
   static size_t configured[3] = {0, 0, 0};  // grow-only opt-in for > 48 KB of dynamic shared memory, per instantiation
   size_t& conf = configured[radius == 4 ? 0 : radius == 3 ? 1 : 2];

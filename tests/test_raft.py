@@ -459,7 +459,37 @@ def test_gpu_recurrent_block_kernels_match_the_oracle():
     out16 = torch.full((2 * 784, 328), 9.0, dtype=torch.float16, device=DEV)
     _lib.check(lib.cwm_raft_corr_lookup_f16(raft._ptr_table(block.corr_pyramid), 4, 4, c2.data_ptr(), 2, 28, 28,
                                             out16.data_ptr(), 328, s))
-    assert torch.equal(out16[:, :324], out32.permute(0, 2, 3, 1).reshape(-1, 324).half()) and out16[:, 324:].abs().max() == 0
+    want16 = out32.permute(0, 2, 3, 1).reshape(-1, 324)
+    # the fast f16 lookup takes the bilinear fractions from floor() directly instead of the reference's normalise /
+    # unnormalise round trip: the same value up to the f16 rounding of the output (1 ulp of the volume's scale)
+    scale = want16.abs().max().item()
+    assert (out16[:, :324].float() - want16).abs().max().item() <= 1.5e-3 * scale and out16[:, 324:].abs().max() == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,H,W,L", [(2, 28, 28, 4), (1, 17, 19, 4), (3, 16, 24, 3), (5, 9, 30, 2), (65, 28, 28, 4)])
+def test_gpu_fast_f16_lookup_matches_the_exact_lookup(B, H, W, L, monkeypatch):
+    """`raft_corr_lookup_fast_kernel` (separable blend of a staged 10x10 window; the mixed-precision recurrent block's lookup)
+    against the reference-arithmetic fp32 lookup: odd map sizes, fewer levels, far-out-of-bounds / half-integer / integer /
+    non-finite centres, pixel counts that do not fill the last CTA."""
+    from counterfactualworldmodels_b200 import _lib, raft
+    lib = _lib.load()
+    f1, f2 = ro.make_fmaps(B, 32, H, W, B + H)
+    block = raft.CorrBlock(torch.from_numpy(f1).to(DEV), torch.from_numpy(f2).to(DEV), num_levels=L, radius=4)
+    c = torch.from_numpy(ro.make_coords(B, H, W, 3, "random"))
+    c[0, 0, 0, 0], c[0, 1, 0, 1], c[0, 0, 1, 0] = float("nan"), float("inf"), -3.0e9
+    c = c.to(DEV)
+    want = block(c).permute(0, 2, 3, 1).reshape(-1, L * 81)
+    ld = (L * 81 + 7) // 8 * 8
+    out16 = torch.full((B * H * W, ld), 9.0, dtype=torch.float16, device=DEV)
+    _lib.check(lib.cwm_raft_corr_lookup_f16(raft._ptr_table(block.corr_pyramid), L, 4, c.data_ptr(), B, H, W, out16.data_ptr(), ld,
+                                            torch.cuda.current_stream().cuda_stream))
+    scale = want.abs().max().item()
+    err = (out16[:, :L * 81].float() - want).abs().max().item()
+    assert err <= 1.5e-3 * scale, (err, scale)
+    assert out16[:, L * 81:].abs().max().item() == 0 if ld > L * 81 else True
+    assert out16[:3].abs().max().item() == 0 or torch.isfinite(out16).all()          # non-finite centres give zeros
+    assert torch.isfinite(out16).all()
 
 
 @pytest.mark.gpu
