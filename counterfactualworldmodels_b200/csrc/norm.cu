@@ -116,40 +116,58 @@ instnorm_apply_kernel(const __half* __restrict__ x, const float2* __restrict__ p
 // at column (ky * k + kx) * Cin + c, zeros outside the image (the padding of the already-normalised image) and in the
 // columns [k*k*Cin, ldo).  The convolution is then ONE plain GEMM with K = ldo on the tcgen05 kernel.  One thread = one
 // 16-byte store (8 columns).
+constexpr int kIm2colTile = 32;   // output pixels of one image row per CTA
+// CIN / K / STRIDE / LDO > 0: compile-time shapes (the index arithmetic is all divisions by these; with run-time divisors
+// the kernel is instruction-bound: 370 us instead of ~100 us for 65 frames); 0 = take the run-time arguments.
+template <int CIN, int K, int STRIDE, int LDO>
 __global__ void __launch_bounds__(256)
-im2col_nchw_kernel(const float* __restrict__ img, int Cin, int H, int W, int Ho, int Wo, int k, int stride, int pad,
-                   float scale, float shift, long long M, __half* __restrict__ out, int ldo) {
-  const int units = ldo >> 3;
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= M * units) return;
-  const long long m = idx / units;
-  const int col0 = static_cast<int>(idx - m * units) * 8;
-  const int hw = Ho * Wo;
-  const long long s = m / hw;
-  const int pix = static_cast<int>(m - s * hw);
-  const int y0 = (pix / Wo) * stride - pad, x0 = (pix % Wo) * stride - pad;
+im2col_nchw_kernel(const float* __restrict__ img, int Cin_rt, int H, int W, int Ho, int Wo, int k_rt, int stride_rt, int pad,
+                   float scale, float shift, __half* __restrict__ out, int ldo_rt) {
+  const int Cin = CIN > 0 ? CIN : Cin_rt, k = K > 0 ? K : k_rt, stride = STRIDE > 0 ? STRIDE : stride_rt;
+  const int ldo = LDO > 0 ? LDO : ldo_rt;
+  // the input patch of this CTA's 32 output pixels: [Cin][k][WT] floats, WT = 31 * stride + k, staged with coalesced
+  // loads (normalised, zero outside the image); the im2col rows are then assembled from shared memory
+  extern __shared__ float patch[];
+  const int WT = (kIm2colTile - 1) * stride + k;
+  const int ox0 = blockIdx.x * kIm2colTile, oy = blockIdx.y;
+  const long long s = blockIdx.z;
   const float* im = img + s * Cin * static_cast<long long>(H) * W;
-  const int kk = k * k * Cin;
-  float v[8];
-  int tap = col0 / Cin, c = col0 - tap * Cin;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    v[i] = 0.f;
-    if (col0 + i < kk) {
-      const int ky = tap / k;
-      const int y = y0 + ky, x = x0 + tap - ky * k;
-      if (y >= 0 && y < H && x >= 0 && x < W) v[i] = fmaf(__ldg(im + (static_cast<long long>(c) * H + y) * W + x), scale, shift);
-    }
-    if (++c == Cin) {
-      c = 0;
-      ++tap;
-    }
+  const int gx0 = ox0 * stride - pad, gy0 = oy * stride - pad;
+  for (int idx = threadIdx.x; idx < Cin * k * WT; idx += 256) {
+    const int x = idx % WT, rc = idx / WT;
+    const int r = rc % k, c = rc / k;
+    const int gy = gy0 + r, gx = gx0 + x;
+    float v = 0.f;
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = fmaf(__ldg(im + (static_cast<long long>(c) * H + gy) * W + gx), scale, shift);
+    patch[idx] = v;
   }
-  const __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]), h2 = __floats2half2_rn(v[4], v[5]),
-                h3 = __floats2half2_rn(v[6], v[7]);
-  *reinterpret_cast<uint4*>(out + m * ldo + col0) =
-      make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
-                 *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
+  __syncthreads();
+  const int units = ldo >> 3, kk = k * k * Cin;
+  for (int task = threadIdx.x; task < kIm2colTile * units; task += 256) {
+    const int px = task / units, u = task - px * units;
+    if (ox0 + px >= Wo) continue;
+    const int col0 = u * 8;
+    int tap = col0 / Cin, c = col0 - tap * Cin;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[i] = 0.f;
+      if (col0 + i < kk) {
+        const int ky = tap / k;
+        v[i] = patch[(c * k + ky) * WT + px * stride + (tap - ky * k)];
+      }
+      if (++c == Cin) {
+        c = 0;
+        ++tap;
+      }
+    }
+    const __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]), h2 = __floats2half2_rn(v[4], v[5]),
+                  h3 = __floats2half2_rn(v[6], v[7]);
+    const long long m = (s * Ho + oy) * Wo + ox0 + px;
+    *reinterpret_cast<uint4*>(out + m * ldo + col0) =
+        make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
+                   *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
+  }
 }
 
 // out = relu?(a + b) on f16 rows (the residual joins of the batch-norm context encoder, whose norms are folded into the
@@ -235,12 +253,18 @@ extern "C" int cwm_im2col_nchw_f16(const float* img, int S, int Cin, int H, int 
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   CWM_REQUIRE(Ho >= 1 && Wo >= 1, "cwm_im2col_nchw_f16: empty output");
   const long long M = static_cast<long long>(S) * Ho * Wo;
-  const long long threads = M * (ldo / 8);
-  CWM_REQUIRE((threads + 255) / 256 < (1ll << 31), "cwm_im2col_nchw_f16: too many rows");
+  CWM_REQUIRE(S <= 65535 && Ho <= 65535, "cwm_im2col_nchw_f16: S=%d / Ho=%d exceed the grid limits", S, Ho);
+  const size_t smem = static_cast<size_t>(Cin) * k * ((cwm::kIm2colTile - 1) * stride + k) * sizeof(float);
+  CWM_REQUIRE(smem <= 48 * 1024, "cwm_im2col_nchw_f16: Cin=%d k=%d stride=%d needs %zu bytes of shared memory", Cin, k, stride, smem);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ProfileScope prof(st, "im2col_nchw", 0.0, static_cast<double>(M) * ldo * 2.0 + static_cast<double>(S) * Cin * H * W * 4.0);
-  cwm::im2col_nchw_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(
-      img, Cin, H, W, Ho, Wo, k, stride, pad, scale, shift, M, reinterpret_cast<__half*>(out), ldo);
+  const dim3 grid((Wo + cwm::kIm2colTile - 1) / cwm::kIm2colTile, Ho, S);
+  if (Cin == 3 && k == 7 && stride == 2 && ldo == 152)   // the encoders' stem (extractor.py:132)
+    cwm::im2col_nchw_kernel<3, 7, 2, 152><<<grid, 256, smem, st>>>(img, Cin, H, W, Ho, Wo, k, stride, pad, scale, shift,
+                                                                   reinterpret_cast<__half*>(out), ldo);
+  else
+    cwm::im2col_nchw_kernel<0, 0, 0, 0><<<grid, 256, smem, st>>>(img, Cin, H, W, Ho, Wo, k, stride, pad, scale, shift,
+                                                                 reinterpret_cast<__half*>(out), ldo);
   CWM_LAUNCH_CHECK();
   return CWM_OK;
 }
