@@ -29,7 +29,7 @@ constexpr int kGemmThreads = 384;
 constexpr int kEpiWarps = 8;
 constexpr int kChunkBytes = 32 * 128;  // one epilogue chunk: 32 rows x 128 bytes
 
-template <int BN, bool kRes>
+template <int BN, bool kRes, bool kConv = false>
 struct GemmCfg {
   // epilogue smem: kRes (fp32 out, optional residual): 2 buffers / warp, else 1 buffer / warp
   // (+ 2 KB per warp for the f16 copy the LayerNorm-producer epilogue emits: 32 rows x 64 bytes, 64B-swizzled)
@@ -43,7 +43,9 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBudget = 232448 - kEpiBytes - kBiasBytes - 512;
   static constexpr int kMaxStages = kBudget / kStageBytes;
-  static constexpr int kStages = kMaxStages > 6 ? 6 : kMaxStages;
+  // plain GEMMs: 6 stages are enough to cover the TMA latency; the convolution instantiation takes the whole budget (its
+  // halo mode carves the ring into up to 4 halo stages + the weight ring / the resident weight matrix)
+  static constexpr int kStages = kConv ? (kMaxStages > 8 ? 8 : kMaxStages) : (kMaxStages > 6 ? 6 : kMaxStages);
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
   static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBiasBytes + 512;
   static_assert(kStages >= 3, "pipeline too shallow");
@@ -123,6 +125,15 @@ struct ConvDev {
                       // pixel maps are tiled in both directions)
   int stride;         // 1 or 2: output pixel (y, x) reads input (stride * y + ky - pad_h, stride * x + kx - pad_w); the A
                       // tensor map then carries the traversal stride (one box still loads hb x wb pixels)
+  int wo;             // output pixels per tile row that are kept (= the tile pitch along x): wb, except in the 2-D halo mode
+                      // where a tile row of wb = 32 slots yields wb - 2 pad_w outputs (the halo of the row sits in the slots)
+  int halo_x;         // halo mode: the staged box starts halo_x pixels left of the tile's first output pixel ...
+  int tap_x;          // ... and tap (ky, kx) reads from ky * wb + kx + tap_x rows further down.  Full-row tiles (maps <= 32 px):
+                      // halo_x = 2 pad_w, tap_x = pad_w (reads past a row's end land on the next row's leading zeros);
+                      // 2-D tiles: halo_x = pad_w, tap_x = 0 (the kept outputs never read past their own row)
+  int w_resident;     // halo mode: the whole weight matrix fits the weight ring -> staged once per CTA, never released
+  int h_stages;       // halo mode: halo stages in flight (2..4: one staged halo is ~2 us of TMA latency away) ...
+  int h_stride;       // ... and the bytes between them (multiple of 1024)
   int hb;             // image rows per 128-row tile
   int rows_per_warp;  // image rows per 32-row epilogue chunk (32 / wb)
   // halo mode (W + 2 pad_w <= wb): per channel slab ONE box of hb + kh - 1 image rows is staged, each row laid out as
@@ -317,14 +328,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w,
                 const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_res,
                 const __grid_constant__ CUtensorMap tma_x16, int M, int N, int K, EpiDev ep, ConvDev cv) {
-  using Cfg = GemmCfg<BN, kRes>;
+  using Cfg = GemmCfg<BN, kRes, kConv>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
   uint8_t* smem_epi = smem + Cfg::kStages * Cfg::kStageBytes;
   uint8_t* smem_bias = smem_epi + Cfg::kEpiBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_bias + Cfg::kBiasBytes);
-  constexpr int kBarSlots = 8;                      // >= kStages; the convolution halo mode uses up to 8 weight stages
+  constexpr int kBarSlots = 12;                     // >= kStages; the convolution halo mode uses up to 12 weight stages
   static_assert(Cfg::kStages <= kBarSlots, "barrier slots");
   uint64_t* full_bar = bars;                        // kBarSlots
   uint64_t* empty_bar = bars + kBarSlots;           // kBarSlots
@@ -332,10 +343,10 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   uint64_t* tempty_bar = tfull_bar + 2;             // 2
   uint64_t* res_bar = tempty_bar + 2;               // kEpiWarps * 2 (residual chunk landed)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2 * kEpiWarps);
-  uint64_t* halo_full = res_bar + 2 * kEpiWarps + 1;   // 2 (convolution halo mode)
-  uint64_t* halo_empty = halo_full + 2;                // 2
-  uint8_t* smem_halo = smem;                           // halo mode: 2 halo stages, then the weight-tile ring
-  uint8_t* smem_wring = smem + 2 * kHaloStageBytes;
+  uint64_t* halo_full = res_bar + 2 * kEpiWarps + 1;   // 4 (convolution halo mode)
+  uint64_t* halo_empty = halo_full + 4;                // 4
+  uint8_t* smem_halo = smem;                           // halo mode: h_stages halo stages, then the weight-tile ring
+  uint8_t* smem_wring = smem + cv.h_stages * cv.h_stride;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
@@ -367,7 +378,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       mbar_init(&tempty_bar[a], kCta2 ? 2 * kEpiWarps : kEpiWarps);
     }
     for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&halo_full[i], 1);
       mbar_init(&halo_empty[i], 1);
     }
@@ -393,31 +404,36 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   // per-lane "waterfall" loop (R2UR + BRA.U.ANY), ~100 cycles of issue per instruction.
   if (kConv && warp == 0 && cv.halo) {
     // ===================== TMA producer, convolution halo mode =====================
-    int stage = 0, hcount = 0;
-    uint32_t phase = 0;
+    int stage = 0, hs = 0;
+    uint32_t phase = 0, hphase = 0;
     const uint32_t halo_bytes = static_cast<uint32_t>(cv.halo_rows * cv.wb) * 128u;
     for (int tile = tile_first; tile < num_tiles; tile += tile_stride) {
       const int m_blk = tile / tiles_n;
       const int n_blk = tile - m_blk * tiles_n;
       const int ct = m_blk * (kCta2 ? 2 : 1) + cta_rank;
       const int cs = ct / cv.tiles_per_img;
-      const int cy0 = (ct - cs * cv.tiles_per_img) * cv.hb;
-      for (int slab = 0; slab < cv.cin_slabs; ++slab, ++hcount) {
-        const int hs = hcount & 1;
-        mbar_wait(&halo_empty[hs], ((hcount >> 1) & 1) ^ 1);
+      const int cti = ct - cs * cv.tiles_per_img, cty = cti / cv.tiles_x;
+      const int cy0 = cty * cv.hb - cv.pad_h, cx0 = (cti - cty * cv.tiles_x) * cv.wo - cv.halo_x;
+      const bool load_w = !(cv.w_resident && tile != tile_first);   // resident weights: staged with the first tile only
+      for (int slab = 0; slab < cv.cin_slabs; ++slab) {
+        mbar_wait(&halo_empty[hs], hphase ^ 1);
         if (elect_one()) {
           if constexpr (kCta2) {
             if (cta_rank == 0) mbar_arrive_expect_tx(&halo_full[hs], 2 * halo_bytes);
-            tma_load_4d_2sm(smem_halo + hs * kHaloStageBytes, &tma_a, &halo_full[hs], slab * BK, -2 * cv.pad_w,
-                            cy0 - cv.pad_h, cs);
+            tma_load_4d_2sm(smem_halo + hs * cv.h_stride, &tma_a, &halo_full[hs], slab * BK, cx0, cy0, cs);
           } else {
             mbar_arrive_expect_tx(&halo_full[hs], halo_bytes);
-            tma_load_4d(smem_halo + hs * kHaloStageBytes, &tma_a, &halo_full[hs], slab * BK, -2 * cv.pad_w, cy0 - cv.pad_h, cs);
+            tma_load_4d(smem_halo + hs * cv.h_stride, &tma_a, &halo_full[hs], slab * BK, cx0, cy0, cs);
           }
         }
         __syncwarp();
+        if (++hs == cv.h_stages) {
+          hs = 0;
+          hphase ^= 1;
+        }
+        if (!load_w) continue;
         for (int tap = 0; tap < cv.taps; ++tap) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (!cv.w_resident) mbar_wait(&empty_bar[stage], phase ^ 1);
           if (elect_one()) {
             const int kcol = (tap * cv.cin_slabs + slab) * BK;
             if constexpr (kCta2) {
@@ -450,7 +466,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       const int cti = (kConv && cv.taps) ? ct - cs * cv.tiles_per_img : 0;
       const int cty = (kConv && cv.taps) ? cti / cv.tiles_x : 0;
       const int cy0 = cty * cv.hb * cv.stride - cv.pad_h;                 // input coordinates of the tile's first pixel
-      const int cx0 = (cti - cty * cv.tiles_x) * cv.wb * cv.stride - cv.pad_w;
+      const int cx0 = (cti - cty * cv.tiles_x) * cv.wo * cv.stride - cv.pad_w;
       int tap = 0, slab = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -492,58 +508,77 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     }
   } else if (kConv && warp == 1 && cta_rank == 0 && cv.halo) {
     // ===================== MMA issuer, convolution halo mode =====================
+    // One elected thread issues everything, so the loop body per tap IS the pace of narrow convolutions: ncu of the
+    // encoders' 64-channel 3x3 convolution showed this warp busy (not waiting) for ~470 cycles per tap against 128 cycles of
+    // tensor work -- ~75 uniform-datapath instructions of descriptor arithmetic per tap.  The descriptors are therefore
+    // advanced incrementally (only their 14-bit start-address field changes: +8 = 128 bytes per tap along a halo row, one
+    // add per row wrap, per halo stage, per weight stage) and the halo / accumulator commits sit outside the tap loop.
+    // The A operand of tap (ky, kx) is the halo read from (ky * wb + kx + tap_x) rows further down: a multiple of 128 B but
+    // not of the 1024-byte swizzle atom; the tensor core applies the 128B-swizzle XOR to the absolute shared-memory
+    // address (like the TMA write did), so the descriptor's base-offset field stays 0.
     constexpr uint32_t idesc = umma_idesc_f16(TM, BN, 0, 0);
     const uint64_t bdesc0 = umma_desc_kmajor_sw128(smem_u32(smem_wring));
-    const uint32_t halo_addr0 = smem_u32(smem_halo);
-    int stage = 0, hcount = 0, as = 0;
-    uint32_t phase = 0, aphase = 0;
+    const uint64_t adesc0 = umma_desc_kmajor_sw128(smem_u32(smem_halo) + static_cast<uint32_t>(cv.tap_x) * 128u);
+    const uint32_t h_step = static_cast<uint32_t>(cv.h_stride) >> 4, w_step = static_cast<uint32_t>(cv.w_stride) >> 4;
+    const uint32_t row_wrap = static_cast<uint32_t>(cv.wb - cv.kw) * 8u;   // from the end of one tap row to the next row's first tap
+    const int kh = cv.taps / cv.kw;
+    int stage = 0, hs = 0, as = 0;
+    uint32_t phase = 0, aphase = 0, hphase = 0;
+    uint64_t bdesc = bdesc0, adesc_h = adesc0;   // current weight stage / current halo stage
     for (int tile = tile_first; tile < num_tiles; tile += tile_stride) {
       mbar_wait(&tempty_bar[as], aphase ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + as * BN;
+      const bool wait_w = !(cv.w_resident && tile != tile_first);   // resident weights landed with the first tile
       uint32_t accumulate = 0;
-      for (int slab = 0; slab < cv.cin_slabs; ++slab, ++hcount) {
-        const int hs = hcount & 1;
-        mbar_wait(&halo_full[hs], (hcount >> 1) & 1);
+      for (int slab = 0; slab < cv.cin_slabs; ++slab) {
+        mbar_wait(&halo_full[hs], hphase);
         tc_fence_after();
-        int ky = 0, kx = 0;
-        for (int tap = 0; tap < cv.taps; ++tap) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          // the A operand of this tap: the halo, read from (ky * wb + kx + pad_w) rows further down.  The start is a
-          // multiple of 128 B but not of the 1024-byte swizzle atom; the tensor core applies the 128B-swizzle XOR to the
-          // absolute shared-memory address (like the TMA write did), so the descriptor's base-offset field stays 0
-          // (tests/test_conv_as_gemm.py fails with the field set: CWM_CONV_BASEOFF=1).
-          const uint32_t a_addr = halo_addr0 + hs * kHaloStageBytes + static_cast<uint32_t>(ky * cv.wb + kx + cv.pad_w) * 128u;
-          const uint64_t adesc = umma_desc_kmajor_sw128(a_addr) |
-                                 (cv.base_off ? (static_cast<uint64_t>((a_addr >> 7) & 7u) << 49) : 0ull);
-          const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(stage * (cv.w_stride >> 4));
-          const bool last = (slab == cv.cin_slabs - 1) && (tap == cv.taps - 1);
-          if (elect_one()) {
-            if constexpr (kCta2) {
+        uint64_t adesc = adesc_h;
+        for (int ky = 0; ky < kh; ++ky) {
+          for (int kx = 0; kx < cv.kw; ++kx) {
+            if (wait_w) {
+              mbar_wait(&full_bar[stage], phase);
+              tc_fence_after();
+            }
+            if (elect_one()) {
+              if constexpr (kCta2) {
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) umma_ss2(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (accumulate | k) != 0 ? 1u : 0u);
-              umma_commit2(&empty_bar[stage]);
-              if (tap == cv.taps - 1) umma_commit2(&halo_empty[hs]);
-              if (last) umma_commit2(&tfull_bar[as]);
-            } else {
+                for (int k = 0; k < BK / 16; ++k) umma_ss2(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (accumulate | k) != 0 ? 1u : 0u);
+                if (!cv.w_resident) umma_commit2(&empty_bar[stage]);
+              } else {
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) umma_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (accumulate | k) != 0 ? 1u : 0u);
-              umma_commit(&empty_bar[stage]);
-              if (tap == cv.taps - 1) umma_commit(&halo_empty[hs]);
-              if (last) umma_commit(&tfull_bar[as]);
+                for (int k = 0; k < BK / 16; ++k) umma_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (accumulate | k) != 0 ? 1u : 0u);
+                if (!cv.w_resident) umma_commit(&empty_bar[stage]);
+              }
+            }
+            __syncwarp();
+            accumulate = 1;
+            adesc += 8;
+            bdesc += w_step;
+            if (++stage == cv.w_stages) {
+              stage = 0;
+              phase ^= 1;
+              bdesc = bdesc0;
             }
           }
-          __syncwarp();
-          accumulate = 1;
-          if (++kx == cv.kw) {
-            kx = 0;
-            ++ky;
+          adesc += row_wrap;
+        }
+        if (elect_one()) {   // this halo is consumed; after the last slab the accumulator is complete
+          if constexpr (kCta2) {
+            umma_commit2(&halo_empty[hs]);
+            if (slab == cv.cin_slabs - 1) umma_commit2(&tfull_bar[as]);
+          } else {
+            umma_commit(&halo_empty[hs]);
+            if (slab == cv.cin_slabs - 1) umma_commit(&tfull_bar[as]);
           }
-          if (++stage == cv.w_stages) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        adesc_h += h_step;
+        if (++hs == cv.h_stages) {
+          hs = 0;
+          hphase ^= 1;
+          adesc_h = adesc0;
         }
       }
       if (++as == 2) {
@@ -622,7 +657,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
                                                    : make_float2(0.f, 0.f);
       };
       if (ln && tile_first < num_tiles) load_ln_stats((tile_first / tiles_n) * TM + cta_rank * BM + quad * 32 + lane);
-      for (int tile = tile_first; tile < num_tiles; tile += tile_stride) {
+      int tile_iter = 0;
+      for (int tile = tile_first; tile < num_tiles; tile += tile_stride, ++tile_iter) {
         const int m_blk = tile / tiles_n;
         const int n_blk = tile - m_blk * tiles_n;
         const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
@@ -658,13 +694,17 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
           const int cs = ct / cv.tiles_per_img;
           const int tr = quad * 32 + lane;
           const int cti = ct - cs * cv.tiles_per_img, cty = cti / cv.tiles_x;
-          const int py = cty * cv.hb + tr / cv.wb, px = (cti - cty * cv.tiles_x) * cv.wb + tr % cv.wb;
+          const int py = cty * cv.hb + tr / cv.wb, px = (cti - cty * cv.tiles_x) * cv.wo + tr % cv.wb;
           if (cs < ep.img_s && py < ep.img_h && px < ep.img_w)
             post_row = (static_cast<long long>(cs) * ep.img_h + py) * ep.img_w + px;
         }
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
-        for (int c = half; c < kChunks; c += 2) {
+        // one 64-column chunk per tile (BN == 64: the narrow convolutions, where the epilogue and not the MMA paces the
+        // kernel): the two warp halves take alternate tiles instead of one half idling (ncu of the encoders' 64-channel
+        // convolutions: ~4500 cycles per 128x64 tile for 600 cycles of MMA work)
+        const int c_first = (kChunks == 1) ? (((tile_iter & 1) == half) ? 0 : kChunks) : half;
+        for (int c = c_first; c < kChunks; c += 2) {
           const int n0 = n_blk * BN + c * 64;
           // bias of the 64 columns -> per-warp smem (broadcast reads below)
           float b_lo = 0.f, b_hi = 0.f, s_lo = 0.f, s_hi = 0.f;
@@ -799,7 +839,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
               const int ct = m_blk * (kCta2 ? 2 : 1) + cta_rank;
               const int cs = ct / cv.tiles_per_img;
               const int cti = ct - cs * cv.tiles_per_img, cty = cti / cv.tiles_x;
-              const int sy = cty * cv.hb + quad * cv.rows_per_warp, sx = (cti - cty * cv.tiles_x) * cv.wb;
+              const int sy = cty * cv.hb + quad * cv.rows_per_warp, sx = (cti - cty * cv.tiles_x) * cv.wo;
               if (ep.post == 1 && n0 >= ep.post_c) {
                 tma_store_4d(&tma_res, buf0, n0 - ep.post_c, sx, sy, cs);      // r * h -> the q convolution's input slot
               } else {
@@ -812,7 +852,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
             bulk_commit();
           }
         }
-        if (half >= kChunks) {  // this warp had no chunk in this tile (BN == 64): still release the stage
+        if (c_first >= kChunks) {  // this warp had no chunk in this tile (BN == 64): still release the stage
           tc_fence_before();
           if (lane == 0) { if constexpr (kCta2) mbar_arrive_leader(&tempty_bar[as]); else mbar_arrive(&tempty_bar[as]); }
         }
@@ -1039,7 +1079,7 @@ template <int BN, bool kRes, bool kCta2, bool kConv>
 static int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const CUtensorMap& tr,
                             const CUtensorMap& tx, int M, int N, int K, const EpiDev& ep, cudaStream_t stream,
                             const ConvDev& cv_in) {
-  using Cfg = GemmCfg<BN, kRes>;
+  using Cfg = GemmCfg<BN, kRes, kConv>;
   static bool attr_set = false;
   if (!attr_set) {
     CWM_CUDA_CHECK(cudaFuncSetAttribute(gemm_f16_kernel<BN, kRes, kCta2, kConv>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1047,10 +1087,32 @@ static int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tw, const 
     attr_set = true;
   }
   ConvDev cv = cv_in;
-  if (cv.halo) {  // carve the operand ring into 2 halo stages + as many weight stages as fit
+  if (cv.halo) {  // carve the operand ring into halo stages + the weight ring (or the resident weight matrix)
+    const int ring = Cfg::kStages * Cfg::kStageBytes;
     cv.w_stride = kCta2 ? Cfg::kBBytes / 2 : Cfg::kBBytes;
-    const int ws = (Cfg::kStages * Cfg::kStageBytes - 2 * kHaloStageBytes) / cv.w_stride;
-    cv.w_stages = ws > 8 ? 8 : ws;
+    // a halo stage: the staged box + 1 KB of slack for the shifted reads of discarded output rows, 1024-byte aligned
+    cv.h_stride = ((cv.halo_rows * cv.wb * 128 + 1024 + 1023) / 1024) * 1024;
+    if (cv.h_stride > kHaloStageBytes) cv.h_stride = kHaloStageBytes;
+    const int k_steps = cv.taps * cv.cin_slabs;
+    static int resident_env = -1, hstage_env = -1;
+    if (resident_env < 0) {
+      const char* v = getenv("CWM_CONV_RESIDENT");
+      resident_env = (v == nullptr) ? 1 : atoi(v);
+      v = getenv("CWM_CONV_HALO_STAGES");
+      hstage_env = (v == nullptr) ? 4 : atoi(v);
+      if (hstage_env < 2) hstage_env = 2;
+      if (hstage_env > 4) hstage_env = 4;
+    }
+    // the whole weight matrix fits beside two halo stages (the encoders' 64-channel 3x3 convolutions: 9 x 8 KB): stage it
+    // once per CTA and give the rest of the ring to halo stages -- one staged halo is ~2 us of TMA latency away, and with
+    // one halo per tile two stages leave a single load in flight (measured: 111 us per 112x112x64 convolution either way)
+    cv.w_resident = (resident_env && N <= BN && k_steps <= 12 && 2 * cv.h_stride + k_steps * cv.w_stride <= ring) ? 1 : 0;
+    const int w_min = cv.w_resident ? k_steps : 4;          // weight stages that must remain
+    int hst = (ring - w_min * cv.w_stride) / cv.h_stride;
+    hst = hst > hstage_env ? hstage_env : hst;
+    cv.h_stages = hst < 2 ? 2 : hst;
+    const int ws = (ring - cv.h_stages * cv.h_stride) / cv.w_stride;
+    cv.w_stages = cv.w_resident ? k_steps : (ws > 12 ? 12 : ws);   // <= kBarSlots
     if (cv.w_stages < 2) return fail(CWM_ERR_INVALID, "convolution halo mode: no room for the weight ring (BN=%d)", BN);
   }
   if constexpr (kCta2) {
@@ -1084,7 +1146,7 @@ static int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tw, const 
 template <int BN, bool kRes, bool kConv = false>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const CUtensorMap& tr,
                        const CUtensorMap& tx, int M, int N, int K, const EpiDev& ep, cudaStream_t stream, bool cta2,
-                       const ConvDev& cv = ConvDev{0, 1, 0, 0, 1 << 30, 1, 1, 1, 1, 1, 0, 0, 32, 1, 0, 0}) {
+                       const ConvDev& cv = ConvDev{0, 1, 0, 0, 1 << 30, 1, 1, 1, 32, 0, 0, 0, 2, 33 * 1024, 1, 1, 0, 0, 32, 1, 0, 0}) {
   if (cta2) return launch_gemm_impl<BN, kRes, true, kConv>(ta, tw, to, tr, tx, M, N, K, ep, stream, cv);
   return launch_gemm_impl<BN, kRes, false, kConv>(ta, tw, to, tr, tx, M, N, K, ep, stream, cv);
 }
@@ -1228,10 +1290,18 @@ static int conv2d_impl(const uint16_t* x, int ldx, int S, int H, int W, int Cin,
   // output map (torch.nn.Conv2d with padding = k // 2): (H + 2 pad - k) / stride + 1 = (H - 1) / stride + 1
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
   CWM_REQUIRE(post.post == 0 || (Wo <= 32 && stride == 1), "cwm_conv2d_gru_*: maps of at most 32 pixels, stride 1");
-  // a 128-row tile = hb image rows of wb pixel slots.  Maps of <= 32 pixels: one column block (wb = 16 / 32 >= Wo); wider
-  // maps are tiled in both directions with the wb in {8, 16, 32} that wastes the fewest slots (ties: the widest)
+  // a 128-row tile = hb image rows of wb pixel slots.  Maps of <= 32 pixels: one column block (wb = 16 / 32 >= Wo).  Wider
+  // maps are tiled in both directions: stride-1 convolutions with more than one tap as 4 x 32-slot halo tiles that keep
+  // 32 - 2 pad_w outputs per row (2-D halo mode), everything else with the wb in {8, 16, 32} that wastes the fewest slots
+  static int halo_env = -1;
+  if (halo_env < 0) {
+    const char* v = getenv("CWM_CONV_HALO");
+    halo_env = (v == nullptr) ? 1 : atoi(v);
+  }
   int wb = Wo <= 16 ? 16 : 32;
-  if (Wo > 32) {
+  const bool halo2d = halo_env != 0 && Wo > 32 && stride == 1 && kh * kw > 1 && 32 - 2 * pad_w >= 16 &&
+                      (BM / 32 + kh - 1) * 32 * 128 <= kHaloStageBytes - 1024;
+  if (Wo > 32 && !halo2d) {
     long long best = -1;
     for (int cand = 32; cand >= 8; cand >>= 1) {
       const int hbc = BM / cand;
@@ -1242,21 +1312,29 @@ static int conv2d_impl(const uint16_t* x, int ldx, int S, int H, int W, int Cin,
   const int hb = BM / wb;
   ConvDev cv;
   cv.taps = kh * kw; cv.kw = kw; cv.pad_h = pad_h; cv.pad_w = pad_w; cv.cin_slabs = (Cin + BK - 1) / BK;
-  cv.tiles_x = (Wo + wb - 1) / wb; cv.stride = stride;
+  cv.wo = halo2d ? wb - 2 * pad_w : wb;
+  cv.tiles_x = (Wo + cv.wo - 1) / cv.wo; cv.stride = stride;
   cv.tiles_per_img = cv.tiles_x * ((Ho + hb - 1) / hb); cv.hb = hb; cv.rows_per_warp = 32 / wb;
+  cv.w_resident = 0;
+  cv.h_stages = 2;
+  cv.h_stride = kHaloStageBytes;
   const int bn = pick_bn(Cout);
   // halo mode: every image row with its zero padding fits one row of wb pixel slots, and there is more than one tap
-  static int halo_env = -1;
-  if (halo_env < 0) {
-    const char* v = getenv("CWM_CONV_HALO");
-    halo_env = (v == nullptr) ? 1 : atoi(v);
-  }
   cv.wb = wb;
-  // one more row when the right-most taps of the right-most pixels read past their row's end (slot W - 1 + kw - 1 + pad_w
-  // >= wb): they land on the NEXT row's leading zero slots, which must exist for the last row of the box too
-  cv.halo_rows = hb + kh - 1 + ((W + 3 * pad_w > wb) ? 1 : 0);
-  cv.halo = (halo_env != 0 && cv.taps > 1 && stride == 1 && cv.tiles_x == 1 && W + 2 * pad_w <= wb &&
-             cv.halo_rows * wb * 128 <= kHaloStageBytes) ? 1 : 0;
+  if (halo2d) {
+    cv.halo = 1;
+    cv.halo_rows = hb + kh - 1;
+    cv.halo_x = pad_w;
+    cv.tap_x = 0;
+  } else {
+    // one more row when the right-most taps of the right-most pixels read past their row's end (slot W - 1 + kw - 1 + pad_w
+    // >= wb): they land on the NEXT row's leading zero slots, which must exist for the last row of the box too
+    cv.halo_rows = hb + kh - 1 + ((W + 3 * pad_w > wb) ? 1 : 0);
+    cv.halo = (halo_env != 0 && cv.taps > 1 && stride == 1 && cv.tiles_x == 1 && W + 2 * pad_w <= wb &&
+               cv.halo_rows * wb * 128 <= kHaloStageBytes) ? 1 : 0;
+    cv.halo_x = 2 * pad_w;
+    cv.tap_x = pad_w;
+  }
   cv.w_stages = 2;
   cv.w_stride = 0;
   {
@@ -1282,16 +1360,18 @@ static int conv2d_impl(const uint16_t* x, int ldx, int S, int H, int W, int Cin,
   if (rc) return rc;
   rc = make_tmap_2d(&tw, w_packed, CWM_TMAP_F16, Cout, K, K, cta2 ? bn / 2 : bn, BK);
   if (rc) return rc;
-  rc = make_tmap_nhwc(&to, out, S, Ho, Wo, out_cols, ldo, cv.rows_per_warp, wb, 64);
+  rc = make_tmap_nhwc(&to, out, S, Ho, Wo, out_cols, ldo, cv.rows_per_warp, cv.wo, 64);
   if (rc) return rc;
   CUtensorMap to2 = to;
   if (post.out2 != nullptr) {
-    rc = make_tmap_nhwc(&to2, post.out2, S, Ho, Wo, post.out2_cols, post.ldo2, cv.rows_per_warp, wb, 64);
+    rc = make_tmap_nhwc(&to2, post.out2, S, Ho, Wo, post.out2_cols, post.ldo2, cv.rows_per_warp, cv.wo, 64);
     if (rc) return rc;
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   ProfileScope prof(s, post.post == 1 ? "conv2d_gru_gate" : (post.post == 2 ? "conv2d_gru_update" :
-                                                                (Wo > 32 || stride > 1 ? "conv2d_f16_wide" : "conv2d_f16")),
+                                                                (Wo > 32 ? (Cout <= 64 ? (cv.taps > 1 ? "conv2d_wide64_3x3" : "conv2d_wide64_1x1")
+                                                                                       : (stride > 1 ? "conv2d_wide_s2" : "conv2d_wide"))
+                                                                         : (stride > 1 ? "conv2d_s2" : "conv2d_f16"))),
                     2.0 * S * Ho * Wo * static_cast<double>(Cout) * cv.taps * Cin,
                     static_cast<double>(S) * (static_cast<double>(H) * W * Cin + static_cast<double>(Ho) * Wo * Cout) * 2.0 +
                         static_cast<double>(Cout) * K * 2.0);

@@ -106,3 +106,42 @@ def im2col_nchw(img, k, stride, pad, ldo, scale=1.0, shift=0.0):
             patch = v[:, :, ky:ky + stride * Ho:stride, kx:kx + stride * Wo:stride]          # [S, C, Ho, Wo]
             out[..., (ky * k + kx) * C:(ky * k + kx + 1) * C] = patch.transpose(0, 2, 3, 1)
     return out.reshape(S * Ho * Wo, ldo)
+
+
+def conv_as_gemm_halo2d(x, w, bias=None, relu=False):
+    """The 2-D halo mode of csrc/gemm.cu (stride-1 convolutions on maps wider than 32 pixels: the encoders' 112 / 56 pixel
+    maps): a 128-row tile is 4 image rows of 32 pixel slots that keep wo = 32 - 2 pad_w outputs each.  Per channel slab ONE
+    box [4 + kh - 1, 32, 64] is staged at (y0 - pad_h, x0 - pad_w); tap (ky, kx) reads the SAME box as 128 consecutive
+    flat rows starting ky * 32 + kx (slot c of image row r -> box row r + ky, slot c + kx; slots c >= wo wrap into the next
+    box row and are discarded by the store, which writes [4, wo] clipped to the image)."""
+    S, H, W, C = x.shape
+    N, _, kh, kw = w.shape
+    pad_h, pad_w = kh // 2, kw // 2
+    hb, wb = 4, 32
+    wo = wb - 2 * pad_w
+    assert W > 32 and wo >= 16
+    slabs = (C + BK - 1) // BK
+    wp = pack_weight(w).astype(np.float64)
+    out = np.zeros((S, H, W, N), np.float64)
+    rows_box = hb + kh - 1
+    for s in range(S):
+        for yt in range(-(-H // hb)):
+            for xt in range(-(-W // wo)):
+                y0, x0 = yt * hb, xt * wo
+                acc = np.zeros((hb * wb, N), np.float64)
+                for j in range(slabs):
+                    box = load_box(x, s, y0 - pad_h, x0 - pad_w, j * BK, rows_box, wb).reshape(rows_box * wb, BK)
+                    box = np.concatenate([box, np.zeros((wb, BK), box.dtype)], 0)      # reads of discarded rows run past the box
+                    for tap in range(kh * kw):
+                        start = (tap // kw) * wb + tap % kw
+                        a = box[start:start + hb * wb]
+                        kb = tap * slabs + j
+                        acc += a.astype(np.float64) @ wp[:, kb * BK:(kb + 1) * BK].T
+                if bias is not None:
+                    acc += bias
+                if relu:
+                    acc = np.maximum(acc, 0)
+                tile = acc.reshape(hb, wb, N)
+                ye, xe = min(H, y0 + hb), min(W, x0 + wo)
+                out[s, y0:ye, x0:xe, :] = tile[:ye - y0, :xe - x0]
+    return out

@@ -41,6 +41,19 @@ def test_strided_and_wide_convolutions_equal_the_box_walk(kh, stride, H, W, C):
     np.testing.assert_allclose(got, want, rtol=1e-11, atol=1e-11)
 
 
+@pytest.mark.parametrize("kh,kw,H,W,C", [(3, 3, 10, 56, 24), (3, 3, 7, 112, 8), (1, 5, 9, 45, 70), (5, 1, 6, 33, 8), (7, 7, 9, 40, 8)])
+def test_2d_halo_tiles_equal_the_convolution(kh, kw, H, W, C):
+    """The 2-D halo mode (4 x 32-slot tiles keeping 32 - 2 pad outputs per row, every tap a shifted read of one staged box)."""
+    g = torch.Generator().manual_seed(kh * 10 + kw + W)
+    S, N = 2, 3
+    x = torch.randn(S, C, H, W, generator=g, dtype=torch.float64)
+    w = torch.randn(N, C, kh, kw, generator=g, dtype=torch.float64)
+    b = torch.randn(N, generator=g, dtype=torch.float64)
+    want = F.conv2d(x, w, b, 1, (kh // 2, kw // 2)).permute(0, 2, 3, 1).numpy()
+    got = cg.conv_as_gemm_halo2d(x.permute(0, 2, 3, 1).numpy(), w.numpy(), b.numpy())
+    np.testing.assert_allclose(got, want, rtol=1e-11, atol=1e-11)
+
+
 def test_stem_im2col_plus_gemm_equals_the_strided_convolution():
     g = torch.Generator().manual_seed(5)
     img = torch.rand(2, 3, 30, 38, generator=g, dtype=torch.float64) * 255
@@ -166,7 +179,9 @@ def test_gpu_gru_gate_and_update_in_the_conv_epilogues(kh, kw, S, H, W):
     ("layer1 3x3", 64, 64, 3, 1, 3, 112, 112), ("layer2 3x3/2", 64, 96, 3, 2, 3, 112, 112), ("layer2 1x1/2", 64, 96, 1, 2, 2, 112, 112),
     ("layer2 3x3", 96, 96, 3, 1, 5, 56, 56), ("layer3 3x3/2", 96, 128, 3, 2, 5, 56, 56), ("layer3 1x1/2", 96, 128, 1, 2, 2, 56, 56),
     ("layer3 3x3", 128, 128, 3, 1, 3, 28, 28), ("conv2 1x1", 128, 256, 1, 1, 3, 28, 28),
-    ("odd sizes /2", 72, 40, 3, 2, 2, 37, 45), ("odd sizes", 24, 136, 3, 1, 2, 40, 50), ("1x1/2 odd", 16, 64, 1, 2, 1, 19, 75)])
+    ("odd sizes /2", 72, 40, 3, 2, 2, 37, 45), ("odd sizes", 24, 136, 3, 1, 2, 40, 50), ("1x1/2 odd", 16, 64, 1, 2, 1, 19, 75),
+    ("layer1, many tiles per CTA", 64, 64, 3, 1, 9, 112, 112), ("resident weights, ragged", 64, 64, 3, 1, 3, 50, 61),
+    ("5x5 wide", 64, 32, 5, 1, 2, 33, 70), ("two N tiles", 64, 320, 3, 1, 1, 20, 40)])
 def test_gpu_encoder_convolutions_match_torch(name, Cin, Cout, k, stride, S, H, W):
     """RAFT's encoder convolutions (extractor.py:6-56, :118-190): wide maps tiled in both directions, stride 2 through the
     tensor map's traversal stride."""
