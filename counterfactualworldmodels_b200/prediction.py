@@ -141,12 +141,9 @@ class PredictorBasedGenerator(nn.Module):
         return (self.sequence_length // pt, h // ph, w // pw)
 
     def set_temporal_dim(self, t_dim=1):
-        if t_dim == 1:
-            self.predictor.t_dim, self.predictor.c_dim = 1, 2
-        elif t_dim == 2:
-            self.predictor.c_dim, self.predictor.t_dim = 1, 2
-        else:
+        if t_dim not in (1, 2):
             raise ValueError("temporal_dim must be 1 or 2")
+        self.predictor.t_dim, self.predictor.c_dim = t_dim, 3 - t_dim       # time and channel axes are 1 and 2, either way
 
     @property
     def t_dim(self):
@@ -163,13 +160,13 @@ class PredictorBasedGenerator(nn.Module):
             self.predictor.image_size = args[0]
 
     def get_zeros_mask(self, x=None, frame=-1):
-        if x is None:
-            x = self.x
+        """All-visible mask [B, N] with (optionally) one fully masked token frame."""
+        x = self.x if x is None else x
         self.inp_shape = x.shape
         mask = torch.zeros(self.mask_shape, device=x.device, dtype=torch.bool)
         if frame is not None:
-            mask[frame, ...] = torch.ones_like(mask[frame, ...])
-        return mask.flatten().unsqueeze(0).expand(x.shape[0], -1)
+            mask[frame] = True
+        return mask.reshape(1, -1).expand(x.shape[0], -1)
 
     def generate_mask(self, x=None):
         assert self.mask_generator is not None
@@ -180,13 +177,11 @@ class PredictorBasedGenerator(nn.Module):
 
     def reset_padding_masks(self):
         """prediction.py:121-129."""
-        if hasattr(self.predictor, 'padding_mask') and not hasattr(self.predictor, 'main_stream'):
-            self.predictor._reset_padding_mask()
-        elif hasattr(self.predictor, 'main_stream'):
-            if hasattr(self.predictor.main_stream, 'padding_mask'):
-                self.predictor.main_stream._reset_padding_mask()
-            if hasattr(self.predictor.context_stream, 'padding_mask'):
-                self.predictor.context_stream._reset_padding_mask()
+        p = self.predictor
+        streams = [p.main_stream, p.context_stream] if hasattr(p, 'main_stream') else [p]    # conjoined: per stream
+        for stream in streams:
+            if hasattr(stream, 'padding_mask'):
+                stream._reset_padding_mask()
 
     # ---- a1 ----
     def _preprocess(self, x):
@@ -194,13 +189,13 @@ class PredictorBasedGenerator(nn.Module):
         transpose + normalisation into the patch gather)."""
         if self.t_dim != 1:
             x = x.transpose(self.t_dim, self.c_dim)
-        if self.imagenet_normalize_inputs:
-            mean = torch.as_tensor(IMAGENET_DEFAULT_MEAN).to(x.device)[None, None, :, None, None].to(x)
-            std = torch.as_tensor(IMAGENET_DEFAULT_STD).to(x.device)[None, None, :, None, None].to(x)
-            if self.t_dim == 2:
-                mean, std = mean.transpose(1, 2), std.transpose(1, 2)
-            x = (x - mean) / std
-        return x
+        if not self.imagenet_normalize_inputs:
+            return x
+        shape = [1] * 5
+        shape[1 if self.t_dim == 2 else 2] = 3          # the channel axis after the transpose above
+        mean = torch.as_tensor(IMAGENET_DEFAULT_MEAN).to(x).view(shape)
+        std = torch.as_tensor(IMAGENET_DEFAULT_STD).to(x).view(shape)
+        return (x - mean) / std
 
     # ---- a12 ----
     def pred_patches_to_video(self, y, x, mask):

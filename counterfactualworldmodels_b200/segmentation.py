@@ -22,6 +22,28 @@ from .prediction import PredictorBasedGenerator
 from .sampling import FlowSampleFilter
 
 
+def _with_sample_axis(t, num_samples=None):
+    """[B, N] -> [B, N, 1] (or expanded to ``num_samples``); a trailing axis of length 1 is expanded likewise."""
+    if t.dim() == 2:
+        t = t.unsqueeze(-1)
+    if num_samples is not None and t.size(-1) == 1 and num_samples != 1:
+        t = t.expand(-1, -1, num_samples)
+    return t
+
+
+def _two_frame_movie(x):
+    """[C, H, W] / [B, C, H, W] / [B, 1, C, H, W] / [B, T >= 2, C, H, W] -> ([B, 2, C, H, W], input was a still image)."""
+    still = x.dim() in (3, 4)
+    if x.dim() == 3:
+        x = x.unsqueeze(0)
+    if x.dim() == 4:
+        x = x.unsqueeze(1)
+    assert x.dim() == 5, x.shape
+    if x.size(1) == 1:
+        x = x.expand(-1, 2, -1, -1, -1)
+    return x[:, 0:2], still
+
+
 _DEFAULT_FILTER = object()   # sentinel: "build the default FlowSampleFilter"
 
 
@@ -390,21 +412,20 @@ class FlowGenerator(PredictorBasedGenerator):
         """Create motion counterfactuals by applying shifts to active_patches and no shifts to masks
         (segmentation.py:279-343).  Returns ``(x_shift [B*S, T, C, H, W], mask_shift [B*S, N])`` after the mask
         rectangulariser.  ``virtual=True`` (extension) returns the prompts as a ``CounterfactualVideo``."""
-        if (getattr(self, 'shifts', None) is None) or reset_shifts:
+        if reset_shifts or getattr(self, 'shifts', None) is None:
             self.reset_shifts()
-        if len(masks.shape) == 2:
+        # every patch tensor ends up [B, N, S]: 2-D inputs are one pattern shared by all samples (:289-304)
+        if masks.dim() == 2:
             assert num_samples is not None, "Choose how many samples to shift with arg num_samples"
-            masks = masks.unsqueeze(-1).expand(-1, -1, num_samples)
-        else:
-            num_samples = masks.size(-1)
+            masks = _with_sample_axis(masks, num_samples)
+        B, N, S = masks.shape
+        num_samples = S
         if active_patches is None:
             active_patches = torch.ones_like(masks)
-        elif len(active_patches.shape) == 2:
-            active_patches = active_patches.unsqueeze(-1).expand(-1, -1, masks.size(-1))
-        B, N, S = masks.shape
-        assert active_patches.size(-1) in [1, S]
-        if active_patches.size(-1) == 1:
-            active_patches = active_patches.expand(-1, -1, S)
+        else:
+            active_patches = _with_sample_axis(active_patches, S)
+            assert active_patches.size(-1) in (1, S)
+            active_patches = _with_sample_axis(active_patches, S)
 
         # `make_static_movie(x[:,0:1], T=2)` + `sample_tile(x, S)` (:309-312) are index arithmetic here: every
         # frame of every sample reads frame 0 of image i // S
@@ -439,43 +460,31 @@ class FlowGenerator(PredictorBasedGenerator):
                                       **kwargs):
         """The video half of ``predict_counterfactual_videos_and_flows`` (segmentation.py:345-430): the predicted
         counterfactual movies ``y_mocos`` [B*S, T, C, H, W]."""
-        # preprocess the input to be a 2-frame movie, regardless of what it is (:364-373)
-        if len(x.shape) == 3:
-            x = x.unsqueeze(0).unsqueeze(1).expand(-1, 2, -1, -1, -1)
-            fix_passive = True
-        elif len(x.shape) == 4:
-            x = x.unsqueeze(1).expand(-1, 2, -1, -1, -1)
-            fix_passive = True
-        elif len(x.shape) == 5 and x.size(1) == 1:
-            x = x.expand(-1, 2, -1, -1, -1)
-        assert len(x.shape) == 5, x.shape
-        x = x[:, 0:2]
+        # whatever comes in becomes a 2-frame movie (:364-373); a single image means the passive patches stay put
+        x, was_image = _two_frame_movie(x)
+        fix_passive = fix_passive or was_image
         self.set_input(x)
         self.reset_shifts()
 
-        # preprocess the patches and shifts so they all have the same number of samples (:379-410)
-        if passive_patches is None:
-            passive_patches = self.get_zeros_mask().unsqueeze(-1)
-        elif len(passive_patches.shape) == 2:
-            passive_patches = passive_patches.unsqueeze(-1)
-        if len(active_patches.shape) == 2:
-            active_patches = active_patches.unsqueeze(-1)
+        # patches and shifts are brought to one common number of samples (:379-410)
+        active_patches = _with_sample_axis(active_patches)
+        passive_patches = (self.get_zeros_mask().unsqueeze(-1) if passive_patches is None
+                           else _with_sample_axis(passive_patches))
         S = max(active_patches.size(-1), passive_patches.size(-1))
-        if (S == 1) and num_samples > 1:
+        if S == 1 and num_samples > 1:
             S = num_samples
         self.shifter.set_shapes(x, mask=active_patches[..., 0])
-        if shifts is None:
+        if shifts is not None:
+            self.shifter.set_num_shifts(shifts.shape[-1] if hasattr(shifts, 'shape') else len(shifts))
+        else:
             self.shifter.set_num_shifts(S)
             if max_shift_fraction is not None:
                 self.shifter.max_shift_fraction = max_shift_fraction
-        else:
-            self.shifter.set_num_shifts(len(shifts) if not hasattr(shifts, 'shape') else shifts.shape[-1])
         shifts = self.shifter._preprocess_shifts_sequence(shifts, is_mask_shift=True)
         num_samples = len(shifts)
-        if (active_patches.size(-1) == 1) and (num_samples > 1):
-            active_patches = active_patches.expand(-1, -1, num_samples)
-        if (passive_patches.size(-1) == 1) and (num_samples > 1):
-            passive_patches = passive_patches.expand(-1, -1, num_samples)
+        if num_samples > 1:
+            active_patches, passive_patches = (t.expand(-1, -1, num_samples) if t.size(-1) == 1 else t
+                                               for t in (active_patches, passive_patches))
         assert active_patches.size(-1) == passive_patches.size(-1) == num_samples, \
             (active_patches.shape, passive_patches.shape, num_samples)
 
