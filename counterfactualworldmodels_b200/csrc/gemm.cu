@@ -543,8 +543,10 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
             }
             if (elect_one()) {
               if constexpr (kCta2) {
+                if (!(cv.base_off & 4)) {   // (timing experiment CWM_CONV_BASEOFF=4: no MMAs, only the commits)
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k) umma_ss2(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (accumulate | k) != 0 ? 1u : 0u);
+                  for (int k = 0; k < BK / 16; ++k) umma_ss2(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (accumulate | k) != 0 ? 1u : 0u);
+                }
                 if (!cv.w_resident) umma_commit2(&empty_bar[stage]);
               } else {
 #pragma unroll
@@ -700,6 +702,15 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         }
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
+        if (kConv && (cv.base_off & 2)) {   // timing experiment (CWM_CONV_BASEOFF=2): hand the accumulator straight back
+          tc_fence_before();
+          if (lane == 0) { if constexpr (kCta2) mbar_arrive_leader(&tempty_bar[as]); else mbar_arrive(&tempty_bar[as]); }
+          if (++as == 2) {
+            as = 0;
+            aphase ^= 1;
+          }
+          continue;
+        }
         // one 64-column chunk per tile (BN == 64: the narrow convolutions, where the epilogue and not the MMA paces the
         // kernel): the two warp halves take alternate tiles instead of one half idling (ncu of the encoders' 64-channel
         // convolutions: ~4500 cycles per 128x64 tile for 600 cycles of MMA work)
