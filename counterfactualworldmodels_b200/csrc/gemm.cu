@@ -47,7 +47,11 @@ struct GemmCfg {
   // halo mode carves the ring into up to 4 halo stages + the weight ring / the resident weight matrix)
   static constexpr int kStages = kConv ? (kMaxStages > 8 ? 8 : kMaxStages) : (kMaxStages > 6 ? 6 : kMaxStages);
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
-  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBiasBytes + 512;
+  // the operand ring: whole stages for the GEMM / per-tap modes; the convolution halo mode carves the entire budget (halo
+  // stages + 8 / 16 KB weight stages), which for BN = 256 is 190 KB instead of 3 x 48 KB
+  static constexpr int kRingBytes = kConv ? (kBudget / 1024) * 1024 : kStages * kStageBytes;
+  static_assert(kRingBytes >= kStages * kStageBytes, "ring");
+  static constexpr int kSmemBytes = kRingBytes + kEpiBytes + kBiasBytes + 512;
   static_assert(kStages >= 3, "pipeline too shallow");
 };
 
@@ -332,7 +336,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
-  uint8_t* smem_epi = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint8_t* smem_epi = smem + Cfg::kRingBytes;
   uint8_t* smem_bias = smem_epi + Cfg::kEpiBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_bias + Cfg::kBiasBytes);
   constexpr int kBarSlots = 12;                     // >= kStages; the convolution halo mode uses up to 12 weight stages
@@ -648,8 +652,10 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     if constexpr (!kRes) {
       // ---------------- f16 output: 64-column chunks, TMA store ----------------
       constexpr int kChunks = BN / 64;
-      const bool gelu = (ep.mode == CWM_EPI_GELU_F16);
-      const bool ln = (ep.ln_stats_in != nullptr);
+      // (the convolution instantiation has neither GELU, LayerNorm folding nor the q-scale: compiled out there -- its
+      // epilogue code was 140 KB of SASS and ncu showed 24 % of the warp samples waiting for instruction fetch)
+      const bool gelu = !kConv && (ep.mode == CWM_EPI_GELU_F16);
+      const bool ln = !kConv && (ep.ln_stats_in != nullptr);
       float2 ln_t[8];  // partial statistics of this thread's row in the tile being prepared (all loads back to back:
                        // a rolled loop serialises one L2 round trip per plane, measured +30 us per launch)
       auto load_ln_stats = [&](int row) {
@@ -739,7 +745,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
           }
           // ConvGRU post-ops: h (and z) of this thread's pixel row for the chunk's 64 columns, fetched as a 4-deep ring of
           // 16-byte loads that is primed here, before the accumulator wait, and refilled 4 units ahead in the loop
-          uint4 h_raw[4], z_raw[4];
+          uint4 h_raw[8], z_raw[4];   // gate: all 8 units of h up front; update: 4-deep rings of h and z
           const uint4* h_ptr = nullptr;
           const uint4* z_ptr = nullptr;
           bool post_ld_h = false;
@@ -750,6 +756,10 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
               h_ptr = reinterpret_cast<const uint4*>(ep.aux_h + post_row * ep.ld_h + hc);
 #pragma unroll
               for (int q = 0; q < 4; ++q) h_raw[q] = __ldg(h_ptr + q);
+              if (ep.post == 1) {
+#pragma unroll
+                for (int q = 4; q < 8; ++q) h_raw[q] = __ldg(h_ptr + q);
+              }
               if (ep.post == 2) {
                 z_ptr = reinterpret_cast<const uint4*>(ep.aux_z + post_row * ep.ld_z + n0);
 #pragma unroll
@@ -768,8 +778,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
           __syncwarp();
           // chunk-uniform q-scale (the boundary is a multiple of 64 for every model: heads * 64); a chunk that
           // straddles it falls back to per-element selection
-          const bool sc_all = !gelu && (n0 + 64 <= ep.scale_cols);
-          const bool sc_mixed = !gelu && !sc_all && (n0 < ep.scale_cols);
+          const bool sc_all = !kConv && !gelu && (n0 + 64 <= ep.scale_cols);
+          const bool sc_mixed = !kConv && !gelu && !sc_all && (n0 < ep.scale_cols);
           const uint64_t sc2 = pk2(ep.scale, ep.scale);
           const uint64_t rstd2 = pk2(ln_rstd, ln_rstd);
           const uint64_t nmr2 = pk2(-ln_mean * ln_rstd, -ln_mean * ln_rstd);
@@ -814,8 +824,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
             if (kConv && ep.post == 1) {          // GRU gate
               float hh[8];
               if (post_ld_h) {
-                h8_unpack(h_raw[u & 3], hh);
-                if (u + 4 < 8) h_raw[u & 3] = __ldg(h_ptr + u + 4);   // 4 units ahead (the smem store below fences the compiler)
+                h8_unpack(h_raw[u], hh);
               } else {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) hh[q] = (n0 >= ep.post_c) ? 0.f : 1.f;
@@ -1099,7 +1108,7 @@ static int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tw, const 
   }
   ConvDev cv = cv_in;
   if (cv.halo) {  // carve the operand ring into halo stages + the weight ring (or the resident weight matrix)
-    const int ring = Cfg::kStages * Cfg::kStageBytes;
+    const int ring = Cfg::kRingBytes;
     cv.w_stride = kCta2 ? Cfg::kBBytes / 2 : Cfg::kBBytes;
     // a halo stage: the staged box + 1 KB of slack for the shifted reads of discarded output rows, 1024-byte aligned
     cv.h_stride = ((cv.halo_rows * cv.wb * 128 + 1024 + 1023) / 1024) * 1024;
@@ -1110,7 +1119,7 @@ static int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tw, const 
       const char* v = getenv("CWM_CONV_RESIDENT");
       resident_env = (v == nullptr) ? 1 : atoi(v);
       v = getenv("CWM_CONV_HALO_STAGES");
-      hstage_env = (v == nullptr) ? 4 : atoi(v);
+      hstage_env = (v == nullptr) ? 3 : atoi(v);
       if (hstage_env < 2) hstage_env = 2;
       if (hstage_env > 4) hstage_env = 4;
     }
