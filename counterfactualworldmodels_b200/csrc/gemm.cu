@@ -327,12 +327,14 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
 // kConv: the convolution instantiation (4-D TMA operands, halo mode, relu / ConvGRU post-ops).  It is a template flag and not
 // a run-time mode because the f16-out epilogue of the plain GEMMs is issue-bound: the extra branches per 16-byte unit cost
 // the qkv / fc1 GEMMs 15 % when they were run-time (measured: 1173 -> 996 TFLOP/s inside a large-4x4 step).
-template <int BN, bool kRes, bool kCta2, bool kConv>
+// kConv: 0 = plain GEMM; 1 + post = convolution with the compile-time post-op (0 none, 1 GRU gate, 2 GRU update, 3 tail)
+template <int BN, bool kRes, bool kCta2, int kConv>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w,
                 const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_res,
                 const __grid_constant__ CUtensorMap tma_x16, int M, int N, int K, EpiDev ep, ConvDev cv) {
-  using Cfg = GemmCfg<BN, kRes, kConv>;
+  using Cfg = GemmCfg<BN, kRes, (kConv != 0)>;
+  constexpr int kPost = kConv > 0 ? kConv - 1 : 0;   // the convolution's post-op, compile-time: one variant per kernel
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
@@ -697,7 +699,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         }
         // convolution post-ops: the pixel row this thread's tile row stands for (-1: a padding slot / beyond the image)
         long long post_row = -1;
-        if (kConv && ep.post) {
+        if (kConv && kPost) {
           const int ct = m_blk * (kCta2 ? 2 : 1) + cta_rank;
           const int cs = ct / cv.tiles_per_img;
           const int tr = quad * 32 + lane;
@@ -749,18 +751,18 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
           const uint4* h_ptr = nullptr;
           const uint4* z_ptr = nullptr;
           bool post_ld_h = false;
-          if (kConv && (ep.post == 1 || ep.post == 2)) {
-            const int hc = (ep.post == 1) ? n0 - ep.post_c : n0;   // gate: only the r columns [C, 2C) read h
+          if (kConv && (kPost == 1 || kPost == 2)) {
+            const int hc = (kPost == 1) ? n0 - ep.post_c : n0;   // gate: only the r columns [C, 2C) read h
             post_ld_h = post_row >= 0 && hc >= 0;
             if (post_ld_h) {
               h_ptr = reinterpret_cast<const uint4*>(ep.aux_h + post_row * ep.ld_h + hc);
 #pragma unroll
               for (int q = 0; q < 4; ++q) h_raw[q] = __ldg(h_ptr + q);
-              if (ep.post == 1) {
+              if (kPost == 1) {
 #pragma unroll
                 for (int q = 4; q < 8; ++q) h_raw[q] = __ldg(h_ptr + q);
               }
-              if (ep.post == 2) {
+              if (kPost == 2) {
                 z_ptr = reinterpret_cast<const uint4*>(ep.aux_z + post_row * ep.ld_z + n0);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) z_raw[q] = __ldg(z_ptr + q);
@@ -821,7 +823,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
 #pragma unroll
               for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
             }
-            if (kConv && ep.post == 1) {          // GRU gate
+            if (kConv && kPost == 1) {          // GRU gate
               float hh[8];
               if (post_ld_h) {
                 h8_unpack(h_raw[u], hh);
@@ -831,7 +833,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
               }
 #pragma unroll
               for (int q = 0; q < 8; ++q) v[q] = sigmoid_fast(v[q]) * hh[q];
-            } else if (kConv && ep.post == 2) {   // GRU update
+            } else if (kConv && kPost == 2) {   // GRU update
               float hh[8], zz[8];
               if (post_ld_h) {
                 h8_unpack(h_raw[u & 3], hh);
@@ -848,7 +850,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
               for (int q = 0; q < 8; ++q) v[q] = fmaf(zz[q], tanh_fast(v[q]) - hh[q], hh[q]);   // (1 - z) h + z tanh(v)
             }
             uint32_t last2 = pack_half2(v[6], v[7]);
-            if (kConv && ep.post == 3 && n0 + u * 8 + 8 == N)   // tail: the last two columns carry 2 f16 of another row buffer
+            if (kConv && kPost == 3 && n0 + u * 8 + 8 == N)   // tail: the last two columns carry 2 f16 of another row buffer
               last2 = post_row >= 0 ? __ldg(reinterpret_cast<const uint32_t*>(ep.aux_h + post_row * ep.ld_h)) : 0u;
             sts128(buf0 + row_s + ((u ^ sw) << 4), pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), last2);
           }
@@ -860,11 +862,11 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
               const int cs = ct / cv.tiles_per_img;
               const int cti = ct - cs * cv.tiles_per_img, cty = cti / cv.tiles_x;
               const int sy = cty * cv.hb + quad * cv.rows_per_warp, sx = (cti - cty * cv.tiles_x) * cv.wo;
-              if (ep.post == 1 && n0 >= ep.post_c) {
+              if (kPost == 1 && n0 >= ep.post_c) {
                 tma_store_4d(&tma_res, buf0, n0 - ep.post_c, sx, sy, cs);      // r * h -> the q convolution's input slot
               } else {
                 tma_store_4d(&tma_out, buf0, n0, sx, sy, cs);
-                if (ep.post != 1 && ep.has_out2) tma_store_4d(&tma_res, buf0, n0, sx, sy, cs);   // second destination (GRU update: the dense copy of h)
+                if (kPost != 1 && ep.has_out2) tma_store_4d(&tma_res, buf0, n0, sx, sy, cs);   // second destination (GRU update: the dense copy of h)
               }
             } else {
               tma_store_2d(&tma_out, buf0, n0, row0);
@@ -1095,11 +1097,11 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
 
 static int g_gemm_cta2 = 1;  // CTA-pair kernels: on by default (cwm_debug_gemm_cta2(0) / CWM_GEMM_CTA2=0 switch them off)
 
-template <int BN, bool kRes, bool kCta2, bool kConv>
+template <int BN, bool kRes, bool kCta2, int kConv>
 static int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const CUtensorMap& tr,
                             const CUtensorMap& tx, int M, int N, int K, const EpiDev& ep, cudaStream_t stream,
                             const ConvDev& cv_in) {
-  using Cfg = GemmCfg<BN, kRes, kConv>;
+  using Cfg = GemmCfg<BN, kRes, (kConv != 0)>;
   static bool attr_set = false;
   if (!attr_set) {
     CWM_CUDA_CHECK(cudaFuncSetAttribute(gemm_f16_kernel<BN, kRes, kCta2, kConv>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1163,7 +1165,7 @@ static int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tw, const 
   }
 }
 
-template <int BN, bool kRes, bool kConv = false>
+template <int BN, bool kRes, int kConv = 0>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const CUtensorMap& tr,
                        const CUtensorMap& tx, int M, int N, int K, const EpiDev& ep, cudaStream_t stream, bool cta2,
                        const ConvDev& cv = ConvDev{0, 1, 0, 0, 1 << 30, 1, 1, 1, 32, 0, 0, 0, 2, 33 * 1024, 1, 1, 0, 0, 32, 1, 0, 0}) {
@@ -1395,11 +1397,25 @@ static int conv2d_impl(const uint16_t* x, int ldx, int S, int H, int W, int Cin,
                     2.0 * S * Ho * Wo * static_cast<double>(Cout) * cv.taps * Cin,
                     static_cast<double>(S) * (static_cast<double>(H) * W * Cin + static_cast<double>(Ho) * Wo * Cout) * 2.0 +
                         static_cast<double>(Cout) * K * 2.0);
+  // one kernel per (N tile, post-op): the post-ops that exist are tied to their N tiles (gate: 2C = 256 columns; update and
+  // tail: C = 128 columns), everything else is the plain bias / relu epilogue
+  if (post.post == 1) {
+    CWM_REQUIRE(bn == 256, "cwm_conv2d_gru_gate_f16: hidden width %d (2C must be a multiple of 256)", post.C);
+    return launch_gemm<256, false, 2>(ta, tw, to, to2, to, M, Cout, K, ep, s, cta2, cv);
+  }
+  if (post.post == 2) {
+    CWM_REQUIRE(bn == 128, "cwm_conv2d_gru_update_f16: hidden width %d (C must be a multiple of 128, not of 256)", post.C);
+    return launch_gemm<128, false, 3>(ta, tw, to, to2, to, M, Cout, K, ep, s, cta2, cv);
+  }
+  if (post.post == 3) {
+    CWM_REQUIRE(bn == 128, "cwm_conv2d_dual_f16 with a tail: %d output channels (a multiple of 128, not of 256)", Cout);
+    return launch_gemm<128, false, 4>(ta, tw, to, to2, to, M, Cout, K, ep, s, cta2, cv);
+  }
   switch (bn) {
-    case 64: return launch_gemm<64, false, true>(ta, tw, to, to2, to, M, Cout, K, ep, s, cta2, cv);
-    case 128: return launch_gemm<128, false, true>(ta, tw, to, to2, to, M, Cout, K, ep, s, cta2, cv);
-    case 192: return launch_gemm<192, false, true>(ta, tw, to, to2, to, M, Cout, K, ep, s, cta2, cv);
-    default: return launch_gemm<256, false, true>(ta, tw, to, to2, to, M, Cout, K, ep, s, cta2, cv);
+    case 64: return launch_gemm<64, false, 1>(ta, tw, to, to2, to, M, Cout, K, ep, s, cta2, cv);
+    case 128: return launch_gemm<128, false, 1>(ta, tw, to, to2, to, M, Cout, K, ep, s, cta2, cv);
+    case 192: return launch_gemm<192, false, 1>(ta, tw, to, to2, to, M, Cout, K, ep, s, cta2, cv);
+    default: return launch_gemm<256, false, 1>(ta, tw, to, to2, to, M, Cout, K, ep, s, cta2, cv);
   }
 }
 
