@@ -333,7 +333,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w,
                 const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_res,
                 const __grid_constant__ CUtensorMap tma_x16, int M, int N, int K, EpiDev ep, ConvDev cv) {
-  using Cfg = GemmCfg<BN, kRes, (kConv != 0)>;
+  constexpr bool kIsConv = kConv > 0;
+  // kConv < 0: plain GEMM with a compile-time f16 epilogue: -1 = fused LayerNorm + chunk-uniform q-scale (qkv), -2 = fused
+  // LayerNorm + GELU (fc1): the run-time variant checks per 16-byte unit disappear from the issue-bound epilogue
+  constexpr int kEpi = kConv < 0 ? -kConv : 0;
+  using Cfg = GemmCfg<BN, kRes, kIsConv>;
   constexpr int kPost = kConv > 0 ? kConv - 1 : 0;   // the convolution's post-op, compile-time: one variant per kernel
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_a = smem;
@@ -408,7 +412,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   // only the TMA / tcgen05 instructions themselves are issued by one elected lane.  Running the whole role under
   // `if (lane == 0)` makes every operand thread-private and the compiler wraps each TMA / MMA instruction in a
   // per-lane "waterfall" loop (R2UR + BRA.U.ANY), ~100 cycles of issue per instruction.
-  if (kConv && warp == 0 && cv.halo) {
+  if (kIsConv && warp == 0 && cv.halo) {
     // ===================== TMA producer, convolution halo mode =====================
     int stage = 0, hs = 0;
     uint32_t phase = 0, hphase = 0;
@@ -468,9 +472,9 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       const int n_blk = tile - m_blk * tiles_n;
       // convolution mode: this CTA's 128-row tile = image rows [cy0, cy0 + hb) of sample cs
       const int ct = m_blk * (kCta2 ? 2 : 1) + cta_rank;
-      const int cs = (kConv && cv.taps) ? ct / cv.tiles_per_img : 0;
-      const int cti = (kConv && cv.taps) ? ct - cs * cv.tiles_per_img : 0;
-      const int cty = (kConv && cv.taps) ? cti / cv.tiles_x : 0;
+      const int cs = (kIsConv && cv.taps) ? ct / cv.tiles_per_img : 0;
+      const int cti = (kIsConv && cv.taps) ? ct - cs * cv.tiles_per_img : 0;
+      const int cty = (kIsConv && cv.taps) ? cti / cv.tiles_x : 0;
       const int cy0 = cty * cv.hb * cv.stride - cv.pad_h;                 // input coordinates of the tile's first pixel
       const int cx0 = (cti - cty * cv.tiles_x) * cv.wo * cv.stride - cv.pad_w;
       int tap = 0, slab = 0;
@@ -480,7 +484,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
           if constexpr (kCta2) {
             // the leader expects the bytes of BOTH CTAs; both CTAs' loads complete on the leader's barrier
             if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (Cfg::kABytes + Cfg::kBBytes / 2));
-            if (kConv && cv.taps) {
+            if (kIsConv && cv.taps) {
               const int dy = tap / cv.kw;
               tma_load_4d_2sm(smem_a + stage * Cfg::kABytes, &tma_a, &full_bar[stage], slab * BK,
                               cx0 + tap - dy * cv.kw, cy0 + dy, cs);
@@ -491,7 +495,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
                             n_blk * BN + cta_rank * (BN / 2));
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            if (kConv && cv.taps) {
+            if (kIsConv && cv.taps) {
               const int dy = tap / cv.kw;
               tma_load_4d(smem_a + stage * Cfg::kABytes, &tma_a, &full_bar[stage], slab * BK, cx0 + tap - dy * cv.kw,
                           cy0 + dy, cs);
@@ -501,7 +505,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
             tma_load_2d(smem_b + stage * Cfg::kBBytes, &tma_w, &full_bar[stage], kb * BK, n_blk * BN);
           }
         }
-        if (kConv && ++slab == cv.cin_slabs) {
+        if (kIsConv && ++slab == cv.cin_slabs) {
           slab = 0;
           ++tap;
         }
@@ -512,7 +516,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         }
       }
     }
-  } else if (kConv && warp == 1 && cta_rank == 0 && cv.halo) {
+  } else if (kIsConv && warp == 1 && cta_rank == 0 && cv.halo) {
     // ===================== MMA issuer, convolution halo mode =====================
     // One elected thread issues everything, so the loop body per tap IS the pace of narrow convolutions: ncu of the
     // encoders' 64-channel 3x3 convolution showed this warp busy (not waiting) for ~470 cycles per tap against 128 cycles of
@@ -656,8 +660,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       constexpr int kChunks = BN / 64;
       // (the convolution instantiation has neither GELU, LayerNorm folding nor the q-scale: compiled out there -- its
       // epilogue code was 140 KB of SASS and ncu showed 24 % of the warp samples waiting for instruction fetch)
-      const bool gelu = !kConv && (ep.mode == CWM_EPI_GELU_F16);
-      const bool ln = !kConv && (ep.ln_stats_in != nullptr);
+      const bool gelu = kEpi == 2 || (kEpi == 0 && !kIsConv && (ep.mode == CWM_EPI_GELU_F16));
+      const bool ln = kEpi != 0 || (!kIsConv && (ep.ln_stats_in != nullptr));
       float2 ln_t[8];  // partial statistics of this thread's row in the tile being prepared (all loads back to back:
                        // a rolled loop serialises one L2 round trip per plane, measured +30 us per launch)
       auto load_ln_stats = [&](int row) {
@@ -699,7 +703,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         }
         // convolution post-ops: the pixel row this thread's tile row stands for (-1: a padding slot / beyond the image)
         long long post_row = -1;
-        if (kConv && kPost) {
+        if (kIsConv && kPost) {
           const int ct = m_blk * (kCta2 ? 2 : 1) + cta_rank;
           const int cs = ct / cv.tiles_per_img;
           const int tr = quad * 32 + lane;
@@ -710,7 +714,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         }
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
-        if (kConv && (cv.base_off & 2)) {   // timing experiment (CWM_CONV_BASEOFF=2): hand the accumulator straight back
+        if (kIsConv && (cv.base_off & 2)) {   // timing experiment (CWM_CONV_BASEOFF=2): hand the accumulator straight back
           tc_fence_before();
           if (lane == 0) { if constexpr (kCta2) mbar_arrive_leader(&tempty_bar[as]); else mbar_arrive(&tempty_bar[as]); }
           if (++as == 2) {
@@ -751,7 +755,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
           const uint4* h_ptr = nullptr;
           const uint4* z_ptr = nullptr;
           bool post_ld_h = false;
-          if (kConv && (kPost == 1 || kPost == 2)) {
+          if (kIsConv && (kPost == 1 || kPost == 2)) {
             const int hc = (kPost == 1) ? n0 - ep.post_c : n0;   // gate: only the r columns [C, 2C) read h
             post_ld_h = post_row >= 0 && hc >= 0;
             if (post_ld_h) {
@@ -780,8 +784,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
           __syncwarp();
           // chunk-uniform q-scale (the boundary is a multiple of 64 for every model: heads * 64); a chunk that
           // straddles it falls back to per-element selection
-          const bool sc_all = !kConv && !gelu && (n0 + 64 <= ep.scale_cols);
-          const bool sc_mixed = !kConv && !gelu && !sc_all && (n0 < ep.scale_cols);
+          const bool sc_all = kEpi == 2 ? false : (!kIsConv && !gelu && (n0 + 64 <= ep.scale_cols));
+          const bool sc_mixed = kEpi != 0 ? false : (!kIsConv && !gelu && !sc_all && (n0 < ep.scale_cols));
           const uint64_t sc2 = pk2(ep.scale, ep.scale);
           const uint64_t rstd2 = pk2(ln_rstd, ln_rstd);
           const uint64_t nmr2 = pk2(-ln_mean * ln_rstd, -ln_mean * ln_rstd);
@@ -819,11 +823,11 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
               for (int q = 0; q < 8; ++q)
                 if (n0 + u * 8 + q < ep.scale_cols) v[q] *= ep.scale;
             }
-            if (kConv && ep.relu) {
+            if (kIsConv && ep.relu) {
 #pragma unroll
               for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
             }
-            if (kConv && kPost == 1) {          // GRU gate
+            if (kIsConv && kPost == 1) {          // GRU gate
               float hh[8];
               if (post_ld_h) {
                 h8_unpack(h_raw[u], hh);
@@ -833,7 +837,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
               }
 #pragma unroll
               for (int q = 0; q < 8; ++q) v[q] = sigmoid_fast(v[q]) * hh[q];
-            } else if (kConv && kPost == 2) {   // GRU update
+            } else if (kIsConv && kPost == 2) {   // GRU update
               float hh[8], zz[8];
               if (post_ld_h) {
                 h8_unpack(h_raw[u & 3], hh);
@@ -850,14 +854,14 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
               for (int q = 0; q < 8; ++q) v[q] = fmaf(zz[q], tanh_fast(v[q]) - hh[q], hh[q]);   // (1 - z) h + z tanh(v)
             }
             uint32_t last2 = pack_half2(v[6], v[7]);
-            if (kConv && kPost == 3 && n0 + u * 8 + 8 == N)   // tail: the last two columns carry 2 f16 of another row buffer
+            if (kIsConv && kPost == 3 && n0 + u * 8 + 8 == N)   // tail: the last two columns carry 2 f16 of another row buffer
               last2 = post_row >= 0 ? __ldg(reinterpret_cast<const uint32_t*>(ep.aux_h + post_row * ep.ld_h)) : 0u;
             sts128(buf0 + row_s + ((u ^ sw) << 4), pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), last2);
           }
           fence_proxy_async_smem();
           __syncwarp();
           if (elect_one()) {
-            if (kConv && cv.taps) {  // this warp's 32 rows = rows_per_warp image rows of wb pixel slots; slots past the width are clipped
+            if (kIsConv && cv.taps) {  // this warp's 32 rows = rows_per_warp image rows of wb pixel slots; slots past the width are clipped
               const int ct = m_blk * (kCta2 ? 2 : 1) + cta_rank;
               const int cs = ct / cv.tiles_per_img;
               const int cti = ct - cs * cv.tiles_per_img, cty = cti / cv.tiles_x;
@@ -1101,7 +1105,7 @@ template <int BN, bool kRes, bool kCta2, int kConv>
 static int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const CUtensorMap& tr,
                             const CUtensorMap& tx, int M, int N, int K, const EpiDev& ep, cudaStream_t stream,
                             const ConvDev& cv_in) {
-  using Cfg = GemmCfg<BN, kRes, (kConv != 0)>;
+  using Cfg = GemmCfg<BN, kRes, (kConv > 0)>;
   static bool attr_set = false;
   if (!attr_set) {
     CWM_CUDA_CHECK(cudaFuncSetAttribute(gemm_f16_kernel<BN, kRes, kCta2, kConv>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1269,6 +1273,23 @@ extern "C" int cwm_gemm_f16(const uint16_t* A, const uint16_t* W, int M, int N, 
   ProfileScope prof(s, kNames[e->mode], 2.0 * M * N * K,
                     (static_cast<double>(M) * K + static_cast<double>(N) * K) * 2.0 + out_bytes);
   if (f16_out) {
+    // the two hot f16 epilogues of the VMAE blocks get compile-time variants (fused LayerNorm + q-scale on whole 64-column
+    // chunks: qkv; fused LayerNorm + GELU: fc1)
+    static int epi_env = -1;
+    if (epi_env < 0) {
+      const char* v = getenv("CWM_GEMM_EPI_VARIANTS");
+      epi_env = (v == nullptr) ? 1 : atoi(v);
+    }
+    if (epi_env && ep.ln_stats_in != nullptr && ep.bias != nullptr && (bn == 256 || bn == 192)) {
+      if (e->mode == CWM_EPI_GELU_F16) {
+        if (bn == 256) return launch_gemm<256, false, -2>(ta, tw, to, tr, tx, M, N, K, ep, s, cta2);
+        return launch_gemm<192, false, -2>(ta, tw, to, tr, tx, M, N, K, ep, s, cta2);
+      }
+      if (ep.scale_cols % 64 == 0) {
+        if (bn == 256) return launch_gemm<256, false, -1>(ta, tw, to, tr, tx, M, N, K, ep, s, cta2);
+        return launch_gemm<192, false, -1>(ta, tw, to, tr, tx, M, N, K, ep, s, cta2);
+      }
+    }
     switch (bn) {
       case 64: return launch_gemm<64, false>(ta, tw, to, tr, tx, M, N, K, ep, s, cta2);
       case 128: return launch_gemm<128, false>(ta, tw, to, tr, tx, M, N, K, ep, s, cta2);
