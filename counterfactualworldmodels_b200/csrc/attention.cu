@@ -30,6 +30,7 @@
 // random-init logits never trigger the rescale path or much warp drift, did not see it.
 
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -152,7 +153,7 @@ __device__ __forceinline__ ItemCoord decode_item(int item, int nq, int H, int N)
   return c;
 }
 
-template <int kPoly, bool kDbg>
+template <int kPoly, bool kDbg, bool kCompact>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attention_persist_kernel(const __grid_constant__ CUtensorMap tma_qkv, int N, int H, int B, __half* __restrict__ out,
                          float scale_log2, int strided, int war_safe, int stale_max) {
@@ -504,7 +505,30 @@ attention_persist_kernel(const __grid_constant__ CUtensorMap tma_qkv, int N, int
           }
           tmem_st_wait();
         };
-        float tile_sum;
+        float tile_sum = 0.f;
+        if constexpr (kCompact) {
+        // One call site for the exponentials (the kernel's largest block of code: four inlined copies made it 68 KB of
+        // SASS).  Before the pass: the first tile of an item takes its maximum as the reference; the exact (non-stale)
+        // mode checks every tile's maximum up front.  After the pass, in stale mode: the tile maximum is checked, and in the
+        // rare case it exceeds the reference by more than the threshold the tile is redone (second pass) after the rescale.
+        if (j == 0) {
+          m_ref = tile_max();
+        } else if (!stale_max) {
+          const float row_max = tile_max();
+          const bool need = (row_max - m_ref) * scale_log2 > kRescaleThreshold;
+          if (__any_sync(0xffffffffu, need)) rescale(row_max, need);
+        }
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+          tile_sum = exp_tile(-m_ref * scale_log2);
+          if (pass == 1 || j == 0 || !stale_max) break;
+          const float row_max = tile_max();
+          const bool need = (row_max - m_ref) * scale_log2 > kRescaleThreshold;
+          if (!__any_sync(0xffffffffu, need)) break;   // the common case
+          tmem_st_wait();
+          rescale(row_max, need);
+        }
+        } else {
         if (j == 0) {
           m_ref = tile_max();
           tile_sum = exp_tile(-m_ref * scale_log2);
@@ -522,6 +546,7 @@ attention_persist_kernel(const __grid_constant__ CUtensorMap tma_qkv, int N, int
           const bool need = (row_max - m_ref) * scale_log2 > kRescaleThreshold;
           if (__any_sync(0xffffffffu, need)) rescale(row_max, need);
           tile_sum = exp_tile(-m_ref * scale_log2);
+        }
         }
         tmem_st_wait();
         l_sum += tile_sum;
@@ -597,12 +622,18 @@ extern "C" int cwm_attention_f16(const uint16_t* qkv, int B, int N, int H, int h
   const long long n_items = static_cast<long long>((N + 255) / 256) * H * B;
   CWM_REQUIRE(n_items < (1ll << 31), "cwm_attention_f16: too many work items");
   using KernelFn = void (*)(const CUtensorMap, int, int, int, __half*, float, int, int, int);
-  static const KernelFn kernels[6] = {attention_persist_kernel<0, false>, attention_persist_kernel<1, false>,
-                                      attention_persist_kernel<2, false>, attention_persist_kernel<3, false>,
-                                      attention_persist_kernel<4, false>, attention_persist_kernel<kDefaultPoly, true>};
+  // [0..4] = exponentials-on-the-FMA-pipe share kPoly, [5] = the debug build, [6] = the default kPoly with the softmax tile
+  // as ONE inlined call site (2864 instead of 4256 SASS instructions; CWM_ATTN_COMPACT=1)
+  static const KernelFn kernels[7] = {attention_persist_kernel<0, false, false>, attention_persist_kernel<1, false, false>,
+                                      attention_persist_kernel<2, false, false>, attention_persist_kernel<3, false, false>,
+                                      attention_persist_kernel<4, false, false>, attention_persist_kernel<kDefaultPoly, true, false>,
+                                      attention_persist_kernel<kDefaultPoly, false, true>};
   static bool attr_set = false;
+  static int compact_env = 0;
   if (!attr_set) {
-    for (int i = 0; i < 6; ++i)
+    const char* v = getenv("CWM_ATTN_COMPACT");
+    compact_env = (v != nullptr) ? atoi(v) : 0;
+    for (int i = 0; i < 7; ++i)
       CWM_CUDA_CHECK(cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kPersistSmemBytes));
     attr_set = true;
   }
@@ -618,7 +649,7 @@ extern "C" int cwm_attention_f16(const uint16_t* qkv, int B, int N, int H, int h
   // (part of) the 126 MB L2, strided otherwise; one item per CTA is the strided map with grid = items
   const double kv_resident = 2.0 * N * 64 * 2 * grid;
   const int strided = !multi ? 1 : (g_attn_persist_map >= 0) ? g_attn_persist_map : (kv_resident > 48e6 ? 1 : 0);
-  kernels[(g_attn_mode == 2 || g_attn_mode == 4) ? 5 : g_attn_poly]<<<grid, kAttnThreads, kPersistSmemBytes,
+  kernels[(g_attn_mode == 2 || g_attn_mode == 4) ? 5 : ((compact_env && g_attn_poly == kDefaultPoly) ? 6 : g_attn_poly)]<<<grid, kAttnThreads, kPersistSmemBytes,
                                                                       static_cast<cudaStream_t>(stream)>>>(
       tm, N, H, B, reinterpret_cast<__half*>(out), kLog2e, strided, g_attn_war_safe, g_attn_stale_max);
   CWM_LAUNCH_CHECK();
