@@ -38,7 +38,7 @@ EXPORTED_SYMBOLS = (
     "cwm_mask_rectangularize_workspace_bytes", "cwm_mask_rectangularize",
     # tuning hooks (header section "tuning hooks")
     "cwm_debug_attention_poly", "cwm_debug_attention_war_safe", "cwm_debug_attention_persistent",
-    "cwm_debug_attention_persist_map", "cwm_debug_attention_stale_max", "cwm_debug_attn_mma_wide", "cwm_debug_attn_mma_split", "cwm_debug_gemm_cta2",
+    "cwm_debug_attention_persist_map", "cwm_debug_attention_stale_max", "cwm_debug_attention_skip_idle", "cwm_debug_attn_mma_wide", "cwm_debug_attn_mma_split", "cwm_debug_gemm_cta2",
 )
 
 
@@ -125,7 +125,7 @@ def _declare(lib):
     lib.cwm_launch_count_reset.restype = c_int
     lib.cwm_total_launches.restype = ctypes.c_longlong
     for name in ("cwm_debug_attention_poly", "cwm_debug_attention_war_safe", "cwm_debug_attention_persistent",
-                 "cwm_debug_attention_persist_map", "cwm_debug_attention_stale_max", "cwm_debug_attn_mma_wide", "cwm_debug_attn_mma_split"):
+                 "cwm_debug_attention_persist_map", "cwm_debug_attention_stale_max", "cwm_debug_attention_skip_idle", "cwm_debug_attn_mma_wide", "cwm_debug_attn_mma_split"):
         getattr(lib, name).argtypes = [c_int]
         getattr(lib, name).restype = None
     lib.cwm_debug_gemm_cta2.argtypes = [c_int]

@@ -417,6 +417,15 @@ attention_persist_kernel(const __grid_constant__ CUtensorMap tma_qkv, int N, int
         const int kv_valid = N - j * 128;                     // columns >= kv_valid are padding
         WAIT(&s_full[2 * t + (gt & 1)], (gt >> 1) & 1, 11 + t, gt);
         tc_fence_after();
+        if ((stale_max & 2) && ic.q0 + t * 128 + quad * 32 >= N) {
+          // every query row of this warp lies beyond the sequence (the ragged last tile: N = 788 leaves 20 rows, N = 1568
+          // leaves 32): its rows of P feed rows of O that are never stored, so the tile's exponentials are skipped and the
+          // buffer is handed on as it is -- the XU / issue slots go to the warps that have rows
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[2 * t + (gt & 1)]);
+          continue;
+        }
         uint32_t s[128];
         tmem_ld_x32(tm_s + 0, s);
         tmem_ld_x32(tm_s + 32, s + 32);
@@ -513,7 +522,7 @@ attention_persist_kernel(const __grid_constant__ CUtensorMap tma_qkv, int N, int
         // rare case it exceeds the reference by more than the threshold the tile is redone (second pass) after the rescale.
         if (j == 0) {
           m_ref = tile_max();
-        } else if (!stale_max) {
+        } else if (!(stale_max & 1)) {
           const float row_max = tile_max();
           const bool need = (row_max - m_ref) * scale_log2 > kRescaleThreshold;
           if (__any_sync(0xffffffffu, need)) rescale(row_max, need);
@@ -521,7 +530,7 @@ attention_persist_kernel(const __grid_constant__ CUtensorMap tma_qkv, int N, int
 #pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {
           tile_sum = exp_tile(-m_ref * scale_log2);
-          if (pass == 1 || j == 0 || !stale_max) break;
+          if (pass == 1 || j == 0 || !(stale_max & 1)) break;
           const float row_max = tile_max();
           const bool need = (row_max - m_ref) * scale_log2 > kRescaleThreshold;
           if (!__any_sync(0xffffffffu, need)) break;   // the common case
@@ -532,7 +541,7 @@ attention_persist_kernel(const __grid_constant__ CUtensorMap tma_qkv, int N, int
         if (j == 0) {
           m_ref = tile_max();
           tile_sum = exp_tile(-m_ref * scale_log2);
-        } else if (stale_max) {
+        } else if (stale_max & 1) {
           tile_sum = exp_tile(-m_ref * scale_log2);
           const float row_max = tile_max();
           const bool need = (row_max - m_ref) * scale_log2 > kRescaleThreshold;
@@ -603,8 +612,10 @@ extern "C" void cwm_debug_attention_poly(int eighths) {
 static int g_attn_mode = 1;
 static int g_attn_persist_map = -1;  // -1 = automatic, 0 = contiguous ranges, 1 = strided
 static int g_attn_war_safe = 1;
-static int g_attn_stale_max = 1;  // exponentials against the running reference, tile maximum checked afterwards
-extern "C" void cwm_debug_attention_stale_max(int on) { g_attn_stale_max = on; }
+static int g_attn_stale_max = 3;  // bit 0: exponentials against the running reference, tile maximum checked afterwards;
+                                  // bit 1: warps whose 32 query rows all lie beyond the sequence skip the tile's exponentials
+extern "C" void cwm_debug_attention_stale_max(int on) { g_attn_stale_max = (g_attn_stale_max & 2) | (on ? 1 : 0); }
+extern "C" void cwm_debug_attention_skip_idle(int on) { g_attn_stale_max = (g_attn_stale_max & 1) | (on ? 2 : 0); }
 extern "C" void cwm_debug_attention_war_safe(int on) { g_attn_war_safe = on; }
 extern "C" void cwm_debug_attention_persistent(int mode) { g_attn_mode = (mode <= 0) ? 3 : mode; }
 extern "C" void cwm_debug_attention_persist_map(int m) { g_attn_persist_map = m; }

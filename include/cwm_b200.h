@@ -564,6 +564,7 @@ long long cwm_total_launches(void);
 void cwm_debug_attention_poly(int eighths);        /* share (in 1/8) of the softmax exponentials evaluated on the FMA pipe */
 void cwm_debug_attention_war_safe(int on);         /* conservative score-buffer reuse (debug) */
 void cwm_debug_attention_stale_max(int on);        /* 1 (default): exponentials first, tile maximum checked afterwards */
+void cwm_debug_attention_skip_idle(int on);        /* 1 (default): warps whose query rows all lie beyond the sequence skip the tile */
 void cwm_debug_attention_persistent(int mode);     /* 1 = persistent CTAs (default), 3 = one work item per CTA; 2 / 4 = the same with watchdog waits */
 void cwm_debug_attention_persist_map(int m);       /* work-item map of the persistent kernel: -1 auto, 0 ranges, 1 strided */
 void cwm_debug_attn_mma_wide(int on);              /* small-attention kernel: 8 warps per K/V tile */

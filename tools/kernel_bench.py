@@ -182,6 +182,9 @@ if __name__ == "__main__":
         lib = _lib.load()
         lib.cwm_debug_attention_persistent(int(os.environ["CWM_ATTN_PERSIST"]))
         print("attention mode (3 = one item per CTA, 1 = experimental multi-item) =", os.environ["CWM_ATTN_PERSIST"])
+    if os.environ.get("CWM_ATTN_SKIP"):
+        _lib.load().cwm_debug_attention_skip_idle(int(os.environ["CWM_ATTN_SKIP"]))
+        print("attention skip-idle-warps =", os.environ["CWM_ATTN_SKIP"])
     if os.environ.get("CWM_ATTN_STALE"):
         _lib.load().cwm_debug_attention_stale_max(int(os.environ["CWM_ATTN_STALE"]))
         print("attention stale-max =", os.environ["CWM_ATTN_STALE"])
