@@ -915,25 +915,33 @@ extern "C" int cwm_raft_flow_update_taps(const uint16_t* taps, int ldt, const fl
 // the 49 taps x 2 channels of pixel m's neighbourhood in (ky, kx, c) order (zero outside the image), padded to `ldo`
 // columns -- a K = 98 convolution becomes one plain K = 128 GEMM instead of 49 nearly empty 64-channel k-steps.
 namespace cwm {
-__global__ void raft_im2col_flow_kernel(const __half* __restrict__ flow16, int ldf, int H, int W, long long M, int k,
-                                        __half* __restrict__ out, int ldo) {
+// K > 0: compile-time kernel size (the index arithmetic is divisions by k and by the map size; with run-time divisors the
+// kernel was instruction bound at 15 us for 12.8 MB)
+template <int K>
+__global__ void __launch_bounds__(256)
+raft_im2col_flow_kernel(const __half* __restrict__ flow16, int ldf, int H, int W, long long M, int k_rt,
+                        __half* __restrict__ out, int ldo) {
+  const int k = K > 0 ? K : k_rt;
   const int units = ldo / 8;   // one thread writes four taps x two channels = one 16-byte store
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= M * units) return;
-  const long long m = idx / units;
-  const int tap0 = static_cast<int>(idx - m * units) * 4;
-  const int hw = H * W;
-  const int pix = static_cast<int>(m % hw);
-  const int py = pix / W - k / 2, px = pix % W - k / 2;
-  const __half* img = flow16 + (m - pix) * ldf;
+  // grid.y = image row (sample, y): no division by the map size; threadIdx / blockIdx.x walk (x, unit)
+  const long long row = blockIdx.y;                 // (sample * H + y)
+  const int y = static_cast<int>(row % H);
+  const int xu = blockIdx.x * blockDim.x + threadIdx.x;
+  if (xu >= W * units) return;
+  const int x = xu / units, u = xu - x * units;
+  const int tap0 = u * 4;
+  const long long m = row * W + x;
+  const __half* img = flow16 + (row - y) * W * ldf;      // first pixel of this sample
+  const int py = y - k / 2, px = x - k / 2;
   uint32_t v[4];
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
     const int tap = tap0 + t;
     v[t] = 0u;
     if (tap < k * k) {
-      const int y = py + tap / k, x = px + tap % k;
-      if (y >= 0 && y < H && x >= 0 && x < W) v[t] = *reinterpret_cast<const uint32_t*>(img + (static_cast<long long>(y) * W + x) * ldf);
+      const int ty = tap / k;
+      const int yy = py + ty, xx = px + tap - ty * k;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v[t] = *reinterpret_cast<const uint32_t*>(img + (static_cast<long long>(yy) * W + xx) * ldf);
     }
   }
   *reinterpret_cast<uint4*>(out + m * ldo + 2 * tap0) = make_uint4(v[0], v[1], v[2], v[3]);
@@ -949,9 +957,14 @@ extern "C" int cwm_raft_im2col_flow(const uint16_t* flow16, int ldf, int B, int 
   const long long M = static_cast<long long>(B) * H * W;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ProfileScope prof(st, "raft_im2col_flow", 0.0, static_cast<double>(M) * (ldo * 2.0 + 4.0 * k * k));
-  const long long threads = M * (ldo / 8);
-  cwm::raft_im2col_flow_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(
-      reinterpret_cast<const __half*>(flow16), ldf, H, W, M, k, reinterpret_cast<__half*>(out), ldo);
+  CWM_REQUIRE(static_cast<long long>(B) * H <= 65535, "cwm_raft_im2col_flow: B * H = %lld exceeds the grid limit", static_cast<long long>(B) * H);
+  const dim3 grid((W * (ldo / 8) + 255) / 256, B * H);
+  if (k == 7)
+    cwm::raft_im2col_flow_kernel<7><<<grid, 256, 0, st>>>(reinterpret_cast<const __half*>(flow16), ldf, H, W, M, k,
+                                                          reinterpret_cast<__half*>(out), ldo);
+  else
+    cwm::raft_im2col_flow_kernel<0><<<grid, 256, 0, st>>>(reinterpret_cast<const __half*>(flow16), ldf, H, W, M, k,
+                                                          reinterpret_cast<__half*>(out), ldo);
   CWM_LAUNCH_CHECK();
   return CWM_OK;
 }
