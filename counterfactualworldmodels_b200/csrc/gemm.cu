@@ -407,6 +407,12 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   if constexpr (kCta2) cluster_sync_all(); else __syncthreads();  // barrier inits visible to the peer CTA as well
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barrier init, tensor-memory allocation, descriptor prefetch) touches
+  // no global memory and may run while the previous kernel of the stream drains; nothing below may start before that
+  // kernel has completed and flushed.  The dependents of THIS kernel are released at once: their CTAs cannot become
+  // resident before ours exit (shared / tensor memory), so all they gain is their launch latency and prologue.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   // NOTE: the producer and MMA roles run warp-uniformly (all 32 lanes execute the loops and the mbarrier waits) and
   // only the TMA / tcgen05 instructions themselves are issued by one elected lane.  Running the whole role under
@@ -1099,6 +1105,16 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   }
 }
 
+// programmatic dependent launch of the GEMM / convolution kernels (CWM_PDL=0 switches it off)
+static bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* v = getenv("CWM_PDL");
+    on = (v == nullptr) ? 1 : atoi(v);
+  }
+  return on != 0;
+}
+
 static int g_gemm_cta2 = 1;  // CTA-pair kernels: on by default (cwm_debug_gemm_cta2(0) / CWM_GEMM_CTA2=0 switch them off)
 
 template <int BN, bool kRes, bool kCta2, int kConv>
@@ -1150,21 +1166,33 @@ static int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tw, const 
     cfg.blockDim = dim3(kGemmThreads);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     CWM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_f16_kernel<BN, kRes, true, kConv>, ta, tw, to, tr, tx, M, N, K, ep, cv));
     count_launch();
     return CWM_OK;
   } else {
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    gemm_f16_kernel<BN, kRes, false, kConv><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tw, to, tr, tx, M, N, K, ep, cv);
-    CWM_LAUNCH_CHECK();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    CWM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_f16_kernel<BN, kRes, false, kConv>, ta, tw, to, tr, tx, M, N, K, ep, cv));
+    count_launch();
     return CWM_OK;
   }
 }
