@@ -7,6 +7,8 @@
 #include <string>
 #include <vector>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace cwm {
@@ -119,6 +121,15 @@ int make_tmap_nhwc(CUtensorMap* map, const void* base, uint64_t S, uint64_t H, u
                 (int)r, (unsigned long long)S, (unsigned long long)H, (unsigned long long)W, (unsigned long long)C,
                 (unsigned long long)ld, box_h, box_w, box_c);
   return CWM_OK;
+}
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* v = getenv("CWM_PDL");
+    on = (v == nullptr) ? 1 : atoi(v);
+  }
+  return on != 0;
 }
 
 int num_sms() {

@@ -248,6 +248,7 @@ attention_persist_kernel(const __grid_constant__ CUtensorMap tma_qkv, int N, int
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  grid_dep_sync();   // programmatic dependent launch: the set-up above overlapped the previous kernel's drain
 
   if (warp < 4) {
     reg_dec<64>();
@@ -660,9 +661,9 @@ extern "C" int cwm_attention_f16(const uint16_t* qkv, int B, int N, int H, int h
   // (part of) the 126 MB L2, strided otherwise; one item per CTA is the strided map with grid = items
   const double kv_resident = 2.0 * N * 64 * 2 * grid;
   const int strided = !multi ? 1 : (g_attn_persist_map >= 0) ? g_attn_persist_map : (kv_resident > 48e6 ? 1 : 0);
-  kernels[(g_attn_mode == 2 || g_attn_mode == 4) ? 5 : ((compact_env && g_attn_poly == kDefaultPoly) ? 6 : g_attn_poly)]<<<grid, kAttnThreads, kPersistSmemBytes,
-                                                                      static_cast<cudaStream_t>(stream)>>>(
-      tm, N, H, B, reinterpret_cast<__half*>(out), kLog2e, strided, g_attn_war_safe, g_attn_stale_max);
+  CWM_CUDA_CHECK(launch_pdl(kernels[(g_attn_mode == 2 || g_attn_mode == 4) ? 5 : ((compact_env && g_attn_poly == kDefaultPoly) ? 6 : g_attn_poly)],
+                            dim3(grid), dim3(kAttnThreads), kPersistSmemBytes, static_cast<cudaStream_t>(stream), tm, N, H, B,
+                            reinterpret_cast<__half*>(out), kLog2e, strided, g_attn_war_safe, g_attn_stale_max));
   CWM_LAUNCH_CHECK();
   return CWM_OK;
 }

@@ -77,6 +77,9 @@ int make_tmap_nhwc(CUtensorMap* map, const void* base, uint64_t S, uint64_t H, u
 int make_tmap_3d_f32(CUtensorMap* map, const void* base, uint64_t S, uint64_t R, uint64_t C, uint32_t box_rows,
                      uint32_t box_cols);
 int num_sms();
+// programmatic dependent launch (CWM_PDL=0 switches it off): kernels launched through launch_pdl() may start while the
+// previous kernel of the stream drains; they call grid_dep_sync() before their first global-memory access
+bool pdl_enabled();
 
 // Optional per-launch CUDA-event timing (cwm_profile_begin/end).  No-op (one branch) when profiling is off.
 struct ProfileScope {
@@ -322,10 +325,35 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// Programmatic dependent launch, device side: wait for the previous kernel of the stream (complete and flushed), then
+// release our own dependents at once (they only gain their launch latency / prologue).  No-ops for a normal launch.
+__device__ __forceinline__ void grid_dep_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 #endif  // __CUDACC__
+
+
+// Launch `kernel` with the programmatic-stream-serialization attribute (when enabled).  The kernel MUST call
+// grid_dep_sync() before its first global-memory access.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 }  // namespace cwm

@@ -411,8 +411,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   // no global memory and may run while the previous kernel of the stream drains; nothing below may start before that
   // kernel has completed and flushed.  The dependents of THIS kernel are released at once: their CTAs cannot become
   // resident before ours exit (shared / tensor memory), so all they gain is their launch latency and prologue.
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  grid_dep_sync();
 
   // NOTE: the producer and MMA roles run warp-uniformly (all 32 lanes execute the loops and the mbarrier waits) and
   // only the TMA / tcgen05 instructions themselves are issued by one elected lane.  Running the whole role under
@@ -1103,16 +1102,6 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     tc_fence_after();
     if constexpr (kCta2) tmem_dealloc2(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
-}
-
-// programmatic dependent launch of the GEMM / convolution kernels (CWM_PDL=0 switches it off)
-static bool pdl_enabled() {
-  static int on = -1;
-  if (on < 0) {
-    const char* v = getenv("CWM_PDL");
-    on = (v == nullptr) ? 1 : atoi(v);
-  }
-  return on != 0;
 }
 
 static int g_gemm_cta2 = 1;  // CTA-pair kernels: on by default (cwm_debug_gemm_cta2(0) / CWM_GEMM_CTA2=0 switch them off)

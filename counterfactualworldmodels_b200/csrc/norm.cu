@@ -26,6 +26,7 @@ __device__ __forceinline__ void h8_to_f32(const uint4& u, float* f) {
 __global__ void __launch_bounds__(kNormThreads)
 instnorm_stats_kernel(const __half* __restrict__ x, int HW, int C, int nslab, float2* __restrict__ partial) {
   extern __shared__ float2 red[];   // [pixel lanes][C]
+  grid_dep_sync();
   const int s = blockIdx.y, slab = blockIdx.x;
   const int groups = C >> 3;                       // 8-channel groups per pixel
   const int lanes = kNormThreads / groups;         // pixels in flight
@@ -67,6 +68,7 @@ instnorm_apply_kernel(const __half* __restrict__ x, const float2* __restrict__ p
                       int relu_inner, const __half* __restrict__ add, int relu_outer, int pixels_per_block,
                       __half* __restrict__ out) {
   extern __shared__ float2 stat[];   // [C]: (mean, rstd)
+  grid_dep_sync();
   const int s = blockIdx.y;
   for (int c = threadIdx.x; c < C; c += kNormThreads) {
     float a = 0.f, b = 0.f;
@@ -236,7 +238,8 @@ extern "C" int cwm_instnorm_f16(const uint16_t* x, int S, int HW, int C, float e
       CWM_CUDA_CHECK(cudaFuncSetAttribute(instnorm_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
       configured = smem;
     }
-    instnorm_stats_kernel<<<dim3(nslab, S), kNormThreads, smem, st>>>(reinterpret_cast<const __half*>(x), HW, C, nslab, partial);
+    CWM_CUDA_CHECK(launch_pdl(instnorm_stats_kernel, dim3(nslab, S), dim3(kNormThreads), smem, st, reinterpret_cast<const __half*>(x),
+                              HW, C, nslab, partial));
     CWM_LAUNCH_CHECK();
   }
   {
@@ -246,9 +249,9 @@ extern "C" int cwm_instnorm_f16(const uint16_t* x, int S, int HW, int C, float e
     int ppb = (HW + blocks - 1) / blocks;
     if (ppb < 8) ppb = 8;
     blocks = (HW + ppb - 1) / ppb;
-    instnorm_apply_kernel<<<dim3(blocks, S), kNormThreads, C * sizeof(float2), st>>>(
-        reinterpret_cast<const __half*>(x), partial, nslab, HW, C, eps, relu_inner, reinterpret_cast<const __half*>(add),
-        relu_outer, ppb, reinterpret_cast<__half*>(out));
+    CWM_CUDA_CHECK(launch_pdl(instnorm_apply_kernel, dim3(blocks, S), dim3(kNormThreads), C * sizeof(float2), st,
+                              reinterpret_cast<const __half*>(x), static_cast<const float2*>(partial), nslab, HW, C, eps, relu_inner,
+                              reinterpret_cast<const __half*>(add), relu_outer, ppb, reinterpret_cast<__half*>(out)));
     CWM_LAUNCH_CHECK();
   }
   return CWM_OK;

@@ -499,6 +499,7 @@ __global__ void __launch_bounds__(256)
 raft_flow_update_taps_kernel(const __half* __restrict__ taps, int ldt, const float* __restrict__ bias, float* __restrict__ coords1,
                              int H, int W, long long M, __half* __restrict__ flow16, __half* __restrict__ dst1, int ld1,
                              __half* __restrict__ dst2, int ld2) {
+  grid_dep_sync();
   const long long m = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (m >= M) return;
   const int HW = H * W;
@@ -561,6 +562,7 @@ raft_corr_lookup_fast_kernel(const __grid_constant__ CorrLevels lv, int L, const
   __shared__ float win[kFastItems * kFastWin * kFastPitch];     // [pix][lvl][10][11]
   __shared__ __align__(16) __half rows[kFastPix * 328];         // [pix][ld <= 328]
   __shared__ FastItem items[kFastItems];
+  grid_dep_sync();   // (launched with programmatic stream serialization)
   const long long p0 = static_cast<long long>(blockIdx.x) * kFastPix;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid < kFastItems) {
@@ -783,8 +785,8 @@ static int corr_lookup_impl(const float* const* levels, int num_levels, int radi
     double pyr_f = 0.0;
     for (int l = 0; l < num_levels; ++l) pyr_f += static_cast<double>(min(kFastWin, lv.w[l])) * min(kFastWin, lv.h[l]);
     ProfileScope prof(st_fast, "raft_corr_lookup", 0.0, static_cast<double>(Pf) * (0.5 * ld16 + pyr_f + 2.0) * 4.0);
-    raft_corr_lookup_fast_kernel<<<static_cast<unsigned>((Pf + kFastPix - 1) / kFastPix), kFastThreads, 0, st_fast>>>(
-        lv, num_levels, coords, Pf, H * W, out16, ld16);
+    CWM_CUDA_CHECK(launch_pdl(raft_corr_lookup_fast_kernel, dim3(static_cast<unsigned>((Pf + kFastPix - 1) / kFastPix)),
+                              dim3(kFastThreads), 0, st_fast, lv, num_levels, coords, Pf, H * W, out16, ld16));
     CWM_LAUNCH_CHECK();
     return CWM_OK;
   }
@@ -904,9 +906,9 @@ extern "C" int cwm_raft_flow_update_taps(const uint16_t* taps, int ldt, const fl
   const long long M = static_cast<long long>(B) * H * W;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ProfileScope prof(st, "raft_flow_update_taps", 0.0, static_cast<double>(M) * (36.0 + 36.0 + 8.0));
-  raft_flow_update_taps_kernel<<<blocks_for(M), 256, 0, st>>>(reinterpret_cast<const __half*>(taps), ldt, bias, coords1, H, W, M,
-                                                             reinterpret_cast<__half*>(flow16), reinterpret_cast<__half*>(dst1),
-                                                             ld1, reinterpret_cast<__half*>(dst2), ld2);
+  CWM_CUDA_CHECK(launch_pdl(raft_flow_update_taps_kernel, dim3(blocks_for(M)), dim3(256), 0, st,
+                            reinterpret_cast<const __half*>(taps), ldt, bias, coords1, H, W, M, reinterpret_cast<__half*>(flow16),
+                            reinterpret_cast<__half*>(dst1), ld1, reinterpret_cast<__half*>(dst2), ld2));
   CWM_LAUNCH_CHECK();
   return CWM_OK;
 }
@@ -921,6 +923,7 @@ template <int K>
 __global__ void __launch_bounds__(256)
 raft_im2col_flow_kernel(const __half* __restrict__ flow16, int ldf, int H, int W, long long M, int k_rt,
                         __half* __restrict__ out, int ldo) {
+  grid_dep_sync();
   const int k = K > 0 ? K : k_rt;
   const int units = ldo / 8;   // one thread writes four taps x two channels = one 16-byte store
   // grid.y = image row (sample, y): no division by the map size; threadIdx / blockIdx.x walk (x, unit)
@@ -960,11 +963,11 @@ extern "C" int cwm_raft_im2col_flow(const uint16_t* flow16, int ldf, int B, int 
   CWM_REQUIRE(static_cast<long long>(B) * H <= 65535, "cwm_raft_im2col_flow: B * H = %lld exceeds the grid limit", static_cast<long long>(B) * H);
   const dim3 grid((W * (ldo / 8) + 255) / 256, B * H);
   if (k == 7)
-    cwm::raft_im2col_flow_kernel<7><<<grid, 256, 0, st>>>(reinterpret_cast<const __half*>(flow16), ldf, H, W, M, k,
-                                                          reinterpret_cast<__half*>(out), ldo);
+    CWM_CUDA_CHECK(cwm::launch_pdl(cwm::raft_im2col_flow_kernel<7>, grid, dim3(256), 0, st, reinterpret_cast<const __half*>(flow16),
+                                   ldf, H, W, M, k, reinterpret_cast<__half*>(out), ldo));
   else
-    cwm::raft_im2col_flow_kernel<0><<<grid, 256, 0, st>>>(reinterpret_cast<const __half*>(flow16), ldf, H, W, M, k,
-                                                          reinterpret_cast<__half*>(out), ldo);
+    CWM_CUDA_CHECK(cwm::launch_pdl(cwm::raft_im2col_flow_kernel<0>, grid, dim3(256), 0, st, reinterpret_cast<const __half*>(flow16),
+                                   ldf, H, W, M, k, reinterpret_cast<__half*>(out), ldo));
   CWM_LAUNCH_CHECK();
   return CWM_OK;
 }
