@@ -195,8 +195,8 @@ def _declare(lib):
                                               c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]
     lib.cwm_conv2d_strided_f16.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
                                            c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]
-    lib.cwm_im2col_nchw_f16.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p,
-                                        c_int, c_void_p]
+    lib.cwm_im2col_nchw_f16.argtypes = [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float,
+                                        c_void_p, c_int, c_void_p]
     lib.cwm_add_act_f16.argtypes = [c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p]
     lib.cwm_conv2d_dual_f16.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                         c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]

@@ -125,8 +125,8 @@ constexpr int kIm2colTile = 32;   // output pixels of one image row per CTA
 // the kernel is instruction-bound: 370 us instead of ~100 us for 65 frames); 0 = take the run-time arguments.
 template <int CIN, int K, int STRIDE, int LDO>
 __global__ void __launch_bounds__(256)
-im2col_nchw_kernel(const float* __restrict__ img, int Cin_rt, int H, int W, int Ho, int Wo, int k_rt, int stride_rt, int pad,
-                   float scale, float shift, __half* __restrict__ out, int ldo_rt) {
+im2col_nchw_kernel(const float* __restrict__ img, long long sample_stride, int Cin_rt, int H, int W, int Ho, int Wo, int k_rt,
+                   int stride_rt, int pad, float scale, float shift, __half* __restrict__ out, int ldo_rt) {
   const int Cin = CIN > 0 ? CIN : Cin_rt, k = K > 0 ? K : k_rt, stride = STRIDE > 0 ? STRIDE : stride_rt;
   const int ldo = LDO > 0 ? LDO : ldo_rt;
   // the input patch of this CTA's 32 output pixels: [Cin][k][WT] floats, WT = 31 * stride + k, staged with coalesced
@@ -137,7 +137,7 @@ im2col_nchw_kernel(const float* __restrict__ img, int Cin_rt, int H, int W, int 
   int* col_off = reinterpret_cast<int*>(patch + Cin * k * WT);   // [ldo]: patch offset of im2col column (ky, kx, c); -1 = pad
   const int ox0 = blockIdx.x * kIm2colTile, oy = blockIdx.y;
   const long long s = blockIdx.z;
-  const float* im = img + s * Cin * static_cast<long long>(H) * W;
+  const float* im = img + s * sample_stride;
   const int gx0 = ox0 * stride - pad, gy0 = oy * stride - pad;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int rc = warp; rc < Cin * k; rc += 8) {          // one (channel, patch row) per warp pass: no per-element divisions
@@ -257,8 +257,10 @@ extern "C" int cwm_instnorm_f16(const uint16_t* x, int S, int HW, int C, float e
   return CWM_OK;
 }
 
-extern "C" int cwm_im2col_nchw_f16(const float* img, int S, int Cin, int H, int W, int k, int stride, int pad, float scale,
-                                   float shift, uint16_t* out, int ldo, cwm_stream_t stream) {
+extern "C" int cwm_im2col_nchw_f16(const float* img, long long sample_stride, int S, int Cin, int H, int W, int k, int stride,
+                                   int pad, float scale, float shift, uint16_t* out, int ldo, cwm_stream_t stream) {
+  if (sample_stride == 0) sample_stride = static_cast<long long>(Cin) * H * W;
+  CWM_REQUIRE(sample_stride >= static_cast<long long>(Cin) * H * W, "cwm_im2col_nchw_f16: sample stride %lld < Cin*H*W", sample_stride);
   CWM_REQUIRE(S >= 0 && Cin >= 1 && H >= 1 && W >= 1 && k >= 1 && stride >= 1 && pad >= 0 && ldo % 8 == 0 && ldo >= k * k * Cin,
               "cwm_im2col_nchw_f16: bad shape S=%d Cin=%d H=%d W=%d k=%d stride=%d pad=%d ldo=%d", S, Cin, H, W, k, stride, pad, ldo);
   if (S == 0) return CWM_OK;
@@ -273,10 +275,10 @@ extern "C" int cwm_im2col_nchw_f16(const float* img, int S, int Cin, int H, int 
   ProfileScope prof(st, "im2col_nchw", 0.0, static_cast<double>(M) * ldo * 2.0 + static_cast<double>(S) * Cin * H * W * 4.0);
   const dim3 grid((Wo + cwm::kIm2colTile - 1) / cwm::kIm2colTile, Ho, S);
   if (Cin == 3 && k == 7 && stride == 2 && ldo == 152)   // the encoders' stem (extractor.py:132)
-    cwm::im2col_nchw_kernel<3, 7, 2, 152><<<grid, 256, smem, st>>>(img, Cin, H, W, Ho, Wo, k, stride, pad, scale, shift,
+    cwm::im2col_nchw_kernel<3, 7, 2, 152><<<grid, 256, smem, st>>>(img, sample_stride, Cin, H, W, Ho, Wo, k, stride, pad, scale, shift,
                                                                    reinterpret_cast<__half*>(out), ldo);
   else
-    cwm::im2col_nchw_kernel<0, 0, 0, 0><<<grid, 256, smem, st>>>(img, Cin, H, W, Ho, Wo, k, stride, pad, scale, shift,
+    cwm::im2col_nchw_kernel<0, 0, 0, 0><<<grid, 256, smem, st>>>(img, sample_stride, Cin, H, W, Ho, Wo, k, stride, pad, scale, shift,
                                                                  reinterpret_cast<__half*>(out), ldo);
   CWM_LAUNCH_CHECK();
   return CWM_OK;

@@ -152,16 +152,21 @@ def conv2d_f16(x_rows, S, H, W, weight, bias=None, relu=False, ldo=None, out=Non
     return out
 
 
-def im2col_nchw_f16(img, k, stride, pad, ldo, scale=1.0, shift=0.0):
+def im2col_nchw_f16(img, k, stride, pad, ldo, scale=1.0, shift=0.0, out=None):
     """fp32 NCHW image ``[S, Cin, H, W]`` -> f16 rows ``[S*Ho*Wo, ldo]``: the k x k neighbourhood of every output pixel of a
-    strided convolution in (ky, kx, c) order, ``scale * v + shift`` applied inside the image, zeros outside."""
-    _req_cuda(img)
-    assert img.dtype == torch.float32 and img.is_contiguous() and img.dim() == 4
+    strided convolution in (ky, kx, c) order, ``scale * v + shift`` applied inside the image, zeros outside.  ``img`` may be
+    a frame slice of a movie (any sample stride, each sample's [Cin, H, W] block contiguous); ``out``: optional destination
+    rows (e.g. a slice of a larger buffer that holds several images)."""
+    _req_cuda(img, out)
+    assert img.dtype == torch.float32 and img.dim() == 4
     S, Cin, H, W = img.shape
+    assert img.stride()[1:] == (H * W, W, 1), "each sample's [Cin, H, W] block must be contiguous"
     Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
-    out = torch.empty(S * Ho * Wo, ldo, dtype=torch.float16, device=img.device)
-    _lib.check(_lib.load().cwm_im2col_nchw_f16(img.data_ptr(), S, Cin, H, W, k, stride, pad, float(scale), float(shift),
-                                               out.data_ptr(), ldo, _stream(img)))
+    if out is None:
+        out = torch.empty(S * Ho * Wo, ldo, dtype=torch.float16, device=img.device)
+    assert out.shape == (S * Ho * Wo, ldo) and out.is_contiguous() and out.dtype == torch.float16
+    _lib.check(_lib.load().cwm_im2col_nchw_f16(img.data_ptr(), img.stride(0) if S > 1 else 0, S, Cin, H, W, k, stride, pad,
+                                               float(scale), float(shift), out.data_ptr(), ldo, _stream(img)))
     return out
 
 

@@ -456,19 +456,32 @@ class FusedFeatureEncoder:
                                                       int(bool(relu and b is not None)), out.data_ptr(), Cout, _stream(rows)))
         return out, Ho, Wo
 
-    def __call__(self, x):
-        """x fp32 / f16 [S, 3, H, W] (already scaled to [-1, 1]) -> f16 [S, output_dim, H/8, W/8] (channels-last strides)."""
+    def __call__(self, x, scale=1.0, shift=0.0):
+        """x: fp32 / f16 ``[S, 3, H, W]`` or a list of such tensors (encoded as one batch, in order); the network sees
+        ``scale * x + shift`` -- the input normalisation 2 (x / 255) - 1 folded into the stem's im2col, so frame slices of a
+        movie are neither copied nor normalised by separate kernels.  -> f16 [S, output_dim, H/8, W/8] (channels-last)."""
         lib = _lib.load()
         inst = self.norm == 'instance'
-        with torch.cuda.device(x.device):
-            S, _, H, W = x.shape
+        parts = list(x) if isinstance(x, (list, tuple)) else [x]
+        with torch.cuda.device(parts[0].device):
+            _, _, H, W = parts[0].shape
+            S = sum(t.shape[0] for t in parts)
             k, stride, pad = self.stem_geom
             H1, W1 = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
             if self.conv_impl == "cudnn":
-                y = F.conv2d(x.to(torch.float16).contiguous(memory_format=torch.channels_last), self.stem_cudnn, None, stride, pad)
+                xin = torch.cat([t.float() for t in parts], 0) * scale + shift
+                y = F.conv2d(xin.to(torch.float16).contiguous(memory_format=torch.channels_last), self.stem_cudnn, None, stride, pad)
                 y = y.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1).reshape(S * H1 * W1, -1)
             else:
-                cols = ops.im2col_nchw_f16(x.float().contiguous(), k, stride, pad, self.K_STEM)
+                cols = torch.empty(S * H1 * W1, self.K_STEM, dtype=torch.float16, device=parts[0].device)
+                row = 0
+                for t in parts:
+                    t = t.float()
+                    if t.stride()[1:] != (H * W, W, 1):
+                        t = t.contiguous()
+                    n = t.shape[0] * H1 * W1
+                    ops.im2col_nchw_f16(t, k, stride, pad, self.K_STEM, scale, shift, out=cols[row:row + n])
+                    row += n
                 y, _, _ = self._conv(cols, S, H1, W1, (self.stem_w, self.stem_b, 1, 1), relu=True)
             if inst:
                 y = self._inorm(y, S, relu_inner=True)
@@ -832,8 +845,11 @@ class RAFT(nn.Module):
         the per-sample instance norm makes the encoders independent of what else is in the batch."""
         if self.iters is not None:
             iters = self.iters
-        image1 = (2 * (image1 / 255.0) - 1.0).contiguous()
-        image2 = (2 * (image2 / 255.0) - 1.0).contiguous()
+        # images arrive in [0, 255] / in_scale: the multiframe front end hands its [0, 1] frames over unscaled (in_scale = 255)
+        # so that the fused encoders can fold the whole normalisation 2 (x / 255) - 1 into their first kernel
+        in_scale = float(kwargs.pop('_in_scale', 1.0))
+        raw1, raw2 = image1, image2
+        normalise = lambda im: (2 * ((im * in_scale if in_scale != 1.0 else im) / 255.0) - 1.0).contiguous()  # noqa: E731
         n1, n2 = image1.shape[0], image2.shape[0]
         N = max(n1, n2)
         assert n1 in (1, N) and n2 in (1, N), (image1.shape, image2.shape)
@@ -841,9 +857,11 @@ class RAFT(nn.Module):
         fused_fnet = (amp and test_mode and isinstance(self.fnet, BasicEncoder) and self.fnet.norm_fn == 'instance'
                       and bool(getattr(self.args, 'fused_encoder', True)) and os.environ.get("CWM_RAFT_ENCODER", "fused") != "eager")
         if fused_fnet:
-            # f16 pixel-major rows, implicit-GEMM convolutions, instance norm + relu (+ shortcut) in cwm_instnorm_f16
-            fmaps = self._fused_feature_encoder()(torch.cat([image1, image2], dim=0))
+            # f16 pixel-major rows, implicit-GEMM convolutions, instance norm + relu (+ shortcut) in cwm_instnorm_f16;
+            # the input normalisation rides on the stem's im2col
+            fmaps = self._fused_feature_encoder()([raw1, raw2], scale=2.0 * in_scale / 255.0, shift=-1.0)
         else:
+            image1, image2 = normalise(raw1), normalise(raw2)
             with torch.autocast("cuda", enabled=amp):
                 fmaps = self.fnet(torch.cat([image1, image2], dim=0))  # both frames in one batch (raft_model.py:221-222)
         fmap1 = fmaps[:n1].float().expand(N, -1, -1, -1)
@@ -852,8 +870,11 @@ class RAFT(nn.Module):
         # the context network: batch norm folded into its convolutions (inference statistics only)
         fused_cnet = (fused_fnet and isinstance(self.cnet, BasicEncoder) and self.cnet.norm_fn == 'batch'
                       and not self.cnet.training)
+        if not fused_cnet and image1 is raw1:      # (not normalised yet: the fused feature encoder took the raw frames)
+            image1 = normalise(raw1)
         with torch.autocast("cuda", enabled=amp):
-            ctx = self._fused_encoder('cnet')(image1) if fused_cnet else self.cnet(image1)
+            ctx = (self._fused_encoder('cnet')(raw1, scale=2.0 * in_scale / 255.0, shift=-1.0) if fused_cnet
+                   else self.cnet(image1))
             net, inp = torch.split(ctx, [self.hidden_dim, self.context_dim], dim=1)
             net = torch.tanh(net).expand(N, -1, -1, -1)
             inp = torch.relu(inp).expand(N, -1, -1, -1)
@@ -910,7 +931,8 @@ class RAFT(nn.Module):
         shared = kwargs.pop('shared_frame', None)
         if not self.multiframe:
             return self._forward_two_images(*args, **kwargs)
-        x = (args[0] * 255.0) if self.scale_inputs else args[0]
+        x = args[0]
+        kwargs['_in_scale'] = 255.0 if self.scale_inputs else 1.0     # applied inside _forward_two_images
         if x.dim() == 4:
             x = x.unsqueeze(1)
         assert x.dim() == 5, x.shape

@@ -509,9 +509,10 @@ int cwm_instnorm_f16(const uint16_t* x, int S, int HW, int C, float eps, int rel
 /* im2col of a few-channel NCHW fp32 image for a strided k x k convolution -- the encoders' 7x7 / 2 stem on the 3-channel frame
  * (extractor.py:132, :172): out[(s, oy, ox), (ky * k + kx) * Cin + c] = scale * img[s, c, stride oy + ky - pad, stride ox + kx
  * - pad] + shift, zero outside the image and in the columns [k k Cin, ldo); the stem is then one cwm_gemm_f16 with K = ldo.
- * scale / shift carry RAFT's input normalisation 2 (x / 255) - 1 (raft_model.py:205-206). */
-int cwm_im2col_nchw_f16(const float* img, int S, int Cin, int H, int W, int k, int stride, int pad, float scale, float shift,
-                        uint16_t* out, int ldo, cwm_stream_t stream);
+ * scale / shift carry RAFT's input normalisation 2 (x / 255) - 1 (raft_model.py:205-206); sample_stride (elements, 0 = Cin*H*W)
+ * lets `img` be one frame of a [S, T, Cin, H, W] movie, so the frames are neither copied nor normalised by separate kernels. */
+int cwm_im2col_nchw_f16(const float* img, long long sample_stride, int S, int Cin, int H, int W, int k, int stride, int pad,
+                        float scale, float shift, uint16_t* out, int ldo, cwm_stream_t stream);
 
 /* out = relu?(a + b) over n f16 elements (n % 8 == 0): the residual joins of the context encoder, whose batch norms are
  * folded into the convolution weights at inference (extractor.py:46-56). */
