@@ -29,7 +29,7 @@ constexpr int kGemmThreads = 384;
 constexpr int kEpiWarps = 8;
 constexpr int kChunkBytes = 32 * 128;  // one epilogue chunk: 32 rows x 128 bytes
 
-template <int BN, bool kRes, bool kConv = false>
+template <int BN, bool kRes, bool kConv = false, bool kCta2 = false>
 struct GemmCfg {
   // epilogue smem: kRes (fp32 out, optional residual): 2 buffers / warp, else 1 buffer / warp
   // (+ 2 KB per warp for the f16 copy the LayerNorm-producer epilogue emits: 32 rows x 64 bytes, 64B-swizzled)
@@ -40,7 +40,10 @@ struct GemmCfg {
   static constexpr int kBiasBytes = kEpiWarps * kBiasWarpBytes;
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  // a CTA of a pair stages only its half of the W tile: the stage is 16 KB smaller and one more stage fits (fc2 with its
+  // 824 MB DRAM-resident A operand ran at 67 % tensor activity on 3 stages = two k-steps of prefetch)
+  static constexpr int kBStageBytes = kCta2 ? kBBytes / 2 : kBBytes;
+  static constexpr int kStageBytes = kABytes + kBStageBytes;
   static constexpr int kBudget = 232448 - kEpiBytes - kBiasBytes - 512;
   static constexpr int kMaxStages = kBudget / kStageBytes;
   // plain GEMMs: 6 stages are enough to cover the TMA latency; the convolution instantiation takes the whole budget (its
@@ -337,7 +340,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   // kConv < 0: plain GEMM with a compile-time f16 epilogue: -1 = fused LayerNorm + chunk-uniform q-scale (qkv), -2 = fused
   // LayerNorm + GELU (fc1): the run-time variant checks per 16-byte unit disappear from the issue-bound epilogue
   constexpr int kEpi = kConv < 0 ? -kConv : 0;
-  using Cfg = GemmCfg<BN, kRes, kIsConv>;
+  using Cfg = GemmCfg<BN, kRes, kIsConv, kCta2>;
   constexpr int kPost = kConv > 0 ? kConv - 1 : 0;   // the convolution's post-op, compile-time: one variant per kernel
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_a = smem;
@@ -496,10 +499,10 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
             } else {
               tma_load_2d_2sm(smem_a + stage * Cfg::kABytes, &tma_a, &full_bar[stage], kb * BK, m_blk * TM + cta_rank * BM);
             }
-            tma_load_2d_2sm(smem_b + stage * Cfg::kBBytes, &tma_w, &full_bar[stage], kb * BK,
+            tma_load_2d_2sm(smem_b + stage * Cfg::kBStageBytes, &tma_w, &full_bar[stage], kb * BK,
                             n_blk * BN + cta_rank * (BN / 2));
           } else {
-            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kABytes + Cfg::kBBytes);
             if (kIsConv && cv.taps) {
               const int dy = tap / cv.kw;
               tma_load_4d(smem_a + stage * Cfg::kABytes, &tma_a, &full_bar[stage], slab * BK, cx0 + tap - dy * cv.kw,
@@ -507,7 +510,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
             } else {
               tma_load_2d(smem_a + stage * Cfg::kABytes, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
             }
-            tma_load_2d(smem_b + stage * Cfg::kBBytes, &tma_w, &full_bar[stage], kb * BK, n_blk * BN);
+            tma_load_2d(smem_b + stage * Cfg::kBStageBytes, &tma_w, &full_bar[stage], kb * BK, n_blk * BN);
           }
         }
         if (kIsConv && ++slab == cv.cin_slabs) {
@@ -621,7 +624,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         tc_fence_after();
         // descriptors: only the start-address field (>> 4 units) changes with the stage and the k-step
         const uint64_t adesc = adesc0 + static_cast<uint64_t>(stage * (Cfg::kABytes >> 4));
-        const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(stage * (Cfg::kBBytes >> 4));
+        const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(stage * (Cfg::kBStageBytes >> 4));
         if (elect_one()) {
           if constexpr (kCta2) {
 #pragma unroll
@@ -1110,7 +1113,7 @@ template <int BN, bool kRes, bool kCta2, int kConv>
 static int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const CUtensorMap& tr,
                             const CUtensorMap& tx, int M, int N, int K, const EpiDev& ep, cudaStream_t stream,
                             const ConvDev& cv_in) {
-  using Cfg = GemmCfg<BN, kRes, (kConv > 0)>;
+  using Cfg = GemmCfg<BN, kRes, (kConv > 0), kCta2>;
   static bool attr_set = false;
   if (!attr_set) {
     CWM_CUDA_CHECK(cudaFuncSetAttribute(gemm_f16_kernel<BN, kRes, kCta2, kConv>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1120,7 +1123,7 @@ static int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tw, const 
   ConvDev cv = cv_in;
   if (cv.halo) {  // carve the operand ring into halo stages + the weight ring (or the resident weight matrix)
     const int ring = Cfg::kRingBytes;
-    cv.w_stride = kCta2 ? Cfg::kBBytes / 2 : Cfg::kBBytes;
+    cv.w_stride = Cfg::kBStageBytes;
     // a halo stage: the staged box + 1 KB of slack for the shifted reads of discarded output rows, 1024-byte aligned
     cv.h_stride = ((cv.halo_rows * cv.wb * 128 + 1024 + 1023) / 1024) * 1024;
     if (cv.h_stride > kHaloStageBytes) cv.h_stride = kHaloStageBytes;
