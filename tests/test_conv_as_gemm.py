@@ -271,3 +271,20 @@ def test_gpu_flow_head_as_tap_products_plus_stencil(S, H, W):
     for got in (flow16[:, :2], HX[:, 382:], RHX[:, 382:]):
         assert (got.cpu().float() - want_flow).abs().max().item() <= 3e-3 * scale + 2e-3 * want_flow.abs().max().item()
     assert bool((HX[:, :382] == 7.0).all()) and bool((RHX[:, :382] == -3.0).all()) and float(flow16[:, 2:].abs().max()) == 0
+
+
+@pytest.mark.gpu
+def test_gpu_stem_im2col_reads_frame_slices_in_place():
+    """The stem's im2col takes one frame of a [S, T, 3, H, W] movie through its sample stride (no copy) and writes into a
+    row slice of a larger buffer: RAFT's fused encoders fold the input normalisation 2 x - 1 into it this way."""
+    from counterfactualworldmodels_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    movie = torch.rand(3, 2, 3, 40, 56, generator=g)
+    dev = movie.to(DEV)
+    rows = 20 * 28
+    cols = torch.full((4 * rows, 152), 9.0, dtype=torch.float16, device=DEV)
+    ops.im2col_nchw_f16(dev[:1, 0], 7, 2, 3, 152, scale=2.0, shift=-1.0, out=cols[:rows])
+    ops.im2col_nchw_f16(dev[:, 1], 7, 2, 3, 152, scale=2.0, shift=-1.0, out=cols[rows:])
+    want = np.concatenate([cg.im2col_nchw(movie[:1, 0].numpy(), 7, 2, 3, 152, 2.0, -1.0),
+                           cg.im2col_nchw(movie[:, 1].numpy(), 7, 2, 3, 152, 2.0, -1.0)], 0)
+    np.testing.assert_allclose(cols.cpu().float().numpy(), want, rtol=0, atol=1e-3)
