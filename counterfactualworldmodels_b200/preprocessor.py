@@ -43,47 +43,48 @@ class Preprocessor(nn.Module):
         return self.channel_dim
 
     def set_frames_list(self, frames_list):
-        if frames_list is not None and isinstance(frames_list, int):
+        """An int t means the frame pair (t, t + 1); any other iterable is taken as it is (preprocessor.py:56-64)."""
+        if isinstance(frames_list, int):
             frames_list = [frames_list, frames_list + 1]
-        elif frames_list is not None and not isinstance(frames_list, list):
+        elif frames_list is not None:
             frames_list = list(frames_list)
         self.frames_list = frames_list
-        if self.frames_list is not None:
+        if frames_list is not None:
             self.num_input_frames = len(frames_list)
 
     def get_num_frames(self):
-        if self.num_frames is None:
-            return len(self.frames_list) if self.frames_list is not None else None
-        return self.num_frames
+        if self.num_frames is not None:
+            return self.num_frames
+        return None if self.frames_list is None else len(self.frames_list)
 
     def get_num_channels(self, x):
-        return x.shape[self.c_dim] if self.c_dim in range(len(x.shape)) else 0
+        return x.shape[self.c_dim] if 0 <= self.c_dim < x.dim() else 0
 
     def set_input_dims(self, x):
+        """Records the input's channel / frame counts; the frame list defaults to all frames and is taken modulo T."""
         self.num_input_channels = self.get_num_channels(x)
-        self.T = x.shape[self.t_dim]
+        self.T = T = x.shape[self.t_dim]
         if self.frames_list is None:
-            self.frames_list = list(range(self.T))
-            self.num_input_frames = self.T
-        self.frames_list = [fr % self.T for fr in self.frames_list]
+            self.frames_list, self.num_input_frames = list(range(T)), T
+        self.frames_list = [t % T for t in self.frames_list]
 
     def set_output_dims(self, x):
-        if self.num_channels is None:
-            self.num_channels = self.get_num_channels(x)
-        else:
-            assert self.num_channels == self.get_num_channels(x), (self.num_channels, self.get_num_channels(x))
-        if self.num_frames is None:
-            self.num_frames = x.shape[self.t_dim]
-        else:
-            assert self.num_frames == x.shape[self.t_dim]
+        """First call fixes the output's channel / frame counts, later calls check them."""
+        for attr, got in (("num_channels", self.get_num_channels(x)), ("num_frames", x.shape[self.t_dim])):
+            want = getattr(self, attr)
+            if want is None:
+                setattr(self, attr, got)
+            else:
+                assert want == got, (attr, want, got)
+
+    def _select_frames(self, x, frames, dim):
+        return torch.index_select(x, dim=dim, index=torch.as_tensor(frames, dtype=torch.long, device=x.device))
 
     def get_input_frames(self, x):
-        idx = torch.tensor(self.frames_list).long().to(x.device)
-        return torch.index_select(x, dim=self.temporal_dim, index=idx)
+        return self._select_frames(x, self.frames_list, self.temporal_dim)
 
     def get_output_frames(self, y, temporal_dim=None):
-        idx = torch.tensor(self.frames_list[-self.num_frames:]).long().to(y.device)
-        return torch.index_select(y, dim=self.t_dim if temporal_dim is None else temporal_dim, index=idx)
+        return self._select_frames(y, self.frames_list[-self.num_frames:], self.t_dim if temporal_dim is None else temporal_dim)
 
     def forward(self, x, *args, **kwargs):
         self.set_input_dims(x)
