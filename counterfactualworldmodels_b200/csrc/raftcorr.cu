@@ -754,6 +754,32 @@ extern "C" int cwm_raft_corr_pyramid_tc(const float* fmap1, const float* fmap2, 
   return CWM_OK;
 }
 
+extern "C" int cwm_raft_corr_volume_rows_f16(const uint16_t* rows1, int n1, const uint16_t* rows2, int B, int D, int H, int W,
+                                             float* out, cwm_stream_t stream);
+
+extern "C" int cwm_raft_corr_pyramid_rows_f16(const uint16_t* rows1, int n1, const uint16_t* rows2, int B, int D, int H, int W,
+                                              int num_levels, float* const* levels, cwm_stream_t stream) {
+  CWM_REQUIRE(B >= 0 && D >= 1 && H >= 1 && W >= 1, "cwm_raft_corr_pyramid_rows_f16: bad shape B=%d D=%d H=%d W=%d", B, D, H, W);
+  int hs[kMaxLevels], ws[kMaxLevels];
+  int rc = level_dims(H, W, num_levels, hs, ws, "cwm_raft_corr_pyramid_rows_f16");
+  if (rc != CWM_OK) return rc;
+  CWM_REQUIRE(levels, "cwm_raft_corr_pyramid_rows_f16: null level table");
+  if (B == 0) return CWM_OK;
+  for (int l = 0; l < num_levels; ++l) CWM_REQUIRE(levels[l], "cwm_raft_corr_pyramid_rows_f16: null level %d", l);
+  rc = cwm_raft_corr_volume_rows_f16(rows1, n1, rows2, B, D, H, W, levels[0], stream);
+  if (rc != CWM_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int HW = H * W;
+  for (int l = 1; l < num_levels; ++l) {
+    const long long total = static_cast<long long>(B) * HW * hs[l] * ws[l];
+    ProfileScope prof(st, "raft_corr_pool", 0.0, static_cast<double>(total) * 20.0);
+    raft_corr_pool_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(levels[l - 1], levels[l], total,
+                                                                                      hs[l - 1], ws[l - 1], hs[l], ws[l]);
+    CWM_LAUNCH_CHECK();
+  }
+  return CWM_OK;
+}
+
 static int corr_lookup_impl(const float* const* levels, int num_levels, int radius, const float* coords, int B, int H, int W,
                             float* out, __half* out16, int ld16, cwm_stream_t stream) {
   CWM_REQUIRE(B >= 0 && H >= 1 && W >= 1, "cwm_raft_corr_lookup: bad shape B=%d H=%d W=%d", B, H, W);

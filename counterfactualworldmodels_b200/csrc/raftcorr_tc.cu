@@ -234,6 +234,167 @@ corr_tf32_kernel(const __grid_constant__ CUtensorMap tma_ahi, const __grid_const
   }
 }
 
+// ---- the same volume from f16 pixel-major rows (the fused feature encoder's output) ----
+// fmap rows [S, HW, D] f16 are already the K-major operands, and f16 x f16 products are exact in the fp32 accumulator, so
+// the mixed-precision path needs neither the fp32 cast, nor the NCHW transpose, nor the hi / lo split: one
+// tcgen05.mma.kind::f16 per 16 channels (a third of the MMAs of the 3xTF32 scheme, half the operand bytes).  Same tile walk,
+// accumulator double buffering and epilogue as corr_tf32_kernel.  a_shared: fmap1 is ONE image shared by all samples (a
+// counterfactual sweep's frame 0).
+constexpr int kCfStages = 4;
+constexpr int kCfTileBytes = 128 * 64 * 2;          // 128 rows x 64 f16 = 16 KB, 128B-swizzled rows
+constexpr int kCfStageBytes = 2 * kCfTileBytes;     // A, B
+constexpr int kCfSmemBytes = 1024 + kCfStages * kCfStageBytes + 256;
+
+__global__ void __launch_bounds__(kCtThreads, 1)
+corr_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int HW, int D,
+                int num_samples, int a_shared, float div, float inv_div_exact, float* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kCfStages * kCfStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kCfStages;
+  uint64_t* tfull_bar = bars + 2 * kCfStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int num_kb = D / 64;
+  const int tiles_1d = (HW + 127) / 128;
+  const int tiles_per_sample = tiles_1d * tiles_1d;
+  const int num_tiles = tiles_per_sample * num_samples;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int i = 0; i < kCfStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  grid_dep_sync();
+
+  if (warp == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int s = tile / tiles_per_sample;
+      const int r = tile - s * tiles_per_sample;
+      const int mb = r / tiles_1d, nb = r - mb * tiles_1d;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
+          uint8_t* st = smem + stage * kCfStageBytes;
+          mbar_arrive_expect_tx(&full_bar[stage], kCfStageBytes);
+          tma_load_4d(st, &tma_a, &full_bar[stage], kb * 64, mb * 128, 0, a_shared ? 0 : s);
+          tma_load_4d(st + kCfTileBytes, &tma_b, &full_bar[stage], kb * 64, nb * 128, 0, s);
+        }
+        __syncwarp();
+        if (++stage == kCfStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = umma_idesc_f16(128, 128, 0, 0);
+    const uint64_t desc0 = umma_desc_kmajor_sw128(smem_u32(smem));
+    int stage = 0, as = 0;
+    uint32_t phase = 0, aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + as * 128;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint64_t a = desc0 + static_cast<uint64_t>((stage * kCfStageBytes) >> 4);
+        const uint64_t b = a + (kCfTileBytes >> 4);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_ss(tmem_d, a + 2 * k, b + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (kb == num_kb - 1) umma_commit(&tfull_bar[as]);
+        }
+        __syncwarp();
+        if (++stage == kCfStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const bool vec = (HW % 4 == 0);
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int s = tile / tiles_per_sample;
+      const int r = tile - s * tiles_per_sample;
+      const int mb = r / tiles_1d, nb = r - mb * tiles_1d;
+      const int row = mb * 128 + quad * 32 + lane;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      float* orow = out + (static_cast<size_t>(s) * HW + row) * HW + nb * 128;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t acc[32];
+        tmem_ld_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * 128 + c * 32, acc);
+        tmem_ld_wait();
+        if (c == 3) {
+          tc_fence_before();
+          if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        }
+        float v[32];
+        if (inv_div_exact != 0.f) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]) * inv_div_exact;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __fdiv_rn(__uint_as_float(acc[i]), div);
+        }
+        if (row < HW) {
+          const int n0 = nb * 128 + c * 32;
+          if (vec && n0 + 32 <= HW) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(orow + c * 32 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (n0 + i < HW) orow[c * 32 + i] = v[i];
+          }
+        }
+      }
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
 }  // namespace cwm
 
 using namespace cwm;
@@ -285,6 +446,40 @@ extern "C" int cwm_raft_corr_volume_tc(const float* fmap1, const float* fmap2, i
   const float m = frexpf(div, &e);                  // div = m * 2^e; m == 0.5 <=> a power of two
   const float inv_exact = (m == 0.5f) ? 1.0f / div : 0.f;
   corr_tf32_kernel<<<grid, kCtThreads, kCtSmemBytes, st>>>(ta, tb, tc, td, HW, D, B, div, inv_exact, out);
+  CWM_LAUNCH_CHECK();
+  return CWM_OK;
+}
+
+// Level 0 from f16 pixel-major feature rows: rows1 [n1 * HW, D] (n1 = 1: one image shared by all B samples, or n1 = B),
+// rows2 [B * HW, D]; out [B, HW, HW] fp32 = rows1 rows2^T / sqrt(D).  D % 64 == 0.
+extern "C" int cwm_raft_corr_volume_rows_f16(const uint16_t* rows1, int n1, const uint16_t* rows2, int B, int D, int H, int W,
+                                             float* out, cwm_stream_t stream) {
+  CWM_REQUIRE(B >= 0 && D >= 64 && D % 64 == 0 && H >= 1 && W >= 1 && (n1 == 1 || n1 == B),
+              "cwm_raft_corr_volume_rows_f16: bad shape B=%d n1=%d D=%d H=%d W=%d (D %% 64 == 0, n1 in {1, B})", B, n1, D, H, W);
+  if (B == 0) return CWM_OK;
+  CWM_REQUIRE(rows1 && rows2 && out, "cwm_raft_corr_volume_rows_f16: null pointer");
+  CWM_REQUIRE(B <= 65535, "cwm_raft_corr_volume_rows_f16: batch %d > 65535 (chunk the sweep)", B);
+  const int HW = H * W;
+  CUtensorMap ta, tb;
+  int rc = make_tmap_nhwc(&ta, rows1, n1, 1, HW, D, D, 1, 128, 64);
+  if (rc) return rc;
+  if ((rc = make_tmap_nhwc(&tb, rows2, B, 1, HW, D, D, 1, 128, 64))) return rc;
+  static bool attr = false;
+  if (!attr) {
+    CWM_CUDA_CHECK(cudaFuncSetAttribute(corr_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCfSmemBytes));
+    attr = true;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfileScope prof(st, "raft_corr_volume_f16", 2.0 * B * static_cast<double>(HW) * HW * D,
+                    static_cast<double>(B) * HW * (static_cast<double>(HW) * 4.0 + 2.0 * D * 2.0));
+  const long long tiles = static_cast<long long>((HW + 127) / 128) * ((HW + 127) / 128) * B;
+  const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+  const float div = sqrtf(static_cast<float>(D));
+  int e = 0;
+  const float m = frexpf(div, &e);
+  const float inv_exact = (m == 0.5f) ? 1.0f / div : 0.f;
+  CWM_CUDA_CHECK(launch_pdl(corr_f16_kernel, dim3(grid), dim3(kCtThreads), kCfSmemBytes, st, ta, tb, HW, D, B, n1 == 1 && B > 1 ? 1 : 0,
+                            div, inv_exact, out));
   CWM_LAUNCH_CHECK();
   return CWM_OK;
 }

@@ -71,6 +71,30 @@ class CorrBlock:
                 _lib.check(lib.cwm_raft_corr_pyramid(fmap1.data_ptr(), fmap2.data_ptr(), batch, dim, ht, wd, num_levels,
                                                      _ptr_table(self.corr_pyramid), _stream(fmap1)))
 
+    @classmethod
+    def from_rows(cls, rows1, rows2, batch, ht, wd, num_levels=4, radius=4):
+        """The same block from f16 pixel-major feature rows (``FusedFeatureEncoder``'s output): ``rows2 [batch*ht*wd, D]``,
+        ``rows1`` likewise or ``[ht*wd, D]`` for one image shared by the whole batch.  f16 products are exact in the fp32
+        accumulator, so level 0 is one ``tcgen05.mma.kind::f16`` GEMM per sample straight from these rows: no fp32 cast, no
+        transpose, no hi / lo split (``cwm_raft_corr_pyramid_rows_f16``)."""
+        self = cls.__new__(cls)
+        self.num_levels, self.radius = num_levels, radius
+        D = rows2.shape[1]
+        hw = ht * wd
+        n1 = rows1.shape[0] // hw
+        assert rows1.dtype == rows2.dtype == _lib.act_dtype() and rows1.is_contiguous() and rows2.is_contiguous()
+        assert rows2.shape == (batch * hw, D) and rows1.shape == (n1 * hw, D) and n1 in (1, batch) and D % 64 == 0
+        self._shape = (batch, ht, wd)
+        self.corr_pyramid = []
+        h, w = ht, wd
+        for _ in range(num_levels):
+            self.corr_pyramid.append(torch.empty(batch * hw, 1, h, w, dtype=torch.float32, device=rows2.device))
+            h, w = h // 2, w // 2
+        with torch.cuda.device(rows2.device):
+            _lib.check(_lib.load().cwm_raft_corr_pyramid_rows_f16(rows1.data_ptr(), n1, rows2.data_ptr(), batch, D, ht, wd,
+                                                                  num_levels, _ptr_table(self.corr_pyramid), _stream(rows2)))
+        return self
+
     def __call__(self, coords):
         coords = _req(coords, "CorrBlock coords", 4)
         batch, ht, wd = self._shape
@@ -864,9 +888,18 @@ class RAFT(nn.Module):
             image1, image2 = normalise(raw1), normalise(raw2)
             with torch.autocast("cuda", enabled=amp):
                 fmaps = self.fnet(torch.cat([image1, image2], dim=0))  # both frames in one batch (raft_model.py:221-222)
-        fmap1 = fmaps[:n1].float().expand(N, -1, -1, -1)
-        fmap2 = fmaps[n1:].float().expand(N, -1, -1, -1)
-        corr_fn = CorrBlock(fmap1, fmap2, num_levels=self.args.corr_levels, radius=self.args.corr_radius)
+        rows_ok = (fused_fnet and fmaps.dtype == torch.float16 and fmaps.shape[1] % 64 == 0 and n2 == N
+                   and fmaps.permute(0, 2, 3, 1).is_contiguous() and os.environ.get("CWM_RAFT_CORR", "tc") == "tc")
+        if rows_ok:
+            # the fused encoder's output IS the operand layout of the volume: f16 pixel-major rows, products exact in fp32
+            hw = fmaps.shape[2] * fmaps.shape[3]
+            rows = fmaps.permute(0, 2, 3, 1).reshape(-1, fmaps.shape[1])
+            corr_fn = CorrBlock.from_rows(rows[:n1 * hw], rows[n1 * hw:], N, fmaps.shape[2], fmaps.shape[3],
+                                          num_levels=self.args.corr_levels, radius=self.args.corr_radius)
+        else:
+            fmap1 = fmaps[:n1].float().expand(N, -1, -1, -1)
+            fmap2 = fmaps[n1:].float().expand(N, -1, -1, -1)
+            corr_fn = CorrBlock(fmap1, fmap2, num_levels=self.args.corr_levels, radius=self.args.corr_radius)
         # the context network: batch norm folded into its convolutions (inference statistics only)
         fused_cnet = (fused_fnet and isinstance(self.cnet, BasicEncoder) and self.cnet.norm_fn == 'batch'
                       and not self.cnet.training)

@@ -408,6 +408,15 @@ int cwm_raft_corr_volume_tc(const float* fmap1, const float* fmap2, int B, int D
                             size_t workspace_bytes, cwm_stream_t stream);
 int cwm_raft_corr_pyramid_tc(const float* fmap1, const float* fmap2, int B, int D, int H, int W, int num_levels,
                              float* const* levels, void* workspace, size_t workspace_bytes, cwm_stream_t stream);
+
+/* The pyramid from f16 pixel-major feature rows (what the fused feature encoder writes: rows [n * H*W, D], D % 64 == 0):
+ * f16 x f16 products are exact in the fp32 accumulator, so the mixed-precision path needs no fp32 cast, no NCHW transpose and
+ * no hi / lo split -- one tcgen05.mma.kind::f16 per 16 channels.  n1 = 1: fmap1 is one image shared by all B samples (a
+ * counterfactual sweep's frame 0), else n1 = B.  levels[l]: fp32 [B*H*W, H>>l, W>>l] as for cwm_raft_corr_pyramid. */
+int cwm_raft_corr_volume_rows_f16(const uint16_t* rows1, int n1, const uint16_t* rows2, int B, int D, int H, int W, float* out,
+                                  cwm_stream_t stream);
+int cwm_raft_corr_pyramid_rows_f16(const uint16_t* rows1, int n1, const uint16_t* rows2, int B, int D, int H, int W,
+                                   int num_levels, float* const* levels, cwm_stream_t stream);
 /* `CorrBlock.__call__` (corr.py:30-51) + `bilinear_sampler` (utils.py:60-80, grid_sample align_corners=True, zero
  * padding): coords [B, 2, H, W] (channel 0 = x, 1 = y, in level-0 pixels) -> out [B, num_levels*(2r+1)^2, H, W];
  * channel l*(2r+1)^2 + a*(2r+1) + b samples level l at (x/2^l + a - r, y/2^l + b - r). */

@@ -698,3 +698,23 @@ def test_gpu_fused_encoders_match_the_autocast_encoders(which, conv_impl, hw):
     e_fused, e_amp = (got - want).abs().max().item() / scale, (amp - want).abs().max().item() / scale
     print(f"{which} ({conv_impl}, {hw} px): fused {e_fused:.2e} of scale, autocast {e_amp:.2e}")
     assert e_fused <= 1e-2 and e_fused <= 3 * e_amp + 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,n1,D,H,W", [(3, 3, 256, 28, 28), (4, 1, 256, 28, 28), (2, 2, 64, 9, 13), (5, 1, 128, 16, 24), (1, 1, 64, 30, 17)])
+def test_gpu_corr_pyramid_from_f16_rows(B, n1, D, H, W):
+    """`CorrBlock.from_rows` (level 0 as one tcgen05.mma.kind::f16 GEMM per sample on the fused encoder's f16 pixel-major
+    rows; one shared first image or one per sample) against the float64 product of the same f16 values: f16 x f16 products
+    are exact and the accumulation is fp32, so the bar is the fp32 SIMT kernel's (1e-6 of scale); levels 1.. are the pooled
+    level 0."""
+    from counterfactualworldmodels_b200 import raft
+    g = torch.Generator().manual_seed(B * 10 + D)
+    f1 = (torch.randn(n1, H * W, D, generator=g) * torch.logspace(-1, 1, D)[torch.randperm(D, generator=g)]).half()
+    f2 = torch.randn(B, H * W, D, generator=g).half()
+    want = torch.einsum("bid,bjd->bij", f1.double().expand(B, -1, -1), f2.double()) / (float(D) ** 0.5)
+    blk = raft.CorrBlock.from_rows(f1.reshape(-1, D).to(DEV), f2.reshape(-1, D).to(DEV), B, H, W, num_levels=2, radius=4)
+    got = blk.corr_pyramid[0].view(B, H * W, H * W).cpu().double()
+    scale = want.abs().max().item()
+    assert (got - want).abs().max().item() <= 1e-6 * scale
+    lvl1 = torch.nn.functional.avg_pool2d(blk.corr_pyramid[0], 2, stride=2)
+    assert torch.allclose(blk.corr_pyramid[1], lvl1, rtol=1e-6, atol=1e-6 * scale)
