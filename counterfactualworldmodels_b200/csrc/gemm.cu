@@ -152,7 +152,10 @@ struct ConvDev {
   int wb;
   int w_stages;       // depth of the weight-tile ring in halo mode
   int w_stride;       // bytes between its stages (a CTA of a pair holds half a tile)
-  int base_off;       // 1: set the descriptor's base-offset field for the row-shifted starts
+  int base_off;       // timing-experiment switches (CWM_CONV_BASEOFF): bit 1 (2) = epilogue hands the accumulator straight back,
+                      // bit 2 (4) = halo-mode MMA issuer skips the MMAs (pair kernels).  (Round 1 used the value 1 to set the
+                      // descriptor's base-offset field for the row-shifted A starts: wrong -- the swizzle XOR follows the
+                      // absolute shared-memory address -- and removed.)
 };
 constexpr int kHaloStageBytes = 33 * 1024;  // 256 rows x 128 B + slack for the shifted reads of discarded output rows
 
@@ -1402,7 +1405,7 @@ static int conv2d_impl(const uint16_t* x, int ldx, int S, int H, int W, int Cin,
   cv.w_stride = 0;
   {
     const char* v = getenv("CWM_CONV_BASEOFF");
-    cv.base_off = (v == nullptr) ? 0 : atoi(v);  // measured: the swizzle XOR follows the ABSOLUTE smem address, so 0
+    cv.base_off = (v == nullptr) ? 0 : atoi(v);  // 0 in production; 2 / 4 / 6: the timing experiments of DESIGN.md section 8
   }
   const int K = cv.taps * cv.cin_slabs * BK;
   const long long Mp = static_cast<long long>(S) * cv.tiles_per_img * BM;
