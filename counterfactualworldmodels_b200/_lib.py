@@ -34,7 +34,8 @@ EXPORTED_SYMBOLS = (
     "cwm_raft_corr_tc_workspace_bytes", "cwm_raft_corr_volume_tc", "cwm_raft_corr_pyramid_tc",
     "cwm_instnorm_workspace_bytes", "cwm_instnorm_f16", "cwm_conv2d_strided_f16", "cwm_im2col_nchw_f16", "cwm_add_act_f16",
     "cwm_conv2d_dual_f16", "cwm_raft_flow_update_taps", "cwm_act_dtype",
-    "cwm_raft_corr_volume_rows_f16", "cwm_raft_corr_pyramid_rows_f16",
+    "cwm_raft_corr_volume_rows_f16", "cwm_raft_corr_pyramid_rows_f16", "cwm_raft_corr_volume_rows_f16_out16",
+    "cwm_raft_corr_pyramid_rows_f16_pyr16", "cwm_raft_corr_lookup_f16_pyr16",
     "cwm_philox4x32_10", "cwm_mask_uniform", "cwm_mask_energy_table", "cwm_mask_energy_sample",
     "cwm_mask_rectangularize_workspace_bytes", "cwm_mask_rectangularize",
     # tuning hooks (header section "tuning hooks")
@@ -204,6 +205,11 @@ def _declare(lib):
     lib.cwm_raft_corr_volume_rows_f16.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]
     lib.cwm_raft_corr_pyramid_rows_f16.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                                    POINTER(c_void_p), c_void_p]
+    lib.cwm_raft_corr_volume_rows_f16_out16.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]
+    lib.cwm_raft_corr_pyramid_rows_f16_pyr16.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                                         POINTER(c_void_p), c_void_p]
+    lib.cwm_raft_corr_lookup_f16_pyr16.argtypes = [POINTER(c_void_p), c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
+                                                   c_int, c_void_p]
     lib.cwm_raft_flow_update_taps.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                                               c_void_p, c_int, c_void_p]
     lib.cwm_raft_im2col_flow.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]

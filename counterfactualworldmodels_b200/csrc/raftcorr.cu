@@ -108,18 +108,25 @@ raft_corr_volume_kernel(const float* __restrict__ f1, const float* __restrict__ 
 
 // F.avg_pool2d(corr, 2, stride=2) (corr.py:26-27): row-major sum of the 2 x 2 window divided by 4, odd trailing
 // row / column dropped.  One thread per output element; HBM-bound (reads 16 B, writes 4 B per element).
+__device__ __forceinline__ float pyr_load(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float pyr_load(const __half* p) { return __half2float(*p); }
+__device__ __forceinline__ void pyr_store(float* p, float v) { *p = v; }
+__device__ __forceinline__ void pyr_store(__half* p, float v) { *p = __float2half_rn(v); }
+
+// T = float: the reference's fp32 pyramid; T = __half: the f16 pyramid of the mixed-precision path (half the bytes: the
+// 64-sample level 0 then fits the L2 across the 24 lookups)
+template <typename T>
 __global__ void __launch_bounds__(256)
-raft_corr_pool_kernel(const float* __restrict__ in, float* __restrict__ out, long long total, int hi, int wi, int ho,
-                      int wo) {
+raft_corr_pool_kernel(const T* __restrict__ in, T* __restrict__ out, long long total, int hi, int wi, int ho, int wo) {
   const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (e >= total) return;
   const int x = static_cast<int>(e % wo);
   const long long t = e / wo;
   const int y = static_cast<int>(t % ho);
   const long long p = t / ho;
-  const float* src = in + (p * hi + 2 * y) * wi + 2 * x;
-  const float s = ((__ldg(src) + __ldg(src + 1)) + __ldg(src + wi)) + __ldg(src + wi + 1);
-  out[e] = __fdiv_rn(s, 4.f);
+  const T* src = in + (p * hi + 2 * y) * wi + 2 * x;
+  const float s = ((pyr_load(src) + pyr_load(src + 1)) + pyr_load(src + wi)) + pyr_load(src + wi + 1);
+  pyr_store(out + e, __fdiv_rn(s, 4.f));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -550,12 +557,13 @@ constexpr int kFastThreads = kFastWarps * 32;                              // 28
 constexpr int kFastItems = kFastPix * 4;                                   // (pixel, level) windows per CTA
 
 struct FastItem {
-  const float* src;   // the (pixel, level) map; nullptr: nothing to load (level >= L, pixel >= P)
+  const void* src;    // the (pixel, level) map (fp32 or f16); nullptr: nothing to load (level >= L, pixel >= P)
   int gx0, gy0;       // map coordinates of window element (0, 0)
   int Hl, Wl;
   float fx, fy;
 };
 
+template <typename T>
 __global__ void __launch_bounds__(kFastThreads)
 raft_corr_lookup_fast_kernel(const __grid_constant__ CorrLevels lv, int L, const float* __restrict__ coords, long long P,
                              int HW, __half* __restrict__ out16, int ld16) {
@@ -585,7 +593,7 @@ raft_corr_lookup_fast_kernel(const __grid_constant__ CorrLevels lv, int L, const
       const float flx = floorf(x), fly = floorf(y);
       it.Hl = lv.h[lvl];
       it.Wl = lv.w[lvl];
-      it.src = lv.p[lvl] + p * (static_cast<long long>(it.Hl) * it.Wl);
+      it.src = reinterpret_cast<const T*>(lv.p[lvl]) + p * (static_cast<long long>(it.Hl) * it.Wl);
       it.gx0 = static_cast<int>(flx) - kFastR;
       it.gy0 = static_cast<int>(fly) - kFastR;
       it.fx = x - flx;
@@ -623,7 +631,7 @@ raft_corr_lookup_fast_kernel(const __grid_constant__ CorrLevels lv, int L, const
             const int gy = it.gy0 + (wyx[q] >> 8), gx = it.gx0 + (wyx[q] & 0xff);
             if (wyx[q] >= 0 && static_cast<unsigned>(gx) < static_cast<unsigned>(it.Wl) &&
                 static_cast<unsigned>(gy) < static_cast<unsigned>(it.Hl))
-              v[h][q] = __ldg(it.src + gy * it.Wl + gx);
+              v[h][q] = pyr_load(static_cast<const T*>(it.src) + gy * it.Wl + gx);
           }
         }
       }
@@ -720,7 +728,7 @@ extern "C" int cwm_raft_corr_pyramid(const float* fmap1, const float* fmap2, int
   for (int l = 1; l < num_levels; ++l) {
     const long long total = static_cast<long long>(B) * HW * hs[l] * ws[l];
     ProfileScope prof(st, "raft_corr_pool", 0.0, static_cast<double>(total) * 20.0);
-    raft_corr_pool_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(levels[l - 1], levels[l], total,
+    raft_corr_pool_kernel<float><<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(levels[l - 1], levels[l], total,
                                                                                       hs[l - 1], ws[l - 1], hs[l], ws[l]);
     CWM_LAUNCH_CHECK();
   }
@@ -747,7 +755,7 @@ extern "C" int cwm_raft_corr_pyramid_tc(const float* fmap1, const float* fmap2, 
   for (int l = 1; l < num_levels; ++l) {
     const long long total = static_cast<long long>(B) * HW * hs[l] * ws[l];
     ProfileScope prof(st, "raft_corr_pool", 0.0, static_cast<double>(total) * 20.0);
-    raft_corr_pool_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(levels[l - 1], levels[l], total,
+    raft_corr_pool_kernel<float><<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(levels[l - 1], levels[l], total,
                                                                                       hs[l - 1], ws[l - 1], hs[l], ws[l]);
     CWM_LAUNCH_CHECK();
   }
@@ -756,6 +764,33 @@ extern "C" int cwm_raft_corr_pyramid_tc(const float* fmap1, const float* fmap2, 
 
 extern "C" int cwm_raft_corr_volume_rows_f16(const uint16_t* rows1, int n1, const uint16_t* rows2, int B, int D, int H, int W,
                                              float* out, cwm_stream_t stream);
+extern "C" int cwm_raft_corr_volume_rows_f16_out16(const uint16_t* rows1, int n1, const uint16_t* rows2, int B, int D, int H,
+                                                   int W, uint16_t* out16, cwm_stream_t stream);
+
+// the pyramid in f16 (every level): half the bytes of the fp32 one -- the 64-sample level 0 (78 MB) then stays in the
+// 126 MB L2 across the 24 lookups of a flow call; read by cwm_raft_corr_lookup_f16_pyr16
+extern "C" int cwm_raft_corr_pyramid_rows_f16_pyr16(const uint16_t* rows1, int n1, const uint16_t* rows2, int B, int D, int H,
+                                                    int W, int num_levels, uint16_t* const* levels, cwm_stream_t stream) {
+  CWM_REQUIRE(B >= 0 && D >= 1 && H >= 1 && W >= 1, "cwm_raft_corr_pyramid_rows_f16_pyr16: bad shape B=%d D=%d H=%d W=%d", B, D, H, W);
+  int hs[kMaxLevels], ws[kMaxLevels];
+  int rc = level_dims(H, W, num_levels, hs, ws, "cwm_raft_corr_pyramid_rows_f16_pyr16");
+  if (rc != CWM_OK) return rc;
+  CWM_REQUIRE(levels, "cwm_raft_corr_pyramid_rows_f16_pyr16: null level table");
+  if (B == 0) return CWM_OK;
+  for (int l = 0; l < num_levels; ++l) CWM_REQUIRE(levels[l], "cwm_raft_corr_pyramid_rows_f16_pyr16: null level %d", l);
+  rc = cwm_raft_corr_volume_rows_f16_out16(rows1, n1, rows2, B, D, H, W, levels[0], stream);
+  if (rc != CWM_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int HW = H * W;
+  for (int l = 1; l < num_levels; ++l) {
+    const long long total = static_cast<long long>(B) * HW * hs[l] * ws[l];
+    ProfileScope prof(st, "raft_corr_pool", 0.0, static_cast<double>(total) * 10.0);
+    raft_corr_pool_kernel<__half><<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<const __half*>(levels[l - 1]), reinterpret_cast<__half*>(levels[l]), total, hs[l - 1], ws[l - 1], hs[l], ws[l]);
+    CWM_LAUNCH_CHECK();
+  }
+  return CWM_OK;
+}
 
 extern "C" int cwm_raft_corr_pyramid_rows_f16(const uint16_t* rows1, int n1, const uint16_t* rows2, int B, int D, int H, int W,
                                               int num_levels, float* const* levels, cwm_stream_t stream) {
@@ -773,7 +808,7 @@ extern "C" int cwm_raft_corr_pyramid_rows_f16(const uint16_t* rows1, int n1, con
   for (int l = 1; l < num_levels; ++l) {
     const long long total = static_cast<long long>(B) * HW * hs[l] * ws[l];
     ProfileScope prof(st, "raft_corr_pool", 0.0, static_cast<double>(total) * 20.0);
-    raft_corr_pool_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(levels[l - 1], levels[l], total,
+    raft_corr_pool_kernel<float><<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(levels[l - 1], levels[l], total,
                                                                                       hs[l - 1], ws[l - 1], hs[l], ws[l]);
     CWM_LAUNCH_CHECK();
   }
@@ -781,7 +816,7 @@ extern "C" int cwm_raft_corr_pyramid_rows_f16(const uint16_t* rows1, int n1, con
 }
 
 static int corr_lookup_impl(const float* const* levels, int num_levels, int radius, const float* coords, int B, int H, int W,
-                            float* out, __half* out16, int ld16, cwm_stream_t stream) {
+                            float* out, __half* out16, int ld16, cwm_stream_t stream, bool src_f16 = false) {
   CWM_REQUIRE(B >= 0 && H >= 1 && W >= 1, "cwm_raft_corr_lookup: bad shape B=%d H=%d W=%d", B, H, W);
   CWM_REQUIRE(radius >= 0 && radius <= 7, "cwm_raft_corr_lookup: radius %d not in [0, 7]", radius);
   CorrLevels lv;
@@ -811,11 +846,17 @@ static int corr_lookup_impl(const float* const* levels, int num_levels, int radi
     double pyr_f = 0.0;
     for (int l = 0; l < num_levels; ++l) pyr_f += static_cast<double>(min(kFastWin, lv.w[l])) * min(kFastWin, lv.h[l]);
     ProfileScope prof(st_fast, "raft_corr_lookup", 0.0, static_cast<double>(Pf) * (0.5 * ld16 + pyr_f + 2.0) * 4.0);
-    CWM_CUDA_CHECK(launch_pdl(raft_corr_lookup_fast_kernel, dim3(static_cast<unsigned>((Pf + kFastPix - 1) / kFastPix)),
-                              dim3(kFastThreads), 0, st_fast, lv, num_levels, coords, Pf, H * W, out16, ld16));
+    if (src_f16)
+      CWM_CUDA_CHECK(launch_pdl(raft_corr_lookup_fast_kernel<__half>, dim3(static_cast<unsigned>((Pf + kFastPix - 1) / kFastPix)),
+                                dim3(kFastThreads), 0, st_fast, lv, num_levels, coords, Pf, H * W, out16, ld16));
+    else
+      CWM_CUDA_CHECK(launch_pdl(raft_corr_lookup_fast_kernel<float>, dim3(static_cast<unsigned>((Pf + kFastPix - 1) / kFastPix)),
+                                dim3(kFastThreads), 0, st_fast, lv, num_levels, coords, Pf, H * W, out16, ld16));
     CWM_LAUNCH_CHECK();
     return CWM_OK;
   }
+  CWM_REQUIRE(!src_f16, "cwm_raft_corr_lookup_f16_pyr16: the f16 pyramid is read by the fast lookup only (radius 4, <= 4 levels, "
+                        "row length a multiple of 8 and <= 328)");
   auto kernel = radius == 4 ? raft_corr_lookup_kernel<4> : radius == 3 ? raft_corr_lookup_kernel<3> : raft_corr_lookup_kernel<-1>;
   static size_t configured[3] = {0, 0, 0};  // grow-only opt-in for > 48 KB of dynamic shared memory, per instantiation
   size_t& conf = configured[radius == 4 ? 0 : radius == 3 ? 1 : 2];
@@ -848,6 +889,12 @@ extern "C" int cwm_raft_corr_lookup(const float* const* levels, int num_levels, 
 extern "C" int cwm_raft_corr_lookup_f16(const float* const* levels, int num_levels, int radius, const float* coords, int B,
                                         int H, int W, uint16_t* out16, int ld16, cwm_stream_t stream) {
   return corr_lookup_impl(levels, num_levels, radius, coords, B, H, W, nullptr, reinterpret_cast<__half*>(out16), ld16, stream);
+}
+
+extern "C" int cwm_raft_corr_lookup_f16_pyr16(const uint16_t* const* levels, int num_levels, int radius, const float* coords,
+                                              int B, int H, int W, uint16_t* out16, int ld16, cwm_stream_t stream) {
+  return corr_lookup_impl(reinterpret_cast<const float* const*>(levels), num_levels, radius, coords, B, H, W, nullptr,
+                          reinterpret_cast<__half*>(out16), ld16, stream, true);
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

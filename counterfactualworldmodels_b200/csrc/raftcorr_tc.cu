@@ -245,9 +245,10 @@ constexpr int kCfTileBytes = 128 * 64 * 2;          // 128 rows x 64 f16 = 16 KB
 constexpr int kCfStageBytes = 2 * kCfTileBytes;     // A, B
 constexpr int kCfSmemBytes = 1024 + kCfStages * kCfStageBytes + 256;
 
+template <typename TO>   // float: the fp32 volume; __half: the f16 pyramid of the mixed-precision path
 __global__ void __launch_bounds__(kCtThreads, 1)
 corr_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int HW, int D,
-                int num_samples, int a_shared, float div, float inv_div_exact, float* __restrict__ out) {
+                int num_samples, int a_shared, float div, float inv_div_exact, TO* __restrict__ out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kCfStages * kCfStageBytes);
@@ -341,7 +342,7 @@ corr_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     }
   } else {
     const int quad = warp & 3;
-    const bool vec = (HW % 4 == 0);
+    const bool vec = (HW % 8 == 0);
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -351,7 +352,7 @@ corr_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       const int row = mb * 128 + quad * 32 + lane;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      float* orow = out + (static_cast<size_t>(s) * HW + row) * HW + nb * 128;
+      TO* orow = out + (static_cast<size_t>(s) * HW + row) * HW + nb * 128;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t acc[32];
@@ -372,12 +373,22 @@ corr_f16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         if (row < HW) {
           const int n0 = nb * 128 + c * 32;
           if (vec && n0 + 32 <= HW) {
+            if constexpr (sizeof(TO) == 4) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(orow + c * 32 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+              for (int i = 0; i < 32; i += 4)
+                *reinterpret_cast<float4*>(orow + c * 32 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; i += 8)
+                *reinterpret_cast<uint4*>(orow + c * 32 + i) = make_uint4(pack_half2(v[i], v[i + 1]), pack_half2(v[i + 2], v[i + 3]),
+                                                                          pack_half2(v[i + 4], v[i + 5]), pack_half2(v[i + 6], v[i + 7]));
+            }
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (n0 + i < HW) orow[c * 32 + i] = v[i];
+              if (n0 + i < HW) {
+                if constexpr (sizeof(TO) == 4) orow[c * 32 + i] = v[i]; else orow[c * 32 + i] = __float2half_rn(v[i]);
+              }
           }
         }
       }
@@ -451,13 +462,14 @@ extern "C" int cwm_raft_corr_volume_tc(const float* fmap1, const float* fmap2, i
 }
 
 // Level 0 from f16 pixel-major feature rows: rows1 [n1 * HW, D] (n1 = 1: one image shared by all B samples, or n1 = B),
-// rows2 [B * HW, D]; out [B, HW, HW] fp32 = rows1 rows2^T / sqrt(D).  D % 64 == 0.
-extern "C" int cwm_raft_corr_volume_rows_f16(const uint16_t* rows1, int n1, const uint16_t* rows2, int B, int D, int H, int W,
-                                             float* out, cwm_stream_t stream) {
+// rows2 [B * HW, D]; out [B, HW, HW] (fp32, or f16 for the f16 pyramid) = rows1 rows2^T / sqrt(D).  D % 64 == 0.
+template <typename TO>
+static int corr_volume_rows_impl(const uint16_t* rows1, int n1, const uint16_t* rows2, int B, int D, int H, int W, TO* out,
+                                 cwm_stream_t stream) {
   CWM_REQUIRE(B >= 0 && D >= 64 && D % 64 == 0 && H >= 1 && W >= 1 && (n1 == 1 || n1 == B),
               "cwm_raft_corr_volume_rows_f16: bad shape B=%d n1=%d D=%d H=%d W=%d (D %% 64 == 0, n1 in {1, B})", B, n1, D, H, W);
   if (B == 0) return CWM_OK;
-  CWM_REQUIRE(rows1 && rows2 && out, "cwm_raft_corr_volume_rows_f16: null pointer");
+  CWM_REQUIRE(rows1 && rows2 && out && reinterpret_cast<uintptr_t>(out) % 16 == 0, "cwm_raft_corr_volume_rows_f16: null / misaligned pointer");
   CWM_REQUIRE(B <= 65535, "cwm_raft_corr_volume_rows_f16: batch %d > 65535 (chunk the sweep)", B);
   const int HW = H * W;
   CUtensorMap ta, tb;
@@ -466,20 +478,30 @@ extern "C" int cwm_raft_corr_volume_rows_f16(const uint16_t* rows1, int n1, cons
   if ((rc = make_tmap_nhwc(&tb, rows2, B, 1, HW, D, D, 1, 128, 64))) return rc;
   static bool attr = false;
   if (!attr) {
-    CWM_CUDA_CHECK(cudaFuncSetAttribute(corr_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCfSmemBytes));
+    CWM_CUDA_CHECK(cudaFuncSetAttribute(corr_f16_kernel<TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCfSmemBytes));
     attr = true;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ProfileScope prof(st, "raft_corr_volume_f16", 2.0 * B * static_cast<double>(HW) * HW * D,
-                    static_cast<double>(B) * HW * (static_cast<double>(HW) * 4.0 + 2.0 * D * 2.0));
+                    static_cast<double>(B) * HW * (static_cast<double>(HW) * sizeof(TO) + 2.0 * D * 2.0));
   const long long tiles = static_cast<long long>((HW + 127) / 128) * ((HW + 127) / 128) * B;
   const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
   const float div = sqrtf(static_cast<float>(D));
   int e = 0;
   const float m = frexpf(div, &e);
   const float inv_exact = (m == 0.5f) ? 1.0f / div : 0.f;
-  CWM_CUDA_CHECK(launch_pdl(corr_f16_kernel, dim3(grid), dim3(kCtThreads), kCfSmemBytes, st, ta, tb, HW, D, B, n1 == 1 && B > 1 ? 1 : 0,
-                            div, inv_exact, out));
+  CWM_CUDA_CHECK(launch_pdl(corr_f16_kernel<TO>, dim3(grid), dim3(kCtThreads), kCfSmemBytes, st, ta, tb, HW, D, B,
+                            n1 == 1 && B > 1 ? 1 : 0, div, inv_exact, out));
   CWM_LAUNCH_CHECK();
   return CWM_OK;
+}
+
+extern "C" int cwm_raft_corr_volume_rows_f16(const uint16_t* rows1, int n1, const uint16_t* rows2, int B, int D, int H, int W,
+                                             float* out, cwm_stream_t stream) {
+  return corr_volume_rows_impl<float>(rows1, n1, rows2, B, D, H, W, out, stream);
+}
+
+extern "C" int cwm_raft_corr_volume_rows_f16_out16(const uint16_t* rows1, int n1, const uint16_t* rows2, int B, int D, int H,
+                                                   int W, uint16_t* out16, cwm_stream_t stream) {
+  return corr_volume_rows_impl<__half>(rows1, n1, rows2, B, D, H, W, reinterpret_cast<__half*>(out16), stream);
 }

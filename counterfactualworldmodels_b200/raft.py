@@ -72,11 +72,13 @@ class CorrBlock:
                                                      _ptr_table(self.corr_pyramid), _stream(fmap1)))
 
     @classmethod
-    def from_rows(cls, rows1, rows2, batch, ht, wd, num_levels=4, radius=4):
+    def from_rows(cls, rows1, rows2, batch, ht, wd, num_levels=4, radius=4, f16_pyramid=False):
         """The same block from f16 pixel-major feature rows (``FusedFeatureEncoder``'s output): ``rows2 [batch*ht*wd, D]``,
         ``rows1`` likewise or ``[ht*wd, D]`` for one image shared by the whole batch.  f16 products are exact in the fp32
         accumulator, so level 0 is one ``tcgen05.mma.kind::f16`` GEMM per sample straight from these rows: no fp32 cast, no
-        transpose, no hi / lo split (``cwm_raft_corr_pyramid_rows_f16``)."""
+        transpose, no hi / lo split (``cwm_raft_corr_pyramid_rows_f16``).  ``f16_pyramid=True`` stores every level in f16
+        (half the bytes: a 64-sample level 0 then stays in L2 across the 24 lookups); such a block serves the f16 row lookup of
+        the fused recurrent block only (``__call__`` raises)."""
         self = cls.__new__(cls)
         self.num_levels, self.radius = num_levels, radius
         D = rows2.shape[1]
@@ -87,16 +89,21 @@ class CorrBlock:
         self._shape = (batch, ht, wd)
         self.corr_pyramid = []
         h, w = ht, wd
+        pyr_dtype = torch.float16 if f16_pyramid else torch.float32
         for _ in range(num_levels):
-            self.corr_pyramid.append(torch.empty(batch * hw, 1, h, w, dtype=torch.float32, device=rows2.device))
+            self.corr_pyramid.append(torch.empty(batch * hw, 1, h, w, dtype=pyr_dtype, device=rows2.device))
             h, w = h // 2, w // 2
+        lib = _lib.load()
+        fn = lib.cwm_raft_corr_pyramid_rows_f16_pyr16 if f16_pyramid else lib.cwm_raft_corr_pyramid_rows_f16
         with torch.cuda.device(rows2.device):
-            _lib.check(_lib.load().cwm_raft_corr_pyramid_rows_f16(rows1.data_ptr(), n1, rows2.data_ptr(), batch, D, ht, wd,
-                                                                  num_levels, _ptr_table(self.corr_pyramid), _stream(rows2)))
+            _lib.check(fn(rows1.data_ptr(), n1, rows2.data_ptr(), batch, D, ht, wd, num_levels, _ptr_table(self.corr_pyramid),
+                          _stream(rows2)))
         return self
 
     def __call__(self, coords):
         coords = _req(coords, "CorrBlock coords", 4)
+        if self.corr_pyramid[0].dtype != torch.float32:
+            raise RuntimeError("an f16 correlation pyramid serves the fused recurrent block's f16 lookup only")
         batch, ht, wd = self._shape
         assert tuple(coords.shape) == (batch, 2, ht, wd), (coords.shape, self._shape)
         n1 = 2 * self.radius + 1
@@ -668,8 +675,10 @@ class FusedBasicUpdate:
                                                  p(tail) if tail is not None else None, 8, 2, s))
 
         with torch.cuda.device(coords1.device):
-            _lib.check(lib.cwm_raft_corr_lookup_f16(_ptr_table(corr_fn.corr_pyramid), corr_fn.num_levels, corr_fn.radius,
-                                                    p(coords1), st.N, st.H, st.W, p(st.corr16), self.CORR_LD, s))
+            lookup = (lib.cwm_raft_corr_lookup_f16_pyr16 if corr_fn.corr_pyramid[0].dtype == torch.float16
+                      else lib.cwm_raft_corr_lookup_f16)
+            _lib.check(lookup(_ptr_table(corr_fn.corr_pyramid), corr_fn.num_levels, corr_fn.radius, p(coords1), st.N, st.H, st.W,
+                              p(st.corr16), self.CORR_LD, s))
             # BasicMotionEncoder (update.py:90-98)
             if st.tc:
                 # bias + relu in the convolution epilogues, every result written straight into its consumer's input slot
@@ -890,12 +899,20 @@ class RAFT(nn.Module):
                 fmaps = self.fnet(torch.cat([image1, image2], dim=0))  # both frames in one batch (raft_model.py:221-222)
         rows_ok = (fused_fnet and fmaps.dtype == torch.float16 and fmaps.shape[1] % 64 == 0 and n2 == N
                    and fmaps.permute(0, 2, 3, 1).is_contiguous() and os.environ.get("CWM_RAFT_CORR", "tc") == "tc")
+        # will the recurrent block run fused (f16 rows, f16 lookups)?  Decided here because it also picks the pyramid's type
+        use_fused_update = (amp and bool(getattr(self.args, 'half_update', True)) and test_mode
+                            and isinstance(self.update_block, BasicUpdateBlock) and self.output_block is None and iters > 0
+                            and bool(getattr(self.args, 'fused_update', True)))
         if rows_ok:
             # the fused encoder's output IS the operand layout of the volume: f16 pixel-major rows, products exact in fp32
             hw = fmaps.shape[2] * fmaps.shape[3]
             rows = fmaps.permute(0, 2, 3, 1).reshape(-1, fmaps.shape[1])
+            pyr16 = (use_fused_update and self.args.corr_radius == 4 and self.args.corr_levels <= 4 and hw % 8 == 0
+                     and fmaps.shape[3] <= 32 and os.environ.get("CWM_RAFT_PYR16", "0") != "0"   # opt-in: measured 11.09 -> 11.07 ms only
+                     and os.environ.get("CWM_RAFT_CONV", "tcgen05") == "tcgen05"
+                     and os.environ.get("CWM_RAFT_LOOKUP", "fast")[0] not in "e0")
             corr_fn = CorrBlock.from_rows(rows[:n1 * hw], rows[n1 * hw:], N, fmaps.shape[2], fmaps.shape[3],
-                                          num_levels=self.args.corr_levels, radius=self.args.corr_radius)
+                                          num_levels=self.args.corr_levels, radius=self.args.corr_radius, f16_pyramid=pyr16)
         else:
             fmap1 = fmaps[:n1].float().expand(N, -1, -1, -1)
             fmap2 = fmaps[n1:].float().expand(N, -1, -1, -1)
@@ -917,8 +934,7 @@ class RAFT(nn.Module):
         has_mask_head = isinstance(self.update_block, BasicUpdateBlock)
         update_block = self.update_block
         half_update = amp and bool(getattr(self.args, 'half_update', True))
-        if (half_update and test_mode and has_mask_head and self.output_block is None and iters > 0
-                and bool(getattr(self.args, 'fused_update', True))):
+        if use_fused_update:
             # RAFT-large, inference: the recurrent block on cuDNN convolutions + the cwm_raft_*_f16 kernels
             fused = self._fused_update_block()
             st = fused.begin(N, coords0.shape[2], coords0.shape[3], net, inp, flow_init)

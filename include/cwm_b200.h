@@ -417,6 +417,16 @@ int cwm_raft_corr_volume_rows_f16(const uint16_t* rows1, int n1, const uint16_t*
                                   cwm_stream_t stream);
 int cwm_raft_corr_pyramid_rows_f16(const uint16_t* rows1, int n1, const uint16_t* rows2, int B, int D, int H, int W,
                                    int num_levels, float* const* levels, cwm_stream_t stream);
+/* The same with every level stored in f16 (levels[l]: f16 [B*H*W, H>>l, W>>l]; H*W % 8 == 0 for the vector stores): half the
+ * bytes, so the level 0 of a 64-sample call (78 MB) stays in L2 across the 24 lookups.  Read by
+ * cwm_raft_corr_lookup_f16_pyr16 (the separable f16 lookup: radius 4, <= 4 levels).  Mixed-precision path only: the lookup
+ * output is f16 either way, the pyramid's own rounding (2^-11 relative) is of the same size. */
+int cwm_raft_corr_volume_rows_f16_out16(const uint16_t* rows1, int n1, const uint16_t* rows2, int B, int D, int H, int W,
+                                        uint16_t* out16, cwm_stream_t stream);
+int cwm_raft_corr_pyramid_rows_f16_pyr16(const uint16_t* rows1, int n1, const uint16_t* rows2, int B, int D, int H, int W,
+                                         int num_levels, uint16_t* const* levels, cwm_stream_t stream);
+int cwm_raft_corr_lookup_f16_pyr16(const uint16_t* const* levels, int num_levels, int radius, const float* coords, int B, int H,
+                                   int W, uint16_t* out16, int ld16, cwm_stream_t stream);
 /* `CorrBlock.__call__` (corr.py:30-51) + `bilinear_sampler` (utils.py:60-80, grid_sample align_corners=True, zero
  * padding): coords [B, 2, H, W] (channel 0 = x, 1 = y, in level-0 pixels) -> out [B, num_levels*(2r+1)^2, H, W];
  * channel l*(2r+1)^2 + a*(2r+1) + b samples level l at (x/2^l + a - r, y/2^l + b - r). */

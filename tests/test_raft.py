@@ -718,3 +718,32 @@ def test_gpu_corr_pyramid_from_f16_rows(B, n1, D, H, W):
     assert (got - want).abs().max().item() <= 1e-6 * scale
     lvl1 = torch.nn.functional.avg_pool2d(blk.corr_pyramid[0], 2, stride=2)
     assert torch.allclose(blk.corr_pyramid[1], lvl1, rtol=1e-6, atol=1e-6 * scale)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,n1,H,W", [(3, 1, 28, 28), (2, 2, 16, 24)])
+def test_gpu_f16_pyramid_and_its_lookup(B, n1, H, W):
+    """The f16 pyramid of the mixed-precision path (`from_rows(..., f16_pyramid=True)` + `cwm_raft_corr_lookup_f16_pyr16`)
+    against the fp32 pyramid from the same rows and its f16 lookup: the extra rounding of the stored volume is 2^-11
+    relative, the lookup output is f16 either way."""
+    from counterfactualworldmodels_b200 import _lib, raft
+    lib = _lib.load()
+    D = 256
+    g = torch.Generator().manual_seed(B + H)
+    f1 = torch.randn(n1 * H * W, D, generator=g).half().to(DEV)
+    f2 = torch.randn(B * H * W, D, generator=g).half().to(DEV)
+    ref = raft.CorrBlock.from_rows(f1, f2, B, H, W)
+    blk = raft.CorrBlock.from_rows(f1, f2, B, H, W, f16_pyramid=True)
+    for a, b in zip(ref.corr_pyramid, blk.corr_pyramid):
+        assert b.dtype == torch.float16 and a.shape == b.shape
+        assert (a - b.float()).abs().max().item() <= 1.5e-3 * a.abs().max().item()
+    c = torch.from_numpy(ro.make_coords(B, H, W, 5, "random")).to(DEV)
+    s = torch.cuda.current_stream().cuda_stream
+    out_ref = torch.empty(B * H * W, 328, dtype=torch.float16, device=DEV)
+    out_16 = torch.empty_like(out_ref)
+    _lib.check(lib.cwm_raft_corr_lookup_f16(raft._ptr_table(ref.corr_pyramid), 4, 4, c.data_ptr(), B, H, W, out_ref.data_ptr(), 328, s))
+    _lib.check(lib.cwm_raft_corr_lookup_f16_pyr16(raft._ptr_table(blk.corr_pyramid), 4, 4, c.data_ptr(), B, H, W, out_16.data_ptr(), 328, s))
+    scale = out_ref.float().abs().max().item()
+    assert (out_ref.float() - out_16.float()).abs().max().item() <= 3e-3 * scale
+    with pytest.raises(RuntimeError):
+        blk(c)
