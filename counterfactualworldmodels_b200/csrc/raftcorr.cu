@@ -553,6 +553,7 @@ raft_flow_update_taps_kernel(const __half* __restrict__ taps, int ldt, const flo
 constexpr int kFastPix = 16;
 constexpr int kFastR = 4, kFastN1 = 9, kFastWin = 10, kFastPitch = 11;   // window rows padded to 11 floats: conflict-free
 constexpr int kFastWarps = 9;
+constexpr int kFastFlight = 4;   // windows a warp has in flight in phase 1
 constexpr int kFastThreads = kFastWarps * 32;                              // 288 = half of the 16 x 4 x 9 blend tasks
 constexpr int kFastItems = kFastPix * 4;                                   // (pixel, level) windows per CTA
 
@@ -615,11 +616,11 @@ raft_corr_lookup_fast_kernel(const __grid_constant__ CorrLevels lv, int L, const
     wyx[q] = (e < kFastWin * kFastWin) ? ((wy << 8) | (e - wy * kFastWin)) : -1;
   }
   __syncthreads();
-  // ---- phase 1: a warp stages whole windows (coalesced along the window rows), two windows in flight ----
-  for (int i0 = warp; i0 < kFastItems; i0 += 2 * kFastWarps) {
-    float v[2][4];
+  // ---- phase 1: a warp stages whole windows (coalesced along the window rows), four windows in flight (the kernel is latency bound: 16 loads per lane outstanding) ----
+  for (int i0 = warp; i0 < kFastItems; i0 += kFastFlight * kFastWarps) {
+    float v[kFastFlight][4];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < kFastFlight; ++h) {
       const int item = i0 + h * kFastWarps;
 #pragma unroll
       for (int q = 0; q < 4; ++q) v[h][q] = 0.f;
@@ -637,7 +638,7 @@ raft_corr_lookup_fast_kernel(const __grid_constant__ CorrLevels lv, int L, const
       }
     }
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < kFastFlight; ++h) {
       const int item = i0 + h * kFastWarps;
       if (item < kFastItems) {
 #pragma unroll
